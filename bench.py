@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- PatchNCE fwd+bwd patches/s on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py --gpus 1 --steps K --warmup W                      # this implementation
+    python bench.py --impl reference --gpus 1 --steps K --warmup W      # CPU port of the reference
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A step = id draw + gather + normalise + logits + diagonal CE + full backward to the dense
+d tgt_feat of every layer, for one batch of synthetic feature maps; the
+generator passes are not part of the metric.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# logical layer id -> (C, H, W, post_relu) at 256x256 (generator_resnet_attn.py:190-235)
+LAYER_SETS = {
+    "b5": [(64, 256, 256, True), (256, 64, 64, False), (256, 64, 64, False), (128, 128, 128, True),
+           (64, 256, 256, True)],                       # nce_layers [0,4,8,12,13]: "5 layers"
+    "r4": [(64, 256, 256, True), (256, 64, 64, False), (256, 64, 64, False), (128, 128, 128, True)],
+}                                                       # what [0,4,8,12,16] really returns
+METRIC = "patchnce_fwd_bwd_patches_per_s"
+UNIT = "patches/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU (weak scaling)")
+    ap.add_argument("--layers", default="b5", choices=sorted(LAYER_SETS))
+    ap.add_argument("--patches", type=int, default=256)
+    ap.add_argument("--tau", type=float, default=0.07)
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "fp16", "bf16"])
+    ap.add_argument("--math", default=None)
+    ap.add_argument("--cpu-batch", type=int, default=4, help="images in the CPU-baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes_per_image(layers, p, elem):
+    """sum_l [2*P*C_l*s (useful q,k gather bytes) + C_l*H_l*W_l*s (dense d tgt)]."""
+    return sum(2 * min(p, h * w) * c * elem + c * h * w * elem for c, h, w, _ in layers)
+
+
+def dense_kernel_bytes_per_image(layers, p, elem):
+    """The backward kernel alone: the dense d tgt it must write + the gradient rows it reads."""
+    return sum(c * h * w * elem + min(p, h * w) * c * 4 for c, h, w, _ in layers)
+
+
+def make_maps(layers, batch, dtype, device, seed):
+    g = torch.Generator(device=device).manual_seed(seed)
+    src, tgt = [], []
+    for c, h, w, relu in layers:
+        for lst in (src, tgt):
+            x = torch.randn(batch, c, h, w, device=device, generator=g)
+            lst.append((x.relu() if relu else x).to(dtype).contiguous())
+    return src, tgt
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip().split(", "))
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_step(orc, src, tgt, tau, patches):
+    """One fwd+bwd of the oracle's op-for-op torch port (same ATen sequence as the reference)."""
+    for t in tgt:
+        t.grad = None
+    loss, _ = orc.patchnce_loss_torch(src, tgt, tau, patches)
+    loss.backward()
+    return loss
+
+
+def cpu_baseline(args, layers, seconds, min_steps=2):
+    """The reference's CPU path (oracle port: /root/reference is Python and cannot travel to the
+    GPU box) on this box's host cores, on a bounded sample of the workload."""
+    from oracle import patchnce_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b = args.cpu_batch
+    g = torch.Generator().manual_seed(1234)
+    src = [torch.randn(b, c, h, w, generator=g) for c, h, w, _ in layers]
+    src = [x.relu() if l[3] else x for x, l in zip(src, layers)]
+    tgt = [torch.randn(b, c, h, w, generator=g) for c, h, w, _ in layers]
+    tgt = [(x.relu() if l[3] else x).requires_grad_() for x, l in zip(tgt, layers)]
+    torch.manual_seed(7)
+    cpu_port_step(orc, src, tgt, args.tau, args.patches)            # warm-up
+    times = []
+    t_end = time.perf_counter() + seconds
+    while len(times) < min_steps or time.perf_counter() < t_end:
+        t0 = time.perf_counter()
+        cpu_port_step(orc, src, tgt, args.tau, args.patches)
+        times.append(time.perf_counter() - t0)
+        if len(times) >= 200:
+            break
+    times.sort()
+    med = times[len(times) // 2]
+    n_patches = b * sum(min(args.patches, h * w) for _, h, w, _ in layers)
+    return {"value": n_patches / med, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(times)} fwd+bwd steps of B={b} images, layer set {args.layers}, P={args.patches}, "
+                      f"fp32, torch CPU port of patchnce_cut.py (oracle/patchnce_oracle.py), median {med * 1e3:.1f} ms"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) as its own arm."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import patchnce_oracle as orc
+    layers = LAYER_SETS[args.layers]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b = args.cpu_batch
+    g = torch.Generator().manual_seed(1234)
+    src = [torch.randn(b, c, h, w, generator=g) for c, h, w, _ in layers]
+    src = [x.relu() if l[3] else x for x, l in zip(src, layers)]
+    tgt = [torch.randn(b, c, h, w, generator=g) for c, h, w, _ in layers]
+    tgt = [(x.relu() if l[3] else x).requires_grad_() for x, l in zip(tgt, layers)]
+    torch.manual_seed(7)
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_step(orc, src, tgt, args.tau, args.patches)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_step(orc, src, tgt, args.tau, args.patches)
+    dt = time.perf_counter() - t0
+    n_patches = b * sum(min(args.patches, h * w) for _, h, w, _ in layers)
+    value = n_patches * args.steps / dt
+    sample = (f"each step = B={b} images of the workload (reference backward is O(B^2), full B={args.batch} "
+              f"would take minutes per step), all {cores} host threads, fp32")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, layers),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args, layers):
+    return {
+        "workload": f"PatchNCE fwd+bwd, CUT 256x256 feature maps, layer set {args.layers} "
+                    f"({len(layers)} maps: " + ", ".join(f"{c}x{h}x{w}" for c, h, w, _ in layers) +
+                    f"), P={args.patches}, tau={args.tau}, batch {args.batch} images per GPU "
+                    "(BASELINE config 5 per-GPU batch, weak scaling), reference-exact mode (no netF head)",
+        "layers": args.layers, "batch_per_gpu": args.batch, "num_patches": args.patches,
+        "l2_policy": "inputs larger than L2 (feature maps >> 126 MB), no explicit flush",
+        "parallelism": f"dp{args.gpus} (batch sharded, identical ids, no collective in no-head mode)",
+    }
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import gan_variant_research_b200 as pn
+    from gan_variant_research_b200 import _lib
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    _lib.load()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    layers = LAYER_SETS[args.layers]
+    tdtype = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[args.dtype]
+    elem = 4 if args.dtype == "fp32" else 2
+    math = args.math or pn.DEFAULT_MATH
+    B = args.batch
+    src, tgt = make_maps(layers, B, tdtype, dev, 1234 + rank)
+    tgt = [t.requires_grad_() for t in tgt]
+    crit = pn.PatchNCELoss(args.tau, args.patches, [0, 4, 8, 12, 13], math=math)
+    torch.manual_seed(7)           # identical ids on every rank
+
+    ev_b0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_b1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def step(i=None):
+        for t in tgt:
+            t.grad = None
+        loss = crit(src, tgt)
+        if i is not None:
+            ev_b0[i].record()
+        loss.backward()
+        if i is not None:
+            ev_b1[i].record()
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = step(i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    tmax = torch.tensor([ms], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+    ms = float(tmax.item())
+    bwd_ms = sorted(a.elapsed_time(b) for a, b in zip(ev_b0, ev_b1))
+    bwd_med = bwd_ms[len(bwd_ms) // 2]
+    patches_per_image = sum(min(args.patches, h * w) for _, h, w, _ in layers)
+    value = world * B * patches_per_image * args.steps / (ms * 1e-3)
+    peak, peak_src = peaks()
+
+    dense_bytes = dense_kernel_bytes_per_image(layers, args.patches, elem) * B
+    roof = {"bound": "hbm", "kernel": "k_dense_bwd (dense d tgt_feat write + patch scatter)",
+            "achieved": dense_bytes / (bwd_med * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "peak_source": peak_src, "traffic": None, "launch_ms": bwd_med}
+    roof["frac"] = roof["achieved"] / peak
+    path_bytes = algorithmic_bytes_per_image(layers, args.patches, elem) * B
+    roof_path = {"bound": "hbm", "achieved": path_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": peak,
+                 "unit": "GB/s", "bytes_per_patch": path_bytes / (B * patches_per_image)}
+    roof_path["frac"] = roof_path["achieved"] / peak
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.dtype],
+        "math": math, "data": "synthetic", "config": workload_config(args, layers),
+        "roofline": roof, "roofline_path": roof_path, "clocks": clocks,
+        "gpu_launches": 3 * args.steps, "loss": float(loss.item()),
+    }
+
+    # ---- e2e: same metric through the public API with HOST buffers ------------------------------
+    if not args.no_e2e:
+        out["e2e"] = run_e2e(args, pn, crit, layers, tdtype, elem, dev, world, rank)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, layers, args.cpu_seconds)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def run_e2e(args, pn, crit, layers, tdtype, elem, dev, world, rank):
+    """Host-resident feature maps in pinned memory -> H2D -> fwd+bwd -> D2H of the dense grads + loss,
+    every step, all inside the timed region."""
+    B = args.batch
+    shapes = [(B, c, h, w) for c, h, w, _ in layers]
+    h_src = [torch.randn(s, dtype=torch.float32).to(tdtype).pin_memory() for s in shapes]
+    h_tgt = [torch.randn(s, dtype=torch.float32).to(tdtype).pin_memory() for s in shapes]
+    h_grad = [torch.empty(s, dtype=tdtype).pin_memory() for s in shapes]
+    h_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    d_src = [torch.empty(s, dtype=tdtype, device=dev) for s in shapes]
+    d_tgt = [torch.empty(s, dtype=tdtype, device=dev).requires_grad_() for s in shapes]
+
+    def step():
+        for d, h in zip(d_src, h_src):
+            d.copy_(h, non_blocking=True)
+        for d, h in zip(d_tgt, h_tgt):
+            d.grad = None
+            d.detach().copy_(h, non_blocking=True)
+        loss = crit(d_src, d_tgt)
+        loss.backward()
+        for h, d in zip(h_grad, d_tgt):
+            h.copy_(d.grad, non_blocking=True)
+        h_loss.copy_(loss.detach(), non_blocking=True)
+
+    step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        step()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
+    patches_per_image = sum(min(args.patches, h * w) for _, h, w, _ in layers)
+    n_elem = sum(c * h * w for c, h, w, _ in layers) * B
+    return {"value": world * B * patches_per_image * args.e2e_steps / float(dt.item()), "unit": UNIT,
+            "h2d_bytes_per_step": 2 * n_elem * elem, "d2h_bytes_per_step": n_elem * elem + 4,
+            "steps": args.e2e_steps, "api": "PatchNCELoss.forward + backward on pinned host maps"}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,25 @@
+"""B200-native PatchNCE contrastive path (CUT variant of Cameronr11/GAN-Variant-Research).
+
+Public surface = the reference's seam (``GAN_Variant1/losses/patchnce_cut.py``) plus the
+north-star module split; see ``patchnce.py``.  Importing this package never touches CUDA; the
+first call into an op loads ``libpnce.so`` (built in-tree for sm_100a) and fails loudly if it,
+or a CUDA device, is missing.
+"""
+from .patchnce import (  # noqa: F401
+    DEFAULT_MATH,
+    PatchNCELoss,
+    PatchSampleF,
+    compute_patchnce_loss,
+    draw_patch_ids,
+    fused_patchnce,
+    install_reference_shim,
+    patch_count,
+    poll_nonfinite_warnings,
+    rows_patchnce,
+)
+
+__all__ = [
+    "PatchNCELoss", "PatchSampleF", "compute_patchnce_loss", "fused_patchnce", "rows_patchnce",
+    "draw_patch_ids", "patch_count", "install_reference_shim", "poll_nonfinite_warnings",
+    "DEFAULT_MATH",
+]

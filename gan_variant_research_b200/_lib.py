@@ -1,0 +1,73 @@
+"""ctypes binding of libpnce.so (include/pnce.h).  Fails loudly: no CPU or eager fallback."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpnce.so")
+
+PNCE_F32, PNCE_F16, PNCE_BF16 = 0, 1, 2
+MATH_SIMT_F32, MATH_TC_BF16X3, MATH_TC_BF16 = 0, 1, 2
+MAX_LAYERS = 8
+MAX_PATCHES = 4096
+MAX_CHANNELS = 1024
+
+EXPORTS = [
+    "pnce_abi_version", "pnce_status_string", "pnce_last_cuda_error", "pnce_workspace_bytes",
+    "pnce_fwd", "pnce_bwd", "pnce_sample_fwd", "pnce_sample_bwd_workspace_bytes",
+    "pnce_sample_bwd", "pnce_rows_loss_workspace_bytes", "pnce_rows_loss_fwd_bwd",
+]
+
+
+class PnceLayer(ctypes.Structure):
+    """struct pnce_layer (include/pnce.h)."""
+    _fields_ = [
+        ("src", ctypes.c_void_p), ("tgt", ctypes.c_void_p), ("dtgt", ctypes.c_void_p),
+        ("ids", ctypes.c_void_p),
+        ("C", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("P", ctypes.c_int32),
+    ]
+
+
+class PnceError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """dlopen libpnce.so; building it first if the in-tree copy is missing or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, f32, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+    lib.pnce_abi_version.restype = i32
+    lib.pnce_status_string.restype = ctypes.c_char_p
+    lib.pnce_status_string.argtypes = [i32]
+    lib.pnce_last_cuda_error.restype = ctypes.c_char_p
+    lib.pnce_workspace_bytes.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, ctypes.POINTER(sz)]
+    lib.pnce_fwd.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, f32, i32, vp, sz, vp, vp, vp]
+    lib.pnce_bwd.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, vp, sz, vp, vp]
+    lib.pnce_sample_fwd.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp]
+    lib.pnce_sample_bwd_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, ctypes.POINTER(sz)]
+    lib.pnce_sample_bwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, sz, vp, vp]
+    lib.pnce_rows_loss_workspace_bytes.argtypes = [i32, i32, i32, ctypes.POINTER(sz)]
+    lib.pnce_rows_loss_fwd_bwd.argtypes = [vp, vp, i32, i32, i32, f32, i32, vp, sz, vp, vp, vp, vp, vp]
+    for name in EXPORTS:
+        if name not in ("pnce_status_string", "pnce_last_cuda_error"):
+            getattr(lib, name).restype = i32
+    if lib.pnce_abi_version() != 1:
+        raise PnceError("libpnce.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        lib = load()
+        msg = lib.pnce_status_string(status).decode()
+        extra = lib.pnce_last_cuda_error().decode()
+        raise PnceError(f"{what}: {msg}" + (f" ({extra})" if status == -4 and extra else ""))

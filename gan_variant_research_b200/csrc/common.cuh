@@ -1,0 +1,90 @@
+// Shared device-side types and helpers for libpnce (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pnce.h"
+
+namespace pnce {
+
+constexpr int kThreads = 256;          // every kernel in this library uses 256-thread CTAs
+constexpr int kRowTile = 32;           // patches per gather / SIMT-loss CTA
+constexpr float kNormEps = 1e-6f;      // F.normalize eps               patchnce_cut.py:77-78
+constexpr float kClamp = 50.0f;        // torch.clamp(logits, -50, 50)  patchnce_cut.py:88
+
+// Per-layer view of the problem plus its slices of the caller's workspace.
+struct LayerDev {
+  const void* src;
+  const void* tgt;
+  void* dtgt;
+  const long long* ids;
+  int C, HW, P, nwords;      // nwords = ceil(HW / 32) bitmap words
+  int ntiles;                // ceil(P / 32)
+  int pad_;
+  // id bookkeeping (written by the prep CTA of the gather launch)
+  int* sid;                  // [P]   ids sorted ascending
+  int* perm;                 // [P]   original index of sorted slot j
+  int* rank;                 // [P]   sorted slot of original index p
+  int* ustart;               // [P+1] start of each run of equal ids in sorted order; [U] = P
+  unsigned* bitmap;          // [nwords] bit h set <=> position h sampled
+  unsigned* prefix;          // [nwords] number of set bits before word w
+  // rows
+  float* qn;                 // [B][P][C] normalised target rows (ids order)
+  float* kn;                 // [B][P][C] normalised source rows
+  float* qinv;               // [B][P]  +1/||x||, or -1/eps when ||x|| < eps, NaN for non-finite rows
+  float* dxT;                // [B][C][P] d loss / d raw target patch, unit upstream, SORTED slot order
+  float* partial;            // [B][ntiles] partial sums of row losses
+  float* dq_rows;            // optional [B][P][C] output of the rows API (then dxT/qinv unused)
+};
+
+struct Params {
+  LayerDev L[PNCE_MAX_LAYERS];
+  int n_layers, B, dtype, math;
+  float tau;
+  int side0;                 // first side the gather launch covers: 0 = src+tgt, 1 = tgt only
+  float* loss_out;           // [1 + n_layers]
+  int* nonfinite;            // [1]
+  unsigned* counter;         // [1] last-CTA election; zeroed by the gather launch
+  float* lossimg;            // [n_layers][B]
+  int* valid;                // [n_layers][B]
+  const float* grad_out;     // device scalar or NULL (=1)
+};
+
+// CTA -> layer map for one launch: blocks [start[l], start[l+1]) work on layer l.
+struct BlockMap {
+  long long start[PNCE_MAX_LAYERS + 2];
+};
+
+__device__ __forceinline__ int find_layer(const BlockMap& m, long long blk, int n) {
+  int l = 0;
+  for (int i = 1; i < n; ++i)
+    if (blk >= m.start[i]) l = i;
+  return l;
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// torch.clamp semantics: NaN propagates (fminf/fmaxf would swallow it).
+__device__ __forceinline__ float clamp_nan(float x, float c) { return x < -c ? -c : (x > c ? c : x); }
+
+}  // namespace pnce

@@ -1,0 +1,207 @@
+// Launch 1 of the forward: random-patch gather + L2 normalise for every (layer, side, image,
+// 32-patch tile), plus one "prep" CTA per layer that sorts the ids and builds the position bitmap
+// the dense backward needs.  Replaces patchnce_cut.py:56-78 (view/permute, index, stack, normalize).
+#pragma once
+#include "common.cuh"
+
+namespace pnce {
+
+// --------------------------------------------------------------------------------------------
+// block-wide exclusive scan of one int per thread (256 threads); returns the exclusive prefix and
+// the block total through *total.  scratch: >= 9 ints of shared memory.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_excl_scan(int v, int* scratch, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) scratch[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < (kThreads / 32) ? scratch[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < (kThreads / 32)) scratch[lane] = winc - w;   // exclusive warp offsets
+    if (lane == (kThreads / 32) - 1) scratch[8] = winc;     // block total
+  }
+  __syncthreads();
+  int res = scratch[warp] + inc - v;
+  *total = scratch[8];
+  __syncthreads();
+  return res;
+}
+
+// --------------------------------------------------------------------------------------------
+// prep CTA: ids -> (sid, perm, rank, ustart, bitmap, prefix).  P <= PNCE_MAX_PATCHES.
+// smem: keys[N2] (u64) + scan scratch.
+// --------------------------------------------------------------------------------------------
+__device__ void prep_layer(const LayerDev& L, unsigned long long* keys, int* scratch) {
+  const int tid = threadIdx.x;
+  const int P = L.P;
+  int N2 = 1;
+  while (N2 < P) N2 <<= 1;
+  for (int i = tid; i < N2; i += kThreads) {
+    unsigned long long k = ~0ull;
+    if (i < P) {
+      long long id = L.ids[i];
+      id = id < 0 ? 0 : (id >= L.HW ? L.HW - 1 : id);          // memory safety only; randint is in range
+      k = ((unsigned long long)(unsigned)id << 32) | (unsigned)i;
+    }
+    keys[i] = k;
+  }
+  __syncthreads();
+  // bitonic sort, ascending by (id, original index): deterministic order inside runs of equal ids
+  for (int k = 2; k <= N2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < N2; i += kThreads) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = keys[i], b = keys[ixj];
+          bool up = (i & k) == 0;
+          if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // sid / perm / rank, run starts
+  int running = 0;
+  for (int base = 0; base < P; base += kThreads) {
+    int i = base + tid;
+    int head = 0, id = 0, pi = 0;
+    if (i < P) {
+      id = (int)(keys[i] >> 32);
+      pi = (int)(keys[i] & 0xffffffffu);
+      head = (i == 0) || ((int)(keys[i - 1] >> 32) != id);
+      L.sid[i] = id;
+      L.perm[i] = pi;
+      L.rank[pi] = i;
+    }
+    int tot;
+    int ex = block_excl_scan(head, scratch, &tot);
+    if (i < P && head) L.ustart[running + ex] = i;
+    running += tot;
+  }
+  if (tid == 0) L.ustart[running] = P;                       // running == number of unique ids
+  // bitmap
+  for (int w = tid; w < L.nwords; w += kThreads) L.bitmap[w] = 0u;
+  __syncthreads();
+  for (int i = tid; i < P; i += kThreads) {
+    int id = (int)(keys[i] >> 32);
+    atomicOr(&L.bitmap[id >> 5], 1u << (id & 31));
+  }
+  __syncthreads();
+  // exclusive popcount prefix over the bitmap words
+  running = 0;
+  for (int base = 0; base < L.nwords; base += kThreads) {
+    int w = base + tid;
+    int cnt = w < L.nwords ? __popc(L.bitmap[w]) : 0;
+    int tot;
+    int ex = block_excl_scan(cnt, scratch, &tot);
+    if (w < L.nwords) L.prefix[w] = (unsigned)(running + ex);
+    running += tot;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// gather + normalise one tile of 32 patches of one image of one side.
+//   lane <-> patch, warp w <-> channels w, w+8, ...  (each load instruction touches 32 sectors of
+//   one channel plane; C/8 independent loads per lane are in flight)
+//   tile staged in smem [32][C+1] so the normalised rows leave as coalesced 128 B row segments.
+// --------------------------------------------------------------------------------------------
+template <typename T>
+__device__ void gather_tile(const LayerDev& L, int B, int side0, long long local, float* tile_s, float* red_s) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nt = L.ntiles;
+  const int tile = (int)(local % nt);
+  const long long rest = local / nt;
+  const int b = (int)(rest % B);
+  const int side = (int)(rest / B) + side0;                   // 0 = src (k), 1 = tgt (q)
+  const int C = L.C, HW = L.HW, P = L.P;
+  const T* feat = reinterpret_cast<const T*>(side ? L.tgt : L.src) + (size_t)b * C * HW;
+  float* out = (side ? L.qn : L.kn) + (size_t)b * P * C;
+  const int p = tile * kRowTile + lane;
+  const bool ok = p < P;
+  long long id = ok ? L.ids[p] : 0;
+  id = id < 0 ? 0 : (id >= HW ? HW - 1 : id);
+  const int ldt = C + 1;
+  const T* col = feat + id;
+  float ss = 0.f;
+  int bad = 0;
+#pragma unroll 8
+  for (int c = warp; c < C; c += 8) {
+    float v = ok ? to_f32<T>(__ldg(col + (size_t)c * HW)) : 0.f;
+    tile_s[lane * ldt + c] = v;
+    ss = fmaf(v, v, ss);
+    bad |= !isfinite(v);
+  }
+  red_s[warp * 32 + lane] = ss;
+  red_s[256 + warp * 32 + lane] = __int_as_float(bad);
+  __syncthreads();
+  if (warp == 0) {
+    float tot = 0.f;
+    int anybad = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      tot += red_s[w * 32 + lane];
+      anybad |= __float_as_int(red_s[256 + w * 32 + lane]);
+    }
+    float nrm = sqrtf(tot);
+    float den = fmaxf(nrm, kNormEps);                          // clamp_min(norm, eps)
+    if (!(nrm == nrm)) den = nrm;                              // NaN norm stays NaN (fmaxf would hide it)
+    red_s[512 + lane] = den;
+    if (side == 1 && ok && L.qinv != nullptr) {
+      float inv = (nrm >= kNormEps) ? 1.0f / nrm : -1.0f / kNormEps;
+      if (anybad) inv = __int_as_float(0x7fc00000);
+      L.qinv[(size_t)b * P + p] = inv;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = warp * 4 + rr;
+    const int pr = tile * kRowTile + r;
+    if (pr < P) {
+      const float den = red_s[512 + r];
+      float* orow = out + (size_t)pr * C;
+      for (int c = lane; c < C; c += 32) orow[c] = tile_s[r * ldt + c] / den;
+    }
+  }
+}
+
+// grid = sum_l 2*B*ntiles_l gather CTAs, then n_layers prep CTAs.
+// dynamic smem = max(32*(Cmax+1)*4 + 544*4, N2max*8 + 64)
+__global__ void __launch_bounds__(kThreads) k_gather_prep(const __grid_constant__ Params p,
+                                                          const __grid_constant__ BlockMap m) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const long long blk = blockIdx.x;
+  const long long n_gather = m.start[p.n_layers];
+  if (blk >= n_gather) {
+    const int l = (int)(blk - n_gather);
+    if (l == 0 && threadIdx.x == 0 && p.counter != nullptr) *p.counter = 0u;
+    if (p.L[l].sid == nullptr) return;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+    int N2 = 1;
+    while (N2 < p.L[l].P) N2 <<= 1;
+    int* scratch = reinterpret_cast<int*>(keys + N2);
+    prep_layer(p.L[l], keys, scratch);
+    return;
+  }
+  const int l = find_layer(m, blk, p.n_layers);
+  const LayerDev& L = p.L[l];
+  float* tile_s = reinterpret_cast<float*>(smem_raw);
+  float* red_s = tile_s + kRowTile * (L.C + 1);
+  const long long local = blk - m.start[l];
+  if (p.dtype == PNCE_F32) gather_tile<float>(L, p.B, p.side0, local, tile_s, red_s);
+  else if (p.dtype == PNCE_F16) gather_tile<__half>(L, p.B, p.side0, local, tile_s, red_s);
+  else gather_tile<__nv_bfloat16>(L, p.B, p.side0, local, tile_s, red_s);
+}
+
+}  // namespace pnce

@@ -1,0 +1,412 @@
+// libpnce.so -- C ABI (include/pnce.h) over the sm_100a kernels.  Host side only: argument checks,
+// workspace carving, launch geometry.  No device allocation, no host sync, graph-capturable.
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "dense.cuh"
+#include "gather.cuh"
+#include "loss_simt.cuh"
+#include "sample_bwd.cuh"
+
+namespace pnce {
+
+static thread_local char g_cuda_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+  return PNCE_ERR_CUDA;
+}
+#define PNCE_CUDA(call)                                  \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+static size_t dtype_size(int dtype) { return dtype == PNCE_F32 ? 4 : 2; }
+
+// Carves the workspace.  With base == nullptr only the size is computed.
+struct Carver {
+  unsigned char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<unsigned char*>(b)) {}
+  template <typename T> T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+static int check_layers(const pnce_layer_t* layers, int n_layers, int B) {
+  if (layers == nullptr || n_layers < 1 || B < 1) return PNCE_ERR_ARG;
+  if (n_layers > PNCE_MAX_LAYERS) return PNCE_ERR_UNSUPPORTED;
+  for (int l = 0; l < n_layers; ++l) {
+    const pnce_layer_t& a = layers[l];
+    if (a.C < 1 || a.H < 1 || a.W < 1 || a.P < 1) return PNCE_ERR_ARG;
+    if ((long long)a.H * a.W > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+    if (a.P > PNCE_MAX_PATCHES || a.C > PNCE_MAX_CHANNELS) return PNCE_ERR_UNSUPPORTED;
+  }
+  return PNCE_OK;
+}
+
+// Fills Params (pointers into the workspace) for the fused path; returns bytes used.
+static size_t carve_fused(const pnce_layer_t* layers, int n_layers, int B, void* ws, Params* out) {
+  Carver cv(ws);
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.n_layers = n_layers;
+  p.B = B;
+  p.counter = cv.take<unsigned>(64);
+  p.lossimg = cv.take<float>((size_t)n_layers * B);
+  p.valid = cv.take<int>((size_t)n_layers * B);
+  for (int l = 0; l < n_layers; ++l) {
+    const pnce_layer_t& a = layers[l];
+    LayerDev& L = p.L[l];
+    L.src = a.src; L.tgt = a.tgt; L.dtgt = a.dtgt;
+    L.ids = reinterpret_cast<const long long*>(a.ids);
+    L.C = a.C; L.HW = a.H * a.W; L.P = a.P;
+    L.nwords = (L.HW + 31) / 32;
+    L.ntiles = (L.P + kRowTile - 1) / kRowTile;
+    const size_t rows = (size_t)B * a.P * a.C;
+    L.sid = cv.take<int>(a.P);
+    L.perm = cv.take<int>(a.P);
+    L.rank = cv.take<int>(a.P);
+    L.ustart = cv.take<int>(a.P + 1);
+    L.bitmap = cv.take<unsigned>(L.nwords);
+    L.prefix = cv.take<unsigned>(L.nwords);
+    L.qn = cv.take<float>(rows);
+    L.kn = cv.take<float>(rows);
+    L.qinv = cv.take<float>((size_t)B * a.P);
+    L.dxT = cv.take<float>(rows);
+    L.partial = cv.take<float>((size_t)B * L.ntiles);
+    L.dq_rows = nullptr;
+  }
+  if (out) *out = p;
+  return align_up(cv.off, 256);
+}
+
+static size_t gather_smem_bytes(const Params& p, bool with_prep) {
+  size_t need = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    size_t g = ((size_t)kRowTile * (p.L[l].C + 1) + 544) * sizeof(float);
+    if (g > need) need = g;
+    if (with_prep) {
+      int n2 = 1;
+      while (n2 < p.L[l].P) n2 <<= 1;
+      size_t s = (size_t)n2 * 8 + 64;
+      if (s > need) need = s;
+    }
+  }
+  return need;
+}
+
+template <typename K> static int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    if (bytes > 227 * 1024) return PNCE_ERR_UNSUPPORTED;
+    PNCE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  }
+  return PNCE_OK;
+}
+
+static int launch_gather(const Params& p, int n_prep, cudaStream_t st) {
+  BlockMap m;
+  memset(&m, 0, sizeof(m));
+  long long acc = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    m.start[l] = acc;
+    const long long sides = 2 - p.side0;
+    acc += sides * p.B * p.L[l].ntiles;
+  }
+  m.start[p.n_layers] = acc;
+  const size_t smem = gather_smem_bytes(p, n_prep > 0);
+  int rc = set_smem(k_gather_prep, smem);
+  if (rc != PNCE_OK) return rc;
+  if (acc + n_prep > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+  k_gather_prep<<<(unsigned)(acc + n_prep), kThreads, smem, st>>>(p, m);
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+
+static int launch_loss_simt(const Params& p, cudaStream_t st) {
+  BlockMap m;
+  memset(&m, 0, sizeof(m));
+  long long acc = 0;
+  size_t smem = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    m.start[l] = acc;
+    acc += (long long)p.B * p.L[l].ntiles;
+    size_t s = loss_simt_smem_bytes(p.L[l].P);
+    if (s > smem) smem = s;
+  }
+  m.start[p.n_layers] = acc;
+  int rc = set_smem(k_loss_simt, smem);
+  if (rc != PNCE_OK) return rc;
+  if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+  k_loss_simt<<<(unsigned)acc, kThreads, smem, st>>>(p, m);
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+
+static int launch_dense(const Params& p, cudaStream_t st) {
+  DenseMap m;
+  memset(&m, 0, sizeof(m));
+  const int vec = (p.dtype == PNCE_F32) ? 4 : 8;
+  long long acc = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const LayerDev& L = p.L[l];
+    m.start[l] = acc;
+    const int per_item = kDenseIters * kThreads * vec;
+    m.tiles[l] = (L.HW + per_item - 1) / per_item;
+    m.vec_ok[l] = (L.HW % vec == 0) && ((reinterpret_cast<uintptr_t>(L.dtgt) & 15u) == 0);
+    acc += (long long)p.B * L.C * m.tiles[l];
+  }
+  m.start[p.n_layers] = acc;
+  m.total = acc;
+  long long grid = (long long)sm_count() * 8;
+  if (grid > acc) grid = acc;
+  k_dense_bwd<<<(unsigned)grid, kThreads, 0, st>>>(p, m);
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+
+static int check_alignment(const pnce_layer_t* layers, int n_layers, int dtype, bool need_dtgt) {
+  const uintptr_t mask = dtype_size(dtype) - 1;
+  for (int l = 0; l < n_layers; ++l) {
+    const pnce_layer_t& a = layers[l];
+    if (a.ids == nullptr || (reinterpret_cast<uintptr_t>(a.ids) & 7u)) return PNCE_ERR_ARG;
+    if (!need_dtgt) {
+      if (a.src == nullptr || a.tgt == nullptr) return PNCE_ERR_ARG;
+      if ((reinterpret_cast<uintptr_t>(a.src) & mask) || (reinterpret_cast<uintptr_t>(a.tgt) & mask))
+        return PNCE_ERR_ALIGN;
+    } else {
+      if (a.dtgt == nullptr) return PNCE_ERR_ARG;
+      if (reinterpret_cast<uintptr_t>(a.dtgt) & mask) return PNCE_ERR_ALIGN;
+    }
+  }
+  return PNCE_OK;
+}
+
+}  // namespace pnce
+
+using namespace pnce;
+
+extern "C" {
+
+int pnce_abi_version(void) { return PNCE_ABI_VERSION; }
+
+const char* pnce_status_string(int s) {
+  switch (s) {
+    case PNCE_OK: return "ok";
+    case PNCE_ERR_ARG: return "invalid argument";
+    case PNCE_ERR_UNSUPPORTED: return "shape outside compiled limits";
+    case PNCE_ERR_WORKSPACE: return "workspace too small or misaligned";
+    case PNCE_ERR_CUDA: return "CUDA runtime error";
+    case PNCE_ERR_ALIGN: return "tensor pointer not element-aligned";
+    default: return "unknown status";
+  }
+}
+
+const char* pnce_last_cuda_error(void) { return g_cuda_err; }
+
+int pnce_workspace_bytes(const pnce_layer_t* layers, int n_layers, int batch, size_t* bytes) {
+  if (bytes == nullptr) return PNCE_ERR_ARG;
+  int rc = check_layers(layers, n_layers, batch);
+  if (rc != PNCE_OK) return rc;
+  *bytes = carve_fused(layers, n_layers, batch, nullptr, nullptr);
+  return PNCE_OK;
+}
+
+int pnce_fwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, float temperature,
+             int math_mode, void* ws, size_t ws_bytes, float* loss_out, int* nonfinite, void* stream) {
+  int rc = check_layers(layers, n_layers, batch);
+  if (rc != PNCE_OK) return rc;
+  if (dtype < PNCE_F32 || dtype > PNCE_BF16 || loss_out == nullptr || !(temperature > 0.f)) return PNCE_ERR_ARG;
+  if (math_mode != PNCE_MATH_SIMT_F32) return PNCE_ERR_UNSUPPORTED;
+  rc = check_alignment(layers, n_layers, dtype, false);
+  if (rc != PNCE_OK) return rc;
+  if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
+  Params p;
+  if (carve_fused(layers, n_layers, batch, ws, &p) > ws_bytes) return PNCE_ERR_WORKSPACE;
+  p.dtype = dtype;
+  p.math = math_mode;
+  p.tau = temperature;
+  p.loss_out = loss_out;
+  p.nonfinite = nonfinite;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = launch_gather(p, n_layers, st);
+  if (rc != PNCE_OK) return rc;
+  return launch_loss_simt(p, st);
+}
+
+int pnce_bwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, void* ws, size_t ws_bytes,
+             const float* grad_out, void* stream) {
+  int rc = check_layers(layers, n_layers, batch);
+  if (rc != PNCE_OK) return rc;
+  if (dtype < PNCE_F32 || dtype > PNCE_BF16) return PNCE_ERR_ARG;
+  rc = check_alignment(layers, n_layers, dtype, true);
+  if (rc != PNCE_OK) return rc;
+  if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
+  Params p;
+  if (carve_fused(layers, n_layers, batch, ws, &p) > ws_bytes) return PNCE_ERR_WORKSPACE;
+  p.dtype = dtype;
+  p.grad_out = grad_out;
+  return launch_dense(p, static_cast<cudaStream_t>(stream));
+}
+
+// ---- module-split API ------------------------------------------------------------------------
+
+int pnce_sample_fwd(const void* feat, int dtype, int batch, int C, int H, int W, const int64_t* ids,
+                    int P, float* rows_out, float* inv_out, void* stream) {
+  pnce_layer_t a;
+  memset(&a, 0, sizeof(a));
+  a.C = C; a.H = H; a.W = W; a.P = P;
+  int rc = check_layers(&a, 1, batch);
+  if (rc != PNCE_OK) return rc;
+  if (feat == nullptr || ids == nullptr || rows_out == nullptr || dtype < PNCE_F32 || dtype > PNCE_BF16)
+    return PNCE_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(feat) & (dtype_size(dtype) - 1)) return PNCE_ERR_ALIGN;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.n_layers = 1; p.B = batch; p.dtype = dtype;
+  LayerDev& L = p.L[0];
+  L.tgt = feat;
+  L.ids = reinterpret_cast<const long long*>(ids);
+  L.C = C; L.HW = H * W; L.P = P;
+  L.nwords = (L.HW + 31) / 32;
+  L.ntiles = (P + kRowTile - 1) / kRowTile;
+  L.qn = rows_out;
+  L.qinv = inv_out;
+  p.side0 = 1;                       // only the "tgt" side exists here
+  return launch_gather(p, 0, static_cast<cudaStream_t>(stream));
+}
+
+static size_t carve_sample_bwd(int B, int C, int H, int W, int P, void* ws, LayerDev* out) {
+  Carver cv(ws);
+  LayerDev L;
+  memset(&L, 0, sizeof(L));
+  L.C = C; L.HW = H * W; L.P = P;
+  L.nwords = (L.HW + 31) / 32;
+  L.ntiles = (P + kRowTile - 1) / kRowTile;
+  L.sid = cv.take<int>(P);
+  L.perm = cv.take<int>(P);
+  L.rank = cv.take<int>(P);
+  L.ustart = cv.take<int>(P + 1);
+  L.bitmap = cv.take<unsigned>(L.nwords);
+  L.prefix = cv.take<unsigned>(L.nwords);
+  L.dxT = cv.take<float>((size_t)B * P * C);
+  if (out) *out = L;
+  return align_up(cv.off, 256);
+}
+
+int pnce_sample_bwd_workspace_bytes(int batch, int C, int H, int W, int P, size_t* bytes) {
+  pnce_layer_t a;
+  memset(&a, 0, sizeof(a));
+  a.C = C; a.H = H; a.W = W; a.P = P;
+  int rc = check_layers(&a, 1, batch);
+  if (rc != PNCE_OK) return rc;
+  if (bytes == nullptr) return PNCE_ERR_ARG;
+  *bytes = carve_sample_bwd(batch, C, H, W, P, nullptr, nullptr);
+  return PNCE_OK;
+}
+
+// One-CTA launch of the id prep alone (module-split backward has no gather to ride on).
+__global__ void __launch_bounds__(kThreads) k_prep_only(const __grid_constant__ Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  int N2 = 1;
+  while (N2 < p.L[0].P) N2 <<= 1;
+  prep_layer(p.L[0], keys, reinterpret_cast<int*>(keys + N2));
+}
+
+int pnce_sample_bwd(const float* drows, const float* rows, const float* inv, int dtype, int batch,
+                    int C, int H, int W, const int64_t* ids, int P, void* ws, size_t ws_bytes,
+                    void* dfeat, void* stream) {
+  pnce_layer_t a;
+  memset(&a, 0, sizeof(a));
+  a.C = C; a.H = H; a.W = W; a.P = P;
+  int rc = check_layers(&a, 1, batch);
+  if (rc != PNCE_OK) return rc;
+  if (!drows || !rows || !inv || !ids || !dfeat || dtype < PNCE_F32 || dtype > PNCE_BF16) return PNCE_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(dfeat) & (dtype_size(dtype) - 1)) return PNCE_ERR_ALIGN;
+  if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  if (carve_sample_bwd(batch, C, H, W, P, ws, &p.L[0]) > ws_bytes) return PNCE_ERR_WORKSPACE;
+  p.n_layers = 1; p.B = batch; p.dtype = dtype;
+  LayerDev& L = p.L[0];
+  L.ids = reinterpret_cast<const long long*>(ids);
+  L.qinv = const_cast<float*>(inv);
+  L.dtgt = dfeat;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int n2 = 1;
+  while (n2 < P) n2 <<= 1;
+  const size_t prep_smem = (size_t)n2 * 8 + 64;
+  k_prep_only<<<1, kThreads, prep_smem, st>>>(p);
+  PNCE_CUDA(cudaGetLastError());
+  const size_t smem = (size_t)kRowTile * (C + 1) * sizeof(float);
+  rc = set_smem(k_rows_normbwd, smem);
+  if (rc != PNCE_OK) return rc;
+  k_rows_normbwd<<<(unsigned)(batch * L.ntiles), kThreads, smem, st>>>(p, drows, rows);
+  PNCE_CUDA(cudaGetLastError());
+  return launch_dense(p, st);
+}
+
+static size_t carve_rows_loss(int B, int P, int D, void* ws, Params* out) {
+  Carver cv(ws);
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.n_layers = 1; p.B = B;
+  p.counter = cv.take<unsigned>(64);
+  p.lossimg = cv.take<float>(B);
+  p.valid = cv.take<int>(B);
+  LayerDev& L = p.L[0];
+  L.C = D; L.P = P; L.HW = 1; L.nwords = 1;
+  L.ntiles = (P + kRowTile - 1) / kRowTile;
+  L.partial = cv.take<float>((size_t)B * L.ntiles);
+  if (out) *out = p;
+  return align_up(cv.off, 256);
+}
+
+int pnce_rows_loss_workspace_bytes(int batch, int P, int D, size_t* bytes) {
+  if (bytes == nullptr || batch < 1 || P < 1 || D < 1) return PNCE_ERR_ARG;
+  if (P > PNCE_MAX_PATCHES || D > PNCE_MAX_CHANNELS) return PNCE_ERR_UNSUPPORTED;
+  *bytes = carve_rows_loss(batch, P, D, nullptr, nullptr);
+  return PNCE_OK;
+}
+
+int pnce_rows_loss_fwd_bwd(const float* q, const float* k, int batch, int P, int D, float temperature,
+                           int math_mode, void* ws, size_t ws_bytes, float* loss_out, int* nonfinite,
+                           float* dq_out, float* dk_out, void* stream) {
+  if (!q || !k || !loss_out || !dq_out || batch < 1 || P < 1 || D < 1 || !(temperature > 0.f)) return PNCE_ERR_ARG;
+  if (P > PNCE_MAX_PATCHES || D > PNCE_MAX_CHANNELS) return PNCE_ERR_UNSUPPORTED;
+  if (dk_out != nullptr) return PNCE_ERR_UNSUPPORTED;   // feat_k is detached in the reference (:142)
+  if (math_mode != PNCE_MATH_SIMT_F32) return PNCE_ERR_UNSUPPORTED;
+  if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
+  Params p;
+  if (carve_rows_loss(batch, P, D, ws, &p) > ws_bytes) return PNCE_ERR_WORKSPACE;
+  p.tau = temperature;
+  p.loss_out = loss_out;
+  p.nonfinite = nonfinite;
+  LayerDev& L = p.L[0];
+  L.qn = const_cast<float*>(q);
+  L.kn = const_cast<float*>(k);
+  L.dq_rows = dq_out;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PNCE_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned), st));
+  return launch_loss_simt(p, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,410 @@
+"""Host side of the B200 PatchNCE path: the reference's Python seam over the libpnce C ABI.
+
+Mirrors ``GAN_Variant1/losses/patchnce_cut.py`` of the reference (same names, arguments and
+return values) so ``training/train_cutpp.py:285-292`` runs unchanged:
+
+* ``compute_patchnce_loss(generator, src_images, tgt_images, nce_layers, temperature, num_patches)``
+  -- patchnce_cut.py:113-149
+* ``PatchNCELoss(temperature, num_patches, nce_layers).forward(src_feats, tgt_feats)``
+  -- patchnce_cut.py:7-110
+
+and adds the north-star module split underneath:
+
+* ``PatchSampleF(use_mlp=False, nc=256).forward(feats, num_patches, patch_ids)``
+* ``PatchNCELoss(...).forward(feat_q, feat_k)`` on (B*P, D) rows.
+
+torch is plumbing here (device memory, streams, autograd glue); every FLOP and byte of the path
+runs in the hand-written sm_100a kernels of ``csrc/``.  There is no CPU or eager fallback: CPU
+tensors or a missing ``libpnce.so`` raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import sys
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.PNCE_F32, torch.float16: _lib.PNCE_F16, torch.bfloat16: _lib.PNCE_BF16}
+_MATH = {"simt_f32": _lib.MATH_SIMT_F32, "tc_bf16x3": _lib.MATH_TC_BF16X3, "tc_bf16": _lib.MATH_TC_BF16}
+
+#: contraction engine used when a module does not choose one
+DEFAULT_MATH = "simt_f32"
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} is on {t.device}: the B200 PatchNCE path has no CPU fallback "
+            "(use the reference implementation or oracle/ for CPU checks)")
+
+
+def patch_count(num_patches: int, hw: int) -> int:
+    """P = min(num_patches, H*W) -- patchnce_cut.py:60"""
+    return min(int(num_patches), int(hw))
+
+
+def draw_patch_ids(feat: torch.Tensor, num_patches: int) -> torch.Tensor:
+    """The reference's id draw, issued exactly as it issues it (shape, range, device, one call per
+    layer) so the ids are bit-identical and the device RNG stream stays aligned with the rest of
+    ``train_step`` -- patchnce_cut.py:60-63, SURVEY.md section 3.1 RNG note."""
+    hw = feat.shape[2] * feat.shape[3]
+    return torch.randint(0, hw, (patch_count(num_patches, hw),), device=feat.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# lazy non-finite warnings (the reference prints from inside the loop after a host sync, :97-98;
+# here the flag is copied to pinned memory asynchronously and reported on a later call)
+# ------------------------------------------------------------------------------------------------
+class _WarnQueue:
+    def __init__(self):
+        self.pending = []
+
+    def push(self, dev_flag: torch.Tensor):
+        if torch.cuda.is_current_stream_capturing():
+            return
+        host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+        host.copy_(dev_flag, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev_flag.device))
+        self.pending.append((ev, host))
+
+    def poll(self, block: bool = False) -> int:
+        """Print the reference's warning for finished launches; returns images guarded so far."""
+        total, keep = 0, []
+        for ev, host in self.pending:
+            if block:
+                ev.synchronize()
+            if ev.query():
+                n = int(host.item())
+                if n:
+                    print(f"Warning: NaN in PatchNCE loss. {n} (layer, image) loss(es) replaced by 0.")
+                total += n
+            else:
+                keep.append((ev, host))
+        self.pending = keep
+        return total
+
+
+_warnings = _WarnQueue()
+
+
+def poll_nonfinite_warnings(block: bool = False) -> int:
+    return _warnings.poll(block)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused path: all layers, forward = 2 launches, backward = 1 launch
+# ------------------------------------------------------------------------------------------------
+class _Plan:
+    """Everything the two C-ABI calls need that is not a differentiable input."""
+
+    def __init__(self, src_feats, ids_list, temperature, math):
+        self.src_feats = src_feats
+        self.ids_list = ids_list
+        self.temperature = float(temperature)
+        self.math = math
+
+
+def _layer_array(src, tgt, dtgt, ids):
+    n = len(tgt)
+    arr = (_lib.PnceLayer * n)()
+    for l in range(n):
+        b, c, h, w = tgt[l].shape
+        arr[l].src = src[l].data_ptr() if src is not None else None
+        arr[l].tgt = tgt[l].data_ptr()
+        arr[l].dtgt = dtgt[l].data_ptr() if dtgt is not None else None
+        arr[l].ids = ids[l].data_ptr()
+        arr[l].C, arr[l].H, arr[l].W, arr[l].P = c, h, w, ids[l].numel()
+    return arr
+
+
+class _FusedPatchNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan: _Plan, *tgt_feats):
+        lib = _lib.load()
+        tgt = [t.detach() for t in tgt_feats]
+        src, ids = plan.src_feats, plan.ids_list
+        dev = tgt[0].device
+        batch = tgt[0].shape[0]
+        n = len(tgt)
+        dtype = _DTYPES[tgt[0].dtype]
+        layers = _layer_array(src, tgt, None, ids)
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.pnce_workspace_bytes(layers, n, batch, ctypes.byref(nbytes)), "pnce_workspace_bytes")
+        with torch.cuda.device(dev):
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            out = torch.empty(1 + n, dtype=torch.float32, device=dev)
+            flag = torch.empty(1, dtype=torch.int32, device=dev)
+            _lib.check(lib.pnce_fwd(layers, n, batch, dtype, plan.temperature, _MATH[plan.math],
+                                    ws.data_ptr(), nbytes.value, out.data_ptr(), flag.data_ptr(),
+                                    _stream_ptr(dev)), "pnce_fwd")
+        _warnings.push(flag)
+        ctx.plan, ctx.ws, ctx.ws_bytes = plan, ws, nbytes.value
+        ctx.tgt_meta = [(t.shape, t.dtype) for t in tgt]
+        ctx.tgt_keep = tgt               # shapes only matter, but keeps data_ptrs stable for the struct
+        ctx.dev, ctx.batch, ctx.dtype = dev, batch, dtype
+        ctx.layer_losses = out[1:]
+        ctx.nonfinite = flag
+        return out.narrow(0, 0, 1).reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        dev = ctx.dev
+        g = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            grads = [torch.empty(shape, dtype=dt, device=dev) for shape, dt in ctx.tgt_meta]
+            layers = _layer_array(ctx.plan.src_feats, ctx.tgt_keep, grads, ctx.plan.ids_list)
+            _lib.check(lib.pnce_bwd(layers, len(grads), ctx.batch, ctx.dtype, ctx.ws.data_ptr(),
+                                    ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev)), "pnce_bwd")
+        return (None, *grads)
+
+
+def _prepare_maps(src_feats, tgt_feats):
+    if len(src_feats) != len(tgt_feats):
+        # the reference zips and silently truncates (:36) but divides by len(src_feats) (:40)
+        n = min(len(src_feats), len(tgt_feats))
+        tgt_feats = list(tgt_feats)[:n]
+        src_trunc = list(src_feats)[:n]
+    else:
+        src_trunc = list(src_feats)
+    if len(src_trunc) == 0:
+        raise ZeroDivisionError("division by zero")      # what `total_loss / len(src_feats)` raises (:40)
+    if len(src_trunc) > _lib.MAX_LAYERS:
+        raise RuntimeError(f"at most {_lib.MAX_LAYERS} nce layers per call")
+    src, tgt = [], []
+    for s, t in zip(src_trunc, tgt_feats):
+        _require_cuda(t, "tgt_feat")
+        _require_cuda(s, "src_feat")
+        if s.dim() != 4 or t.dim() != 4:
+            raise ValueError("not enough values to unpack (expected 4): feature maps must be (B, C, H, W)")
+        if s.shape != t.shape:
+            raise RuntimeError(f"src/tgt feature shapes differ: {tuple(s.shape)} vs {tuple(t.shape)}")
+        if t.dtype not in _DTYPES:
+            raise RuntimeError(f"unsupported feature dtype {t.dtype}")
+        if s.dtype != t.dtype:
+            s = s.to(t.dtype)
+        src.append(s.detach().contiguous())
+        tgt.append(t.contiguous())
+    return src, tgt, len(src_feats)
+
+
+def fused_patchnce(src_feats, tgt_feats, ids_list, temperature=0.07, math: Optional[str] = None,
+                   denom_layers: Optional[int] = None):
+    """All-layer PatchNCE on dense NCHW maps with given ids.  Returns the scalar loss tensor
+    (fp32, on device, differentiable w.r.t. every ``tgt_feats[l]`` that requires grad)."""
+    src, tgt, n_src = _prepare_maps(src_feats, tgt_feats)
+    ids = []
+    for i, t in zip(ids_list, tgt):
+        _require_cuda(i, "patch_ids")
+        ids.append(i.to(torch.int64).contiguous())
+        if ids[-1].numel() > _lib.MAX_PATCHES:
+            raise RuntimeError(f"num_patches > {_lib.MAX_PATCHES} is not supported")
+    plan = _Plan(src, ids, temperature, math or DEFAULT_MATH)
+    loss = _FusedPatchNCE.apply(plan, *tgt)
+    n = len(tgt)
+    denom = n_src if denom_layers is None else denom_layers
+    if denom != n:                       # zip truncation case: kernel divided by n, reference by len(src)
+        loss = loss * (float(n) / float(denom))
+    return loss
+
+
+class PatchNCELoss(nn.Module):
+    """Drop-in for ``PatchNCELoss`` of patchnce_cut.py:7-110 -- and, on 2-D inputs, the north-star
+    ``PatchNCELoss(feat_q, feat_k)``.
+
+    ``forward(src_feats, tgt_feats)`` with two lists of (B,C,H,W) maps follows the reference: one
+    id draw per zipped layer, loss = sum over layers / len(src_feats).
+    ``forward(feat_q, feat_k)`` with two (B*P, D) row tensors (rows grouped per image, already
+    L2-normalised, e.g. from ``PatchSampleF``) returns that layer's mean diagonal CE; the number of
+    images is ``feat_q.shape[0] // min(num_patches, rows)`` unless ``batch_size`` is given."""
+
+    def __init__(self, temperature: float = 0.07, num_patches: int = 256,
+                 nce_layers: Sequence[int] = (0, 4, 8, 12, 16), math: Optional[str] = None):
+        super().__init__()
+        self.temperature = temperature
+        self.num_patches = num_patches
+        self.nce_layers = list(nce_layers)      # stored, never used -- as in the reference (:22)
+        self.math = math
+        self.last_patch_ids: Optional[List[torch.Tensor]] = None
+
+    def forward(self, a, b, batch_size: Optional[int] = None):
+        if isinstance(a, torch.Tensor) and a.dim() == 2:
+            return rows_patchnce(a, b, self.temperature, self.num_patches, batch_size, self.math)
+        src_feats, tgt_feats = list(a), list(b)
+        _warnings.poll()
+        n = min(len(src_feats), len(tgt_feats))
+        ids = [draw_patch_ids(src_feats[l], self.num_patches) for l in range(n)]      # :60-63
+        self.last_patch_ids = ids
+        return fused_patchnce(src_feats, tgt_feats, ids, self.temperature, self.math)
+
+
+def compute_patchnce_loss(generator, src_images, tgt_images, nce_layers, temperature=0.07,
+                          num_patches=256, math: Optional[str] = None):
+    """Drop-in for ``compute_patchnce_loss`` -- patchnce_cut.py:113-149 (call site
+    training/train_cutpp.py:285-292).  ``generator`` only needs ``get_feature_layers``."""
+    nce_loss_fn = PatchNCELoss(temperature, num_patches, nce_layers, math=math)       # :135
+    with torch.no_grad():                                                              # :138-139
+        src_feats = generator.get_feature_layers(src_images, nce_layers)
+    src_feats = [f.detach() for f in src_feats]                                        # :142
+    tgt_feats = generator.get_feature_layers(tgt_images, nce_layers)                   # :145
+    return nce_loss_fn(src_feats, tgt_feats)                                           # :147
+
+
+# ------------------------------------------------------------------------------------------------
+# module split: PatchSampleF and the rows loss
+# ------------------------------------------------------------------------------------------------
+class _SampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, ids):
+        lib = _lib.load()
+        f = feat.detach().contiguous()
+        b, c, h, w = f.shape
+        p = ids.numel()
+        dev = f.device
+        with torch.cuda.device(dev):
+            rows = torch.empty(b * p, c, dtype=torch.float32, device=dev)
+            inv = torch.empty(b * p, dtype=torch.float32, device=dev)
+            _lib.check(lib.pnce_sample_fwd(f.data_ptr(), _DTYPES[f.dtype], b, c, h, w, ids.data_ptr(), p,
+                                           rows.data_ptr(), inv.data_ptr(), _stream_ptr(dev)),
+                       "pnce_sample_fwd")
+        ctx.save_for_backward(rows, inv, ids)
+        ctx.meta = (b, c, h, w, p, f.dtype, dev)
+        ctx.mark_non_differentiable(inv)
+        return rows, inv
+
+    @staticmethod
+    def backward(ctx, drows, _dinv):
+        lib = _lib.load()
+        rows, inv, ids = ctx.saved_tensors
+        b, c, h, w, p, dt, dev = ctx.meta
+        g = drows.detach().to(torch.float32).contiguous()
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.pnce_sample_bwd_workspace_bytes(b, c, h, w, p, ctypes.byref(nbytes)),
+                   "pnce_sample_bwd_workspace_bytes")
+        with torch.cuda.device(dev):
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            dfeat = torch.empty(b, c, h, w, dtype=dt, device=dev)
+            _lib.check(lib.pnce_sample_bwd(g.data_ptr(), rows.data_ptr(), inv.data_ptr(), _DTYPES[dt],
+                                           b, c, h, w, ids.data_ptr(), p, ws.data_ptr(), nbytes.value,
+                                           dfeat.data_ptr(), _stream_ptr(dev)), "pnce_sample_bwd")
+        return dfeat, None
+
+
+class _RowsLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, batch, p, temperature, math):
+        lib = _lib.load()
+        qq = q.detach().to(torch.float32).contiguous()
+        kk = k.detach().to(torch.float32).contiguous()
+        d = qq.shape[1]
+        dev = qq.device
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.pnce_rows_loss_workspace_bytes(batch, p, d, ctypes.byref(nbytes)),
+                   "pnce_rows_loss_workspace_bytes")
+        with torch.cuda.device(dev):
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            out = torch.empty(2, dtype=torch.float32, device=dev)
+            flag = torch.empty(1, dtype=torch.int32, device=dev)
+            dq = torch.empty_like(qq)
+            _lib.check(lib.pnce_rows_loss_fwd_bwd(qq.data_ptr(), kk.data_ptr(), batch, p, d, temperature,
+                                                  _MATH[math], ws.data_ptr(), nbytes.value, out.data_ptr(),
+                                                  flag.data_ptr(), dq.data_ptr(), None, _stream_ptr(dev)),
+                       "pnce_rows_loss_fwd_bwd")
+        _warnings.push(flag)
+        ctx.save_for_backward(dq)
+        ctx.q_dtype = q.dtype
+        return out.narrow(0, 0, 1).reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dq,) = ctx.saved_tensors
+        return (dq * grad_out).to(ctx.q_dtype), None, None, None, None, None
+
+
+def rows_patchnce(feat_q, feat_k, temperature=0.07, num_patches=256, batch_size=None, math=None):
+    """PatchNCELoss(feat_q, feat_k): rows (B*P, D), grouped per image, L2-normalised."""
+    _require_cuda(feat_q, "feat_q")
+    _require_cuda(feat_k, "feat_k")
+    if feat_q.shape != feat_k.shape or feat_q.dim() != 2:
+        raise RuntimeError("feat_q and feat_k must both be (B*P, D)")
+    if feat_k.requires_grad:
+        feat_k = feat_k.detach()          # upstream CUT and the reference (:142) detach k
+    rows = feat_q.shape[0]
+    if batch_size is None:
+        p = min(int(num_patches), rows)
+        if rows % p:
+            raise RuntimeError(f"{rows} rows are not a multiple of num_patches={p}; pass batch_size")
+        batch_size = rows // p
+    p = rows // batch_size
+    return _RowsLossFn.apply(feat_q, feat_k, batch_size, p, float(temperature), math or DEFAULT_MATH)
+
+
+class PatchSampleF(nn.Module):
+    """North-star ``PatchSampleF.forward(feats, num_patches, patch_ids)`` (SURVEY.md section 8 row
+    a13): per-layer random-patch gather from NCHW maps + L2 normalisation, ids drawn like the
+    reference (:60-63) when ``patch_ids`` is None.  Returns ``(list[(B*P_l, D_l)], list[(P_l,)])``.
+
+    ``use_mlp=True`` adds the netF head Linear(C_l, nc) -> ReLU -> Linear(nc, nc) before the
+    normalisation (created lazily per layer on first use, like upstream CUT's ``create_mlp``)."""
+
+    def __init__(self, use_mlp: bool = False, nc: int = 256, init_gain: float = 0.02):
+        super().__init__()
+        self.use_mlp = use_mlp
+        self.nc = nc
+        self.init_gain = init_gain
+        self.mlp_init = False
+
+    def create_mlp(self, feats):
+        for mlp_id, feat in enumerate(feats):
+            input_nc = feat.shape[1]
+            mlp = nn.Sequential(nn.Linear(input_nc, self.nc), nn.ReLU(), nn.Linear(self.nc, self.nc))
+            for m in mlp:
+                if isinstance(m, nn.Linear):
+                    nn.init.normal_(m.weight, 0.0, self.init_gain)
+                    nn.init.zeros_(m.bias)
+            setattr(self, f"mlp_{mlp_id}", mlp.to(feat.device))
+        self.mlp_init = True
+
+    def forward(self, feats, num_patches: int = 256, patch_ids=None):
+        return_feats, return_ids = [], []
+        if self.use_mlp and not self.mlp_init:
+            self.create_mlp(feats)
+        for feat_id, feat in enumerate(feats):
+            _require_cuda(feat, "feat")
+            if feat.dim() != 4:
+                raise ValueError("feature maps must be (B, C, H, W)")
+            if patch_ids is not None:
+                ids = patch_ids[feat_id].to(device=feat.device, dtype=torch.int64).contiguous()
+            else:
+                ids = draw_patch_ids(feat, num_patches)
+            if self.use_mlp:
+                raise NotImplementedError("netF head kernels land in a later milestone")
+            rows, _ = _SampleFn.apply(feat, ids)
+            return_feats.append(rows)
+            return_ids.append(ids)
+        return return_feats, return_ids
+
+
+def install_reference_shim():
+    """Make ``from GAN_Variant1.losses.patchnce_cut import compute_patchnce_loss`` resolve to this
+    implementation, so the unchanged reference training loop (train_cutpp.py:28) uses the B200
+    path.  Call before importing ``GAN_Variant1.training.train_cutpp``."""
+    import types
+    mod = types.ModuleType("GAN_Variant1.losses.patchnce_cut")
+    mod.PatchNCELoss = PatchNCELoss
+    mod.compute_patchnce_loss = compute_patchnce_loss
+    mod.__doc__ = "B200-native PatchNCE (gan_variant_research_b200) behind the reference's module path."
+    sys.modules["GAN_Variant1.losses.patchnce_cut"] = mod
+    pkg = sys.modules.get("GAN_Variant1.losses")
+    if pkg is not None:
+        setattr(pkg, "patchnce_cut", mod)
+    return mod

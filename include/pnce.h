@@ -1,0 +1,114 @@
+/*
+ * pnce.h -- C ABI of libpnce.so, the B200 (sm_100a) PatchNCE hot path.
+ *
+ * The reference (Cameronr11/GAN-Variant-Research) has no FFI: its seam is two Python symbols in
+ * GAN_Variant1/losses/patchnce_cut.py.  These entry points are what a
+ * binding for that seam calls; each one cites the reference lines it replaces.  The Python host
+ * (gan_variant_research_b200/patchnce.py) binds them with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions (all entry points):
+ *   - every pointer named dev_* / inside pnce_layer_t is a DEVICE pointer owned by the caller
+ *     (torch tensors in practice); the library allocates nothing persistent on the device path;
+ *   - every call is asynchronous on `stream` (a cudaStream_t / CUstream passed as void*), performs
+ *     no host synchronisation and is CUDA-graph capturable;
+ *   - return value: 0 on success, a negative pnce_status_t otherwise; nothing throws;
+ *   - thread-safe per (workspace, stream) pair.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     PNCE_ERR_CUDA.
+ */
+#ifndef PNCE_H_
+#define PNCE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNCE_ABI_VERSION 1
+#define PNCE_MAX_LAYERS 8      /* nce_layers per call (reference config uses 5 ids -> 4 maps)   */
+#define PNCE_MAX_PATCHES 4096  /* P = min(num_patches, H*W)  patchnce_cut.py:60                 */
+#define PNCE_MAX_CHANNELS 1024
+
+typedef enum {
+  PNCE_OK = 0,
+  PNCE_ERR_ARG = -1,        /* NULL pointer, bad shape, too many layers ...                      */
+  PNCE_ERR_UNSUPPORTED = -2,/* shape outside the compiled limits                                 */
+  PNCE_ERR_WORKSPACE = -3,  /* workspace too small / misaligned                                  */
+  PNCE_ERR_CUDA = -4,       /* a CUDA runtime call failed (see pnce_last_cuda_error)             */
+  PNCE_ERR_ALIGN = -5       /* a tensor base pointer is not element-aligned                      */
+} pnce_status_t;
+
+typedef enum { PNCE_F32 = 0, PNCE_F16 = 1, PNCE_BF16 = 2 } pnce_dtype_t;
+
+/* How the per-image logits / dQ contractions are evaluated.
+ *   PNCE_MATH_SIMT_F32 : fp32 FFMA, bit-for-bit the reference's fp32 op order up to summation order
+ *   PNCE_MATH_TC_BF16X3: tcgen05 bf16 tensor cores, operands split hi+lo (3 MMAs), fp32 accumulate
+ *   PNCE_MATH_TC_BF16  : tcgen05 bf16 single pass (the AMP regime of the reference: fp16 GEMM)    */
+typedef enum { PNCE_MATH_SIMT_F32 = 0, PNCE_MATH_TC_BF16X3 = 1, PNCE_MATH_TC_BF16 = 2 } pnce_math_t;
+
+/* One nce layer: a pair of contiguous NCHW feature maps and the ids sampled on it.
+ * Replaces the (src_feat, tgt_feat) pair zipped at patchnce_cut.py:36 plus patch_ids of :63.   */
+typedef struct pnce_layer {
+  const void*    src;   /* (B,C,H,W) source features, no gradient          patchnce_cut.py:142 */
+  const void*    tgt;   /* (B,C,H,W) target features                       patchnce_cut.py:145 */
+  void*          dtgt;  /* (B,C,H,W) dense d loss / d tgt, same dtype; written by pnce_bwd only  */
+  const int64_t* ids;   /* (P,) int64 in [0,H*W), with replacement, shared by the batch     :63 */
+  int32_t C, H, W, P;
+} pnce_layer_t;
+
+int         pnce_abi_version(void);
+const char* pnce_status_string(int status);
+const char* pnce_last_cuda_error(void);
+
+/* Bytes of device scratch pnce_fwd/pnce_bwd need for this problem (ids order, normalised rows,
+ * d rows, id bitmap ...).  Contents need no initialisation.                                    */
+int pnce_workspace_bytes(const pnce_layer_t* layers, int n_layers, int batch, size_t* bytes);
+
+/* Forward of PatchNCELoss.forward for all layers in one pass        patchnce_cut.py:25-110
+ *   gather (:66-74) -> L2 normalise (:77-78) -> per-image logits/tau, clamp (:85-88)
+ *   -> diagonal CE (:91-94) -> non-finite guards (:97-108) -> batch mean, layer mean (:103,:40)
+ * and, fused, the backward of all of that up to the per-patch gradient rows (unit upstream
+ * gradient), kept in the workspace for pnce_bwd.  Logits never reach HBM.
+ *   dev_loss_out : float[1 + n_layers]  -> [0] total loss, [1+l] layer losses
+ *   dev_nonfinite: int[1]               -> number of (layer,image) pairs whose loss was replaced
+ *                                          by 0 (the reference prints a warning for each, :98)   */
+int pnce_fwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, float temperature,
+             int math_mode, void* dev_workspace, size_t workspace_bytes, float* dev_loss_out,
+             int* dev_nonfinite, void* stream);
+
+/* Backward: writes every layers[l].dtgt densely (zero off the sampled positions, duplicate ids
+ * accumulated) scaled by the upstream gradient *dev_grad_out (NULL = 1.0).  Replaces the autograd
+ * chain of SURVEY.md section 8 row a11 (index_put_ / select_backward / zeros + adds).           */
+int pnce_bwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, void* dev_workspace,
+             size_t workspace_bytes, const float* dev_grad_out, void* stream);
+
+/* ---- north-star module split ------------------------------ */
+
+/* PatchSampleF(use_mlp=False) forward for one map: rows_out (B*P, C) fp32 = L2-normalised patches
+ * in ids order, inv_out (B*P) = 1/||x|| (negative -1/eps when ||x|| < eps, NaN for a non-finite
+ * row).                                                                  patchnce_cut.py:53-78 */
+int pnce_sample_fwd(const void* dev_feat, int dtype, int batch, int C, int H, int W,
+                    const int64_t* dev_ids, int P, float* dev_rows_out, float* dev_inv_out,
+                    void* stream);
+
+/* Backward of pnce_sample_fwd: d rows (B*P, C) fp32 -> dense d feat (B,C,H,W) in `dtype`.       */
+int pnce_sample_bwd_workspace_bytes(int batch, int C, int H, int W, int P, size_t* bytes);
+int pnce_sample_bwd(const float* dev_drows, const float* dev_rows, const float* dev_inv, int dtype,
+                    int batch, int C, int H, int W, const int64_t* dev_ids, int P,
+                    void* dev_workspace, size_t workspace_bytes, void* dev_dfeat, void* stream);
+
+/* PatchNCELoss(feat_q, feat_k) on already-normalised rows (B*P, D) fp32, rows grouped per image:
+ * loss_out[0] = mean_b mean_i CE_i (:83-103); dq_out = d loss / d feat_q for unit upstream;
+ * dk_out optional (NULL when feat_k is detached, as in the reference :142).                     */
+int pnce_rows_loss_workspace_bytes(int batch, int P, int D, size_t* bytes);
+int pnce_rows_loss_fwd_bwd(const float* dev_q, const float* dev_k, int batch, int P, int D,
+                           float temperature, int math_mode, void* dev_workspace,
+                           size_t workspace_bytes, float* dev_loss_out, int* dev_nonfinite,
+                           float* dev_dq_out, float* dev_dk_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNCE_H_ */

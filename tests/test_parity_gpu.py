@@ -1,0 +1,317 @@
+"""Parity tests proper: the CUDA path (through the ctypes C ABI) against the golden fixtures
+frozen from the unmodified reference and against the oracle on the same seeded inputs.
+Tolerances: ids bit-exact; loss and gradients 1e-3 relative (north_star) -- the fp32 SIMT mode is
+held to 2e-5 / 1e-4 so the gate has teeth."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SMALL = sorted(glob.glob(os.path.join(HERE, "golden", "small_*.npz")))
+R4 = [(64, 256, 256), (256, 64, 64), (256, 64, 64), (128, 128, 128)]
+B5 = R4 + [(64, 256, 256)]
+
+
+@pytest.fixture(scope="module")
+def pn():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import gan_variant_research_b200 as m
+    from gan_variant_research_b200 import _lib
+    _lib.load()
+    return m
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import patchnce_oracle
+    return patchnce_oracle
+
+
+def dev(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def assert_grad_close(got, want, rtol, what=""):
+    """max-abs error relative to the largest reference entry; NaN patterns must coincide."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want), err_msg=f"{what}: NaN pattern")
+    m = ~np.isnan(want)
+    scale = max(float(np.abs(want[m]).max()) if m.any() else 0.0, 1e-30)
+    err = float(np.abs(got[m] - want[m]).max()) / scale if m.any() else 0.0
+    assert err <= rtol, f"{what}: rel err {err:.3e} > {rtol}"
+    # exact zeros stay exact zeros (dense gradient is zero off the sampled positions)
+    np.testing.assert_array_equal(got[m] != 0, want[m] != 0, err_msg=f"{what}: sparsity pattern")
+
+
+def load_small(path):
+    d = np.load(path)
+    n = int(d["n_layers"])
+    return (d, [d[f"src{i}"] for i in range(n)], [d[f"tgt{i}"] for i in range(n)],
+            [d[f"ids{i}"] for i in range(n)], [d[f"grad{i}"] for i in range(n)])
+
+
+@pytest.mark.parametrize("path", SMALL, ids=[os.path.basename(p)[6:-4] for p in SMALL])
+def test_fused_matches_reference_goldens(pn, path):
+    d, src, tgt, ids, grads = load_small(path)
+    t = [dev(x).requires_grad_() for x in tgt]
+    loss = pn.fused_patchnce([dev(x) for x in src], t, [dev(i) for i in ids], float(d["tau"]))
+    (loss * float(d["upstream"])).backward()
+    assert loss.dtype == torch.float32 and loss.dim() == 0 and loss.is_cuda
+    assert loss.item() == pytest.approx(float(d["loss"]), rel=2e-5, abs=1e-6)
+    for i, (tt, g) in enumerate(zip(t, grads)):
+        assert_grad_close(tt.grad.cpu().numpy(), g, 1e-4, f"layer {i}")
+
+
+def test_nonfinite_images_are_counted_and_reported(pn, capsys):
+    d, src, tgt, ids, _ = load_small(os.path.join(HERE, "golden", "small_nan_image.npz"))
+    pn.poll_nonfinite_warnings(block=True)
+    loss = pn.fused_patchnce([dev(x) for x in src], [dev(x) for x in tgt], [dev(i) for i in ids], 0.07)
+    assert torch.isfinite(loss)
+    assert pn.poll_nonfinite_warnings(block=True) == 1
+    assert "Warning: NaN in PatchNCE loss" in capsys.readouterr().out
+
+
+def test_patch_ids_bit_exact_and_rng_stream_aligned(pn, orc):
+    """Same generator state on the same device => identical ids per layer (int64, with
+    replacement, shared by the batch, one draw per returned layer, P = min(num_patches, HW)) and
+    the generator is left in the same state (SURVEY.md 3.1 RNG note)."""
+    shapes = [(8, 64, 64), (4, 7, 9), (16, 128, 128), (4, 3, 3)]
+    src = [torch.randn(2, *s, device="cuda") for s in shapes]
+    tgt = [torch.randn(2, *s, device="cuda") for s in shapes]
+    torch.manual_seed(7)
+    want = [orc.draw_patch_ids(s[1] * s[2], 256, "cuda") for s in shapes]
+    after_want = torch.rand(4, device="cuda")
+    torch.manual_seed(7)
+    mod = pn.PatchNCELoss(0.07, 256, [0, 4, 8, 12, 16])
+    mod(src, tgt)
+    after_got = torch.rand(4, device="cuda")
+    for g, w, s in zip(mod.last_patch_ids, want, shapes):
+        assert g.dtype == torch.int64 and g.numel() == min(256, s[1] * s[2])
+        assert torch.equal(g, w)
+    assert torch.equal(after_got, after_want)
+    # PatchSampleF draws the same way
+    torch.manual_seed(7)
+    _, ids = pn.PatchSampleF()(tgt, 256)
+    for g, w in zip(ids, want):
+        assert torch.equal(g, w)
+
+
+@pytest.mark.parametrize("b", [1, 2])
+def test_survey_tripwire_full_size(pn, b):
+    """full-size R4 maps, the reference's own CPU-drawn ids."""
+    d = np.load(os.path.join(HERE, "golden", f"survey_r4_b{b}.npz"))
+    g = torch.Generator().manual_seed(1234)
+    src = [torch.randn(b, *s, generator=g).relu() for s in R4]
+    tgt = [torch.randn(b, *s, generator=g).relu() for s in R4]
+    ids = [dev(d[f"ids{i}"]) for i in range(4)]
+    t = [x.cuda().requires_grad_() for x in tgt]
+    loss = pn.fused_patchnce([x.cuda() for x in src], t, ids, 0.07)
+    loss.backward()
+    assert loss.item() == pytest.approx(float(d["loss"]), rel=2e-5)
+    for i, tt in enumerate(t):
+        gr = tt.grad
+        assert gr.double().norm().item() == pytest.approx(float(d[f"gnorm{i}"]), rel=1e-4)
+        assert gr.double().sum().item() == pytest.approx(float(d[f"gsum{i}"]), rel=1e-3, abs=1e-7)
+        assert int((gr != 0).sum()) == int(d[f"nnz{i}"])            # = unique(ids) * C
+        cols = gr[0].reshape(gr.shape[1], -1)[:, ids[i][:8]].cpu().numpy()
+        assert_grad_close(cols, d[f"gcols{i}"], 1e-4, f"layer {i} columns")
+
+
+def test_layer_mean_divides_by_number_of_maps(pn, orc):
+    """[0,4,8,12,16] returns 4 maps and the loss divides by 4 (patchnce_cut.py:40): checked with a
+    stub generator that numbers layers like generator_resnet_attn.py:203-235."""
+    class StubG(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.convs = torch.nn.ModuleList(
+                [torch.nn.Conv2d(3 if i == 0 else 8, 8, 3, padding=1) for i in range(14)])
+
+        def get_feature_layers(self, x, layer_ids=None):
+            feats = []
+            for i, c in enumerate(self.convs):       # logical layers 0..13 only
+                x = torch.relu(c(x))
+                if i in layer_ids:
+                    feats.append(x)
+            return feats
+
+    torch.manual_seed(0)
+    gen = StubG().cuda()
+    x = torch.randn(2, 3, 16, 16, device="cuda")
+    y = torch.randn(2, 3, 16, 16, device="cuda", requires_grad=True)
+    assert len(gen.get_feature_layers(x, [0, 4, 8, 12, 16])) == 4
+    torch.manual_seed(3)
+    loss = pn.compute_patchnce_loss(gen, x, y, [0, 4, 8, 12, 16], 0.07, 64)
+    loss.backward()
+    g_got = y.grad.clone()
+    y.grad = None
+    gen_cpu = StubG()
+    gen_cpu.load_state_dict(gen.state_dict())
+    # same ids: redraw on the device with the same seed
+    torch.manual_seed(3)
+    ids = [orc.draw_patch_ids(256, 64, "cuda").cpu() for _ in range(4)]
+    y_cpu = y.detach().cpu().requires_grad_()
+    want = orc.compute_patchnce_loss_torch(gen_cpu, x.cpu(), y_cpu, [0, 4, 8, 12, 16], 0.07, 64, ids_list=ids)
+    want.backward()
+    assert loss.item() == pytest.approx(want.item(), rel=1e-4)
+    assert_grad_close(g_got.cpu().numpy(), y_cpu.grad.numpy(), 2e-3, "d loss / d tgt image")
+    # params of the generator received gradient only through the tgt pass
+    assert all(p.grad is not None for p in gen.parameters())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_half_precision_feature_maps(pn, orc, dtype):
+    """AMP regime: 16-bit maps in, fp32 math inside, dense gradient in the map dtype."""
+    g = torch.Generator().manual_seed(21)
+    shapes = [(32, 16, 16), (24, 8, 8)]
+    src = [torch.randn(2, *s, generator=g).to(dtype) for s in shapes]
+    tgt = [torch.randn(2, *s, generator=g).to(dtype) for s in shapes]
+    ids = [torch.randint(0, s[1] * s[2], (min(64, s[1] * s[2]),), generator=g) for s in shapes]
+    t = [x.cuda().requires_grad_() for x in tgt]
+    loss = pn.fused_patchnce([x.cuda() for x in src], t, [i.cuda() for i in ids], 0.07)
+    loss.backward()
+    want, _, gw = orc.patchnce_loss_and_grads_np([x.float().numpy() for x in src],
+                                                 [x.float().numpy() for x in tgt],
+                                                 [i.numpy() for i in ids], 0.07)
+    assert loss.item() == pytest.approx(want, rel=2e-5)
+    for tt, gg in zip(t, gw):
+        assert tt.grad.dtype == dtype
+        got = tt.grad.float().cpu().numpy()
+        scale = np.abs(gg).max()
+        assert np.abs(got - gg).max() / scale < (2e-3 if dtype == torch.float16 else 1e-2)
+        np.testing.assert_array_equal(got != 0, gg != 0)
+
+
+def test_patch_sample_f_rows_and_backward(pn, orc):
+    g = torch.Generator().manual_seed(31)
+    feats = [torch.randn(3, 20, 9, 7, generator=g), torch.randn(3, 64, 16, 16, generator=g).relu()]
+    ids = [torch.randint(0, 63, (40,), generator=g), torch.randint(0, 256, (256,), generator=g)]
+    fd = [f.cuda().requires_grad_() for f in feats]
+    rows, rid = pn.PatchSampleF()(fd, 256, [i.cuda() for i in ids])
+    upstream = [torch.randn(r.shape, generator=g) for r in rows]
+    torch.autograd.backward(rows, [u.cuda() for u in upstream])
+    for f, i, r, u, fdev, ri in zip(feats, ids, rows, upstream, fd, rid):
+        want, _ = orc.gather_normalize_np(f.numpy(), i.numpy())
+        assert r.shape == (3 * i.numel(), f.shape[1]) and r.dtype == torch.float32
+        np.testing.assert_allclose(r.detach().cpu().numpy(), want, rtol=2e-6, atol=2e-7)
+        assert torch.equal(ri.cpu(), i)
+        fc = f.clone().requires_grad_()
+        b, c = f.shape[:2]
+        ref = torch.nn.functional.normalize(
+            fc.reshape(b, c, -1).transpose(1, 2)[:, i, :], dim=2, eps=1e-6).reshape(-1, c)
+        ref.backward(u)
+        assert_grad_close(fdev.grad.cpu().numpy(), fc.grad.numpy(), 1e-5, "PatchSampleF backward")
+
+
+def test_module_split_composes_to_the_reference(pn):
+    """PatchSampleF (no head) + PatchNCELoss(feat_q, feat_k), summed / L, equals the fused
+    reference-compat path on the same ids (consequence 2)."""
+    d, src, tgt, ids, grads = load_small(os.path.join(HERE, "golden", "small_ragged.npz"))
+    t = [dev(x).requires_grad_() for x in tgt]
+    s = [dev(x) for x in src]
+    idd = [dev(i) for i in ids]
+    sampler, crit = pn.PatchSampleF(), pn.PatchNCELoss(0.07, 64)
+    fq, _ = sampler(t, 64, idd)
+    with torch.no_grad():
+        fk, _ = sampler(s, 64, idd)
+    total = 0.0
+    for q, k in zip(fq, fk):
+        total = total + crit(q, k, batch_size=3)
+    loss = total / len(fq)
+    loss.backward()
+    assert loss.item() == pytest.approx(float(d["loss"]), rel=2e-5)
+    for i, (tt, g) in enumerate(zip(t, grads)):
+        assert_grad_close(tt.grad.cpu().numpy(), g, 1e-4, f"layer {i}")
+
+
+def test_rows_loss_matches_torch(pn):
+    g = torch.Generator().manual_seed(41)
+    b, p, dd = 3, 100, 48
+    q = torch.nn.functional.normalize(torch.randn(b * p, dd, generator=g), dim=1)
+    k = torch.nn.functional.normalize(torch.randn(b * p, dd, generator=g), dim=1)
+    qd = q.cuda().requires_grad_()
+    loss = pn.rows_patchnce(qd, k.cuda(), 0.07, num_patches=p)
+    (loss * 2.5).backward()
+    qc = q.clone().requires_grad_()
+    acc = 0.0
+    for i in range(b):
+        z = (qc[i * p:(i + 1) * p] @ k[i * p:(i + 1) * p].t() / 0.07).clamp(-50, 50)
+        acc = acc + torch.nn.functional.cross_entropy(z, torch.arange(p))
+    want = acc / b
+    (want * 2.5).backward()
+    assert loss.item() == pytest.approx(want.item(), rel=2e-5)
+    assert_grad_close(qd.grad.cpu().numpy(), qc.grad.numpy(), 1e-4, "dq")
+
+
+def test_full_size_properties_b5(pn):
+    """Size-independent properties at BASELINE's full sizes (B5 layer set, B=4, P=256):
+    sparsity = unique(ids)*C per image, linearity in the upstream gradient, and the virtual-shard
+    law of SURVEY.md 8e (same ids, batch split in two, losses averaged, grads halved)."""
+    b = 4
+    g = torch.Generator(device="cuda").manual_seed(99)
+    src = [torch.randn(b, *s, device="cuda", generator=g).relu() for s in B5]
+    tgt = [torch.randn(b, *s, device="cuda", generator=g).relu() for s in B5]
+    ids = [torch.randint(0, s[1] * s[2], (256,), device="cuda", generator=g) for s in B5]
+
+    def run(sl, scale):
+        t = [x[sl].clone().requires_grad_() for x in tgt]
+        loss = pn.fused_patchnce([x[sl] for x in src], t, ids, 0.07)
+        (loss * scale).backward()
+        return loss.detach(), [x.grad for x in t]
+
+    loss, grads = run(slice(0, b), 1.0)
+    loss2, grads2 = run(slice(0, b), 4.0)
+    assert torch.equal(loss, loss2)
+    for l, (ga, gb, i) in enumerate(zip(grads, grads2, ids)):
+        u = torch.unique(i).numel()
+        per_image = (ga != 0).reshape(b, -1).sum(1)
+        assert torch.all(per_image <= u * B5[l][0])
+        assert torch.all(per_image >= u * B5[l][0] - 8)         # an exact 0.0 entry is possible, barely
+        mask = torch.zeros(B5[l][1] * B5[l][2], dtype=torch.bool, device="cuda")
+        mask[i] = True
+        assert not (ga.reshape(b, B5[l][0], -1)[:, :, ~mask] != 0).any()
+        torch.testing.assert_close(gb, ga * 4.0, rtol=1e-6, atol=0)
+    la, gA = run(slice(0, 2), 1.0)
+    lb, gB = run(slice(2, 4), 1.0)
+    assert ((la + lb) / 2).item() == pytest.approx(loss.item(), rel=1e-6)
+    for ga, g1, g2 in zip(grads, gA, gB):
+        torch.testing.assert_close(torch.cat([g1, g2]) / 2, ga, rtol=1e-5, atol=1e-12)
+
+
+def test_stress_config_p1024_512(pn, orc):
+    """BASELINE config 4 shape class: 512^2 maps, num_patches=1024 (one 256x128x128 layer, B=2),
+    checked against the float64 analytic oracle."""
+    g = torch.Generator().manual_seed(77)
+    s = (256, 128, 128)
+    src = [torch.randn(2, *s, generator=g)]
+    tgt = [torch.randn(2, *s, generator=g)]
+    ids = [torch.randint(0, s[1] * s[2], (1024,), generator=g)]
+    t = [x.cuda().requires_grad_() for x in tgt]
+    loss = pn.fused_patchnce([x.cuda() for x in src], t, [i.cuda() for i in ids], 0.07)
+    loss.backward()
+    want, _, gw = orc.patchnce_loss_and_grads_np([x.numpy() for x in src], [x.numpy() for x in tgt],
+                                                 [i.numpy() for i in ids], 0.07)
+    assert loss.item() == pytest.approx(want, rel=2e-5)
+    assert_grad_close(t[0].grad.cpu().numpy(), gw[0], 1e-4, "P=1024")
+
+
+def test_empty_and_mismatched_inputs(pn):
+    with pytest.raises(ZeroDivisionError):
+        pn.PatchNCELoss()([], [])
+    a = torch.randn(1, 4, 4, 4, device="cuda")
+    with pytest.raises(RuntimeError):
+        pn.fused_patchnce([a], [torch.randn(1, 4, 5, 4, device="cuda")], [torch.zeros(4, dtype=torch.int64, device="cuda")])
+    # zip truncation: 2 src maps, 1 tgt map -> one layer computed, divided by len(src_feats) = 2 (:36-40)
+    torch.manual_seed(1)
+    l2 = pn.PatchNCELoss(0.07, 8)([a, a], [a.clone()])
+    torch.manual_seed(1)
+    l1 = pn.PatchNCELoss(0.07, 8)([a], [a.clone()])
+    assert l2.item() == pytest.approx(l1.item() / 2, rel=1e-6)
