@@ -37,6 +37,16 @@ struct LayerDev {
   float* dxT;                // [B][C][P] d loss / d raw target patch, unit upstream, SORTED slot order
   float* partial;            // [B][ntiles] partial sums of row losses
   float* dq_rows;            // optional [B][P][C] output of the rows API (then dxT/qinv unused)
+  int nparts;                // partial row-loss sums per image (ntiles on the SIMT path, halves on TC)
+  // ---- tensor-core path (gather_tc.cuh / loss_tc.cuh) ----
+  int Cp, Ppad, nchunk;      // C rounded up to 32, P rounded up to 128 (<= 256), Cp / 32
+  __nv_bfloat16* qhi;        // Q operand blob, bf16 high part   [B][Ppad/128][Cp/8][16][8][8]
+  __nv_bfloat16* qlo;        // low part (value - hi), NULL in single-pass bf16 mode
+  __nv_bfloat16* khi;        // K operand blob                   [B][Cp/8][Ppad/8][8][8]
+  __nv_bfloat16* klo;
+  float* qT;                 // [B][C][Ppad] raw fp32 target patches (transposed)
+  float* qss;                // [B][nchunk][Ppad] partial sums of squares (NaN: non-finite element)
+  float* kss;
 };
 
 struct Params {

@@ -137,7 +137,7 @@ __device__ void gather_tile(const LayerDev& L, int B, int side0, long long local
   int bad = 0;
 #pragma unroll 8
   for (int c = warp; c < C; c += 8) {
-    float v = ok ? to_f32<T>(__ldg(col + (size_t)c * HW)) : 0.f;
+    float v = ok ? to_f32<T>(__ldcg(col + (size_t)c * HW)) : 0.f;   // L2-only: no 128 B L1 line fill
     tile_s[lane * ldt + c] = v;
     ss = fmaf(v, v, ss);
     bad |= !isfinite(v);
@@ -185,7 +185,10 @@ __global__ void __launch_bounds__(kThreads) k_gather_prep(const __grid_constant_
   const long long n_gather = m.start[p.n_layers];
   if (blk >= n_gather) {
     const int l = (int)(blk - n_gather);
-    if (l == 0 && threadIdx.x == 0 && p.counter != nullptr) *p.counter = 0u;
+    if (l == 0 && threadIdx.x == 0 && p.counter != nullptr) {
+      *p.counter = 0u;
+      if (p.nonfinite != nullptr) p.nonfinite[1] = 0;
+    }
     if (p.L[l].sid == nullptr) return;
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     int N2 = 1;

@@ -1,0 +1,109 @@
+// Tensor-core path, launch 1: random-patch gather that writes the MMA operands directly.
+//   CTA  <-> (layer, side, image, chunk of 32 channels);  thread <-> patch p  (P <= 256)
+//   every thread issues 32 independent L2-only loads (one sector each: element (c, id) of an NCHW
+//   plane), splits each value into bf16 hi + lo, and stores 8 consecutive channels as one 16-byte
+//   row of an 8x8 core matrix.  The global operand blobs are laid out exactly as the shared-memory
+//   image the tensor core reads (no-swizzle canonical layout), so the loss kernel moves them with
+//   1-D bulk copies:
+//     Q blob: [image][half m = p/128][c/8][16 row groups][8 rows][8 ch]   bf16
+//     K blob: [image][c/8][Ppad/8 row groups][8 rows][8 ch]                bf16
+//   Values are RAW (not normalised): the row norms are only known once all channels are seen, so
+//   each chunk also emits its partial sum of squares and the loss kernel folds 1/||q||, 1/||k||
+//   into its epilogues.  The raw fp32 target patches are kept transposed (C, Ppad) for the
+//   normalise backward.  Replaces patchnce_cut.py:56-78 on the tensor-core path.
+#pragma once
+#include "common.cuh"
+#include "gather.cuh"
+
+namespace pnce {
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+template <typename T>
+__device__ void gather_tc_chunk(const LayerDev& L, int B, long long local) {
+  const int p = threadIdx.x;
+  const int nchunk = L.nchunk;
+  const int s = (int)(local % nchunk);
+  const long long rest = local / nchunk;
+  const int b = (int)(rest % B);
+  const int side = (int)(rest / B);                          // 0 = src (k), 1 = tgt (q)
+  const int C = L.C, HW = L.HW, P = L.P, Ppad = L.Ppad, Cp8 = L.Cp >> 3;
+  if (p >= Ppad) return;
+  const bool valid = p < P;
+  long long id = valid ? L.ids[p] : 0;
+  id = id < 0 ? 0 : (id >= HW ? HW - 1 : id);
+  const T* col = reinterpret_cast<const T*>(side ? L.tgt : L.src) + (size_t)b * C * HW + id;
+  float v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int c = s * 32 + k;
+    v[k] = (valid && c < C) ? to_f32<T>(__ldcg(col + (size_t)c * HW)) : 0.f;
+  }
+  float ss = 0.f;
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    ss = fmaf(v[k], v[k], ss);
+    bad |= !isfinite(v[k]);
+  }
+  float* ssout = (side ? L.qss : L.kss) + ((size_t)b * nchunk + s) * Ppad + p;
+  *ssout = bad ? __int_as_float(0x7fc00000) : ss;
+  __nv_bfloat16* hi_base = side ? L.qhi : L.khi;
+  __nv_bfloat16* lo_base = side ? L.qlo : L.klo;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int c8 = s * 4 + g;
+    size_t cm;                                                // core-matrix index
+    if (side) cm = (((size_t)b * (Ppad >> 7) + (p >> 7)) * Cp8 + c8) * 16 + ((p & 127) >> 3);
+    else cm = ((size_t)b * Cp8 + c8) * (Ppad >> 3) + (p >> 3);
+    const size_t off = cm * 64 + (size_t)(p & 7) * 8;         // elements
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = v[g * 8 + 2 * k], c2 = v[g * 8 + 2 * k + 1];
+      const __nv_bfloat16 ah = __float2bfloat16_rn(a), ch = __float2bfloat16_rn(c2);
+      const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+      const __nv_bfloat16 cl = __float2bfloat16_rn(c2 - __bfloat162float(ch));
+      hw[k] = pack_bf16x2(ah, ch);
+      lw[k] = pack_bf16x2(al, cl);
+    }
+    *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    if (lo_base != nullptr) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+  if (side) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int c = s * 32 + k;
+      if (c < C) L.qT[((size_t)b * C + c) * Ppad + p] = v[k];
+    }
+  }
+}
+
+// grid = sum_l 2*B*nchunk_l gather CTAs, then n_layers prep CTAs (same prep as the SIMT path).
+__global__ void __launch_bounds__(kThreads) k_gather_tc(const __grid_constant__ Params p,
+                                                        const __grid_constant__ BlockMap m) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const long long blk = blockIdx.x;
+  const long long n_gather = m.start[p.n_layers];
+  if (blk >= n_gather) {
+    const int l = (int)(blk - n_gather);
+    if (l == 0 && threadIdx.x == 0 && p.counter != nullptr) {
+      *p.counter = 0u;
+      if (p.nonfinite != nullptr) p.nonfinite[1] = 0;
+    }
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+    int N2 = 1;
+    while (N2 < p.L[l].P) N2 <<= 1;
+    prep_layer(p.L[l], keys, reinterpret_cast<int*>(keys + N2));
+    return;
+  }
+  const int l = find_layer(m, blk, p.n_layers);
+  const long long local = blk - m.start[l];
+  if (p.dtype == PNCE_F32) gather_tc_chunk<float>(p.L[l], p.B, local);
+  else if (p.dtype == PNCE_F16) gather_tc_chunk<__half>(p.L[l], p.B, local);
+  else gather_tc_chunk<__nv_bfloat16>(p.L[l], p.B, local);
+}
+
+}  // namespace pnce

@@ -19,13 +19,13 @@ __host__ __device__ inline size_t loss_simt_smem_bytes(int P) {
 
 // Deterministic epilogue run by the last CTA of the launch.
 __device__ void finalize_losses(const Params& p) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const int B = p.B, nl = p.n_layers;
   for (int l = 0; l < nl; ++l) {
     const LayerDev& L = p.L[l];
-    for (int b = tid; b < B; b += kThreads) {
+    for (int b = tid; b < B; b += nthr) {
       float s = 0.f;
-      for (int t = 0; t < L.ntiles; ++t) s += __ldcg(L.partial + (size_t)b * L.ntiles + t);
+      for (int t = 0; t < L.nparts; ++t) s += __ldcg(L.partial + (size_t)b * L.nparts + t);
       float lb = s / (float)L.P;                                // CE reduction='mean' over rows  :94
       int ok = isfinite(lb) ? 1 : 0;                            // :97
       p.lossimg[l * B + b] = ok ? lb : 0.f;                     // :99
@@ -61,9 +61,9 @@ __device__ void finalize_losses(const Params& p) {
       if (p.valid[l * B + b] && !layer_bad[l]) continue;
       const size_t n = (size_t)L.C * L.P;
       if (L.dq_rows != nullptr) {
-        for (size_t i = tid; i < n; i += kThreads) L.dq_rows[(size_t)b * n + i] = 0.f;
+        for (size_t i = tid; i < n; i += nthr) L.dq_rows[(size_t)b * n + i] = 0.f;
       } else {
-        for (size_t i = tid; i < n; i += kThreads) {
+        for (size_t i = tid; i < n; i += nthr) {
           int c = (int)(i / L.P), pp = (int)(i % L.P);
           float inv = L.qinv[(size_t)b * L.P + pp];
           float v = (!layer_bad[l] && !(inv == inv)) ? __int_as_float(0x7fc00000) : 0.f;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kThreads) k_loss_simt(const __grid_constant__ 
   if (tid == 0) {
     float s = 0.f;
     for (int r = 0; r < 32; ++r) s += rl[r];
-    L.partial[(size_t)b * L.ntiles + tile] = s;
+    L.partial[(size_t)b * L.nparts + tile] = s;
   }
 
   // ---- phase C/D: dQ tile = dZ K / tau, normalise backward, transposed store -----------------

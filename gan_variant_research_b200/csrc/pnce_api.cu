@@ -6,7 +6,9 @@
 #include "common.cuh"
 #include "dense.cuh"
 #include "gather.cuh"
+#include "gather_tc.cuh"
 #include "loss_simt.cuh"
+#include "loss_tc.cuh"
 #include "sample_bwd.cuh"
 
 namespace pnce {
@@ -62,8 +64,16 @@ static int check_layers(const pnce_layer_t* layers, int n_layers, int B) {
   return PNCE_OK;
 }
 
+static bool tc_shapes_ok(const pnce_layer_t* layers, int n_layers) {
+  for (int l = 0; l < n_layers; ++l)
+    if (layers[l].P > 256 || layers[l].C > 256) return false;
+  return true;
+}
+
 // Fills Params (pointers into the workspace) for the fused path; returns bytes used.
-static size_t carve_fused(const pnce_layer_t* layers, int n_layers, int B, void* ws, Params* out) {
+// tc = carve the tensor-core operand blobs instead of the fp32 normalised rows.
+static size_t carve_fused(const pnce_layer_t* layers, int n_layers, int B, bool tc, bool x3, void* ws,
+                          Params* out) {
   Carver cv(ws);
   Params p;
   memset(&p, 0, sizeof(p));
@@ -87,12 +97,30 @@ static size_t carve_fused(const pnce_layer_t* layers, int n_layers, int B, void*
     L.ustart = cv.take<int>(a.P + 1);
     L.bitmap = cv.take<unsigned>(L.nwords);
     L.prefix = cv.take<unsigned>(L.nwords);
-    L.qn = cv.take<float>(rows);
-    L.kn = cv.take<float>(rows);
     L.qinv = cv.take<float>((size_t)B * a.P);
     L.dxT = cv.take<float>(rows);
-    L.partial = cv.take<float>((size_t)B * L.ntiles);
     L.dq_rows = nullptr;
+    if (!tc) {
+      L.nparts = L.ntiles;
+      L.qn = cv.take<float>(rows);
+      L.kn = cv.take<float>(rows);
+    } else {
+      L.Cp = (a.C + 31) / 32 * 32;
+      L.Ppad = (a.P + 127) / 128 * 128;
+      L.nchunk = L.Cp / 32;
+      L.nparts = L.Ppad / 128;
+      const size_t blob = (size_t)B * L.Ppad * L.Cp;
+      L.qhi = cv.take<__nv_bfloat16>(blob);
+      L.khi = cv.take<__nv_bfloat16>(blob);
+      if (x3) {
+        L.qlo = cv.take<__nv_bfloat16>(blob);
+        L.klo = cv.take<__nv_bfloat16>(blob);
+      }
+      L.qT = cv.take<float>((size_t)B * a.C * L.Ppad);
+      L.qss = cv.take<float>((size_t)B * L.nchunk * L.Ppad);
+      L.kss = cv.take<float>((size_t)B * L.nchunk * L.Ppad);
+    }
+    L.partial = cv.take<float>((size_t)B * (L.ntiles > 2 ? L.ntiles : 2));
   }
   if (out) *out = p;
   return align_up(cv.off, 256);
@@ -160,6 +188,43 @@ static int launch_loss_simt(const Params& p, cudaStream_t st) {
   return PNCE_OK;
 }
 
+static int launch_gather_tc(const Params& p, cudaStream_t st) {
+  BlockMap m;
+  memset(&m, 0, sizeof(m));
+  long long acc = 0;
+  size_t smem = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    m.start[l] = acc;
+    acc += 2ll * p.B * p.L[l].nchunk;
+    int n2 = 1;
+    while (n2 < p.L[l].P) n2 <<= 1;
+    const size_t s = (size_t)n2 * 8 + 64;
+    if (s > smem) smem = s;
+  }
+  m.start[p.n_layers] = acc;
+  if (acc + p.n_layers > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+  k_gather_tc<<<(unsigned)(acc + p.n_layers), kThreads, smem, st>>>(p, m);
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+
+static int launch_loss_tc(const Params& p, cudaStream_t st) {
+  BlockMap m;
+  memset(&m, 0, sizeof(m));
+  long long acc = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    m.start[l] = acc;
+    acc += (long long)p.B * (p.L[l].Ppad / 128);
+  }
+  m.start[p.n_layers] = acc;
+  int rc = set_smem(k_loss_tc, kTcSmemBytes);
+  if (rc != PNCE_OK) return rc;
+  if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+  k_loss_tc<<<(unsigned)acc, kTcThreads, kTcSmemBytes, st>>>(p, m);
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+
 static int launch_dense(const Params& p, cudaStream_t st) {
   DenseMap m;
   memset(&m, 0, sizeof(m));
@@ -168,15 +233,15 @@ static int launch_dense(const Params& p, cudaStream_t st) {
   for (int l = 0; l < p.n_layers; ++l) {
     const LayerDev& L = p.L[l];
     m.start[l] = acc;
-    const int per_item = kDenseIters * kThreads * vec;
-    m.tiles[l] = (L.HW + per_item - 1) / per_item;
+    m.segs[l] = (L.HW + kSegPos - 1) / kSegPos;
     m.vec_ok[l] = (L.HW % vec == 0) && ((reinterpret_cast<uintptr_t>(L.dtgt) & 15u) == 0);
-    acc += (long long)p.B * L.C * m.tiles[l];
+    acc += (long long)p.B * L.C * m.segs[l];
   }
   m.start[p.n_layers] = acc;
   m.total = acc;
-  long long grid = (long long)sm_count() * 8;
-  if (grid > acc) grid = acc;
+  const long long ctas_needed = (acc + (kThreads / 32) - 1) / (kThreads / 32);
+  long long grid = (long long)sm_count() * 8;            // 8 x 256-thread CTAs per SM, persistent
+  if (grid > ctas_needed) grid = ctas_needed;
   k_dense_bwd<<<(unsigned)grid, kThreads, 0, st>>>(p, m);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
@@ -225,7 +290,12 @@ int pnce_workspace_bytes(const pnce_layer_t* layers, int n_layers, int batch, si
   if (bytes == nullptr) return PNCE_ERR_ARG;
   int rc = check_layers(layers, n_layers, batch);
   if (rc != PNCE_OK) return rc;
-  *bytes = carve_fused(layers, n_layers, batch, nullptr, nullptr);
+  size_t need = carve_fused(layers, n_layers, batch, false, false, nullptr, nullptr);
+  if (tc_shapes_ok(layers, n_layers)) {
+    const size_t t = carve_fused(layers, n_layers, batch, true, true, nullptr, nullptr);
+    if (t > need) need = t;
+  }
+  *bytes = need;
   return PNCE_OK;
 }
 
@@ -234,33 +304,45 @@ int pnce_fwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, flo
   int rc = check_layers(layers, n_layers, batch);
   if (rc != PNCE_OK) return rc;
   if (dtype < PNCE_F32 || dtype > PNCE_BF16 || loss_out == nullptr || !(temperature > 0.f)) return PNCE_ERR_ARG;
-  if (math_mode != PNCE_MATH_SIMT_F32) return PNCE_ERR_UNSUPPORTED;
+  if (math_mode < PNCE_MATH_SIMT_F32 || math_mode > PNCE_MATH_TC_BF16) return PNCE_ERR_ARG;
   rc = check_alignment(layers, n_layers, dtype, false);
   if (rc != PNCE_OK) return rc;
   if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
+  // the tcgen05 kernel covers P <= 256, C <= 256 (every 256^2 CUT layer); other shapes take the
+  // fp32 CUDA-core kernel -- both are device paths of this library, neither is a fallback off the GPU
+  const bool tc = math_mode != PNCE_MATH_SIMT_F32 && tc_shapes_ok(layers, n_layers);
+  const bool x3 = math_mode == PNCE_MATH_TC_BF16X3;
   Params p;
-  if (carve_fused(layers, n_layers, batch, ws, &p) > ws_bytes) return PNCE_ERR_WORKSPACE;
+  if (carve_fused(layers, n_layers, batch, tc, x3, ws, &p) > ws_bytes) return PNCE_ERR_WORKSPACE;
   p.dtype = dtype;
-  p.math = math_mode;
+  p.math = tc ? math_mode : PNCE_MATH_SIMT_F32;
   p.tau = temperature;
   p.loss_out = loss_out;
   p.nonfinite = nonfinite;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tc) {
+    rc = launch_gather_tc(p, st);
+    if (rc != PNCE_OK) return rc;
+    return launch_loss_tc(p, st);
+  }
   rc = launch_gather(p, n_layers, st);
   if (rc != PNCE_OK) return rc;
   return launch_loss_simt(p, st);
 }
 
-int pnce_bwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, void* ws, size_t ws_bytes,
-             const float* grad_out, void* stream) {
+int pnce_bwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int math_mode, void* ws,
+             size_t ws_bytes, const float* grad_out, void* stream) {
   int rc = check_layers(layers, n_layers, batch);
   if (rc != PNCE_OK) return rc;
   if (dtype < PNCE_F32 || dtype > PNCE_BF16) return PNCE_ERR_ARG;
   rc = check_alignment(layers, n_layers, dtype, true);
   if (rc != PNCE_OK) return rc;
   if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
+  if (math_mode < PNCE_MATH_SIMT_F32 || math_mode > PNCE_MATH_TC_BF16) return PNCE_ERR_ARG;
+  const bool tc = math_mode != PNCE_MATH_SIMT_F32 && tc_shapes_ok(layers, n_layers);
   Params p;
-  if (carve_fused(layers, n_layers, batch, ws, &p) > ws_bytes) return PNCE_ERR_WORKSPACE;
+  if (carve_fused(layers, n_layers, batch, tc, math_mode == PNCE_MATH_TC_BF16X3, ws, &p) > ws_bytes)
+    return PNCE_ERR_WORKSPACE;
   p.dtype = dtype;
   p.grad_out = grad_out;
   return launch_dense(p, static_cast<cudaStream_t>(stream));
@@ -375,6 +457,7 @@ static size_t carve_rows_loss(int B, int P, int D, void* ws, Params* out) {
   LayerDev& L = p.L[0];
   L.C = D; L.P = P; L.HW = 1; L.nwords = 1;
   L.ntiles = (P + kRowTile - 1) / kRowTile;
+  L.nparts = L.ntiles;
   L.partial = cv.take<float>((size_t)B * L.ntiles);
   if (out) *out = p;
   return align_up(cv.off, 256);
@@ -407,6 +490,25 @@ int pnce_rows_loss_fwd_bwd(const float* q, const float* k, int batch, int P, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PNCE_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned), st));
   return launch_loss_simt(p, st);
+}
+
+int pnce_selftest_umma(const void* a_blob, size_t a_bytes, const void* b_blob, size_t b_bytes,
+                       unsigned a_lbo, unsigned a_sbo, unsigned a_kstep, unsigned b_lbo, unsigned b_sbo,
+                       unsigned b_kstep, int n, int k, int b_mn_major, float* d_out, int* err, void* stream) {
+  if (!a_blob || !b_blob || !d_out || !err) return PNCE_ERR_ARG;
+  if (n < 16 || n > 256 || (n % 32) || k < 16 || (k % 16) || (a_bytes % 16) || (b_bytes % 16)) return PNCE_ERR_ARG;
+  ProbeArgs a;
+  a.a_blob = a_blob; a.b_blob = b_blob; a.d_out = d_out; a.err = err;
+  a.a_bytes = (uint32_t)a_bytes; a.b_bytes = (uint32_t)b_bytes;
+  a.a_lbo = a_lbo; a.a_sbo = a_sbo; a.a_kstep = a_kstep;
+  a.b_lbo = b_lbo; a.b_sbo = b_sbo; a.b_kstep = b_kstep;
+  a.n = n; a.k = k; a.b_mn_major = b_mn_major;
+  const size_t smem = ((a_bytes + 1023) & ~(size_t)1023) + b_bytes;
+  int rc = set_smem(k_umma_probe, smem);
+  if (rc != PNCE_OK) return rc;
+  k_umma_probe<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
 }
 
 }  // extern "C"

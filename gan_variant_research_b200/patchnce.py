@@ -70,7 +70,7 @@ class _WarnQueue:
     def push(self, dev_flag: torch.Tensor):
         if torch.cuda.is_current_stream_capturing():
             return
-        host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+        host = torch.empty(dev_flag.numel(), dtype=torch.int32, pin_memory=True)
         host.copy_(dev_flag, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev_flag.device))
@@ -83,7 +83,9 @@ class _WarnQueue:
             if block:
                 ev.synchronize()
             if ev.query():
-                n = int(host.item())
+                n = int(host[0].item())
+                if host.numel() > 1 and int(host[1].item()):
+                    raise _lib.PnceError("libpnce kernel protocol timeout (tcgen05 pipeline stalled)")
                 if n:
                     print(f"Warning: NaN in PatchNCE loss. {n} (layer, image) loss(es) replaced by 0.")
                 total += n
@@ -142,7 +144,7 @@ class _FusedPatchNCE(torch.autograd.Function):
         with torch.cuda.device(dev):
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
             out = torch.empty(1 + n, dtype=torch.float32, device=dev)
-            flag = torch.empty(1, dtype=torch.int32, device=dev)
+            flag = torch.zeros(2, dtype=torch.int32, device=dev)
             _lib.check(lib.pnce_fwd(layers, n, batch, dtype, plan.temperature, _MATH[plan.math],
                                     ws.data_ptr(), nbytes.value, out.data_ptr(), flag.data_ptr(),
                                     _stream_ptr(dev)), "pnce_fwd")
@@ -163,8 +165,9 @@ class _FusedPatchNCE(torch.autograd.Function):
         with torch.cuda.device(dev):
             grads = [torch.empty(shape, dtype=dt, device=dev) for shape, dt in ctx.tgt_meta]
             layers = _layer_array(ctx.plan.src_feats, ctx.tgt_keep, grads, ctx.plan.ids_list)
-            _lib.check(lib.pnce_bwd(layers, len(grads), ctx.batch, ctx.dtype, ctx.ws.data_ptr(),
-                                    ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev)), "pnce_bwd")
+            _lib.check(lib.pnce_bwd(layers, len(grads), ctx.batch, ctx.dtype, _MATH[ctx.plan.math],
+                                    ctx.ws.data_ptr(), ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev)),
+                       "pnce_bwd")
         return (None, *grads)
 
 

@@ -72,17 +72,19 @@ int pnce_workspace_bytes(const pnce_layer_t* layers, int n_layers, int batch, si
  * and, fused, the backward of all of that up to the per-patch gradient rows (unit upstream
  * gradient), kept in the workspace for pnce_bwd.  Logits never reach HBM.
  *   dev_loss_out : float[1 + n_layers]  -> [0] total loss, [1+l] layer losses
- *   dev_nonfinite: int[1]               -> number of (layer,image) pairs whose loss was replaced
- *                                          by 0 (the reference prints a warning for each, :98)   */
+ *   dev_nonfinite: int[2]               -> [0] number of (layer,image) pairs whose loss was replaced
+ *                                          by 0 (the reference prints a warning for each, :98);
+ *                                          [1] internal kernel-protocol timeout flag (must read 0) */
 int pnce_fwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, float temperature,
              int math_mode, void* dev_workspace, size_t workspace_bytes, float* dev_loss_out,
              int* dev_nonfinite, void* stream);
 
 /* Backward: writes every layers[l].dtgt densely (zero off the sampled positions, duplicate ids
- * accumulated) scaled by the upstream gradient *dev_grad_out (NULL = 1.0).  Replaces the autograd
+ * accumulated) scaled by the upstream gradient *dev_grad_out (NULL = 1.0).  `math_mode` and the
+ * workspace must be the ones given to the matching pnce_fwd.  Replaces the autograd
  * chain of SURVEY.md section 8 row a11 (index_put_ / select_backward / zeros + adds).           */
-int pnce_bwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, void* dev_workspace,
-             size_t workspace_bytes, const float* dev_grad_out, void* stream);
+int pnce_bwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int math_mode,
+             void* dev_workspace, size_t workspace_bytes, const float* dev_grad_out, void* stream);
 
 /* ---- north-star module split ------------------------------ */
 
@@ -107,6 +109,14 @@ int pnce_rows_loss_fwd_bwd(const float* dev_q, const float* dev_k, int batch, in
                            float temperature, int math_mode, void* dev_workspace,
                            size_t workspace_bytes, float* dev_loss_out, int* dev_nonfinite,
                            float* dev_dq_out, float* dev_dk_out, void* stream);
+
+/* Library self-test of the tcgen05 building blocks (bulk copy -> smem, tcgen05.mma with a K-major
+ * or MN-major B operand, commit, tcgen05.ld): D(128 x n) = A(128 x k) * B on pre-tiled bf16 operand
+ * blobs with host-supplied descriptor strides.  *dev_err is set to 1 on a protocol timeout.       */
+int pnce_selftest_umma(const void* dev_a_blob, size_t a_bytes, const void* dev_b_blob, size_t b_bytes,
+                       unsigned a_lbo, unsigned a_sbo, unsigned a_kstep, unsigned b_lbo, unsigned b_sbo,
+                       unsigned b_kstep, int n, int k, int b_mn_major, float* dev_d_out, int* dev_err,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -49,7 +49,8 @@ def test_workspace_query_and_argument_errors(lib):
     b5 = [(64, 256, 256), (256, 64, 64), (256, 64, 64), (128, 128, 128), (64, 256, 256)]
     assert lib.pnce_workspace_bytes(_layers(b5, 256), 5, 64, ctypes.byref(n)) == 0
     rows = 64 * 256 * (64 + 256 + 256 + 128 + 64) * 4
-    assert 3 * rows <= n.value <= 3 * rows + (1 << 20)
+    # dxT + (SIMT: 2 fp32 row sets | tensor-core: 4 bf16 operand blobs + raw fp32 q)
+    assert 3 * rows <= n.value <= 4 * rows + (4 << 20)
     assert lib.pnce_workspace_bytes(_layers(b5, 256), 5, 0, ctypes.byref(n)) == -1       # batch < 1
     assert lib.pnce_workspace_bytes(_layers(b5, 256), 9, 1, ctypes.byref(n)) == -2       # > 8 layers
     assert lib.pnce_workspace_bytes(_layers([(2048, 4, 4)], 16), 1, 1, ctypes.byref(n)) == -2
@@ -65,7 +66,7 @@ def test_compute_entry_points_reject_bad_arguments_without_touching_cuda(lib):
     # NULL workspace / loss pointers are rejected before any launch
     assert lib.pnce_fwd(lay, 1, 1, 0, 0.07, 0, None, 0, None, None, None) == -1
     assert lib.pnce_fwd(lay, 1, 1, 7, 0.07, 0, None, 0, None, None, None) == -1          # bad dtype
-    assert lib.pnce_bwd(lay, 1, 1, 0, None, 0, None, None) == -1                         # dtgt NULL
+    assert lib.pnce_bwd(lay, 1, 1, 0, 0, None, 0, None, None) == -1                         # dtgt NULL
 
 
 def test_no_cpu_fallback():

@@ -38,8 +38,11 @@ def dev(x, dtype=None):
     return t if dtype is None else t.to(dtype)
 
 
-def assert_grad_close(got, want, rtol, what=""):
-    """max-abs error relative to the largest reference entry; NaN patterns must coincide."""
+def assert_grad_close(got, want, rtol, what="", ids=None):
+    """max-abs error relative to the largest reference entry; NaN patterns must coincide.
+    With ``ids`` the dense gradient must be EXACTLY zero off the sampled positions (at a sampled
+    position an analytically-zero entry may differ from 0.0 by rounding, e.g. a one-hot post-ReLU
+    row, so closeness is the test there)."""
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
     assert got.shape == want.shape
@@ -48,8 +51,12 @@ def assert_grad_close(got, want, rtol, what=""):
     scale = max(float(np.abs(want[m]).max()) if m.any() else 0.0, 1e-30)
     err = float(np.abs(got[m] - want[m]).max()) / scale if m.any() else 0.0
     assert err <= rtol, f"{what}: rel err {err:.3e} > {rtol}"
-    # exact zeros stay exact zeros (dense gradient is zero off the sampled positions)
-    np.testing.assert_array_equal(got[m] != 0, want[m] != 0, err_msg=f"{what}: sparsity pattern")
+    if ids is not None:
+        b, c = got.shape[:2]
+        flat = got.reshape(b, c, -1)
+        off = np.ones(flat.shape[2], dtype=bool)
+        off[np.asarray(ids)] = False
+        assert not np.any(flat[:, :, off] != 0), f"{what}: non-zero gradient off the sampled positions"
 
 
 def load_small(path):
@@ -59,16 +66,25 @@ def load_small(path):
             [d[f"ids{i}"] for i in range(n)], [d[f"grad{i}"] for i in range(n)])
 
 
+# (loss rtol, grad rtol) per contraction engine; north_star asks 1e-3 in fp32-accumulate mode
+MATH_TOL = {"simt_f32": (2e-5, 1e-4), "tc_bf16x3": (2e-5, 2e-4), "tc_bf16": (2e-3, 3e-2)}
+
+
+@pytest.mark.parametrize("math", list(MATH_TOL))
 @pytest.mark.parametrize("path", SMALL, ids=[os.path.basename(p)[6:-4] for p in SMALL])
-def test_fused_matches_reference_goldens(pn, path):
+def test_fused_matches_reference_goldens(pn, path, math):
     d, src, tgt, ids, grads = load_small(path)
     t = [dev(x).requires_grad_() for x in tgt]
-    loss = pn.fused_patchnce([dev(x) for x in src], t, [dev(i) for i in ids], float(d["tau"]))
+    loss = pn.fused_patchnce([dev(x) for x in src], t, [dev(i) for i in ids], float(d["tau"]), math=math)
     (loss * float(d["upstream"])).backward()
     assert loss.dtype == torch.float32 and loss.dim() == 0 and loss.is_cuda
-    assert loss.item() == pytest.approx(float(d["loss"]), rel=2e-5, abs=1e-6)
+    ltol, gtol = MATH_TOL[math]
+    if math == "tc_bf16" and float(d["tau"]) < 0.05:
+        ltol, gtol = 2e-2, 2e-1            # 1/tau = 100 amplifies the single-pass bf16 rounding
+    assert loss.item() == pytest.approx(float(d["loss"]), rel=ltol, abs=1e-6)
     for i, (tt, g) in enumerate(zip(t, grads)):
-        assert_grad_close(tt.grad.cpu().numpy(), g, 1e-4, f"layer {i}")
+        assert_grad_close(tt.grad.cpu().numpy(), g, gtol, f"layer {i}", ids=ids[i])
+    assert pn.poll_nonfinite_warnings(block=True) >= 0      # raises on a kernel protocol timeout
 
 
 def test_nonfinite_images_are_counted_and_reported(pn, capsys):
@@ -105,8 +121,9 @@ def test_patch_ids_bit_exact_and_rng_stream_aligned(pn, orc):
         assert torch.equal(g, w)
 
 
+@pytest.mark.parametrize("math", ["simt_f32", "tc_bf16x3"])
 @pytest.mark.parametrize("b", [1, 2])
-def test_survey_tripwire_full_size(pn, b):
+def test_survey_tripwire_full_size(pn, b, math):
     """full-size R4 maps, the reference's own CPU-drawn ids."""
     d = np.load(os.path.join(HERE, "golden", f"survey_r4_b{b}.npz"))
     g = torch.Generator().manual_seed(1234)
@@ -114,7 +131,7 @@ def test_survey_tripwire_full_size(pn, b):
     tgt = [torch.randn(b, *s, generator=g).relu() for s in R4]
     ids = [dev(d[f"ids{i}"]) for i in range(4)]
     t = [x.cuda().requires_grad_() for x in tgt]
-    loss = pn.fused_patchnce([x.cuda() for x in src], t, ids, 0.07)
+    loss = pn.fused_patchnce([x.cuda() for x in src], t, ids, 0.07, math=math)
     loss.backward()
     assert loss.item() == pytest.approx(float(d["loss"]), rel=2e-5)
     for i, tt in enumerate(t):
@@ -164,7 +181,7 @@ def test_layer_mean_divides_by_number_of_maps(pn, orc):
     assert loss.item() == pytest.approx(want.item(), rel=1e-4)
     assert_grad_close(g_got.cpu().numpy(), y_cpu.grad.numpy(), 2e-3, "d loss / d tgt image")
     # params of the generator received gradient only through the tgt pass
-    assert all(p.grad is not None for p in gen.parameters())
+    assert all(p.grad is not None for c in list(gen.convs)[:13] for p in c.parameters())
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
@@ -187,7 +204,7 @@ def test_half_precision_feature_maps(pn, orc, dtype):
         got = tt.grad.float().cpu().numpy()
         scale = np.abs(gg).max()
         assert np.abs(got - gg).max() / scale < (2e-3 if dtype == torch.float16 else 1e-2)
-        np.testing.assert_array_equal(got != 0, gg != 0)
+        np.testing.assert_array_equal(got[gg == 0], 0)
 
 
 def test_patch_sample_f_rows_and_backward(pn, orc):
@@ -229,7 +246,7 @@ def test_module_split_composes_to_the_reference(pn):
     loss.backward()
     assert loss.item() == pytest.approx(float(d["loss"]), rel=2e-5)
     for i, (tt, g) in enumerate(zip(t, grads)):
-        assert_grad_close(tt.grad.cpu().numpy(), g, 1e-4, f"layer {i}")
+        assert_grad_close(tt.grad.cpu().numpy(), g, 1e-4, f"layer {i}", ids=ids[i])
 
 
 def test_rows_loss_matches_torch(pn):
