@@ -11,6 +11,7 @@ namespace pnce {
 
 constexpr int kThreads = 256;          // every kernel in this library uses 256-thread CTAs
 constexpr int kRowTile = 32;           // patches per gather / SIMT-loss CTA
+constexpr int kTilePos = 2048;         // positions per tile of the dense backward (8 KB of fp32)
 constexpr float kNormEps = 1e-6f;      // F.normalize eps               patchnce_cut.py:77-78
 constexpr float kClamp = 50.0f;        // torch.clamp(logits, -50, 50)  patchnce_cut.py:88
 
@@ -22,7 +23,7 @@ struct LayerDev {
   const long long* ids;
   int C, HW, P, nwords;      // nwords = ceil(HW / 32) bitmap words
   int ntiles;                // ceil(P / 32)
-  int pad_;
+  int sorted;                // 1: rows / qinv are in sorted-slot order (tensor-core path), 0: ids order
   // id bookkeeping (written by the prep CTA of the gather launch)
   int* sid;                  // [P]   ids sorted ascending
   int* perm;                 // [P]   original index of sorted slot j
@@ -30,6 +31,7 @@ struct LayerDev {
   int* ustart;               // [P+1] start of each run of equal ids in sorted order; [U] = P
   unsigned* bitmap;          // [nwords] bit h set <=> position h sampled
   unsigned* prefix;          // [nwords] number of set bits before word w
+  int* cslot;                // [ceil(HW/kTilePos)+1] first sorted slot whose id >= t * kTilePos
   // rows
   float* qn;                 // [B][P][C] normalised target rows (ids order)
   float* kn;                 // [B][P][C] normalised source rows
@@ -60,6 +62,7 @@ struct Params {
   float* lossimg;            // [n_layers][B]
   int* valid;                // [n_layers][B]
   const float* grad_out;     // device scalar or NULL (=1)
+  long long* trace;          // debug: clock64 stamps of two CTAs of the tcgen05 loss kernel, or NULL
 };
 
 // CTA -> layer map for one launch: blocks [start[l], start[l+1]) work on layer l.

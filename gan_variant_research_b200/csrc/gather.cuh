@@ -98,6 +98,19 @@ __device__ void prep_layer(const LayerDev& L, unsigned long long* keys, int* scr
     atomicOr(&L.bitmap[id >> 5], 1u << (id & 31));
   }
   __syncthreads();
+  // tile -> first sorted slot (the dense backward's per-tile slot range)
+  if (L.cslot != nullptr) {
+    const int ntile = (L.HW + kTilePos - 1) / kTilePos;
+    for (int t = tid; t <= ntile; t += kThreads) {
+      const int pos = t * kTilePos;
+      int lo = 0, hi = P;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)(keys[mid] >> 32) < pos) lo = mid + 1; else hi = mid;
+      }
+      L.cslot[t] = lo;
+    }
+  }
   // exclusive popcount prefix over the bitmap words
   running = 0;
   for (int base = 0; base < L.nwords; base += kThreads) {

@@ -1,5 +1,6 @@
-// Tensor-core path, launch 1: random-patch gather that writes the MMA operands directly.
-//   CTA  <-> (layer, side, image, chunk of 32 channels);  thread <-> patch p  (P <= 256)
+// Tensor-core path, launch 2 (after k_prep): random-patch gather that writes the MMA operands directly.
+//   CTA  <-> (layer, side, image, chunk of 32 channels);  thread <-> sorted slot p  (P <= 256):
+//   row p of every operand is the patch with the p-th smallest id (k_prep's sid[]), see loss_tc.cuh
 //   every thread issues 32 independent L2-only loads (one sector each: element (c, id) of an NCHW
 //   plane), splits each value into bf16 hi + lo, and stores 8 consecutive channels as one 16-byte
 //   row of an 8x8 core matrix.  The global operand blobs are laid out exactly as the shared-memory
@@ -32,8 +33,7 @@ __device__ void gather_tc_chunk(const LayerDev& L, int B, long long local) {
   const int C = L.C, HW = L.HW, P = L.P, Ppad = L.Ppad, Cp8 = L.Cp >> 3;
   if (p >= Ppad) return;
   const bool valid = p < P;
-  long long id = valid ? L.ids[p] : 0;
-  id = id < 0 ? 0 : (id >= HW ? HW - 1 : id);
+  const int id = valid ? __ldg(L.sid + p) : 0;                // already clamped to [0, HW) by k_prep
   const T* col = reinterpret_cast<const T*>(side ? L.tgt : L.src) + (size_t)b * C * HW + id;
   float v[32];
 #pragma unroll
@@ -81,29 +81,30 @@ __device__ void gather_tc_chunk(const LayerDev& L, int B, long long local) {
   }
 }
 
-// grid = sum_l 2*B*nchunk_l gather CTAs, then n_layers prep CTAs (same prep as the SIMT path).
+// grid = sum_l 2*B*nchunk_l
 __global__ void __launch_bounds__(kThreads) k_gather_tc(const __grid_constant__ Params p,
                                                         const __grid_constant__ BlockMap m) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   const long long blk = blockIdx.x;
-  const long long n_gather = m.start[p.n_layers];
-  if (blk >= n_gather) {
-    const int l = (int)(blk - n_gather);
-    if (l == 0 && threadIdx.x == 0 && p.counter != nullptr) {
-      *p.counter = 0u;
-      if (p.nonfinite != nullptr) p.nonfinite[1] = 0;
-    }
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
-    int N2 = 1;
-    while (N2 < p.L[l].P) N2 <<= 1;
-    prep_layer(p.L[l], keys, reinterpret_cast<int*>(keys + N2));
-    return;
-  }
   const int l = find_layer(m, blk, p.n_layers);
   const long long local = blk - m.start[l];
   if (p.dtype == PNCE_F32) gather_tc_chunk<float>(p.L[l], p.B, local);
   else if (p.dtype == PNCE_F16) gather_tc_chunk<__half>(p.L[l], p.B, local);
   else gather_tc_chunk<__nv_bfloat16>(p.L[l], p.B, local);
+}
+
+// One CTA per layer: ids -> (sid, perm, rank, ustart, bitmap, prefix); CTA 0 also resets the
+// last-CTA counter and the protocol flag of the launch sequence.
+__global__ void __launch_bounds__(kThreads) k_prep(const __grid_constant__ Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int l = blockIdx.x;
+  if (l == 0 && threadIdx.x == 0 && p.counter != nullptr) {
+    *p.counter = 0u;
+    if (p.nonfinite != nullptr) p.nonfinite[1] = 0;
+  }
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  int N2 = 1;
+  while (N2 < p.L[l].P) N2 <<= 1;
+  prep_layer(p.L[l], keys, reinterpret_cast<int*>(keys + N2));
 }
 
 }  // namespace pnce

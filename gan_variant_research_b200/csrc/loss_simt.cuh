@@ -67,7 +67,7 @@ __device__ void finalize_losses(const Params& p) {
           int c = (int)(i / L.P), pp = (int)(i % L.P);
           float inv = L.qinv[(size_t)b * L.P + pp];
           float v = (!layer_bad[l] && !(inv == inv)) ? __int_as_float(0x7fc00000) : 0.f;
-          L.dxT[((size_t)b * L.C + c) * L.P + L.rank[pp]] = v;
+          L.dxT[((size_t)b * L.C + c) * L.P + (L.sorted ? pp : L.rank[pp])] = v;
         }
       }
     }

@@ -1,19 +1,23 @@
-// Tensor-core path, launch 2: fused logits + diagonal CE forward/backward on tcgen05.
+// Tensor-core path, launch 3: fused logits + diagonal CE forward/backward on tcgen05.
 // One CTA per (layer, image, 128-row half of the P x P logits); 192 threads, warp-specialised:
 //   warp 0      bulk-copy producer (TMA engine, 1-D, operand blobs are pre-tiled by k_gather_tc)
 //   warp 1      TMEM owner + the single MMA-issuing thread
 //   warps 2..5  epilogue: one thread per logits row (TMEM lane), tcgen05.ld -> registers
+// Rows are in SORTED-ID order (k_gather_tc gathers slot i = i-th smallest id): the loss is invariant
+// under a common permutation of q and k rows, and the gradient rows then leave as coalesced stores
+// in exactly the order the dense backward reads them.
 //
 //   phase 1   Z(128 x N) = Q_half K^T           kind::f16 bf16, fp32 accumulate in TMEM cols [0,N)
 //             streamed over C in chunks of 32 channels through a 2-slot smem ring.
 //             bf16x3 mode issues hi*hi + hi*lo + lo*hi into the same accumulator (~2^-17 operand error).
-//   epilogue  z_ij = acc * (1/||q_i||)(1/||k_j||)/tau, clamp +-50, row sum of exp, diagonal pick,
-//             row loss (warp-shuffle reduced), dZ = (softmax - I) * mask / (P B L),
+//   epilogue  y_ij = acc * (log2e/tau)(1/||q_i||)(1/||k_j||)   (logits in log2 units), clamp, row sum of
+//             exp2, diagonal pick, row loss (warp-shuffle reduced), dZ = (softmax - I) * mask / (P B L),
 //             s_i = sum_j dZ_ij z_ij (= q_hat . dq, no second reduction needed),
 //             dZ_ij / ||k_j|| split hi/lo -> shared memory as the next MMA's A operand.
+//             The element loops are branch-free (32 independent columns per tcgen05.ld).
 //   phase 2   dQ(128 x C) = dZ K               K re-streamed in the same chunks and read MN-major from
 //             the very same shared-memory image; accumulate in TMEM cols [256, 256+C)
-//   epilogue  dq/tau, normalise backward, dxT[b][c][rank[p]] (unit upstream gradient).
+//   epilogue  dq/tau, normalise backward, dxT[b][c][slot] (unit upstream gradient), coalesced.
 // The logits, softmax and dZ never leave the SM.  Replaces patchnce_cut.py:83-110 and the autograd
 // backward of :77-94.  Shapes: P <= 256, C <= 256.
 #pragma once
@@ -28,14 +32,137 @@ constexpr int kTcStageBytes = 49152;        // Qhi 8K | Qlo 8K | Khi 16K | Klo 1
 constexpr int kTcOffQlo = 8192, kTcOffKhi = 16384, kTcOffKlo = 32768;
 constexpr int kTcDzBytes = 65536;           // 128 x 256 bf16
 constexpr int kTcSmemBytes = 2 * kTcStageBytes + 2 * kTcDzBytes + 1024 /*invk*/ + 256 /*barriers, misc*/;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
 
 struct TcShared {
   uint64_t full[2], empty[2], zfull, dzready, dqfull;
   uint32_t tmem_base;
   int dead;
   int flag;
+  int badk;                                  // some key row of this image is non-finite
   float red[4];
 };
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t bf16x2_bits(float lo_elem, float hi_elem) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);   // .x = first (low 16 bits)
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// ---- pass A over one 32-column chunk: sum of exp2 of the (clamped) logits, 4 partial sums -------
+// CLAMP: the +-50 clamp can bind (1/tau > 50).  Padding columns carry w = 0 -> y = 0 -> exp2 = 1
+// exactly; the caller subtracts their count.
+template <bool CLAMP>
+__device__ __forceinline__ void tc_pass_a(const uint32_t (&r)[32], const float* __restrict__ wk, float a,
+                                          float cl, float (&se)[4]) {
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 w = *reinterpret_cast<const float4*>(wk + k4 * 4);
+    const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float y = __uint_as_float(r[k4 * 4 + t]) * a * ww[t];
+      if (CLAMP) y = fminf(fmaxf(y, -cl), cl);
+      se[t] += ex2f(y);
+    }
+  }
+}
+
+// ---- pass B over one 32-column chunk: softmax * coef / ||k_j|| -> bf16 hi (+lo) A-operand rows,
+//      s2 += dZ * y.  The "- I" of the diagonal is patched in afterwards by the owning thread.
+//      Padding columns: w = 0 -> the stored operand and the s2 term are exactly 0.
+template <bool CLAMP>
+__device__ __forceinline__ void tc_pass_b(const uint32_t (&r)[32], const float* __restrict__ wk, float a,
+                                          float cl, float lse2, float coef, bool x3, unsigned char* dzhi,
+                                          unsigned char* dzlo, uint32_t off0, float& s2) {
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8) {
+    float dd[8];
+#pragma unroll
+    for (int h4 = 0; h4 < 2; ++h4) {
+      const float4 w = *reinterpret_cast<const float4*>(wk + g8 * 8 + h4 * 4);
+      const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float y = __uint_as_float(r[g8 * 8 + h4 * 4 + t]) * a * ww[t];
+        const float yc = CLAMP ? fminf(fmaxf(y, -cl), cl) : y;
+        float d = ex2f(yc - lse2) * coef;
+        if (CLAMP) d = (fabsf(y) <= cl) ? d : 0.f;             // clamp backward mask (inclusive)
+        s2 = fmaf(d, y, s2);
+        dd[h4 * 4 + t] = d * ww[t];
+      }
+    }
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+      hw[k2] = bf16x2_bits(dd[2 * k2], dd[2 * k2 + 1]);
+      const float r0 = dd[2 * k2] - __uint_as_float(hw[k2] << 16);
+      const float r1 = dd[2 * k2 + 1] - __uint_as_float(hw[k2] & 0xffff0000u);
+      lw[k2] = bf16x2_bits(r0, r1);
+    }
+    const uint32_t off = off0 + (uint32_t)g8 * 2048u;          // next 8-column slab of the A operand
+    *reinterpret_cast<uint4*>(dzhi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    if (x3) *reinterpret_cast<uint4*>(dzlo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
+// Both passes walk the row in 32-column chunks with two STATIC register buffers so that the
+// tcgen05.ld of chunk ch+1 is in flight while chunk ch is processed.
+template <bool CLAMP>
+__device__ __forceinline__ void tc_row_pass_a(uint32_t trow, int nch, const float* __restrict__ invk_s, float a,
+                                              float cl, int chd, int lane, float (&se)[4], float& ydraw) {
+  using namespace umma;
+  uint32_t r0[32], r1[32];
+  tmem_ld32(trow, r0);
+  for (int ch = 0; ch < nch; ch += 2) {
+    tmem_ld_wait();
+    if (ch + 1 < nch) tmem_ld32(trow + (ch + 1) * 32, r1);
+    tc_pass_a<CLAMP>(r0, invk_s + ch * 32, a, cl, se);
+    if (ch == chd) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) ydraw = (k == lane) ? __uint_as_float(r0[k]) : ydraw;
+    }
+    if (ch + 1 < nch) {
+      tmem_ld_wait();
+      if (ch + 2 < nch) tmem_ld32(trow + (ch + 2) * 32, r0);
+      tc_pass_a<CLAMP>(r1, invk_s + (ch + 1) * 32, a, cl, se);
+      if (ch + 1 == chd) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) ydraw = (k == lane) ? __uint_as_float(r1[k]) : ydraw;
+      }
+    }
+  }
+}
+
+template <bool CLAMP>
+__device__ __forceinline__ void tc_row_pass_b(uint32_t trow, int nch, const float* __restrict__ invk_s, float a,
+                                              float cl, float lse2, float coef, bool x3, unsigned char* dzhi,
+                                              unsigned char* dzlo, uint32_t rowoff, float& s2) {
+  using namespace umma;
+  uint32_t r0[32], r1[32];
+  tmem_ld32(trow, r0);
+  for (int ch = 0; ch < nch; ch += 2) {
+    tmem_ld_wait();
+    if (ch + 1 < nch) tmem_ld32(trow + (ch + 1) * 32, r1);
+    tc_pass_b<CLAMP>(r0, invk_s + ch * 32, a, cl, lse2, coef, x3, dzhi, dzlo, (uint32_t)(ch * 4) * 2048u + rowoff, s2);
+    if (ch + 1 < nch) {
+      tmem_ld_wait();
+      if (ch + 2 < nch) tmem_ld32(trow + (ch + 2) * 32, r0);
+      tc_pass_b<CLAMP>(r1, invk_s + (ch + 1) * 32, a, cl, lse2, coef, x3, dzhi, dzlo,
+                       (uint32_t)((ch + 1) * 4) * 2048u + rowoff, s2);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant__ Params p,
                                                            const __grid_constant__ BlockMap m) {
@@ -56,12 +183,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
   const int N = L.Ppad, P = L.P, C = L.C, Cp8 = L.Cp >> 3, nstage = L.nchunk;
   const bool x3 = (p.math == PNCE_MATH_TC_BF16X3);
   volatile int* dead = &sh->dead;
+  long long* tr = nullptr;                                   // debug stamps (pnce_debug_set key 3)
+  if (p.trace != nullptr && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) tr = p.trace + (blockIdx.x ? 16 : 0);
+#define PNCE_TR(slot) do { if (tr) tr[slot] = clock64(); } while (0)
 
   if (tid == 0) {
     mbar_init(&sh->full[0], 1); mbar_init(&sh->full[1], 1);
     mbar_init(&sh->empty[0], 1); mbar_init(&sh->empty[1], 1);
     mbar_init(&sh->zfull, 1); mbar_init(&sh->dzready, 128); mbar_init(&sh->dqfull, 1);
     sh->dead = 0;
+    sh->badk = 0;
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&sh->tmem_base);
@@ -106,6 +237,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       const uint32_t idesc2 = idesc_bf16(128, 32, 0, 1);     // B read MN-major (N = channel)
       uint32_t it = 0;
       bool ok = true;
+      PNCE_TR(8);
       // phase 1: Z = Q K^T
       for (int s = 0; s < nstage && ok; ++s, ++it) {
         const int slot = it & 1;
@@ -127,9 +259,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
         mma_commit(&sh->empty[slot]);
       }
       mma_commit(&sh->zfull);
+      PNCE_TR(9);
       // phase 2: dQ = dZ K
       if (ok) ok = mbar_wait(&sh->dzready, 0u, dead);
       tc_fence_after();
+      PNCE_TR(10);
       const uint32_t dzh = smem_u32(dzhi), dzl = smem_u32(dzlo);
       for (int s = 0; s < nstage && ok; ++s, ++it) {
         const int slot = it & 1;
@@ -152,133 +286,166 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
         mma_commit(&sh->empty[slot]);
       }
       mma_commit(&sh->dqfull);
+      PNCE_TR(11);
     }
   } else {
     // ===================== epilogue: thread <-> logits row =====================
     const int q = warp & 3;                                  // TMEM lane quadrant this warp may touch
     const int i = q * 32 + lane;                             // row inside the half
-    const int gi = mh * 128 + i;                             // patch index
+    const int gi = mh * 128 + i;                             // sorted patch slot
     const bool rowok = gi < P;
     const int et = tid - 64;                                 // 0..127
-    // 1/||k_j|| for the N key rows, 1/||q_i|| for this row
-    for (int j = et; j < N; j += 128) {
+    if (et != 0) tr = nullptr;
+    PNCE_TR(0);
+    // 1/||k_j|| for the N key rows, ||q_i|| for this row: all partial-sum loads are issued up front
+    float rownrm;
+    {
+      float ssk[2][8], ssq[8];
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = et + 128 * h;
+          ssk[h][s] = (s < nstage && j < P) ? __ldcg(L.kss + ((size_t)b * nstage + s) * N + j) : 0.f;
+        }
+        ssq[s] = (s < nstage && rowok) ? __ldcg(L.qss + ((size_t)b * nstage + s) * N + gi) : 0.f;
+      }
+      bool anybad = false;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = et + 128 * h;
+        if (j < N) {
+          float ss = 0.f;
+#pragma unroll
+          for (int s = 0; s < 8; ++s) ss += ssk[h][s];
+          const float nrm = sqrtf(ss);
+          const bool bad = !(nrm == nrm);                     // the gather marks non-finite rows with NaN
+          anybad |= bad && j < P;
+          invk_s[j] = (j < P && !bad) ? 1.0f / fmaxf(nrm, kNormEps) : 0.f;
+        }
+      }
+      if (anybad) sh->badk = 1;
       float ss = 0.f;
-      if (j < P)
-        for (int s = 0; s < nstage; ++s) ss += L.kss[((size_t)b * nstage + s) * N + j];
-      const float nrm = sqrtf(ss);
-      float inv = 1.0f / fmaxf(nrm, kNormEps);
-      if (!(nrm == nrm)) inv = nrm;
-      invk_s[j] = (j < P) ? inv : 0.f;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) ss += ssq[s];
+      rownrm = sqrtf(ss);
+      if (rowok)
+        L.qinv[(size_t)b * P + gi] =
+            (rownrm == rownrm) ? (rownrm < kNormEps ? -1.0f / kNormEps : 1.0f / rownrm) : rownrm;
     }
-    float sc = 0.f;                                           // 1 / max(||q_i||, eps)
-    bool noproj = false;
-    if (rowok) {
-      float ss = 0.f;
-      for (int s = 0; s < nstage; ++s) ss += L.qss[((size_t)b * nstage + s) * N + gi];
-      const float nrm = sqrtf(ss);
-      sc = 1.0f / fmaxf(nrm, kNormEps);
-      if (!(nrm == nrm)) sc = nrm;
-      noproj = nrm < kNormEps;
-      L.qinv[(size_t)b * P + gi] = (nrm == nrm) ? (noproj ? -1.0f / kNormEps : 1.0f / nrm) : nrm;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const float inv_tau = 1.0f / p.tau;
-    const float zscale = sc * inv_tau;
-    const float coef = 1.0f / ((float)P * (float)p.B * (float)p.n_layers);
-    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    bool ok = mbar_wait(&sh->zfull, 0u, dead);
-    tc_fence_after();
-    // ---- pass A: row sum of exp, diagonal ----
-    float se = 0.f, zd = 0.f;
-    const int nch = N >> 5;
-    for (int ch = 0; ch < nch; ++ch) {
-      uint32_t r[32];
-      tmem_ld32(trow + ch * 32, r);
-      tmem_ld_wait();
+    asm volatile("bar.sync 1, 128;" ::: "memory");            // publishes invk_s and badk
+    {
+      const bool badq = rowok && !(rownrm == rownrm);
+      const float sc = (rowok && !badq) ? 1.0f / fmaxf(rownrm, kNormEps) : 0.f;     // 1 / max(||q_i||, eps)
+      const bool noproj = rownrm < kNormEps;
+      const bool badrow = badq || (sh->badk != 0);
+
+      const float inv_tau = 1.0f / p.tau;
+      const float a = sc * inv_tau * kLog2e;                  // acc -> logit in log2 units (times 1/||k_j||)
+      const float cl = kClamp * kLog2e;
+      const bool need_clamp = inv_tau * 1.02f > kClamp;       // |cos| <= 1: the clamp cannot bind otherwise
+      const float coef = rowok ? 1.0f / ((float)P * (float)p.B * (float)p.n_layers) : 0.f;
+      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+      const int nch = (P + 31) >> 5;                          // chunks that hold real columns
+      const int chd = gi >> 5;                                // chunk holding this warp's diagonal (warp-uniform)
+      PNCE_TR(1);
+      bool ok = mbar_wait(&sh->zfull, 0u, dead);
+      tc_fence_after();
+      PNCE_TR(2);
+      // ---- pass A: row sum of exp2, diagonal ----
+      float se4[4] = {0.f, 0.f, 0.f, 0.f};
+      float ydacc = 0.f;                                      // raw accumulator of the diagonal element
+      if (need_clamp) tc_row_pass_a<true>(trow, nch, invk_s, a, cl, chd, lane, se4, ydacc);
+      else tc_row_pass_a<false>(trow, nch, invk_s, a, cl, chd, lane, se4, ydacc);
+      const float wd = invk_s[gi];
+      const float ydr = ydacc * a * wd;                       // unclamped diagonal logit (log2 units)
+      const float yd = need_clamp ? fminf(fmaxf(ydr, -cl), cl) : ydr;
+      // padding columns of the last chunk contributed exp2(0) = 1 each
+      const float se = ((se4[0] + se4[1]) + (se4[2] + se4[3])) - (float)(nch * 32 - P);
+      const float lse2 = lg2f(se);
+      float rowloss = rowok ? (lse2 - yd) * kLn2 : 0.f;        // :94, labels = arange
+      if (badrow && rowok) rowloss = __int_as_float(0x7fc00000);
+      PNCE_TR(3);
+      // ---- pass B: dZ (pre-divided by ||k_j||) -> smem A operand, s_i ----
+      float s2 = 0.f;
+      const uint32_t rowoff = (uint32_t)(i >> 3) * 128u + (uint32_t)(i & 7) * 16u;
+      if (need_clamp) tc_row_pass_b<true>(trow, nch, invk_s, a, cl, lse2, coef, x3, dzhi, dzlo, rowoff, s2);
+      else tc_row_pass_b<false>(trow, nch, invk_s, a, cl, lse2, coef, x3, dzhi, dzlo, rowoff, s2);
+      // the "- I" of (softmax - I): fix this row's diagonal element (same thread wrote it above)
+      if (rowok) {
+        const bool pass = !need_clamp || fabsf(ydr) <= cl;
+        const float d = pass ? (ex2f(yd - lse2) - 1.f) * coef : 0.f;
+        if (pass) s2 = fmaf(-coef, ydr, s2);
+        const float ddv = d * wd;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(ddv);
+        const uint32_t off = (uint32_t)(gi >> 3) * 2048u + rowoff + (uint32_t)(gi & 7) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(dzhi + off) = hi;
+        if (x3) *reinterpret_cast<__nv_bfloat16*>(dzlo + off) = __float2bfloat16_rn(ddv - __bfloat162float(hi));
+      }
+      // padding chunks of the A operand must be finite (they meet all-zero key rows)
+      for (int ch = nch; ch < (N >> 5); ++ch) {
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const uint32_t off = (uint32_t)(ch * 4 + g8) * 2048u + rowoff;
+          *reinterpret_cast<uint4*>(dzhi + off) = make_uint4(0u, 0u, 0u, 0u);
+          if (x3) *reinterpret_cast<uint4*>(dzlo + off) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      const float s_i = s2 * kLn2;                              // sum_j dZ_ij z_ij
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&sh->dzready);
+      PNCE_TR(4);
+      // row losses: warp shuffle, then one partial per CTA (deterministic order)
+      rowloss = warp_sum(rowloss);
+      if (lane == 0) sh->red[q] = rowloss;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) L.partial[(size_t)b * L.nparts + mh] = sh->red[0] + sh->red[1] + sh->red[2] + sh->red[3];
+      // ---- dQ epilogue: dq/tau -> normalise backward -> dxT (coalesced: lane <-> consecutive slot) ----
+      // F.normalize backward: (g - x^(x^.g)) / n when n >= eps, else g / eps
+      //   dx = dq*sc - q_raw * (sc^2 s_i)       with dq = acc / tau
+      const float c1 = inv_tau * sc;
+      const float c2 = noproj ? 0.f : sc * sc * s_i;
+      const float* __restrict__ qrow = L.qT + (size_t)b * C * N + gi;
+      float* __restrict__ dxrow = L.dxT + (size_t)b * C * P + gi;
+      // raw q values are prefetched two chunks ahead (static double buffer)
+      float qa[32], qb[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
-        const int j = ch * 32 + k;
-        if (j < P) {
-          const float zc = clamp_nan(__uint_as_float(r[k]) * zscale * invk_s[j], kClamp);   // :85, :88
-          se += __expf(zc);
-          if (j == gi) zd = zc;
-        }
+        qa[k] = (rowok && k < C) ? __ldcg(qrow + (size_t)k * N) : 0.f;
+        qb[k] = (rowok && 32 + k < C) ? __ldcg(qrow + (size_t)(32 + k) * N) : 0.f;
       }
-    }
-    const float lse = logf(se);
-    float rowloss = rowok ? (lse - zd) : 0.f;                 // :94, labels = arange
-    // ---- pass B: dZ (pre-divided by ||k_j||) -> smem A operand, s_i ----
-    float s_i = 0.f;
-    for (int ch = 0; ch < nch; ++ch) {
-      uint32_t r[32];
-      tmem_ld32(trow + ch * 32, r);
-      tmem_ld_wait();
+      if (ok) ok = mbar_wait(&sh->dqfull, 0u, dead);
+      tc_fence_after();
+      PNCE_TR(5);
+      for (int s = 0; s < nstage; s += 2) {
 #pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) {
-        uint32_t hw[4], lw[4];
+        for (int hb = 0; hb < 2; ++hb) {
+          const int sc_ = s + hb;
+          if (sc_ < nstage) {
+            float (&qv)[32] = hb ? qb : qa;
+            uint32_t r[32];
+            tmem_ld32(trow + 256u + sc_ * 32, r);
+            tmem_ld_wait();
+            float out[32];
 #pragma unroll
-        for (int k2 = 0; k2 < 4; ++k2) {
-          float dd[2];
+            for (int k = 0; k < 32; ++k) out[k] = fmaf(-qv[k], c2, __uint_as_float(r[k]) * c1);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int k = g8 * 8 + k2 * 2 + h;
-            const int j = ch * 32 + k;
-            float d = 0.f;
-            if (rowok && j < P) {
-              const float ik = invk_s[j];
-              const float zraw = __uint_as_float(r[k]) * zscale * ik;
-              const float pj = __expf(clamp_nan(zraw, kClamp) - lse);
-              const bool pass = (zraw >= -kClamp) && (zraw <= kClamp);
-              d = pass ? (pj - (j == gi ? 1.f : 0.f)) * coef : 0.f;
-              s_i = fmaf(d, zraw, s_i);
-              d *= ik;
+            for (int k = 0; k < 32; ++k) {
+              const int c = (sc_ + 2) * 32 + k;
+              qv[k] = (rowok && c < C) ? __ldcg(qrow + (size_t)c * N) : 0.f;
             }
-            dd[h] = d;
-          }
-          const __nv_bfloat16 ah = __float2bfloat16_rn(dd[0]), bh = __float2bfloat16_rn(dd[1]);
-          hw[k2] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-          const __nv_bfloat16 al = __float2bfloat16_rn(dd[0] - __bfloat162float(ah));
-          const __nv_bfloat16 bl = __float2bfloat16_rn(dd[1] - __bfloat162float(bh));
-          lw[k2] = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
-        }
-        const int j8 = ch * 4 + g8;
-        const uint32_t off = (uint32_t)(j8 * 16 + (i >> 3)) * 128u + (uint32_t)(i & 7) * 16u;
-        *reinterpret_cast<uint4*>(dzhi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        if (x3) *reinterpret_cast<uint4*>(dzlo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    mbar_arrive(&sh->dzready);
-    // row losses: warp shuffle, then one partial per CTA (deterministic order)
-    rowloss = warp_sum(rowloss);
-    if (lane == 0) sh->red[q] = rowloss;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (et == 0) L.partial[(size_t)b * L.nparts + mh] = sh->red[0] + sh->red[1] + sh->red[2] + sh->red[3];
-    // ---- dQ epilogue: dq/tau -> normalise backward -> dxT ----
-    if (ok) ok = mbar_wait(&sh->dqfull, 0u, dead);
-    tc_fence_after();
-    const int slot_out = rowok ? L.rank[gi] : 0;
-    const float* qrow = L.qT + (size_t)b * C * N + gi;
-    float* dxrow = L.dxT + (size_t)b * C * P + slot_out;
-    for (int s = 0; s < nstage; ++s) {
-      uint32_t r[32];
-      tmem_ld32(trow + 256u + s * 32, r);
-      tmem_ld_wait();
-      if (rowok) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const int c = s * 32 + k;
-          if (c < C) {
-            const float dq = __uint_as_float(r[k]) * inv_tau;
-            const float qh = qrow[(size_t)c * N] * sc;
-            // F.normalize backward: (g - x^(x^.g)) / n when n >= eps, else g / eps
-            dxrow[(size_t)c * P] = noproj ? dq * sc : (dq - qh * s_i) * sc;
+            for (int k = 0; k < 32; ++k) {
+              const int c = sc_ * 32 + k;
+              if (rowok && c < C) dxrow[(size_t)c * P] = out[k];
+            }
           }
         }
       }
+      PNCE_TR(6);
+      tc_fence_before();
     }
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {

@@ -1,6 +1,7 @@
 // libpnce.so -- C ABI (include/pnce.h) over the sm_100a kernels.  Host side only: argument checks,
 // workspace carving, launch geometry.  No device allocation, no host sync, graph-capturable.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -97,6 +98,7 @@ static size_t carve_fused(const pnce_layer_t* layers, int n_layers, int B, bool 
     L.ustart = cv.take<int>(a.P + 1);
     L.bitmap = cv.take<unsigned>(L.nwords);
     L.prefix = cv.take<unsigned>(L.nwords);
+    L.cslot = cv.take<int>((size_t)(L.HW + kTilePos - 1) / kTilePos + 1);
     L.qinv = cv.take<float>((size_t)B * a.P);
     L.dxT = cv.take<float>(rows);
     L.dq_rows = nullptr;
@@ -105,6 +107,7 @@ static size_t carve_fused(const pnce_layer_t* layers, int n_layers, int B, bool 
       L.qn = cv.take<float>(rows);
       L.kn = cv.take<float>(rows);
     } else {
+      L.sorted = 1;
       L.Cp = (a.C + 31) / 32 * 32;
       L.Ppad = (a.P + 127) / 128 * 128;
       L.nchunk = L.Cp / 32;
@@ -188,22 +191,30 @@ static int launch_loss_simt(const Params& p, cudaStream_t st) {
   return PNCE_OK;
 }
 
-static int launch_gather_tc(const Params& p, cudaStream_t st) {
-  BlockMap m;
-  memset(&m, 0, sizeof(m));
-  long long acc = 0;
+static int launch_prep(const Params& p, cudaStream_t st) {
   size_t smem = 0;
   for (int l = 0; l < p.n_layers; ++l) {
-    m.start[l] = acc;
-    acc += 2ll * p.B * p.L[l].nchunk;
     int n2 = 1;
     while (n2 < p.L[l].P) n2 <<= 1;
     const size_t s = (size_t)n2 * 8 + 64;
     if (s > smem) smem = s;
   }
+  k_prep<<<(unsigned)p.n_layers, kThreads, smem, st>>>(p);
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+
+static int launch_gather_tc(const Params& p, cudaStream_t st) {
+  BlockMap m;
+  memset(&m, 0, sizeof(m));
+  long long acc = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    m.start[l] = acc;
+    acc += 2ll * p.B * p.L[l].nchunk;
+  }
   m.start[p.n_layers] = acc;
-  if (acc + p.n_layers > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
-  k_gather_tc<<<(unsigned)(acc + p.n_layers), kThreads, smem, st>>>(p, m);
+  if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+  k_gather_tc<<<(unsigned)acc, kThreads, 0, st>>>(p, m);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
@@ -225,7 +236,17 @@ static int launch_loss_tc(const Params& p, cudaStream_t st) {
   return PNCE_OK;
 }
 
-static int launch_dense(const Params& p, cudaStream_t st) {
+// Experiment knobs (pnce_debug_set; not part of pnce.h).  0 = library default.
+struct DebugKnobs {
+  int dense_variant = 0;     // 0: flat tiles (default), 1: warp-per-segment LSU kernel, 2: persistent bulk-copy kernel
+  int dense_flags = 0;       // bit 0: skip the patch phase (fill ceiling)
+  int dense_ctas_per_sm = 0;
+  int flat_threads = 0;      // 64: 64-thread tiles in the flat dense kernel (default 128)
+  long long* trace = nullptr;
+};
+static DebugKnobs g_dbg;
+
+static int launch_dense_warp(const Params& p, cudaStream_t st) {
   DenseMap m;
   memset(&m, 0, sizeof(m));
   const int vec = (p.dtype == PNCE_F32) ? 4 : 8;
@@ -240,9 +261,80 @@ static int launch_dense(const Params& p, cudaStream_t st) {
   m.start[p.n_layers] = acc;
   m.total = acc;
   const long long ctas_needed = (acc + (kThreads / 32) - 1) / (kThreads / 32);
-  long long grid = (long long)sm_count() * 8;            // 8 x 256-thread CTAs per SM, persistent
+  // persistent grid = exactly the CTAs that are co-resident (a partial second wave of a
+  // persistent kernel would run alone at the end)
+  static int occ = 0;
+  if (occ == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dense_bwd<float>, kThreads, 0) !=
+                       cudaSuccess || occ < 1))
+    occ = 4;
+  const int per_sm = g_dbg.dense_ctas_per_sm > 0 ? g_dbg.dense_ctas_per_sm : occ;
+  long long grid = (long long)sm_count() * per_sm;
   if (grid > ctas_needed) grid = ctas_needed;
-  k_dense_bwd<<<(unsigned)grid, kThreads, 0, st>>>(p, m);
+  if (p.dtype == PNCE_F32) k_dense_bwd<float><<<(unsigned)grid, kThreads, 0, st>>>(p, m);
+  else if (p.dtype == PNCE_F16) k_dense_bwd<__half><<<(unsigned)grid, kThreads, 0, st>>>(p, m);
+  else k_dense_bwd<__nv_bfloat16><<<(unsigned)grid, kThreads, 0, st>>>(p, m);
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+
+static int launch_dense(const Params& p, cudaStream_t st) {
+  // the bulk-copy kernel needs every row start and every chunk to be 16-byte tileable
+  const size_t es = dtype_size(p.dtype);
+  bool tma_ok = g_dbg.dense_variant != 1;
+  for (int l = 0; l < p.n_layers && tma_ok; ++l) {
+    const LayerDev& L = p.L[l];
+    if (((size_t)L.HW * es) % 16 != 0 || (reinterpret_cast<uintptr_t>(L.dtgt) & 15u)) tma_ok = false;
+  }
+  if (!tma_ok) return launch_dense_warp(p, st);
+  if (g_dbg.dense_variant != 2) {
+    // default: one small CTA per 8 KB tile, in address order
+    DenseFlatMap f;
+    memset(&f, 0, sizeof(f));
+    long long tot = 0;
+    const int tp = kFlatBytes / (int)es;
+    for (int l = 0; l < p.n_layers; ++l) {
+      f.start[l] = tot;
+      f.tiles[l] = (p.L[l].HW + tp - 1) / tp;
+      tot += (long long)p.B * p.L[l].C * f.tiles[l];
+    }
+    f.start[p.n_layers] = tot;
+    f.flags = g_dbg.dense_flags;
+    if (tot > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+    const unsigned grid = (unsigned)tot;
+    if (g_dbg.flat_threads == 64) {
+      if (p.dtype == PNCE_F32) k_dense_flat<float, 64><<<grid, 64, 0, st>>>(p, f);
+      else if (p.dtype == PNCE_F16) k_dense_flat<__half, 64><<<grid, 64, 0, st>>>(p, f);
+      else k_dense_flat<__nv_bfloat16, 64><<<grid, 64, 0, st>>>(p, f);
+    } else {
+      if (p.dtype == PNCE_F32) k_dense_flat<float, 128><<<grid, 128, 0, st>>>(p, f);
+      else if (p.dtype == PNCE_F16) k_dense_flat<__half, 128><<<grid, 128, 0, st>>>(p, f);
+      else k_dense_flat<__nv_bfloat16, 128><<<grid, 128, 0, st>>>(p, f);
+    }
+    PNCE_CUDA(cudaGetLastError());
+    return PNCE_OK;
+  }
+  DenseTmaMap m;
+  memset(&m, 0, sizeof(m));
+  long long acc = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const LayerDev& L = p.L[l];
+    m.start[l] = acc;
+    m.chunks[l] = (L.HW + kChunkPos - 1) / kChunkPos;
+    acc += (long long)p.B * L.C * m.chunks[l];
+  }
+  m.start[p.n_layers] = acc;
+  m.total = acc;
+  m.flags = g_dbg.dense_flags;
+  // persistent grid: every CTA takes one contiguous range of items (so it stays inside one column
+  // of equal sample positions as long as possible); 6 CTAs x 32 KB staging per SM
+  const int per_sm = g_dbg.dense_ctas_per_sm > 0 ? g_dbg.dense_ctas_per_sm : 6;
+  long long grid = (long long)sm_count() * per_sm;
+  if (grid > acc) grid = acc;
+  m.per_cta = (acc + grid - 1) / grid;
+  grid = (acc + m.per_cta - 1) / m.per_cta;
+  if (p.dtype == PNCE_F32) k_dense_tma<float><<<(unsigned)grid, kDenseTmaThreads, 0, st>>>(p, m);
+  else if (p.dtype == PNCE_F16) k_dense_tma<__half><<<(unsigned)grid, kDenseTmaThreads, 0, st>>>(p, m);
+  else k_dense_tma<__nv_bfloat16><<<(unsigned)grid, kDenseTmaThreads, 0, st>>>(p, m);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
@@ -286,6 +378,26 @@ const char* pnce_status_string(int s) {
 
 const char* pnce_last_cuda_error(void) { return g_cuda_err; }
 
+// Experiment hooks (not part of pnce.h).
+int pnce_debug_set(int key, long long value) {
+  switch (key) {
+    case 0: g_dbg.dense_variant = (int)value; break;
+    case 1: g_dbg.dense_flags = (int)value; break;
+    case 2: g_dbg.dense_ctas_per_sm = (int)value; break;
+    case 3: g_dbg.trace = reinterpret_cast<long long*>(value); break;
+    case 4: g_dbg.flat_threads = (int)value; break;
+    default: return PNCE_ERR_ARG;
+  }
+  return PNCE_OK;
+}
+// device-wide L2 fetch granularity hint, 32/64/128 bytes
+int pnce_debug_set_l2_fetch_granularity(int bytes) {
+  PNCE_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+  size_t v = 0;
+  PNCE_CUDA(cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
+  return (int)v;
+}
+
 int pnce_workspace_bytes(const pnce_layer_t* layers, int n_layers, int batch, size_t* bytes) {
   if (bytes == nullptr) return PNCE_ERR_ARG;
   int rc = check_layers(layers, n_layers, batch);
@@ -319,8 +431,11 @@ int pnce_fwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, flo
   p.tau = temperature;
   p.loss_out = loss_out;
   p.nonfinite = nonfinite;
+  p.trace = g_dbg.trace;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (tc) {
+    rc = launch_prep(p, st);
+    if (rc != PNCE_OK) return rc;
     rc = launch_gather_tc(p, st);
     if (rc != PNCE_OK) return rc;
     return launch_loss_tc(p, st);
@@ -388,6 +503,7 @@ static size_t carve_sample_bwd(int B, int C, int H, int W, int P, void* ws, Laye
   L.ustart = cv.take<int>(P + 1);
   L.bitmap = cv.take<unsigned>(L.nwords);
   L.prefix = cv.take<unsigned>(L.nwords);
+  L.cslot = cv.take<int>((size_t)(L.HW + kTilePos - 1) / kTilePos + 1);
   L.dxT = cv.take<float>((size_t)B * P * C);
   if (out) *out = L;
   return align_up(cv.off, 256);
@@ -476,7 +592,9 @@ int pnce_rows_loss_fwd_bwd(const float* q, const float* k, int batch, int P, int
   if (!q || !k || !loss_out || !dq_out || batch < 1 || P < 1 || D < 1 || !(temperature > 0.f)) return PNCE_ERR_ARG;
   if (P > PNCE_MAX_PATCHES || D > PNCE_MAX_CHANNELS) return PNCE_ERR_UNSUPPORTED;
   if (dk_out != nullptr) return PNCE_ERR_UNSUPPORTED;   // feat_k is detached in the reference (:142)
-  if (math_mode != PNCE_MATH_SIMT_F32) return PNCE_ERR_UNSUPPORTED;
+  if (math_mode < PNCE_MATH_SIMT_F32 || math_mode > PNCE_MATH_TC_BF16) return PNCE_ERR_ARG;
+  // rows arrive normalised in fp32 (module-split API): evaluated by the fp32 CUDA-core kernel in every
+  // math mode (the tcgen05 kernels consume the operand blobs written by the fused gather)
   if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
   Params p;
   if (carve_rows_loss(batch, P, D, ws, &p) > ws_bytes) return PNCE_ERR_WORKSPACE;

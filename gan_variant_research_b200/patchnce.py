@@ -32,7 +32,7 @@ _DTYPES = {torch.float32: _lib.PNCE_F32, torch.float16: _lib.PNCE_F16, torch.bfl
 _MATH = {"simt_f32": _lib.MATH_SIMT_F32, "tc_bf16x3": _lib.MATH_TC_BF16X3, "tc_bf16": _lib.MATH_TC_BF16}
 
 #: contraction engine used when a module does not choose one
-DEFAULT_MATH = "simt_f32"
+DEFAULT_MATH = "tc_bf16x3"
 
 
 def _stream_ptr(device) -> int:
@@ -64,33 +64,47 @@ def draw_patch_ids(feat: torch.Tensor, num_patches: int) -> torch.Tensor:
 # here the flag is copied to pinned memory asynchronously and reported on a later call)
 # ------------------------------------------------------------------------------------------------
 class _WarnQueue:
+    """Ring of pinned int32[2] slots allocated once; a slot is reused after its event completed."""
+    SLOTS = 64
+
     def __init__(self):
         self.pending = []
+        self.host = None
+        self.free = []
 
     def push(self, dev_flag: torch.Tensor):
         if torch.cuda.is_current_stream_capturing():
             return
-        host = torch.empty(dev_flag.numel(), dtype=torch.int32, pin_memory=True)
-        host.copy_(dev_flag, non_blocking=True)
+        if self.host is None:
+            self.host = torch.zeros(self.SLOTS, 2, dtype=torch.int32).pin_memory()
+            self.free = list(range(self.SLOTS))
+        if not self.free:
+            self.poll()
+            if not self.free:                    # 64 launches in flight un-polled: drop the oldest check
+                self.pending[0][0].synchronize()
+                self.poll()
+        slot = self.free.pop()
+        self.host[slot].copy_(dev_flag, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev_flag.device))
-        self.pending.append((ev, host))
+        self.pending.append((ev, slot))
 
     def poll(self, block: bool = False) -> int:
         """Print the reference's warning for finished launches; returns images guarded so far."""
         total, keep = 0, []
-        for ev, host in self.pending:
+        for ev, slot in self.pending:
             if block:
                 ev.synchronize()
             if ev.query():
-                n = int(host[0].item())
-                if host.numel() > 1 and int(host[1].item()):
+                n, proto = int(self.host[slot, 0]), int(self.host[slot, 1])
+                self.free.append(slot)
+                if proto:
                     raise _lib.PnceError("libpnce kernel protocol timeout (tcgen05 pipeline stalled)")
                 if n:
                     print(f"Warning: NaN in PatchNCE loss. {n} (layer, image) loss(es) replaced by 0.")
                 total += n
             else:
-                keep.append((ev, host))
+                keep.append((ev, slot))
         self.pending = keep
         return total
 
