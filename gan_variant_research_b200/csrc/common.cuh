@@ -21,22 +21,20 @@ struct LayerDev {
   const void* tgt;
   void* dtgt;
   const long long* ids;
-  int C, HW, P, nwords;      // nwords = ceil(HW / 32) bitmap words
+  int C, HW, P, nwords;      // nwords: unused (kept for layout stability)
   int ntiles;                // ceil(P / 32)
   int sorted;                // 1: rows / qinv are in sorted-slot order (tensor-core path), 0: ids order
   // id bookkeeping (written by the prep CTA of the gather launch)
   int* sid;                  // [P]   ids sorted ascending
   int* perm;                 // [P]   original index of sorted slot j
   int* rank;                 // [P]   sorted slot of original index p
-  int* ustart;               // [P+1] start of each run of equal ids in sorted order; [U] = P
-  unsigned* bitmap;          // [nwords] bit h set <=> position h sampled
-  unsigned* prefix;          // [nwords] number of set bits before word w
   int* cslot;                // [ceil(HW/kTilePos)+1] first sorted slot whose id >= t * kTilePos
   // rows
   float* qn;                 // [B][P][C] normalised target rows (ids order)
   float* kn;                 // [B][P][C] normalised source rows
   float* qinv;               // [B][P]  +1/||x||, or -1/eps when ||x|| < eps, NaN for non-finite rows
-  float* dxT;                // [B][C][P] d loss / d raw target patch, unit upstream, SORTED slot order
+  float* dxT;                // [B][C][dxpitch] d loss / d raw target patch, unit upstream, SORTED slot order
+  int dxpitch;               // row pitch of dxT: P, or Ppad on the tensor-core path
   float* partial;            // [B][ntiles] partial sums of row losses
   float* dq_rows;            // optional [B][P][C] output of the rows API (then dxT/qinv unused)
   int nparts;                // partial row-loss sums per image (ntiles on the SIMT path, halves on TC)
@@ -46,6 +44,8 @@ struct LayerDev {
   __nv_bfloat16* qlo;        // low part (value - hi), NULL in single-pass bf16 mode
   __nv_bfloat16* khi;        // K operand blob                   [B][Cp/8][Ppad/8][8][8]
   __nv_bfloat16* klo;
+  __nv_bfloat16* k2hi;       // the same K values, key-major  [B][Ppad/8][Cp/8][8][8]  (phase-2 B operand)
+  __nv_bfloat16* k2lo;
   float* qT;                 // [B][C][Ppad] raw fp32 target patches (transposed)
   float* qss;                // [B][nchunk][Ppad] partial sums of squares (NaN: non-finite element)
   float* kss;
@@ -56,6 +56,8 @@ struct Params {
   int n_layers, B, dtype, math;
   float tau;
   int side0;                 // first side the gather launch covers: 0 = src+tgt, 1 = tgt only
+  int b0, bn;                // images [b0, b0+bn) of the batch are covered by this launch (chunked forward)
+  unsigned total_ctas;       // loss CTAs over all chunks: the one that arrives last finalises
   float* loss_out;           // [1 + n_layers]
   int* nonfinite;            // [1]
   unsigned* counter;         // [1] last-CTA election; zeroed by the gather launch

@@ -7,42 +7,9 @@
 namespace pnce {
 
 // --------------------------------------------------------------------------------------------
-// block-wide exclusive scan of one int per thread (256 threads); returns the exclusive prefix and
-// the block total through *total.  scratch: >= 9 ints of shared memory.
+// prep CTA: ids -> (sid, perm, rank, cslot).  P <= PNCE_MAX_PATCHES.   smem: keys[N2] (u64).
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ int block_excl_scan(int v, int* scratch, int* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) scratch[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    int w = lane < (kThreads / 32) ? scratch[lane] : 0;
-    int winc = w;
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, winc, o);
-      if (lane >= o) winc += t;
-    }
-    if (lane < (kThreads / 32)) scratch[lane] = winc - w;   // exclusive warp offsets
-    if (lane == (kThreads / 32) - 1) scratch[8] = winc;     // block total
-  }
-  __syncthreads();
-  int res = scratch[warp] + inc - v;
-  *total = scratch[8];
-  __syncthreads();
-  return res;
-}
-
-// --------------------------------------------------------------------------------------------
-// prep CTA: ids -> (sid, perm, rank, ustart, bitmap, prefix).  P <= PNCE_MAX_PATCHES.
-// smem: keys[N2] (u64) + scan scratch.
-// --------------------------------------------------------------------------------------------
-__device__ void prep_layer(const LayerDev& L, unsigned long long* keys, int* scratch) {
+__device__ void prep_layer(const LayerDev& L, unsigned long long* keys) {
   const int tid = threadIdx.x;
   const int P = L.P;
   int N2 = 1;
@@ -71,33 +38,14 @@ __device__ void prep_layer(const LayerDev& L, unsigned long long* keys, int* scr
       __syncthreads();
     }
   }
-  // sid / perm / rank, run starts
-  int running = 0;
-  for (int base = 0; base < P; base += kThreads) {
-    int i = base + tid;
-    int head = 0, id = 0, pi = 0;
-    if (i < P) {
-      id = (int)(keys[i] >> 32);
-      pi = (int)(keys[i] & 0xffffffffu);
-      head = (i == 0) || ((int)(keys[i - 1] >> 32) != id);
-      L.sid[i] = id;
-      L.perm[i] = pi;
-      L.rank[pi] = i;
-    }
-    int tot;
-    int ex = block_excl_scan(head, scratch, &tot);
-    if (i < P && head) L.ustart[running + ex] = i;
-    running += tot;
-  }
-  if (tid == 0) L.ustart[running] = P;                       // running == number of unique ids
-  // bitmap
-  for (int w = tid; w < L.nwords; w += kThreads) L.bitmap[w] = 0u;
-  __syncthreads();
+  // sid / perm / rank
   for (int i = tid; i < P; i += kThreads) {
-    int id = (int)(keys[i] >> 32);
-    atomicOr(&L.bitmap[id >> 5], 1u << (id & 31));
+    const int id = (int)(keys[i] >> 32);
+    const int pi = (int)(keys[i] & 0xffffffffu);
+    L.sid[i] = id;
+    L.perm[i] = pi;
+    L.rank[pi] = i;
   }
-  __syncthreads();
   // tile -> first sorted slot (the dense backward's per-tile slot range)
   if (L.cslot != nullptr) {
     const int ntile = (L.HW + kTilePos - 1) / kTilePos;
@@ -110,16 +58,6 @@ __device__ void prep_layer(const LayerDev& L, unsigned long long* keys, int* scr
       }
       L.cslot[t] = lo;
     }
-  }
-  // exclusive popcount prefix over the bitmap words
-  running = 0;
-  for (int base = 0; base < L.nwords; base += kThreads) {
-    int w = base + tid;
-    int cnt = w < L.nwords ? __popc(L.bitmap[w]) : 0;
-    int tot;
-    int ex = block_excl_scan(cnt, scratch, &tot);
-    if (w < L.nwords) L.prefix[w] = (unsigned)(running + ex);
-    running += tot;
   }
 }
 
@@ -206,8 +144,7 @@ __global__ void __launch_bounds__(kThreads) k_gather_prep(const __grid_constant_
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     int N2 = 1;
     while (N2 < p.L[l].P) N2 <<= 1;
-    int* scratch = reinterpret_cast<int*>(keys + N2);
-    prep_layer(p.L[l], keys, scratch);
+    prep_layer(p.L[l], keys);
     return;
   }
   const int l = find_layer(m, blk, p.n_layers);

@@ -23,12 +23,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
 }
 
 template <typename T>
-__device__ void gather_tc_chunk(const LayerDev& L, int B, long long local) {
+__device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long local) {
   const int p = threadIdx.x;
   const int nchunk = L.nchunk;
   const int s = (int)(local % nchunk);
   const long long rest = local / nchunk;
-  const int b = (int)(rest % B);
+  const int b = b0 + (int)(rest % B);
   const int side = (int)(rest / B);                          // 0 = src (k), 1 = tgt (q)
   const int C = L.C, HW = L.HW, P = L.P, Ppad = L.Ppad, Cp8 = L.Cp >> 3;
   if (p >= Ppad) return;
@@ -71,6 +71,13 @@ __device__ void gather_tc_chunk(const LayerDev& L, int B, long long local) {
     }
     *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     if (lo_base != nullptr) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    if (!side) {
+      // second, key-major copy of K: [image][p/8][c/8][8 keys][8 ch] -- a chunk of 32 keys x all
+      // channels is one contiguous bulk copy and is read MN-major (N = channel) by dQ = dZ K
+      const size_t off2 = (((size_t)b * (Ppad >> 3) + (p >> 3)) * Cp8 + c8) * 64 + (size_t)(p & 7) * 8;
+      *reinterpret_cast<uint4*>(L.k2hi + off2) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      if (L.k2lo != nullptr) *reinterpret_cast<uint4*>(L.k2lo + off2) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
   }
   if (side) {
 #pragma unroll
@@ -87,9 +94,9 @@ __global__ void __launch_bounds__(kThreads) k_gather_tc(const __grid_constant__ 
   const long long blk = blockIdx.x;
   const int l = find_layer(m, blk, p.n_layers);
   const long long local = blk - m.start[l];
-  if (p.dtype == PNCE_F32) gather_tc_chunk<float>(p.L[l], p.B, local);
-  else if (p.dtype == PNCE_F16) gather_tc_chunk<__half>(p.L[l], p.B, local);
-  else gather_tc_chunk<__nv_bfloat16>(p.L[l], p.B, local);
+  if (p.dtype == PNCE_F32) gather_tc_chunk<float>(p.L[l], p.b0, p.bn, local);
+  else if (p.dtype == PNCE_F16) gather_tc_chunk<__half>(p.L[l], p.b0, p.bn, local);
+  else gather_tc_chunk<__nv_bfloat16>(p.L[l], p.b0, p.bn, local);
 }
 
 // One CTA per layer: ids -> (sid, perm, rank, ustart, bitmap, prefix); CTA 0 also resets the
@@ -104,7 +111,7 @@ __global__ void __launch_bounds__(kThreads) k_prep(const __grid_constant__ Param
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
   int N2 = 1;
   while (N2 < p.L[l].P) N2 <<= 1;
-  prep_layer(p.L[l], keys, reinterpret_cast<int*>(keys + N2));
+  prep_layer(p.L[l], keys);
 }
 
 }  // namespace pnce

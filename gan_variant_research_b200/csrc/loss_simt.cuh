@@ -67,7 +67,7 @@ __device__ void finalize_losses(const Params& p) {
           int c = (int)(i / L.P), pp = (int)(i % L.P);
           float inv = L.qinv[(size_t)b * L.P + pp];
           float v = (!layer_bad[l] && !(inv == inv)) ? __int_as_float(0x7fc00000) : 0.f;
-          L.dxT[((size_t)b * L.C + c) * L.P + (L.sorted ? pp : L.rank[pp])] = v;
+          L.dxT[((size_t)b * L.C + c) * L.dxpitch + (L.sorted ? pp : L.rank[pp])] = v;
         }
       }
     }
@@ -79,7 +79,7 @@ __device__ __forceinline__ void last_cta_finalize(const Params& p, int* flag_s) 
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned t = atomicAdd(p.counter, 1u);
-    *flag_s = (t == gridDim.x - 1) ? 1 : 0;
+    *flag_s = (t == p.total_ctas - 1) ? 1 : 0;
   }
   __syncthreads();
   if (*flag_s) {
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) k_loss_simt(const __grid_constant__ 
         const int slot = (i < P) ? L.rank[i] : 0;
         for (int cc = ty; cc < 256; cc += 8) {
           const int c = cb + cc;
-          if (c < C && i < P) L.dxT[((size_t)b * C + c) * P + slot] = St[cc * 33 + tx];
+          if (c < C && i < P) L.dxT[((size_t)b * C + c) * L.dxpitch + slot] = St[cc * 33 + tx];
         }
       }
       __syncthreads();

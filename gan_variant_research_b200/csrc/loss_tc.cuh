@@ -8,15 +8,19 @@
 // in exactly the order the dense backward reads them.
 //
 //   phase 1   Z(128 x N) = Q_half K^T           kind::f16 bf16, fp32 accumulate in TMEM cols [0,N)
-//             streamed over C in chunks of 32 channels through a 2-slot smem ring.
+//             streamed over C in chunks of 32 channels through a 4-slot ring (2 slots live in the dZ
+//             region, idle until the epilogue), so the bulk copies run 3 stages ahead of the MMAs.
 //             bf16x3 mode issues hi*hi + hi*lo + lo*hi into the same accumulator (~2^-17 operand error).
 //   epilogue  y_ij = acc * (log2e/tau)(1/||q_i||)(1/||k_j||)   (logits in log2 units), clamp, row sum of
 //             exp2, diagonal pick, row loss (warp-shuffle reduced), dZ = (softmax - I) * mask / (P B L),
 //             s_i = sum_j dZ_ij z_ij (= q_hat . dq, no second reduction needed),
 //             dZ_ij / ||k_j|| split hi/lo -> shared memory as the next MMA's A operand.
 //             The element loops are branch-free (32 independent columns per tcgen05.ld).
-//   phase 2   dQ(128 x C) = dZ K               K re-streamed in the same chunks and read MN-major from
-//             the very same shared-memory image; accumulate in TMEM cols [256, 256+C)
+//   phase 2   dQ(128 x C) = dZ K               K streamed a second time, KEY-major (32 keys x all channels
+//             per 3-slot ring stage, from the gather's second K blob) and read MN-major, so every MMA
+//             is M128 x N=C x K16 (N=32 MMAs re-read the whole A tile and starve on shared-memory
+//             bandwidth).  Chunk j's MMAs start as soon as the four epilogue warps have written
+//             dZ[:, 32j..32j+31]: phase 2 overlaps pass B.  Accumulator: TMEM cols [256, 256+C)
 //   epilogue  dq/tau, normalise backward, dxT[b][c][slot] (unit upstream gradient), coalesced.
 // The logits, softmax and dZ never leave the SM.  Replaces patchnce_cut.py:83-110 and the autograd
 // backward of :77-94.  Shapes: P <= 256, C <= 256.
@@ -35,8 +39,12 @@ constexpr int kTcSmemBytes = 2 * kTcStageBytes + 2 * kTcDzBytes + 1024 /*invk*/ 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
+constexpr int kTcSlots1 = 4;                // phase-1 slots: 2 in the ring region + 2 in the (still idle) dZ region
+constexpr int kTcSlots2 = 3;                // phase-2 slots (K only, 32 KB each) in the ring region
+constexpr int kTcStage2Bytes = 32768;       // Khi 16K | Klo 16K
+
 struct TcShared {
-  uint64_t full[2], empty[2], zfull, dzready, dqfull;
+  uint64_t full1[kTcSlots1], empty1[kTcSlots1], full2[kTcSlots2], empty2[kTcSlots2], zfull, dzready[8], dqfull;
   uint32_t tmem_base;
   int dead;
   int flag;
@@ -144,10 +152,25 @@ __device__ __forceinline__ void tc_row_pass_a(uint32_t trow, int nch, const floa
   }
 }
 
+// the "- I" of (softmax - I): the thread that owns row i rewrites its diagonal element
+struct TcDiag {
+  bool rowok, pass;
+  float d_w;                 // (p_ii - 1) * coef / ||k_i||, or 0 when the clamp masks it
+  uint32_t off;              // byte offset of the element in the dZ operand
+};
+__device__ __forceinline__ void tc_fix_diag(const TcDiag& dg, bool x3, unsigned char* dzhi, unsigned char* dzlo) {
+  if (dg.rowok) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(dg.d_w);
+    *reinterpret_cast<__nv_bfloat16*>(dzhi + dg.off) = hi;
+    if (x3) *reinterpret_cast<__nv_bfloat16*>(dzlo + dg.off) = __float2bfloat16_rn(dg.d_w - __bfloat162float(hi));
+  }
+}
+
 template <bool CLAMP>
 __device__ __forceinline__ void tc_row_pass_b(uint32_t trow, int nch, const float* __restrict__ invk_s, float a,
                                               float cl, float lse2, float coef, bool x3, unsigned char* dzhi,
-                                              unsigned char* dzlo, uint32_t rowoff, float& s2) {
+                                              unsigned char* dzlo, uint32_t rowoff, int chd, const TcDiag& dg,
+                                              uint64_t* dzready, float& s2) {
   using namespace umma;
   uint32_t r0[32], r1[32];
   tmem_ld32(trow, r0);
@@ -155,11 +178,75 @@ __device__ __forceinline__ void tc_row_pass_b(uint32_t trow, int nch, const floa
     tmem_ld_wait();
     if (ch + 1 < nch) tmem_ld32(trow + (ch + 1) * 32, r1);
     tc_pass_b<CLAMP>(r0, invk_s + ch * 32, a, cl, lse2, coef, x3, dzhi, dzlo, (uint32_t)(ch * 4) * 2048u + rowoff, s2);
+    if (ch == chd) tc_fix_diag(dg, x3, dzhi, dzlo);
+    fence_proxy_async_smem();
+    mbar_arrive(&dzready[ch]);                               // 128 arrivals release chunk ch to the MMA thread
     if (ch + 1 < nch) {
       tmem_ld_wait();
       if (ch + 2 < nch) tmem_ld32(trow + (ch + 2) * 32, r0);
       tc_pass_b<CLAMP>(r1, invk_s + (ch + 1) * 32, a, cl, lse2, coef, x3, dzhi, dzlo,
                        (uint32_t)((ch + 1) * 4) * 2048u + rowoff, s2);
+      if (ch + 1 == chd) tc_fix_diag(dg, x3, dzhi, dzlo);
+      fence_proxy_async_smem();
+      mbar_arrive(&dzready[ch + 1]);
+    }
+  }
+}
+
+// dQ epilogue for one 32-channel chunk; NP = pitch of qT and dxT rows (compile-time: immediates)
+template <int NP>
+__device__ __forceinline__ void tc_dq_chunk(const uint32_t (&r)[32], float (&qv)[32], const float* __restrict__ qp,
+                                            float* __restrict__ dp, int nvalid, int nnext, float c1, float c2,
+                                            bool rowok) {
+  float out[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) out[k] = fmaf(-qv[k], c2, __uint_as_float(r[k]) * c1);
+  // raw q of the chunk after next (qp already points there); whole chunks take the unpredicated path
+  if (nnext >= 32) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) qv[k] = __ldcg(qp + k * NP);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) qv[k] = (k < nnext) ? __ldcg(qp + k * NP) : 0.f;
+  }
+  if (rowok) {
+    if (nvalid >= 32) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) dp[k * NP] = out[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < nvalid) dp[k * NP] = out[k];
+    }
+  }
+}
+
+template <int NP>
+__device__ __forceinline__ void tc_dq_epilogue(uint32_t tacc, int nstage, int C, const float* __restrict__ qrow,
+                                               float* __restrict__ dxrow, float c1, float c2, bool rowok,
+                                               uint64_t* dqfull, volatile int* dead) {
+  using namespace umma;
+  // raw q values are prefetched two chunks ahead (static double buffer); padding rows read row 0 of
+  // the image (always mapped) and never store
+  float qa[32], qb[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    qa[k] = (k < C) ? __ldcg(qrow + k * NP) : 0.f;
+    qb[k] = (32 + k < C) ? __ldcg(qrow + (32 + k) * NP) : 0.f;
+  }
+  mbar_wait(dqfull, 0u, dead);
+  tc_fence_after();
+  for (int s = 0; s < nstage; s += 2) {
+    uint32_t r[32];
+    tmem_ld32(tacc + s * 32, r);
+    tmem_ld_wait();
+    tc_dq_chunk<NP>(r, qa, qrow + (size_t)(s + 2) * 32 * NP, dxrow + (size_t)s * 32 * NP, C - s * 32,
+                    C - (s + 2) * 32, c1, c2, rowok);
+    if (s + 1 < nstage) {
+      tmem_ld32(tacc + (s + 1) * 32, r);
+      tmem_ld_wait();
+      tc_dq_chunk<NP>(r, qb, qrow + (size_t)(s + 3) * 32 * NP, dxrow + (size_t)(s + 1) * 32 * NP, C - (s + 1) * 32,
+                      C - (s + 3) * 32, c1, c2, rowok);
     }
   }
 }
@@ -179,7 +266,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
   const LayerDev& L = p.L[l];
   const int local = (int)(blockIdx.x - m.start[l]);
   const int halves = L.Ppad >> 7;
-  const int mh = local % halves, b = local / halves;
+  const int mh = local % halves, b = p.b0 + local / halves;
   const int N = L.Ppad, P = L.P, C = L.C, Cp8 = L.Cp >> 3, nstage = L.nchunk;
   const bool x3 = (p.math == PNCE_MATH_TC_BF16X3);
   volatile int* dead = &sh->dead;
@@ -188,9 +275,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
 #define PNCE_TR(slot) do { if (tr) tr[slot] = clock64(); } while (0)
 
   if (tid == 0) {
-    mbar_init(&sh->full[0], 1); mbar_init(&sh->full[1], 1);
-    mbar_init(&sh->empty[0], 1); mbar_init(&sh->empty[1], 1);
-    mbar_init(&sh->zfull, 1); mbar_init(&sh->dzready, 128); mbar_init(&sh->dqfull, 1);
+    for (int k = 0; k < kTcSlots1; ++k) { mbar_init(&sh->full1[k], 1); mbar_init(&sh->empty1[k], 1); }
+    for (int k = 0; k < kTcSlots2; ++k) { mbar_init(&sh->full2[k], 1); mbar_init(&sh->empty2[k], 1); }
+    mbar_init(&sh->zfull, 1); mbar_init(&sh->dqfull, 1);
+    for (int k = 0; k < 8; ++k) mbar_init(&sh->dzready[k], 128);
     sh->dead = 0;
     sh->badk = 0;
     fence_barrier_init();
@@ -212,38 +300,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
                                    ((size_t)b * halves + mh) * Cp8 * 2048;
       const unsigned char* gk_hi = reinterpret_cast<const unsigned char*>(L.khi) + (size_t)b * Cp8 * (N * 16);
       const unsigned char* gk_lo = reinterpret_cast<const unsigned char*>(L.klo) + (size_t)b * Cp8 * (N * 16);
-      uint32_t it = 0;
-      for (int ph = 0; ph < 2; ++ph) {
-        for (int s = 0; s < nstage; ++s, ++it) {
-          const int slot = it & 1;
-          const uint32_t par = (it >> 1) & 1u;
-          if (!mbar_wait(&sh->empty[slot], par ^ 1u, dead)) break;
-          unsigned char* st = stage0 + slot * kTcStageBytes;
-          const uint32_t tx = (ph == 0 ? 8192u : 0u) * (x3 ? 2u : 1u) + kbytes * (x3 ? 2u : 1u);
-          mbar_expect_tx(&sh->full[slot], tx);
-          if (ph == 0) {
-            bulk_g2s(st, gq_hi + (size_t)s * 8192, 8192u, &sh->full[slot]);
-            if (x3) bulk_g2s(st + kTcOffQlo, gq_lo + (size_t)s * 8192, 8192u, &sh->full[slot]);
-          }
-          bulk_g2s(st + kTcOffKhi, gk_hi + (size_t)s * kbytes, kbytes, &sh->full[slot]);
-          if (x3) bulk_g2s(st + kTcOffKlo, gk_lo + (size_t)s * kbytes, kbytes, &sh->full[slot]);
-        }
+      bool ok = true;
+      for (int s = 0; s < nstage && ok; ++s) {                // phase 1: Q and K chunks
+        const int slot = s % kTcSlots1;
+        ok = mbar_wait(&sh->empty1[slot], ((uint32_t)(s / kTcSlots1) & 1u) ^ 1u, dead);
+        if (!ok) break;
+        unsigned char* st = (slot < 2 ? stage0 : dzhi - 2 * kTcStageBytes) + slot * kTcStageBytes;
+        mbar_expect_tx(&sh->full1[slot], (8192u + kbytes) * (x3 ? 2u : 1u));
+        bulk_g2s(st, gq_hi + (size_t)s * 8192, 8192u, &sh->full1[slot]);
+        if (x3) bulk_g2s(st + kTcOffQlo, gq_lo + (size_t)s * 8192, 8192u, &sh->full1[slot]);
+        bulk_g2s(st + kTcOffKhi, gk_hi + (size_t)s * kbytes, kbytes, &sh->full1[slot]);
+        if (x3) bulk_g2s(st + kTcOffKlo, gk_lo + (size_t)s * kbytes, kbytes, &sh->full1[slot]);
+      }
+      // phase 2 re-uses the ring region with its own slot geometry: wait until phase 1 has drained
+      if (ok) ok = mbar_wait(&sh->zfull, 0u, dead);
+      const unsigned char* g2_hi = reinterpret_cast<const unsigned char*>(L.k2hi) + (size_t)b * N * L.Cp * 2;
+      const unsigned char* g2_lo = reinterpret_cast<const unsigned char*>(L.k2lo) + (size_t)b * N * L.Cp * 2;
+      const uint32_t k2bytes = (uint32_t)L.Cp * 64u;          // 32 keys x Cp channels x 2 B
+      const int nkey = (P + 31) >> 5;
+      for (int j = 0; j < nkey && ok; ++j) {                  // phase 2: key-major K chunks
+        const int slot = j % kTcSlots2;
+        ok = mbar_wait(&sh->empty2[slot], ((uint32_t)(j / kTcSlots2) & 1u) ^ 1u, dead);
+        if (!ok) break;
+        unsigned char* st = stage0 + slot * kTcStage2Bytes;
+        mbar_expect_tx(&sh->full2[slot], k2bytes * (x3 ? 2u : 1u));
+        bulk_g2s(st, g2_hi + (size_t)j * k2bytes, k2bytes, &sh->full2[slot]);
+        if (x3) bulk_g2s(st + 16384, g2_lo + (size_t)j * k2bytes, k2bytes, &sh->full2[slot]);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc1 = idesc_bf16(128, N, 0, 0);
-      const uint32_t idesc2 = idesc_bf16(128, 32, 0, 1);     // B read MN-major (N = channel)
-      uint32_t it = 0;
       bool ok = true;
       PNCE_TR(8);
       // phase 1: Z = Q K^T
-      for (int s = 0; s < nstage && ok; ++s, ++it) {
-        const int slot = it & 1;
-        ok = mbar_wait(&sh->full[slot], (it >> 1) & 1u, dead);
+      for (int s = 0; s < nstage && ok; ++s) {
+        const int slot = s % kTcSlots1;
+        ok = mbar_wait(&sh->full1[slot], (uint32_t)(s / kTcSlots1) & 1u, dead);
         tc_fence_after();
-        const uint32_t st = smem_u32(stage0 + slot * kTcStageBytes);
+        const uint32_t st = smem_u32((slot < 2 ? stage0 : dzhi - 2 * kTcStageBytes) + slot * kTcStageBytes);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {                     // 16 channels = 2 slabs per MMA
           const uint64_t a_hi = smem_desc(st + ks * 4096, 2048, 128);
@@ -256,34 +352,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
             mma_bf16(tmem, a_lo, b_hi, idesc1, 1u);
           }
         }
-        mma_commit(&sh->empty[slot]);
+        mma_commit(&sh->empty1[slot]);
       }
       mma_commit(&sh->zfull);
       PNCE_TR(9);
-      // phase 2: dQ = dZ K
-      if (ok) ok = mbar_wait(&sh->dzready, 0u, dead);
-      tc_fence_after();
-      PNCE_TR(10);
+      // phase 2: dQ = dZ K, one stage per 32 keys, released chunk by chunk by the epilogue warps
+      const uint32_t idesc2 = idesc_bf16(128, L.Cp, 0, 1);   // B read MN-major (N = channel)
       const uint32_t dzh = smem_u32(dzhi), dzl = smem_u32(dzlo);
-      for (int s = 0; s < nstage && ok; ++s, ++it) {
-        const int slot = it & 1;
-        ok = mbar_wait(&sh->full[slot], (it >> 1) & 1u, dead);
+      const uint32_t lbo2 = (uint32_t)Cp8 * 128u;             // 8-key group stride of a key-major chunk
+      const int nkey = (P + 31) >> 5;
+      for (int j = 0; j < nkey && ok; ++j) {
+        const int slot = j % kTcSlots2;
+        ok = mbar_wait(&sh->dzready[j], 0u, dead);
+        if (ok) ok = mbar_wait(&sh->full2[slot], (uint32_t)(j / kTcSlots2) & 1u, dead);
         tc_fence_after();
-        const uint32_t st = smem_u32(stage0 + slot * kTcStageBytes);
-        const uint32_t d = tmem + 256u + (uint32_t)s * 32u;
-        const int ksteps = N >> 4;
-        for (int ks = 0; ks < ksteps; ++ks) {                // 16 key rows j per MMA
-          const uint64_t a_hi = smem_desc(dzh + ks * 4096, 2048, 128);
-          const uint64_t b_hi = smem_desc(st + kTcOffKhi + ks * 256, 128, lbo_k);
-          mma_bf16(d, a_hi, b_hi, idesc2, ks ? 1u : 0u);
+        if (j == 0) PNCE_TR(10);
+        const uint32_t st = smem_u32(stage0 + slot * kTcStage2Bytes);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {                     // 16 keys per MMA
+          const uint64_t a_hi = smem_desc(dzh + (uint32_t)(j * 2 + ks) * 4096u, 2048, 128);
+          const uint64_t b_hi = smem_desc(st + (uint32_t)ks * 2u * lbo2, lbo2, 128);
+          mma_bf16(tmem + 256u, a_hi, b_hi, idesc2, (j | ks) ? 1u : 0u);
           if (x3) {
-            const uint64_t a_lo = smem_desc(dzl + ks * 4096, 2048, 128);
-            const uint64_t b_lo = smem_desc(st + kTcOffKlo + ks * 256, 128, lbo_k);
-            mma_bf16(d, a_lo, b_hi, idesc2, 1u);
-            mma_bf16(d, a_hi, b_lo, idesc2, 1u);
+            const uint64_t a_lo = smem_desc(dzl + (uint32_t)(j * 2 + ks) * 4096u, 2048, 128);
+            const uint64_t b_lo = smem_desc(st + 16384u + (uint32_t)ks * 2u * lbo2, lbo2, 128);
+            mma_bf16(tmem + 256u, a_lo, b_hi, idesc2, 1u);
+            mma_bf16(tmem + 256u, a_hi, b_lo, idesc2, 1u);
           }
         }
-        mma_commit(&sh->empty[slot]);
+        mma_commit(&sh->empty2[slot]);
       }
       mma_commit(&sh->dqfull);
       PNCE_TR(11);
@@ -349,7 +446,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       const int nch = (P + 31) >> 5;                          // chunks that hold real columns
       const int chd = gi >> 5;                                // chunk holding this warp's diagonal (warp-uniform)
       PNCE_TR(1);
-      bool ok = mbar_wait(&sh->zfull, 0u, dead);
+      mbar_wait(&sh->zfull, 0u, dead);
       tc_fence_after();
       PNCE_TR(2);
       // ---- pass A: row sum of exp2, diagonal ----
@@ -366,35 +463,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       float rowloss = rowok ? (lse2 - yd) * kLn2 : 0.f;        // :94, labels = arange
       if (badrow && rowok) rowloss = __int_as_float(0x7fc00000);
       PNCE_TR(3);
-      // ---- pass B: dZ (pre-divided by ||k_j||) -> smem A operand, s_i ----
+      // ---- pass B: dZ (pre-divided by ||k_j||) -> smem A operand chunk by chunk, s_i ----
       float s2 = 0.f;
       const uint32_t rowoff = (uint32_t)(i >> 3) * 128u + (uint32_t)(i & 7) * 16u;
-      if (need_clamp) tc_row_pass_b<true>(trow, nch, invk_s, a, cl, lse2, coef, x3, dzhi, dzlo, rowoff, s2);
-      else tc_row_pass_b<false>(trow, nch, invk_s, a, cl, lse2, coef, x3, dzhi, dzlo, rowoff, s2);
-      // the "- I" of (softmax - I): fix this row's diagonal element (same thread wrote it above)
-      if (rowok) {
-        const bool pass = !need_clamp || fabsf(ydr) <= cl;
-        const float d = pass ? (ex2f(yd - lse2) - 1.f) * coef : 0.f;
-        if (pass) s2 = fmaf(-coef, ydr, s2);
-        const float ddv = d * wd;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(ddv);
-        const uint32_t off = (uint32_t)(gi >> 3) * 2048u + rowoff + (uint32_t)(gi & 7) * 2u;
-        *reinterpret_cast<__nv_bfloat16*>(dzhi + off) = hi;
-        if (x3) *reinterpret_cast<__nv_bfloat16*>(dzlo + off) = __float2bfloat16_rn(ddv - __bfloat162float(hi));
-      }
-      // padding chunks of the A operand must be finite (they meet all-zero key rows)
-      for (int ch = nch; ch < (N >> 5); ++ch) {
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          const uint32_t off = (uint32_t)(ch * 4 + g8) * 2048u + rowoff;
-          *reinterpret_cast<uint4*>(dzhi + off) = make_uint4(0u, 0u, 0u, 0u);
-          if (x3) *reinterpret_cast<uint4*>(dzlo + off) = make_uint4(0u, 0u, 0u, 0u);
-        }
-      }
+      TcDiag dg;
+      dg.rowok = rowok;
+      dg.pass = !need_clamp || fabsf(ydr) <= cl;
+      dg.d_w = dg.pass ? (ex2f(yd - lse2) - 1.f) * coef * wd : 0.f;
+      dg.off = (uint32_t)(gi >> 3) * 2048u + rowoff + (uint32_t)(gi & 7) * 2u;
+      if (need_clamp) tc_row_pass_b<true>(trow, nch, invk_s, a, cl, lse2, coef, x3, dzhi, dzlo, rowoff, chd, dg, sh->dzready, s2);
+      else tc_row_pass_b<false>(trow, nch, invk_s, a, cl, lse2, coef, x3, dzhi, dzlo, rowoff, chd, dg, sh->dzready, s2);
+      if (rowok && dg.pass) s2 = fmaf(-coef, ydr, s2);         // the diagonal's "- I" term of sum_j dZ_ij y_ij
       const float s_i = s2 * kLn2;                              // sum_j dZ_ij z_ij
-      fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&sh->dzready);
       PNCE_TR(4);
       // row losses: warp shuffle, then one partial per CTA (deterministic order)
       rowloss = warp_sum(rowloss);
@@ -406,43 +487,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       //   dx = dq*sc - q_raw * (sc^2 s_i)       with dq = acc / tau
       const float c1 = inv_tau * sc;
       const float c2 = noproj ? 0.f : sc * sc * s_i;
-      const float* __restrict__ qrow = L.qT + (size_t)b * C * N + gi;
-      float* __restrict__ dxrow = L.dxT + (size_t)b * C * P + gi;
-      // raw q values are prefetched two chunks ahead (static double buffer)
-      float qa[32], qb[32];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        qa[k] = (rowok && k < C) ? __ldcg(qrow + (size_t)k * N) : 0.f;
-        qb[k] = (rowok && 32 + k < C) ? __ldcg(qrow + (size_t)(32 + k) * N) : 0.f;
-      }
-      if (ok) ok = mbar_wait(&sh->dqfull, 0u, dead);
-      tc_fence_after();
+      const int gsafe = rowok ? gi : 0;
+      const float* __restrict__ qrow = L.qT + (size_t)b * C * N + gsafe;
+      float* __restrict__ dxrow = L.dxT + (size_t)b * C * N + gsafe;        // dxpitch == N on this path
       PNCE_TR(5);
-      for (int s = 0; s < nstage; s += 2) {
-#pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-          const int sc_ = s + hb;
-          if (sc_ < nstage) {
-            float (&qv)[32] = hb ? qb : qa;
-            uint32_t r[32];
-            tmem_ld32(trow + 256u + sc_ * 32, r);
-            tmem_ld_wait();
-            float out[32];
-#pragma unroll
-            for (int k = 0; k < 32; ++k) out[k] = fmaf(-qv[k], c2, __uint_as_float(r[k]) * c1);
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const int c = (sc_ + 2) * 32 + k;
-              qv[k] = (rowok && c < C) ? __ldcg(qrow + (size_t)c * N) : 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const int c = sc_ * 32 + k;
-              if (rowok && c < C) dxrow[(size_t)c * P] = out[k];
-            }
-          }
-        }
-      }
+      if (N == 256) tc_dq_epilogue<256>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, &sh->dqfull, dead);
+      else tc_dq_epilogue<128>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, &sh->dqfull, dead);
       PNCE_TR(6);
       tc_fence_before();
     }

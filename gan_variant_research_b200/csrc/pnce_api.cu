@@ -95,12 +95,10 @@ static size_t carve_fused(const pnce_layer_t* layers, int n_layers, int B, bool 
     L.sid = cv.take<int>(a.P);
     L.perm = cv.take<int>(a.P);
     L.rank = cv.take<int>(a.P);
-    L.ustart = cv.take<int>(a.P + 1);
-    L.bitmap = cv.take<unsigned>(L.nwords);
-    L.prefix = cv.take<unsigned>(L.nwords);
     L.cslot = cv.take<int>((size_t)(L.HW + kTilePos - 1) / kTilePos + 1);
     L.qinv = cv.take<float>((size_t)B * a.P);
-    L.dxT = cv.take<float>(rows);
+    L.dxpitch = tc ? (a.P + 127) / 128 * 128 : a.P;
+    L.dxT = cv.take<float>((size_t)B * a.C * L.dxpitch);
     L.dq_rows = nullptr;
     if (!tc) {
       L.nparts = L.ntiles;
@@ -119,6 +117,8 @@ static size_t carve_fused(const pnce_layer_t* layers, int n_layers, int B, bool 
         L.qlo = cv.take<__nv_bfloat16>(blob);
         L.klo = cv.take<__nv_bfloat16>(blob);
       }
+      L.k2hi = cv.take<__nv_bfloat16>(blob);
+      if (x3) L.k2lo = cv.take<__nv_bfloat16>(blob);
       L.qT = cv.take<float>((size_t)B * a.C * L.Ppad);
       L.qss = cv.take<float>((size_t)B * L.nchunk * L.Ppad);
       L.kss = cv.take<float>((size_t)B * L.nchunk * L.Ppad);
@@ -186,7 +186,9 @@ static int launch_loss_simt(const Params& p, cudaStream_t st) {
   int rc = set_smem(k_loss_simt, smem);
   if (rc != PNCE_OK) return rc;
   if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
-  k_loss_simt<<<(unsigned)acc, kThreads, smem, st>>>(p, m);
+  Params q = p;
+  q.total_ctas = (unsigned)acc;
+  k_loss_simt<<<(unsigned)acc, kThreads, smem, st>>>(q, m);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
@@ -210,7 +212,7 @@ static int launch_gather_tc(const Params& p, cudaStream_t st) {
   long long acc = 0;
   for (int l = 0; l < p.n_layers; ++l) {
     m.start[l] = acc;
-    acc += 2ll * p.B * p.L[l].nchunk;
+    acc += 2ll * p.bn * p.L[l].nchunk;
   }
   m.start[p.n_layers] = acc;
   if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
@@ -225,7 +227,7 @@ static int launch_loss_tc(const Params& p, cudaStream_t st) {
   long long acc = 0;
   for (int l = 0; l < p.n_layers; ++l) {
     m.start[l] = acc;
-    acc += (long long)p.B * (p.L[l].Ppad / 128);
+    acc += (long long)p.bn * (p.L[l].Ppad / 128);
   }
   m.start[p.n_layers] = acc;
   int rc = set_smem(k_loss_tc, kTcSmemBytes);
@@ -236,105 +238,109 @@ static int launch_loss_tc(const Params& p, cudaStream_t st) {
   return PNCE_OK;
 }
 
+
 // Experiment knobs (pnce_debug_set; not part of pnce.h).  0 = library default.
 struct DebugKnobs {
-  int dense_variant = 0;     // 0: flat tiles (default), 1: warp-per-segment LSU kernel, 2: persistent bulk-copy kernel
   int dense_flags = 0;       // bit 0: skip the patch phase (fill ceiling)
-  int dense_ctas_per_sm = 0;
-  int flat_threads = 0;      // 64: 64-thread tiles in the flat dense kernel (default 128)
+  int fwd_chunks = 0;        // n > 1: cut the tensor-core forward into n chunks, loss(c) on an aux stream || gather(c+1)
   long long* trace = nullptr;
 };
 static DebugKnobs g_dbg;
 
-static int launch_dense_warp(const Params& p, cudaStream_t st) {
-  DenseMap m;
-  memset(&m, 0, sizeof(m));
-  const int vec = (p.dtype == PNCE_F32) ? 4 : 8;
-  long long acc = 0;
-  for (int l = 0; l < p.n_layers; ++l) {
-    const LayerDev& L = p.L[l];
-    m.start[l] = acc;
-    m.segs[l] = (L.HW + kSegPos - 1) / kSegPos;
-    m.vec_ok[l] = (L.HW % vec == 0) && ((reinterpret_cast<uintptr_t>(L.dtgt) & 15u) == 0);
-    acc += (long long)p.B * L.C * m.segs[l];
+// ---- chunked tensor-core forward ---------------------------------------------------------------
+// The gather is HBM-bound and the tcgen05 loss kernel is not, so the batch is cut into chunks and
+// loss(chunk c) runs on an auxiliary stream while gather(chunk c+1) runs on the caller's stream:
+//   st : prep, gather(0), gather(1), ...            aux: loss(0), loss(1), ...   (loss(c) after gather(c))
+// Fork/join with events only -- no host sync, and the pattern is CUDA-graph capturable.
+struct AuxStreams {
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev[16] = {};
+  cudaEvent_t join = nullptr;
+  int device = -1;
+};
+static thread_local AuxStreams g_aux;
+
+static int aux_streams(AuxStreams** out) {
+  int dev = 0;
+  PNCE_CUDA(cudaGetDevice(&dev));
+  if (g_aux.aux == nullptr || g_aux.device != dev) {
+    int lo = 0, hi = 0;
+    PNCE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    PNCE_CUDA(cudaStreamCreateWithPriority(&g_aux.aux, cudaStreamNonBlocking, hi));
+    for (auto& e : g_aux.ev) PNCE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    PNCE_CUDA(cudaEventCreateWithFlags(&g_aux.join, cudaEventDisableTiming));
+    g_aux.device = dev;
   }
-  m.start[p.n_layers] = acc;
-  m.total = acc;
-  const long long ctas_needed = (acc + (kThreads / 32) - 1) / (kThreads / 32);
-  // persistent grid = exactly the CTAs that are co-resident (a partial second wave of a
-  // persistent kernel would run alone at the end)
-  static int occ = 0;
-  if (occ == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dense_bwd<float>, kThreads, 0) !=
-                       cudaSuccess || occ < 1))
-    occ = 4;
-  const int per_sm = g_dbg.dense_ctas_per_sm > 0 ? g_dbg.dense_ctas_per_sm : occ;
-  long long grid = (long long)sm_count() * per_sm;
-  if (grid > ctas_needed) grid = ctas_needed;
-  if (p.dtype == PNCE_F32) k_dense_bwd<float><<<(unsigned)grid, kThreads, 0, st>>>(p, m);
-  else if (p.dtype == PNCE_F16) k_dense_bwd<__half><<<(unsigned)grid, kThreads, 0, st>>>(p, m);
-  else k_dense_bwd<__nv_bfloat16><<<(unsigned)grid, kThreads, 0, st>>>(p, m);
-  PNCE_CUDA(cudaGetLastError());
+  *out = &g_aux;
+  return PNCE_OK;
+}
+
+static int forward_tc(Params& p, cudaStream_t st) {
+  int rc = launch_prep(p, st);
+  if (rc != PNCE_OK) return rc;
+  int ctas_per_image = 0;
+  for (int l = 0; l < p.n_layers; ++l) ctas_per_image += p.L[l].Ppad / 128;
+  // Chunking is OFF by default: on B200 the 14-image chunks that fill the SMs once make the gather
+  // pay ~30% wave quantisation and the overlap does not win it back (measured: 0.70 ms vs 0.50 ms
+  // forward at B=64).  Kept behind the debug knob for larger batches.
+  int nchunk = g_dbg.fwd_chunks > 1 ? g_dbg.fwd_chunks : 1;
+  if (nchunk > 16) nchunk = 16;
+  if (nchunk > p.B) nchunk = p.B;
+  int per = (p.B + nchunk - 1) / nchunk;
+  nchunk = (p.B + per - 1) / per;
+  p.total_ctas = (unsigned)(p.B * ctas_per_image);
+  if (nchunk == 1) {
+    p.b0 = 0; p.bn = p.B;
+    rc = launch_gather_tc(p, st);
+    if (rc != PNCE_OK) return rc;
+    return launch_loss_tc(p, st);
+  }
+  AuxStreams* ax = nullptr;
+  rc = aux_streams(&ax);
+  if (rc != PNCE_OK) return rc;
+  for (int c = 0; c < nchunk; ++c) {
+    p.b0 = c * per;
+    p.bn = (p.b0 + per <= p.B) ? per : p.B - p.b0;
+    rc = launch_gather_tc(p, st);
+    if (rc != PNCE_OK) return rc;
+    PNCE_CUDA(cudaEventRecord(ax->ev[c], st));
+    PNCE_CUDA(cudaStreamWaitEvent(ax->aux, ax->ev[c], 0));
+    rc = launch_loss_tc(p, ax->aux);
+    if (rc != PNCE_OK) return rc;
+  }
+  PNCE_CUDA(cudaEventRecord(ax->join, ax->aux));
+  PNCE_CUDA(cudaStreamWaitEvent(st, ax->join, 0));
   return PNCE_OK;
 }
 
 static int launch_dense(const Params& p, cudaStream_t st) {
-  // the bulk-copy kernel needs every row start and every chunk to be 16-byte tileable
   const size_t es = dtype_size(p.dtype);
-  bool tma_ok = g_dbg.dense_variant != 1;
-  for (int l = 0; l < p.n_layers && tma_ok; ++l) {
-    const LayerDev& L = p.L[l];
-    if (((size_t)L.HW * es) % 16 != 0 || (reinterpret_cast<uintptr_t>(L.dtgt) & 15u)) tma_ok = false;
-  }
-  if (!tma_ok) return launch_dense_warp(p, st);
-  if (g_dbg.dense_variant != 2) {
-    // default: one small CTA per 8 KB tile, in address order
-    DenseFlatMap f;
-    memset(&f, 0, sizeof(f));
-    long long tot = 0;
-    const int tp = kFlatBytes / (int)es;
-    for (int l = 0; l < p.n_layers; ++l) {
-      f.start[l] = tot;
-      f.tiles[l] = (p.L[l].HW + tp - 1) / tp;
-      tot += (long long)p.B * p.L[l].C * f.tiles[l];
-    }
-    f.start[p.n_layers] = tot;
-    f.flags = g_dbg.dense_flags;
-    if (tot > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
-    const unsigned grid = (unsigned)tot;
-    if (g_dbg.flat_threads == 64) {
-      if (p.dtype == PNCE_F32) k_dense_flat<float, 64><<<grid, 64, 0, st>>>(p, f);
-      else if (p.dtype == PNCE_F16) k_dense_flat<__half, 64><<<grid, 64, 0, st>>>(p, f);
-      else k_dense_flat<__nv_bfloat16, 64><<<grid, 64, 0, st>>>(p, f);
-    } else {
-      if (p.dtype == PNCE_F32) k_dense_flat<float, 128><<<grid, 128, 0, st>>>(p, f);
-      else if (p.dtype == PNCE_F16) k_dense_flat<__half, 128><<<grid, 128, 0, st>>>(p, f);
-      else k_dense_flat<__nv_bfloat16, 128><<<grid, 128, 0, st>>>(p, f);
-    }
-    PNCE_CUDA(cudaGetLastError());
-    return PNCE_OK;
-  }
-  DenseTmaMap m;
-  memset(&m, 0, sizeof(m));
-  long long acc = 0;
+  // default: one small CTA per 8 KB tile, in address order
+  DenseFlatMap f;
+  memset(&f, 0, sizeof(f));
+  bool vec = true;
+  long long tot = 0;
+  const int tp = kFlatBytes / (int)es;
   for (int l = 0; l < p.n_layers; ++l) {
-    const LayerDev& L = p.L[l];
-    m.start[l] = acc;
-    m.chunks[l] = (L.HW + kChunkPos - 1) / kChunkPos;
-    acc += (long long)p.B * L.C * m.chunks[l];
+    f.start[l] = tot;
+    f.tiles[l] = (p.L[l].HW + tp - 1) / tp;
+    // 128-bit copy-out needs every row start and every tile to be 16-byte aligned
+    if ((((size_t)p.L[l].HW * es) % 16 != 0) || (reinterpret_cast<uintptr_t>(p.L[l].dtgt) & 15u)) vec = false;
+    tot += (long long)p.B * p.L[l].C * f.tiles[l];
   }
-  m.start[p.n_layers] = acc;
-  m.total = acc;
-  m.flags = g_dbg.dense_flags;
-  // persistent grid: every CTA takes one contiguous range of items (so it stays inside one column
-  // of equal sample positions as long as possible); 6 CTAs x 32 KB staging per SM
-  const int per_sm = g_dbg.dense_ctas_per_sm > 0 ? g_dbg.dense_ctas_per_sm : 6;
-  long long grid = (long long)sm_count() * per_sm;
-  if (grid > acc) grid = acc;
-  m.per_cta = (acc + grid - 1) / grid;
-  grid = (acc + m.per_cta - 1) / m.per_cta;
-  if (p.dtype == PNCE_F32) k_dense_tma<float><<<(unsigned)grid, kDenseTmaThreads, 0, st>>>(p, m);
-  else if (p.dtype == PNCE_F16) k_dense_tma<__half><<<(unsigned)grid, kDenseTmaThreads, 0, st>>>(p, m);
-  else k_dense_tma<__nv_bfloat16><<<(unsigned)grid, kDenseTmaThreads, 0, st>>>(p, m);
+  f.start[p.n_layers] = tot;
+  f.flags = g_dbg.dense_flags;
+  if (tot > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+  const unsigned grid = (unsigned)tot;
+  if (vec) {
+    if (p.dtype == PNCE_F32) k_dense_flat<float, 128, true><<<grid, 128, 0, st>>>(p, f);
+    else if (p.dtype == PNCE_F16) k_dense_flat<__half, 128, true><<<grid, 128, 0, st>>>(p, f);
+    else k_dense_flat<__nv_bfloat16, 128, true><<<grid, 128, 0, st>>>(p, f);
+  } else {
+    if (p.dtype == PNCE_F32) k_dense_flat<float, 128, false><<<grid, 128, 0, st>>>(p, f);
+    else if (p.dtype == PNCE_F16) k_dense_flat<__half, 128, false><<<grid, 128, 0, st>>>(p, f);
+    else k_dense_flat<__nv_bfloat16, 128, false><<<grid, 128, 0, st>>>(p, f);
+  }
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
@@ -381,11 +387,9 @@ const char* pnce_last_cuda_error(void) { return g_cuda_err; }
 // Experiment hooks (not part of pnce.h).
 int pnce_debug_set(int key, long long value) {
   switch (key) {
-    case 0: g_dbg.dense_variant = (int)value; break;
     case 1: g_dbg.dense_flags = (int)value; break;
-    case 2: g_dbg.dense_ctas_per_sm = (int)value; break;
     case 3: g_dbg.trace = reinterpret_cast<long long*>(value); break;
-    case 4: g_dbg.flat_threads = (int)value; break;
+    case 5: g_dbg.fwd_chunks = (int)value; break;
     default: return PNCE_ERR_ARG;
   }
   return PNCE_OK;
@@ -432,14 +436,9 @@ int pnce_fwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, flo
   p.loss_out = loss_out;
   p.nonfinite = nonfinite;
   p.trace = g_dbg.trace;
+  p.b0 = 0; p.bn = batch;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (tc) {
-    rc = launch_prep(p, st);
-    if (rc != PNCE_OK) return rc;
-    rc = launch_gather_tc(p, st);
-    if (rc != PNCE_OK) return rc;
-    return launch_loss_tc(p, st);
-  }
+  if (tc) return forward_tc(p, st);
   rc = launch_gather(p, n_layers, st);
   if (rc != PNCE_OK) return rc;
   return launch_loss_simt(p, st);
@@ -500,10 +499,8 @@ static size_t carve_sample_bwd(int B, int C, int H, int W, int P, void* ws, Laye
   L.sid = cv.take<int>(P);
   L.perm = cv.take<int>(P);
   L.rank = cv.take<int>(P);
-  L.ustart = cv.take<int>(P + 1);
-  L.bitmap = cv.take<unsigned>(L.nwords);
-  L.prefix = cv.take<unsigned>(L.nwords);
   L.cslot = cv.take<int>((size_t)(L.HW + kTilePos - 1) / kTilePos + 1);
+  L.dxpitch = P;
   L.dxT = cv.take<float>((size_t)B * P * C);
   if (out) *out = L;
   return align_up(cv.off, 256);
@@ -526,7 +523,7 @@ __global__ void __launch_bounds__(kThreads) k_prep_only(const __grid_constant__ 
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
   int N2 = 1;
   while (N2 < p.L[0].P) N2 <<= 1;
-  prep_layer(p.L[0], keys, reinterpret_cast<int*>(keys + N2));
+  prep_layer(p.L[0], keys);
 }
 
 int pnce_sample_bwd(const float* drows, const float* rows, const float* inv, int dtype, int batch,

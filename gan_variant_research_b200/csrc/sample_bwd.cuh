@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(kThreads) k_rows_normbwd(const __grid_constant
   const int i = tile * kRowTile + lane;
   if (i < P) {
     const int slot = L.rank[i];
-    for (int c = warp; c < C; c += 8) L.dxT[((size_t)b * C + c) * P + slot] = st[lane * ldt + c];
+    for (int c = warp; c < C; c += 8) L.dxT[((size_t)b * C + c) * L.dxpitch + slot] = st[lane * ldt + c];
   }
 }
 

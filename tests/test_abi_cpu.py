@@ -49,8 +49,8 @@ def test_workspace_query_and_argument_errors(lib):
     b5 = [(64, 256, 256), (256, 64, 64), (256, 64, 64), (128, 128, 128), (64, 256, 256)]
     assert lib.pnce_workspace_bytes(_layers(b5, 256), 5, 64, ctypes.byref(n)) == 0
     rows = 64 * 256 * (64 + 256 + 256 + 128 + 64) * 4
-    # dxT + (SIMT: 2 fp32 row sets | tensor-core: 4 bf16 operand blobs + raw fp32 q)
-    assert 3 * rows <= n.value <= 4 * rows + (4 << 20)
+    # dxT + (SIMT: 2 fp32 row sets | tensor-core: 6 bf16 operand blobs (q, k, key-major k; hi+lo) + raw fp32 q)
+    assert 3 * rows <= n.value <= 5 * rows + (4 << 20)
     assert lib.pnce_workspace_bytes(_layers(b5, 256), 5, 0, ctypes.byref(n)) == -1       # batch < 1
     assert lib.pnce_workspace_bytes(_layers(b5, 256), 9, 1, ctypes.byref(n)) == -2       # > 8 layers
     assert lib.pnce_workspace_bytes(_layers([(2048, 4, 4)], 16), 1, 1, ctypes.byref(n)) == -2

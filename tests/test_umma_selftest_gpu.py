@@ -58,3 +58,17 @@ def test_mn_major_b_operand(need_cuda, n, k):
                        (128, k // 8 * 128, 2 * 128), n, k, 1)
     assert err == 0
     np.testing.assert_array_equal(d.numpy(), (a @ kmat).numpy())
+
+
+@pytest.mark.parametrize("n,k", [(64, 32), (256, 32), (256, 64), (128, 128)])
+def test_mn_major_b_operand_key_major_blob(need_cuda, n, k):
+    """The gather's second K blob: [j/8][c/8][8 j][8 c] (a chunk of keys x all channels), read
+    MN-major with N = all channels as in phase 2 of k_loss_tc (dQ = dZ K, M128 x N=C x K16)."""
+    g = torch.Generator().manual_seed(11 * n + k)
+    a = torch.randint(-4, 5, (128, k), generator=g).float()
+    kmat = torch.randint(-4, 5, (k, n), generator=g).float()
+    blob = kmat.reshape(k // 8, 8, n // 8, 8).permute(0, 2, 1, 3).contiguous().to(torch.bfloat16)
+    d, err = run_probe(tile_blob(a), blob, (16 * 128, 128, 2 * 16 * 128),
+                       (n // 8 * 128, 128, 2 * (n // 8) * 128), n, k, 1)
+    assert err == 0
+    np.testing.assert_array_equal(d.numpy(), (a @ kmat).numpy())
