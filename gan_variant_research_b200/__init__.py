@@ -14,12 +14,14 @@ from .patchnce import (  # noqa: F401
     fused_patchnce,
     install_reference_shim,
     patch_count,
+    patchnce_with_head,
     poll_nonfinite_warnings,
     rows_patchnce,
 )
+from .dp import allreduce_head_grads, broadcast_patch_ids, shard_batch  # noqa: F401
 
 __all__ = [
     "PatchNCELoss", "PatchSampleF", "compute_patchnce_loss", "fused_patchnce", "rows_patchnce",
     "draw_patch_ids", "patch_count", "install_reference_shim", "poll_nonfinite_warnings",
-    "DEFAULT_MATH",
+    "DEFAULT_MATH", "patchnce_with_head", "allreduce_head_grads", "broadcast_patch_ids", "shard_batch",
 ]

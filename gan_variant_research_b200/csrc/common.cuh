@@ -56,6 +56,7 @@ struct Params {
   int n_layers, B, dtype, math;
   float tau;
   int side0;                 // first side the gather launch covers: 0 = src+tgt, 1 = tgt only
+  int raw;                   // module-split API: 1 = rows are the raw patches (no L2 normalisation)
   int b0, bn;                // images [b0, b0+bn) of the batch are covered by this launch (chunked forward)
   unsigned total_ctas;       // loss CTAs over all chunks: the one that arrives last finalises
   float* loss_out;           // [1 + n_layers]

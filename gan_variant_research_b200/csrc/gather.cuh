@@ -68,7 +68,7 @@ __device__ void prep_layer(const LayerDev& L, unsigned long long* keys) {
 //   tile staged in smem [32][C+1] so the normalised rows leave as coalesced 128 B row segments.
 // --------------------------------------------------------------------------------------------
 template <typename T>
-__device__ void gather_tile(const LayerDev& L, int B, int side0, long long local, float* tile_s, float* red_s) {
+__device__ void gather_tile(const LayerDev& L, int B, int side0, int raw, long long local, float* tile_s, float* red_s) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nt = L.ntiles;
   const int tile = (int)(local % nt);
@@ -107,7 +107,7 @@ __device__ void gather_tile(const LayerDev& L, int B, int side0, long long local
     float nrm = sqrtf(tot);
     float den = fmaxf(nrm, kNormEps);                          // clamp_min(norm, eps)
     if (!(nrm == nrm)) den = nrm;                              // NaN norm stays NaN (fmaxf would hide it)
-    red_s[512 + lane] = den;
+    red_s[512 + lane] = raw ? 1.0f : den;
     if (side == 1 && ok && L.qinv != nullptr) {
       float inv = (nrm >= kNormEps) ? 1.0f / nrm : -1.0f / kNormEps;
       if (anybad) inv = __int_as_float(0x7fc00000);
@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(kThreads) k_gather_prep(const __grid_constant_
   float* tile_s = reinterpret_cast<float*>(smem_raw);
   float* red_s = tile_s + kRowTile * (L.C + 1);
   const long long local = blk - m.start[l];
-  if (p.dtype == PNCE_F32) gather_tile<float>(L, p.B, p.side0, local, tile_s, red_s);
-  else if (p.dtype == PNCE_F16) gather_tile<__half>(L, p.B, p.side0, local, tile_s, red_s);
-  else gather_tile<__nv_bfloat16>(L, p.B, p.side0, local, tile_s, red_s);
+  if (p.dtype == PNCE_F32) gather_tile<float>(L, p.B, p.side0, p.raw, local, tile_s, red_s);
+  else if (p.dtype == PNCE_F16) gather_tile<__half>(L, p.B, p.side0, p.raw, local, tile_s, red_s);
+  else gather_tile<__nv_bfloat16>(L, p.B, p.side0, p.raw, local, tile_s, red_s);
 }
 
 }  // namespace pnce

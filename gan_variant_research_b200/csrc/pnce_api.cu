@@ -486,6 +486,7 @@ int pnce_sample_fwd(const void* feat, int dtype, int batch, int C, int H, int W,
   L.qn = rows_out;
   L.qinv = inv_out;
   p.side0 = 1;                       // only the "tgt" side exists here
+  p.raw = (inv_out == nullptr) ? 1 : 0;
   return launch_gather(p, 0, static_cast<cudaStream_t>(stream));
 }
 
@@ -534,7 +535,8 @@ int pnce_sample_bwd(const float* drows, const float* rows, const float* inv, int
   a.C = C; a.H = H; a.W = W; a.P = P;
   int rc = check_layers(&a, 1, batch);
   if (rc != PNCE_OK) return rc;
-  if (!drows || !rows || !inv || !ids || !dfeat || dtype < PNCE_F32 || dtype > PNCE_BF16) return PNCE_ERR_ARG;
+  if (!drows || !ids || !dfeat || dtype < PNCE_F32 || dtype > PNCE_BF16) return PNCE_ERR_ARG;
+  if ((rows == nullptr) != (inv == nullptr)) return PNCE_ERR_ARG;       // both NULL = raw rows (no normalisation)
   if (reinterpret_cast<uintptr_t>(dfeat) & (dtype_size(dtype) - 1)) return PNCE_ERR_ALIGN;
   if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
   Params p;
@@ -545,6 +547,7 @@ int pnce_sample_bwd(const float* drows, const float* rows, const float* inv, int
   L.ids = reinterpret_cast<const long long*>(ids);
   L.qinv = const_cast<float*>(inv);
   L.dtgt = dfeat;
+  p.raw = (rows == nullptr) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int n2 = 1;
   while (n2 < P) n2 <<= 1;

@@ -19,6 +19,10 @@ __global__ void __launch_bounds__(kThreads) k_rows_normbwd(const __grid_constant
     const int r = warp * 4 + rr, i = tile * kRowTile + r;
     if (i >= P) continue;                                       // warp-uniform
     const float* g = drows + ((size_t)b * P + i) * C;
+    if (p.raw) {                                                // rows were the raw patches: dx = g
+      for (int c = lane; c < C; c += 32) st[r * ldt + c] = g[c];
+      continue;
+    }
     const float* x = rows + ((size_t)b * P + i) * C;
     const float inv = L.qinv[(size_t)b * P + i];
     float s = 0.f;

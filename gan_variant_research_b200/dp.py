@@ -1,0 +1,68 @@
+"""Data-parallel plumbing for the PatchNCE path: one process per GPU.
+
+The path shards on the batch dimension and needs NO collective in the reference-exact mode:
+negatives are per image (patchnce_cut.py:83-94), the dense ``d tgt_feat`` stays on the rank that
+owns the image.  Two things have to agree across ranks:
+
+* the ``patch_ids`` of every layer -- the reference shares ONE draw per layer across the whole batch
+  (patchnce_cut.py:63): seed the id generator identically on all ranks, or ``broadcast_patch_ids``;
+* the loss scale -- each rank averages over its own B/N images, so gradients are averaged over
+  ranks (what DDP does); for the dense feature gradients this is a local ``1 / world_size`` factor.
+
+Only the netF head (north-star extension, absent from the reference) owns parameters whose
+gradients must be summed: ``allreduce_head_grads`` does it as ONE flat all-reduce (<= 2.1 MB, latency
+bound on NVLink 5) on the current stream; torch.distributed (NCCL on GPUs, gloo in the CPU tests)
+is plumbing here.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def _world(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def shard_batch(tensors: Iterable[torch.Tensor], rank: Optional[int] = None, world: Optional[int] = None,
+                group=None) -> List[torch.Tensor]:
+    """This rank's contiguous slice of the batch dimension of every tensor (equal shards)."""
+    world = _world(group) if world is None else world
+    rank = (dist.get_rank(group) if world > 1 else 0) if rank is None else rank
+    out = []
+    for t in tensors:
+        b = t.shape[0]
+        if b % world:
+            raise ValueError(f"batch {b} is not divisible by world size {world}")
+        per = b // world
+        out.append(t[rank * per:(rank + 1) * per])
+    return out
+
+
+def broadcast_patch_ids(ids: List[torch.Tensor], src: int = 0, group=None) -> List[torch.Tensor]:
+    """Make every rank use rank ``src``'s ids (in place; one small broadcast per layer, <= 32 KB)."""
+    if _world(group) > 1:
+        for t in ids:
+            dist.broadcast(t, src=src, group=group)
+    return ids
+
+
+def allreduce_head_grads(module: torch.nn.Module, group=None, average: bool = True) -> int:
+    """Sum (or average) the gradients of ``module``'s parameters over the ranks with one flat
+    all-reduce.  Returns the number of elements reduced (0 when there is nothing to do)."""
+    world = _world(group)
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if world == 1 or not grads:
+        return 0
+    flat = torch.cat([g.reshape(-1).to(torch.float32) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat.div_(world)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+    return off

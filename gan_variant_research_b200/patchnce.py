@@ -33,6 +33,7 @@ _MATH = {"simt_f32": _lib.MATH_SIMT_F32, "tc_bf16x3": _lib.MATH_TC_BF16X3, "tc_b
 
 #: contraction engine used when a module does not choose one
 DEFAULT_MATH = "tc_bf16x3"
+NORM_EPS = 1e-6          # F.normalize(..., eps=1e-6)   patchnce_cut.py:77-78
 
 
 def _stream_ptr(device) -> int:
@@ -280,8 +281,11 @@ def compute_patchnce_loss(generator, src_images, tgt_images, nce_layers, tempera
 # module split: PatchSampleF and the rows loss
 # ------------------------------------------------------------------------------------------------
 class _SampleFn(torch.autograd.Function):
+    """Random-patch gather (+ L2 normalisation unless ``raw``) of one NCHW map; backward = dense
+    scatter with duplicate ids accumulated.  ``raw=True`` feeds the netF head."""
+
     @staticmethod
-    def forward(ctx, feat, ids):
+    def forward(ctx, feat, ids, raw=False):
         lib = _lib.load()
         f = feat.detach().contiguous()
         b, c, h, w = f.shape
@@ -289,20 +293,26 @@ class _SampleFn(torch.autograd.Function):
         dev = f.device
         with torch.cuda.device(dev):
             rows = torch.empty(b * p, c, dtype=torch.float32, device=dev)
-            inv = torch.empty(b * p, dtype=torch.float32, device=dev)
+            inv = None if raw else torch.empty(b * p, dtype=torch.float32, device=dev)
             _lib.check(lib.pnce_sample_fwd(f.data_ptr(), _DTYPES[f.dtype], b, c, h, w, ids.data_ptr(), p,
-                                           rows.data_ptr(), inv.data_ptr(), _stream_ptr(dev)),
-                       "pnce_sample_fwd")
-        ctx.save_for_backward(rows, inv, ids)
-        ctx.meta = (b, c, h, w, p, f.dtype, dev)
-        ctx.mark_non_differentiable(inv)
-        return rows, inv
+                                           rows.data_ptr(), None if raw else inv.data_ptr(),
+                                           _stream_ptr(dev)), "pnce_sample_fwd")
+        if raw:
+            ctx.save_for_backward(ids)
+        else:
+            ctx.save_for_backward(ids, rows, inv)
+        ctx.meta = (b, c, h, w, p, f.dtype, dev, raw)
+        return rows
 
     @staticmethod
-    def backward(ctx, drows, _dinv):
+    def backward(ctx, drows):
         lib = _lib.load()
-        rows, inv, ids = ctx.saved_tensors
-        b, c, h, w, p, dt, dev = ctx.meta
+        b, c, h, w, p, dt, dev, raw = ctx.meta
+        if raw:
+            (ids,) = ctx.saved_tensors
+            rows = inv = None
+        else:
+            ids, rows, inv = ctx.saved_tensors
         g = drows.detach().to(torch.float32).contiguous()
         nbytes = ctypes.c_size_t(0)
         _lib.check(lib.pnce_sample_bwd_workspace_bytes(b, c, h, w, p, ctypes.byref(nbytes)),
@@ -310,10 +320,11 @@ class _SampleFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
             dfeat = torch.empty(b, c, h, w, dtype=dt, device=dev)
-            _lib.check(lib.pnce_sample_bwd(g.data_ptr(), rows.data_ptr(), inv.data_ptr(), _DTYPES[dt],
+            _lib.check(lib.pnce_sample_bwd(g.data_ptr(), None if raw else rows.data_ptr(),
+                                           None if raw else inv.data_ptr(), _DTYPES[dt],
                                            b, c, h, w, ids.data_ptr(), p, ws.data_ptr(), nbytes.value,
                                            dfeat.data_ptr(), _stream_ptr(dev)), "pnce_sample_bwd")
-        return dfeat, None
+        return dfeat, None, None
 
 
 class _RowsLossFn(torch.autograd.Function):
@@ -404,11 +415,32 @@ class PatchSampleF(nn.Module):
             else:
                 ids = draw_patch_ids(feat, num_patches)
             if self.use_mlp:
-                raise NotImplementedError("netF head kernels land in a later milestone")
-            rows, _ = _SampleFn.apply(feat, ids)
+                # gather (libpnce) -> Linear-ReLU-Linear -> x / max(||x||, 1e-6)
+                raw = _SampleFn.apply(feat, ids, True)
+                mlp = getattr(self, f"mlp_{feat_id}")
+                rows = torch.nn.functional.normalize(mlp(raw), dim=1, eps=NORM_EPS)
+            else:
+                rows = _SampleFn.apply(feat, ids, False)
             return_feats.append(rows)
             return_ids.append(ids)
         return return_feats, return_ids
+
+
+def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0.07, num_patches=256,
+                       patch_ids=None, math: Optional[str] = None):
+    """North-star composition:
+    ``feat_k, ids = netF(src_feats, num_patches, patch_ids)`` (no grad into k, as upstream CUT and the
+    reference's ``detach`` :142), ``feat_q, _ = netF(tgt_feats, num_patches, ids)``, then
+    ``mean_l PatchNCELoss(feat_q_l, feat_k_l)``.  Returns ``(loss, ids)``."""
+    with torch.no_grad():
+        feat_k, ids = netF(src_feats, num_patches, patch_ids)
+    feat_q, _ = netF(tgt_feats, num_patches, ids)
+    batch = tgt_feats[0].shape[0]
+    total = None
+    for q, k in zip(feat_q, feat_k):
+        l = rows_patchnce(q, k, temperature, num_patches, batch, math)
+        total = l if total is None else total + l
+    return total / len(feat_q), ids
 
 
 def install_reference_shim():

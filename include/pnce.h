@@ -90,12 +90,14 @@ int pnce_bwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int
 
 /* PatchSampleF(use_mlp=False) forward for one map: rows_out (B*P, C) fp32 = L2-normalised patches
  * in ids order, inv_out (B*P) = 1/||x|| (negative -1/eps when ||x|| < eps, NaN for a non-finite
- * row).                                                                  patchnce_cut.py:53-78 */
+ * row).  inv_out == NULL selects the RAW gather (no normalisation) that feeds the netF head.
+ *                                                                         patchnce_cut.py:53-78 */
 int pnce_sample_fwd(const void* dev_feat, int dtype, int batch, int C, int H, int W,
                     const int64_t* dev_ids, int P, float* dev_rows_out, float* dev_inv_out,
                     void* stream);
 
-/* Backward of pnce_sample_fwd: d rows (B*P, C) fp32 -> dense d feat (B,C,H,W) in `dtype`.       */
+/* Backward of pnce_sample_fwd: d rows (B*P, C) fp32 -> dense d feat (B,C,H,W) in `dtype`.
+ * dev_rows == dev_inv == NULL: backward of the raw gather (pure scatter, duplicates accumulated). */
 int pnce_sample_bwd_workspace_bytes(int batch, int C, int H, int W, int P, size_t* bytes);
 int pnce_sample_bwd(const float* dev_drows, const float* dev_rows, const float* dev_inv, int dtype,
                     int batch, int C, int H, int W, const int64_t* dev_ids, int P,

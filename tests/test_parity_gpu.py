@@ -332,3 +332,66 @@ def test_empty_and_mismatched_inputs(pn):
     torch.manual_seed(1)
     l1 = pn.PatchNCELoss(0.07, 8)([a], [a.clone()])
     assert l2.item() == pytest.approx(l1.item() / 2, rel=1e-6)
+
+
+def _head_problem(seed, b, shapes, p):
+    g = torch.Generator().manual_seed(seed)
+    src = [torch.randn(b, *s, generator=g) for s in shapes]
+    tgt = [torch.randn(b, *s, generator=g) for s in shapes]
+    ids = [torch.randint(0, s[1] * s[2], (min(p, s[1] * s[2]),), generator=g) for s in shapes]
+    return src, tgt, ids
+
+
+@pytest.mark.parametrize("nc", [64, 256])
+def test_netf_head_matches_the_oracle(pn, orc, nc):
+    """North-star PatchSampleF(use_mlp=True) + PatchNCELoss(feat_q, feat_k): loss, dense d tgt and
+    the head gradients against the oracle's torch restatement (PARITY UNPINNED by the reference,
+    which has no head: SURVEY.md section 8 row a13).  Tolerance 1e-3 relative (north_star)."""
+    shapes = [(64, 32, 32), (128, 16, 16), (24, 20, 12)]
+    src, tgt, ids = _head_problem(123, 3, shapes, 64)
+    torch.manual_seed(5)
+    netF = pn.PatchSampleF(use_mlp=True, nc=nc, init_gain=0.3)
+    t = [x.cuda().requires_grad_() for x in tgt]
+    idd = [i.cuda() for i in ids]
+    loss, rid = pn.patchnce_with_head(netF, [x.cuda() for x in src], t, 0.07, 64, idd)
+    (loss * 2.0).backward()
+    assert all(torch.equal(a, b) for a, b in zip(rid, idd))
+    heads = []
+    for l in range(len(shapes)):
+        mlp = getattr(netF, f"mlp_{l}")
+        heads.append(tuple(x.detach().cpu().clone().requires_grad_()
+                           for x in (mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias)))
+    tc = [x.clone().requires_grad_() for x in tgt]
+    want = orc.patchnce_head_loss_torch(src, tc, ids, heads)
+    (want * 2.0).backward()
+    assert loss.item() == pytest.approx(want.item(), rel=1e-3)
+    for l in range(len(shapes)):
+        assert_grad_close(t[l].grad.cpu().numpy(), tc[l].grad.numpy(), 1e-3, f"d tgt layer {l}", ids=ids[l])
+        mlp = getattr(netF, f"mlp_{l}")
+        for got, w, name in zip((mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias), heads[l],
+                                ("W1", "b1", "W2", "b2")):
+            assert_grad_close(got.grad.cpu().numpy(), w.grad.numpy(), 1e-3, f"d{name} layer {l}")
+
+
+def test_netf_head_virtual_shard_law(pn):
+    """SURVEY.md 8e with the head: same ids, batch split in two, head gradients averaged over the
+    'ranks' equal the full-batch gradients (what allreduce_head_grads computes across GPUs)."""
+    shapes = [(32, 16, 16), (48, 8, 8)]
+    src, tgt, ids = _head_problem(9, 4, shapes, 32)
+    torch.manual_seed(2)
+    netF = pn.PatchSampleF(use_mlp=True, nc=64, init_gain=0.3)
+    idd = [i.cuda() for i in ids]
+
+    def run(sl):
+        netF.zero_grad()
+        t = [x[sl].cuda().requires_grad_() for x in tgt]
+        loss, _ = pn.patchnce_with_head(netF, [x[sl].cuda() for x in src], t, 0.07, 32, idd)
+        loss.backward()
+        return loss.detach(), [p.grad.clone() for p in netF.parameters()]
+
+    full, gfull = run(slice(0, 4))
+    la, ga = run(slice(0, 2))
+    lb, gb = run(slice(2, 4))
+    assert ((la + lb) / 2).item() == pytest.approx(full.item(), rel=1e-5)
+    for a, b, f in zip(ga, gb, gfull):
+        torch.testing.assert_close((a + b) / 2, f, rtol=2e-4, atol=1e-7)
