@@ -11,6 +11,7 @@ from .patchnce import (  # noqa: F401
     PatchSampleF,
     compute_patchnce_loss,
     draw_patch_ids,
+    fused_head_supported,
     fused_patchnce,
     install_reference_shim,
     patch_count,

@@ -15,6 +15,7 @@ EXPORTS = [
     "pnce_abi_version", "pnce_status_string", "pnce_last_cuda_error", "pnce_workspace_bytes",
     "pnce_fwd", "pnce_bwd", "pnce_sample_fwd", "pnce_sample_bwd_workspace_bytes",
     "pnce_sample_bwd", "pnce_rows_loss_workspace_bytes", "pnce_rows_loss_fwd_bwd", "pnce_selftest_umma",
+    "pnce_head_workspace_bytes", "pnce_head_fwd", "pnce_head_bwd",
 ]
 
 
@@ -25,6 +26,11 @@ class PnceLayer(ctypes.Structure):
         ("ids", ctypes.c_void_p),
         ("C", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("P", ctypes.c_int32),
     ]
+
+
+class PnceHead(ctypes.Structure):
+    """struct pnce_head (include/pnce.h)."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("w1", "b1", "w2", "b2", "dw1", "db1", "dw2", "db2")]
 
 
 class PnceError(RuntimeError):
@@ -56,12 +62,17 @@ def load():
     lib.pnce_sample_bwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, sz, vp, vp]
     lib.pnce_rows_loss_workspace_bytes.argtypes = [i32, i32, i32, ctypes.POINTER(sz)]
     lib.pnce_rows_loss_fwd_bwd.argtypes = [vp, vp, i32, i32, i32, f32, i32, vp, sz, vp, vp, vp, vp, vp]
+    lib.pnce_head_workspace_bytes.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, ctypes.POINTER(sz)]
+    lib.pnce_head_fwd.argtypes = [ctypes.POINTER(PnceLayer), ctypes.POINTER(PnceHead), i32, i32, i32, i32, f32, i32,
+                                  vp, sz, vp, vp, vp]
+    lib.pnce_head_bwd.argtypes = [ctypes.POINTER(PnceLayer), ctypes.POINTER(PnceHead), i32, i32, i32, i32, i32,
+                                  vp, sz, vp, vp]
     u32 = ctypes.c_uint
     lib.pnce_selftest_umma.argtypes = [vp, sz, vp, sz, u32, u32, u32, u32, u32, u32, i32, i32, i32, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("pnce_status_string", "pnce_last_cuda_error"):
             getattr(lib, name).restype = i32
-    if lib.pnce_abi_version() != 1:
+    if lib.pnce_abi_version() != 2:
         raise PnceError("libpnce.so ABI version mismatch")
     _lib = lib
     return lib

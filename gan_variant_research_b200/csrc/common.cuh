@@ -46,6 +46,9 @@ struct LayerDev {
   __nv_bfloat16* klo;
   __nv_bfloat16* k2hi;       // the same K values, key-major  [B][Ppad/8][Cp/8][8][8]  (phase-2 B operand)
   __nv_bfloat16* k2lo;
+  __nv_bfloat16* dyhi;       // head mode: d loss / d head output as a row blob (then dxT is not written)
+  __nv_bfloat16* dylo;
+  int head_src_rows;         // head mode gather: the src side is written as a row blob too (into khi/klo)
   float* qT;                 // [B][C][Ppad] raw fp32 target patches (transposed)
   float* qss;                // [B][nchunk][Ppad] partial sums of squares (NaN: non-finite element)
   float* kss;

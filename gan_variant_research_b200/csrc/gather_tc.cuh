@@ -48,15 +48,15 @@ __device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long loca
     ss = fmaf(v[k], v[k], ss);
     bad |= !isfinite(v[k]);
   }
-  float* ssout = (side ? L.qss : L.kss) + ((size_t)b * nchunk + s) * Ppad + p;
-  *ssout = bad ? __int_as_float(0x7fc00000) : ss;
+  float* ssbase = side ? L.qss : L.kss;                      // NULL in head mode (the head's output is normalised)
+  if (ssbase != nullptr) ssbase[((size_t)b * nchunk + s) * Ppad + p] = bad ? __int_as_float(0x7fc00000) : ss;
   __nv_bfloat16* hi_base = side ? L.qhi : L.khi;
   __nv_bfloat16* lo_base = side ? L.qlo : L.klo;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int c8 = s * 4 + g;
     size_t cm;                                                // core-matrix index
-    if (side) cm = (((size_t)b * (Ppad >> 7) + (p >> 7)) * Cp8 + c8) * 16 + ((p & 127) >> 3);
+    if (side || L.head_src_rows) cm = (((size_t)b * (Ppad >> 7) + (p >> 7)) * Cp8 + c8) * 16 + ((p & 127) >> 3);
     else cm = ((size_t)b * Cp8 + c8) * (Ppad >> 3) + (p >> 3);
     const size_t off = cm * 64 + (size_t)(p & 7) * 8;         // elements
     uint32_t hw[4], lw[4];
@@ -71,7 +71,7 @@ __device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long loca
     }
     *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     if (lo_base != nullptr) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-    if (!side) {
+    if (!side && !L.head_src_rows) {
       // second, key-major copy of K: [image][p/8][c/8][8 keys][8 ch] -- a chunk of 32 keys x all
       // channels is one contiguous bulk copy and is read MN-major (N = channel) by dQ = dZ K
       const size_t off2 = (((size_t)b * (Ppad >> 3) + (p >> 3)) * Cp8 + c8) * 64 + (size_t)(p & 7) * 8;
@@ -79,7 +79,7 @@ __device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long loca
       if (L.k2lo != nullptr) *reinterpret_cast<uint4*>(L.k2lo + off2) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     }
   }
-  if (side) {
+  if (side && L.qT != nullptr) {
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
       const int c = s * 32 + k;

@@ -62,6 +62,13 @@ __device__ void finalize_losses(const Params& p) {
       const size_t n = (size_t)L.C * L.P;
       if (L.dq_rows != nullptr) {
         for (size_t i = tid; i < n; i += nthr) L.dq_rows[(size_t)b * n + i] = 0.f;
+      } else if (L.dyhi != nullptr) {
+        // head mode: the image's rows of the d loss / d Y blob (zero upstream gradient)
+        const size_t per = (size_t)L.Ppad * L.Cp;
+        for (size_t i = tid; i < per; i += nthr) {
+          L.dyhi[(size_t)b * per + i] = __float2bfloat16_rn(0.f);
+          if (L.dylo != nullptr) L.dylo[(size_t)b * per + i] = __float2bfloat16_rn(0.f);
+        }
       } else {
         for (size_t i = tid; i < n; i += nthr) {
           int c = (int)(i / L.P), pp = (int)(i % L.P);

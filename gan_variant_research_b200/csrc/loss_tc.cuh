@@ -193,11 +193,13 @@ __device__ __forceinline__ void tc_row_pass_b(uint32_t trow, int nch, const floa
   }
 }
 
-// dQ epilogue for one 32-channel chunk; NP = pitch of qT and dxT rows (compile-time: immediates)
+// dQ epilogue for one 32-channel chunk; NP = pitch of qT and dxT rows (compile-time: immediates).
+// Head mode (dyh != NULL): the gradient w.r.t. the head output leaves as a bf16 hi(+lo) row blob
+// (the A operand of the head's backward GEMMs) instead of fp32 rows; padding rows are written as 0.
 template <int NP>
 __device__ __forceinline__ void tc_dq_chunk(const uint32_t (&r)[32], float (&qv)[32], const float* __restrict__ qp,
                                             float* __restrict__ dp, int nvalid, int nnext, float c1, float c2,
-                                            bool rowok) {
+                                            bool rowok, __nv_bfloat16* dyh, __nv_bfloat16* dyl) {
   float out[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) out[k] = fmaf(-qv[k], c2, __uint_as_float(r[k]) * c1);
@@ -208,6 +210,21 @@ __device__ __forceinline__ void tc_dq_chunk(const uint32_t (&r)[32], float (&qv)
   } else {
 #pragma unroll
     for (int k = 0; k < 32; ++k) qv[k] = (k < nnext) ? __ldcg(qp + k * NP) : 0.f;
+  }
+  if (dyh != nullptr) {
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        const float a0 = rowok ? out[g8 * 8 + 2 * k2] : 0.f, a1 = rowok ? out[g8 * 8 + 2 * k2 + 1] : 0.f;
+        h[k2] = bf16x2_bits(a0, a1);
+        l[k2] = bf16x2_bits(a0 - __uint_as_float(h[k2] << 16), a1 - __uint_as_float(h[k2] & 0xffff0000u));
+      }
+      *reinterpret_cast<uint4*>(dyh + g8 * 1024) = make_uint4(h[0], h[1], h[2], h[3]);
+      if (dyl != nullptr) *reinterpret_cast<uint4*>(dyl + g8 * 1024) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    return;
   }
   if (rowok) {
     if (nvalid >= 32) {
@@ -224,7 +241,8 @@ __device__ __forceinline__ void tc_dq_chunk(const uint32_t (&r)[32], float (&qv)
 template <int NP>
 __device__ __forceinline__ void tc_dq_epilogue(uint32_t tacc, int nstage, int C, const float* __restrict__ qrow,
                                                float* __restrict__ dxrow, float c1, float c2, bool rowok,
-                                               uint64_t* dqfull, volatile int* dead) {
+                                               __nv_bfloat16* dyh, __nv_bfloat16* dyl, uint64_t* dqfull,
+                                               volatile int* dead) {
   using namespace umma;
   // raw q values are prefetched two chunks ahead (static double buffer); padding rows read row 0 of
   // the image (always mapped) and never store
@@ -241,12 +259,14 @@ __device__ __forceinline__ void tc_dq_epilogue(uint32_t tacc, int nstage, int C,
     tmem_ld32(tacc + s * 32, r);
     tmem_ld_wait();
     tc_dq_chunk<NP>(r, qa, qrow + (size_t)(s + 2) * 32 * NP, dxrow + (size_t)s * 32 * NP, C - s * 32,
-                    C - (s + 2) * 32, c1, c2, rowok);
+                    C - (s + 2) * 32, c1, c2, rowok, dyh ? dyh + (size_t)s * 4096 : nullptr,
+                    dyl ? dyl + (size_t)s * 4096 : nullptr);
     if (s + 1 < nstage) {
       tmem_ld32(tacc + (s + 1) * 32, r);
       tmem_ld_wait();
       tc_dq_chunk<NP>(r, qb, qrow + (size_t)(s + 3) * 32 * NP, dxrow + (size_t)(s + 1) * 32 * NP, C - (s + 1) * 32,
-                      C - (s + 3) * 32, c1, c2, rowok);
+                      C - (s + 3) * 32, c1, c2, rowok, dyh ? dyh + (size_t)(s + 1) * 4096 : nullptr,
+                      dyl ? dyl + (size_t)(s + 1) * 4096 : nullptr);
     }
   }
 }
@@ -491,8 +511,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       const float* __restrict__ qrow = L.qT + (size_t)b * C * N + gsafe;
       float* __restrict__ dxrow = L.dxT + (size_t)b * C * N + gsafe;        // dxpitch == N on this path
       PNCE_TR(5);
-      if (N == 256) tc_dq_epilogue<256>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, &sh->dqfull, dead);
-      else tc_dq_epilogue<128>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, &sh->dqfull, dead);
+      // head mode: d loss / d (head output) as a row blob [tile = b*halves+mh][c/8][16][8][8]
+      const size_t dyoff = (((size_t)b * halves + mh) * Cp8 * 16 + (size_t)(i >> 3)) * 64 + (size_t)(i & 7) * 8;
+      __nv_bfloat16* dyh = L.dyhi ? L.dyhi + dyoff : nullptr;
+      __nv_bfloat16* dyl = (L.dyhi && L.dylo) ? L.dylo + dyoff : nullptr;
+      if (N == 256) tc_dq_epilogue<256>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead);
+      else tc_dq_epilogue<128>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead);
       PNCE_TR(6);
       tc_fence_before();
     }
@@ -544,7 +568,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_probe(const __grid_constant__ P
     bulk_g2s(sb, a.b_blob, a.b_bytes, &full);
     if (mbar_wait(&full, 0u, &dead)) {
       tc_fence_after();
-      const uint32_t idesc = idesc_bf16(128, a.n, 0, a.b_mn_major);
+      const uint32_t idesc = idesc_bf16(128, a.n, (a.b_mn_major >> 1) & 1, a.b_mn_major & 1);   // bit 0: B, bit 1: A
       for (int ks = 0; ks < a.k / 16; ++ks) {
         const uint64_t da = smem_desc(smem_u32(sa) + ks * a.a_kstep, a.a_lbo, a.a_sbo);
         const uint64_t db = smem_desc(smem_u32(sb) + ks * a.b_kstep, a.b_lbo, a.b_sbo);

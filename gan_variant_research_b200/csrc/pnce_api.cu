@@ -8,6 +8,7 @@
 #include "dense.cuh"
 #include "gather.cuh"
 #include "gather_tc.cuh"
+#include "gemm_tc.cuh"
 #include "loss_simt.cuh"
 #include "loss_tc.cuh"
 #include "sample_bwd.cuh"
@@ -27,16 +28,6 @@ static int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
 
 static size_t dtype_size(int dtype) { return dtype == PNCE_F32 ? 4 : 2; }
 
@@ -608,6 +599,316 @@ int pnce_rows_loss_fwd_bwd(const float* q, const float* k, int batch, int P, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PNCE_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned), st));
   return launch_loss_simt(p, st);
+}
+
+// ---- netF head (tcgen05) ---------------------------------------------------------------------
+
+namespace pnce {
+
+struct HeadLayerBufs {
+  __nv_bfloat16 *xq[2], *xk[2], *hq[2], *hk[2], *dh[2];     // [0] = hi, [1] = lo
+  __nv_bfloat16 *w1[2], *w2[2], *w1t[2], *w2t[2];
+  float *pw2, *pb2, *pw1, *pb1;                              // split-K partials
+  int slabs;
+};
+struct HeadPlan {
+  Params pg;                   // the real layers: gather of raw patches, dense backward of dX
+  Params pl;                   // "virtual" layers seen by k_loss_tc: C = nc, operands = the head's output
+  HeadLayerBufs hb[PNCE_MAX_LAYERS];
+};
+
+static bool head_shapes_ok(const pnce_layer_t* layers, int n_layers, int nc) {
+  if (nc != 128 && nc != 256) return false;
+  return tc_shapes_ok(layers, n_layers);
+}
+
+static size_t carve_head(const pnce_layer_t* layers, int n_layers, int B, int nc, bool x3, void* ws, HeadPlan* out) {
+  Carver cv(ws);
+  HeadPlan* hp = out;
+  HeadPlan local;
+  if (hp == nullptr) hp = &local;
+  memset(hp, 0, sizeof(HeadPlan));
+  Params& pg = hp->pg;
+  Params& pl = hp->pl;
+  pg.n_layers = pl.n_layers = n_layers;
+  pg.B = pl.B = B;
+  pl.counter = pg.counter = cv.take<unsigned>(64);
+  pl.lossimg = cv.take<float>((size_t)n_layers * B);
+  pl.valid = cv.take<int>((size_t)n_layers * B);
+  const int nparts = x3 ? 2 : 1;
+  for (int l = 0; l < n_layers; ++l) {
+    const pnce_layer_t& a = layers[l];
+    LayerDev& G = pg.L[l];
+    LayerDev& V = pl.L[l];
+    HeadLayerBufs& hb = hp->hb[l];
+    const int Ppad = (a.P + 127) / 128 * 128, Cp = (a.C + 31) / 32 * 32;
+    G.src = a.src; G.tgt = a.tgt; G.dtgt = a.dtgt;
+    G.ids = reinterpret_cast<const long long*>(a.ids);
+    G.C = a.C; G.HW = a.H * a.W; G.P = a.P;
+    G.ntiles = (a.P + kRowTile - 1) / kRowTile;
+    G.sorted = 1;
+    G.Cp = Cp; G.Ppad = Ppad; G.nchunk = Cp / 32; G.nparts = Ppad / 128;
+    G.head_src_rows = 1;
+    G.sid = cv.take<int>(a.P);
+    G.perm = cv.take<int>(a.P);
+    G.rank = cv.take<int>(a.P);
+    G.cslot = cv.take<int>((size_t)(G.HW + kTilePos - 1) / kTilePos + 1);
+    G.dxpitch = Ppad;
+    G.dxT = cv.take<float>((size_t)B * a.C * Ppad);
+    const size_t xblob = (size_t)B * Ppad * Cp, yblob = (size_t)B * Ppad * nc;
+    for (int k = 0; k < nparts; ++k) {
+      hb.xq[k] = cv.take<__nv_bfloat16>(xblob);
+      hb.xk[k] = cv.take<__nv_bfloat16>(xblob);
+      hb.hq[k] = cv.take<__nv_bfloat16>(yblob);
+      hb.hk[k] = cv.take<__nv_bfloat16>(yblob);
+      hb.w1[k] = cv.take<__nv_bfloat16>((size_t)nc * Cp);
+      hb.w1t[k] = cv.take<__nv_bfloat16>((size_t)nc * Cp);
+      hb.w2[k] = cv.take<__nv_bfloat16>((size_t)nc * nc);
+      hb.w2t[k] = cv.take<__nv_bfloat16>((size_t)nc * nc);
+      hb.dh[k] = hb.hk[k];                                   // H of the key side is dead once Y_k exists
+    }
+    G.qhi = hb.xq[0]; G.qlo = hb.xq[1]; G.khi = hb.xk[0]; G.klo = hb.xk[1];
+    // virtual layer: what k_loss_tc sees
+    V = G;
+    V.src = V.tgt = nullptr; V.dtgt = nullptr;
+    V.C = nc; V.Cp = nc; V.nchunk = nc / 32;
+    V.head_src_rows = 0;
+    V.qhi = cv.take<__nv_bfloat16>(yblob);
+    V.khi = cv.take<__nv_bfloat16>(yblob);
+    V.k2hi = cv.take<__nv_bfloat16>(yblob);
+    V.dyhi = cv.take<__nv_bfloat16>(yblob);
+    if (x3) {
+      V.qlo = cv.take<__nv_bfloat16>(yblob);
+      V.klo = cv.take<__nv_bfloat16>(yblob);
+      V.k2lo = cv.take<__nv_bfloat16>(yblob);
+      V.dylo = cv.take<__nv_bfloat16>(yblob);
+    } else {
+      V.qlo = V.klo = V.k2lo = V.dylo = nullptr;
+    }
+    V.qT = cv.take<float>((size_t)B * nc * Ppad);
+    V.qss = cv.take<float>((size_t)B * (nc / 32) * Ppad);
+    V.kss = cv.take<float>((size_t)B * (nc / 32) * Ppad);
+    V.qinv = cv.take<float>((size_t)B * a.P);
+    V.partial = cv.take<float>((size_t)B * 2);
+    V.dxT = nullptr;
+    const int tiles = B * (Ppad / 128);
+    hb.slabs = tiles < 8 ? tiles : 8;
+    hb.pw2 = cv.take<float>((size_t)hb.slabs * nc * nc);
+    hb.pb2 = cv.take<float>((size_t)hb.slabs * nc);
+    hb.pw1 = cv.take<float>((size_t)hb.slabs * nc * Cp);
+    hb.pb1 = cv.take<float>((size_t)hb.slabs * nc);
+  }
+  return align_up(cv.off, 256);
+}
+
+static int launch_gemm(GemmLaunch& g, cudaStream_t st) {
+  long long acc = 0;
+  for (int i = 0; i < g.n; ++i) { g.start[i] = acc; acc += g.pr[i].tiles; }
+  g.start[g.n] = acc;
+  if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+  int rc = set_smem(k_gemm_tc, kGemmSmemBytes);
+  if (rc != PNCE_OK) return rc;
+  k_gemm_tc<<<(unsigned)acc, kTcThreads, kGemmSmemBytes, st>>>(g);
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+
+static int check_head_args(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch,
+                           int dtype, int nc, int math_mode, void* ws, bool bwd) {
+  int rc = check_layers(layers, n_layers, batch);
+  if (rc != PNCE_OK) return rc;
+  if (heads == nullptr || dtype < PNCE_F32 || dtype > PNCE_BF16) return PNCE_ERR_ARG;
+  if (math_mode != PNCE_MATH_TC_BF16X3 && math_mode != PNCE_MATH_TC_BF16) return PNCE_ERR_UNSUPPORTED;
+  if (!head_shapes_ok(layers, n_layers, nc)) return PNCE_ERR_UNSUPPORTED;
+  for (int l = 0; l < n_layers; ++l) {
+    const pnce_head_t& h = heads[l];
+    if (!h.w1 || !h.b1 || !h.w2 || !h.b2) return PNCE_ERR_ARG;
+    if (bwd && (!h.dw1 || !h.db1 || !h.dw2 || !h.db2)) return PNCE_ERR_ARG;
+  }
+  rc = check_alignment(layers, n_layers, dtype, bwd);
+  if (rc != PNCE_OK) return rc;
+  if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
+  return PNCE_OK;
+}
+
+}  // namespace pnce
+
+int pnce_head_workspace_bytes(const pnce_layer_t* layers, int n_layers, int batch, int nc, size_t* bytes) {
+  if (bytes == nullptr) return PNCE_ERR_ARG;
+  int rc = check_layers(layers, n_layers, batch);
+  if (rc != PNCE_OK) return rc;
+  if (!head_shapes_ok(layers, n_layers, nc)) return PNCE_ERR_UNSUPPORTED;
+  *bytes = carve_head(layers, n_layers, batch, nc, true, nullptr, nullptr);
+  return PNCE_OK;
+}
+
+int pnce_head_fwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
+                  int nc, float temperature, int math_mode, void* ws, size_t ws_bytes, float* loss_out,
+                  int* nonfinite, void* stream) {
+  int rc = check_head_args(layers, heads, n_layers, batch, dtype, nc, math_mode, ws, false);
+  if (rc != PNCE_OK) return rc;
+  if (loss_out == nullptr || !(temperature > 0.f)) return PNCE_ERR_ARG;
+  const bool x3 = math_mode == PNCE_MATH_TC_BF16X3;
+  static thread_local HeadPlan hp;
+  if (carve_head(layers, n_layers, batch, nc, x3, ws, &hp) > ws_bytes) return PNCE_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Params& pg = hp.pg;
+  Params& pl = hp.pl;
+  pg.dtype = pl.dtype = dtype;
+  pg.math = pl.math = math_mode;
+  pg.tau = pl.tau = temperature;
+  pl.loss_out = loss_out;
+  pg.nonfinite = pl.nonfinite = nonfinite;
+  pg.b0 = pl.b0 = 0; pg.bn = pl.bn = batch;
+  pl.trace = g_dbg.trace;
+  // 1. ids -> sorted slots; weights -> operand blobs
+  rc = launch_prep(pg, st);
+  if (rc != PNCE_OK) return rc;
+  for (int l = 0; l < n_layers; ++l) {
+    const HeadLayerBufs& hb = hp.hb[l];
+    const int C = layers[l].C, Cp = pg.L[l].Cp;
+    WprepArgs a;
+    a.w = heads[l].w1; a.hi = hb.w1[0]; a.lo = hb.w1[1]; a.R = nc; a.Cw = C; a.N = nc; a.K = Cp; a.transpose = 0;
+    k_wprep<<<(nc / 8) * (Cp / 8), 64, 0, st>>>(a);
+    a.hi = hb.w1t[0]; a.lo = hb.w1t[1]; a.N = Cp; a.K = nc; a.transpose = 1;
+    k_wprep<<<(Cp / 8) * (nc / 8), 64, 0, st>>>(a);
+    a.w = heads[l].w2; a.hi = hb.w2[0]; a.lo = hb.w2[1]; a.R = nc; a.Cw = nc; a.N = nc; a.K = nc; a.transpose = 0;
+    k_wprep<<<(nc / 8) * (nc / 8), 64, 0, st>>>(a);
+    a.hi = hb.w2t[0]; a.lo = hb.w2t[1]; a.transpose = 1;
+    k_wprep<<<(nc / 8) * (nc / 8), 64, 0, st>>>(a);
+  }
+  PNCE_CUDA(cudaGetLastError());
+  // 2. raw patches of both sides as row blobs
+  rc = launch_gather_tc(pg, st);
+  if (rc != PNCE_OK) return rc;
+  // 3. H = relu(X W1^T + b1), both sides
+  static thread_local GemmLaunch g;
+  memset(&g, 0, sizeof(g));
+  g.x3 = x3 ? 1 : 0;
+  g.err = nonfinite ? nonfinite + 1 : nullptr;
+  for (int l = 0; l < n_layers; ++l) {
+    const HeadLayerBufs& hb = hp.hb[l];
+    const LayerDev& G = pg.L[l];
+    for (int side = 0; side < 2; ++side) {
+      GemmProb& pr = g.pr[g.n++];
+      pr.a_hi = side ? hb.xq[0] : hb.xk[0]; pr.a_lo = side ? hb.xq[1] : hb.xk[1];
+      pr.b_hi = hb.w1[0]; pr.b_lo = hb.w1[1];
+      pr.bias = heads[l].b1;
+      pr.K = G.Cp; pr.N = nc; pr.tiles = batch * (G.Ppad / 128); pr.mode = GM_H;
+      pr.P = G.P; pr.Ppad = G.Ppad; pr.halves = G.Ppad / 128; pr.C = G.C;
+      pr.o_hi = side ? hb.hq[0] : hb.hk[0]; pr.o_lo = side ? hb.hq[1] : hb.hk[1];
+    }
+  }
+  rc = launch_gemm(g, st);
+  if (rc != PNCE_OK) return rc;
+  // 4. Y = H W2^T + b2 straight into the operand formats of k_loss_tc
+  memset(&g, 0, sizeof(g));
+  g.x3 = x3 ? 1 : 0;
+  g.err = nonfinite ? nonfinite + 1 : nullptr;
+  for (int l = 0; l < n_layers; ++l) {
+    const HeadLayerBufs& hb = hp.hb[l];
+    const LayerDev& G = pg.L[l];
+    const LayerDev& V = pl.L[l];
+    for (int side = 0; side < 2; ++side) {
+      GemmProb& pr = g.pr[g.n++];
+      pr.a_hi = side ? hb.hq[0] : hb.hk[0]; pr.a_lo = side ? hb.hq[1] : hb.hk[1];
+      pr.b_hi = hb.w2[0]; pr.b_lo = hb.w2[1];
+      pr.bias = heads[l].b2;
+      pr.K = nc; pr.N = nc; pr.tiles = batch * (G.Ppad / 128); pr.mode = side ? GM_YQ : GM_YK;
+      pr.P = G.P; pr.Ppad = G.Ppad; pr.halves = G.Ppad / 128; pr.C = nc;
+      if (side) { pr.o_hi = V.qhi; pr.o_lo = V.qlo; pr.ss = V.qss; pr.outT = V.qT; }
+      else { pr.k_hi = V.khi; pr.k_lo = V.klo; pr.k2_hi = V.k2hi; pr.k2_lo = V.k2lo; pr.ss = V.kss; }
+    }
+  }
+  rc = launch_gemm(g, st);
+  if (rc != PNCE_OK) return rc;
+  // 5. logits / diagonal CE / d loss / d Y (as a row blob) on the head's output
+  int ctas = 0;
+  for (int l = 0; l < n_layers; ++l) ctas += pl.L[l].Ppad / 128;
+  pl.total_ctas = (unsigned)(batch * ctas);
+  return launch_loss_tc(pl, st);
+}
+
+int pnce_head_bwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
+                  int nc, int math_mode, void* ws, size_t ws_bytes, const float* grad_out, void* stream) {
+  int rc = check_head_args(layers, heads, n_layers, batch, dtype, nc, math_mode, ws, true);
+  if (rc != PNCE_OK) return rc;
+  const bool x3 = math_mode == PNCE_MATH_TC_BF16X3;
+  static thread_local HeadPlan hp;
+  if (carve_head(layers, n_layers, batch, nc, x3, ws, &hp) > ws_bytes) return PNCE_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Params& pg = hp.pg;
+  pg.dtype = dtype;
+  pg.grad_out = grad_out;
+  static thread_local GemmLaunch g;
+  // 1. dH = (dY W2) * [H > 0]
+  memset(&g, 0, sizeof(g));
+  g.x3 = x3 ? 1 : 0;
+  for (int l = 0; l < n_layers; ++l) {
+    const HeadLayerBufs& hb = hp.hb[l];
+    const LayerDev& G = pg.L[l];
+    const LayerDev& V = hp.pl.L[l];
+    GemmProb& pr = g.pr[g.n++];
+    pr.a_hi = V.dyhi; pr.a_lo = V.dylo; pr.b_hi = hb.w2t[0]; pr.b_lo = hb.w2t[1];
+    pr.K = nc; pr.N = nc; pr.tiles = batch * (G.Ppad / 128); pr.mode = GM_DH;
+    pr.P = G.P; pr.Ppad = G.Ppad; pr.halves = G.Ppad / 128; pr.C = nc;
+    pr.o_hi = hb.dh[0]; pr.o_lo = hb.dh[1]; pr.mask_hi = hb.hq[0];
+  }
+  rc = launch_gemm(g, st);
+  if (rc != PNCE_OK) return rc;
+  // 2. dX = dH W1 -> the transposed fp32 rows the dense backward reads
+  memset(&g, 0, sizeof(g));
+  g.x3 = x3 ? 1 : 0;
+  for (int l = 0; l < n_layers; ++l) {
+    const HeadLayerBufs& hb = hp.hb[l];
+    const LayerDev& G = pg.L[l];
+    GemmProb& pr = g.pr[g.n++];
+    pr.a_hi = hb.dh[0]; pr.a_lo = hb.dh[1]; pr.b_hi = hb.w1t[0]; pr.b_lo = hb.w1t[1];
+    pr.K = nc; pr.N = G.Cp; pr.tiles = batch * (G.Ppad / 128); pr.mode = GM_DX;
+    pr.P = G.P; pr.Ppad = G.Ppad; pr.halves = G.Ppad / 128; pr.C = G.C;
+    pr.outT = G.dxT;
+  }
+  rc = launch_gemm(g, st);
+  if (rc != PNCE_OK) return rc;
+  // 3. weight / bias gradients: split-K partials, then a deterministic reduce scaled by the upstream
+  static thread_local WgradLaunch wg;
+  memset(&wg, 0, sizeof(wg));
+  wg.x3 = x3 ? 1 : 0;
+  long long acc = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    const HeadLayerBufs& hb = hp.hb[l];
+    const LayerDev& G = pg.L[l];
+    const LayerDev& V = hp.pl.L[l];
+    const int tiles = batch * (G.Ppad / 128);
+    for (int which = 0; which < 2; ++which) {
+      WgradProb& pr = wg.pr[wg.n];
+      pr.a_hi = which ? hb.dh[0] : V.dyhi; pr.a_lo = which ? hb.dh[1] : V.dylo;
+      pr.b_hi = which ? hb.xq[0] : hb.hq[0]; pr.b_lo = which ? hb.xq[1] : hb.hq[1];
+      pr.NA = nc; pr.N = which ? G.Cp : nc; pr.tiles = tiles; pr.slabs = hb.slabs;
+      pr.partial = which ? hb.pw1 : hb.pw2; pr.pbias = which ? hb.pb1 : hb.pb2;
+      wg.start[wg.n++] = acc;
+      acc += (long long)hb.slabs * (nc / 128);
+    }
+  }
+  wg.start[wg.n] = acc;
+  rc = set_smem(k_wgrad_tc, kWgSmemBytes);
+  if (rc != PNCE_OK) return rc;
+  k_wgrad_tc<<<(unsigned)acc, kTcThreads, kWgSmemBytes, st>>>(wg);
+  PNCE_CUDA(cudaGetLastError());
+  for (int l = 0; l < n_layers; ++l) {
+    const HeadLayerBufs& hb = hp.hb[l];
+    const LayerDev& G = pg.L[l];
+    WreduceArgs a;
+    a.partial = hb.pw2; a.pbias = hb.pb2; a.dw = heads[l].dw2; a.db = heads[l].db2;
+    a.NA = nc; a.N = nc; a.Nout = nc; a.slabs = hb.slabs; a.grad_out = grad_out;
+    k_wreduce<<<(unsigned)(((long long)nc * nc + nc + kThreads - 1) / kThreads), kThreads, 0, st>>>(a);
+    a.partial = hb.pw1; a.pbias = hb.pb1; a.dw = heads[l].dw1; a.db = heads[l].db1;
+    a.N = G.Cp; a.Nout = G.C;
+    k_wreduce<<<(unsigned)(((long long)nc * G.Cp + nc + kThreads - 1) / kThreads), kThreads, 0, st>>>(a);
+  }
+  PNCE_CUDA(cudaGetLastError());
+  // 4. dense d tgt_feat (zero fill + sampled positions), scaled by the upstream gradient
+  return launch_dense(pg, st);
 }
 
 int pnce_selftest_umma(const void* a_blob, size_t a_bytes, const void* b_blob, size_t b_bytes,

@@ -426,21 +426,116 @@ class PatchSampleF(nn.Module):
         return return_feats, return_ids
 
 
+class _FusedHeadPatchNCE(torch.autograd.Function):
+    """All layers of the head path through the C ABI: pnce_head_fwd (prep, weight blobs, gather,
+    2 GEMM launches, fused logits/CE/dY) and pnce_head_bwd (dH, dX, weight gradients, dense d tgt).
+    Inputs: plan, L target maps, then 4 L head parameters (w1, b1, w2, b2 per layer)."""
+
+    @staticmethod
+    def forward(ctx, plan, nc, *args):
+        lib = _lib.load()
+        n = len(plan.ids_list)
+        tgt = [t.detach() for t in args[:n]]
+        params = [a.detach().to(torch.float32).contiguous() for a in args[n:]]
+        src, ids = plan.src_feats, plan.ids_list
+        dev = tgt[0].device
+        batch = tgt[0].shape[0]
+        dtype = _DTYPES[tgt[0].dtype]
+        layers = _layer_array(src, tgt, None, ids)
+        heads = (_lib.PnceHead * n)()
+        for l in range(n):
+            w1, b1, w2, b2 = params[4 * l:4 * l + 4]
+            heads[l].w1, heads[l].b1, heads[l].w2, heads[l].b2 = (w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                                                  b2.data_ptr())
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.pnce_head_workspace_bytes(layers, n, batch, nc, ctypes.byref(nbytes)),
+                   "pnce_head_workspace_bytes")
+        with torch.cuda.device(dev):
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            out = torch.empty(1 + n, dtype=torch.float32, device=dev)
+            flag = torch.zeros(2, dtype=torch.int32, device=dev)
+            _lib.check(lib.pnce_head_fwd(layers, heads, n, batch, dtype, nc, plan.temperature, _MATH[plan.math],
+                                         ws.data_ptr(), nbytes.value, out.data_ptr(), flag.data_ptr(),
+                                         _stream_ptr(dev)), "pnce_head_fwd")
+        _warnings.push(flag)
+        ctx.plan, ctx.ws, ctx.ws_bytes, ctx.nc = plan, ws, nbytes.value, nc
+        ctx.tgt_keep, ctx.params = tgt, params
+        ctx.param_meta = [(a.shape, a.dtype) for a in args[n:]]
+        ctx.dev, ctx.batch, ctx.dtype = dev, batch, dtype
+        ctx.layer_losses = out[1:]
+        return out.narrow(0, 0, 1).reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        dev, n = ctx.dev, len(ctx.tgt_keep)
+        g = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            grads = [torch.empty_like(t) for t in ctx.tgt_keep]
+            pgrads = [torch.empty_like(p) for p in ctx.params]
+            layers = _layer_array(ctx.plan.src_feats, ctx.tgt_keep, grads, ctx.plan.ids_list)
+            heads = (_lib.PnceHead * n)()
+            for l in range(n):
+                w1, b1, w2, b2 = ctx.params[4 * l:4 * l + 4]
+                d1, e1, d2, e2 = pgrads[4 * l:4 * l + 4]
+                heads[l].w1, heads[l].b1, heads[l].w2, heads[l].b2 = (w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                                                      b2.data_ptr())
+                heads[l].dw1, heads[l].db1, heads[l].dw2, heads[l].db2 = (d1.data_ptr(), e1.data_ptr(),
+                                                                          d2.data_ptr(), e2.data_ptr())
+            _lib.check(lib.pnce_head_bwd(layers, heads, n, ctx.batch, ctx.dtype, ctx.nc, _MATH[ctx.plan.math],
+                                         ctx.ws.data_ptr(), ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev)),
+                       "pnce_head_bwd")
+        pgrads = [pg.to(dt).reshape(shape) for pg, (shape, dt) in zip(pgrads, ctx.param_meta)]
+        return (None, None, *grads, *pgrads)
+
+
+def fused_head_supported(netF: "PatchSampleF", feats, num_patches) -> bool:
+    """The tcgen05 head kernels cover nc in {128, 256}, P <= 256 and C <= 256 (every 256^2 CUT layer)."""
+    if not netF.use_mlp or netF.nc not in (128, 256):
+        return False
+    return all(f.shape[1] <= 256 and patch_count(num_patches, f.shape[2] * f.shape[3]) <= 256 for f in feats)
+
+
 def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0.07, num_patches=256,
-                       patch_ids=None, math: Optional[str] = None):
+                       patch_ids=None, math: Optional[str] = None, fused: Optional[bool] = None):
     """North-star composition:
     ``feat_k, ids = netF(src_feats, num_patches, patch_ids)`` (no grad into k, as upstream CUT and the
     reference's ``detach`` :142), ``feat_q, _ = netF(tgt_feats, num_patches, ids)``, then
-    ``mean_l PatchNCELoss(feat_q_l, feat_k_l)``.  Returns ``(loss, ids)``."""
-    with torch.no_grad():
-        feat_k, ids = netF(src_feats, num_patches, patch_ids)
-    feat_q, _ = netF(tgt_feats, num_patches, ids)
-    batch = tgt_feats[0].shape[0]
-    total = None
-    for q, k in zip(feat_q, feat_k):
-        l = rows_patchnce(q, k, temperature, num_patches, batch, math)
-        total = l if total is None else total + l
-    return total / len(feat_q), ids
+    ``mean_l PatchNCELoss(feat_q_l, feat_k_l)``.  Returns ``(loss, ids)``.
+
+    ``fused`` (default: whenever the shapes allow) runs the whole thing -- gather, both Linear layers,
+    normalisation, logits, CE and the complete backward including the head gradients -- in the
+    tcgen05 kernels of libpnce; otherwise the module-split composition is used (libpnce gather /
+    scatter / rows loss around ATen's Linear)."""
+    if fused is None:
+        fused = fused_head_supported(netF, tgt_feats, num_patches) and (math or DEFAULT_MATH) != "simt_f32"
+    if not fused:
+        with torch.no_grad():
+            feat_k, ids = netF(src_feats, num_patches, patch_ids)
+        feat_q, _ = netF(tgt_feats, num_patches, ids)
+        batch = tgt_feats[0].shape[0]
+        total = None
+        for q, k in zip(feat_q, feat_k):
+            l = rows_patchnce(q, k, temperature, num_patches, batch, math)
+            total = l if total is None else total + l
+        return total / len(feat_q), ids
+    if not fused_head_supported(netF, tgt_feats, num_patches):
+        raise RuntimeError("fused head: nc must be 128 or 256, num_patches <= 256 and C <= 256")
+    if not netF.mlp_init:
+        netF.create_mlp(tgt_feats)
+    src, tgt, _ = _prepare_maps(src_feats, tgt_feats)
+    if patch_ids is None:
+        ids = [draw_patch_ids(t, num_patches) for t in tgt]
+    else:
+        ids = [i.to(device=t.device, dtype=torch.int64).contiguous() for i, t in zip(patch_ids, tgt)]
+    params = []
+    for l in range(len(tgt)):
+        mlp = getattr(netF, f"mlp_{l}")
+        params += [mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias]
+    plan = _Plan(src, ids, temperature, math or DEFAULT_MATH)
+    _warnings.poll()
+    loss = _FusedHeadPatchNCE.apply(plan, netF.nc, *tgt, *params)
+    return loss, ids
 
 
 def install_reference_shim():

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PNCE_ABI_VERSION 1
+#define PNCE_ABI_VERSION 2
 #define PNCE_MAX_LAYERS 8      /* nce_layers per call (reference config uses 5 ids -> 4 maps)   */
 #define PNCE_MAX_PATCHES 4096  /* P = min(num_patches, H*W)  patchnce_cut.py:60                 */
 #define PNCE_MAX_CHANNELS 1024
@@ -111,6 +111,31 @@ int pnce_rows_loss_fwd_bwd(const float* dev_q, const float* dev_k, int batch, in
                            float temperature, int math_mode, void* dev_workspace,
                            size_t workspace_bytes, float* dev_loss_out, int* dev_nonfinite,
                            float* dev_dq_out, float* dev_dk_out, void* stream);
+
+/* ---- netF head, fused (north-star pieces 3-5; absent from the reference: SURVEY.md 8 row a13) ---
+ * PatchSampleF(use_mlp=True): raw gather -> Linear(C_l, nc) -> ReLU -> Linear(nc, nc) -> L2 normalise for the
+ * src (k, no gradient) and tgt (q) patches of every layer, then the same logits / diagonal CE as
+ * pnce_fwd on the head's output; all contractions on tcgen05 (math_mode TC_BF16X3 or TC_BF16).
+ * Supported: nc = 128 or 256, P <= 256, C <= 256.  Weights are fp32, nn.Linear layout (out, in).      */
+typedef struct pnce_head {
+  const float* w1;  /* (nc, C)  */
+  const float* b1;  /* (nc)     */
+  const float* w2;  /* (nc, nc) */
+  const float* b2;  /* (nc)     */
+  float* dw1;       /* outputs of pnce_head_bwd, same shapes, overwritten; may be NULL for pnce_head_fwd */
+  float* db1;
+  float* dw2;
+  float* db2;
+} pnce_head_t;
+
+int pnce_head_workspace_bytes(const pnce_layer_t* layers, int n_layers, int batch, int nc, size_t* bytes);
+int pnce_head_fwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
+                  int nc, float temperature, int math_mode, void* dev_workspace, size_t workspace_bytes,
+                  float* dev_loss_out, int* dev_nonfinite, void* stream);
+/* Writes every layers[l].dtgt densely and every heads[l].d*, all scaled by *dev_grad_out (NULL = 1). */
+int pnce_head_bwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
+                  int nc, int math_mode, void* dev_workspace, size_t workspace_bytes,
+                  const float* dev_grad_out, void* stream);
 
 /* Library self-test of the tcgen05 building blocks (bulk copy -> smem, tcgen05.mma with a K-major
  * or MN-major B operand, commit, tcgen05.ld): D(128 x n) = A(128 x k) * B on pre-tiled bf16 operand

@@ -1,3 +1,4 @@
 set -x
-python -m pytest tests -m gpu -q 2>&1 | tail -15
-python bench.py --no-cpu-baseline --no-e2e | cut -c1-200
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -5
+timeout 300 python scratch/exp4.py 2>&1 | grep -v Warn
+MATH=tc_bf16 timeout 300 python scratch/exp4.py 2>&1 | grep -v Warn

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in pnce.h but not exported"
     assert sorted(_lib.EXPORTS) == declared
-    assert lib.pnce_abi_version() == 1
+    assert lib.pnce_abi_version() == 2
 
 
 def test_ctypes_struct_matches_header_layout():

@@ -342,8 +342,8 @@ def _head_problem(seed, b, shapes, p):
     return src, tgt, ids
 
 
-@pytest.mark.parametrize("nc", [64, 256])
-def test_netf_head_matches_the_oracle(pn, orc, nc):
+@pytest.mark.parametrize("nc,fused", [(64, False), (256, False), (128, True), (256, True)])
+def test_netf_head_matches_the_oracle(pn, orc, nc, fused):
     """North-star PatchSampleF(use_mlp=True) + PatchNCELoss(feat_q, feat_k): loss, dense d tgt and
     the head gradients against the oracle's torch restatement (PARITY UNPINNED by the reference,
     which has no head: SURVEY.md section 8 row a13).  Tolerance 1e-3 relative (north_star)."""
@@ -351,10 +351,15 @@ def test_netf_head_matches_the_oracle(pn, orc, nc):
     src, tgt, ids = _head_problem(123, 3, shapes, 64)
     torch.manual_seed(5)
     netF = pn.PatchSampleF(use_mlp=True, nc=nc, init_gain=0.3)
+    netF.create_mlp([x.cuda() for x in tgt])
+    for prm in netF.parameters():                           # non-zero biases so their gradients are exercised
+        if prm.dim() == 1:
+            torch.nn.init.normal_(prm, 0.0, 0.1)
     t = [x.cuda().requires_grad_() for x in tgt]
     idd = [i.cuda() for i in ids]
-    loss, rid = pn.patchnce_with_head(netF, [x.cuda() for x in src], t, 0.07, 64, idd)
+    loss, rid = pn.patchnce_with_head(netF, [x.cuda() for x in src], t, 0.07, 64, idd, fused=fused)
     (loss * 2.0).backward()
+    assert pn.poll_nonfinite_warnings(block=True) == 0      # raises on a kernel protocol timeout
     assert all(torch.equal(a, b) for a, b in zip(rid, idd))
     heads = []
     for l in range(len(shapes)):

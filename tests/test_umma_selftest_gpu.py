@@ -72,3 +72,16 @@ def test_mn_major_b_operand_key_major_blob(need_cuda, n, k):
                        (n // 8 * 128, 128, 2 * (n // 8) * 128), n, k, 1)
     assert err == 0
     np.testing.assert_array_equal(d.numpy(), (a @ kmat).numpy())
+
+
+@pytest.mark.parametrize("n,k", [(64, 32), (256, 128)])
+def test_mn_major_a_and_b_operands(need_cuda, n, k):
+    """Weight gradients (k_wgrad_tc): D = A^T-view . B with BOTH operands read MN-major from row blobs
+    [col/8][row/8][8 rows][8 cols] whose rows are the contraction index."""
+    g = torch.Generator().manual_seed(13 * n + k)
+    at = torch.randint(-4, 5, (k, 128), generator=g).float()      # (contraction m, output row i)
+    bt = torch.randint(-4, 5, (k, n), generator=g).float()        # (contraction m, output col j)
+    d, err = run_probe(tile_blob(at), tile_blob(bt), (128, k // 8 * 128, 2 * 128),
+                       (128, k // 8 * 128, 2 * 128), n, k, 3)
+    assert err == 0
+    np.testing.assert_array_equal(d.numpy(), (at.t() @ bt).numpy())
