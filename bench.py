@@ -50,7 +50,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph")
+    ap.add_argument("--head", action="store_true", help="time the netF-head mode (nc=256) as the workload")
+    ap.add_argument("--no-head-line", action="store_true", help="skip the secondary head-mode measurement")
     return ap.parse_args()
 
 
@@ -253,6 +254,11 @@ def main():
     src, tgt = make_maps(layers, B, tdtype, dev, 1234 + rank)
     tgt = [t.requires_grad_() for t in tgt]
     crit = pn.PatchNCELoss(args.tau, args.patches, [0, 4, 8, 12, 13], math=math)
+    netF = None
+    if args.head:
+        torch.manual_seed(11)      # identical head weights on every rank
+        netF = pn.PatchSampleF(use_mlp=True, nc=256).to(dev)
+        netF.create_mlp(tgt)
     torch.manual_seed(7)           # identical ids on every rank
 
     ev_b0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -261,10 +267,16 @@ def main():
     def step(i=None):
         for t in tgt:
             t.grad = None
-        loss = crit(src, tgt)
+        if netF is None:
+            loss = crit(src, tgt)
+        else:
+            netF.zero_grad(set_to_none=True)
+            loss, _ = pn.patchnce_with_head(netF, src, tgt, args.tau, args.patches, math=math)
         if i is not None:
             ev_b0[i].record()
         loss.backward()
+        if netF is not None and world > 1:
+            pn.allreduce_head_grads(netF)          # the only collective of the path
         if i is not None:
             ev_b1[i].record()
         return loss
@@ -300,9 +312,11 @@ def main():
     peak, peak_src = peaks()
 
     dense_bytes = dense_kernel_bytes_per_image(layers, args.patches, elem) * B
-    roof = {"bound": "hbm", "kernel": "k_dense_bwd (dense d tgt_feat write + patch scatter)",
+    roof = {"bound": "hbm", "kernel": "k_dense_flat (dense d tgt_feat: zero fill + sampled values, one write per line)",
             "achieved": dense_bytes / (bwd_med * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            "peak_source": peak_src, "traffic": None, "launch_ms": bwd_med}
+            "peak_source": peak_src, "traffic": ncu_traffic("k_dense_flat", B, elem), "launch_ms": bwd_med}
+    if args.head:
+        roof["note"] = "head mode: the backward events also cover the head's backward GEMMs"
     roof["frac"] = roof["achieved"] / peak
     path_bytes = algorithmic_bytes_per_image(layers, args.patches, elem) * B
     roof_path = {"bound": "hbm", "achieved": path_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": peak,
@@ -315,8 +329,13 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.dtype],
         "math": math, "data": "synthetic", "config": workload_config(args, layers),
         "roofline": roof, "roofline_path": roof_path, "clocks": clocks,
-        "gpu_launches": 3 * args.steps, "loss": float(loss.item()),
+        "gpu_launches": (10 if args.head else 4) * args.steps, "loss": float(loss.item()),
     }
+    if args.head:
+        out["config"]["workload"] = out["config"]["workload"].replace(
+            "reference-exact mode (no netF head)", "netF head mode (Linear-ReLU-Linear, nc=256, tcgen05)")
+    elif rank == 0 and world == 1 and not args.no_head_line:
+        out["head_mode"] = head_line(args, pn, src, tgt, math, patches_per_image)
 
     # ---- e2e: same metric through the public API with HOST buffers ------------------------------
     if not args.no_e2e:
@@ -327,6 +346,45 @@ def main():
         print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def ncu_traffic(kernel, batch, elem):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    ncu --set full capture (profiles/traffic.json), scaled to this batch; None when never captured."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path) or elem != 4:
+        return None
+    d = json.load(open(path)).get(kernel)
+    if not d:
+        return None
+    return d["dram_bytes_per_launch"] * batch / d["batch"]
+
+
+def head_line(args, pn, src, tgt, math, patches_per_image, steps=20):
+    """Secondary measurement: the same maps through the netF head (nc=256), fused tcgen05 path."""
+    torch.manual_seed(11)
+    netF = pn.PatchSampleF(use_mlp=True, nc=256).to(tgt[0].device)
+    netF.create_mlp(tgt)
+
+    def step():
+        for t in tgt:
+            t.grad = None
+        netF.zero_grad(set_to_none=True)
+        loss, _ = pn.patchnce_with_head(netF, src, tgt, args.tau, args.patches, math=math)
+        loss.backward()
+
+    for _ in range(3):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "value": args.batch * patches_per_image / (ms * 1e-3), "unit": UNIT, "nc": 256,
+            "steps": steps, "note": "netF head Linear-ReLU-Linear on tcgen05, parity unpinned by the reference"}
 
 
 def run_e2e(args, pn, crit, layers, tdtype, elem, dev, world, rank):

@@ -6,7 +6,7 @@
 //     row blob   [tile of 128 rows][col/8][16 row groups][8 rows][8 cols]   activations X, H, Y, dY, dH
 //     weight blob          [k/8][n/8 row groups][8 n][8 k]                  W as the B operand (N x K)
 //   * k_gemm_tc  : D(128 x N) = A_tile(128 x K) B^T, both K-major, K streamed in chunks of 32 through a
-//                  4-slot ring; warp-specialised like k_loss_tc (producer / MMA issuer / 4 epilogue
+//                  2-slot ring, two CTAs per SM; warp-specialised like k_loss_tc (producer / MMA issuer / 4 epilogue
 //                  warps, thread <-> row).  The epilogue mode decides what leaves the SM:
 //                  H = relu(.+b1) as the next GEMM's A blob; Y = .+b2 directly in the operand formats
 //                  k_loss_tc consumes (so the logits kernel runs unchanged on the head's output);
@@ -46,7 +46,7 @@ struct GemmLaunch {
   int* err;                                // protocol-timeout flag (nonfinite[1])
 };
 
-constexpr int kGemmSlots = 4;
+constexpr int kGemmSlots = 2;                // 2 x 48 KB: two CTAs per SM, one's epilogue overlaps the other's MMAs
 constexpr int kGemmSmemBytes = kGemmSlots * kTcStageBytes + 256;
 
 struct GemmShared {
@@ -66,7 +66,7 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant__ GemmLaunch g) {
+__global__ void __launch_bounds__(kTcThreads, 2) k_gemm_tc(const __grid_constant__ GemmLaunch g) {
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
   GemmShared* sh = reinterpret_cast<GemmShared*>(smem + kGemmSlots * kTcStageBytes);
@@ -365,16 +365,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
   if (tid == 0 && sh->dead && g.err != nullptr) atomicExch(g.err, 1);
 }
 
-// dW = upstream * sum_slabs partial, db likewise; deterministic order.  grid = ceil(NA*N / 256) + 1
-struct WreduceArgs {
+// dW = upstream * sum_slabs partial, db likewise; deterministic order; all layers in one launch.
+struct WreduceJob {
   const float* partial; const float* pbias; float* dw; float* db;
   int NA, N, Nout, slabs;                  // dw is (NA, Nout) row-major, Nout <= N (channel padding dropped)
+};
+struct WreduceLaunch {
+  WreduceJob job[2 * PNCE_MAX_LAYERS];
+  int start[2 * PNCE_MAX_LAYERS + 1];      // block prefix
+  int n;
   const float* grad_out;
 };
-__global__ void __launch_bounds__(kThreads) k_wreduce(const WreduceArgs a) {
-  const float g = a.grad_out ? __ldg(a.grad_out) : 1.0f;
+__global__ void __launch_bounds__(kThreads) k_wreduce(const __grid_constant__ WreduceLaunch gl) {
+  int ji = 0;
+  for (int i = 1; i < gl.n; ++i)
+    if ((int)blockIdx.x >= gl.start[i]) ji = i;
+  const WreduceJob& a = gl.job[ji];
+  const float g = gl.grad_out ? __ldg(gl.grad_out) : 1.0f;
   const long long total = (long long)a.NA * a.N;
-  const long long e = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long e = (long long)(blockIdx.x - gl.start[ji]) * kThreads + threadIdx.x;
   if (e < total) {
     const int i = (int)(e / a.N), n = (int)(e - (long long)i * a.N);
     if (n < a.Nout) {
@@ -390,15 +399,26 @@ __global__ void __launch_bounds__(kThreads) k_wreduce(const WreduceArgs a) {
   }
 }
 
-// fp32 weights -> weight blobs.  w is (R, Cw) row-major; the blob holds B[n][k] = transpose ? w[k][n] : w[n][k]
-// for n < N, k < K (zero padded).  grid = N/8 * K/8 blocks of 64 threads.
-struct WprepArgs {
+// fp32 weights -> weight blobs, every blob of every layer in ONE launch.  w is (R, Cw) row-major; the
+// blob holds B[n][k] = transpose ? w[k][n] : w[n][k] for n < N, k < K (zero padded).
+// One block of 64 threads per 8x8 core matrix.
+struct WprepJob {
   const float* w; __nv_bfloat16 *hi, *lo;
   int R, Cw, N, K, transpose;
 };
-__global__ void __launch_bounds__(64) k_wprep(const WprepArgs a) {
+struct WprepLaunch {
+  WprepJob job[4 * PNCE_MAX_LAYERS];
+  int start[4 * PNCE_MAX_LAYERS + 1];
+  int n;
+};
+__global__ void __launch_bounds__(64) k_wprep(const __grid_constant__ WprepLaunch g) {
+  int ji = 0;
+  for (int i = 1; i < g.n; ++i)
+    if ((int)blockIdx.x >= g.start[i]) ji = i;
+  const WprepJob& a = g.job[ji];
+  const int blk = blockIdx.x - g.start[ji];
   const int N8 = a.N >> 3;
-  const int n8 = blockIdx.x % N8, k8 = blockIdx.x / N8;
+  const int n8 = blk % N8, k8 = blk / N8;
   const int n = n8 * 8 + (threadIdx.x >> 3), k = k8 * 8 + (threadIdx.x & 7);
   float v = 0.f;
   if (!a.transpose) { if (n < a.R && k < a.Cw) v = a.w[(size_t)n * a.Cw + k]; }

@@ -764,20 +764,28 @@ int pnce_head_fwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_la
   // 1. ids -> sorted slots; weights -> operand blobs
   rc = launch_prep(pg, st);
   if (rc != PNCE_OK) return rc;
-  for (int l = 0; l < n_layers; ++l) {
-    const HeadLayerBufs& hb = hp.hb[l];
-    const int C = layers[l].C, Cp = pg.L[l].Cp;
-    WprepArgs a;
-    a.w = heads[l].w1; a.hi = hb.w1[0]; a.lo = hb.w1[1]; a.R = nc; a.Cw = C; a.N = nc; a.K = Cp; a.transpose = 0;
-    k_wprep<<<(nc / 8) * (Cp / 8), 64, 0, st>>>(a);
-    a.hi = hb.w1t[0]; a.lo = hb.w1t[1]; a.N = Cp; a.K = nc; a.transpose = 1;
-    k_wprep<<<(Cp / 8) * (nc / 8), 64, 0, st>>>(a);
-    a.w = heads[l].w2; a.hi = hb.w2[0]; a.lo = hb.w2[1]; a.R = nc; a.Cw = nc; a.N = nc; a.K = nc; a.transpose = 0;
-    k_wprep<<<(nc / 8) * (nc / 8), 64, 0, st>>>(a);
-    a.hi = hb.w2t[0]; a.lo = hb.w2t[1]; a.transpose = 1;
-    k_wprep<<<(nc / 8) * (nc / 8), 64, 0, st>>>(a);
+  {
+    static thread_local WprepLaunch wl;
+    memset(&wl, 0, sizeof(wl));
+    int blocks = 0;
+    auto add = [&](const float* w, __nv_bfloat16* hi, __nv_bfloat16* lo, int R, int Cw, int N, int K, int tr) {
+      WprepJob& j = wl.job[wl.n];
+      j.w = w; j.hi = hi; j.lo = lo; j.R = R; j.Cw = Cw; j.N = N; j.K = K; j.transpose = tr;
+      wl.start[wl.n++] = blocks;
+      blocks += (N / 8) * (K / 8);
+    };
+    for (int l = 0; l < n_layers; ++l) {
+      const HeadLayerBufs& hb = hp.hb[l];
+      const int C = layers[l].C, Cp = pg.L[l].Cp;
+      add(heads[l].w1, hb.w1[0], hb.w1[1], nc, C, nc, Cp, 0);     // B[n][k] = W1[n][k]      (H = X W1^T)
+      add(heads[l].w1, hb.w1t[0], hb.w1t[1], nc, C, Cp, nc, 1);   // B[c][j] = W1[j][c]      (dX = dH W1)
+      add(heads[l].w2, hb.w2[0], hb.w2[1], nc, nc, nc, nc, 0);    // B[n][k] = W2[n][k]      (Y = H W2^T)
+      add(heads[l].w2, hb.w2t[0], hb.w2t[1], nc, nc, nc, nc, 1);  // B[j][i] = W2[i][j]      (dH = dY W2)
+    }
+    wl.start[wl.n] = blocks;
+    k_wprep<<<(unsigned)blocks, 64, 0, st>>>(wl);
+    PNCE_CUDA(cudaGetLastError());
   }
-  PNCE_CUDA(cudaGetLastError());
   // 2. raw patches of both sides as row blobs
   rc = launch_gather_tc(pg, st);
   if (rc != PNCE_OK) return rc;
@@ -895,18 +903,27 @@ int pnce_head_bwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_la
   if (rc != PNCE_OK) return rc;
   k_wgrad_tc<<<(unsigned)acc, kTcThreads, kWgSmemBytes, st>>>(wg);
   PNCE_CUDA(cudaGetLastError());
-  for (int l = 0; l < n_layers; ++l) {
-    const HeadLayerBufs& hb = hp.hb[l];
-    const LayerDev& G = pg.L[l];
-    WreduceArgs a;
-    a.partial = hb.pw2; a.pbias = hb.pb2; a.dw = heads[l].dw2; a.db = heads[l].db2;
-    a.NA = nc; a.N = nc; a.Nout = nc; a.slabs = hb.slabs; a.grad_out = grad_out;
-    k_wreduce<<<(unsigned)(((long long)nc * nc + nc + kThreads - 1) / kThreads), kThreads, 0, st>>>(a);
-    a.partial = hb.pw1; a.pbias = hb.pb1; a.dw = heads[l].dw1; a.db = heads[l].db1;
-    a.N = G.Cp; a.Nout = G.C;
-    k_wreduce<<<(unsigned)(((long long)nc * G.Cp + nc + kThreads - 1) / kThreads), kThreads, 0, st>>>(a);
+  {
+    static thread_local WreduceLaunch rl;
+    memset(&rl, 0, sizeof(rl));
+    rl.grad_out = grad_out;
+    int blocks = 0;
+    for (int l = 0; l < n_layers; ++l) {
+      const HeadLayerBufs& hb = hp.hb[l];
+      const LayerDev& G = pg.L[l];
+      for (int which = 0; which < 2; ++which) {
+        WreduceJob& j = rl.job[rl.n];
+        j.partial = which ? hb.pw1 : hb.pw2; j.pbias = which ? hb.pb1 : hb.pb2;
+        j.dw = which ? heads[l].dw1 : heads[l].dw2; j.db = which ? heads[l].db1 : heads[l].db2;
+        j.NA = nc; j.N = which ? G.Cp : nc; j.Nout = which ? G.C : nc; j.slabs = hb.slabs;
+        rl.start[rl.n++] = blocks;
+        blocks += (int)(((long long)nc * j.N + nc + kThreads - 1) / kThreads);
+      }
+    }
+    rl.start[rl.n] = blocks;
+    k_wreduce<<<(unsigned)blocks, kThreads, 0, st>>>(rl);
+    PNCE_CUDA(cudaGetLastError());
   }
-  PNCE_CUDA(cudaGetLastError());
   // 4. dense d tgt_feat (zero fill + sampled positions), scaled by the upstream gradient
   return launch_dense(pg, st);
 }
