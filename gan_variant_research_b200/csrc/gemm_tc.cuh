@@ -5,8 +5,8 @@
 //   matrices of 128 B), so one 1-D bulk copy (UBLKCP) lands an operand chunk ready for UTCHMMA:
 //     row blob   [tile of 128 rows][col/8][16 row groups][8 rows][8 cols]   activations X, H, Y, dY, dH
 //     weight blob          [k/8][n/8 row groups][8 n][8 k]                  W as the B operand (N x K)
-//   * k_gemm_tc  : D(128 x N) = A_tile(128 x K) B^T, both K-major, K streamed in chunks of 32 through a
-//                  2-slot ring, two CTAs per SM; warp-specialised like k_loss_tc (producer / MMA issuer / 4 epilogue
+//   * k_gemm_tc  : D(128 x N) = A_tile(128 x K) B^T, both K-major, K streamed in chunks of 16 through a
+//                  4-slot ring, two CTAs per SM; warp-specialised like k_loss_tc (producer / MMA issuer / 4 epilogue
 //                  warps, thread <-> row).  The epilogue mode decides what leaves the SM:
 //                  H = relu(.+b1) as the next GEMM's A blob; Y = .+b2 directly in the operand formats
 //                  k_loss_tc consumes (so the logits kernel runs unchanged on the head's output);
@@ -46,8 +46,12 @@ struct GemmLaunch {
   int* err;                                // protocol-timeout flag (nonfinite[1])
 };
 
-constexpr int kGemmSlots = 2;                // 2 x 48 KB: two CTAs per SM, one's epilogue overlaps the other's MMAs
-constexpr int kGemmSmemBytes = kGemmSlots * kTcStageBytes + 256;
+// ring: 4 slots x 24 KB (16 columns of K per stage: A hi 4K | A lo 4K | B hi 8K | B lo 8K) = 96 KB, so two
+// CTAs fit one SM (one's epilogue overlaps the other's MMAs) and each keeps 3 bulk copies in flight
+constexpr int kGemmSlots = 4;
+constexpr int kGemmStageBytes = 24576;
+constexpr int kGemmOffAlo = 4096, kGemmOffBhi = 8192, kGemmOffBlo = 16384;
+constexpr int kGemmSmemBytes = kGemmSlots * kGemmStageBytes + 256;
 
 struct GemmShared {
   uint64_t full[kGemmSlots], empty[kGemmSlots], dfull;
@@ -69,14 +73,14 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
 __global__ void __launch_bounds__(kTcThreads, 2) k_gemm_tc(const __grid_constant__ GemmLaunch g) {
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
-  GemmShared* sh = reinterpret_cast<GemmShared*>(smem + kGemmSlots * kTcStageBytes);
+  GemmShared* sh = reinterpret_cast<GemmShared*>(smem + kGemmSlots * kGemmStageBytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int pi = 0;
   for (int i = 1; i < g.n; ++i)
     if ((long long)blockIdx.x >= g.start[i]) pi = i;
   const GemmProb& pr = g.pr[pi];
   const int tile = (int)(blockIdx.x - g.start[pi]);
-  const int K = pr.K, N = pr.N, nstage = K >> 5, K8 = K >> 3, N8 = N >> 3;
+  const int K = pr.K, N = pr.N, nstage = K >> 4, K8 = K >> 3, N8 = N >> 3;
   const bool x3 = g.x3 != 0;
   volatile int* dead = &sh->dead;
   if (tid == 0) {
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_gemm_tc(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
-  const uint32_t bbytes = (uint32_t)N * 64u;                // one B chunk: 4 slabs x N rows x 16 B
+  const uint32_t bbytes = (uint32_t)N * 32u;                // one B chunk: 2 slabs x N rows x 16 B
   const uint32_t lbo_b = (uint32_t)N * 16u;
 
   if (warp == 0) {
@@ -102,12 +106,12 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_gemm_tc(const __grid_constant
       for (int s = 0; s < nstage; ++s) {
         const int slot = s % kGemmSlots;
         if (!mbar_wait(&sh->empty[slot], ((uint32_t)(s / kGemmSlots) & 1u) ^ 1u, dead)) break;
-        unsigned char* st = smem + slot * kTcStageBytes;
-        mbar_expect_tx(&sh->full[slot], (8192u + bbytes) * (x3 ? 2u : 1u));
-        bulk_g2s(st, ga_hi + (size_t)s * 8192, 8192u, &sh->full[slot]);
-        if (x3) bulk_g2s(st + kTcOffQlo, ga_lo + (size_t)s * 8192, 8192u, &sh->full[slot]);
-        bulk_g2s(st + kTcOffKhi, gb_hi + (size_t)s * bbytes, bbytes, &sh->full[slot]);
-        if (x3) bulk_g2s(st + kTcOffKlo, gb_lo + (size_t)s * bbytes, bbytes, &sh->full[slot]);
+        unsigned char* st = smem + slot * kGemmStageBytes;
+        mbar_expect_tx(&sh->full[slot], (4096u + bbytes) * (x3 ? 2u : 1u));
+        bulk_g2s(st, ga_hi + (size_t)s * 4096, 4096u, &sh->full[slot]);
+        if (x3) bulk_g2s(st + kGemmOffAlo, ga_lo + (size_t)s * 4096, 4096u, &sh->full[slot]);
+        bulk_g2s(st + kGemmOffBhi, gb_hi + (size_t)s * bbytes, bbytes, &sh->full[slot]);
+        if (x3) bulk_g2s(st + kGemmOffBlo, gb_lo + (size_t)s * bbytes, bbytes, &sh->full[slot]);
       }
     }
   } else if (warp == 1) {
@@ -118,18 +122,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_gemm_tc(const __grid_constant
         const int slot = s % kGemmSlots;
         ok = mbar_wait(&sh->full[slot], (uint32_t)(s / kGemmSlots) & 1u, dead);
         tc_fence_after();
-        const uint32_t st = smem_u32(smem + slot * kTcStageBytes);
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t a_hi = smem_desc(st + ks * 4096, 2048, 128);
-          const uint64_t b_hi = smem_desc(st + kTcOffKhi + ks * 2 * lbo_b, lbo_b, 128);
-          mma_bf16(tmem, a_hi, b_hi, idesc, (s | ks) ? 1u : 0u);
-          if (x3) {
-            const uint64_t a_lo = smem_desc(st + kTcOffQlo + ks * 4096, 2048, 128);
-            const uint64_t b_lo = smem_desc(st + kTcOffKlo + ks * 2 * lbo_b, lbo_b, 128);
-            mma_bf16(tmem, a_hi, b_lo, idesc, 1u);
-            mma_bf16(tmem, a_lo, b_hi, idesc, 1u);
-          }
+        const uint32_t st = smem_u32(smem + slot * kGemmStageBytes);
+        const uint64_t a_hi = smem_desc(st, 2048, 128);
+        const uint64_t b_hi = smem_desc(st + kGemmOffBhi, lbo_b, 128);
+        mma_bf16(tmem, a_hi, b_hi, idesc, s ? 1u : 0u);
+        if (x3) {
+          const uint64_t a_lo = smem_desc(st + kGemmOffAlo, 2048, 128);
+          const uint64_t b_lo = smem_desc(st + kGemmOffBlo, lbo_b, 128);
+          mma_bf16(tmem, a_hi, b_lo, idesc, 1u);
+          mma_bf16(tmem, a_lo, b_hi, idesc, 1u);
         }
         mma_commit(&sh->empty[slot]);
       }

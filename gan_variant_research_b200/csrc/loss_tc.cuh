@@ -242,16 +242,8 @@ template <int NP>
 __device__ __forceinline__ void tc_dq_epilogue(uint32_t tacc, int nstage, int C, const float* __restrict__ qrow,
                                                float* __restrict__ dxrow, float c1, float c2, bool rowok,
                                                __nv_bfloat16* dyh, __nv_bfloat16* dyl, uint64_t* dqfull,
-                                               volatile int* dead) {
+                                               volatile int* dead, float (&qa)[32], float (&qb)[32]) {
   using namespace umma;
-  // raw q values are prefetched two chunks ahead (static double buffer); padding rows read row 0 of
-  // the image (always mapped) and never store
-  float qa[32], qb[32];
-#pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    qa[k] = (k < C) ? __ldcg(qrow + k * NP) : 0.f;
-    qb[k] = (32 + k < C) ? __ldcg(qrow + (32 + k) * NP) : 0.f;
-  }
   mbar_wait(dqfull, 0u, dead);
   tc_fence_after();
   for (int s = 0; s < nstage; s += 2) {
@@ -483,6 +475,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       float rowloss = rowok ? (lse2 - yd) * kLn2 : 0.f;        // :94, labels = arange
       if (badrow && rowok) rowloss = __int_as_float(0x7fc00000);
       PNCE_TR(3);
+      // raw q of the first two channel chunks for the dQ epilogue: issued now, so the loads fly under
+      // pass B (phase 2 finishes right behind pass B: there is no other slack to hide them in);
+      // padding rows read slot 0 of the image (always mapped) and never store
+      const int gsafe = rowok ? gi : 0;
+      const float* __restrict__ qrow = L.qT + (size_t)b * C * N + gsafe;
+      float qa[32], qb[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        qa[k] = (k < C) ? __ldcg(qrow + (size_t)k * N) : 0.f;
+        qb[k] = (32 + k < C) ? __ldcg(qrow + (size_t)(32 + k) * N) : 0.f;
+      }
       // ---- pass B: dZ (pre-divided by ||k_j||) -> smem A operand chunk by chunk, s_i ----
       float s2 = 0.f;
       const uint32_t rowoff = (uint32_t)(i >> 3) * 128u + (uint32_t)(i & 7) * 16u;
@@ -507,16 +510,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       //   dx = dq*sc - q_raw * (sc^2 s_i)       with dq = acc / tau
       const float c1 = inv_tau * sc;
       const float c2 = noproj ? 0.f : sc * sc * s_i;
-      const int gsafe = rowok ? gi : 0;
-      const float* __restrict__ qrow = L.qT + (size_t)b * C * N + gsafe;
       float* __restrict__ dxrow = L.dxT + (size_t)b * C * N + gsafe;        // dxpitch == N on this path
       PNCE_TR(5);
       // head mode: d loss / d (head output) as a row blob [tile = b*halves+mh][c/8][16][8][8]
       const size_t dyoff = (((size_t)b * halves + mh) * Cp8 * 16 + (size_t)(i >> 3)) * 64 + (size_t)(i & 7) * 8;
       __nv_bfloat16* dyh = L.dyhi ? L.dyhi + dyoff : nullptr;
       __nv_bfloat16* dyl = (L.dyhi && L.dylo) ? L.dylo + dyoff : nullptr;
-      if (N == 256) tc_dq_epilogue<256>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead);
-      else tc_dq_epilogue<128>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead);
+      if (N == 256) tc_dq_epilogue<256>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb);
+      else tc_dq_epilogue<128>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb);
       PNCE_TR(6);
       tc_fence_before();
     }
