@@ -74,6 +74,7 @@ struct Params {
 // CTA -> layer map for one launch: blocks [start[l], start[l+1]) work on layer l.
 struct BlockMap {
   long long start[PNCE_MAX_LAYERS + 2];
+  int layer[PNCE_MAX_LAYERS];          // slot -> layer (launch_loss_tc orders heavy layers first)
 };
 
 __device__ __forceinline__ int find_layer(const BlockMap& m, long long blk, int n) {

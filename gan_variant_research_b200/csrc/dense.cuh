@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(THREADS) k_dense_flat(const __grid_constant__ 
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int i = k * THREADS + tid;
-      if (i < n16) dst[i] = t4[i];
+      if (i < n16) __stcs(dst + i, t4[i]);               // streaming: keep dxT / sid resident in L2 instead
     }
   } else {                                                   // odd map sizes: element-wise, still coalesced
     for (int i = tid; i < npos; i += THREADS) drow[i] = tile[i];

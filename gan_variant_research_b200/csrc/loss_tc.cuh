@@ -274,9 +274,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
   TcShared* sh = reinterpret_cast<TcShared*>(invk_s + 256);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int l = find_layer(m, blockIdx.x, p.n_layers);
+  const int slot_l = find_layer(m, blockIdx.x, p.n_layers);
+  const int l = m.layer[slot_l];
   const LayerDev& L = p.L[l];
-  const int local = (int)(blockIdx.x - m.start[l]);
+  const int local = (int)(blockIdx.x - m.start[slot_l]);
   const int halves = L.Ppad >> 7;
   const int mh = local % halves, b = p.b0 + local / halves;
   const int N = L.Ppad, P = L.P, C = L.C, Cp8 = L.Cp >> 3, nstage = L.nchunk;

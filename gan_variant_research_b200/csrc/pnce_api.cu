@@ -215,10 +215,16 @@ static int launch_gather_tc(const Params& p, cudaStream_t st) {
 static int launch_loss_tc(const Params& p, cudaStream_t st) {
   BlockMap m;
   memset(&m, 0, sizeof(m));
+  // heavy layers (large C) first: the last, partially filled wave of CTAs is then made of the cheap ones
+  int order[PNCE_MAX_LAYERS];
+  for (int l = 0; l < p.n_layers; ++l) order[l] = l;
+  for (int i = 1; i < p.n_layers; ++i)
+    for (int j = i; j > 0 && p.L[order[j]].C > p.L[order[j - 1]].C; --j) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
   long long acc = 0;
-  for (int l = 0; l < p.n_layers; ++l) {
-    m.start[l] = acc;
-    acc += (long long)p.bn * (p.L[l].Ppad / 128);
+  for (int s = 0; s < p.n_layers; ++s) {
+    m.start[s] = acc;
+    m.layer[s] = order[s];
+    acc += (long long)p.bn * (p.L[order[s]].Ppad / 128);
   }
   m.start[p.n_layers] = acc;
   int rc = set_smem(k_loss_tc, kTcSmemBytes);

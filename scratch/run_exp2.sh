@@ -1,4 +1,3 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
-timeout 300 python scratch/exp4.py 2>&1 | grep -v Warn | head -12
-timeout 300 python scratch/exp3.py 2>&1 | grep -v Warn | head -9
+timeout 600 python -m pytest tests/test_vs_eager_gpu.py -m gpu -q -s 2>&1 | tail -8
+timeout 900 python scratch/config_sweep.py 2>&1 | grep -v Warn | tee gpurun_out/config_sweep.jsonl
