@@ -39,10 +39,10 @@ struct LayerDev {
   float* dq_rows;            // optional [B][P][C] output of the rows API (then dxT/qinv unused)
   int nparts;                // partial row-loss sums per image (ntiles on the SIMT path, halves on TC)
   // ---- tensor-core path (gather_tc.cuh / loss_tc.cuh) ----
-  int Cp, Ppad, nchunk;      // C rounded up to 32, P rounded up to 128 (<= 256), Cp / 32
+  int Cp, Ppad, nchunk;      // C rounded up to 32, P rounded up to 128 (<= 1024), Cp / 32
   __nv_bfloat16* qhi;        // Q operand blob, bf16 high part   [B][Ppad/128][Cp/8][16][8][8]
   __nv_bfloat16* qlo;        // low part (value - hi), NULL in single-pass bf16 mode
-  __nv_bfloat16* khi;        // K operand blob                   [B][Cp/8][Ppad/8][8][8]
+  __nv_bfloat16* khi;        // K operand blob, key blocks of <= 256  [B][kb][Cp/8][NB/8][8][8]
   __nv_bfloat16* klo;
   __nv_bfloat16* k2hi;       // the same K values, key-major  [B][Ppad/8][Cp/8][8][8]  (phase-2 B operand)
   __nv_bfloat16* k2lo;
@@ -52,6 +52,7 @@ struct LayerDev {
   float* qT;                 // [B][C][Ppad] raw fp32 target patches (transposed)
   float* qss;                // [B][nchunk][Ppad] partial sums of squares (NaN: non-finite element)
   float* kss;
+  float* kinv;               // [B][Ppad] 1/max(||k_j||, eps) (0 for padding / non-finite rows), P > 256 only
 };
 
 struct Params {

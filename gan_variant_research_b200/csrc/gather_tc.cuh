@@ -24,10 +24,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
 
 template <typename T>
 __device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long local) {
-  const int p = threadIdx.x;
   const int nchunk = L.nchunk;
+  const int npb = (L.Ppad + 255) >> 8;                       // CTAs of 256 patch slots per (image, side, chunk)
   const int s = (int)(local % nchunk);
-  const long long rest = local / nchunk;
+  const int pb = (int)((local / nchunk) % npb);
+  const long long rest = local / nchunk / npb;
+  const int p = pb * 256 + threadIdx.x;
   const int b = b0 + (int)(rest % B);
   const int side = (int)(rest / B);                          // 0 = src (k), 1 = tgt (q)
   const int C = L.C, HW = L.HW, P = L.P, Ppad = L.Ppad, Cp8 = L.Cp >> 3;
@@ -57,7 +59,10 @@ __device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long loca
     const int c8 = s * 4 + g;
     size_t cm;                                                // core-matrix index
     if (side || L.head_src_rows) cm = (((size_t)b * (Ppad >> 7) + (p >> 7)) * Cp8 + c8) * 16 + ((p & 127) >> 3);
-    else cm = ((size_t)b * Cp8 + c8) * (Ppad >> 3) + (p >> 3);
+    else {                                                    // key blocks of <= 256 rows, one after the other
+      const int nb8 = min(256, Ppad - pb * 256) >> 3;
+      cm = (((size_t)b * Ppad + (size_t)pb * 256) * Cp8) / 8 + (size_t)c8 * nb8 + ((p & 255) >> 3);
+    }
     const size_t off = cm * 64 + (size_t)(p & 7) * 8;         // elements
     uint32_t hw[4], lw[4];
 #pragma unroll
@@ -88,7 +93,7 @@ __device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long loca
   }
 }
 
-// grid = sum_l 2*B*nchunk_l
+// grid = sum_l 2 * B * ceil(Ppad_l / 256) * nchunk_l
 __global__ void __launch_bounds__(kThreads) k_gather_tc(const __grid_constant__ Params p,
                                                         const __grid_constant__ BlockMap m) {
   const long long blk = blockIdx.x;

@@ -23,7 +23,9 @@
 //             dZ[:, 32j..32j+31]: phase 2 overlaps pass B.  Accumulator: TMEM cols [256, 256+C)
 //   epilogue  dq/tau, normalise backward, dxT[b][c][slot] (unit upstream gradient), coalesced.
 // The logits, softmax and dZ never leave the SM.  Replaces patchnce_cut.py:83-110 and the autograd
-// backward of :77-94.  Shapes: P <= 256, C <= 256.
+// backward of :77-94.  Shapes: P <= 1024, C <= 256.
+// P > 256: the keys are processed in blocks of 256 (flash-style): pass 1 accumulates the row sums block
+// by block, pass 2 recomputes each logits block, turns it into dZ and accumulates dQ += dZ_blk K_blk.
 #pragma once
 #include "common.cuh"
 #include "loss_simt.cuh"
@@ -44,7 +46,7 @@ constexpr int kTcSlots2 = 3;                // phase-2 slots (K only, 32 KB each
 constexpr int kTcStage2Bytes = 32768;       // Khi 16K | Klo 16K
 
 struct TcShared {
-  uint64_t full1[kTcSlots1], empty1[kTcSlots1], full2[kTcSlots2], empty2[kTcSlots2], zfull, dzready[8], dqfull;
+  uint64_t full1[kTcSlots1], empty1[kTcSlots1], full2[kTcSlots2], empty2[kTcSlots2], zfull, dzready[8], dqfull, zfree, p2done;
   uint32_t tmem_base;
   int dead;
   int flag;
@@ -196,10 +198,11 @@ __device__ __forceinline__ void tc_row_pass_b(uint32_t trow, int nch, const floa
 // dQ epilogue for one 32-channel chunk; NP = pitch of qT and dxT rows (compile-time: immediates).
 // Head mode (dyh != NULL): the gradient w.r.t. the head output leaves as a bf16 hi(+lo) row blob
 // (the A operand of the head's backward GEMMs) instead of fp32 rows; padding rows are written as 0.
-template <int NP>
+template <int NPC>
 __device__ __forceinline__ void tc_dq_chunk(const uint32_t (&r)[32], float (&qv)[32], const float* __restrict__ qp,
                                             float* __restrict__ dp, int nvalid, int nnext, float c1, float c2,
-                                            bool rowok, __nv_bfloat16* dyh, __nv_bfloat16* dyl) {
+                                            bool rowok, __nv_bfloat16* dyh, __nv_bfloat16* dyl, int np_rt) {
+  const size_t NP = NPC ? (size_t)NPC : (size_t)np_rt;      // NPC = 0: run-time pitch (P > 256)
   float out[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) out[k] = fmaf(-qv[k], c2, __uint_as_float(r[k]) * c1);
@@ -238,27 +241,28 @@ __device__ __forceinline__ void tc_dq_chunk(const uint32_t (&r)[32], float (&qv)
   }
 }
 
-template <int NP>
+template <int NPC>
 __device__ __forceinline__ void tc_dq_epilogue(uint32_t tacc, int nstage, int C, const float* __restrict__ qrow,
                                                float* __restrict__ dxrow, float c1, float c2, bool rowok,
                                                __nv_bfloat16* dyh, __nv_bfloat16* dyl, uint64_t* dqfull,
-                                               volatile int* dead, float (&qa)[32], float (&qb)[32]) {
+                                               volatile int* dead, float (&qa)[32], float (&qb)[32], int np_rt = 0) {
   using namespace umma;
+  const size_t NP = NPC ? (size_t)NPC : (size_t)np_rt;
   mbar_wait(dqfull, 0u, dead);
   tc_fence_after();
   for (int s = 0; s < nstage; s += 2) {
     uint32_t r[32];
     tmem_ld32(tacc + s * 32, r);
     tmem_ld_wait();
-    tc_dq_chunk<NP>(r, qa, qrow + (size_t)(s + 2) * 32 * NP, dxrow + (size_t)s * 32 * NP, C - s * 32,
-                    C - (s + 2) * 32, c1, c2, rowok, dyh ? dyh + (size_t)s * 4096 : nullptr,
-                    dyl ? dyl + (size_t)s * 4096 : nullptr);
+    tc_dq_chunk<NPC>(r, qa, qrow + (size_t)(s + 2) * 32 * NP, dxrow + (size_t)s * 32 * NP, C - s * 32,
+                     C - (s + 2) * 32, c1, c2, rowok, dyh ? dyh + (size_t)s * 4096 : nullptr,
+                     dyl ? dyl + (size_t)s * 4096 : nullptr, np_rt);
     if (s + 1 < nstage) {
       tmem_ld32(tacc + (s + 1) * 32, r);
       tmem_ld_wait();
-      tc_dq_chunk<NP>(r, qb, qrow + (size_t)(s + 3) * 32 * NP, dxrow + (size_t)(s + 1) * 32 * NP, C - (s + 1) * 32,
-                      C - (s + 3) * 32, c1, c2, rowok, dyh ? dyh + (size_t)(s + 1) * 4096 : nullptr,
-                      dyl ? dyl + (size_t)(s + 1) * 4096 : nullptr);
+      tc_dq_chunk<NPC>(r, qb, qrow + (size_t)(s + 3) * 32 * NP, dxrow + (size_t)(s + 1) * 32 * NP, C - (s + 1) * 32,
+                       C - (s + 3) * 32, c1, c2, rowok, dyh ? dyh + (size_t)(s + 1) * 4096 : nullptr,
+                       dyl ? dyl + (size_t)(s + 1) * 4096 : nullptr, np_rt);
     }
   }
 }
@@ -280,7 +284,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
   const int local = (int)(blockIdx.x - m.start[slot_l]);
   const int halves = L.Ppad >> 7;
   const int mh = local % halves, b = p.b0 + local / halves;
-  const int N = L.Ppad, P = L.P, C = L.C, Cp8 = L.Cp >> 3, nstage = L.nchunk;
+  const int Ppad = L.Ppad, P = L.P, C = L.C, Cp = L.Cp, Cp8 = L.Cp >> 3, nstage = L.nchunk;
+  // keys are processed in blocks of <= 256 (the logits block must fit 256 TMEM columns next to the dQ
+  // accumulator).  One block (P <= 256): Z is computed once.  More blocks: flash-style two passes --
+  // pass 1 accumulates the row sums of exp2 block by block, pass 2 recomputes each Z block for dZ.
+  const int nkb = (Ppad + 255) >> 8;
+  const bool multi = nkb > 1;
+  const int nslots1 = multi ? 2 : kTcSlots1;                  // the dZ region is busy in pass 2 of the multi-block case
   const bool x3 = (p.math == PNCE_MATH_TC_BF16X3);
   volatile int* dead = &sh->dead;
   long long* tr = nullptr;                                   // debug stamps (pnce_debug_set key 3)
@@ -290,7 +300,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
   if (tid == 0) {
     for (int k = 0; k < kTcSlots1; ++k) { mbar_init(&sh->full1[k], 1); mbar_init(&sh->empty1[k], 1); }
     for (int k = 0; k < kTcSlots2; ++k) { mbar_init(&sh->full2[k], 1); mbar_init(&sh->empty2[k], 1); }
-    mbar_init(&sh->zfull, 1); mbar_init(&sh->dqfull, 1);
+    mbar_init(&sh->zfull, 1); mbar_init(&sh->dqfull, 1); mbar_init(&sh->zfree, 128); mbar_init(&sh->p2done, 1);
     for (int k = 0; k < 8; ++k) mbar_init(&sh->dzready[k], 128);
     sh->dead = 0;
     sh->badk = 0;
@@ -301,99 +311,125 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
-  const uint32_t kbytes = (uint32_t)N * 64u;                 // one K chunk: 4 slabs x N/8 core matrices x 128 B
-  const uint32_t lbo_k = (uint32_t)N * 16u;                  // slab (c/8) stride of a K chunk in smem
+  const int npass = multi ? 2 : 1;
 
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
-      const unsigned char* gq_hi = reinterpret_cast<const unsigned char*>(L.qhi) +
-                                   ((size_t)b * halves + mh) * Cp8 * 2048;
-      const unsigned char* gq_lo = reinterpret_cast<const unsigned char*>(L.qlo) +
-                                   ((size_t)b * halves + mh) * Cp8 * 2048;
-      const unsigned char* gk_hi = reinterpret_cast<const unsigned char*>(L.khi) + (size_t)b * Cp8 * (N * 16);
-      const unsigned char* gk_lo = reinterpret_cast<const unsigned char*>(L.klo) + (size_t)b * Cp8 * (N * 16);
+      const unsigned char* gq_hi = reinterpret_cast<const unsigned char*>(L.qhi) + ((size_t)b * halves + mh) * Cp8 * 2048;
+      const unsigned char* gq_lo = reinterpret_cast<const unsigned char*>(L.qlo) + ((size_t)b * halves + mh) * Cp8 * 2048;
+      const unsigned char* gk_hi = reinterpret_cast<const unsigned char*>(L.khi) + (size_t)b * Ppad * Cp * 2;
+      const unsigned char* gk_lo = reinterpret_cast<const unsigned char*>(L.klo) + (size_t)b * Ppad * Cp * 2;
+      const unsigned char* g2_hi = reinterpret_cast<const unsigned char*>(L.k2hi) + (size_t)b * Ppad * Cp * 2;
+      const unsigned char* g2_lo = reinterpret_cast<const unsigned char*>(L.k2lo) + (size_t)b * Ppad * Cp * 2;
+      const uint32_t k2bytes = (uint32_t)Cp * 64u;            // 32 keys x Cp channels x 2 B
+      uint32_t it1 = 0, it2 = 0, nz = 0;
       bool ok = true;
-      for (int s = 0; s < nstage && ok; ++s) {                // phase 1: Q and K chunks
-        const int slot = s % kTcSlots1;
-        ok = mbar_wait(&sh->empty1[slot], ((uint32_t)(s / kTcSlots1) & 1u) ^ 1u, dead);
-        if (!ok) break;
-        unsigned char* st = (slot < 2 ? stage0 : dzhi - 2 * kTcStageBytes) + slot * kTcStageBytes;
-        mbar_expect_tx(&sh->full1[slot], (8192u + kbytes) * (x3 ? 2u : 1u));
-        bulk_g2s(st, gq_hi + (size_t)s * 8192, 8192u, &sh->full1[slot]);
-        if (x3) bulk_g2s(st + kTcOffQlo, gq_lo + (size_t)s * 8192, 8192u, &sh->full1[slot]);
-        bulk_g2s(st + kTcOffKhi, gk_hi + (size_t)s * kbytes, kbytes, &sh->full1[slot]);
-        if (x3) bulk_g2s(st + kTcOffKlo, gk_lo + (size_t)s * kbytes, kbytes, &sh->full1[slot]);
-      }
-      // phase 2 re-uses the ring region with its own slot geometry: wait until phase 1 has drained
-      if (ok) ok = mbar_wait(&sh->zfull, 0u, dead);
-      const unsigned char* g2_hi = reinterpret_cast<const unsigned char*>(L.k2hi) + (size_t)b * N * L.Cp * 2;
-      const unsigned char* g2_lo = reinterpret_cast<const unsigned char*>(L.k2lo) + (size_t)b * N * L.Cp * 2;
-      const uint32_t k2bytes = (uint32_t)L.Cp * 64u;          // 32 keys x Cp channels x 2 B
-      const int nkey = (P + 31) >> 5;
-      for (int j = 0; j < nkey && ok; ++j) {                  // phase 2: key-major K chunks
-        const int slot = j % kTcSlots2;
-        ok = mbar_wait(&sh->empty2[slot], ((uint32_t)(j / kTcSlots2) & 1u) ^ 1u, dead);
-        if (!ok) break;
-        unsigned char* st = stage0 + slot * kTcStage2Bytes;
-        mbar_expect_tx(&sh->full2[slot], k2bytes * (x3 ? 2u : 1u));
-        bulk_g2s(st, g2_hi + (size_t)j * k2bytes, k2bytes, &sh->full2[slot]);
-        if (x3) bulk_g2s(st + 16384, g2_lo + (size_t)j * k2bytes, k2bytes, &sh->full2[slot]);
+      for (int pass = 0; pass < npass && ok; ++pass) {
+        for (int kb = 0; kb < nkb && ok; ++kb) {
+          const int NB = min(256, Ppad - kb * 256);           // keys of this block (128 or 256)
+          const uint32_t kbytes = (uint32_t)NB * 64u;         // one K chunk: 4 slabs x NB/8 core matrices x 128 B
+          const size_t kblk = (size_t)kb * 256 * Cp * 2;      // blocks are stored one after the other
+          for (int s = 0; s < nstage && ok; ++s, ++it1) {     // Z block: Q and K chunks of 32 channels
+            const int slot = it1 % nslots1;
+            ok = mbar_wait(&sh->empty1[slot], ((it1 / nslots1) & 1u) ^ 1u, dead);
+            if (!ok) break;
+            unsigned char* st = stage0 + slot * kTcStageBytes;
+            mbar_expect_tx(&sh->full1[slot], (8192u + kbytes) * (x3 ? 2u : 1u));
+            bulk_g2s(st, gq_hi + (size_t)s * 8192, 8192u, &sh->full1[slot]);
+            if (x3) bulk_g2s(st + kTcOffQlo, gq_lo + (size_t)s * 8192, 8192u, &sh->full1[slot]);
+            bulk_g2s(st + kTcOffKhi, gk_hi + kblk + (size_t)s * kbytes, kbytes, &sh->full1[slot]);
+            if (x3) bulk_g2s(st + kTcOffKlo, gk_lo + kblk + (size_t)s * kbytes, kbytes, &sh->full1[slot]);
+          }
+          // stay in lock-step with the MMA thread (a parity wait must never lag two phases behind)
+          if (ok) ok = mbar_wait(&sh->zfull, nz & 1u, dead);
+          if (pass == npass - 1) {
+            // dQ += dZ_block K_block: the ring region is re-used with the key-major slot geometry now
+            // that the Z block's MMAs have drained, and handed back when this block's dQ MMAs have
+            const int key0 = kb * 256, keys = min(P, key0 + 256) - key0;
+            const int nj = (keys + 31) >> 5;
+            for (int j = 0; j < nj && ok; ++j, ++it2) {
+              const int slot = it2 % kTcSlots2;
+              ok = mbar_wait(&sh->empty2[slot], ((it2 / kTcSlots2) & 1u) ^ 1u, dead);
+              if (!ok) break;
+              unsigned char* st = stage0 + slot * kTcStage2Bytes;
+              mbar_expect_tx(&sh->full2[slot], k2bytes * (x3 ? 2u : 1u));
+              bulk_g2s(st, g2_hi + (size_t)(kb * 8 + j) * k2bytes, k2bytes, &sh->full2[slot]);
+              if (x3) bulk_g2s(st + 16384, g2_lo + (size_t)(kb * 8 + j) * k2bytes, k2bytes, &sh->full2[slot]);
+            }
+            if (multi && kb + 1 < nkb && ok) ok = mbar_wait(&sh->p2done, (uint32_t)kb & 1u, dead);
+          }
+          ++nz;
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc1 = idesc_bf16(128, N, 0, 0);
-      bool ok = true;
-      PNCE_TR(8);
-      // phase 1: Z = Q K^T
-      for (int s = 0; s < nstage && ok; ++s) {
-        const int slot = s % kTcSlots1;
-        ok = mbar_wait(&sh->full1[slot], (uint32_t)(s / kTcSlots1) & 1u, dead);
-        tc_fence_after();
-        const uint32_t st = smem_u32((slot < 2 ? stage0 : dzhi - 2 * kTcStageBytes) + slot * kTcStageBytes);
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {                     // 16 channels = 2 slabs per MMA
-          const uint64_t a_hi = smem_desc(st + ks * 4096, 2048, 128);
-          const uint64_t b_hi = smem_desc(st + kTcOffKhi + ks * 2 * lbo_k, lbo_k, 128);
-          mma_bf16(tmem, a_hi, b_hi, idesc1, (s | ks) ? 1u : 0u);
-          if (x3) {
-            const uint64_t a_lo = smem_desc(st + kTcOffQlo + ks * 4096, 2048, 128);
-            const uint64_t b_lo = smem_desc(st + kTcOffKlo + ks * 2 * lbo_k, lbo_k, 128);
-            mma_bf16(tmem, a_hi, b_lo, idesc1, 1u);
-            mma_bf16(tmem, a_lo, b_hi, idesc1, 1u);
-          }
-        }
-        mma_commit(&sh->empty1[slot]);
-      }
-      mma_commit(&sh->zfull);
-      PNCE_TR(9);
-      // phase 2: dQ = dZ K, one stage per 32 keys, released chunk by chunk by the epilogue warps
-      const uint32_t idesc2 = idesc_bf16(128, L.Cp, 0, 1);   // B read MN-major (N = channel)
+      const uint32_t idesc2 = idesc_bf16(128, Cp, 0, 1);     // dQ: B read MN-major (N = channel)
       const uint32_t dzh = smem_u32(dzhi), dzl = smem_u32(dzlo);
       const uint32_t lbo2 = (uint32_t)Cp8 * 128u;             // 8-key group stride of a key-major chunk
-      const int nkey = (P + 31) >> 5;
-      for (int j = 0; j < nkey && ok; ++j) {
-        const int slot = j % kTcSlots2;
-        ok = mbar_wait(&sh->dzready[j], 0u, dead);
-        if (ok) ok = mbar_wait(&sh->full2[slot], (uint32_t)(j / kTcSlots2) & 1u, dead);
-        tc_fence_after();
-        if (j == 0) PNCE_TR(10);
-        const uint32_t st = smem_u32(stage0 + slot * kTcStage2Bytes);
+      uint32_t it1 = 0, it2 = 0, nz = 0;
+      bool ok = true;
+      PNCE_TR(8);
+      for (int pass = 0; pass < npass && ok; ++pass) {
+        for (int kb = 0; kb < nkb && ok; ++kb) {
+          const int NB = min(256, Ppad - kb * 256);
+          const uint32_t idesc1 = idesc_bf16(128, NB, 0, 0);
+          const uint32_t lbo_k = (uint32_t)NB * 16u;          // slab (c/8) stride of a K chunk in smem
+          // the previous Z block must have been read out of TMEM.  Pass 1: the epilogue says so (zfree);
+          // pass 2, kb > 0: implied by having consumed every dzready of the previous block.
+          if (multi && nz > 0 && (pass == 0 || kb == 0)) ok = mbar_wait(&sh->zfree, (nz - 1) & 1u, dead);
+          // ---- Z block = Q_half K_block^T ----
+          for (int s = 0; s < nstage && ok; ++s, ++it1) {
+            const int slot = it1 % nslots1;
+            ok = mbar_wait(&sh->full1[slot], (it1 / nslots1) & 1u, dead);
+            tc_fence_after();
+            const uint32_t st = smem_u32(stage0 + slot * kTcStageBytes);
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {                     // 16 keys per MMA
-          const uint64_t a_hi = smem_desc(dzh + (uint32_t)(j * 2 + ks) * 4096u, 2048, 128);
-          const uint64_t b_hi = smem_desc(st + (uint32_t)ks * 2u * lbo2, lbo2, 128);
-          mma_bf16(tmem + 256u, a_hi, b_hi, idesc2, (j | ks) ? 1u : 0u);
-          if (x3) {
-            const uint64_t a_lo = smem_desc(dzl + (uint32_t)(j * 2 + ks) * 4096u, 2048, 128);
-            const uint64_t b_lo = smem_desc(st + 16384u + (uint32_t)ks * 2u * lbo2, lbo2, 128);
-            mma_bf16(tmem + 256u, a_lo, b_hi, idesc2, 1u);
-            mma_bf16(tmem + 256u, a_hi, b_lo, idesc2, 1u);
+            for (int ks = 0; ks < 2; ++ks) {                 // 16 channels = 2 slabs per MMA
+              const uint64_t a_hi = smem_desc(st + ks * 4096, 2048, 128);
+              const uint64_t b_hi = smem_desc(st + kTcOffKhi + ks * 2 * lbo_k, lbo_k, 128);
+              mma_bf16(tmem, a_hi, b_hi, idesc1, (s | ks) ? 1u : 0u);
+              if (x3) {
+                const uint64_t a_lo = smem_desc(st + kTcOffQlo + ks * 4096, 2048, 128);
+                const uint64_t b_lo = smem_desc(st + kTcOffKlo + ks * 2 * lbo_k, lbo_k, 128);
+                mma_bf16(tmem, a_hi, b_lo, idesc1, 1u);
+                mma_bf16(tmem, a_lo, b_hi, idesc1, 1u);
+              }
+            }
+            mma_commit(&sh->empty1[slot]);
           }
+          mma_commit(&sh->zfull);
+          ++nz;
+          if (pass == 0 && kb == 0) PNCE_TR(9);
+          if (pass != npass - 1) continue;
+          // ---- dQ += dZ_block K_block, one stage per 32 keys, released chunk by chunk by the epilogue ----
+          const int key0 = kb * 256, keys = min(P, key0 + 256) - key0;
+          const int nj = (keys + 31) >> 5;
+          for (int j = 0; j < nj && ok; ++j, ++it2) {
+            const int slot = it2 % kTcSlots2;
+            ok = mbar_wait(&sh->dzready[j], (uint32_t)kb & 1u, dead);
+            if (ok) ok = mbar_wait(&sh->full2[slot], (it2 / kTcSlots2) & 1u, dead);
+            tc_fence_after();
+            if (kb == 0 && j == 0) PNCE_TR(10);
+            const uint32_t st = smem_u32(stage0 + slot * kTcStage2Bytes);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {                 // 16 keys per MMA
+              const uint64_t a_hi = smem_desc(dzh + (uint32_t)(j * 2 + ks) * 4096u, 2048, 128);
+              const uint64_t b_hi = smem_desc(st + (uint32_t)ks * 2u * lbo2, lbo2, 128);
+              mma_bf16(tmem + 256u, a_hi, b_hi, idesc2, (kb | j | ks) ? 1u : 0u);
+              if (x3) {
+                const uint64_t a_lo = smem_desc(dzl + (uint32_t)(j * 2 + ks) * 4096u, 2048, 128);
+                const uint64_t b_lo = smem_desc(st + 16384u + (uint32_t)ks * 2u * lbo2, lbo2, 128);
+                mma_bf16(tmem + 256u, a_lo, b_hi, idesc2, 1u);
+                mma_bf16(tmem + 256u, a_hi, b_lo, idesc2, 1u);
+              }
+            }
+            mma_commit(&sh->empty2[slot]);
+          }
+          if (multi) mma_commit(&sh->p2done);
         }
-        mma_commit(&sh->empty2[slot]);
       }
       mma_commit(&sh->dqfull);
       PNCE_TR(11);
@@ -407,32 +443,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
     const int et = tid - 64;                                 // 0..127
     if (et != 0) tr = nullptr;
     PNCE_TR(0);
-    // 1/||k_j|| for the N key rows, ||q_i|| for this row: all partial-sum loads are issued up front
+    // 1/||k_j|| of every key (kept in global scratch, reloaded per key block) and ||q_i|| of this row;
+    // all partial-sum loads are issued up front
     float rownrm;
     {
-      float ssk[2][8], ssq[8];
+      float ssq[8];
 #pragma unroll
-      for (int s = 0; s < 8; ++s) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int j = et + 128 * h;
-          ssk[h][s] = (s < nstage && j < P) ? __ldcg(L.kss + ((size_t)b * nstage + s) * N + j) : 0.f;
-        }
-        ssq[s] = (s < nstage && rowok) ? __ldcg(L.qss + ((size_t)b * nstage + s) * N + gi) : 0.f;
-      }
+      for (int s = 0; s < 8; ++s)
+        ssq[s] = (s < nstage && rowok) ? __ldcg(L.qss + ((size_t)b * nstage + s) * Ppad + gi) : 0.f;
       bool anybad = false;
+      for (int j = et; j < Ppad; j += 128) {
+        float ssk[8];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int j = et + 128 * h;
-        if (j < N) {
-          float ss = 0.f;
+        for (int s = 0; s < 8; ++s)
+          ssk[s] = (s < nstage && j < P) ? __ldcg(L.kss + ((size_t)b * nstage + s) * Ppad + j) : 0.f;
+        float ss = 0.f;
 #pragma unroll
-          for (int s = 0; s < 8; ++s) ss += ssk[h][s];
-          const float nrm = sqrtf(ss);
-          const bool bad = !(nrm == nrm);                     // the gather marks non-finite rows with NaN
-          anybad |= bad && j < P;
-          invk_s[j] = (j < P && !bad) ? 1.0f / fmaxf(nrm, kNormEps) : 0.f;
-        }
+        for (int s = 0; s < 8; ++s) ss += ssk[s];
+        const float nrm = sqrtf(ss);
+        const bool bad = !(nrm == nrm);                       // the gather marks non-finite rows with NaN
+        anybad |= bad && j < P;
+        const float w = (j < P && !bad) ? 1.0f / fmaxf(nrm, kNormEps) : 0.f;
+        if (j < 256) invk_s[j] = w;
+        if (multi) L.kinv[(size_t)b * Ppad + j] = w;          // both halves' CTAs write identical values
       }
       if (anybad) sh->badk = 1;
       float ss = 0.f;
@@ -443,7 +476,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
         L.qinv[(size_t)b * P + gi] =
             (rownrm == rownrm) ? (rownrm < kNormEps ? -1.0f / kNormEps : 1.0f / rownrm) : rownrm;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");            // publishes invk_s and badk
+    if (multi) __threadfence_block();
+    asm volatile("bar.sync 1, 128;" ::: "memory");            // publishes invk_s (block 0), kinv and badk
     {
       const bool badq = rowok && !(rownrm == rownrm);
       const float sc = (rowok && !badq) ? 1.0f / fmaxf(rownrm, kNormEps) : 0.f;     // 1 / max(||q_i||, eps)
@@ -456,22 +490,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       const bool need_clamp = inv_tau * 1.02f > kClamp;       // |cos| <= 1: the clamp cannot bind otherwise
       const float coef = rowok ? 1.0f / ((float)P * (float)p.B * (float)p.n_layers) : 0.f;
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-      const int nch = (P + 31) >> 5;                          // chunks that hold real columns
-      const int chd = gi >> 5;                                // chunk holding this warp's diagonal (warp-uniform)
+      const int kbd = gi >> 8;                                // key block holding this row's diagonal
+      const int chd = (gi & 255) >> 5;                        // and the chunk inside it (both warp-uniform)
+      uint32_t nz = 0;
       PNCE_TR(1);
-      mbar_wait(&sh->zfull, 0u, dead);
-      tc_fence_after();
-      PNCE_TR(2);
-      // ---- pass A: row sum of exp2, diagonal ----
+      // ---- pass A: row sum of exp2 over all key blocks, diagonal ----
       float se4[4] = {0.f, 0.f, 0.f, 0.f};
       float ydacc = 0.f;                                      // raw accumulator of the diagonal element
-      if (need_clamp) tc_row_pass_a<true>(trow, nch, invk_s, a, cl, chd, lane, se4, ydacc);
-      else tc_row_pass_a<false>(trow, nch, invk_s, a, cl, chd, lane, se4, ydacc);
-      const float wd = invk_s[gi];
+      int padcols = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int key0 = kb * 256, keys = min(P, key0 + 256) - key0;
+        const int nch = (keys + 31) >> 5;                     // chunks that hold real columns
+        padcols += nch * 32 - keys;
+        if (kb > 0) {                                          // swap in this block's 1/||k_j||
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int j = et; j < 256; j += 128) invk_s[j] = (key0 + j < Ppad) ? __ldcg(L.kinv + (size_t)b * Ppad + key0 + j) : 0.f;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        mbar_wait(&sh->zfull, nz & 1u, dead);
+        ++nz;
+        tc_fence_after();
+        if (kb == 0) PNCE_TR(2);
+        const int cd = (kb == kbd) ? chd : -1;
+        if (need_clamp) tc_row_pass_a<true>(trow, nch, invk_s, a, cl, cd, lane, se4, ydacc);
+        else tc_row_pass_a<false>(trow, nch, invk_s, a, cl, cd, lane, se4, ydacc);
+        if (multi) {
+          tc_fence_before();
+          mbar_arrive(&sh->zfree);                             // this Z block may be overwritten
+        }
+      }
+      const float wd = multi ? __ldcg(L.kinv + (size_t)b * Ppad + (rowok ? gi : 0)) : invk_s[gi];
       const float ydr = ydacc * a * wd;                       // unclamped diagonal logit (log2 units)
       const float yd = need_clamp ? fminf(fmaxf(ydr, -cl), cl) : ydr;
-      // padding columns of the last chunk contributed exp2(0) = 1 each
-      const float se = ((se4[0] + se4[1]) + (se4[2] + se4[3])) - (float)(nch * 32 - P);
+      // padding columns of the last chunk of a block contributed exp2(0) = 1 each
+      const float se = ((se4[0] + se4[1]) + (se4[2] + se4[3])) - (float)padcols;
       const float lse2 = lg2f(se);
       float rowloss = rowok ? (lse2 - yd) * kLn2 : 0.f;        // :94, labels = arange
       if (badrow && rowok) rowloss = __int_as_float(0x7fc00000);
@@ -480,12 +532,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       // pass B (phase 2 finishes right behind pass B: there is no other slack to hide them in);
       // padding rows read slot 0 of the image (always mapped) and never store
       const int gsafe = rowok ? gi : 0;
-      const float* __restrict__ qrow = L.qT + (size_t)b * C * N + gsafe;
+      const float* __restrict__ qrow = L.qT + (size_t)b * C * Ppad + gsafe;
       float qa[32], qb[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
-        qa[k] = (k < C) ? __ldcg(qrow + (size_t)k * N) : 0.f;
-        qb[k] = (32 + k < C) ? __ldcg(qrow + (size_t)(32 + k) * N) : 0.f;
+        qa[k] = (k < C) ? __ldcg(qrow + (size_t)k * Ppad) : 0.f;
+        qb[k] = (32 + k < C) ? __ldcg(qrow + (size_t)(32 + k) * Ppad) : 0.f;
       }
       // ---- pass B: dZ (pre-divided by ||k_j||) -> smem A operand chunk by chunk, s_i ----
       float s2 = 0.f;
@@ -494,9 +546,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       dg.rowok = rowok;
       dg.pass = !need_clamp || fabsf(ydr) <= cl;
       dg.d_w = dg.pass ? (ex2f(yd - lse2) - 1.f) * coef * wd : 0.f;
-      dg.off = (uint32_t)(gi >> 3) * 2048u + rowoff + (uint32_t)(gi & 7) * 2u;
-      if (need_clamp) tc_row_pass_b<true>(trow, nch, invk_s, a, cl, lse2, coef, x3, dzhi, dzlo, rowoff, chd, dg, sh->dzready, s2);
-      else tc_row_pass_b<false>(trow, nch, invk_s, a, cl, lse2, coef, x3, dzhi, dzlo, rowoff, chd, dg, sh->dzready, s2);
+      dg.off = (uint32_t)((gi & 255) >> 3) * 2048u + rowoff + (uint32_t)(gi & 7) * 2u;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int key0 = kb * 256, keys = min(P, key0 + 256) - key0;
+        const int nch = (keys + 31) >> 5;
+        if (multi) {
+          // this block's 1/||k_j||; the Z block is recomputed by the MMA thread (pass 2).  zfull of this
+          // block also means the previous block's dQ MMAs have finished reading the dZ operand.
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int j = et; j < 256; j += 128) invk_s[j] = (key0 + j < Ppad) ? __ldcg(L.kinv + (size_t)b * Ppad + key0 + j) : 0.f;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          mbar_wait(&sh->zfull, nz & 1u, dead);
+          ++nz;
+          tc_fence_after();
+        }
+        const int cd = (kb == kbd) ? chd : -1;
+        uint64_t* dzr = sh->dzready;
+        if (need_clamp) tc_row_pass_b<true>(trow, nch, invk_s, a, cl, lse2, coef, x3, dzhi, dzlo, rowoff, cd, dg, dzr, s2);
+        else tc_row_pass_b<false>(trow, nch, invk_s, a, cl, lse2, coef, x3, dzhi, dzlo, rowoff, cd, dg, dzr, s2);
+      }
       if (rowok && dg.pass) s2 = fmaf(-coef, ydr, s2);         // the diagonal's "- I" term of sum_j dZ_ij y_ij
       const float s_i = s2 * kLn2;                              // sum_j dZ_ij z_ij
       tc_fence_before();
@@ -511,14 +579,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       //   dx = dq*sc - q_raw * (sc^2 s_i)       with dq = acc / tau
       const float c1 = inv_tau * sc;
       const float c2 = noproj ? 0.f : sc * sc * s_i;
-      float* __restrict__ dxrow = L.dxT + (size_t)b * C * N + gsafe;        // dxpitch == N on this path
+      float* __restrict__ dxrow = L.dxT + (size_t)b * C * Ppad + gsafe;     // dxpitch == Ppad on this path
       PNCE_TR(5);
       // head mode: d loss / d (head output) as a row blob [tile = b*halves+mh][c/8][16][8][8]
       const size_t dyoff = (((size_t)b * halves + mh) * Cp8 * 16 + (size_t)(i >> 3)) * 64 + (size_t)(i & 7) * 8;
       __nv_bfloat16* dyh = L.dyhi ? L.dyhi + dyoff : nullptr;
       __nv_bfloat16* dyl = (L.dyhi && L.dylo) ? L.dylo + dyoff : nullptr;
-      if (N == 256) tc_dq_epilogue<256>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb);
-      else tc_dq_epilogue<128>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb);
+      switch (Ppad >> 7) {
+        case 1: tc_dq_epilogue<128>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb); break;
+        case 2: tc_dq_epilogue<256>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb); break;
+        default: tc_dq_epilogue<0>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb, Ppad); break;
+      }
       PNCE_TR(6);
       tc_fence_before();
     }

@@ -58,7 +58,7 @@ static int check_layers(const pnce_layer_t* layers, int n_layers, int B) {
 
 static bool tc_shapes_ok(const pnce_layer_t* layers, int n_layers) {
   for (int l = 0; l < n_layers; ++l)
-    if (layers[l].P > 256 || layers[l].C > 256) return false;
+    if (layers[l].P > 1024 || layers[l].C > 256) return false;
   return true;
 }
 
@@ -113,6 +113,7 @@ static size_t carve_fused(const pnce_layer_t* layers, int n_layers, int B, bool 
       L.qT = cv.take<float>((size_t)B * a.C * L.Ppad);
       L.qss = cv.take<float>((size_t)B * L.nchunk * L.Ppad);
       L.kss = cv.take<float>((size_t)B * L.nchunk * L.Ppad);
+      L.kinv = cv.take<float>((size_t)B * L.Ppad);
     }
     L.partial = cv.take<float>((size_t)B * (L.ntiles > 2 ? L.ntiles : 2));
   }
@@ -135,11 +136,25 @@ static size_t gather_smem_bytes(const Params& p, bool with_prep) {
   return need;
 }
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is sticky per kernel and
+// device: what has been set is remembered so the driver call is made once, not per launch.
+struct SmemOptIn { const void* fn; int dev; size_t bytes; };
+static thread_local SmemOptIn g_optin[64];
+static thread_local int g_noptin = 0;
+
 template <typename K> static int set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) {
-    if (bytes > 227 * 1024) return PNCE_ERR_UNSUPPORTED;
-    PNCE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  }
+  if (bytes <= 48 * 1024) return PNCE_OK;
+  if (bytes > 227 * 1024) return PNCE_ERR_UNSUPPORTED;
+  int dev = 0;
+  PNCE_CUDA(cudaGetDevice(&dev));
+  const void* fn = reinterpret_cast<const void*>(kernel);
+  SmemOptIn* e = nullptr;
+  for (int i = 0; i < g_noptin; ++i)
+    if (g_optin[i].fn == fn && g_optin[i].dev == dev) e = &g_optin[i];
+  if (e != nullptr && e->bytes >= bytes) return PNCE_OK;
+  PNCE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (e == nullptr && g_noptin < 64) e = &g_optin[g_noptin++];
+  if (e != nullptr) { e->fn = fn; e->dev = dev; e->bytes = bytes; }
   return PNCE_OK;
 }
 
@@ -203,7 +218,7 @@ static int launch_gather_tc(const Params& p, cudaStream_t st) {
   long long acc = 0;
   for (int l = 0; l < p.n_layers; ++l) {
     m.start[l] = acc;
-    acc += 2ll * p.bn * p.L[l].nchunk;
+    acc += 2ll * p.bn * ((p.L[l].Ppad + 255) / 256) * p.L[l].nchunk;
   }
   m.start[p.n_layers] = acc;
   if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
@@ -421,7 +436,7 @@ int pnce_fwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, flo
   rc = check_alignment(layers, n_layers, dtype, false);
   if (rc != PNCE_OK) return rc;
   if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
-  // the tcgen05 kernel covers P <= 256, C <= 256 (every 256^2 CUT layer); other shapes take the
+  // the tcgen05 kernel covers P <= 1024, C <= 256 (every CUT layer up to the 512^2 stress config); other shapes take the
   // fp32 CUDA-core kernel -- both are device paths of this library, neither is a fallback off the GPU
   const bool tc = math_mode != PNCE_MATH_SIMT_F32 && tc_shapes_ok(layers, n_layers);
   const bool x3 = math_mode == PNCE_MATH_TC_BF16X3;
@@ -625,7 +640,9 @@ struct HeadPlan {
 
 static bool head_shapes_ok(const pnce_layer_t* layers, int n_layers, int nc) {
   if (nc != 128 && nc != 256) return false;
-  return tc_shapes_ok(layers, n_layers);
+  for (int l = 0; l < n_layers; ++l)
+    if (layers[l].P > 256 || layers[l].C > 256) return false;
+  return true;
 }
 
 static size_t carve_head(const pnce_layer_t* layers, int n_layers, int B, int nc, bool x3, void* ws, HeadPlan* out) {

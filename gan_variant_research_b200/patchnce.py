@@ -65,13 +65,15 @@ def draw_patch_ids(feat: torch.Tensor, num_patches: int) -> torch.Tensor:
 # here the flag is copied to pinned memory asynchronously and reported on a later call)
 # ------------------------------------------------------------------------------------------------
 class _WarnQueue:
-    """Ring of pinned int32[2] slots allocated once; a slot is reused after its event completed."""
+    """Ring of pinned int32[2] slots and CUDA events allocated once; a slot is reused after its
+    event completed."""
     SLOTS = 64
 
     def __init__(self):
         self.pending = []
         self.host = None
         self.free = []
+        self.events = []
 
     def push(self, dev_flag: torch.Tensor):
         if torch.cuda.is_current_stream_capturing():
@@ -79,25 +81,29 @@ class _WarnQueue:
         if self.host is None:
             self.host = torch.zeros(self.SLOTS, 2, dtype=torch.int32).pin_memory()
             self.free = list(range(self.SLOTS))
+            self.events = [torch.cuda.Event() for _ in range(self.SLOTS)]
         if not self.free:
             self.poll()
-            if not self.free:                    # 64 launches in flight un-polled: drop the oldest check
+            if not self.free:                    # 64 launches in flight un-polled: wait for the oldest
                 self.pending[0][0].synchronize()
                 self.poll()
         slot = self.free.pop()
-        self.host[slot].copy_(dev_flag, non_blocking=True)
-        ev = torch.cuda.Event()
+        self.host[slot, :dev_flag.numel()].copy_(dev_flag, non_blocking=True)
+        ev = self.events[slot]
         ev.record(torch.cuda.current_stream(dev_flag.device))
-        self.pending.append((ev, slot))
+        self.pending.append((ev, slot, dev_flag.numel()))
 
     def poll(self, block: bool = False) -> int:
         """Print the reference's warning for finished launches; returns images guarded so far."""
+        if not self.pending:
+            return 0
         total, keep = 0, []
-        for ev, slot in self.pending:
+        for ev, slot, n_flags in self.pending:
             if block:
                 ev.synchronize()
             if ev.query():
-                n, proto = int(self.host[slot, 0]), int(self.host[slot, 1])
+                n = int(self.host[slot, 0])
+                proto = int(self.host[slot, 1]) if n_flags > 1 else 0
                 self.free.append(slot)
                 if proto:
                     raise _lib.PnceError("libpnce kernel protocol timeout (tcgen05 pipeline stalled)")
@@ -105,7 +111,7 @@ class _WarnQueue:
                     print(f"Warning: NaN in PatchNCE loss. {n} (layer, image) loss(es) replaced by 0.")
                 total += n
             else:
-                keep.append((ev, slot))
+                keep.append((ev, slot, n_flags))
         self.pending = keep
         return total
 
@@ -128,6 +134,9 @@ class _Plan:
         self.ids_list = ids_list
         self.temperature = float(temperature)
         self.math = math
+
+
+_WS_BYTES = {}      # (batch, layer shapes) -> pnce_workspace_bytes, queried once per problem shape
 
 
 def _layer_array(src, tgt, dtgt, ids):
@@ -154,17 +163,21 @@ class _FusedPatchNCE(torch.autograd.Function):
         n = len(tgt)
         dtype = _DTYPES[tgt[0].dtype]
         layers = _layer_array(src, tgt, None, ids)
-        nbytes = ctypes.c_size_t(0)
-        _lib.check(lib.pnce_workspace_bytes(layers, n, batch, ctypes.byref(nbytes)), "pnce_workspace_bytes")
+        key = (batch, tuple((t.shape[1], t.shape[2], t.shape[3], i.numel()) for t, i in zip(tgt, ids)))
+        ws_bytes = _WS_BYTES.get(key)
+        if ws_bytes is None:
+            nbytes = ctypes.c_size_t(0)
+            _lib.check(lib.pnce_workspace_bytes(layers, n, batch, ctypes.byref(nbytes)), "pnce_workspace_bytes")
+            ws_bytes = _WS_BYTES[key] = nbytes.value
         with torch.cuda.device(dev):
-            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             out = torch.empty(1 + n, dtype=torch.float32, device=dev)
-            flag = torch.zeros(2, dtype=torch.int32, device=dev)
+            flag = torch.empty(2, dtype=torch.int32, device=dev)     # both words are written by the kernels
             _lib.check(lib.pnce_fwd(layers, n, batch, dtype, plan.temperature, _MATH[plan.math],
-                                    ws.data_ptr(), nbytes.value, out.data_ptr(), flag.data_ptr(),
+                                    ws.data_ptr(), ws_bytes, out.data_ptr(), flag.data_ptr(),
                                     _stream_ptr(dev)), "pnce_fwd")
         _warnings.push(flag)
-        ctx.plan, ctx.ws, ctx.ws_bytes = plan, ws, nbytes.value
+        ctx.plan, ctx.ws, ctx.ws_bytes = plan, ws, ws_bytes
         ctx.tgt_meta = [(t.shape, t.dtype) for t in tgt]
         ctx.tgt_keep = tgt               # shapes only matter, but keeps data_ptrs stable for the struct
         ctx.dev, ctx.batch, ctx.dtype = dev, batch, dtype

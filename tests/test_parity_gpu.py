@@ -400,3 +400,25 @@ def test_netf_head_virtual_shard_law(pn):
     assert ((la + lb) / 2).item() == pytest.approx(full.item(), rel=1e-5)
     for a, b, f in zip(ga, gb, gfull):
         torch.testing.assert_close((a + b) / 2, f, rtol=2e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("p,c", [(300, 24), (600, 96), (1000, 256), (1024, 64)])
+@pytest.mark.parametrize("math", ["tc_bf16x3", "simt_f32"])
+def test_more_than_256_patches(pn, orc, p, c, math):
+    """num_patches > 256 (BASELINE config 4 asks for 1024): the tcgen05 kernel walks the keys in
+    blocks of 256 (two passes, logits recomputed for dZ); checked against the float64 oracle, with
+    duplicate ids (the map has 1600 positions) and a second, small layer in the same launch."""
+    g = torch.Generator().manual_seed(1000 * p + c)
+    shapes = [(c, 40, 40), (16, 12, 12)]
+    src = [torch.randn(2, *s, generator=g) for s in shapes]
+    tgt = [torch.randn(2, *s, generator=g) for s in shapes]
+    ids = [torch.randint(0, s[1] * s[2], (min(p, s[1] * s[2]),), generator=g) for s in shapes]
+    t = [x.cuda().requires_grad_() for x in tgt]
+    loss = pn.fused_patchnce([x.cuda() for x in src], t, [i.cuda() for i in ids], 0.07, math=math)
+    (loss * 1.5).backward()
+    assert pn.poll_nonfinite_warnings(block=True) == 0
+    want, _, gw = orc.patchnce_loss_and_grads_np([x.numpy() for x in src], [x.numpy() for x in tgt],
+                                                 [i.numpy() for i in ids], 0.07, upstream=1.5)
+    assert loss.item() == pytest.approx(want, rel=2e-5)
+    for l in range(2):
+        assert_grad_close(t[l].grad.cpu().numpy(), gw[l], 2e-4, f"P={p} layer {l}", ids=ids[l].numpy())
