@@ -422,3 +422,45 @@ def test_more_than_256_patches(pn, orc, p, c, math):
     assert loss.item() == pytest.approx(want, rel=2e-5)
     for l in range(2):
         assert_grad_close(t[l].grad.cpu().numpy(), gw[l], 2e-4, f"P={p} layer {l}", ids=ids[l].numpy())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_half_precision_maps_head_and_many_patches(pn, orc, dtype):
+    """The AMP regime of the real training loop (fp16 features under autocast, train_cutpp.py:268) through
+    the two newer kernels: the fused netF head and the key-blocked path for num_patches > 256.  The oracle
+    sees the same rounded inputs; the dense gradients come back in the maps' dtype."""
+    g = torch.Generator().manual_seed(77)
+    # (a) head, P <= 256
+    shapes = [(48, 16, 16), (128, 12, 12)]
+    src = [torch.randn(2, *s, generator=g).to(dtype) for s in shapes]
+    tgt = [torch.randn(2, *s, generator=g).to(dtype) for s in shapes]
+    ids = [torch.randint(0, s[1] * s[2], (96,), generator=g) for s in shapes]
+    torch.manual_seed(3)
+    netF = pn.PatchSampleF(use_mlp=True, nc=128, init_gain=0.3)
+    t = [x.cuda().requires_grad_() for x in tgt]
+    loss, _ = pn.patchnce_with_head(netF, [x.cuda() for x in src], t, 0.07, 96, [i.cuda() for i in ids], fused=True)
+    loss.backward()
+    heads = [tuple(x.detach().cpu().clone().requires_grad_() for x in
+                   (getattr(netF, f"mlp_{l}")[0].weight, getattr(netF, f"mlp_{l}")[0].bias,
+                    getattr(netF, f"mlp_{l}")[2].weight, getattr(netF, f"mlp_{l}")[2].bias)) for l in range(2)]
+    tc = [x.float().clone().requires_grad_() for x in tgt]
+    want = orc.patchnce_head_loss_torch([x.float() for x in src], tc, ids, heads)
+    want.backward()
+    assert loss.item() == pytest.approx(want.item(), rel=1e-3)
+    for l in range(2):
+        assert t[l].grad.dtype == dtype
+        assert_grad_close(t[l].grad.float().cpu().numpy(), tc[l].grad.numpy(), 1e-2, f"head d tgt {l}", ids=ids[l])
+        assert_grad_close(getattr(netF, f"mlp_{l}")[2].weight.grad.cpu().numpy(), heads[l][2].grad.numpy(), 1e-3, "dW2")
+    # (b) 600 patches, no head
+    s = (40, 32, 32)
+    src = [torch.randn(2, *s, generator=g).to(dtype)]
+    tgt = [torch.randn(2, *s, generator=g).to(dtype)]
+    ids = [torch.randint(0, 1024, (600,), generator=g)]
+    t = [x.cuda().requires_grad_() for x in tgt]
+    loss = pn.fused_patchnce([x.cuda() for x in src], t, [i.cuda() for i in ids], 0.07)
+    loss.backward()
+    want, _, gw = orc.patchnce_loss_and_grads_np([x.float().numpy() for x in src], [x.float().numpy() for x in tgt],
+                                                 [i.numpy() for i in ids], 0.07)
+    assert loss.item() == pytest.approx(want, rel=2e-5)
+    assert_grad_close(t[0].grad.float().cpu().numpy(), gw[0], 1e-2, "P=600 half maps", ids=ids[0].numpy())
+    assert pn.poll_nonfinite_warnings(block=True) == 0
