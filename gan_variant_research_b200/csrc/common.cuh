@@ -49,7 +49,6 @@ struct LayerDev {
   __nv_bfloat16* dyhi;       // head mode: d loss / d head output as a row blob (then dxT is not written)
   __nv_bfloat16* dylo;
   int head_src_rows;         // head mode gather: the src side is written as a row blob too (into khi/klo)
-  float* qT;                 // [B][C][Ppad] raw fp32 target patches (transposed)
   float* qss;                // [B][nchunk][Ppad] partial sums of squares (NaN: non-finite element)
   float* kss;
   float* kinv;               // [B][Ppad] 1/max(||k_j||, eps) (0 for padding / non-finite rows), P > 256 only

@@ -10,8 +10,8 @@
 //     K blob: [image][c/8][Ppad/8 row groups][8 rows][8 ch]                bf16
 //   Values are RAW (not normalised): the row norms are only known once all channels are seen, so
 //   each chunk also emits its partial sum of squares and the loss kernel folds 1/||q||, 1/||k||
-//   into its epilogues.  The raw fp32 target patches are kept transposed (C, Ppad) for the
-//   normalise backward.  Replaces patchnce_cut.py:56-78 on the tensor-core path.
+//   into its epilogues (the normalise backward re-reads the raw q values as hi + lo from the Q blob).
+//   Replaces patchnce_cut.py:56-78 on the tensor-core path.
 #pragma once
 #include "common.cuh"
 #include "gather.cuh"
@@ -82,13 +82,6 @@ __device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long loca
       const size_t off2 = (((size_t)b * (Ppad >> 3) + (p >> 3)) * Cp8 + c8) * 64 + (size_t)(p & 7) * 8;
       *reinterpret_cast<uint4*>(L.k2hi + off2) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
       if (L.k2lo != nullptr) *reinterpret_cast<uint4*>(L.k2lo + off2) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-    }
-  }
-  if (side && L.qT != nullptr) {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const int c = s * 32 + k;
-      if (c < C) L.qT[((size_t)b * C + c) * Ppad + p] = v[k];
     }
   }
 }

@@ -34,7 +34,7 @@ struct GemmProb {
   __nv_bfloat16 *o_hi, *o_lo;              // GM_H / GM_DH / GM_YQ: row blob with N columns
   __nv_bfloat16 *k_hi, *k_lo, *k2_hi, *k2_lo;   // GM_YK: the two K layouts of k_loss_tc
   float* ss;                               // GM_YQ / GM_YK: [B][N/32][Ppad] partial sums of squares
-  float* outT;                             // GM_YQ: raw fp32 [B][N][Ppad];  GM_DX: dxT [B][C][Ppad]
+  float* outT;                             // GM_DX: dxT [B][C][Ppad]
   const __nv_bfloat16* mask_hi;            // GM_DH: H blob (hi part), same indexing as o_hi
 };
 
@@ -191,10 +191,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_gemm_tc(const __grid_constant
           bad |= !isfinite(v[k]);
         }
         pr.ss[((size_t)b * nch + ch) * Ppad + p] = bad ? __int_as_float(0x7fc00000) : ssum;
-        if (mode == GM_YQ && rowok) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) pr.outT[((size_t)b * N + ch * 32 + k) * Ppad + p] = v[k];
-        }
       }
 #pragma unroll
       for (int g8 = 0; g8 < 4; ++g8) {

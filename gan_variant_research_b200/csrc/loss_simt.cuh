@@ -17,42 +17,60 @@ __host__ __device__ inline size_t loss_simt_smem_bytes(int P) {
   return (size_t)(32 * Pp + kStageFloats + 32 + 8) * sizeof(float);
 }
 
-// Deterministic epilogue run by the last CTA of the launch.
+// Deterministic epilogue run by the last CTA of the launch: per-image losses, the reference's
+// non-finite guards, batch and layer means.  Parallel over the batch (a block-wide reduction in a
+// fixed order per layer) -- a single thread walking L*B values costs one L2 round trip per value,
+// ~40 us at B=64, on the critical path of every step.
 __device__ void finalize_losses(const Params& p) {
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
   const int B = p.B, nl = p.n_layers;
+  __shared__ float w_sum[8];
+  __shared__ int w_bad[8];
+  __shared__ int layer_bad[PNCE_MAX_LAYERS];
+  __shared__ int any_guard;
+  float total = 0.f;                                            // thread 0 only
+  int bad_total = 0;
   for (int l = 0; l < nl; ++l) {
     const LayerDev& L = p.L[l];
+    float acc = 0.f;
+    int nbad = 0;
     for (int b = tid; b < B; b += nthr) {
       float s = 0.f;
       for (int t = 0; t < L.nparts; ++t) s += __ldcg(L.partial + (size_t)b * L.nparts + t);
-      float lb = s / (float)L.P;                                // CE reduction='mean' over rows  :94
-      int ok = isfinite(lb) ? 1 : 0;                            // :97
+      const float lb = s / (float)L.P;                          // CE reduction='mean' over rows  :94
+      const int ok = isfinite(lb) ? 1 : 0;                      // :97
       p.lossimg[l * B + b] = ok ? lb : 0.f;                     // :99
       p.valid[l * B + b] = ok;
+      acc += ok ? lb : 0.f;                                     // :101
+      nbad += ok ? 0 : 1;
     }
-  }
-  __syncthreads();
-  __shared__ int layer_bad[PNCE_MAX_LAYERS];
-  if (tid == 0) {
-    float total = 0.f;
-    int bad = 0;
-    for (int l = 0; l < nl; ++l) {
+    acc = warp_sum(acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nbad += __shfl_xor_sync(0xffffffffu, nbad, o);
+    if (lane == 0) { w_sum[warp] = acc; w_bad[warp] = nbad; }
+    __syncthreads();
+    if (tid == 0) {
       float sl = 0.f;
-      for (int b = 0; b < B; ++b) {
-        sl += p.lossimg[l * B + b];                             // :101
-        bad += p.valid[l * B + b] ? 0 : 1;
-      }
+      int nb = 0;
+      for (int w = 0; w < nwarp; ++w) { sl += w_sum[w]; nb += w_bad[w]; }
       sl = sl / (float)B;                                       // :103
       layer_bad[l] = isfinite(sl) ? 0 : 1;                      // :106-108
       if (layer_bad[l]) sl = 0.f;
       p.loss_out[1 + l] = sl;
       total += sl;                                              // :38
+      bad_total += nb + layer_bad[l];
     }
+    __syncthreads();
+  }
+  if (tid == 0) {
     p.loss_out[0] = total / (float)nl;                          // :40
-    if (p.nonfinite) *p.nonfinite = bad;
+    int nb = 0;
+    for (int l = 0; l < nl; ++l) nb += layer_bad[l];
+    if (p.nonfinite) *p.nonfinite = bad_total - nb;             // images guarded (layer guards are not counted)
+    any_guard = bad_total > 0;
   }
   __syncthreads();
+  if (!any_guard) return;                                       // the common case: nothing to overwrite
   // Guarded images receive an exactly-zero upstream gradient; autograd still pushes it through the
   // normalise backward, so rows holding NaN/Inf come out NaN and everything else 0 (see oracle).
   for (int l = 0; l < nl; ++l) {

@@ -21,7 +21,8 @@
 //             is M128 x N=C x K16 (N=32 MMAs re-read the whole A tile and starve on shared-memory
 //             bandwidth).  Chunk j's MMAs start as soon as the four epilogue warps have written
 //             dZ[:, 32j..32j+31]: phase 2 overlaps pass B.  Accumulator: TMEM cols [256, 256+C)
-//   epilogue  dq/tau, normalise backward, dxT[b][c][slot] (unit upstream gradient), coalesced.
+//   epilogue  dq/tau, normalise backward (raw q re-read from the Q operand blob, hi + lo),
+//             dxT[b][c][slot] (unit upstream gradient), coalesced.
 // The logits, softmax and dZ never leave the SM.  Replaces patchnce_cut.py:83-110 and the autograd
 // backward of :77-94.  Shapes: P <= 1024, C <= 256.
 // P > 256: the keys are processed in blocks of 256 (flash-style): pass 1 accumulates the row sums block
@@ -195,25 +196,47 @@ __device__ __forceinline__ void tc_row_pass_b(uint32_t trow, int nch, const floa
   }
 }
 
-// dQ epilogue for one 32-channel chunk; NP = pitch of qT and dxT rows (compile-time: immediates).
+// Raw q values of one 32-channel chunk of this thread's row, re-read from the Q operand blob (hi + lo
+// = the fp32 value to 2^-17; the blob was streamed through this SM a few microseconds ago, so these are
+// L2 hits): 4 slabs x (16 B hi + 16 B lo).
+struct TcQChunk {
+  uint4 h[4], l[4];
+};
+__device__ __forceinline__ void tc_q_load(TcQChunk& qc, const __nv_bfloat16* __restrict__ qh,
+                                          const __nv_bfloat16* __restrict__ ql, int s, int nstage) {
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8) {
+    const bool in = s < nstage;
+    qc.h[g8] = in ? __ldcg(reinterpret_cast<const uint4*>(qh + (size_t)(s * 4 + g8) * 1024)) : make_uint4(0u, 0u, 0u, 0u);
+    qc.l[g8] = (in && ql != nullptr) ? __ldcg(reinterpret_cast<const uint4*>(ql + (size_t)(s * 4 + g8) * 1024))
+                                     : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+__device__ __forceinline__ void tc_q_unpack(const TcQChunk& qc, float (&q)[32]) {
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8) {
+    const uint32_t hw[4] = {qc.h[g8].x, qc.h[g8].y, qc.h[g8].z, qc.h[g8].w};
+    const uint32_t lw[4] = {qc.l[g8].x, qc.l[g8].y, qc.l[g8].z, qc.l[g8].w};
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+      q[g8 * 8 + 2 * k2] = __uint_as_float(hw[k2] << 16) + __uint_as_float(lw[k2] << 16);
+      q[g8 * 8 + 2 * k2 + 1] = __uint_as_float(hw[k2] & 0xffff0000u) + __uint_as_float(lw[k2] & 0xffff0000u);
+    }
+  }
+}
+
+// dQ epilogue for one 32-channel chunk; NPC = pitch of dxT rows (compile-time: immediates; 0 = run time).
 // Head mode (dyh != NULL): the gradient w.r.t. the head output leaves as a bf16 hi(+lo) row blob
 // (the A operand of the head's backward GEMMs) instead of fp32 rows; padding rows are written as 0.
 template <int NPC>
-__device__ __forceinline__ void tc_dq_chunk(const uint32_t (&r)[32], float (&qv)[32], const float* __restrict__ qp,
-                                            float* __restrict__ dp, int nvalid, int nnext, float c1, float c2,
-                                            bool rowok, __nv_bfloat16* dyh, __nv_bfloat16* dyl, int np_rt) {
-  const size_t NP = NPC ? (size_t)NPC : (size_t)np_rt;      // NPC = 0: run-time pitch (P > 256)
-  float out[32];
+__device__ __forceinline__ void tc_dq_chunk(const uint32_t (&r)[32], const TcQChunk& qc, float* __restrict__ dp,
+                                            int nvalid, float c1, float c2, bool rowok, __nv_bfloat16* dyh,
+                                            __nv_bfloat16* dyl, int np_rt) {
+  const size_t NP = NPC ? (size_t)NPC : (size_t)np_rt;
+  float qv[32], out[32];
+  tc_q_unpack(qc, qv);
 #pragma unroll
   for (int k = 0; k < 32; ++k) out[k] = fmaf(-qv[k], c2, __uint_as_float(r[k]) * c1);
-  // raw q of the chunk after next (qp already points there); whole chunks take the unpredicated path
-  if (nnext >= 32) {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) qv[k] = __ldcg(qp + k * NP);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) qv[k] = (k < nnext) ? __ldcg(qp + k * NP) : 0.f;
-  }
   if (dyh != nullptr) {
 #pragma unroll
     for (int g8 = 0; g8 < 4; ++g8) {
@@ -242,10 +265,11 @@ __device__ __forceinline__ void tc_dq_chunk(const uint32_t (&r)[32], float (&qv)
 }
 
 template <int NPC>
-__device__ __forceinline__ void tc_dq_epilogue(uint32_t tacc, int nstage, int C, const float* __restrict__ qrow,
-                                               float* __restrict__ dxrow, float c1, float c2, bool rowok,
-                                               __nv_bfloat16* dyh, __nv_bfloat16* dyl, uint64_t* dqfull,
-                                               volatile int* dead, float (&qa)[32], float (&qb)[32], int np_rt = 0) {
+__device__ __forceinline__ void tc_dq_epilogue(uint32_t tacc, int nstage, int C, const __nv_bfloat16* __restrict__ qh,
+                                               const __nv_bfloat16* __restrict__ ql, float* __restrict__ dxrow,
+                                               float c1, float c2, bool rowok, __nv_bfloat16* dyh,
+                                               __nv_bfloat16* dyl, uint64_t* dqfull, volatile int* dead,
+                                               TcQChunk& qa, TcQChunk& qb, int np_rt = 0) {
   using namespace umma;
   const size_t NP = NPC ? (size_t)NPC : (size_t)np_rt;
   mbar_wait(dqfull, 0u, dead);
@@ -254,15 +278,16 @@ __device__ __forceinline__ void tc_dq_epilogue(uint32_t tacc, int nstage, int C,
     uint32_t r[32];
     tmem_ld32(tacc + s * 32, r);
     tmem_ld_wait();
-    tc_dq_chunk<NPC>(r, qa, qrow + (size_t)(s + 2) * 32 * NP, dxrow + (size_t)s * 32 * NP, C - s * 32,
-                     C - (s + 2) * 32, c1, c2, rowok, dyh ? dyh + (size_t)s * 4096 : nullptr,
-                     dyl ? dyl + (size_t)s * 4096 : nullptr, np_rt);
+    tc_dq_chunk<NPC>(r, qa, dxrow + (size_t)s * 32 * NP, C - s * 32, c1, c2, rowok,
+                     dyh ? dyh + (size_t)s * 4096 : nullptr, dyl ? dyl + (size_t)s * 4096 : nullptr, np_rt);
+    tc_q_load(qa, qh, ql, s + 2, nstage);                     // two chunks ahead (static double buffer)
     if (s + 1 < nstage) {
       tmem_ld32(tacc + (s + 1) * 32, r);
       tmem_ld_wait();
-      tc_dq_chunk<NPC>(r, qb, qrow + (size_t)(s + 3) * 32 * NP, dxrow + (size_t)(s + 1) * 32 * NP, C - (s + 1) * 32,
-                       C - (s + 3) * 32, c1, c2, rowok, dyh ? dyh + (size_t)(s + 1) * 4096 : nullptr,
-                       dyl ? dyl + (size_t)(s + 1) * 4096 : nullptr, np_rt);
+      tc_dq_chunk<NPC>(r, qb, dxrow + (size_t)(s + 1) * 32 * NP, C - (s + 1) * 32, c1, c2, rowok,
+                       dyh ? dyh + (size_t)(s + 1) * 4096 : nullptr, dyl ? dyl + (size_t)(s + 1) * 4096 : nullptr,
+                       np_rt);
+      tc_q_load(qb, qh, ql, s + 3, nstage);
     }
   }
 }
@@ -296,6 +321,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
   long long* tr = nullptr;                                   // debug stamps (pnce_debug_set key 3)
   if (p.trace != nullptr && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) tr = p.trace + (blockIdx.x ? 16 : 0);
 #define PNCE_TR(slot) do { if (tr) tr[slot] = clock64(); } while (0)
+  // debug timeline: (sm id, start ns, end ns) of every CTA at trace[64 + 3 * blockIdx.x]
+  if (p.trace != nullptr && tid == 0) {
+    unsigned sm; unsigned long long t;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[64 + 3 * (size_t)blockIdx.x] = sm;
+    p.trace[64 + 3 * (size_t)blockIdx.x + 1] = (long long)t;
+  }
 
   if (tid == 0) {
     for (int k = 0; k < kTcSlots1; ++k) { mbar_init(&sh->full1[k], 1); mbar_init(&sh->empty1[k], 1); }
@@ -528,17 +561,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       float rowloss = rowok ? (lse2 - yd) * kLn2 : 0.f;        // :94, labels = arange
       if (badrow && rowok) rowloss = __int_as_float(0x7fc00000);
       PNCE_TR(3);
-      // raw q of the first two channel chunks for the dQ epilogue: issued now, so the loads fly under
-      // pass B (phase 2 finishes right behind pass B: there is no other slack to hide them in);
-      // padding rows read slot 0 of the image (always mapped) and never store
-      const int gsafe = rowok ? gi : 0;
-      const float* __restrict__ qrow = L.qT + (size_t)b * C * Ppad + gsafe;
-      float qa[32], qb[32];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        qa[k] = (k < C) ? __ldcg(qrow + (size_t)k * Ppad) : 0.f;
-        qb[k] = (32 + k < C) ? __ldcg(qrow + (size_t)(32 + k) * Ppad) : 0.f;
-      }
+      // raw q of the first two channel chunks for the dQ epilogue, from this row's slice of the Q operand
+      // blob: issued now, so the loads fly under pass B (phase 2 finishes right behind pass B: there is
+      // no other slack to hide them in)
+      const size_t qoff = (((size_t)b * halves + mh) * Cp8 * 16 + (size_t)(i >> 3)) * 64 + (size_t)(i & 7) * 8;
+      const __nv_bfloat16* __restrict__ qh = L.qhi + qoff;
+      const __nv_bfloat16* __restrict__ ql = (x3 && L.qlo != nullptr) ? L.qlo + qoff : nullptr;
+      TcQChunk qa, qb;
+      tc_q_load(qa, qh, ql, 0, nstage);
+      tc_q_load(qb, qh, ql, 1, nstage);
       // ---- pass B: dZ (pre-divided by ||k_j||) -> smem A operand chunk by chunk, s_i ----
       float s2 = 0.f;
       const uint32_t rowoff = (uint32_t)(i >> 3) * 128u + (uint32_t)(i & 7) * 16u;
@@ -579,16 +610,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       //   dx = dq*sc - q_raw * (sc^2 s_i)       with dq = acc / tau
       const float c1 = inv_tau * sc;
       const float c2 = noproj ? 0.f : sc * sc * s_i;
-      float* __restrict__ dxrow = L.dxT + (size_t)b * C * Ppad + gsafe;     // dxpitch == Ppad on this path
+      float* __restrict__ dxrow = L.dxT + (size_t)b * C * Ppad + (rowok ? gi : 0);   // dxpitch == Ppad on this path
       PNCE_TR(5);
       // head mode: d loss / d (head output) as a row blob [tile = b*halves+mh][c/8][16][8][8]
-      const size_t dyoff = (((size_t)b * halves + mh) * Cp8 * 16 + (size_t)(i >> 3)) * 64 + (size_t)(i & 7) * 8;
-      __nv_bfloat16* dyh = L.dyhi ? L.dyhi + dyoff : nullptr;
-      __nv_bfloat16* dyl = (L.dyhi && L.dylo) ? L.dylo + dyoff : nullptr;
+      __nv_bfloat16* dyh = L.dyhi ? L.dyhi + qoff : nullptr;
+      __nv_bfloat16* dyl = (L.dyhi && L.dylo) ? L.dylo + qoff : nullptr;
       switch (Ppad >> 7) {
-        case 1: tc_dq_epilogue<128>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb); break;
-        case 2: tc_dq_epilogue<256>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb); break;
-        default: tc_dq_epilogue<0>(trow + 256u, nstage, C, qrow, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb, Ppad); break;
+        case 1: tc_dq_epilogue<128>(trow + 256u, nstage, C, qh, ql, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb); break;
+        case 2: tc_dq_epilogue<256>(trow + 256u, nstage, C, qh, ql, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb); break;
+        default: tc_dq_epilogue<0>(trow + 256u, nstage, C, qh, ql, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb, Ppad); break;
       }
       PNCE_TR(6);
       tc_fence_before();
@@ -600,6 +630,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
     tmem_dealloc<512>(tmem);
   }
   if (tid == 0 && sh->dead && p.nonfinite != nullptr) atomicExch(p.nonfinite + 1, 1);   // protocol timeout flag
+  if (p.trace != nullptr && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[64 + 3 * (size_t)blockIdx.x + 2] = (long long)t;
+  }
   last_cta_finalize(p, &sh->flag);
 }
 

@@ -110,7 +110,6 @@ static size_t carve_fused(const pnce_layer_t* layers, int n_layers, int B, bool 
       }
       L.k2hi = cv.take<__nv_bfloat16>(blob);
       if (x3) L.k2lo = cv.take<__nv_bfloat16>(blob);
-      L.qT = cv.take<float>((size_t)B * a.C * L.Ppad);
       L.qss = cv.take<float>((size_t)B * L.nchunk * L.Ppad);
       L.kss = cv.take<float>((size_t)B * L.nchunk * L.Ppad);
       L.kinv = cv.take<float>((size_t)B * L.Ppad);
@@ -708,7 +707,6 @@ static size_t carve_head(const pnce_layer_t* layers, int n_layers, int B, int nc
     } else {
       V.qlo = V.klo = V.k2lo = V.dylo = nullptr;
     }
-    V.qT = cv.take<float>((size_t)B * nc * Ppad);
     V.qss = cv.take<float>((size_t)B * (nc / 32) * Ppad);
     V.kss = cv.take<float>((size_t)B * (nc / 32) * Ppad);
     V.qinv = cv.take<float>((size_t)B * a.P);
@@ -847,7 +845,7 @@ int pnce_head_fwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_la
       pr.bias = heads[l].b2;
       pr.K = nc; pr.N = nc; pr.tiles = batch * (G.Ppad / 128); pr.mode = side ? GM_YQ : GM_YK;
       pr.P = G.P; pr.Ppad = G.Ppad; pr.halves = G.Ppad / 128; pr.C = nc;
-      if (side) { pr.o_hi = V.qhi; pr.o_lo = V.qlo; pr.ss = V.qss; pr.outT = V.qT; }
+      if (side) { pr.o_hi = V.qhi; pr.o_lo = V.qlo; pr.ss = V.qss; }
       else { pr.k_hi = V.khi; pr.k_lo = V.klo; pr.k2_hi = V.k2hi; pr.k2_lo = V.k2lo; pr.ss = V.kss; }
     }
   }
