@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_gemm_tc(const __grid_constant
     tc_fence_after();
     tmem_dealloc<256>(tmem);
   }
-  if (tid == 0 && sh->dead && g.err != nullptr) atomicExch(g.err, 1);
+  if (tid == 0 && sh->dead && g.err != nullptr) *reinterpret_cast<volatile int*>(g.err) = 1;   // plain store: the flag may live in mapped host memory
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
-  if (tid == 0 && sh->dead && g.err != nullptr) atomicExch(g.err, 1);
+  if (tid == 0 && sh->dead && g.err != nullptr) *reinterpret_cast<volatile int*>(g.err) = 1;   // plain store: the flag may live in mapped host memory
 }
 
 // dW = upstream * sum_slabs partial, db likewise; deterministic order; all layers in one launch.

@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
-  if (tid == 0 && sh->dead && p.nonfinite != nullptr) atomicExch(p.nonfinite + 1, 1);   // protocol timeout flag
+  if (tid == 0 && sh->dead && p.nonfinite != nullptr) *reinterpret_cast<volatile int*>(p.nonfinite + 1) = 1;   // protocol timeout flag (may be mapped host memory)
   if (p.trace != nullptr && tid == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -65,8 +65,11 @@ def draw_patch_ids(feat: torch.Tensor, num_patches: int) -> torch.Tensor:
 # here the flag is copied to pinned memory asynchronously and reported on a later call)
 # ------------------------------------------------------------------------------------------------
 class _WarnQueue:
-    """Ring of pinned int32[2] slots and CUDA events allocated once; a slot is reused after its
-    event completed."""
+    """The kernels write their two status words (guarded-image count, protocol-timeout flag) STRAIGHT
+    INTO PINNED HOST MEMORY (zero-copy over PCIe: pinned allocations are device-addressable under
+    unified addressing), so no D2H memcpy sits on the stream between the forward and the backward
+    kernels.  A ring of 64 slots, each guarded by a CUDA event recorded after the launch; a slot is
+    reused once its event has completed."""
     SLOTS = 64
 
     def __init__(self):
@@ -75,9 +78,10 @@ class _WarnQueue:
         self.free = []
         self.events = []
 
-    def push(self, dev_flag: torch.Tensor):
+    def acquire(self, device):
+        """-> (slot, device-usable pointer to int32[2]) or (None, 0) while a CUDA graph is being captured."""
         if torch.cuda.is_current_stream_capturing():
-            return
+            return None, 0
         if self.host is None:
             self.host = torch.zeros(self.SLOTS, 2, dtype=torch.int32).pin_memory()
             self.free = list(range(self.SLOTS))
@@ -88,22 +92,26 @@ class _WarnQueue:
                 self.pending[0][0].synchronize()
                 self.poll()
         slot = self.free.pop()
-        self.host[slot, :dev_flag.numel()].copy_(dev_flag, non_blocking=True)
+        self.host[slot].zero_()
+        return slot, self.host[slot].data_ptr()
+
+    def commit(self, slot, device):
+        if slot is None:
+            return
         ev = self.events[slot]
-        ev.record(torch.cuda.current_stream(dev_flag.device))
-        self.pending.append((ev, slot, dev_flag.numel()))
+        ev.record(torch.cuda.current_stream(device))
+        self.pending.append((ev, slot))
 
     def poll(self, block: bool = False) -> int:
         """Print the reference's warning for finished launches; returns images guarded so far."""
         if not self.pending:
             return 0
         total, keep = 0, []
-        for ev, slot, n_flags in self.pending:
+        for ev, slot in self.pending:
             if block:
                 ev.synchronize()
             if ev.query():
-                n = int(self.host[slot, 0])
-                proto = int(self.host[slot, 1]) if n_flags > 1 else 0
+                n, proto = int(self.host[slot, 0]), int(self.host[slot, 1])
                 self.free.append(slot)
                 if proto:
                     raise _lib.PnceError("libpnce kernel protocol timeout (tcgen05 pipeline stalled)")
@@ -111,7 +119,7 @@ class _WarnQueue:
                     print(f"Warning: NaN in PatchNCE loss. {n} (layer, image) loss(es) replaced by 0.")
                 total += n
             else:
-                keep.append((ev, slot, n_flags))
+                keep.append((ev, slot))
         self.pending = keep
         return total
 
@@ -172,17 +180,16 @@ class _FusedPatchNCE(torch.autograd.Function):
         with torch.cuda.device(dev):
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             out = torch.empty(1 + n, dtype=torch.float32, device=dev)
-            flag = torch.empty(2, dtype=torch.int32, device=dev)     # both words are written by the kernels
+            slot, flag_ptr = _warnings.acquire(dev)           # both words are written by the kernels
             _lib.check(lib.pnce_fwd(layers, n, batch, dtype, plan.temperature, _MATH[plan.math],
-                                    ws.data_ptr(), ws_bytes, out.data_ptr(), flag.data_ptr(),
+                                    ws.data_ptr(), ws_bytes, out.data_ptr(), flag_ptr or None,
                                     _stream_ptr(dev)), "pnce_fwd")
-        _warnings.push(flag)
+            _warnings.commit(slot, dev)
         ctx.plan, ctx.ws, ctx.ws_bytes = plan, ws, ws_bytes
         ctx.tgt_meta = [(t.shape, t.dtype) for t in tgt]
         ctx.tgt_keep = tgt               # shapes only matter, but keeps data_ptrs stable for the struct
         ctx.dev, ctx.batch, ctx.dtype = dev, batch, dtype
         ctx.layer_losses = out[1:]
-        ctx.nonfinite = flag
         return out.narrow(0, 0, 1).reshape(())
 
     @staticmethod
@@ -354,13 +361,13 @@ class _RowsLossFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
             out = torch.empty(2, dtype=torch.float32, device=dev)
-            flag = torch.empty(1, dtype=torch.int32, device=dev)
+            slot, flag_ptr = _warnings.acquire(dev)
             dq = torch.empty_like(qq)
             _lib.check(lib.pnce_rows_loss_fwd_bwd(qq.data_ptr(), kk.data_ptr(), batch, p, d, temperature,
                                                   _MATH[math], ws.data_ptr(), nbytes.value, out.data_ptr(),
-                                                  flag.data_ptr(), dq.data_ptr(), None, _stream_ptr(dev)),
+                                                  flag_ptr or None, dq.data_ptr(), None, _stream_ptr(dev)),
                        "pnce_rows_loss_fwd_bwd")
-        _warnings.push(flag)
+            _warnings.commit(slot, dev)
         ctx.save_for_backward(dq)
         ctx.q_dtype = q.dtype
         return out.narrow(0, 0, 1).reshape(())
@@ -466,11 +473,11 @@ class _FusedHeadPatchNCE(torch.autograd.Function):
         with torch.cuda.device(dev):
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
             out = torch.empty(1 + n, dtype=torch.float32, device=dev)
-            flag = torch.zeros(2, dtype=torch.int32, device=dev)
+            slot, flag_ptr = _warnings.acquire(dev)
             _lib.check(lib.pnce_head_fwd(layers, heads, n, batch, dtype, nc, plan.temperature, _MATH[plan.math],
-                                         ws.data_ptr(), nbytes.value, out.data_ptr(), flag.data_ptr(),
+                                         ws.data_ptr(), nbytes.value, out.data_ptr(), flag_ptr or None,
                                          _stream_ptr(dev)), "pnce_head_fwd")
-        _warnings.push(flag)
+            _warnings.commit(slot, dev)
         ctx.plan, ctx.ws, ctx.ws_bytes, ctx.nc = plan, ws, nbytes.value, nc
         ctx.tgt_keep, ctx.params = tgt, params
         ctx.param_meta = [(a.shape, a.dtype) for a in args[n:]]
