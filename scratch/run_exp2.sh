@@ -1,4 +1,3 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
-timeout 300 python scratch/exp3.py 2>&1 | grep -v Warn | head -9
-python bench.py --no-cpu-baseline --no-e2e | cut -c1-250
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+timeout 300 python scratch/exp3.py 2>&1 | grep -E "wall"
