@@ -104,8 +104,8 @@ class _WarnQueue:
 
     def poll(self, block: bool = False) -> int:
         """Print the reference's warning for finished launches; returns images guarded so far."""
-        if not self.pending:
-            return 0
+        if not self.pending or torch.cuda.is_current_stream_capturing():
+            return 0                             # (cudaEventQuery is not allowed while a graph is being captured)
         total, keep = 0, []
         for ev, slot in self.pending:
             if block:

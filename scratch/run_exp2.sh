@@ -1,3 +1,2 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-timeout 300 python scratch/exp3.py 2>&1 | grep -E "wall"
+timeout 300 python scratch/exp4.py 2>&1 | grep -v Warn | head -14

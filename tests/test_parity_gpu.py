@@ -464,3 +464,42 @@ def test_half_precision_maps_head_and_many_patches(pn, orc, dtype):
     assert loss.item() == pytest.approx(want, rel=2e-5)
     assert_grad_close(t[0].grad.float().cpu().numpy(), gw[0], 1e-2, "P=600 half maps", ids=ids[0].numpy())
     assert pn.poll_nonfinite_warnings(block=True) == 0
+
+
+def test_cuda_graph_capture_and_replay(pn, orc):
+    """include/pnce.h promises that every entry point is asynchronous, sync-free and CUDA-graph
+    capturable: capture forward + backward (ids drawn inside the graph, as the reference draws them),
+    replay it, and check every replay against the oracle on the ids that replay drew."""
+    g = torch.Generator().manual_seed(4)
+    shapes = [(32, 24, 24), (64, 16, 16)]
+    src = [torch.randn(2, *s, generator=g).cuda() for s in shapes]
+    tgt = [torch.randn(2, *s, generator=g).cuda().requires_grad_() for s in shapes]
+    crit = pn.PatchNCELoss(0.07, 128)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                      # warm-up outside the capture (lazy init, smem opt-in)
+        for _ in range(2):
+            for t in tgt:
+                t.grad = None
+            crit(src, tgt).backward()
+    torch.cuda.current_stream().wait_stream(side)
+    for t in tgt:
+        t.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss = crit(src, tgt)
+        loss.backward()
+        ids_static = [i.clone() for i in crit.last_patch_ids]
+    seen = []
+    for _ in range(3):
+        graph.replay()
+        torch.cuda.synchronize()
+        ids = [i.cpu() for i in ids_static]
+        seen.append(ids[0].clone())
+        want, _, gw = orc.patchnce_loss_and_grads_np([x.cpu().numpy() for x in src],
+                                                     [x.detach().cpu().numpy() for x in tgt],
+                                                     [i.numpy() for i in ids], 0.07)
+        assert loss.item() == pytest.approx(want, rel=2e-5)
+        for l in range(2):
+            assert_grad_close(tgt[l].grad.cpu().numpy(), gw[l], 2e-4, f"replay layer {l}", ids=ids[l].numpy())
+    assert not torch.equal(seen[0], seen[1])            # the RNG stream advances from replay to replay
