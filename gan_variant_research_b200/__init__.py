@@ -11,11 +11,13 @@ from .patchnce import (  # noqa: F401
     PatchSampleF,
     compute_patchnce_loss,
     draw_patch_ids,
+    draw_patch_ids_all,
     fused_head_supported,
     fused_patchnce,
     install_reference_shim,
     patch_count,
     patchnce_with_head,
+    pinned_as_device,
     poll_nonfinite_warnings,
     rows_patchnce,
 )
@@ -23,6 +25,6 @@ from .dp import allreduce_head_grads, broadcast_patch_ids, shard_batch  # noqa: 
 
 __all__ = [
     "PatchNCELoss", "PatchSampleF", "compute_patchnce_loss", "fused_patchnce", "rows_patchnce",
-    "draw_patch_ids", "patch_count", "install_reference_shim", "poll_nonfinite_warnings",
+    "draw_patch_ids", "draw_patch_ids_all", "pinned_as_device", "patch_count", "install_reference_shim", "poll_nonfinite_warnings",
     "DEFAULT_MATH", "patchnce_with_head", "allreduce_head_grads", "broadcast_patch_ids", "shard_batch",
 ]

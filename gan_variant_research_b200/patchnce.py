@@ -60,6 +60,66 @@ def draw_patch_ids(feat: torch.Tensor, num_patches: int) -> torch.Tensor:
     return torch.randint(0, hw, (patch_count(num_patches, hw),), device=feat.device)
 
 
+_ID_STREAMS = {}         # device index -> side stream the id draws are issued on
+
+
+def draw_patch_ids_all(feats, num_patches: int) -> List[torch.Tensor]:
+    """One ``draw_patch_ids`` per layer, in layer order (patchnce_cut.py:36-38, :63) -- issued on a
+    side stream.  The draws read nothing but the generator state, which torch advances on the HOST at
+    launch time, so the ids and the RNG stream are exactly what the reference gets; on a side stream
+    the five tiny Philox kernels run under whatever the caller's stream is still busy with (the
+    previous backward, the generator's forward) instead of sitting at the head of this step's
+    critical path (measured: 18 us of a 0.92 ms step at B=64).  While a CUDA graph is being captured
+    the draws stay on the capturing stream."""
+    dev = feats[0].device
+    if not feats[0].is_cuda or torch.cuda.is_current_stream_capturing():
+        return [draw_patch_ids(f, num_patches) for f in feats]
+    main = torch.cuda.current_stream(dev)
+    side = _ID_STREAMS.get(dev.index)
+    if side is None:
+        side = _ID_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        ids = [draw_patch_ids(f, num_patches) for f in feats]
+    main.wait_stream(side)
+    for i in ids:
+        i.record_stream(main)        # allocated on the side stream's pool, consumed on the caller's
+    return ids
+
+
+class _PinnedAlias:
+    """``__cuda_array_interface__`` view of a pinned host tensor (unified addressing: a pinned
+    allocation is addressable from the device under the same pointer)."""
+
+    def __init__(self, t: torch.Tensor):
+        typestr = {torch.float32: "<f4", torch.float16: "<f2", torch.int64: "<i8"}.get(t.dtype)
+        if typestr is None:
+            raise RuntimeError(f"pinned_as_device: unsupported dtype {t.dtype}")
+        self.__cuda_array_interface__ = {"shape": tuple(t.shape), "typestr": typestr,
+                                         "data": (t.data_ptr(), False), "version": 2, "strides": None}
+
+
+def pinned_as_device(t: torch.Tensor, device=None) -> torch.Tensor:
+    """Device-side view of a PINNED, contiguous host tensor -- no copy.  Feature maps that live in host
+    memory can be handed to ``PatchNCELoss`` / ``PatchSampleF`` through this view: the gather kernel
+    then pulls exactly the sampled 32-byte sectors over PCIe (2*B*P*C of them per layer) instead of
+    the caller copying whole maps to the device first (B*C*H*W elements each) -- 8x fewer bytes on
+    the bus at the CUT shapes (bench.py ``e2e``).  The view shares storage with ``t``; keep ``t`` alive.
+    The returned tensor is a CUDA tensor as far as autograd is concerned (gradients are device
+    tensors), so ``pinned_as_device(h).requires_grad_()`` works as a target map."""
+    if t.is_cuda:
+        return t
+    if not t.is_pinned() or not t.is_contiguous():
+        raise RuntimeError("pinned_as_device needs a pinned, contiguous host tensor (tensor.pin_memory())")
+    if t.dtype == torch.bfloat16:            # no typestr for bf16: alias the bits as int16, then view
+        alias = torch.as_tensor(_PinnedAlias(t.view(torch.float16)),
+                                device=device or torch.device("cuda", torch.cuda.current_device()))
+        out = alias.view(torch.bfloat16)
+    else:
+        out = torch.as_tensor(_PinnedAlias(t), device=device or torch.device("cuda", torch.cuda.current_device()))
+    out._pnce_host_owner = t                  # keeps the pinned storage alive as long as the view
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # lazy non-finite warnings (the reference prints from inside the loop after a host sync, :97-98;
 # here the flag is copied to pinned memory asynchronously and reported on a later call)
@@ -280,7 +340,7 @@ class PatchNCELoss(nn.Module):
         src_feats, tgt_feats = list(a), list(b)
         _warnings.poll()
         n = min(len(src_feats), len(tgt_feats))
-        ids = [draw_patch_ids(src_feats[l], self.num_patches) for l in range(n)]      # :60-63
+        ids = draw_patch_ids_all(src_feats[:n], self.num_patches)                      # :60-63
         self.last_patch_ids = ids
         return fused_patchnce(src_feats, tgt_feats, ids, self.temperature, self.math)
 
@@ -545,7 +605,7 @@ def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0
         netF.create_mlp(tgt_feats)
     src, tgt, _ = _prepare_maps(src_feats, tgt_feats)
     if patch_ids is None:
-        ids = [draw_patch_ids(t, num_patches) for t in tgt]
+        ids = draw_patch_ids_all(tgt, num_patches)
     else:
         ids = [i.to(device=t.device, dtype=torch.int64).contiguous() for i, t in zip(patch_ids, tgt)]
     params = []

@@ -28,3 +28,9 @@ for s_, d_ in zip(sm, dur): busy[int(s_)] += d_
 print(f'per-SM busy: mean {busy.mean():.1f} min {busy.min():.1f} max {busy.max():.1f} us; SMs used {len(set(sm.tolist()))}')
 order = np.argsort(t0)
 print('first 10 starts', np.round(t0[order][:10], 1), 'last 5 ends', np.round(np.sort(t1)[-5:], 1))
+
+# per-phase clock64 stamps of CTA 0 (C=256 layer) and CTA grid/2: epilogue slots 0..6, MMA thread 8..11
+raw = tr.cpu().numpy()[:32]
+for base_, name in ((0, 'CTA 0'), (16, 'CTA grid/2')):
+    st = raw[base_:base_ + 16]; ref = min(x for x in st if x > 0)
+    print(name, 'cycles since first stamp:', {k: int(v - ref) for k, v in enumerate(st) if v > 0})

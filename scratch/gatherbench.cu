@@ -33,6 +33,35 @@ __global__ void gather(const float* __restrict__ base, const int* __restrict__ i
   if (acc == 12345.678f) out[0] = acc;
 }
 
+// MODE 7: every thread fetches its 32 elements with 16-byte cp.async.bulk copies (TMA engine) into
+// shared memory: does the L2 still fill whole 128 B lines for a TMA-side miss?
+__global__ void gather_bulk(const float* __restrict__ base, const int* __restrict__ ids, int HW, int C, float* out) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  __shared__ uint64_t bar;
+  const int p = threadIdx.x;
+  const int chunk = blockIdx.x % (C / 32), img = blockIdx.x / (C / 32);
+  const float* col = base + ((size_t)img * C + chunk * 32) * HW + (ids[p] & ~3);
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (p == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  __syncthreads();
+  if (p == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(256 * 32 * 16));
+  __syncthreads();
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sm) + p * 512;
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], 16, [%2];"
+                 ::"r"(dst + k * 16), "l"(col + (size_t)k * HW), "r"(bar_a) : "memory");
+  uint32_t ok = 0;
+  while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar_a) : "memory");
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) acc += *reinterpret_cast<float*>(sm + p * 512 + k * 16);
+  if (acc == 12345.678f) out[0] = acc;
+}
+
 template <typename F> float timeit(F f, int n = 5) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   f();
@@ -64,6 +93,9 @@ int main(int argc, char** argv) {
     rep("ld.cg L2::64B", timeit([&] { gather<4><<<grid, 256>>>(base, ids, HW, C, out); }));
     rep("ld.cs", timeit([&] { gather<5><<<grid, 256>>>(base, ids, HW, C, out); }));
     rep("ld.cg evict_first hint", timeit([&] { gather<6><<<grid, 256>>>(base, ids, HW, C, out); }));
+    CK(cudaFuncSetAttribute(gather_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+    rep("cp.async.bulk 16 B (TMA)", timeit([&] { gather_bulk<<<grid, 256, 131072>>>(base, ids, HW, C, out); }));
+    CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     cudaFree(base);
   }

@@ -503,3 +503,30 @@ def test_cuda_graph_capture_and_replay(pn, orc):
         for l in range(2):
             assert_grad_close(tgt[l].grad.cpu().numpy(), gw[l], 2e-4, f"replay layer {l}", ids=ids[l].numpy())
     assert not torch.equal(seen[0], seen[1])            # the RNG stream advances from replay to replay
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_pinned_host_maps_zero_copy(pn, dtype):
+    """Feature maps left in pinned HOST memory and passed through ``pinned_as_device`` (the gather reads
+    the sampled sectors over PCIe) give bit-identical loss and gradients to device-resident copies."""
+    g = torch.Generator().manual_seed(8)
+    shapes = [(2, 32, 24, 24), (2, 64, 16, 16)]
+    h_src = [torch.randn(s, generator=g).to(dtype).pin_memory() for s in shapes]
+    h_tgt = [torch.randn(s, generator=g).to(dtype).pin_memory() for s in shapes]
+    a_src = [pn.pinned_as_device(h) for h in h_src]
+    a_tgt = [pn.pinned_as_device(h).requires_grad_() for h in h_tgt]
+    d_src = [h.cuda() for h in h_src]
+    d_tgt = [h.cuda().requires_grad_() for h in h_tgt]
+    assert a_src[0].is_cuda and a_src[0].data_ptr() == h_src[0].data_ptr() and a_src[0].dtype == dtype
+    crit = pn.PatchNCELoss(0.07, 128)
+    torch.manual_seed(5)
+    la = crit(a_src, a_tgt)
+    la.backward()
+    torch.manual_seed(5)
+    ld = crit(d_src, d_tgt)
+    ld.backward()
+    assert la.item() == ld.item()
+    for x, y in zip(a_tgt, d_tgt):
+        assert x.grad.is_cuda and torch.equal(x.grad, y.grad)
+    with pytest.raises(RuntimeError):
+        pn.pinned_as_device(torch.randn(4, 4))            # pageable memory is refused
