@@ -269,10 +269,10 @@ __device__ __forceinline__ void tc_dq_epilogue(uint32_t tacc, int nstage, int C,
                                                const __nv_bfloat16* __restrict__ ql, float* __restrict__ dxrow,
                                                float c1, float c2, bool rowok, __nv_bfloat16* dyh,
                                                __nv_bfloat16* dyl, uint64_t* dqfull, volatile int* dead,
-                                               TcQChunk& qa, TcQChunk& qb, int np_rt = 0) {
+                                               TcQChunk& qa, TcQChunk& qb, int np_rt = 0, uint32_t parity = 0u) {
   using namespace umma;
   const size_t NP = NPC ? (size_t)NPC : (size_t)np_rt;
-  mbar_wait(dqfull, 0u, dead);
+  mbar_wait(dqfull, parity, dead);
   tc_fence_after();
   for (int s = 0; s < nstage; s += 2) {
     uint32_t r[32];

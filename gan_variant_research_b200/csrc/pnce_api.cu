@@ -11,6 +11,7 @@
 #include "gemm_tc.cuh"
 #include "loss_simt.cuh"
 #include "loss_tc.cuh"
+#include "loss_tc_persist.cuh"
 #include "sample_bwd.cuh"
 
 namespace pnce {
@@ -226,7 +227,29 @@ static int launch_gather_tc(const Params& p, cudaStream_t st) {
   return PNCE_OK;
 }
 
-static int launch_loss_tc(const Params& p, cudaStream_t st) {
+// Experiment knobs (pnce_debug_set; not part of pnce.h).  0 = library default.
+struct DebugKnobs {
+  int dense_flags = 0;       // bit 0: skip the patch phase (fill ceiling)
+  int fwd_chunks = 0;        // n > 1: cut the tensor-core forward into n chunks, loss(c) on an aux stream || gather(c+1)
+  int no_persist = 0;        // 1: one CTA per item (k_loss_tc) even where the persistent kernel applies
+  int persist_ctas = 0;      // > 0: grid of the persistent loss kernel (default: one CTA per SM)
+  long long* trace = nullptr;
+};
+static DebugKnobs g_dbg;
+
+static int sm_count(int* out) {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  PNCE_CUDA(cudaGetDevice(&dev));
+  if (dev != cached_dev) {
+    PNCE_CUDA(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
+    cached_dev = dev;
+  }
+  *out = cached;
+  return PNCE_OK;
+}
+
+static int launch_loss_tc(const Params& p, cudaStream_t st, bool single_launch = true) {
   BlockMap m;
   memset(&m, 0, sizeof(m));
   // heavy layers (large C) first: the last, partially filled wave of CTAs is then made of the cheap ones
@@ -241,22 +264,32 @@ static int launch_loss_tc(const Params& p, cudaStream_t st) {
     acc += (long long)p.bn * (p.L[order[s]].Ppad / 128);
   }
   m.start[p.n_layers] = acc;
+  if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+  // P <= 256 everywhere (one key block per item): persistent kernel, one CTA per SM walking the item list
+  bool persist = single_launch && !g_dbg.no_persist;
+  for (int l = 0; l < p.n_layers; ++l)
+    if (p.L[l].Ppad > 256) persist = false;
+  if (persist) {
+    int nsm = 0;
+    int rc = sm_count(&nsm);
+    if (rc != PNCE_OK) return rc;
+    long long grid = g_dbg.persist_ctas > 0 ? g_dbg.persist_ctas : nsm;
+    if (grid > acc) grid = acc;
+    rc = set_smem(k_loss_tc_p, kTpSmemBytes);
+    if (rc != PNCE_OK) return rc;
+    Params q = p;
+    q.total_ctas = (unsigned)grid;
+    k_loss_tc_p<<<(unsigned)grid, kTpThreads, kTpSmemBytes, st>>>(q, m);
+    PNCE_CUDA(cudaGetLastError());
+    return PNCE_OK;
+  }
   int rc = set_smem(k_loss_tc, kTcSmemBytes);
   if (rc != PNCE_OK) return rc;
-  if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
   k_loss_tc<<<(unsigned)acc, kTcThreads, kTcSmemBytes, st>>>(p, m);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
 
-
-// Experiment knobs (pnce_debug_set; not part of pnce.h).  0 = library default.
-struct DebugKnobs {
-  int dense_flags = 0;       // bit 0: skip the patch phase (fill ceiling)
-  int fwd_chunks = 0;        // n > 1: cut the tensor-core forward into n chunks, loss(c) on an aux stream || gather(c+1)
-  long long* trace = nullptr;
-};
-static DebugKnobs g_dbg;
 
 // ---- chunked tensor-core forward ---------------------------------------------------------------
 // The gather is HBM-bound and the tcgen05 loss kernel is not, so the batch is cut into chunks and
@@ -316,7 +349,7 @@ static int forward_tc(Params& p, cudaStream_t st) {
     if (rc != PNCE_OK) return rc;
     PNCE_CUDA(cudaEventRecord(ax->ev[c], st));
     PNCE_CUDA(cudaStreamWaitEvent(ax->aux, ax->ev[c], 0));
-    rc = launch_loss_tc(p, ax->aux);
+    rc = launch_loss_tc(p, ax->aux, false);
     if (rc != PNCE_OK) return rc;
   }
   PNCE_CUDA(cudaEventRecord(ax->join, ax->aux));
@@ -401,8 +434,28 @@ int pnce_debug_set(int key, long long value) {
     case 1: g_dbg.dense_flags = (int)value; break;
     case 3: g_dbg.trace = reinterpret_cast<long long*>(value); break;
     case 5: g_dbg.fwd_chunks = (int)value; break;
+    case 6: g_dbg.no_persist = (int)value; break;
+    case 7: g_dbg.persist_ctas = (int)value; break;
     default: return PNCE_ERR_ARG;
   }
+  return PNCE_OK;
+}
+// Experiment: occupy `n_sms` SMs (one CTA with 227 KB of shared memory each) until *stop != 0 (bounded, ~40 ms):
+// what do the other kernels lose when a persistent kernel owns part of the GPU?
+__global__ void k_debug_blocker(volatile int* stop, int* resident) {
+  extern __shared__ unsigned char bs[];
+  if (threadIdx.x == 0) atomicAdd(resident, 1);
+  const long long t0 = clock64();
+  while (clock64() - t0 < 80000000ll) {
+    if (*stop != 0) break;
+    __nanosleep(10000);
+  }
+  if (bs[0] == 77 && *stop == 12345) *resident = -1;
+}
+int pnce_debug_block_sms(int n_sms, int* stop_and_resident, void* stream) {
+  PNCE_CUDA(cudaFuncSetAttribute(k_debug_blocker, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  k_debug_blocker<<<n_sms, 1, 226 * 1024, static_cast<cudaStream_t>(stream)>>>(stop_and_resident, stop_and_resident + 1);
+  PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
 // device-wide L2 fetch granularity hint, 32/64/128 bytes

@@ -71,6 +71,8 @@ def draw_patch_ids_all(feats, num_patches: int) -> List[torch.Tensor]:
     previous backward, the generator's forward) instead of sitting at the head of this step's
     critical path (measured: 18 us of a 0.92 ms step at B=64).  While a CUDA graph is being captured
     the draws stay on the capturing stream."""
+    if len(feats) == 0:
+        return []
     dev = feats[0].device
     if not feats[0].is_cuda or torch.cuda.is_current_stream_capturing():
         return [draw_patch_ids(f, num_patches) for f in feats]

@@ -62,6 +62,19 @@ __global__ void gather_bulk(const float* __restrict__ base, const int* __restric
   if (acc == 12345.678f) out[0] = acc;
 }
 
+// Occupies one SM per CTA (227 KB of dynamic shared memory) and spins for `cycles`: emulates a persistent
+// kernel that owns S SMs while the gather runs on the others.
+__global__ void blocker(volatile int* stop, int* resident, float* out) {
+  extern __shared__ unsigned char bs[];
+  if (threadIdx.x == 0) atomicAdd(resident, 1);
+  const long long t0 = clock64();
+  while (clock64() - t0 < 40000000ll) {                     // released by the host (bounded: ~20 ms)
+    if (threadIdx.x == 0 && *stop != 0) break;              // one poll per ~10 us, by one thread: no memory traffic to speak of
+    __nanosleep(10000);
+  }
+  if (bs[threadIdx.x] == 77 && *stop == 12345) out[0] = 1.f;
+}
+
 template <typename F> float timeit(F f, int n = 5) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   f();
@@ -93,6 +106,30 @@ int main(int argc, char** argv) {
     rep("ld.cg L2::64B", timeit([&] { gather<4><<<grid, 256>>>(base, ids, HW, C, out); }));
     rep("ld.cs", timeit([&] { gather<5><<<grid, 256>>>(base, ids, HW, C, out); }));
     rep("ld.cg evict_first hint", timeit([&] { gather<6><<<grid, 256>>>(base, ids, HW, C, out); }));
+    // gather speed when S SMs are owned by another (persistent) kernel
+    {
+      CK(cudaFuncSetAttribute(blocker, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      cudaStream_t sa, sb; CK(cudaStreamCreateWithFlags(&sa, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking));
+      cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+      int* stop; CK(cudaHostAlloc(&stop, 8, cudaHostAllocMapped));
+      volatile int* res = stop + 1;
+      for (int S : {0, 16, 32, 48, 64, 80}) {
+        CK(cudaDeviceSynchronize());
+        stop[0] = 0; stop[1] = 0;
+        if (S) blocker<<<S, 1, 227 * 1024, sa>>>(stop, stop + 1, out);
+        while (*res < S) { }                                             // all blocker CTAs are resident
+        gather<0><<<grid, 256, 0, sb>>>(base, ids, HW, C, out);          // warm
+        CK(cudaEventRecord(e0, sb));
+        for (int r = 0; r < 3; ++r) gather<0><<<grid, 256, 0, sb>>>(base, ids, HW, C, out);
+        CK(cudaEventRecord(e1, sb));
+        CK(cudaEventSynchronize(e1));
+        stop[0] = 1;
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        char nm[64]; snprintf(nm, sizeof(nm), "ld.cg, %d SMs blocked", S);
+        rep(nm, ms / 3 * 1e3f);
+      }
+      CK(cudaDeviceSynchronize());
+    }
     CK(cudaFuncSetAttribute(gather_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
     rep("cp.async.bulk 16 B (TMA)", timeit([&] { gather_bulk<<<grid, 256, 131072>>>(base, ids, HW, C, out); }));
     CK(cudaGetLastError());
