@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--head", action="store_true", help="time the netF-head mode (nc=256) as the workload")
     ap.add_argument("--no-head-line", action="store_true", help="skip the secondary head-mode measurement")
+    ap.add_argument("--clock-period", type=float, default=0.02, help="seconds between NVML clock samples (0: no sampling)")
     return ap.parse_args()
 
 
@@ -261,8 +262,12 @@ def main():
         netF.create_mlp(tgt)
     torch.manual_seed(7)           # identical ids on every rank
 
-    ev_b0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev_b1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    # CUDA events around the backward (the dominant kernel's launch) on every EV_STRIDE-th step of the
+    # timed region: a timing event between two kernels costs a few microseconds of stream bubble, which
+    # on a 0.9 ms step is worth measuring around, not paying 2x per step
+    EV_STRIDE = 4
+    ev_b0 = {i: torch.cuda.Event(enable_timing=True) for i in range(0, args.steps, EV_STRIDE)}
+    ev_b1 = {i: torch.cuda.Event(enable_timing=True) for i in range(0, args.steps, EV_STRIDE)}
 
     def step(i=None):
         for t in tgt:
@@ -271,13 +276,14 @@ def main():
             loss = crit(src, tgt)
         else:
             netF.zero_grad(set_to_none=True)
-            loss, _ = pn.patchnce_with_head(netF, src, tgt, args.tau, args.patches, math=math)
-        if i is not None:
+            # dp_group: the head gradients leave backward() already averaged over the ranks -- the only
+            # collective of the path, started on a side stream under the dense kernel
+            loss, _ = pn.patchnce_with_head(netF, src, tgt, args.tau, args.patches, math=math,
+                                            dp_group=True if world > 1 else None)
+        if i in ev_b0:
             ev_b0[i].record()
         loss.backward()
-        if netF is not None and world > 1:
-            pn.allreduce_head_grads(netF)          # the only collective of the path
-        if i is not None:
+        if i in ev_b1:
             ev_b1[i].record()
         return loss
 
@@ -286,7 +292,7 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, period=args.clock_period or 1e9)
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -305,7 +311,7 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
     ms = float(tmax.item())
-    bwd_ms = sorted(a.elapsed_time(b) for a, b in zip(ev_b0, ev_b1))
+    bwd_ms = sorted(ev_b0[i].elapsed_time(ev_b1[i]) for i in ev_b0)
     bwd_med = bwd_ms[len(bwd_ms) // 2]
     patches_per_image = sum(min(args.patches, h * w) for _, h, w, _ in layers)
     value = world * B * patches_per_image * args.steps / (ms * 1e-3)

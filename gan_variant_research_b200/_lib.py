@@ -15,7 +15,7 @@ EXPORTS = [
     "pnce_abi_version", "pnce_status_string", "pnce_last_cuda_error", "pnce_workspace_bytes",
     "pnce_fwd", "pnce_bwd", "pnce_sample_fwd", "pnce_sample_bwd_workspace_bytes",
     "pnce_sample_bwd", "pnce_rows_loss_workspace_bytes", "pnce_rows_loss_fwd_bwd", "pnce_selftest_umma",
-    "pnce_head_workspace_bytes", "pnce_head_fwd", "pnce_head_bwd",
+    "pnce_head_workspace_bytes", "pnce_head_fwd", "pnce_head_bwd", "pnce_head_bwd_params", "pnce_head_bwd_dense",
 ]
 
 
@@ -65,8 +65,8 @@ def load():
     lib.pnce_head_workspace_bytes.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, ctypes.POINTER(sz)]
     lib.pnce_head_fwd.argtypes = [ctypes.POINTER(PnceLayer), ctypes.POINTER(PnceHead), i32, i32, i32, i32, f32, i32,
                                   vp, sz, vp, vp, vp]
-    lib.pnce_head_bwd.argtypes = [ctypes.POINTER(PnceLayer), ctypes.POINTER(PnceHead), i32, i32, i32, i32, i32,
-                                  vp, sz, vp, vp]
+    for fn in (lib.pnce_head_bwd, lib.pnce_head_bwd_params, lib.pnce_head_bwd_dense):
+        fn.argtypes = [ctypes.POINTER(PnceLayer), ctypes.POINTER(PnceHead), i32, i32, i32, i32, i32, vp, sz, vp, vp]
     u32 = ctypes.c_uint
     lib.pnce_selftest_umma.argtypes = [vp, sz, vp, sz, u32, u32, u32, u32, u32, u32, i32, i32, i32, vp, vp, vp]
     for name in EXPORTS:

@@ -911,10 +911,15 @@ int pnce_head_fwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_la
   return launch_loss_tc(pl, st);
 }
 
-int pnce_head_bwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
-                  int nc, int math_mode, void* ws, size_t ws_bytes, const float* grad_out, void* stream) {
-  int rc = check_head_args(layers, heads, n_layers, batch, dtype, nc, math_mode, ws, true);
+// phases: bit 0 = head backward proper (dH, dX, weight / bias gradients), bit 1 = dense d tgt_feat
+static int head_bwd_phases(int phases, const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch,
+                           int dtype, int nc, int math_mode, void* ws, size_t ws_bytes, const float* grad_out,
+                           void* stream) {
+  int rc = check_head_args(layers, heads, n_layers, batch, dtype, nc, math_mode, ws, (phases & 2) != 0);
   if (rc != PNCE_OK) return rc;
+  if (phases & 1)
+    for (int l = 0; l < n_layers; ++l)
+      if (!heads[l].dw1 || !heads[l].db1 || !heads[l].dw2 || !heads[l].db2) return PNCE_ERR_ARG;
   const bool x3 = math_mode == PNCE_MATH_TC_BF16X3;
   static thread_local HeadPlan hp;
   if (carve_head(layers, n_layers, batch, nc, x3, ws, &hp) > ws_bytes) return PNCE_ERR_WORKSPACE;
@@ -922,6 +927,7 @@ int pnce_head_bwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_la
   Params& pg = hp.pg;
   pg.dtype = dtype;
   pg.grad_out = grad_out;
+  if (!(phases & 1)) return launch_dense(pg, st);
   static thread_local GemmLaunch g;
   // 1. dH = (dY W2) * [H > 0]
   memset(&g, 0, sizeof(g));
@@ -999,7 +1005,21 @@ int pnce_head_bwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_la
     PNCE_CUDA(cudaGetLastError());
   }
   // 4. dense d tgt_feat (zero fill + sampled positions), scaled by the upstream gradient
+  if (!(phases & 2)) return PNCE_OK;
   return launch_dense(pg, st);
+}
+
+int pnce_head_bwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
+                  int nc, int math_mode, void* ws, size_t ws_bytes, const float* grad_out, void* stream) {
+  return head_bwd_phases(3, layers, heads, n_layers, batch, dtype, nc, math_mode, ws, ws_bytes, grad_out, stream);
+}
+int pnce_head_bwd_params(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
+                         int nc, int math_mode, void* ws, size_t ws_bytes, const float* grad_out, void* stream) {
+  return head_bwd_phases(1, layers, heads, n_layers, batch, dtype, nc, math_mode, ws, ws_bytes, grad_out, stream);
+}
+int pnce_head_bwd_dense(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
+                        int nc, int math_mode, void* ws, size_t ws_bytes, const float* grad_out, void* stream) {
+  return head_bwd_phases(2, layers, heads, n_layers, batch, dtype, nc, math_mode, ws, ws_bytes, grad_out, stream);
 }
 
 int pnce_selftest_umma(const void* a_blob, size_t a_bytes, const void* b_blob, size_t b_bytes,

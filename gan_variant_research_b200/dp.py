@@ -49,6 +49,41 @@ def broadcast_patch_ids(ids: List[torch.Tensor], src: int = 0, group=None) -> Li
     return ids
 
 
+_COMM_STREAMS = {}
+
+
+def comm_stream(device) -> "torch.cuda.Stream":
+    """Side stream the overlapped head-gradient all-reduce runs on (one per device)."""
+    key = torch.device(device).index
+    st = _COMM_STREAMS.get(key)
+    if st is None:
+        st = _COMM_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
+def resolve_group(group):
+    """``True`` -> the default process group; returns None when there is nothing to reduce over."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    if group is True:
+        group = dist.group.WORLD
+    return group if dist.get_world_size(group) > 1 else None
+
+
+def allreduce_flat_(flat: torch.Tensor, group=None, average: bool = True) -> torch.Tensor:
+    """In-place sum (or mean) of one flat buffer over the ranks, on the current stream."""
+    world = _world(group)
+    if world == 1:
+        return flat
+    if average and dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat.div_(world)
+    return flat
+
+
 def allreduce_head_grads(module: torch.nn.Module, group=None, average: bool = True) -> int:
     """Sum (or average) the gradients of ``module``'s parameters over the ranks with one flat
     all-reduce.  Returns the number of elements reduced (0 when there is nothing to do)."""

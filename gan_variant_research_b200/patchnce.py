@@ -199,11 +199,12 @@ def poll_nonfinite_warnings(block: bool = False) -> int:
 class _Plan:
     """Everything the two C-ABI calls need that is not a differentiable input."""
 
-    def __init__(self, src_feats, ids_list, temperature, math):
+    def __init__(self, src_feats, ids_list, temperature, math, dp_group=None):
         self.src_feats = src_feats
         self.ids_list = ids_list
         self.temperature = float(temperature)
         self.math = math
+        self.dp_group = dp_group      # head mode: process group whose ranks average the head gradients
 
 
 _WS_BYTES = {}      # (batch, layer shapes) -> pnce_workspace_bytes, queried once per problem shape
@@ -552,9 +553,13 @@ class _FusedHeadPatchNCE(torch.autograd.Function):
         lib = _lib.load()
         dev, n = ctx.dev, len(ctx.tgt_keep)
         g = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous()
+        group = ctx.plan.dp_group
         with torch.cuda.device(dev):
             grads = [torch.empty_like(t) for t in ctx.tgt_keep]
-            pgrads = [torch.empty_like(p) for p in ctx.params]
+            # every head gradient is a view of ONE flat fp32 buffer: the data-parallel all-reduce needs no packing
+            sizes = [p.numel() for p in ctx.params]
+            flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            pgrads = [v.view_as(p) for v, p in zip(flat.split(sizes), ctx.params)]
             layers = _layer_array(ctx.plan.src_feats, ctx.tgt_keep, grads, ctx.plan.ids_list)
             heads = (_lib.PnceHead * n)()
             for l in range(n):
@@ -564,9 +569,22 @@ class _FusedHeadPatchNCE(torch.autograd.Function):
                                                                       b2.data_ptr())
                 heads[l].dw1, heads[l].db1, heads[l].dw2, heads[l].db2 = (d1.data_ptr(), e1.data_ptr(),
                                                                           d2.data_ptr(), e2.data_ptr())
-            _lib.check(lib.pnce_head_bwd(layers, heads, n, ctx.batch, ctx.dtype, ctx.nc, _MATH[ctx.plan.math],
-                                         ctx.ws.data_ptr(), ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev)),
-                       "pnce_head_bwd")
+            args = (layers, heads, n, ctx.batch, ctx.dtype, ctx.nc, _MATH[ctx.plan.math], ctx.ws.data_ptr(),
+                    ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev))
+            if group is None:
+                _lib.check(lib.pnce_head_bwd(*args), "pnce_head_bwd")
+            else:
+                # data parallel: head gradients first, their all-reduce on a side stream UNDER the dense kernel
+                from . import dp
+                _lib.check(lib.pnce_head_bwd_params(*args), "pnce_head_bwd_params")
+                main = torch.cuda.current_stream(dev)
+                side = dp.comm_stream(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    dp.allreduce_flat_(flat, group, average=True)
+                flat.record_stream(side)
+                _lib.check(lib.pnce_head_bwd_dense(*args), "pnce_head_bwd_dense")
+                main.wait_stream(side)
         pgrads = [pg.to(dt).reshape(shape) for pg, (shape, dt) in zip(pgrads, ctx.param_meta)]
         return (None, None, *grads, *pgrads)
 
@@ -579,7 +597,8 @@ def fused_head_supported(netF: "PatchSampleF", feats, num_patches) -> bool:
 
 
 def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0.07, num_patches=256,
-                       patch_ids=None, math: Optional[str] = None, fused: Optional[bool] = None):
+                       patch_ids=None, math: Optional[str] = None, fused: Optional[bool] = None,
+                       dp_group=None):
     """North-star composition:
     ``feat_k, ids = netF(src_feats, num_patches, patch_ids)`` (no grad into k, as upstream CUT and the
     reference's ``detach`` :142), ``feat_q, _ = netF(tgt_feats, num_patches, ids)``, then
@@ -588,7 +607,13 @@ def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0
     ``fused`` (default: whenever the shapes allow) runs the whole thing -- gather, both Linear layers,
     normalisation, logits, CE and the complete backward including the head gradients -- in the
     tcgen05 kernels of libpnce; otherwise the module-split composition is used (libpnce gather /
-    scatter / rows loss around ATen's Linear)."""
+    scatter / rows loss around ATen's Linear).
+
+    ``dp_group`` (fused path; ``True`` = the default process group): data-parallel training with the batch
+    sharded over the ranks -- the head gradients that come out of ``backward`` are already AVERAGED over
+    the group: one flat all-reduce, started on a side stream as soon as the weight-gradient kernels are
+    done, so it runs under the HBM-bound dense-gradient kernel.  Do not call
+    ``allreduce_head_grads`` as well."""
     if fused is None:
         fused = fused_head_supported(netF, tgt_feats, num_patches) and (math or DEFAULT_MATH) != "simt_f32"
     if not fused:
@@ -614,7 +639,10 @@ def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0
     for l in range(len(tgt)):
         mlp = getattr(netF, f"mlp_{l}")
         params += [mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias]
-    plan = _Plan(src, ids, temperature, math or DEFAULT_MATH)
+    if dp_group is not None:
+        from . import dp
+        dp_group = dp.resolve_group(dp_group)          # None when not initialised or world size 1
+    plan = _Plan(src, ids, temperature, math or DEFAULT_MATH, dp_group)
     _warnings.poll()
     loss = _FusedHeadPatchNCE.apply(plan, netF.nc, *tgt, *params)
     return loss, ids

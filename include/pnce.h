@@ -136,6 +136,16 @@ int pnce_head_fwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_la
 int pnce_head_bwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
                   int nc, int math_mode, void* dev_workspace, size_t workspace_bytes,
                   const float* dev_grad_out, void* stream);
+/* The same backward in two calls, for data-parallel callers: _params writes every heads[l].d* (layers[l].dtgt
+ * may be NULL), _dense then writes every layers[l].dtgt.  Between the two the caller can start the all-reduce
+ * of the head gradients on another stream, so that the only collective of the path
+ * runs under the HBM-bound dense kernel instead of after it.  Same workspace and arguments for both.      */
+int pnce_head_bwd_params(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
+                         int nc, int math_mode, void* dev_workspace, size_t workspace_bytes,
+                         const float* dev_grad_out, void* stream);
+int pnce_head_bwd_dense(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
+                        int nc, int math_mode, void* dev_workspace, size_t workspace_bytes,
+                        const float* dev_grad_out, void* stream);
 
 /* Library self-test of the tcgen05 building blocks (bulk copy -> smem, tcgen05.mma with a K-major
  * or MN-major B operand, commit, tcgen05.ld): D(128 x n) = A(128 x k) * B on pre-tiled bf16 operand

@@ -120,3 +120,26 @@ def test_patch_count_and_signature_defaults():
     assert (m.temperature, m.num_patches, m.nce_layers) == (0.07, 256, [0, 4, 8, 12, 16])
     s = inspect.signature(pn.PatchSampleF.forward)
     assert list(s.parameters)[1:] == ["feats", "num_patches", "patch_ids"]
+
+
+def test_id_draw_helper_follows_the_reference_order_on_cpu():
+    """draw_patch_ids_all = one randint per layer in layer order (patchnce_cut.py:36-38, :63); on CPU
+    tensors (no side stream) it must consume the global generator exactly like the reference loop."""
+    import gan_variant_research_b200 as pn
+    shapes = [(8, 16, 16), (4, 3, 3), (16, 32, 32)]
+    feats = [torch.zeros(2, *s) for s in shapes]
+    torch.manual_seed(7)
+    got = pn.draw_patch_ids_all(feats, 64)
+    after_got = torch.rand(3)
+    torch.manual_seed(7)
+    want = [torch.randint(0, s[1] * s[2], (min(64, s[1] * s[2]),)) for s in shapes]
+    after_want = torch.rand(3)
+    assert all(torch.equal(g, w) and g.dtype == torch.int64 for g, w in zip(got, want))
+    assert torch.equal(after_got, after_want)
+    assert pn.draw_patch_ids_all([], 64) == []
+
+
+def test_pinned_view_refuses_pageable_memory():
+    import gan_variant_research_b200 as pn
+    with pytest.raises(RuntimeError, match="pinned"):
+        pn.pinned_as_device(torch.zeros(4, 4))

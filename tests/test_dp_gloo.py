@@ -62,6 +62,11 @@ def _worker(rank, world, port, out_dir):
         loss.backward()
         n = dp.allreduce_head_grads(net)
         assert n == sum(p.numel() for p in net.parameters())
+        # the flat in-place reduction the fused head backward uses (mean over the group)
+        assert dp.resolve_group(True) is dist.group.WORLD
+        flat = torch.full((5,), float(rank + 1))
+        dp.allreduce_flat_(flat, dp.resolve_group(True), average=True)
+        assert torch.equal(flat, torch.full((5,), 1.5))
         lsum = loss.detach().clone()
         dist.all_reduce(lsum)
         torch.save({"loss": lsum / world, "head": [p.grad.clone() for p in net.parameters()],
@@ -102,3 +107,6 @@ def test_single_process_helpers_are_no_ops():
     assert dp.allreduce_head_grads(lin) == 0
     ids = [torch.arange(3)]
     assert dp.broadcast_patch_ids(ids) is ids
+    assert dp.resolve_group(True) is None            # no process group: nothing to reduce over
+    flat = torch.ones(3)
+    assert dp.allreduce_flat_(flat) is flat and torch.equal(flat, torch.ones(3))
