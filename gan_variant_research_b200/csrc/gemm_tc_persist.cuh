@@ -1,0 +1,226 @@
+// netF head GEMMs, PERSISTENT variant of k_gemm_tc (gemm_tc.cuh): same operand blobs, same five epilogue
+// modes, but one CTA per SM walks the tile list of the launch with a DOUBLE-BUFFERED TMEM accumulator
+// (2 x 256 columns), so the MMAs of tile n+1 run under the epilogue of tile n:
+//   warp 0      bulk-copy producer, 8-slot ring of 16-column K stages (192 KB): runs up to a whole tile ahead
+//   warp 1      MMA issuer (waits accfree[buf], commits accfull[buf])
+//   warps 2..9  epilogue, two warps per TMEM lane quadrant (= two per warp scheduler): the pair splits the
+//               32-column chunks of its rows even/odd -- every chunk (bias, ReLU / mask, sums of squares,
+//               hi/lo split, blob store) is self-contained, so the two never exchange anything
+// Tiles are taken round-robin (CTA c: tiles c, c+G, ...): neighbouring SMs work on the same problem at the
+// same time and share its weight blob in L2.  Launch, TMEM allocation and barrier set-up once per SM.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace pnce {
+
+constexpr int kGpThreads = 320;
+constexpr int kGpSlots = 8;
+constexpr int kGpSmemBytes = kGpSlots * kGemmStageBytes + 512;
+
+struct GpShared {
+  uint64_t full[kGpSlots], empty[kGpSlots], accfull[2], accfree[2];
+  uint32_t tmem_base;
+  int dead;
+};
+static_assert(sizeof(GpShared) <= 512, "GpShared must fit its slot");
+
+struct GpTile {
+  const GemmProb* pr;
+  int tile, K, N, nstage;
+};
+__device__ __forceinline__ void gp_decode(const GemmLaunch& g, long long t, GpTile& o) {
+  int pi = 0;
+  for (int i = 1; i < g.n; ++i)
+    if (t >= g.start[i]) pi = i;
+  o.pr = &g.pr[pi];
+  o.tile = (int)(t - g.start[pi]);
+  o.K = o.pr->K; o.N = o.pr->N; o.nstage = o.K >> 4;
+}
+
+__global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_constant__ GemmLaunch g) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  using namespace umma;
+  GpShared* sh = reinterpret_cast<GpShared*>(smem + kGpSlots * kGemmStageBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long total = g.start[g.n];
+  const bool x3 = g.x3 != 0;
+  volatile int* dead = &sh->dead;
+  if (tid == 0) {
+    for (int k = 0; k < kGpSlots; ++k) { mbar_init(&sh->full[k], 1); mbar_init(&sh->empty[k], 1); }
+    for (int k = 0; k < 2; ++k) { mbar_init(&sh->accfull[k], 1); mbar_init(&sh->accfree[k], 256); }
+    sh->dead = 0;
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&sh->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh->tmem_base;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      bool ok = true;
+      for (long long t = blockIdx.x; t < total && ok; t += gridDim.x) {
+        GpTile w;
+        gp_decode(g, t, w);
+        const GemmProb& pr = *w.pr;
+        const uint32_t bbytes = (uint32_t)w.N * 32u;          // one B chunk: 2 slabs x N rows x 16 B
+        const unsigned char* ga_hi = reinterpret_cast<const unsigned char*>(pr.a_hi) + (size_t)w.tile * (w.K >> 3) * 2048;
+        const unsigned char* ga_lo = reinterpret_cast<const unsigned char*>(pr.a_lo) + (size_t)w.tile * (w.K >> 3) * 2048;
+        const unsigned char* gb_hi = reinterpret_cast<const unsigned char*>(pr.b_hi);
+        const unsigned char* gb_lo = reinterpret_cast<const unsigned char*>(pr.b_lo);
+        for (int s = 0; s < w.nstage; ++s, ++it) {
+          const int slot = it % kGpSlots;
+          ok = mbar_wait(&sh->empty[slot], ((it / kGpSlots) & 1u) ^ 1u, dead);
+          if (!ok) break;
+          unsigned char* st = smem + slot * kGemmStageBytes;
+          mbar_expect_tx(&sh->full[slot], (4096u + bbytes) * (x3 ? 2u : 1u));
+          bulk_g2s(st, ga_hi + (size_t)s * 4096, 4096u, &sh->full[slot]);
+          if (x3) bulk_g2s(st + kGemmOffAlo, ga_lo + (size_t)s * 4096, 4096u, &sh->full[slot]);
+          bulk_g2s(st + kGemmOffBhi, gb_hi + (size_t)s * bbytes, bbytes, &sh->full[slot]);
+          if (x3) bulk_g2s(st + kGemmOffBlo, gb_lo + (size_t)s * bbytes, bbytes, &sh->full[slot]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      int n = 0;
+      bool ok = true;
+      for (long long t = blockIdx.x; t < total && ok; t += gridDim.x, ++n) {
+        GpTile w;
+        gp_decode(g, t, w);
+        const uint32_t idesc = idesc_bf16(128, w.N, 0, 0);
+        const uint32_t lbo_b = (uint32_t)w.N * 16u;
+        const uint32_t acc = tmem + (uint32_t)(n & 1) * 256u;
+        // the accumulator buffer must have been read out by the epilogue of tile n-2
+        ok = mbar_wait(&sh->accfree[n & 1], (((uint32_t)n >> 1) & 1u) ^ 1u, dead);
+        tc_fence_after();
+        for (int s = 0; s < w.nstage && ok; ++s, ++it) {
+          const int slot = it % kGpSlots;
+          ok = mbar_wait(&sh->full[slot], (it / kGpSlots) & 1u, dead);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + slot * kGemmStageBytes);
+          const uint64_t a_hi = smem_desc(st, 2048, 128);
+          const uint64_t b_hi = smem_desc(st + kGemmOffBhi, lbo_b, 128);
+          mma_bf16(acc, a_hi, b_hi, idesc, s ? 1u : 0u);
+          if (x3) {
+            const uint64_t a_lo = smem_desc(st + kGemmOffAlo, 2048, 128);
+            const uint64_t b_lo = smem_desc(st + kGemmOffBlo, lbo_b, 128);
+            mma_bf16(acc, a_hi, b_lo, idesc, 1u);
+            mma_bf16(acc, a_lo, b_hi, idesc, 1u);
+          }
+          mma_commit(&sh->empty[slot]);
+        }
+        mma_commit(&sh->accfull[n & 1]);
+      }
+    }
+  } else {
+    // ===================== epilogue: two warps per quadrant, thread <-> row of the tile =====================
+    const int q = warp & 3, i = q * 32 + lane;
+    const int half = (warp - 2) >> 2;                        // 0: even 32-column chunks, 1: odd ones
+    int n = 0;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++n) {
+      GpTile w;
+      gp_decode(g, t, w);
+      const GemmProb& pr = *w.pr;
+      const int tile = w.tile, N = w.N, N8 = N >> 3;
+      const int b = tile / pr.halves, mh = tile - b * pr.halves;
+      const int p = mh * 128 + i;                             // patch slot of this row
+      const bool rowok = p < pr.P;
+      const int Ppad = pr.Ppad, mode = pr.mode;
+      const uint32_t trow = tmem + (uint32_t)(n & 1) * 256u + ((uint32_t)(q * 32) << 16);
+      const size_t rowblob = ((size_t)tile * N8 * 16 + (size_t)(i >> 3)) * 64 + (size_t)(i & 7) * 8;   // + n8 * 1024
+      mbar_wait(&sh->accfull[n & 1], ((uint32_t)n >> 1) & 1u, dead);
+      tc_fence_after();
+      const int nch = N >> 5;
+      for (int ch = half; ch < nch; ch += 2) {
+        uint32_t r[32];
+        tmem_ld32(trow + ch * 32, r);
+        // the ReLU mask of this chunk (GM_DH) is fetched while the TMEM load is in flight
+        uint4 hm[4];
+        if (mode == GM_DH) {
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8)
+            hm[g8] = __ldcg(reinterpret_cast<const uint4*>(pr.mask_hi + rowblob + (size_t)(ch * 4 + g8) * 1024));
+        }
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          float x = __uint_as_float(r[k]);
+          if (pr.bias != nullptr) x += __ldg(pr.bias + ch * 32 + k);
+          if (mode == GM_H) x = fmaxf(x, 0.f);
+          v[k] = rowok ? x : 0.f;                             // padding rows stay exactly zero
+        }
+        if (mode == GM_DX) {
+          if (rowok) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const int c = ch * 32 + k;
+              if (c < pr.C) pr.outT[((size_t)b * pr.C + c) * Ppad + p] = v[k];
+            }
+          }
+          continue;
+        }
+        if (mode == GM_DH) {
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const uint32_t wv[4] = {hm[g8].x, hm[g8].y, hm[g8].z, hm[g8].w};
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              if ((wv[k2] & 0x7fffu) == 0u) v[g8 * 8 + 2 * k2] = 0.f;            // relu'(0) = 0
+              if ((wv[k2] & 0x7fff0000u) == 0u) v[g8 * 8 + 2 * k2 + 1] = 0.f;
+            }
+          }
+        }
+        if (mode == GM_YQ || mode == GM_YK) {
+          float ssum = 0.f;
+          bool bad = false;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            ssum = fmaf(v[k], v[k], ssum);
+            bad |= !isfinite(v[k]);
+          }
+          pr.ss[((size_t)b * nch + ch) * Ppad + p] = bad ? __int_as_float(0x7fc00000) : ssum;
+        }
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          float v8[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v8[k] = v[g8 * 8 + k];
+          uint4 hi, lo;
+          split8(v8, hi, lo);
+          const int n8 = ch * 4 + g8;
+          if (mode == GM_YK) {
+            const size_t o1 = (((size_t)b * N8 + n8) * (Ppad >> 3) + (p >> 3)) * 64 + (size_t)(p & 7) * 8;
+            const size_t o2 = (((size_t)b * (Ppad >> 3) + (p >> 3)) * N8 + n8) * 64 + (size_t)(p & 7) * 8;
+            *reinterpret_cast<uint4*>(pr.k_hi + o1) = hi;
+            *reinterpret_cast<uint4*>(pr.k2_hi + o2) = hi;
+            if (x3) {
+              *reinterpret_cast<uint4*>(pr.k_lo + o1) = lo;
+              *reinterpret_cast<uint4*>(pr.k2_lo + o2) = lo;
+            }
+          } else {
+            const size_t o = rowblob + (size_t)n8 * 1024;
+            *reinterpret_cast<uint4*>(pr.o_hi + o) = hi;
+            if (x3) *reinterpret_cast<uint4*>(pr.o_lo + o) = lo;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sh->accfree[n & 1]);                       // 256 arrivals hand the buffer back to the MMA thread
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+  if (tid == 0 && sh->dead && g.err != nullptr) *reinterpret_cast<volatile int*>(g.err) = 1;   // plain store: the flag may live in mapped host memory
+}
+
+}  // namespace pnce

@@ -9,6 +9,7 @@
 #include "gather.cuh"
 #include "gather_tc.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc_persist.cuh"
 #include "loss_simt.cuh"
 #include "loss_tc.cuh"
 #include "loss_tc_persist.cuh"
@@ -780,6 +781,19 @@ static int launch_gemm(GemmLaunch& g, cudaStream_t st) {
   for (int i = 0; i < g.n; ++i) { g.start[i] = acc; acc += g.pr[i].tiles; }
   g.start[g.n] = acc;
   if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+  if (!g_dbg.no_persist) {
+    // persistent: one CTA per SM, double-buffered TMEM accumulator (tile n+1's MMAs under tile n's epilogue)
+    int nsm = 0;
+    int rc = sm_count(&nsm);
+    if (rc != PNCE_OK) return rc;
+    long long grid = g_dbg.persist_ctas > 0 ? g_dbg.persist_ctas : nsm;
+    if (grid > acc) grid = acc;
+    rc = set_smem(k_gemm_tc_p, kGpSmemBytes);
+    if (rc != PNCE_OK) return rc;
+    k_gemm_tc_p<<<(unsigned)grid, kGpThreads, kGpSmemBytes, st>>>(g);
+    PNCE_CUDA(cudaGetLastError());
+    return PNCE_OK;
+  }
   int rc = set_smem(k_gemm_tc, kGemmSmemBytes);
   if (rc != PNCE_OK) return rc;
   k_gemm_tc<<<(unsigned)acc, kTcThreads, kGemmSmemBytes, st>>>(g);
