@@ -40,6 +40,23 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL_CTX = _NullCtx()
+
+
+def _on_device(dev):
+    """``torch.cuda.device(dev)``, or nothing when ``dev`` already is the current device (the usual case:
+    the context manager costs ~10 us of host time per use, which matters at the reference's batch of 1)."""
+    return _NULL_CTX if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+
 def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise RuntimeError(
@@ -61,6 +78,7 @@ def draw_patch_ids(feat: torch.Tensor, num_patches: int) -> torch.Tensor:
 
 
 _ID_STREAMS = {}         # device index -> side stream the id draws are issued on
+_SIDE_STREAM_MIN_BYTES = 1 << 30
 
 
 def draw_patch_ids_all(feats, num_patches: int) -> List[torch.Tensor]:
@@ -74,7 +92,10 @@ def draw_patch_ids_all(feats, num_patches: int) -> List[torch.Tensor]:
     if len(feats) == 0:
         return []
     dev = feats[0].device
-    if not feats[0].is_cuda or torch.cuda.is_current_stream_capturing():
+    # small problems are bound by this Python host, not by the GPU: the stream switch would
+    # only add host time there.  ~1 GB of feature maps is where the step's GPU time passes the host's.
+    small = sum(f.numel() * f.element_size() for f in feats) < _SIDE_STREAM_MIN_BYTES
+    if not feats[0].is_cuda or small or torch.cuda.is_current_stream_capturing():
         return [draw_patch_ids(f, num_patches) for f in feats]
     main = torch.cuda.current_stream(dev)
     side = _ID_STREAMS.get(dev.index)
@@ -240,7 +261,7 @@ class _FusedPatchNCE(torch.autograd.Function):
             nbytes = ctypes.c_size_t(0)
             _lib.check(lib.pnce_workspace_bytes(layers, n, batch, ctypes.byref(nbytes)), "pnce_workspace_bytes")
             ws_bytes = _WS_BYTES[key] = nbytes.value
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             out = torch.empty(1 + n, dtype=torch.float32, device=dev)
             slot, flag_ptr = _warnings.acquire(dev)           # both words are written by the kernels
@@ -249,6 +270,7 @@ class _FusedPatchNCE(torch.autograd.Function):
                                     _stream_ptr(dev)), "pnce_fwd")
             _warnings.commit(slot, dev)
         ctx.plan, ctx.ws, ctx.ws_bytes = plan, ws, ws_bytes
+        ctx.layers = layers              # the backward only fills in the dtgt pointers
         ctx.tgt_meta = [(t.shape, t.dtype) for t in tgt]
         ctx.tgt_keep = tgt               # shapes only matter, but keeps data_ptrs stable for the struct
         ctx.dev, ctx.batch, ctx.dtype = dev, batch, dtype
@@ -260,9 +282,11 @@ class _FusedPatchNCE(torch.autograd.Function):
         lib = _lib.load()
         dev = ctx.dev
         g = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous()
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             grads = [torch.empty(shape, dtype=dt, device=dev) for shape, dt in ctx.tgt_meta]
-            layers = _layer_array(ctx.plan.src_feats, ctx.tgt_keep, grads, ctx.plan.ids_list)
+            layers = ctx.layers
+            for l, gl in enumerate(grads):
+                layers[l].dtgt = gl.data_ptr()
             _lib.check(lib.pnce_bwd(layers, len(grads), ctx.batch, ctx.dtype, _MATH[ctx.plan.math],
                                     ctx.ws.data_ptr(), ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev)),
                        "pnce_bwd")

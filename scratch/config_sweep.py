@@ -84,7 +84,7 @@ time_case("cfg5 per-GPU AMP: B=64, 256^2, B5, bf16 maps, single-pass bf16 MMA", 
 time_case("cfg5 strong-scaling shard: B=8, 256^2, B5", B5, 8, 256, steps=100)
 time_case("north star: B=64, 256^2, B5, netF head nc=256", B5, 64, 256, head=True)
 time_case("north star: B=16, 256^2, B5, netF head nc=256", B5, 16, 256, head=True, steps=50)
-time_case("cfg4: B=8, 512^2, B5, P=1024 (fp32 CUDA-core kernels: P > 256)", B5_512, 8, 1024, steps=5)
+time_case("cfg4: B=8, 512^2, B5, P=1024 (tcgen05 kernel, key blocks of 256)", B5_512, 8, 1024, steps=5)
 time_case("cfg4 shapes at P=256: B=8, 512^2, B5", B5_512, 8, 256, steps=20)
 time_case_graph("cfg1/2: B=1, 256^2, B5", B5, 1, 256)
 time_case_graph("cfg5 strong-scaling shard: B=8, 256^2, B5", B5, 8, 256)

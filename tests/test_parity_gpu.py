@@ -119,6 +119,19 @@ def test_patch_ids_bit_exact_and_rng_stream_aligned(pn, orc):
     _, ids = pn.PatchSampleF()(tgt, 256)
     for g, w in zip(ids, want):
         assert torch.equal(g, w)
+    # large problems issue the draws on a side stream: same ids, same generator state afterwards
+    from gan_variant_research_b200 import patchnce as pmod
+    keep = pmod._SIDE_STREAM_MIN_BYTES
+    pmod._SIDE_STREAM_MIN_BYTES = 0
+    try:
+        torch.manual_seed(7)
+        mod(src, tgt)
+        after_side = torch.rand(4, device="cuda")
+    finally:
+        pmod._SIDE_STREAM_MIN_BYTES = keep
+    for g, w in zip(mod.last_patch_ids, want):
+        assert torch.equal(g, w)
+    assert torch.equal(after_side, after_want)
 
 
 @pytest.mark.parametrize("math", ["simt_f32", "tc_bf16x3"])
