@@ -90,8 +90,9 @@ __device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long loca
 __global__ void __launch_bounds__(kThreads) k_gather_tc(const __grid_constant__ Params p,
                                                         const __grid_constant__ BlockMap m) {
   const long long blk = blockIdx.x;
-  const int l = find_layer(m, blk, p.n_layers);
-  const long long local = blk - m.start[l];
+  const int slot = find_layer(m, blk, p.n_layers);
+  const int l = m.layer[slot];                                 // launch_gather_tc orders light layers first
+  const long long local = blk - m.start[slot];
   if (p.dtype == PNCE_F32) gather_tc_chunk<float>(p.L[l], p.b0, p.bn, local);
   else if (p.dtype == PNCE_F16) gather_tc_chunk<__half>(p.L[l], p.b0, p.bn, local);
   else gather_tc_chunk<__nv_bfloat16>(p.L[l], p.b0, p.bn, local);

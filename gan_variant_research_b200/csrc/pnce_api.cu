@@ -213,13 +213,23 @@ static int launch_prep(const Params& p, cudaStream_t st) {
   return PNCE_OK;
 }
 
+static int g_gather_in_layer_order = 0;   // debug knob 8
+
 static int launch_gather_tc(const Params& p, cudaStream_t st) {
   BlockMap m;
   memset(&m, 0, sizeof(m));
+  // light layers (small C) first, heavy layers last: the loss kernel starts with the heavy layers, whose
+  // operand blobs are then the most recently written lines in L2 (its first items otherwise start on cold DRAM)
+  int order[PNCE_MAX_LAYERS];
+  for (int l = 0; l < p.n_layers; ++l) order[l] = l;
+  if (!g_gather_in_layer_order)
+    for (int i = 1; i < p.n_layers; ++i)
+      for (int j = i; j > 0 && p.L[order[j]].C <= p.L[order[j - 1]].C; --j) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
   long long acc = 0;
-  for (int l = 0; l < p.n_layers; ++l) {
-    m.start[l] = acc;
-    acc += 2ll * p.bn * ((p.L[l].Ppad + 255) / 256) * p.L[l].nchunk;
+  for (int s = 0; s < p.n_layers; ++s) {
+    m.start[s] = acc;
+    m.layer[s] = order[s];
+    acc += 2ll * p.bn * ((p.L[order[s]].Ppad + 255) / 256) * p.L[order[s]].nchunk;
   }
   m.start[p.n_layers] = acc;
   if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
@@ -437,6 +447,7 @@ int pnce_debug_set(int key, long long value) {
     case 5: g_dbg.fwd_chunks = (int)value; break;
     case 6: g_dbg.no_persist = (int)value; break;
     case 7: g_dbg.persist_ctas = (int)value; break;
+    case 8: g_gather_in_layer_order = (int)value; break;
     default: return PNCE_ERR_ARG;
   }
   return PNCE_OK;
