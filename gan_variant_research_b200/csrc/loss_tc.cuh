@@ -225,6 +225,17 @@ __device__ __forceinline__ void tc_q_unpack(const TcQChunk& qc, float (&q)[32]) 
   }
 }
 
+// dxT stores carry an L2 evict_last policy: the rows (50 MB at B=64) are then still in L2 when the dense
+// backward reads them, instead of having been pushed out by the blob traffic of the rest of this kernel --
+// reads that would interleave with the dense kernel's 7 TB/s write stream (measured: dense 464 -> 454 us,
+// step 896 -> 877 us; pnce_debug_set key 9 = 0 turns it off).  k_dense_flat reads them with ld.global.cs,
+// which hands the lines back to the replacement policy as soon as they are consumed.
+__device__ int g_dx_evict_last = 1;
+__device__ __forceinline__ void st_dx(float* p, float v, bool keep, uint64_t pol) {
+  if (keep) asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+  else *p = v;
+}
+
 // dQ epilogue for one 32-channel chunk; NPC = pitch of dxT rows (compile-time: immediates; 0 = run time).
 // Head mode (dyh != NULL): the gradient w.r.t. the head output leaves as a bf16 hi(+lo) row blob
 // (the A operand of the head's backward GEMMs) instead of fp32 rows; padding rows are written as 0.
@@ -253,13 +264,16 @@ __device__ __forceinline__ void tc_dq_chunk(const uint32_t (&r)[32], const TcQCh
     return;
   }
   if (rowok) {
+    const bool keep = g_dx_evict_last != 0;
+    uint64_t pol = 0;
+    if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     if (nvalid >= 32) {
 #pragma unroll
-      for (int k = 0; k < 32; ++k) dp[k * NP] = out[k];
+      for (int k = 0; k < 32; ++k) st_dx(dp + k * NP, out[k], keep, pol);
     } else {
 #pragma unroll
       for (int k = 0; k < 32; ++k)
-        if (k < nvalid) dp[k * NP] = out[k];
+        if (k < nvalid) st_dx(dp + k * NP, out[k], keep, pol);
     }
   }
 }

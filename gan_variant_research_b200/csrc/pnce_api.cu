@@ -387,7 +387,15 @@ static int launch_dense(const Params& p, cudaStream_t st) {
   f.flags = g_dbg.dense_flags;
   if (tot > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)tot;
-  if (vec) {
+  if (vec && (g_dbg.dense_flags & 2)) {                      // experiment: store-first variant
+    if (p.dtype == PNCE_F32) k_dense_direct<float, 128><<<grid, 128, 0, st>>>(p, f);
+    else if (p.dtype == PNCE_F16) k_dense_direct<__half, 128><<<grid, 128, 0, st>>>(p, f);
+    else k_dense_direct<__nv_bfloat16, 128><<<grid, 128, 0, st>>>(p, f);
+  } else if (vec && (g_dbg.dense_flags & 4)) {               // experiment: 64-thread CTAs (more tiles in flight per SM)
+    if (p.dtype == PNCE_F32) k_dense_flat<float, 64, true><<<grid, 64, 0, st>>>(p, f);
+    else if (p.dtype == PNCE_F16) k_dense_flat<__half, 64, true><<<grid, 64, 0, st>>>(p, f);
+    else k_dense_flat<__nv_bfloat16, 64, true><<<grid, 64, 0, st>>>(p, f);
+  } else if (vec) {
     if (p.dtype == PNCE_F32) k_dense_flat<float, 128, true><<<grid, 128, 0, st>>>(p, f);
     else if (p.dtype == PNCE_F16) k_dense_flat<__half, 128, true><<<grid, 128, 0, st>>>(p, f);
     else k_dense_flat<__nv_bfloat16, 128, true><<<grid, 128, 0, st>>>(p, f);
@@ -448,6 +456,7 @@ int pnce_debug_set(int key, long long value) {
     case 6: g_dbg.no_persist = (int)value; break;
     case 7: g_dbg.persist_ctas = (int)value; break;
     case 8: g_gather_in_layer_order = (int)value; break;
+    case 9: { int v = (int)value; PNCE_CUDA(cudaMemcpyToSymbol(g_dx_evict_last, &v, sizeof(int))); break; }
     default: return PNCE_ERR_ARG;
   }
   return PNCE_OK;
