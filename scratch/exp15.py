@@ -1,4 +1,4 @@
-"""A/B: dxT stores with an L2 evict_last policy (debug knob 9)."""
+"""A/B of an L2 policy knob: python exp15.py <knob> (9: dxT evict_last, 10: gather streaming loads)."""
 import sys, ctypes
 sys.path.insert(0, '.')
 import torch
@@ -14,9 +14,10 @@ crit = pn.PatchNCELoss(0.07, 256)
 def step():
     for t in tgt: t.grad = None
     loss = crit(src, tgt); loss.backward(); return loss
+KEY = int(sys.argv[1]) if len(sys.argv) > 1 else 9
 for rep in range(2):
   for knob in (0, 1):
-    lib.pnce_debug_set(9, knob)
+    lib.pnce_debug_set(KEY, knob)
     for _ in range(5): l = step()
     torch.cuda.synchronize()
     n = 100
@@ -29,5 +30,5 @@ for rep in range(2):
         for _ in range(5): step()
         torch.cuda.synchronize()
     rows = {e.key[:40]: e.device_time_total / 5 for e in prof.key_averages() if e.device_time_total > 0}
-    print(f'evict_last={knob}: step {ms*1e3:.1f} us; ' + '  '.join(f'{k.split("::")[-1][:12]}={v:.1f}' for k, v in rows.items() if 'pnce::k_' in k), f'loss {l.item():.6f}')
-lib.pnce_debug_set(9, 0)
+    print(f'knob{KEY}={knob}: step {ms*1e3:.1f} us; ' + '  '.join(f'{k.split("::")[-1][:12]}={v:.1f}' for k, v in rows.items() if 'pnce::k_' in k), f'loss {l.item():.6f}')
+lib.pnce_debug_set(KEY, 1 if KEY == 9 else 0)
