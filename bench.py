@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--head", action="store_true", help="time the netF-head mode (nc=256) as the workload")
     ap.add_argument("--no-head-line", action="store_true", help="skip the secondary head-mode measurement")
     ap.add_argument("--clock-period", type=float, default=0.02, help="seconds between NVML clock samples (0: no sampling)")
+    ap.add_argument("--settle", type=float, default=0.0, help="experiment: seconds to idle after the maps are created, before warm-up")
     return ap.parse_args()
 
 
@@ -293,6 +294,9 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local, period=args.clock_period or 1e9)
+    if args.settle > 0:
+        torch.cuda.synchronize()
+        time.sleep(args.settle)
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()

@@ -13,7 +13,7 @@ MAX_CHANNELS = 1024
 
 EXPORTS = [
     "pnce_abi_version", "pnce_status_string", "pnce_last_cuda_error", "pnce_workspace_bytes",
-    "pnce_fwd", "pnce_bwd", "pnce_sample_fwd", "pnce_sample_bwd_workspace_bytes",
+    "pnce_fwd", "pnce_bwd", "pnce_plan_bytes", "pnce_plan_ids", "pnce_fwd_planned", "pnce_bwd_planned", "pnce_sample_fwd", "pnce_sample_bwd_workspace_bytes",
     "pnce_sample_bwd", "pnce_rows_loss_workspace_bytes", "pnce_rows_loss_fwd_bwd", "pnce_selftest_umma",
     "pnce_head_workspace_bytes", "pnce_head_fwd", "pnce_head_bwd", "pnce_head_bwd_params", "pnce_head_bwd_dense",
 ]
@@ -57,6 +57,10 @@ def load():
     lib.pnce_workspace_bytes.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, ctypes.POINTER(sz)]
     lib.pnce_fwd.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, f32, i32, vp, sz, vp, vp, vp]
     lib.pnce_bwd.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, i32, vp, sz, vp, vp]
+    lib.pnce_plan_bytes.argtypes = [ctypes.POINTER(PnceLayer), i32, ctypes.POINTER(sz)]
+    lib.pnce_plan_ids.argtypes = [ctypes.POINTER(PnceLayer), i32, vp, sz, vp]
+    lib.pnce_fwd_planned.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, f32, i32, vp, sz, vp, sz, vp, vp, vp]
+    lib.pnce_bwd_planned.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, i32, vp, sz, vp, sz, vp, vp]
     lib.pnce_sample_fwd.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp]
     lib.pnce_sample_bwd_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, ctypes.POINTER(sz)]
     lib.pnce_sample_bwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, sz, vp, vp]

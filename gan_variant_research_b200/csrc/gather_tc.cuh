@@ -90,6 +90,12 @@ __device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long loca
 __global__ void __launch_bounds__(kThreads) k_gather_tc(const __grid_constant__ Params p,
                                                         const __grid_constant__ BlockMap m) {
   const long long blk = blockIdx.x;
+  if (blk == 0 && threadIdx.x == 0 && p.b0 == 0 && p.counter != nullptr) {
+    // launch-sequence state of the loss kernel that follows on this stream (k_prep does the same when it
+    // runs on this stream; with pnce_plan_ids it ran elsewhere, before the workspace existed)
+    *p.counter = 0u;
+    if (p.nonfinite != nullptr) p.nonfinite[1] = 0;
+  }
   const int slot = find_layer(m, blk, p.n_layers);
   const int l = m.layer[slot];                                 // launch_gather_tc orders light layers first
   const long long local = blk - m.start[slot];

@@ -66,8 +66,28 @@ static bool tc_shapes_ok(const pnce_layer_t* layers, int n_layers) {
 
 // Fills Params (pointers into the workspace) for the fused path; returns bytes used.
 // tc = carve the tensor-core operand blobs instead of the fp32 normalised rows.
+// The id bookkeeping of every layer (k_prep's outputs): sid, perm, rank, cslot.  It lives at the head of the
+// workspace, or -- pnce_plan_ids / pnce_fwd_planned -- in a buffer of its own, so that the id sort can run on
+// another stream before the workspace of the step even exists.  With base == nullptr only the size is computed.
+static size_t carve_plan(const pnce_layer_t* layers, int n_layers, void* base, Params* p) {
+  Carver cv(base);
+  for (int l = 0; l < n_layers; ++l) {
+    const pnce_layer_t& a = layers[l];
+    const int HW = a.H * a.W;
+    int* sid = cv.take<int>(a.P);
+    int* perm = cv.take<int>(a.P);
+    int* rank = cv.take<int>(a.P);
+    int* cslot = cv.take<int>((size_t)(HW + kTilePos - 1) / kTilePos + 1);
+    if (p != nullptr) {
+      LayerDev& L = p->L[l];
+      L.sid = sid; L.perm = perm; L.rank = rank; L.cslot = cslot;
+    }
+  }
+  return align_up(cv.off, 256);
+}
+
 static size_t carve_fused(const pnce_layer_t* layers, int n_layers, int B, bool tc, bool x3, void* ws,
-                          Params* out) {
+                          Params* out, void* plan = nullptr) {
   Carver cv(ws);
   Params p;
   memset(&p, 0, sizeof(p));
@@ -85,10 +105,12 @@ static size_t carve_fused(const pnce_layer_t* layers, int n_layers, int B, bool 
     L.nwords = (L.HW + 31) / 32;
     L.ntiles = (L.P + kRowTile - 1) / kRowTile;
     const size_t rows = (size_t)B * a.P * a.C;
-    L.sid = cv.take<int>(a.P);
-    L.perm = cv.take<int>(a.P);
-    L.rank = cv.take<int>(a.P);
-    L.cslot = cv.take<int>((size_t)(L.HW + kTilePos - 1) / kTilePos + 1);
+    if (plan == nullptr) {
+      L.sid = cv.take<int>(a.P);
+      L.perm = cv.take<int>(a.P);
+      L.rank = cv.take<int>(a.P);
+      L.cslot = cv.take<int>((size_t)(L.HW + kTilePos - 1) / kTilePos + 1);
+    }
     L.qinv = cv.take<float>((size_t)B * a.P);
     L.dxpitch = tc ? (a.P + 127) / 128 * 128 : a.P;
     L.dxT = cv.take<float>((size_t)B * a.C * L.dxpitch);
@@ -118,6 +140,7 @@ static size_t carve_fused(const pnce_layer_t* layers, int n_layers, int B, bool 
     }
     L.partial = cv.take<float>((size_t)B * (L.ntiles > 2 ? L.ntiles : 2));
   }
+  if (plan != nullptr) carve_plan(layers, n_layers, plan, &p);
   if (out) *out = p;
   return align_up(cv.off, 256);
 }
@@ -330,8 +353,9 @@ static int aux_streams(AuxStreams** out) {
   return PNCE_OK;
 }
 
-static int forward_tc(Params& p, cudaStream_t st) {
-  int rc = launch_prep(p, st);
+static int forward_tc(Params& p, cudaStream_t st, bool planned = false) {
+  int rc = PNCE_OK;
+  if (!planned) rc = launch_prep(p, st);      // planned: pnce_plan_ids has run k_prep already (gather CTA 0 resets the counter)
   if (rc != PNCE_OK) return rc;
   int ctas_per_image = 0;
   for (int l = 0; l < p.n_layers; ++l) ctas_per_image += p.L[l].Ppad / 128;
@@ -500,8 +524,9 @@ int pnce_workspace_bytes(const pnce_layer_t* layers, int n_layers, int batch, si
   return PNCE_OK;
 }
 
-int pnce_fwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, float temperature,
-             int math_mode, void* ws, size_t ws_bytes, float* loss_out, int* nonfinite, void* stream) {
+static int fwd_impl(const pnce_layer_t* layers, int n_layers, int batch, int dtype, float temperature,
+                    int math_mode, void* ws, size_t ws_bytes, void* plan, size_t plan_bytes, float* loss_out,
+                    int* nonfinite, void* stream) {
   int rc = check_layers(layers, n_layers, batch);
   if (rc != PNCE_OK) return rc;
   if (dtype < PNCE_F32 || dtype > PNCE_BF16 || loss_out == nullptr || !(temperature > 0.f)) return PNCE_ERR_ARG;
@@ -513,8 +538,13 @@ int pnce_fwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, flo
   // fp32 CUDA-core kernel -- both are device paths of this library, neither is a fallback off the GPU
   const bool tc = math_mode != PNCE_MATH_SIMT_F32 && tc_shapes_ok(layers, n_layers);
   const bool x3 = math_mode == PNCE_MATH_TC_BF16X3;
+  if (plan != nullptr) {
+    if (!tc) return PNCE_ERR_UNSUPPORTED;                      // planned ids: tensor-core path only
+    if ((reinterpret_cast<uintptr_t>(plan) & 255u) || carve_plan(layers, n_layers, nullptr, nullptr) > plan_bytes)
+      return PNCE_ERR_WORKSPACE;
+  }
   Params p;
-  if (carve_fused(layers, n_layers, batch, tc, x3, ws, &p) > ws_bytes) return PNCE_ERR_WORKSPACE;
+  if (carve_fused(layers, n_layers, batch, tc, x3, ws, &p, plan) > ws_bytes) return PNCE_ERR_WORKSPACE;
   p.dtype = dtype;
   p.math = tc ? math_mode : PNCE_MATH_SIMT_F32;
   p.tau = temperature;
@@ -523,14 +553,56 @@ int pnce_fwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, flo
   p.trace = g_dbg.trace;
   p.b0 = 0; p.bn = batch;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (tc) return forward_tc(p, st);
+  if (tc) return forward_tc(p, st, plan != nullptr);
   rc = launch_gather(p, n_layers, st);
   if (rc != PNCE_OK) return rc;
   return launch_loss_simt(p, st);
 }
 
-int pnce_bwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int math_mode, void* ws,
-             size_t ws_bytes, const float* grad_out, void* stream) {
+int pnce_fwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, float temperature,
+             int math_mode, void* ws, size_t ws_bytes, float* loss_out, int* nonfinite, void* stream) {
+  return fwd_impl(layers, n_layers, batch, dtype, temperature, math_mode, ws, ws_bytes, nullptr, 0, loss_out,
+                  nonfinite, stream);
+}
+
+int pnce_fwd_planned(const pnce_layer_t* layers, int n_layers, int batch, int dtype, float temperature,
+                     int math_mode, void* ws, size_t ws_bytes, void* plan, size_t plan_bytes, float* loss_out,
+                     int* nonfinite, void* stream) {
+  if (plan == nullptr) return PNCE_ERR_ARG;
+  return fwd_impl(layers, n_layers, batch, dtype, temperature, math_mode, ws, ws_bytes, plan, plan_bytes,
+                  loss_out, nonfinite, stream);
+}
+
+int pnce_plan_bytes(const pnce_layer_t* layers, int n_layers, size_t* bytes) {
+  if (bytes == nullptr) return PNCE_ERR_ARG;
+  int rc = check_layers(layers, n_layers, 1);
+  if (rc != PNCE_OK) return rc;
+  *bytes = carve_plan(layers, n_layers, nullptr, nullptr);
+  return PNCE_OK;
+}
+
+int pnce_plan_ids(const pnce_layer_t* layers, int n_layers, void* plan, size_t plan_bytes, void* stream) {
+  int rc = check_layers(layers, n_layers, 1);
+  if (rc != PNCE_OK) return rc;
+  if (plan == nullptr || (reinterpret_cast<uintptr_t>(plan) & 255u)) return PNCE_ERR_WORKSPACE;
+  if (carve_plan(layers, n_layers, nullptr, nullptr) > plan_bytes) return PNCE_ERR_WORKSPACE;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.n_layers = n_layers;
+  p.B = 1;
+  for (int l = 0; l < n_layers; ++l) {
+    const pnce_layer_t& a = layers[l];
+    if (a.ids == nullptr || (reinterpret_cast<uintptr_t>(a.ids) & 7u)) return PNCE_ERR_ARG;
+    LayerDev& L = p.L[l];
+    L.ids = reinterpret_cast<const long long*>(a.ids);
+    L.C = a.C; L.HW = a.H * a.W; L.P = a.P;
+  }
+  carve_plan(layers, n_layers, plan, &p);
+  return launch_prep(p, static_cast<cudaStream_t>(stream));    // counter == nullptr: nothing else is touched
+}
+
+static int bwd_impl(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int math_mode, void* ws,
+                    size_t ws_bytes, void* plan, size_t plan_bytes, const float* grad_out, void* stream) {
   int rc = check_layers(layers, n_layers, batch);
   if (rc != PNCE_OK) return rc;
   if (dtype < PNCE_F32 || dtype > PNCE_BF16) return PNCE_ERR_ARG;
@@ -539,12 +611,24 @@ int pnce_bwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int
   if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
   if (math_mode < PNCE_MATH_SIMT_F32 || math_mode > PNCE_MATH_TC_BF16) return PNCE_ERR_ARG;
   const bool tc = math_mode != PNCE_MATH_SIMT_F32 && tc_shapes_ok(layers, n_layers);
+  if (plan != nullptr && (!tc || carve_plan(layers, n_layers, nullptr, nullptr) > plan_bytes)) return PNCE_ERR_WORKSPACE;
   Params p;
-  if (carve_fused(layers, n_layers, batch, tc, math_mode == PNCE_MATH_TC_BF16X3, ws, &p) > ws_bytes)
+  if (carve_fused(layers, n_layers, batch, tc, math_mode == PNCE_MATH_TC_BF16X3, ws, &p, plan) > ws_bytes)
     return PNCE_ERR_WORKSPACE;
   p.dtype = dtype;
   p.grad_out = grad_out;
   return launch_dense(p, static_cast<cudaStream_t>(stream));
+}
+
+int pnce_bwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int math_mode, void* ws,
+             size_t ws_bytes, const float* grad_out, void* stream) {
+  return bwd_impl(layers, n_layers, batch, dtype, math_mode, ws, ws_bytes, nullptr, 0, grad_out, stream);
+}
+
+int pnce_bwd_planned(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int math_mode, void* ws,
+                     size_t ws_bytes, void* plan, size_t plan_bytes, const float* grad_out, void* stream) {
+  if (plan == nullptr) return PNCE_ERR_ARG;
+  return bwd_impl(layers, n_layers, batch, dtype, math_mode, ws, ws_bytes, plan, plan_bytes, grad_out, stream);
 }
 
 // ---- module-split API ------------------------------------------------------------------------

@@ -81,14 +81,15 @@ _ID_STREAMS = {}         # device index -> side stream the id draws are issued o
 _SIDE_STREAM_MIN_BYTES = 1 << 30
 
 
-def draw_patch_ids_all(feats, num_patches: int) -> List[torch.Tensor]:
+def draw_patch_ids_all(feats, num_patches: int, want_plan: bool = False) -> List[torch.Tensor]:
     """One ``draw_patch_ids`` per layer, in layer order (patchnce_cut.py:36-38, :63) -- issued on a
     side stream.  The draws read nothing but the generator state, which torch advances on the HOST at
     launch time, so the ids and the RNG stream are exactly what the reference gets; on a side stream
     the five tiny Philox kernels run under whatever the caller's stream is still busy with (the
     previous backward, the generator's forward) instead of sitting at the head of this step's
     critical path (measured: 18 us of a 0.92 ms step at B=64).  While a CUDA graph is being captured
-    the draws stay on the capturing stream."""
+    the draws stay on the capturing stream.  ``want_plan``: the id sort (k_prep, 8 us + two launch gaps)
+    goes to the side stream as well; ``fused_patchnce`` picks the result up."""
     if len(feats) == 0:
         return []
     dev = feats[0].device
@@ -100,13 +101,59 @@ def draw_patch_ids_all(feats, num_patches: int) -> List[torch.Tensor]:
     main = torch.cuda.current_stream(dev)
     side = _ID_STREAMS.get(dev.index)
     if side is None:
-        side = _ID_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+        # high priority: its few small CTAs take the first slots that free up under a kernel that fills the GPU
+        # (at equal priority they wait until that kernel's whole grid has been dispatched)
+        side = _ID_STREAMS[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
     with torch.cuda.stream(side):
         ids = [draw_patch_ids(f, num_patches) for f in feats]
+        plan = _plan_ids_on_current_stream(feats, ids) if want_plan else None
     main.wait_stream(side)
     for i in ids:
         i.record_stream(main)        # allocated on the side stream's pool, consumed on the caller's
+    if plan is not None:
+        plan.record_stream(main)
+        _PLANS[id(ids[0])] = (ids[0], plan)      # handed to fused_patchnce through the first id tensor
     return ids
+
+
+_PLANS = {}             # id(first id tensor) -> (that tensor, plan buffer) of the most recent side-stream draw
+_PLAN_BYTES = {}        # layer geometry -> pnce_plan_bytes
+
+
+def _plan_ids_on_current_stream(feats, ids) -> Optional[torch.Tensor]:
+    """k_prep (sorted ids, ranks, per-tile slot ranges of every layer) into a buffer of its own, on the
+    current -- side -- stream: like the draws it depends on nothing but the ids (include/pnce.h,
+    pnce_plan_ids).  None when the shapes are outside the tensor-core kernels' envelope."""
+    if len(feats) > _lib.MAX_LAYERS or any(f.dim() != 4 or f.shape[1] > 256 or i.numel() > 1024
+                                           for f, i in zip(feats, ids)):
+        return None
+    lib = _lib.load()
+    n = len(feats)
+    arr = (_lib.PnceLayer * n)()
+    for l, (f, i) in enumerate(zip(feats, ids)):
+        arr[l].ids = i.data_ptr()
+        arr[l].C, arr[l].H, arr[l].W, arr[l].P = f.shape[1], f.shape[2], f.shape[3], i.numel()
+    key = tuple((f.shape[1], f.shape[2], f.shape[3], i.numel()) for f, i in zip(feats, ids))
+    nbytes = _PLAN_BYTES.get(key)
+    if nbytes is None:
+        sz = ctypes.c_size_t(0)
+        _lib.check(lib.pnce_plan_bytes(arr, n, ctypes.byref(sz)), "pnce_plan_bytes")
+        nbytes = _PLAN_BYTES[key] = sz.value
+    dev = feats[0].device
+    plan = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.pnce_plan_ids(arr, n, plan.data_ptr(), nbytes, _stream_ptr(dev)), "pnce_plan_ids")
+    return plan
+
+
+def _take_plan(ids_list) -> Optional[torch.Tensor]:
+    """The plan buffer that belongs to exactly these id tensors, if the side-stream draw made one."""
+    if not ids_list:
+        return None
+    hit = _PLANS.pop(id(ids_list[0]), None)
+    _PLANS.clear()                                   # at most one draw is ever pending
+    if hit is None or hit[0] is not ids_list[0]:
+        return None
+    return hit[1]
 
 
 class _PinnedAlias:
@@ -226,6 +273,7 @@ class _Plan:
         self.temperature = float(temperature)
         self.math = math
         self.dp_group = dp_group      # head mode: process group whose ranks average the head gradients
+        self.idplan = None            # k_prep's outputs when the id sort already ran on the side stream
 
 
 _WS_BYTES = {}      # (batch, layer shapes) -> pnce_workspace_bytes, queried once per problem shape
@@ -265,9 +313,15 @@ class _FusedPatchNCE(torch.autograd.Function):
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             out = torch.empty(1 + n, dtype=torch.float32, device=dev)
             slot, flag_ptr = _warnings.acquire(dev)           # both words are written by the kernels
-            _lib.check(lib.pnce_fwd(layers, n, batch, dtype, plan.temperature, _MATH[plan.math],
-                                    ws.data_ptr(), ws_bytes, out.data_ptr(), flag_ptr or None,
-                                    _stream_ptr(dev)), "pnce_fwd")
+            if plan.idplan is None:
+                _lib.check(lib.pnce_fwd(layers, n, batch, dtype, plan.temperature, _MATH[plan.math],
+                                        ws.data_ptr(), ws_bytes, out.data_ptr(), flag_ptr or None,
+                                        _stream_ptr(dev)), "pnce_fwd")
+            else:
+                _lib.check(lib.pnce_fwd_planned(layers, n, batch, dtype, plan.temperature, _MATH[plan.math],
+                                                ws.data_ptr(), ws_bytes, plan.idplan.data_ptr(),
+                                                plan.idplan.numel(), out.data_ptr(), flag_ptr or None,
+                                                _stream_ptr(dev)), "pnce_fwd_planned")
             _warnings.commit(slot, dev)
         ctx.plan, ctx.ws, ctx.ws_bytes = plan, ws, ws_bytes
         ctx.layers = layers              # the backward only fills in the dtgt pointers
@@ -287,9 +341,15 @@ class _FusedPatchNCE(torch.autograd.Function):
             layers = ctx.layers
             for l, gl in enumerate(grads):
                 layers[l].dtgt = gl.data_ptr()
-            _lib.check(lib.pnce_bwd(layers, len(grads), ctx.batch, ctx.dtype, _MATH[ctx.plan.math],
-                                    ctx.ws.data_ptr(), ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev)),
-                       "pnce_bwd")
+            if ctx.plan.idplan is None:
+                _lib.check(lib.pnce_bwd(layers, len(grads), ctx.batch, ctx.dtype, _MATH[ctx.plan.math],
+                                        ctx.ws.data_ptr(), ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev)),
+                           "pnce_bwd")
+            else:
+                _lib.check(lib.pnce_bwd_planned(layers, len(grads), ctx.batch, ctx.dtype, _MATH[ctx.plan.math],
+                                                ctx.ws.data_ptr(), ctx.ws_bytes, ctx.plan.idplan.data_ptr(),
+                                                ctx.plan.idplan.numel(), g.data_ptr(), _stream_ptr(dev)),
+                           "pnce_bwd_planned")
         return (None, *grads)
 
 
@@ -334,6 +394,9 @@ def fused_patchnce(src_feats, tgt_feats, ids_list, temperature=0.07, math: Optio
         if ids[-1].numel() > _lib.MAX_PATCHES:
             raise RuntimeError(f"num_patches > {_lib.MAX_PATCHES} is not supported")
     plan = _Plan(src, ids, temperature, math or DEFAULT_MATH)
+    idplan = _take_plan(ids_list)
+    if idplan is not None and all(a is b for a, b in zip(ids, ids_list)) and plan.math != "simt_f32":
+        plan.idplan = idplan
     loss = _FusedPatchNCE.apply(plan, *tgt)
     n = len(tgt)
     denom = n_src if denom_layers is None else denom_layers
@@ -367,7 +430,8 @@ class PatchNCELoss(nn.Module):
         src_feats, tgt_feats = list(a), list(b)
         _warnings.poll()
         n = min(len(src_feats), len(tgt_feats))
-        ids = draw_patch_ids_all(src_feats[:n], self.num_patches)                      # :60-63
+        ids = draw_patch_ids_all(src_feats[:n], self.num_patches,                      # :60-63
+                                 want_plan=(self.math or DEFAULT_MATH) != "simt_f32")
         self.last_patch_ids = ids
         return fused_patchnce(src_feats, tgt_feats, ids, self.temperature, self.math)
 

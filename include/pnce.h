@@ -79,6 +79,21 @@ int pnce_fwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, flo
              int math_mode, void* dev_workspace, size_t workspace_bytes, float* dev_loss_out,
              int* dev_nonfinite, void* stream);
 
+/* The id bookkeeping (sorted ids, ranks, per-tile slot ranges) as a step of its own: pnce_plan_ids sorts the
+ * ids of every layer into a caller-owned buffer of pnce_plan_bytes bytes (only layers[l].ids, C, H, W, P are
+ * read); pnce_fwd_planned / pnce_bwd_planned then take it instead of sorting themselves.  The ids
+ * (patchnce_cut.py:63) depend on nothing but the generator state, so a caller can draw AND sort them on a
+ * side stream while the GPU is still busy with whatever precedes the loss -- 10 us less at the head of the
+ * step.  Tensor-core math modes only (PNCE_ERR_UNSUPPORTED otherwise).                               */
+int pnce_plan_bytes(const pnce_layer_t* layers, int n_layers, size_t* bytes);
+int pnce_plan_ids(const pnce_layer_t* layers, int n_layers, void* dev_plan, size_t plan_bytes, void* stream);
+int pnce_fwd_planned(const pnce_layer_t* layers, int n_layers, int batch, int dtype, float temperature,
+                     int math_mode, void* dev_workspace, size_t workspace_bytes, void* dev_plan,
+                     size_t plan_bytes, float* dev_loss_out, int* dev_nonfinite, void* stream);
+int pnce_bwd_planned(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int math_mode,
+                     void* dev_workspace, size_t workspace_bytes, void* dev_plan, size_t plan_bytes,
+                     const float* dev_grad_out, void* stream);
+
 /* Backward: writes every layers[l].dtgt densely (zero off the sampled positions, duplicate ids
  * accumulated) scaled by the upstream gradient *dev_grad_out (NULL = 1.0).  `math_mode` and the
  * workspace must be the ones given to the matching pnce_fwd.  Replaces the autograd

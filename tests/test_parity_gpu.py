@@ -543,3 +543,40 @@ def test_pinned_host_maps_zero_copy(pn, dtype):
         assert x.grad.is_cuda and torch.equal(x.grad, y.grad)
     with pytest.raises(RuntimeError):
         pn.pinned_as_device(torch.randn(4, 4))            # pageable memory is refused
+
+
+def test_side_stream_id_plan_gives_identical_results(pn, orc):
+    """Large problems draw AND sort the ids on a side stream (pnce_plan_ids / pnce_fwd_planned /
+    pnce_bwd_planned); forced here on a small ragged problem: bit-identical to the in-line path, and
+    right against the oracle."""
+    from gan_variant_research_b200 import patchnce as pmod
+    g = torch.Generator().manual_seed(17)
+    shapes = [(32, 24, 24), (64, 16, 16), (8, 3, 5), (128, 40, 40)]
+    src = [torch.randn(3, *s, generator=g).cuda() for s in shapes]
+    tgt_a = [torch.randn(3, *s, generator=g).cuda().requires_grad_() for s in shapes]
+    tgt_b = [t.detach().clone().requires_grad_() for t in tgt_a]
+    crit = pn.PatchNCELoss(0.07, 256)
+    torch.manual_seed(9)
+    la = crit(src, tgt_a)
+    la.backward()
+    ids_a = [i.clone() for i in crit.last_patch_ids]
+    keep = pmod._SIDE_STREAM_MIN_BYTES
+    pmod._SIDE_STREAM_MIN_BYTES = 0
+    try:
+        torch.manual_seed(9)
+        lb = crit(src, tgt_b)
+        assert pmod._PLANS == {}                       # the plan was picked up by the fused call
+        (lb * 2.0).backward()
+    finally:
+        pmod._SIDE_STREAM_MIN_BYTES = keep
+    assert all(torch.equal(a, b) for a, b in zip(ids_a, crit.last_patch_ids))
+    assert la.item() == lb.item()
+    for a, b in zip(tgt_a, tgt_b):
+        assert torch.equal(a.grad * 2.0, b.grad)
+    want, _, gw = orc.patchnce_loss_and_grads_np([x.cpu().numpy() for x in src],
+                                                 [x.detach().cpu().numpy() for x in tgt_a],
+                                                 [i.cpu().numpy() for i in ids_a], 0.07)
+    assert la.item() == pytest.approx(want, rel=2e-5)
+    for l in range(len(shapes)):
+        assert_grad_close(tgt_a[l].grad.cpu().numpy(), gw[l], 2e-4, f"layer {l}", ids=ids_a[l].cpu().numpy())
+    assert pn.poll_nonfinite_warnings(block=True) == 0
