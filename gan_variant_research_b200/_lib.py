@@ -14,7 +14,8 @@ MAX_CHANNELS = 1024
 EXPORTS = [
     "pnce_abi_version", "pnce_status_string", "pnce_last_cuda_error", "pnce_workspace_bytes",
     "pnce_fwd", "pnce_bwd", "pnce_plan_bytes", "pnce_plan_ids", "pnce_fwd_planned", "pnce_bwd_planned", "pnce_sample_fwd", "pnce_sample_bwd_workspace_bytes",
-    "pnce_sample_bwd", "pnce_rows_loss_workspace_bytes", "pnce_rows_loss_fwd_bwd", "pnce_selftest_umma",
+    "pnce_sample_bwd", "pnce_sample_multi_fwd", "pnce_sample_multi_bwd_workspace_bytes", "pnce_sample_multi_bwd",
+    "pnce_rows_loss_workspace_bytes", "pnce_rows_loss_fwd_bwd", "pnce_selftest_umma",
     "pnce_head_workspace_bytes", "pnce_head_fwd", "pnce_head_bwd", "pnce_head_bwd_params", "pnce_head_bwd_dense",
 ]
 
@@ -26,6 +27,13 @@ class PnceLayer(ctypes.Structure):
         ("ids", ctypes.c_void_p),
         ("C", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("P", ctypes.c_int32),
     ]
+
+
+class PnceSample(ctypes.Structure):
+    """struct pnce_sample (include/pnce.h)."""
+    _fields_ = [("feat", ctypes.c_void_p), ("ids", ctypes.c_void_p), ("rows", ctypes.c_void_p),
+                ("inv", ctypes.c_void_p), ("drows", ctypes.c_void_p), ("dfeat", ctypes.c_void_p),
+                ("C", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("P", ctypes.c_int32)]
 
 
 class PnceHead(ctypes.Structure):
@@ -64,6 +72,9 @@ def load():
     lib.pnce_sample_fwd.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp]
     lib.pnce_sample_bwd_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, ctypes.POINTER(sz)]
     lib.pnce_sample_bwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, sz, vp, vp]
+    lib.pnce_sample_multi_fwd.argtypes = [ctypes.POINTER(PnceSample), i32, i32, i32, vp]
+    lib.pnce_sample_multi_bwd_workspace_bytes.argtypes = [ctypes.POINTER(PnceSample), i32, i32, ctypes.POINTER(sz)]
+    lib.pnce_sample_multi_bwd.argtypes = [ctypes.POINTER(PnceSample), i32, i32, i32, vp, sz, vp]
     lib.pnce_rows_loss_workspace_bytes.argtypes = [i32, i32, i32, ctypes.POINTER(sz)]
     lib.pnce_rows_loss_fwd_bwd.argtypes = [vp, vp, i32, i32, i32, f32, i32, vp, sz, vp, vp, vp, vp, vp]
     lib.pnce_head_workspace_bytes.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, ctypes.POINTER(sz)]

@@ -86,12 +86,24 @@ __device__ void gather_tile(const LayerDev& L, int B, int side0, int raw, long l
   const T* col = feat + id;
   float ss = 0.f;
   int bad = 0;
-#pragma unroll 8
-  for (int c = warp; c < C; c += 8) {
-    float v = ok ? to_f32<T>(__ldcg(col + (size_t)c * HW)) : 0.f;   // L2-only: no 128 B L1 line fill
-    tile_s[lane * ldt + c] = v;
-    ss = fmaf(v, v, ss);
-    bad |= !isfinite(v);
+  // batches of 16 independent sector loads per lane before the first use (8 left the memory system idle:
+  // 590 us for the five CUT maps of both sides at B=64 against 310 us for the tensor-core gather)
+  for (int c0 = warp; c0 < C; c0 += 128) {
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int c = c0 + 8 * k;
+      v[k] = (ok && c < C) ? to_f32<T>(__ldcg(col + (size_t)c * HW)) : 0.f;   // L2-only: no 128 B L1 line fill
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int c = c0 + 8 * k;
+      if (c < C) {
+        tile_s[lane * ldt + c] = v[k];
+        ss = fmaf(v[k], v[k], ss);
+        bad |= !isfinite(v[k]);
+      }
+    }
   }
   red_s[warp * 32 + lane] = ss;
   red_s[256 + warp * 32 + lane] = __int_as_float(bad);

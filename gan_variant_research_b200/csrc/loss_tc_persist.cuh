@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
 #pragma unroll
         for (int s8 = 0; s8 < 8; ++s8) tss += ssq[s8];
         rownrm = sqrtf(tss);                                  // NaN: the gather saw a non-finite element
-        if (rowok && half == 0)
+        if (rowok && half == 0 && L.qinv != nullptr)
           L.qinv[(size_t)b * P + gi] = (rownrm == rownrm) ? (rownrm < kNormEps ? -1.0f / kNormEps : 1.0f / rownrm) : rownrm;
       }
       const bool badq = rowok && !(rownrm == rownrm);
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
       // ---- dQ epilogue: dq/tau -> normalise backward -> dxT (coalesced: lane <-> consecutive slot) ----
       //   dx = dq*sc - q_raw * (sc^2 s_i)       with dq = acc / tau;  g / eps when ||q|| < eps
       const float c1 = inv_tau * sc;
-      const float c2 = noproj ? 0.f : sc * sc * s_i;
+      const float c2 = (noproj || p.rows_mode) ? 0.f : sc * sc * s_i;   // rows API: rows are used as given, no projection
       float* __restrict__ dxrow = L.dxT + (size_t)b * C * Ppad + (rowok ? gi : 0);   // dxpitch == Ppad on this path
       __nv_bfloat16* dyh = L.dyhi ? L.dyhi + qoff : nullptr;   // head mode: d loss / d (head output) as a row blob
       __nv_bfloat16* dyl = (L.dyhi && L.dylo) ? L.dylo + qoff : nullptr;
@@ -475,7 +475,29 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
       mbar_wait(&sh->dqfull, par, dead);
       tc_fence_after();
       PNCE_TS(n, 4);
-      if (Ppad == 128) tp_dq_epilogue<128>(trow + 256u, half, nstage, C, qh, ql, dxrow, c1, c2, rowok, dyh, dyl, qa, qb);
+      if (p.rows_mode) {
+        // module-split rows API: d loss / d q row-major, rows in the caller's order (the raw q values are not needed)
+        float* __restrict__ drow = L.dq_rows + ((size_t)b * P + (rowok ? gi : 0)) * C;
+        for (int s = half; s < nstage; s += 2) {
+          uint32_t r[32];
+          tmem_ld32(trow + 256u + s * 32, r);
+          tmem_ld_wait();
+          if (rowok) {
+            const int nvalid = C - s * 32;
+            if (nvalid >= 32 && (C & 3) == 0) {
+#pragma unroll
+              for (int k4 = 0; k4 < 8; ++k4)
+                *reinterpret_cast<float4*>(drow + s * 32 + k4 * 4) =
+                    make_float4(__uint_as_float(r[k4 * 4]) * c1, __uint_as_float(r[k4 * 4 + 1]) * c1,
+                                __uint_as_float(r[k4 * 4 + 2]) * c1, __uint_as_float(r[k4 * 4 + 3]) * c1);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (k < nvalid) drow[s * 32 + k] = __uint_as_float(r[k]) * c1;
+            }
+          }
+        }
+      } else if (Ppad == 128) tp_dq_epilogue<128>(trow + 256u, half, nstage, C, qh, ql, dxrow, c1, c2, rowok, dyh, dyl, qa, qb);
       else tp_dq_epilogue<256>(trow + 256u, half, nstage, C, qh, ql, dxrow, c1, c2, rowok, dyh, dyl, qa, qb);
       tc_fence_before();
       PNCE_TS(n, 5);

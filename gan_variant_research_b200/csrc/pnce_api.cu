@@ -13,6 +13,7 @@
 #include "loss_simt.cuh"
 #include "loss_tc.cuh"
 #include "loss_tc_persist.cuh"
+#include "rows_pack.cuh"
 #include "sample_bwd.cuh"
 
 namespace pnce {
@@ -726,9 +727,112 @@ int pnce_sample_bwd(const float* drows, const float* rows, const float* inv, int
   const size_t smem = (size_t)kRowTile * (C + 1) * sizeof(float);
   rc = set_smem(k_rows_normbwd, smem);
   if (rc != PNCE_OK) return rc;
-  k_rows_normbwd<<<(unsigned)(batch * L.ntiles), kThreads, smem, st>>>(p, drows, rows);
+  k_rows_normbwd<<<(unsigned)(batch * L.ntiles), kThreads, smem, st>>>(p, drows, rows, 0);
   PNCE_CUDA(cudaGetLastError());
   return launch_dense(p, st);
+}
+
+// ---- all layers of a PatchSampleF call in one go -------------------------------------------------
+static int check_samples(const pnce_sample_t* sm, int n, int batch, int dtype) {
+  if (sm == nullptr || n < 1 || batch < 1 || dtype < PNCE_F32 || dtype > PNCE_BF16) return PNCE_ERR_ARG;
+  if (n > PNCE_MAX_LAYERS) return PNCE_ERR_UNSUPPORTED;
+  for (int l = 0; l < n; ++l) {
+    pnce_layer_t a;
+    memset(&a, 0, sizeof(a));
+    a.C = sm[l].C; a.H = sm[l].H; a.W = sm[l].W; a.P = sm[l].P;
+    int rc = check_layers(&a, 1, batch);
+    if (rc != PNCE_OK) return rc;
+    if (sm[l].ids == nullptr) return PNCE_ERR_ARG;
+  }
+  return PNCE_OK;
+}
+
+int pnce_sample_multi_fwd(const pnce_sample_t* sm, int n, int batch, int dtype, void* stream) {
+  int rc = check_samples(sm, n, batch, dtype);
+  if (rc != PNCE_OK) return rc;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.n_layers = n; p.B = batch; p.dtype = dtype;
+  p.side0 = 1;                       // only the "tgt" side exists here
+  p.raw = (sm[0].inv == nullptr) ? 1 : 0;
+  for (int l = 0; l < n; ++l) {
+    if (sm[l].feat == nullptr || sm[l].rows == nullptr) return PNCE_ERR_ARG;
+    if ((sm[l].inv == nullptr) != (p.raw != 0)) return PNCE_ERR_ARG;       // raw or normalised, for all layers alike
+    if (reinterpret_cast<uintptr_t>(sm[l].feat) & (dtype_size(dtype) - 1)) return PNCE_ERR_ALIGN;
+    LayerDev& L = p.L[l];
+    L.tgt = sm[l].feat;
+    L.ids = reinterpret_cast<const long long*>(sm[l].ids);
+    L.C = sm[l].C; L.HW = sm[l].H * sm[l].W; L.P = sm[l].P;
+    L.nwords = (L.HW + 31) / 32;
+    L.ntiles = (L.P + kRowTile - 1) / kRowTile;
+    L.qn = sm[l].rows;
+    L.qinv = sm[l].inv;
+  }
+  return launch_gather(p, 0, static_cast<cudaStream_t>(stream));
+}
+
+static size_t carve_sample_multi_bwd(const pnce_sample_t* sm, int n, int B, void* ws, Params* out) {
+  Carver cv(ws);
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.n_layers = n; p.B = B;
+  for (int l = 0; l < n; ++l) {
+    LayerDev& L = p.L[l];
+    L.C = sm[l].C; L.HW = sm[l].H * sm[l].W; L.P = sm[l].P;
+    L.nwords = (L.HW + 31) / 32;
+    L.ntiles = (L.P + kRowTile - 1) / kRowTile;
+    L.sid = cv.take<int>(L.P);
+    L.perm = cv.take<int>(L.P);
+    L.rank = cv.take<int>(L.P);
+    L.cslot = cv.take<int>((size_t)(L.HW + kTilePos - 1) / kTilePos + 1);
+    L.dxpitch = L.P;
+    L.dxT = cv.take<float>((size_t)B * L.P * L.C);
+  }
+  if (out) *out = p;
+  return align_up(cv.off, 256);
+}
+
+int pnce_sample_multi_bwd_workspace_bytes(const pnce_sample_t* sm, int n, int batch, size_t* bytes) {
+  if (bytes == nullptr) return PNCE_ERR_ARG;
+  int rc = check_samples(sm, n, batch, PNCE_F32);
+  if (rc != PNCE_OK) return rc;
+  *bytes = carve_sample_multi_bwd(sm, n, batch, nullptr, nullptr);
+  return PNCE_OK;
+}
+
+int pnce_sample_multi_bwd(const pnce_sample_t* sm, int n, int batch, int dtype, void* ws, size_t ws_bytes,
+                          void* stream) {
+  int rc = check_samples(sm, n, batch, dtype);
+  if (rc != PNCE_OK) return rc;
+  if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
+  Params p;
+  if (carve_sample_multi_bwd(sm, n, batch, ws, &p) > ws_bytes) return PNCE_ERR_WORKSPACE;
+  p.dtype = dtype;
+  p.raw = (sm[0].rows == nullptr) ? 1 : 0;
+  size_t smem = 0;
+  for (int l = 0; l < n; ++l) {
+    if (sm[l].drows == nullptr || sm[l].dfeat == nullptr) return PNCE_ERR_ARG;
+    if ((sm[l].rows == nullptr) != (sm[l].inv == nullptr) || (sm[l].rows == nullptr) != (p.raw != 0)) return PNCE_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(sm[l].dfeat) & (dtype_size(dtype) - 1)) return PNCE_ERR_ALIGN;
+    LayerDev& L = p.L[l];
+    L.ids = reinterpret_cast<const long long*>(sm[l].ids);
+    L.qinv = sm[l].inv;
+    L.dtgt = sm[l].dfeat;
+    const size_t s = (size_t)kRowTile * (L.C + 1) * sizeof(float);
+    if (s > smem) smem = s;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = launch_prep(p, st);                                    // one CTA per layer: sorted ids, ranks, tile slot ranges
+  if (rc != PNCE_OK) return rc;
+  rc = set_smem(k_rows_normbwd, smem);
+  if (rc != PNCE_OK) return rc;
+  for (int l = 0; l < n; ++l) {
+    const LayerDev& L = p.L[l];
+    k_rows_normbwd<<<(unsigned)(batch * L.ntiles), kThreads, (size_t)kRowTile * (L.C + 1) * sizeof(float), st>>>(
+        p, sm[l].drows, sm[l].rows, l);
+    PNCE_CUDA(cudaGetLastError());
+  }
+  return launch_dense(p, st);                                 // every layer's dense gradient in one launch
 }
 
 static size_t carve_rows_loss(int B, int P, int D, void* ws, Params* out) {
@@ -748,10 +852,50 @@ static size_t carve_rows_loss(int B, int P, int D, void* ws, Params* out) {
   return align_up(cv.off, 256);
 }
 
+// the same problem on the tensor-core kernel (P, D <= 256): operand blobs + per-chunk norm words
+static bool rows_tc_ok(int P, int D) { return P <= 256 && D <= 256; }
+static size_t carve_rows_loss_tc(int B, int P, int D, bool x3, void* ws, Params* out) {
+  Carver cv(ws);
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.n_layers = 1; p.B = B; p.rows_mode = 1;
+  p.counter = cv.take<unsigned>(64);
+  p.lossimg = cv.take<float>(B);
+  p.valid = cv.take<int>(B);
+  LayerDev& L = p.L[0];
+  L.C = D; L.P = P; L.HW = 1; L.nwords = 1;
+  L.ntiles = (P + kRowTile - 1) / kRowTile;
+  L.sorted = 1;
+  L.Cp = (D + 31) / 32 * 32;
+  L.Ppad = (P + 127) / 128 * 128;
+  L.nchunk = L.Cp / 32;
+  L.nparts = L.Ppad / 128;
+  L.dxpitch = L.Ppad;
+  const size_t blob = (size_t)B * L.Ppad * L.Cp;
+  L.qhi = cv.take<__nv_bfloat16>(blob);
+  L.khi = cv.take<__nv_bfloat16>(blob);
+  L.k2hi = cv.take<__nv_bfloat16>(blob);
+  if (x3) {
+    L.qlo = cv.take<__nv_bfloat16>(blob);
+    L.klo = cv.take<__nv_bfloat16>(blob);
+    L.k2lo = cv.take<__nv_bfloat16>(blob);
+  }
+  L.qss = cv.take<float>((size_t)B * L.nchunk * L.Ppad);
+  L.kss = cv.take<float>((size_t)B * L.nchunk * L.Ppad);
+  L.partial = cv.take<float>((size_t)B * 2);
+  if (out) *out = p;
+  return align_up(cv.off, 256);
+}
+
 int pnce_rows_loss_workspace_bytes(int batch, int P, int D, size_t* bytes) {
   if (bytes == nullptr || batch < 1 || P < 1 || D < 1) return PNCE_ERR_ARG;
   if (P > PNCE_MAX_PATCHES || D > PNCE_MAX_CHANNELS) return PNCE_ERR_UNSUPPORTED;
-  *bytes = carve_rows_loss(batch, P, D, nullptr, nullptr);
+  size_t need = carve_rows_loss(batch, P, D, nullptr, nullptr);
+  if (rows_tc_ok(P, D)) {
+    const size_t t = carve_rows_loss_tc(batch, P, D, true, nullptr, nullptr);
+    if (t > need) need = t;
+  }
+  *bytes = need;
   return PNCE_OK;
 }
 
@@ -762,9 +906,30 @@ int pnce_rows_loss_fwd_bwd(const float* q, const float* k, int batch, int P, int
   if (P > PNCE_MAX_PATCHES || D > PNCE_MAX_CHANNELS) return PNCE_ERR_UNSUPPORTED;
   if (dk_out != nullptr) return PNCE_ERR_UNSUPPORTED;   // feat_k is detached in the reference (:142)
   if (math_mode < PNCE_MATH_SIMT_F32 || math_mode > PNCE_MATH_TC_BF16) return PNCE_ERR_ARG;
-  // rows arrive normalised in fp32 (module-split API): evaluated by the fp32 CUDA-core kernel in every
-  // math mode (the tcgen05 kernels consume the operand blobs written by the fused gather)
   if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
+  cudaStream_t st0 = static_cast<cudaStream_t>(stream);
+  if (math_mode != PNCE_MATH_SIMT_F32 && rows_tc_ok(P, D)) {
+    // tensor-core modes: re-tile the rows into operand blobs (k_rows_pack), then the tcgen05 loss kernel in
+    // rows mode (rows used as given, d loss / d q written row-major).  P or D > 256: CUDA-core kernel below.
+    const bool x3 = math_mode == PNCE_MATH_TC_BF16X3;
+    Params t;
+    if (carve_rows_loss_tc(batch, P, D, x3, ws, &t) > ws_bytes) return PNCE_ERR_WORKSPACE;
+    t.math = math_mode;
+    t.tau = temperature;
+    t.loss_out = loss_out;
+    t.nonfinite = nonfinite;
+    t.b0 = 0; t.bn = batch;
+    LayerDev& T = t.L[0];
+    T.qn = const_cast<float*>(q);
+    T.kn = const_cast<float*>(k);
+    T.dq_rows = dq_out;
+    PNCE_CUDA(cudaMemsetAsync(t.counter, 0, sizeof(unsigned), st0));
+    const long long threads = 2ll * batch * T.Ppad * (T.Cp >> 3);
+    k_rows_pack<<<(unsigned)((threads + kThreads - 1) / kThreads), kThreads, 0, st0>>>(t);
+    PNCE_CUDA(cudaGetLastError());
+    return launch_loss_tc(t, st0);
+  }
+  // fp32 CUDA-core kernel on the rows as they are
   Params p;
   if (carve_rows_loss(batch, P, D, ws, &p) > ws_bytes) return PNCE_ERR_WORKSPACE;
   p.tau = temperature;

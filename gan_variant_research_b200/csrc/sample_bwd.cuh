@@ -8,9 +8,9 @@ namespace pnce {
 // grid = B * ntiles ; smem = 32*(C+1) floats
 __global__ void __launch_bounds__(kThreads) k_rows_normbwd(const __grid_constant__ Params p,
                                                            const float* __restrict__ drows,
-                                                           const float* __restrict__ rows) {
+                                                           const float* __restrict__ rows, int l) {
   extern __shared__ __align__(16) float st[];
-  const LayerDev& L = p.L[0];
+  const LayerDev& L = p.L[l];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x % L.ntiles, b = blockIdx.x / L.ntiles;
   const int P = L.P, C = L.C, ldt = C + 1;

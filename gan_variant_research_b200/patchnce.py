@@ -498,6 +498,73 @@ class _SampleFn(torch.autograd.Function):
         return dfeat, None, None
 
 
+class _SampleAllFn(torch.autograd.Function):
+    """``_SampleFn`` for every map of a ``PatchSampleF`` call at once: one gather launch forward, and in
+    the backward one id prep, a normalise-backward launch per map and ONE dense launch for all maps
+    (pnce_sample_multi_fwd / _bwd).  Inputs: raw flag, n, the n maps, the n id tensors."""
+
+    @staticmethod
+    def forward(ctx, raw, n, *args):
+        lib = _lib.load()
+        feats = [a.detach().contiguous() for a in args[:n]]
+        ids = list(args[n:2 * n])
+        dev = feats[0].device
+        b = feats[0].shape[0]
+        maps = (_lib.PnceSample * n)()
+        rows, invs = [], []
+        with _on_device(dev):
+            for l, (f, i) in enumerate(zip(feats, ids)):
+                _, c, h, w = f.shape
+                p = i.numel()
+                r = torch.empty(b * p, c, dtype=torch.float32, device=dev)
+                v = None if raw else torch.empty(b * p, dtype=torch.float32, device=dev)
+                rows.append(r)
+                invs.append(v)
+                maps[l].feat, maps[l].ids, maps[l].rows = f.data_ptr(), i.data_ptr(), r.data_ptr()
+                maps[l].inv = None if raw else v.data_ptr()
+                maps[l].C, maps[l].H, maps[l].W, maps[l].P = c, h, w, p
+            _lib.check(lib.pnce_sample_multi_fwd(maps, n, b, _DTYPES[feats[0].dtype], _stream_ptr(dev)),
+                       "pnce_sample_multi_fwd")
+        ctx.meta = (raw, n, b, dev, feats[0].dtype, [tuple(f.shape) for f in feats])
+        if raw:
+            ctx.save_for_backward(*ids)
+        else:
+            ctx.save_for_backward(*ids, *rows, *invs)
+        return tuple(rows)
+
+    @staticmethod
+    def backward(ctx, *drows):
+        lib = _lib.load()
+        raw, n, b, dev, dt, shapes = ctx.meta
+        saved = ctx.saved_tensors
+        ids = saved[:n]
+        rows_s = None if raw else saved[n:2 * n]
+        invs_s = None if raw else saved[2 * n:3 * n]
+        maps = (_lib.PnceSample * n)()
+        keep, dfeats = [], []
+        with _on_device(dev):
+            for l in range(n):
+                _, c, h, w = shapes[l]
+                p = ids[l].numel()
+                g = drows[l]
+                g = (torch.zeros(b * p, c, dtype=torch.float32, device=dev) if g is None
+                     else g.detach().to(torch.float32).contiguous())
+                d = torch.empty(shapes[l], dtype=dt, device=dev)
+                keep.append(g)
+                dfeats.append(d)
+                maps[l].ids, maps[l].drows, maps[l].dfeat = ids[l].data_ptr(), g.data_ptr(), d.data_ptr()
+                maps[l].rows = None if raw else rows_s[l].data_ptr()
+                maps[l].inv = None if raw else invs_s[l].data_ptr()
+                maps[l].C, maps[l].H, maps[l].W, maps[l].P = c, h, w, p
+            nbytes = ctypes.c_size_t(0)
+            _lib.check(lib.pnce_sample_multi_bwd_workspace_bytes(maps, n, b, ctypes.byref(nbytes)),
+                       "pnce_sample_multi_bwd_workspace_bytes")
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            _lib.check(lib.pnce_sample_multi_bwd(maps, n, b, _DTYPES[dt], ws.data_ptr(), nbytes.value,
+                                                 _stream_ptr(dev)), "pnce_sample_multi_bwd")
+        return (None, None, *dfeats, *([None] * n))
+
+
 class _RowsLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, batch, p, temperature, math):
@@ -577,23 +644,28 @@ class PatchSampleF(nn.Module):
         return_feats, return_ids = [], []
         if self.use_mlp and not self.mlp_init:
             self.create_mlp(feats)
-        for feat_id, feat in enumerate(feats):
+        feats = list(feats)
+        for feat in feats:
             _require_cuda(feat, "feat")
             if feat.dim() != 4:
                 raise ValueError("feature maps must be (B, C, H, W)")
-            if patch_ids is not None:
-                ids = patch_ids[feat_id].to(device=feat.device, dtype=torch.int64).contiguous()
-            else:
-                ids = draw_patch_ids(feat, num_patches)
+        if patch_ids is not None:
+            return_ids = [patch_ids[k].to(device=f.device, dtype=torch.int64).contiguous() for k, f in enumerate(feats)]
+        else:
+            return_ids = [draw_patch_ids(f, num_patches) for f in feats]
+        same = all(f.shape[0] == feats[0].shape[0] and f.dtype == feats[0].dtype and f.device == feats[0].device
+                   for f in feats)
+        if same and 0 < len(feats) <= _lib.MAX_LAYERS and feats[0].dtype in _DTYPES:
+            # every map in one gather launch (and one dense launch in the backward)
+            raw_rows = _SampleAllFn.apply(self.use_mlp, len(feats), *feats, *return_ids)
+        else:
+            raw_rows = [_SampleFn.apply(f, i, self.use_mlp) for f, i in zip(feats, return_ids)]
+        for feat_id, rows in enumerate(raw_rows):
             if self.use_mlp:
                 # gather (libpnce) -> Linear-ReLU-Linear -> x / max(||x||, 1e-6)
-                raw = _SampleFn.apply(feat, ids, True)
                 mlp = getattr(self, f"mlp_{feat_id}")
-                rows = torch.nn.functional.normalize(mlp(raw), dim=1, eps=NORM_EPS)
-            else:
-                rows = _SampleFn.apply(feat, ids, False)
+                rows = torch.nn.functional.normalize(mlp(rows), dim=1, eps=NORM_EPS)
             return_feats.append(rows)
-            return_ids.append(ids)
         return return_feats, return_ids
 
 

@@ -127,6 +127,23 @@ int pnce_rows_loss_fwd_bwd(const float* dev_q, const float* dev_k, int batch, in
                            size_t workspace_bytes, float* dev_loss_out, int* dev_nonfinite,
                            float* dev_dq_out, float* dev_dk_out, void* stream);
 
+/* All maps of one PatchSampleF call in ONE launch each way (the per-map entry points above cost a launch per
+ * layer and leave the GPU half empty on the small layers): forward reads feat / ids and writes rows (and inv,
+ * NULL for all layers = raw patches); backward reads drows / rows / inv / ids and writes dfeat densely.   */
+typedef struct pnce_sample {
+  const void*    feat;   /* (B,C,H,W), dtype of the call                        forward  */
+  const int64_t* ids;    /* (P) positions in [0, H*W)                           both     */
+  float*         rows;   /* (B*P, C) fp32: written by forward, read by backward (NULL there = raw) */
+  float*         inv;    /* (B*P) norm bookkeeping of the forward, or NULL (raw patches)           */
+  const float*   drows;  /* (B*P, C) incoming gradient                          backward */
+  void*          dfeat;  /* (B,C,H,W) dense gradient, dtype of the call         backward */
+  int32_t        C, H, W, P;
+} pnce_sample_t;
+int pnce_sample_multi_fwd(const pnce_sample_t* maps, int n_maps, int batch, int dtype, void* stream);
+int pnce_sample_multi_bwd_workspace_bytes(const pnce_sample_t* maps, int n_maps, int batch, size_t* bytes);
+int pnce_sample_multi_bwd(const pnce_sample_t* maps, int n_maps, int batch, int dtype, void* dev_workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* ---- netF head, fused (north-star pieces 3-5; absent from the reference: SURVEY.md 8 row a13) ---
  * PatchSampleF(use_mlp=True): raw gather -> Linear(C_l, nc) -> ReLU -> Linear(nc, nc) -> L2 normalise for the
  * src (k, no gradient) and tgt (q) patches of every layer, then the same logits / diagonal CE as
