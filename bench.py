@@ -348,6 +348,7 @@ def main():
             "reference-exact mode (no netF head)", "netF head mode (Linear-ReLU-Linear, nc=256, tcgen05)")
     elif rank == 0 and world == 1 and not args.no_head_line:
         out["head_mode"] = head_line(args, pn, src, tgt, math, patches_per_image)
+        out["module_split"] = module_split_line(args, pn, src, tgt, math, patches_per_image)
 
     # ---- e2e: same metric through the public API with HOST buffers ------------------------------
     if not args.no_e2e:
@@ -397,6 +398,37 @@ def head_line(args, pn, src, tgt, math, patches_per_image, steps=20):
     ms = e0.elapsed_time(e1) / steps
     return {"ms_per_step": ms, "value": args.batch * patches_per_image / (ms * 1e-3), "unit": UNIT, "nc": 256,
             "steps": steps, "note": "netF head Linear-ReLU-Linear on tcgen05, parity unpinned by the reference"}
+
+
+def module_split_line(args, pn, src, tgt, math, patches_per_image, steps=20):
+    """Secondary measurement: the same maps through the north-star module signatures, composed in Python the way
+    upstream CUT does -- feat_k, ids = PatchSampleF(src); feat_q, _ = PatchSampleF(tgt, ids); mean over layers of
+    PatchNCELoss(feat_q_l, feat_k_l) -- instead of the fused all-layer call."""
+    samp = pn.PatchSampleF(use_mlp=False)
+    crit = pn.PatchNCELoss(args.tau, args.patches, math=math)
+    batch = tgt[0].shape[0]
+
+    def step():
+        for t in tgt:
+            t.grad = None
+        with torch.no_grad():
+            feat_k, ids = samp(src, args.patches, None)
+        feat_q, _ = samp(tgt, args.patches, ids)
+        loss = sum(crit(q, k, batch_size=batch) for q, k in zip(feat_q, feat_k)) / len(feat_q)
+        loss.backward()
+
+    for _ in range(3):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "value": args.batch * patches_per_image / (ms * 1e-3), "unit": UNIT, "steps": steps,
+            "note": "PatchSampleF.forward(feats, num_patches, patch_ids) + per-layer PatchNCELoss(feat_q, feat_k)"}
 
 
 def run_e2e(args, pn, crit, layers, tdtype, elem, dev, world, rank):

@@ -573,10 +573,15 @@ class _RowsLossFn(torch.autograd.Function):
         kk = k.detach().to(torch.float32).contiguous()
         d = qq.shape[1]
         dev = qq.device
-        nbytes = ctypes.c_size_t(0)
-        _lib.check(lib.pnce_rows_loss_workspace_bytes(batch, p, d, ctypes.byref(nbytes)),
-                   "pnce_rows_loss_workspace_bytes")
-        with torch.cuda.device(dev):
+        key = ("rows", batch, p, d)
+        ws_bytes = _WS_BYTES.get(key)
+        if ws_bytes is None:
+            nbytes = ctypes.c_size_t(0)
+            _lib.check(lib.pnce_rows_loss_workspace_bytes(batch, p, d, ctypes.byref(nbytes)),
+                       "pnce_rows_loss_workspace_bytes")
+            ws_bytes = _WS_BYTES[key] = nbytes.value
+        nbytes = ctypes.c_size_t(ws_bytes)
+        with _on_device(dev):
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
             out = torch.empty(2, dtype=torch.float32, device=dev)
             slot, flag_ptr = _warnings.acquire(dev)
