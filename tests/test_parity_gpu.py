@@ -580,3 +580,40 @@ def test_side_stream_id_plan_gives_identical_results(pn, orc):
     for l in range(len(shapes)):
         assert_grad_close(tgt_a[l].grad.cpu().numpy(), gw[l], 2e-4, f"layer {l}", ids=ids_a[l].cpu().numpy())
     assert pn.poll_nonfinite_warnings(block=True) == 0
+
+
+@pytest.mark.parametrize("b,c,h,w,p", [(5, 200, 20, 20, 200), (1, 130, 16, 16, 129), (7, 64, 12, 12, 256),
+                                       (3, 255, 17, 15, 255), (2, 32, 128, 128, 160)])
+def test_odd_shapes_against_the_oracle(pn, orc, b, c, h, w, p):
+    """Channel counts that are not multiples of 32, patch counts that leave the second 128-row half of the
+    logits partly empty, maps whose rows are not 16-byte multiples: persistent tcgen05 kernel vs the oracle."""
+    g = torch.Generator().manual_seed(b * 1000 + c)
+    src = [torch.randn(b, c, h, w, generator=g)]
+    tgt = [torch.randn(b, c, h, w, generator=g)]
+    ids = [torch.randint(0, h * w, (min(p, h * w),), generator=g)]
+    t = [x.cuda().requires_grad_() for x in tgt]
+    loss = pn.fused_patchnce([x.cuda() for x in src], t, [i.cuda() for i in ids], 0.07)
+    (loss * 0.5).backward()
+    want, _, gw = orc.patchnce_loss_and_grads_np([x.numpy() for x in src], [x.numpy() for x in tgt],
+                                                 [i.numpy() for i in ids], 0.07, upstream=0.5)
+    assert loss.item() == pytest.approx(want, rel=2e-5)
+    assert_grad_close(t[0].grad.cpu().numpy(), gw[0], 2e-4, "odd shape", ids=ids[0].numpy())
+    assert pn.poll_nonfinite_warnings(block=True) == 0
+
+
+def test_eight_layers_is_the_limit(pn, orc):
+    g = torch.Generator().manual_seed(88)
+    shapes = [(8 + 8 * l, 6 + l, 5 + l) for l in range(8)]
+    src = [torch.randn(2, *s, generator=g) for s in shapes]
+    tgt = [torch.randn(2, *s, generator=g) for s in shapes]
+    ids = [torch.randint(0, s[1] * s[2], (min(64, s[1] * s[2]),), generator=g) for s in shapes]
+    t = [x.cuda().requires_grad_() for x in tgt]
+    loss = pn.fused_patchnce([x.cuda() for x in src], t, [i.cuda() for i in ids], 0.07)
+    loss.backward()
+    want, _, gw = orc.patchnce_loss_and_grads_np([x.numpy() for x in src], [x.numpy() for x in tgt],
+                                                 [i.numpy() for i in ids], 0.07)
+    assert loss.item() == pytest.approx(want, rel=2e-5)
+    for l in range(8):
+        assert_grad_close(t[l].grad.cpu().numpy(), gw[l], 2e-4, f"layer {l}", ids=ids[l].numpy())
+    with pytest.raises(RuntimeError):
+        pn.fused_patchnce([x.cuda() for x in src] * 2, [x.cuda() for x in tgt] * 2, [i.cuda() for i in ids] * 2, 0.07)
