@@ -101,3 +101,99 @@ def allreduce_head_grads(module: torch.nn.Module, group=None, average: bool = Tr
         g.copy_(flat[off:off + n].view_as(g))
         off += n
     return off
+
+
+class GradReducer:
+    """Data-parallel gradient averaging around the UNCHANGED reference training step (SURVEY.md section 8f row 1,
+    BASELINE config 5: "NCCL allreduce of netF/G/D grads"): attach it to the generator's and the
+    discriminator's parameters once, and every ``backward()`` of ``train_step`` (training/train_cutpp.py:253,
+    :261, :307 -- ``amp_ctx.scale_backward``) leaves ``.grad`` averaged over the ranks by the time it returns,
+    i.e. before ``amp_ctx.step_optimizer`` unscales, clips and steps (utils/amp_utils.py:29-41).  Nothing
+    in ``train_cutpp.py`` changes; ranks feed different shards of the batch (``shard_batch``).
+
+    Mechanics (what DDP's reducer does, kept small): parameters are grouped into flat fp32 buckets of
+    ``bucket_bytes`` in reverse registration order (gradients arrive roughly back to front); a
+    post-accumulate-grad hook copies each gradient into its bucket slot; a full bucket is all-reduced
+    (mean) on a side stream while the backward pass keeps running; an end-of-backward callback launches the
+    buckets that only filled partially (a pass that touches a subset of the parameters, e.g. the D step),
+    joins the side stream and copies the averaged values back into ``.grad``.  Scaled (GradScaler)
+    gradients average like any others; an inf on one rank becomes an inf on all, so every rank skips the
+    same steps."""
+
+    def __init__(self, params, group=None, bucket_bytes: int = 32 << 20, average: bool = True):
+        self.group = group
+        self.average = average
+        self.params = [p for p in params if p.requires_grad]
+        self.world = _world(group)
+        self.buckets = []            # each: dict(flat, slots=[(param, offset, numel)], ready=set(), launched=bool)
+        self.where = {}              # id(param) -> (bucket index, slot index)
+        cur, cur_elems = [], 0
+        for p in reversed(self.params):
+            if cur and (cur_elems + p.numel()) * 4 > bucket_bytes:
+                self._close_bucket(cur)
+                cur, cur_elems = [], 0
+            cur.append(p)
+            cur_elems += p.numel()
+        if cur:
+            self._close_bucket(cur)
+        self._callback_queued = False
+        self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+
+    def _close_bucket(self, plist):
+        dev = plist[0].device
+        total = sum(p.numel() for p in plist)
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        slots, off = [], 0
+        for k, p in enumerate(plist):
+            slots.append((p, off, p.numel()))
+            self.where[id(p)] = (len(self.buckets), k)
+            off += p.numel()
+        self.buckets.append({"flat": flat, "slots": slots, "ready": set(), "launched": False})
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+    # ---- hooks -------------------------------------------------------------------------------
+    def _on_grad(self, p):
+        if self.world == 1:
+            return
+        bi, si = self.where[id(p)]
+        b = self.buckets[bi]
+        _, off, n = b["slots"][si]
+        b["flat"][off:off + n].copy_(p.grad.detach().reshape(-1))
+        b["ready"].add(si)
+        if not self._callback_queued:
+            self._callback_queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(self._finalize)
+        if len(b["ready"]) == len(b["slots"]):
+            self._launch(b)
+
+    def _launch(self, b):
+        flat = b["flat"]
+        b["launched"] = True
+        if flat.is_cuda:
+            main = torch.cuda.current_stream(flat.device)
+            side = comm_stream(flat.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                allreduce_flat_(flat, self.group, self.average)
+        else:
+            allreduce_flat_(flat, self.group, self.average)
+
+    def _finalize(self):
+        self._callback_queued = False
+        touched = [b for b in self.buckets if b["ready"]]
+        for b in touched:                      # same set on every rank: same autograd graph everywhere
+            if not b["launched"]:
+                self._launch(b)
+        for b in touched:
+            flat = b["flat"]
+            if flat.is_cuda:
+                torch.cuda.current_stream(flat.device).wait_stream(comm_stream(flat.device))
+            for si in b["ready"]:
+                p, off, n = b["slots"][si]
+                p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            b["ready"] = set()
+            b["launched"] = False

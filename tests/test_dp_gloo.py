@@ -110,3 +110,77 @@ def test_single_process_helpers_are_no_ops():
     assert dp.resolve_group(True) is None            # no process group: nothing to reduce over
     flat = torch.ones(3)
     assert dp.allreduce_flat_(flat) is flat and torch.equal(flat, torch.ones(3))
+
+
+def _reducer_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from gan_variant_research_b200 import dp
+        torch.manual_seed(0)                                   # same weights on both ranks
+        g_net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16),
+                                    torch.nn.ReLU(), torch.nn.Linear(16, 3))
+        d_net = torch.nn.Sequential(torch.nn.Linear(3, 8), torch.nn.ReLU(), torch.nn.Linear(8, 1))
+        params = list(g_net.parameters()) + list(d_net.parameters())
+        red = dp.GradReducer(params, bucket_bytes=600)         # tiny buckets: several of them, some partial
+        assert len(red.buckets) >= 3
+        data = torch.Generator().manual_seed(5)
+        x_all = torch.randn(8, 6, generator=data)
+        x = dp.shard_batch([x_all])[0]
+        out = {}
+        # "D step": only d_net gets gradients (its input is detached) -> a subset of the buckets fills
+        d_loss = d_net(g_net(x).detach()).mean()
+        d_loss.backward()
+        out["d_step"] = [None if p.grad is None else p.grad.clone() for p in params]
+        for p in params:
+            p.grad = None
+        # "G step": gradients flow through both nets; a GradScaler-like factor rides along
+        g_loss = (d_net(g_net(x)).mean() + g_net(x).pow(2).mean()) * 1024.0
+        g_loss.backward()
+        out["g_step"] = [p.grad.clone() for p in params]
+        # second backward into existing grads (accumulation) stays consistent
+        (g_net(x).sum() * 0.5).backward()
+        out["accum"] = [p.grad.clone() for p in g_net.parameters()]
+        red.remove()
+        torch.save(out, os.path.join(out_dir, f"red{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_reducer_matches_full_batch(tmp_path):
+    """GradReducer on two gloo ranks: after every backward() the gradients equal the full-batch ones
+    (mean losses over equal shards), including a pass that touches only part of the parameters."""
+    world = 2
+    mp.spawn(_reducer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    torch.manual_seed(0)
+    g_net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16),
+                                torch.nn.ReLU(), torch.nn.Linear(16, 3))
+    d_net = torch.nn.Sequential(torch.nn.Linear(3, 8), torch.nn.ReLU(), torch.nn.Linear(8, 1))
+    params = list(g_net.parameters()) + list(d_net.parameters())
+    x = torch.randn(8, 6, generator=torch.Generator().manual_seed(5))
+    r = [torch.load(os.path.join(tmp_path, f"red{k}.pt")) for k in range(world)]
+    d_net(g_net(x).detach()).mean().backward()
+    for k in range(world):
+        for got, p in zip(r[k]["d_step"], params):
+            if p.grad is None:
+                assert got is None
+            else:
+                torch.testing.assert_close(got, p.grad, rtol=1e-5, atol=1e-7)
+    for p in params:
+        p.grad = None
+    ((d_net(g_net(x)).mean() + g_net(x).pow(2).mean()) * 1024.0).backward()
+    for k in range(world):
+        for got, p in zip(r[k]["g_step"], params):
+            torch.testing.assert_close(got, p.grad, rtol=1e-5, atol=1e-5)
+    # the accumulation pass: sum over the local shard, averaged over ranks = half the full-batch sum,
+    # added to the (already averaged) gradients of the previous pass
+    want = [p.grad.clone() for p in g_net.parameters()]
+    for p in params:
+        p.grad = None
+    (g_net(x).sum() * 0.5).backward()
+    for k in range(world):
+        for got, w, p in zip(r[k]["accum"], want, g_net.parameters()):
+            torch.testing.assert_close(got, (w + p.grad / world) / 1.0, rtol=1e-4, atol=1e-4)

@@ -79,3 +79,51 @@ def test_two_gpu_head_gradients_are_averaged_under_the_dense_kernel(tmp_path):
         got = torch.cat([r[k]["dtgt"][l] for k in range(world)]) / world
         scale = max(full_dtgt[l].abs().max().item(), 1e-30)
         assert (got - full_dtgt[l]).abs().max().item() / scale < 5e-4
+
+
+def _reducer_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from gan_variant_research_b200 import dp
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 3, padding=1), torch.nn.ReLU(),
+                                  torch.nn.Conv2d(16, 16, 3, padding=1), torch.nn.ReLU(),
+                                  torch.nn.Conv2d(16, 3, 3, padding=1)).to(dev)
+        red = dp.GradReducer(net.parameters(), bucket_bytes=4096)
+        x = torch.randn(4, 3, 16, 16, generator=torch.Generator().manual_seed(3))
+        xs = dp.shard_batch([x])[0].to(dev)
+        with torch.amp.autocast("cuda"):
+            loss = net(xs).float().pow(2).mean()
+        (loss * 256.0).backward()
+        torch.cuda.synchronize(dev)
+        torch.save([p.grad.cpu() for p in net.parameters()], os.path.join(out_dir, f"g{rank}.pt"))
+        red.remove()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_grad_reducer_matches_full_batch(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world = 2
+    mp.spawn(_reducer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    torch.manual_seed(0)
+    dev = torch.device("cuda", 0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 3, padding=1), torch.nn.ReLU(),
+                              torch.nn.Conv2d(16, 16, 3, padding=1), torch.nn.ReLU(),
+                              torch.nn.Conv2d(16, 3, 3, padding=1)).to(dev)
+    x = torch.randn(4, 3, 16, 16, generator=torch.Generator().manual_seed(3)).to(dev)
+    with torch.amp.autocast("cuda"):
+        loss = net(x).float().pow(2).mean()
+    (loss * 256.0).backward()
+    for k in range(world):
+        got = torch.load(os.path.join(tmp_path, f"g{k}.pt"))
+        for g, p in zip(got, net.parameters()):
+            scale = max(p.grad.abs().max().item(), 1e-30)
+            assert (g - p.grad.cpu()).abs().max().item() / scale < 5e-3      # fp16 autocast convolutions
