@@ -14,6 +14,7 @@
 #include "loss_tc.cuh"
 #include "loss_tc_persist.cuh"
 #include "rows_pack.cuh"
+#include "multi_tensor.cuh"
 #include "sample_bwd.cuh"
 
 namespace pnce {
@@ -1304,6 +1305,19 @@ int pnce_head_bwd_dense(const pnce_layer_t* layers, const pnce_head_t* heads, in
                         int nc, int math_mode, void* ws, size_t ws_bytes, const float* grad_out, void* stream) {
   return head_bwd_phases(2, layers, heads, n_layers, batch, dtype, nc, math_mode, ws, ws_bytes, grad_out, stream);
 }
+
+int pnce_multi_axpby(float* const* dev_dst, const float* const* dev_src, const long long* dev_numel,
+                     const int* dev_chunk_tensor, const long long* dev_chunk_start, int n_chunks, float a, float b,
+                     int mode, void* stream) {
+  if (!dev_dst || !dev_src || !dev_numel || !dev_chunk_tensor || !dev_chunk_start || n_chunks < 0) return PNCE_ERR_ARG;
+  if (mode != 0 && mode != 1) return PNCE_ERR_ARG;
+  if (n_chunks == 0) return PNCE_OK;
+  k_multi_axpby<<<(unsigned)n_chunks, kMtThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      dev_dst, dev_src, dev_numel, dev_chunk_tensor, dev_chunk_start, a, b, mode);
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+int pnce_multi_chunk_elems(void) { return kMtChunk; }
 
 int pnce_selftest_umma(const void* a_blob, size_t a_bytes, const void* b_blob, size_t b_bytes,
                        unsigned a_lbo, unsigned a_sbo, unsigned a_kstep, unsigned b_lbo, unsigned b_sbo,

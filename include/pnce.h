@@ -179,6 +179,18 @@ int pnce_head_bwd_dense(const pnce_layer_t* layers, const pnce_head_t* heads, in
                         int nc, int math_mode, void* dev_workspace, size_t workspace_bytes,
                         const float* dev_grad_out, void* stream);
 
+/* ---- "next" row 3: optimiser-side multi-tensor ops ------------------------------------
+ * One launch over a list of fp32 tensors described by device-resident tables (built once by the caller: parameter
+ * storage does not move during training): chunk c covers elements [chunk_start[c], chunk_start[c] +
+ * pnce_multi_chunk_elems()) of tensor chunk_tensor[c].
+ *   mode 0: dst = a * src + b * dst, both products and the sum rounded separately -- EMA.update(), utils/io_ckpt.py:23-29,
+ *           with a = 1 - decay, b = decay, dst = shadow, src = param (bit-identical to the reference's expression);
+ *   mode 1: dst = src                                   -- EMA.apply_shadow() / restore(), :31-43                 */
+int pnce_multi_chunk_elems(void);
+int pnce_multi_axpby(float* const* dev_dst, const float* const* dev_src, const long long* dev_numel,
+                     const int* dev_chunk_tensor, const long long* dev_chunk_start, int n_chunks, float a, float b,
+                     int mode, void* stream);
+
 /* Library self-test of the tcgen05 building blocks (bulk copy -> smem, tcgen05.mma with a K-major
  * or MN-major B operand, commit, tcgen05.ld): D(128 x n) = A(128 x k) * B on pre-tiled bf16 operand
  * blobs with host-supplied descriptor strides.  *dev_err is set to 1 on a protocol timeout.       */
