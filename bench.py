@@ -343,6 +343,8 @@ def main():
         "roofline": roof, "roofline_path": roof_path, "clocks": clocks,
         "gpu_launches": (10 if args.head else 4) * args.steps, "loss": float(loss.item()),
     }
+    if rank == 0:
+        out["kernels_us"] = kernel_breakdown(step)
     if args.head:
         out["config"]["workload"] = out["config"]["workload"].replace(
             "reference-exact mode (no netF head)", "netF head mode (Linear-ReLU-Linear, nc=256, tcgen05)")
@@ -359,6 +361,26 @@ def main():
         print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def kernel_breakdown(step, n=5):
+    """Mean duration (us) of every kernel of one step, from the torch profiler over n extra steps AFTER the
+    timed region (never inside it): says which launch moved when ms_per_step moves."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(n):
+                step()
+            torch.cuda.synchronize()
+        rows = {}
+        for e in prof.key_averages():
+            if e.device_time_total > 0:
+                name = e.key.split("(")[0].replace("void ", "").replace("pnce::", "").split("<")[0]
+                rows[name[:40]] = round(rows.get(name[:40], 0.0) + e.device_time_total / n, 1)
+        return dict(sorted(rows.items(), key=lambda kv: -kv[1])[:8])
+    except Exception as e:                                     # noqa: BLE001
+        return {"unavailable": repr(e)}
 
 
 def ncu_traffic(kernel, batch, elem):
