@@ -10,6 +10,7 @@ d tgt_feat of every layer, for one batch of synthetic feature maps (SURVEY.md se
 generator passes are not part of the metric.  Prints ONE JSON line on rank 0.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -94,6 +95,8 @@ class ClockSampler:
 
     def __init__(self, index, period=0.02):
         self.index, self.period, self.rows = index, period, []
+        self.recording = False
+        self.first_at = 0.0
         self.stop_flag = threading.Event()
         self.thread = None
         self.h = None
@@ -115,16 +118,30 @@ class ClockSampler:
                 return int(ids[index])
         return index
 
+    def sample(self):
+        try:
+            sm = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+            mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            self.rows.append((float(sm), int(mask)))
+        except Exception:                                      # noqa: BLE001
+            pass
+
     def _loop(self):
-        nv = self.nv
         while not self.stop_flag.is_set():
-            try:
-                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                self.rows.append((float(sm), int(mask)))
-            except Exception:                                  # noqa: BLE001
-                pass
+            if self.recording and time.perf_counter() >= self.first_at:
+                self.sample()
             self.stop_flag.wait(self.period)
+
+    def begin(self, head_start=0.04):
+        """Start sampling: called when the timed region starts.  An NVML query holds a driver lock that kernel
+        launches need, for up to several milliseconds.  With nothing queued ahead of the host -- the first steps
+        after the barrier -- that is a GPU bubble of the same length (it showed up as one 3-11 ms step in an
+        otherwise flat 0.86 ms series, always the second step: step_us.max / max_at_step), so the first query
+        waits until the host has built a lead (it issues a step in about half the time the GPU needs for it);
+        bench takes one more sample right after the last launch, while the queue is still draining."""
+        self.rows = []
+        self.first_at = time.perf_counter() + head_start
+        self.recording = True
 
     def start(self):
         if self.h is None:
@@ -269,6 +286,8 @@ def main():
     EV_STRIDE = 4
     ev_b0 = {i: torch.cuda.Event(enable_timing=True) for i in range(0, args.steps, EV_STRIDE)}
     ev_b1 = {i: torch.cuda.Event(enable_timing=True) for i in range(0, args.steps, EV_STRIDE)}
+    ev_step = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]     # end of every step
+    host_us = []
 
     def step(i=None):
         for t in tgt:
@@ -297,18 +316,31 @@ def main():
     if args.settle > 0:
         torch.cuda.synchronize()
         time.sleep(args.settle)
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        loss = step()                       # same object lifetimes as in the timed loop (the allocator's steady state)
+    barrier()
+    if rank == 0:
+        sampler.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the cyclic garbage collector stays out of the timed region (what timeit does): a full collection over
+    # torch's heap takes 3-15 ms, and it used to land on the second timed step, when nothing is queued ahead
+    # of the host yet -- one long step in an otherwise flat series (step_us.max / max_at_step)
+    gc.collect()
+    gc.disable()
     barrier()
     e0.record()
     for i in range(args.steps):
+        h0 = time.perf_counter()
         loss = step(i)
+        host_us.append((time.perf_counter() - h0) * 1e6)
+        ev_step[i].record()
     e1.record()
+    if rank == 0 and sampler.h is not None:
+        sampler.sample()                    # the GPU is still working through the queued steps
     barrier()
+    gc.enable()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     tmax = torch.tensor([ms], device=dev)
@@ -344,6 +376,16 @@ def main():
         "gpu_launches": (10 if args.head else 4) * args.steps, "loss": float(loss.item()),
     }
     if rank == 0:
+        # distribution of the per-step device time inside the timed region (ms_per_step is its mean): a handful of
+        # slow steps means the host stalled (a busy node), a uniform shift means the kernels themselves moved
+        marks = [e0] + ev_step
+        raw = [marks[i].elapsed_time(marks[i + 1]) * 1e3 for i in range(args.steps)]
+        slowest = max(range(args.steps), key=lambda i: raw[i])
+        d = sorted(raw)
+        h = sorted(host_us)
+        n = len(d)
+        out["step_us"] = {"p10": round(d[n // 10], 1), "p50": round(d[n // 2], 1), "p90": round(d[(9 * n) // 10], 1),
+                          "max": round(d[-1], 1), "max_at_step": slowest, "host_issue_p50": round(h[n // 2], 1), "host_issue_max": round(h[-1], 1)}
         out["kernels_us"] = kernel_breakdown(step)
     if args.head:
         out["config"]["workload"] = out["config"]["workload"].replace(

@@ -323,7 +323,11 @@ class _FusedPatchNCE(torch.autograd.Function):
                                                 plan.idplan.numel(), out.data_ptr(), flag_ptr or None,
                                                 _stream_ptr(dev)), "pnce_fwd_planned")
             _warnings.commit(slot, dev)
-        ctx.plan, ctx.ws, ctx.ws_bytes = plan, ws, ws_bytes
+        # the workspace goes through save_for_backward: autograd then frees it with the graph, right after
+        # backward() -- kept as a plain ctx attribute it lived as long as the loss tensor did, and a caller that
+        # holds on to the loss across steps (loss = step()) made every step allocate a second 0.26 GB workspace
+        ctx.save_for_backward(ws)
+        ctx.plan, ctx.ws_bytes = plan, ws_bytes
         ctx.layers = layers              # the backward only fills in the dtgt pointers
         ctx.tgt_meta = [(t.shape, t.dtype) for t in tgt]
         ctx.tgt_keep = tgt               # shapes only matter, but keeps data_ptrs stable for the struct
@@ -336,6 +340,7 @@ class _FusedPatchNCE(torch.autograd.Function):
         lib = _lib.load()
         dev = ctx.dev
         g = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous()
+        (ws,) = ctx.saved_tensors
         with _on_device(dev):
             grads = [torch.empty(shape, dtype=dt, device=dev) for shape, dt in ctx.tgt_meta]
             layers = ctx.layers
@@ -343,11 +348,11 @@ class _FusedPatchNCE(torch.autograd.Function):
                 layers[l].dtgt = gl.data_ptr()
             if ctx.plan.idplan is None:
                 _lib.check(lib.pnce_bwd(layers, len(grads), ctx.batch, ctx.dtype, _MATH[ctx.plan.math],
-                                        ctx.ws.data_ptr(), ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev)),
+                                        ws.data_ptr(), ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev)),
                            "pnce_bwd")
             else:
                 _lib.check(lib.pnce_bwd_planned(layers, len(grads), ctx.batch, ctx.dtype, _MATH[ctx.plan.math],
-                                                ctx.ws.data_ptr(), ctx.ws_bytes, ctx.plan.idplan.data_ptr(),
+                                                ws.data_ptr(), ctx.ws_bytes, ctx.plan.idplan.data_ptr(),
                                                 ctx.plan.idplan.numel(), g.data_ptr(), _stream_ptr(dev)),
                            "pnce_bwd_planned")
         return (None, *grads)
@@ -706,7 +711,8 @@ class _FusedHeadPatchNCE(torch.autograd.Function):
                                          ws.data_ptr(), nbytes.value, out.data_ptr(), flag_ptr or None,
                                          _stream_ptr(dev)), "pnce_head_fwd")
             _warnings.commit(slot, dev)
-        ctx.plan, ctx.ws, ctx.ws_bytes, ctx.nc = plan, ws, nbytes.value, nc
+        ctx.save_for_backward(ws)            # freed with the graph, right after backward() (see _FusedPatchNCE)
+        ctx.plan, ctx.ws_bytes, ctx.nc = plan, nbytes.value, nc
         ctx.tgt_keep, ctx.params = tgt, params
         ctx.param_meta = [(a.shape, a.dtype) for a in args[n:]]
         ctx.dev, ctx.batch, ctx.dtype = dev, batch, dtype
@@ -734,7 +740,8 @@ class _FusedHeadPatchNCE(torch.autograd.Function):
                                                                       b2.data_ptr())
                 heads[l].dw1, heads[l].db1, heads[l].dw2, heads[l].db2 = (d1.data_ptr(), e1.data_ptr(),
                                                                           d2.data_ptr(), e2.data_ptr())
-            args = (layers, heads, n, ctx.batch, ctx.dtype, ctx.nc, _MATH[ctx.plan.math], ctx.ws.data_ptr(),
+            (ws,) = ctx.saved_tensors
+            args = (layers, heads, n, ctx.batch, ctx.dtype, ctx.nc, _MATH[ctx.plan.math], ws.data_ptr(),
                     ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev))
             if group is None:
                 _lib.check(lib.pnce_head_bwd(*args), "pnce_head_bwd")
