@@ -386,7 +386,9 @@ def main():
         n = len(d)
         out["step_us"] = {"p10": round(d[n // 10], 1), "p50": round(d[n // 2], 1), "p90": round(d[(9 * n) // 10], 1),
                           "max": round(d[-1], 1), "max_at_step": slowest, "host_issue_p50": round(h[n // 2], 1), "host_issue_max": round(h[-1], 1)}
-        out["kernels_us"] = kernel_breakdown(step)
+    kernels = kernel_breakdown(step)        # on every rank: head mode's backward holds a collective
+    if rank == 0:
+        out["kernels_us"] = kernels
     if args.head:
         out["config"]["workload"] = out["config"]["workload"].replace(
             "reference-exact mode (no netF head)", "netF head mode (Linear-ReLU-Linear, nc=256, tcgen05)")
