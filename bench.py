@@ -389,6 +389,8 @@ def main():
     kernels = kernel_breakdown(step)        # on every rank: head mode's backward holds a collective
     if rank == 0:
         out["kernels_us"] = kernels
+        if not args.head and "k_gather_tc" in kernels and "k_loss_tc_p" in kernels:
+            out["roofline_other_kernels"] = other_kernel_rooflines(args, layers, B, elem, kernels, peak)
     if args.head:
         out["config"]["workload"] = out["config"]["workload"].replace(
             "reference-exact mode (no netF head)", "netF head mode (Linear-ReLU-Linear, nc=256, tcgen05)")
@@ -425,6 +427,31 @@ def kernel_breakdown(step, n=5):
         return dict(sorted(rows.items(), key=lambda kv: -kv[1])[:8])
     except Exception as e:                                     # noqa: BLE001
         return {"unavailable": repr(e)}
+
+
+def other_kernel_rooflines(args, layers, B, elem, kernels, hbm_peak):
+    """The two kernels beside the dominant one, timed by the profiler pass above (SURVEY.md 8d figures):
+    the gather against HBM with its USEFUL bytes (and the DRAM traffic ncu measured: NCHW puts every channel of a
+    patch in its own 128-byte line, so the traffic is ~19x the useful bytes -- inherent to the reference's layout),
+    the logits/CE kernel against the tensor pipe with its algorithmic flops (4 P^2 C per image-layer: QK^T and
+    dZ K; the bf16x3 mode issues three MMAs per product, so 'issued' is 3x 'achieved')."""
+    p = args.patches
+    useful = B * sum(2 * min(p, h * w) * c * elem for c, h, w, _ in layers)
+    flops = B * sum(4 * min(p, h * w) ** 2 * c for c, h, w, _ in layers)
+    tg, tl = kernels["k_gather_tc"] * 1e-6, kernels["k_loss_tc_p"] * 1e-6
+    tensor_peak = 1408.6
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        tensor_peak = float(json.load(open(path)).get("bf16_tflops_sustained", tensor_peak))
+    ach = flops / tl / 1e12
+    return [
+        {"kernel": "k_gather_tc", "bound": "hbm", "achieved": useful / tg / 1e9, "peak": hbm_peak, "unit": "GB/s",
+         "frac": useful / tg / 1e9 / hbm_peak, "traffic": ncu_traffic("k_gather_tc", B, elem),
+         "traffic_gbs": (ncu_traffic("k_gather_tc", B, elem) or 0) / tg / 1e9, "launch_ms": tg * 1e3},
+        {"kernel": "k_loss_tc_p", "bound": "tensor", "achieved": ach, "issued_bf16x3": 3 * ach, "peak": tensor_peak,
+         "unit": "TFLOP/s", "frac": ach / tensor_peak, "traffic": ncu_traffic("k_loss_tc_p", B, elem),
+         "launch_ms": tl * 1e3},
+    ]
 
 
 def ncu_traffic(kernel, batch, elem):
