@@ -1,0 +1,45 @@
+"""Randomised stress of the fused path against the oracle: ragged shapes, every math mode, both id paths
+(in-line and side-stream plan), repeated launches (races in the persistent kernels would show as mismatches
+or protocol timeouts)."""
+import sys, random
+sys.path.insert(0, '.')
+import numpy as np, torch
+import gan_variant_research_b200 as pn
+from gan_variant_research_b200 import patchnce as pm
+from oracle import patchnce_oracle as orc
+rnd = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+ncase = int(sys.argv[2]) if len(sys.argv) > 2 else 150
+worst = {'loss': 0.0, 'grad': 0.0}
+for case in range(ncase):
+    b = rnd.randint(1, 5); nl = rnd.randint(1, 5)
+    shapes = [(rnd.choice([1, 3, 8, 31, 32, 33, 64, 100, 128, 200, 256]), rnd.randint(2, 36), rnd.randint(2, 36)) for _ in range(nl)]
+    p = rnd.choice([1, 7, 32, 64, 127, 128, 129, 200, 256])
+    tau = rnd.choice([0.07, 0.07, 0.07, 0.5, 0.015])
+    math = rnd.choice(['tc_bf16x3', 'tc_bf16x3', 'simt_f32'])
+    g = torch.Generator().manual_seed(case)
+    src = [torch.randn(b, *s, generator=g) for s in shapes]
+    tgt = [torch.randn(b, *s, generator=g) for s in shapes]
+    if rnd.random() < 0.3:
+        src = [x.relu() for x in src]; tgt = [x.relu() for x in tgt]
+    pm._SIDE_STREAM_MIN_BYTES = 0 if rnd.random() < 0.5 else (1 << 30)
+    crit = pn.PatchNCELoss(tau, p, math=math)
+    t = [x.cuda().requires_grad_() for x in tgt]
+    up = rnd.choice([1.0, 0.25, 1024.0])
+    for rep in range(2):
+        for x in t: x.grad = None
+        loss = crit([x.cuda() for x in src], t)
+        (loss * up).backward()
+    ids = [i.cpu().numpy() for i in crit.last_patch_ids]
+    want, _, gw = orc.patchnce_loss_and_grads_np([x.numpy() for x in src], [x.numpy() for x in tgt], ids, tau, upstream=up)
+    le = abs(loss.item() - want) / max(abs(want), 1e-12)
+    ge = 0.0
+    for l in range(nl):
+        got = t[l].grad.double().cpu().numpy()
+        sc = max(np.abs(gw[l]).max(), 1e-30)
+        ge = max(ge, np.abs(got - gw[l]).max() / sc)
+    tol_l, tol_g = (2e-5, 2e-4) if tau > 0.05 else (2e-4, 2e-3)
+    worst['loss'] = max(worst['loss'], le); worst['grad'] = max(worst['grad'], ge)
+    if not (le <= tol_l and ge <= tol_g) or not np.isfinite(le + ge):
+        print(f'MISMATCH case {case}: b={b} shapes={shapes} p={p} tau={tau} math={math} loss err {le:.2e} grad err {ge:.2e}')
+n = pn.poll_nonfinite_warnings(block=True)
+print(f'{ncase} cases done, worst loss err {worst["loss"]:.2e}, worst grad err {worst["grad"]:.2e}, guarded images {n}')
