@@ -89,6 +89,27 @@ __device__ __forceinline__ void tc_pass_a(const uint32_t (&r)[32], const float* 
   }
 }
 
+// The same for the LAST chunk of a key block when it holds padding columns (key weight w == 0): those
+// columns are excluded by a select instead of being counted as exp2(0) = 1 and subtracted afterwards -- the
+// subtraction cancels catastrophically when every real logit of the row is very negative (sum of exp2 below
+// one ulp of the pad count: P = 1, C = 1, constant maps ...), found by scratch/stress.py.  A key with w == 0
+// that is NOT padding is a non-finite row, and the image is guarded anyway.
+template <bool CLAMP>
+__device__ __forceinline__ void tc_pass_a_masked(const uint32_t (&r)[32], const float* __restrict__ wk, float a,
+                                                 float cl, float (&se)[4]) {
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const float4 w = *reinterpret_cast<const float4*>(wk + k4 * 4);
+    const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float y = __uint_as_float(r[k4 * 4 + t]) * a * ww[t];
+      if (CLAMP) y = fminf(fmaxf(y, -cl), cl);
+      se[t] += (ww[t] != 0.f) ? ex2f(y) : 0.f;
+    }
+  }
+}
+
 // ---- pass B over one 32-column chunk: softmax * coef / ||k_j|| -> bf16 hi (+lo) A-operand rows,
 //      s2 += dZ * y.  The "- I" of the diagonal is patched in afterwards by the owning thread.
 //      Padding columns: w = 0 -> the stored operand and the s2 term are exactly 0.
@@ -131,14 +152,15 @@ __device__ __forceinline__ void tc_pass_b(const uint32_t (&r)[32], const float* 
 // tcgen05.ld of chunk ch+1 is in flight while chunk ch is processed.
 template <bool CLAMP>
 __device__ __forceinline__ void tc_row_pass_a(uint32_t trow, int nch, const float* __restrict__ invk_s, float a,
-                                              float cl, int chd, int lane, float (&se)[4], float& ydraw) {
+                                              float cl, int chd, int lane, float (&se)[4], float& ydraw, bool pad) {
   using namespace umma;
   uint32_t r0[32], r1[32];
   tmem_ld32(trow, r0);
   for (int ch = 0; ch < nch; ch += 2) {
     tmem_ld_wait();
     if (ch + 1 < nch) tmem_ld32(trow + (ch + 1) * 32, r1);
-    tc_pass_a<CLAMP>(r0, invk_s + ch * 32, a, cl, se);
+    if (pad && ch == nch - 1) tc_pass_a_masked<CLAMP>(r0, invk_s + ch * 32, a, cl, se);
+    else tc_pass_a<CLAMP>(r0, invk_s + ch * 32, a, cl, se);
     if (ch == chd) {
 #pragma unroll
       for (int k = 0; k < 32; ++k) ydraw = (k == lane) ? __uint_as_float(r0[k]) : ydraw;
@@ -146,7 +168,8 @@ __device__ __forceinline__ void tc_row_pass_a(uint32_t trow, int nch, const floa
     if (ch + 1 < nch) {
       tmem_ld_wait();
       if (ch + 2 < nch) tmem_ld32(trow + (ch + 2) * 32, r0);
-      tc_pass_a<CLAMP>(r1, invk_s + (ch + 1) * 32, a, cl, se);
+      if (pad && ch + 1 == nch - 1) tc_pass_a_masked<CLAMP>(r1, invk_s + (ch + 1) * 32, a, cl, se);
+      else tc_pass_a<CLAMP>(r1, invk_s + (ch + 1) * 32, a, cl, se);
       if (ch + 1 == chd) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) ydraw = (k == lane) ? __uint_as_float(r1[k]) : ydraw;
@@ -544,11 +567,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       // ---- pass A: row sum of exp2 over all key blocks, diagonal ----
       float se4[4] = {0.f, 0.f, 0.f, 0.f};
       float ydacc = 0.f;                                      // raw accumulator of the diagonal element
-      int padcols = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int key0 = kb * 256, keys = min(P, key0 + 256) - key0;
         const int nch = (keys + 31) >> 5;                     // chunks that hold real columns
-        padcols += nch * 32 - keys;
+        const bool pad = (nch * 32 != keys);                  // the block's last chunk holds padding columns
         if (kb > 0) {                                          // swap in this block's 1/||k_j||
           asm volatile("bar.sync 1, 128;" ::: "memory");
           for (int j = et; j < 256; j += 128) invk_s[j] = (key0 + j < Ppad) ? __ldcg(L.kinv + (size_t)b * Ppad + key0 + j) : 0.f;
@@ -559,8 +581,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
         tc_fence_after();
         if (kb == 0) PNCE_TR(2);
         const int cd = (kb == kbd) ? chd : -1;
-        if (need_clamp) tc_row_pass_a<true>(trow, nch, invk_s, a, cl, cd, lane, se4, ydacc);
-        else tc_row_pass_a<false>(trow, nch, invk_s, a, cl, cd, lane, se4, ydacc);
+        if (need_clamp) tc_row_pass_a<true>(trow, nch, invk_s, a, cl, cd, lane, se4, ydacc, pad);
+        else tc_row_pass_a<false>(trow, nch, invk_s, a, cl, cd, lane, se4, ydacc, pad);
         if (multi) {
           tc_fence_before();
           mbar_arrive(&sh->zfree);                             // this Z block may be overwritten
@@ -569,8 +591,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       const float wd = multi ? __ldcg(L.kinv + (size_t)b * Ppad + (rowok ? gi : 0)) : invk_s[gi];
       const float ydr = ydacc * a * wd;                       // unclamped diagonal logit (log2 units)
       const float yd = need_clamp ? fminf(fmaxf(ydr, -cl), cl) : ydr;
-      // padding columns of the last chunk of a block contributed exp2(0) = 1 each
-      const float se = ((se4[0] + se4[1]) + (se4[2] + se4[3])) - (float)padcols;
+      const float se = (se4[0] + se4[1]) + (se4[2] + se4[3]);   // padding columns were masked out in pass A
       const float lse2 = lg2f(se);
       float rowloss = rowok ? (lse2 - yd) * kLn2 : 0.f;        // :94, labels = arange
       if (badrow && rowok) rowloss = __int_as_float(0x7fc00000);

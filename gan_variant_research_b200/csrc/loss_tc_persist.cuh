@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
       const float coef = rowok ? 1.0f / ((float)P * (float)p.B * (float)p.n_layers) : 0.f;
       const int chd = (gi & 255) >> 5;                        // chunk holding this row's diagonal (warp-uniform)
       const int nch = t.nj;                                   // chunks that hold real columns
-      const int padcols = nch * 32 - P;
+      const bool pad = (nch * 32 != P);                       // the last chunk holds padding columns (masked in pass A)
       // ---- pass A: row sum of exp2 over this warp's chunks, diagonal ----
       mbar_wait(&sh->zfull, par, dead);
       tc_fence_after();
@@ -385,7 +385,10 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
         uint32_t r[32];
         tmem_ld32(trow + ch * 32, r);
         tmem_ld_wait();
-        if (need_clamp) tc_pass_a<true>(r, invk_s + ch * 32, a, cl, se4);
+        if (pad && ch == nch - 1) {
+          if (need_clamp) tc_pass_a_masked<true>(r, invk_s + ch * 32, a, cl, se4);
+          else tc_pass_a_masked<false>(r, invk_s + ch * 32, a, cl, se4);
+        } else if (need_clamp) tc_pass_a<true>(r, invk_s + ch * 32, a, cl, se4);
         else tc_pass_a<false>(r, invk_s + ch * 32, a, cl, se4);
         if (ch == chd) {
 #pragma unroll
@@ -420,8 +423,7 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
       const float wd = invk_s[gi & 255];
       const float ydr = ydacc * a * wd;                       // unclamped diagonal logit (log2 units); owner only
       const float yd = need_clamp ? fminf(fmaxf(ydr, -cl), cl) : ydr;
-      // padding columns of the last chunk contributed exp2(0) = 1 each
-      const float lse2 = lg2f(se - (float)padcols);
+      const float lse2 = lg2f(se);
       float rowloss = (rowok && own) ? (lse2 - yd) * kLn2 : 0.f;            // :94, labels = arange
       if (badrow && rowok && own) rowloss = __int_as_float(0x7fc00000);
       // ---- pass B: dZ (pre-divided by ||k_j||) -> smem A operand chunk by chunk, s_i ----

@@ -617,3 +617,26 @@ def test_eight_layers_is_the_limit(pn, orc):
         assert_grad_close(t[l].grad.cpu().numpy(), gw[l], 2e-4, f"layer {l}", ids=ids[l].numpy())
     with pytest.raises(RuntimeError):
         pn.fused_patchnce([x.cuda() for x in src] * 2, [x.cuda() for x in tgt] * 2, [i.cuda() for i in ids] * 2, 0.07)
+
+
+@pytest.mark.parametrize("tau", [0.07, 0.03])            # logits near -14 / -33 (0.02 would sit exactly on the +-50 clamp)
+@pytest.mark.parametrize("p", [1, 20, 150])
+def test_all_logits_very_negative_with_padding_columns(pn, orc, tau, p):
+    """Every real logit of a row far below zero while the last 32-column chunk holds padding columns (P not a
+    multiple of 32): the sum of exp2 must not be formed as (sum incl. padding) - (pad count) -- found by
+    scratch/stress.py with P = 1 / C = 1 layers.  Target patches point away from every source patch."""
+    g = torch.Generator().manual_seed(p)
+    v = torch.randn(1, 16, 1, 1, generator=g)
+    src = [(v + 0.01 * torch.randn(2, 16, 12, 12, generator=g))]
+    tgt = [(-v + 0.01 * torch.randn(2, 16, 12, 12, generator=g))]
+    ids = [torch.randint(0, 144, (p,), generator=g)]
+    for math in ("tc_bf16x3", "simt_f32"):
+        t = [x.cuda().requires_grad_() for x in tgt]
+        loss = pn.fused_patchnce([x.cuda() for x in src], t, [i.cuda() for i in ids], tau, math=math)
+        loss.backward()
+        want, _, gw = orc.patchnce_loss_and_grads_np([x.numpy() for x in src], [x.numpy() for x in tgt],
+                                                     [i.numpy() for i in ids], tau)
+        assert loss.item() == pytest.approx(want, rel=1e-4, abs=2e-5), (math, loss.item(), want)
+        if p > 1:
+            assert_grad_close(t[0].grad.cpu().numpy(), gw[0], 2e-3, f"{math} P={p}", ids=ids[0].numpy())
+    assert pn.poll_nonfinite_warnings(block=True) == 0
