@@ -444,10 +444,15 @@ class PatchNCELoss(nn.Module):
 def compute_patchnce_loss(generator, src_images, tgt_images, nce_layers, temperature=0.07,
                           num_patches=256, math: Optional[str] = None):
     """Drop-in for ``compute_patchnce_loss`` -- patchnce_cut.py:113-149 (call site
-    training/train_cutpp.py:285-292).  ``generator`` only needs ``get_feature_layers``."""
+    training/train_cutpp.py:285-292).  ``generator`` only needs ``get_feature_layers``.  After
+    ``enable_encoder_feature_reuse(generator, nce_layers)`` the source features are the activations of the
+    ``generator(src_images)`` call that produced ``tgt_images`` (feature_reuse.py), not a second pass."""
     nce_loss_fn = PatchNCELoss(temperature, num_patches, nce_layers, math=math)       # :135
-    with torch.no_grad():                                                              # :138-139
-        src_feats = generator.get_feature_layers(src_images, nce_layers)
+    from .feature_reuse import cached_source_features
+    src_feats = cached_source_features(generator, src_images, nce_layers)  # maps of the generator(src) just run, if tapped
+    if src_feats is None:
+        with torch.no_grad():                                                          # :138-139
+            src_feats = generator.get_feature_layers(src_images, nce_layers)
     src_feats = [f.detach() for f in src_feats]                                        # :142
     tgt_feats = generator.get_feature_layers(tgt_images, nce_layers)                   # :145
     return nce_loss_fn(src_feats, tgt_feats)                                           # :147
