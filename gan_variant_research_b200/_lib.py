@@ -16,7 +16,7 @@ EXPORTS = [
     "pnce_fwd", "pnce_bwd", "pnce_plan_bytes", "pnce_plan_ids", "pnce_fwd_planned", "pnce_bwd_planned", "pnce_sample_fwd", "pnce_sample_bwd_workspace_bytes",
     "pnce_sample_bwd", "pnce_sample_multi_fwd", "pnce_sample_multi_bwd_workspace_bytes", "pnce_sample_multi_bwd",
     "pnce_rows_loss_workspace_bytes", "pnce_rows_loss_fwd_bwd", "pnce_selftest_umma",
-    "pnce_multi_chunk_elems", "pnce_multi_axpby",
+    "pnce_multi_chunk_elems", "pnce_multi_axpby", "pnce_amp_adam_scratch_floats", "pnce_amp_adam_step",
     "pnce_head_workspace_bytes", "pnce_head_fwd", "pnce_head_bwd", "pnce_head_bwd_params", "pnce_head_bwd_dense",
 ]
 
@@ -84,11 +84,16 @@ def load():
     for fn in (lib.pnce_head_bwd, lib.pnce_head_bwd_params, lib.pnce_head_bwd_dense):
         fn.argtypes = [ctypes.POINTER(PnceLayer), ctypes.POINTER(PnceHead), i32, i32, i32, i32, i32, vp, sz, vp, vp]
     lib.pnce_multi_axpby.argtypes = [vp, vp, vp, vp, vp, i32, f32, f32, i32, vp]
+    f64 = ctypes.c_double
+    lib.pnce_amp_adam_scratch_floats.argtypes = [i32]
+    lib.pnce_amp_adam_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, f32, f32, i32, f32,
+                                       f64, f64, f64, f64, f64, vp, vp]
     u32 = ctypes.c_uint
     lib.pnce_selftest_umma.argtypes = [vp, sz, vp, sz, u32, u32, u32, u32, u32, u32, i32, i32, i32, vp, vp, vp]
     for name in EXPORTS:
-        if name not in ("pnce_status_string", "pnce_last_cuda_error"):
+        if name not in ("pnce_status_string", "pnce_last_cuda_error", "pnce_amp_adam_scratch_floats"):
             getattr(lib, name).restype = i32
+    lib.pnce_amp_adam_scratch_floats.restype = sz
     if lib.pnce_abi_version() != 2:
         raise PnceError("libpnce.so ABI version mismatch")
     _lib = lib

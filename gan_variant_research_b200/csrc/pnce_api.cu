@@ -1319,6 +1319,40 @@ int pnce_multi_axpby(float* const* dev_dst, const float* const* dev_src, const l
 }
 int pnce_multi_chunk_elems(void) { return kMtChunk; }
 
+int pnce_amp_adam_step(float* const* dev_param, float* const* dev_grad, float* const* dev_exp_avg,
+                       float* const* dev_exp_avg_sq, float* const* dev_step, const long long* dev_numel,
+                       const int* dev_chunk_tensor, const long long* dev_chunk_start, int n_chunks, int n_tensors,
+                       float* dev_scale, int* dev_growth_tracker, float growth_factor, float backoff_factor,
+                       int growth_interval, float max_grad_norm, double lr, double beta1, double beta2, double eps,
+                       double weight_decay, float* dev_scratch, void* stream) {
+  if (!dev_param || !dev_grad || !dev_exp_avg || !dev_exp_avg_sq || !dev_step || !dev_numel || !dev_chunk_tensor ||
+      !dev_chunk_start || !dev_scratch || n_chunks < 0 || n_tensors < 0)
+    return PNCE_ERR_ARG;
+  if ((dev_scale == nullptr) != (dev_growth_tracker == nullptr)) return PNCE_ERR_ARG;
+  if (dev_scale && growth_interval < 1) return PNCE_ERR_ARG;
+  if (!(lr >= 0.0) || !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0) ||
+      !(weight_decay >= 0.0))
+    return PNCE_ERR_ARG;                                         // the checks of torch.optim.Adam.__init__
+  AmpAdamTable a;
+  a.param = dev_param; a.grad = dev_grad; a.m = dev_exp_avg; a.v = dev_exp_avg_sq; a.step = dev_step;
+  a.numel = dev_numel; a.chunk_tensor = dev_chunk_tensor; a.chunk_start = dev_chunk_start;
+  a.n_chunks = n_chunks; a.n_tensors = n_tensors;
+  a.scale = dev_scale; a.growth_tracker = dev_growth_tracker;
+  a.growth_factor = growth_factor; a.backoff_factor = backoff_factor; a.growth_interval = growth_interval;
+  a.max_norm = max_grad_norm;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+  a.scratch = dev_scratch;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_chunks > 0) {
+    k_amp_gradnorm<<<(unsigned)n_chunks, kMtThreads, 0, st>>>(a);
+    k_amp_adam<<<(unsigned)n_chunks, kMtThreads, 0, st>>>(a);
+  }
+  k_amp_finish<<<1, kMtThreads, 0, st>>>(a);       // with no gradients at all GradScaler.update() still runs
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+size_t pnce_amp_adam_scratch_floats(int n_chunks) { return (size_t)(n_chunks < 0 ? 0 : n_chunks) + 2; }
+
 int pnce_selftest_umma(const void* a_blob, size_t a_bytes, const void* b_blob, size_t b_bytes,
                        unsigned a_lbo, unsigned a_sbo, unsigned a_kstep, unsigned b_lbo, unsigned b_sbo,
                        unsigned b_kstep, int n, int k, int b_mn_major, float* d_out, int* err, void* stream) {

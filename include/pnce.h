@@ -191,6 +191,28 @@ int pnce_multi_axpby(float* const* dev_dst, const float* const* dev_src, const l
                      const int* dev_chunk_tensor, const long long* dev_chunk_start, int n_chunks, float a, float b,
                      int mode, void* stream);
 
+/* AMPContext.step_optimizer(optimizer, max_grad_norm) of the reference (utils/amp_utils.py:29-41) for an optim.Adam
+ * (training/sched_optim.py:20-25): GradScaler.unscale_, clip_grad_norm_, the skip-on-non-finite optimizer.step() and
+ * GradScaler.update(), as three launches over the same chunk tables as above (one entry per parameter that has a
+ * gradient) and with no host sync: the skip decision, the per-tensor step counters (dev_step[t]: one float each,
+ * torch's "capturable" layout) and the loss scale stay on the device.
+ *   dev_scale / dev_growth_tracker : GradScaler._scale (float) and ._growth_tracker (int32) device scalars, or both
+ *                                    NULL = no scaler (gradients used as they are, never skipped)
+ *   max_grad_norm < 0              : no clipping
+ *   dev_scratch                    : pnce_amp_adam_scratch_floats(n_chunks) floats, zeroed ONCE by the caller; after
+ *                                    the call [1] holds the total gradient norm (before clipping, after unscaling)
+ * Arithmetic = ATen's foreach Adam (lerp_, mul_, addcmul_, sqrt, div_, add_, addcdiv_), bias corrections in double:
+ * bit-identical to torch whenever the clip coefficient clamps to 1; otherwise the total norm is summed in another
+ * order than torch's (norm of per-tensor norms) and values agree to fp32 rounding.  Gradients are left unscaled and
+ * clipped, as the reference leaves them; amsgrad / maximize are not supported.                                  */
+size_t pnce_amp_adam_scratch_floats(int n_chunks);
+int pnce_amp_adam_step(float* const* dev_param, float* const* dev_grad, float* const* dev_exp_avg,
+                       float* const* dev_exp_avg_sq, float* const* dev_step, const long long* dev_numel,
+                       const int* dev_chunk_tensor, const long long* dev_chunk_start, int n_chunks, int n_tensors,
+                       float* dev_scale, int* dev_growth_tracker, float growth_factor, float backoff_factor,
+                       int growth_interval, float max_grad_norm, double lr, double beta1, double beta2, double eps,
+                       double weight_decay, float* dev_scratch, void* stream);
+
 /* Library self-test of the tcgen05 building blocks (bulk copy -> smem, tcgen05.mma with a K-major
  * or MN-major B operand, commit, tcgen05.ld): D(128 x n) = A(128 x k) * B on pre-tiled bf16 operand
  * blobs with host-supplied descriptor strides.  *dev_err is set to 1 on a protocol timeout.       */
