@@ -825,11 +825,22 @@ def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0
     return loss, ids
 
 
-def install_reference_shim():
+def install_reference_shim(optimiser_side: bool = False):
     """Make ``from GAN_Variant1.losses.patchnce_cut import compute_patchnce_loss`` resolve to this
     implementation, so the unchanged reference training loop (train_cutpp.py:28) uses the B200
-    path.  Call before importing ``GAN_Variant1.training.train_cutpp``."""
+    path.  Call before importing ``GAN_Variant1.training.train_cutpp``.
+
+    ``optimiser_side=True`` also re-points the two optimiser-side seams of SURVEY.md section 8f row 3 (the
+    reference package must be importable): ``GAN_Variant1.utils.io_ckpt.EMA`` (imported by name at
+    train_cutpp.py:34) -> the one-launch ``EMA``, and ``AMPContext.step_optimizer`` (amp_utils.py:29) -> the
+    three-launch ``amp_step_optimizer``."""
     import types
+    if optimiser_side:
+        import importlib
+        from .amp_step import amp_step_optimizer
+        from .ema import EMA
+        importlib.import_module("GAN_Variant1.utils.io_ckpt").EMA = EMA
+        importlib.import_module("GAN_Variant1.utils.amp_utils").AMPContext.step_optimizer = amp_step_optimizer
     mod = types.ModuleType("GAN_Variant1.losses.patchnce_cut")
     mod.PatchNCELoss = PatchNCELoss
     mod.compute_patchnce_loss = compute_patchnce_loss

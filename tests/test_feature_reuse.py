@@ -143,3 +143,24 @@ def test_compute_patchnce_loss_with_reuse_equals_without(monkeypatch):
         assert torch.isfinite(b).all()
         if a.dim() > 1:          # biases in front of an InstanceNorm have a zero gradient: rounding noise only
             assert float((a - b).abs().max()) <= 0.3 * float(a.abs().max())
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "GAN_Variant1")), reason="reference tree not mounted")
+def test_shim_repoints_the_optimiser_side_seams():
+    import gan_variant_research_b200 as pn
+    sys.path.insert(0, REF)
+    saved = {k: v for k, v in sys.modules.items() if k.startswith("GAN_Variant1")}
+    try:
+        import GAN_Variant1.utils.amp_utils as au
+        import GAN_Variant1.utils.io_ckpt as ck
+        keep = (ck.EMA, au.AMPContext.step_optimizer)
+        pn.install_reference_shim(optimiser_side=True)
+        assert ck.EMA is pn.EMA and au.AMPContext.step_optimizer is pn.amp_step_optimizer
+        from GAN_Variant1.losses.patchnce_cut import compute_patchnce_loss
+        assert compute_patchnce_loss is pn.compute_patchnce_loss
+        ck.EMA, au.AMPContext.step_optimizer = keep
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k.startswith("GAN_Variant1")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
