@@ -24,8 +24,8 @@ __host__ __device__ inline size_t loss_simt_smem_bytes(int P) {
 __device__ void finalize_losses(const Params& p) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
   const int B = p.B, nl = p.n_layers;
-  __shared__ float w_sum[8];
-  __shared__ int w_bad[8];
+  __shared__ float w_sum[32];                                   // one slot per warp of ANY launch shape (k_loss_tc_p: 11-12 warps)
+  __shared__ int w_bad[32];
   __shared__ int layer_bad[PNCE_MAX_LAYERS];
   __shared__ int any_guard;
   float total = 0.f;                                            // thread 0 only

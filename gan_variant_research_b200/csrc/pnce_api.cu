@@ -270,6 +270,7 @@ struct DebugKnobs {
   int no_persist = 0;        // 1: one CTA per item (k_loss_tc) even where the persistent kernel applies
   int persist_ctas = 0;      // > 0: grid of the persistent loss kernel (default: one CTA per SM)
   long long* trace = nullptr;
+  cudaEvent_t post_gather_event = nullptr;   // recorded on the caller's stream between the gather and the loss kernel
 };
 static DebugKnobs g_dbg;
 
@@ -374,6 +375,7 @@ static int forward_tc(Params& p, cudaStream_t st, bool planned = false) {
     p.b0 = 0; p.bn = p.B;
     rc = launch_gather_tc(p, st);
     if (rc != PNCE_OK) return rc;
+    if (g_dbg.post_gather_event) PNCE_CUDA(cudaEventRecord(g_dbg.post_gather_event, st));
     return launch_loss_tc(p, st);
   }
   AuxStreams* ax = nullptr;
@@ -482,6 +484,7 @@ int pnce_debug_set(int key, long long value) {
     case 6: g_dbg.no_persist = (int)value; break;
     case 7: g_dbg.persist_ctas = (int)value; break;
     case 8: g_gather_in_layer_order = (int)value; break;
+    case 10: g_dbg.post_gather_event = reinterpret_cast<cudaEvent_t>(value); break;
     case 9: { int v = (int)value; PNCE_CUDA(cudaMemcpyToSymbol(g_dx_evict_last, &v, sizeof(int))); break; }
     default: return PNCE_ERR_ARG;
   }
@@ -502,6 +505,29 @@ __global__ void k_debug_blocker(volatile int* stop, int* resident) {
 int pnce_debug_block_sms(int n_sms, int* stop_and_resident, void* stream) {
   PNCE_CUDA(cudaFuncSetAttribute(k_debug_blocker, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   k_debug_blocker<<<n_sms, 1, 226 * 1024, static_cast<cudaStream_t>(stream)>>>(stop_and_resident, stop_and_resident + 1);
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+// Experiment (scratch/exp31.py): zero fill by 128-thread CTAs without shared memory -- can it run beside k_loss_tc_p?
+// ctas > 0: persistent grid-stride CTAs; ctas == 0: one CTA per 8 KB, in address order.
+__global__ void __launch_bounds__(128) k_debug_fill(float4* __restrict__ p, long long n16, int persistent) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (persistent) {
+    for (long long i = (long long)blockIdx.x * 128 + threadIdx.x; i < n16; i += (long long)gridDim.x * 128) p[i] = z;
+  } else {
+    const long long base = (long long)blockIdx.x * 512;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = base + k * 128 + threadIdx.x;
+      if (i < n16) p[i] = z;
+    }
+  }
+}
+int pnce_debug_fill(void* ptr, long long bytes, int ctas, void* stream) {
+  PNCE_CUDA(cudaFuncSetAttribute(k_debug_fill, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  const long long n16 = bytes / 16;
+  const unsigned grid = ctas > 0 ? (unsigned)ctas : (unsigned)((n16 + 511) / 512);
+  k_debug_fill<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<float4*>(ptr), n16, ctas > 0);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }

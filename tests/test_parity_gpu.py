@@ -640,3 +640,24 @@ def test_all_logits_very_negative_with_padding_columns(pn, orc, tau, p):
         if p > 1:
             assert_grad_close(t[0].grad.cpu().numpy(), gw[0], 2e-3, f"{math} P={p}", ids=ids[0].numpy())
     assert pn.poll_nonfinite_warnings(block=True) == 0
+
+
+@pytest.mark.parametrize("b", [300, 513])
+def test_more_images_than_the_finalize_has_lanes(pn, orc, b):
+    """Batches above 256 images: the last-CTA finalize sums the per-image losses with every thread of the launch
+    (352 in the persistent kernel = 11 warps) -- its per-warp scratch used to hold 8 warps only, which batches up
+    to 256 never noticed (threads >= 256 had nothing to add)."""
+    g = torch.Generator().manual_seed(b)
+    src = [torch.randn(b, 8, 6, 6, generator=g)]
+    tgt = [torch.randn(b, 8, 6, 6, generator=g)]
+    tgt[0][b - 1, :, :, :] = float("nan")                      # a guarded image handled by a thread of a high warp
+    ids = [torch.randint(0, 36, (16,), generator=g)]
+    for math in ("tc_bf16x3", "simt_f32"):
+        t = [x.cuda().requires_grad_() for x in tgt]
+        loss = pn.fused_patchnce([x.cuda() for x in src], t, [i.cuda() for i in ids], 0.07, math=math)
+        loss.backward()
+        assert pn.poll_nonfinite_warnings(block=True) == 1
+        want, _, gw = orc.patchnce_loss_and_grads_np([x.numpy() for x in src], [x.numpy() for x in tgt],
+                                                     [i.numpy() for i in ids], 0.07)
+        assert loss.item() == pytest.approx(want, rel=2e-5), math
+        assert_grad_close(t[0].grad.cpu().numpy(), gw[0], 2e-4, f"{math} B={b}")
