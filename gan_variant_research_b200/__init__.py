@@ -22,6 +22,7 @@ from .patchnce import (  # noqa: F401
     rows_patchnce,
 )
 from .ema import EMA  # noqa: F401
+from .dside import DiffAugment, discriminator_hinge_loss, generator_hinge_loss  # noqa: F401
 from .amp_step import FusedAdamStep, amp_step_optimizer  # noqa: F401
 from .feature_reuse import EncoderFeatureCache, enable_encoder_feature_reuse  # noqa: F401
 from .dp import GradReducer, allreduce_head_grads, broadcast_patch_ids, shard_batch  # noqa: F401
@@ -31,4 +32,5 @@ __all__ = [
     "draw_patch_ids", "draw_patch_ids_all", "pinned_as_device", "patch_count", "install_reference_shim", "poll_nonfinite_warnings",
     "DEFAULT_MATH", "patchnce_with_head", "allreduce_head_grads", "broadcast_patch_ids", "shard_batch", "GradReducer", "EMA",
     "EncoderFeatureCache", "enable_encoder_feature_reuse", "FusedAdamStep", "amp_step_optimizer",
+    "DiffAugment", "discriminator_hinge_loss", "generator_hinge_loss",
 ]

@@ -17,6 +17,7 @@ EXPORTS = [
     "pnce_sample_bwd", "pnce_sample_multi_fwd", "pnce_sample_multi_bwd_workspace_bytes", "pnce_sample_multi_bwd",
     "pnce_rows_loss_workspace_bytes", "pnce_rows_loss_fwd_bwd", "pnce_selftest_umma",
     "pnce_multi_chunk_elems", "pnce_multi_axpby", "pnce_amp_adam_scratch_floats", "pnce_amp_adam_step",
+    "pnce_diffaug_scratch_floats", "pnce_diffaug", "pnce_hinge_fwd", "pnce_hinge_bwd",
     "pnce_head_workspace_bytes", "pnce_head_fwd", "pnce_head_bwd", "pnce_head_bwd_params", "pnce_head_bwd_dense",
 ]
 
@@ -88,12 +89,18 @@ def load():
     lib.pnce_amp_adam_scratch_floats.argtypes = [i32]
     lib.pnce_amp_adam_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, f32, f32, i32, f32,
                                        f64, f64, f64, f64, f64, vp, vp]
+    lib.pnce_diffaug_scratch_floats.argtypes = [i32, i32, i32]
+    lib.pnce_diffaug.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, vp]
+    lib.pnce_hinge_fwd.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.pnce_hinge_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
     u32 = ctypes.c_uint
     lib.pnce_selftest_umma.argtypes = [vp, sz, vp, sz, u32, u32, u32, u32, u32, u32, i32, i32, i32, vp, vp, vp]
     for name in EXPORTS:
-        if name not in ("pnce_status_string", "pnce_last_cuda_error", "pnce_amp_adam_scratch_floats"):
+        if name not in ("pnce_status_string", "pnce_last_cuda_error", "pnce_amp_adam_scratch_floats",
+                        "pnce_diffaug_scratch_floats"):
             getattr(lib, name).restype = i32
     lib.pnce_amp_adam_scratch_floats.restype = sz
+    lib.pnce_diffaug_scratch_floats.restype = sz
     if lib.pnce_abi_version() != 2:
         raise PnceError("libpnce.so ABI version mismatch")
     _lib = lib

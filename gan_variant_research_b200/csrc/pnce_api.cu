@@ -16,6 +16,7 @@
 #include "rows_pack.cuh"
 #include "multi_tensor.cuh"
 #include "sample_bwd.cuh"
+#include "dside.cuh"
 
 namespace pnce {
 
@@ -1377,6 +1378,106 @@ int pnce_amp_adam_step(float* const* dev_param, float* const* dev_grad, float* c
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
+// ---- D-side row -------------------------------------------------------------------
+static int aug_blocks(int H, int W) {
+  const int per = (H * W + kAugThreads - 1) / kAugThreads;
+  return per < 32 ? per : 32;
+}
+size_t pnce_diffaug_scratch_floats(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return (size_t)B * aug_blocks(H, W);
+}
+int pnce_diffaug(const void* dev_in, void* dev_out, int dtype, int B, int C, int H, int W, const void* dev_rb,
+                 const void* dev_rs, const void* dev_rc, const long long* dev_tx, const long long* dev_ty,
+                 const long long* dev_ox, const long long* dev_oy, int cut_h, int cut_w, float* dev_scratch,
+                 int backward, void* stream) {
+  if (!dev_in || !dev_out || dev_in == dev_out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return PNCE_ERR_ARG;
+  if (dtype < PNCE_F32 || dtype > PNCE_BF16) return PNCE_ERR_ARG;
+  if (C > kAugMaxC || (long long)C * H * W > 0x7fffffffLL || B > 65535) return PNCE_ERR_UNSUPPORTED;
+  const bool color = dev_rb != nullptr;
+  if (color != (dev_rs != nullptr) || color != (dev_rc != nullptr)) return PNCE_ERR_ARG;   // 'color' is all three
+  if ((dev_tx != nullptr) != (dev_ty != nullptr)) return PNCE_ERR_ARG;
+  const bool cut = cut_h > 0 || cut_w > 0;
+  if (cut && (cut_h <= 0 || cut_w <= 0 || !dev_ox || !dev_oy)) return PNCE_ERR_ARG;
+  if (color && !dev_scratch) return PNCE_ERR_WORKSPACE;
+  AugParams a;
+  memset(&a, 0, sizeof(a));
+  a.x = dev_in; a.y = dev_out; a.dtype = dtype; a.B = B; a.C = C; a.H = H; a.W = W;
+  a.rb = dev_rb; a.rs = dev_rs; a.rc = dev_rc; a.tx = dev_tx; a.ty = dev_ty;
+  a.ox = cut ? dev_ox : nullptr; a.oy = cut ? dev_oy : nullptr;
+  a.cut_h = cut ? cut_h : 0; a.cut_w = cut ? cut_w : 0;
+  a.part = dev_scratch; a.nblk = aug_blocks(H, W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 rgrid((unsigned)a.nblk, (unsigned)B), grid((unsigned)((H * W + kAugThreads - 1) / kAugThreads), (unsigned)B);
+#define PNCE_AUG_LAUNCH(T)                                                              \
+  do {                                                                                  \
+    if (color) {                                                                        \
+      if (backward) k_aug_reduce<T, true><<<rgrid, kAugThreads, 0, st>>>(a);            \
+      else k_aug_reduce<T, false><<<rgrid, kAugThreads, 0, st>>>(a);                    \
+    }                                                                                   \
+    if (backward) k_aug_bwd<T><<<grid, kAugThreads, 0, st>>>(a);                        \
+    else k_aug_fwd<T><<<grid, kAugThreads, 0, st>>>(a);                                 \
+  } while (0)
+  if (dtype == PNCE_F32) PNCE_AUG_LAUNCH(float);
+  else if (dtype == PNCE_F16) PNCE_AUG_LAUNCH(__half);
+  else PNCE_AUG_LAUNCH(__nv_bfloat16);
+#undef PNCE_AUG_LAUNCH
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+
+static int hinge_fill(HingeParams& h, const void* const* real, const void* const* fake, void* const* dreal,
+                      void* const* dfake, const long long* numel, int scales, int mode, int dtype) {
+  if (!fake || !numel || scales < 1 || (mode != 0 && mode != 1)) return PNCE_ERR_ARG;
+  if (scales > kHingeMaxScales) return PNCE_ERR_UNSUPPORTED;
+  if (dtype < PNCE_F32 || dtype > PNCE_BF16) return PNCE_ERR_ARG;
+  if (mode == 0 && !real) return PNCE_ERR_ARG;
+  memset(&h, 0, sizeof(h));
+  for (int s = 0; s < scales; ++s) {
+    if (!fake[s] || (mode == 0 && !real[s]) || numel[s] <= 0) return PNCE_ERR_ARG;
+    h.fake[s] = fake[s];
+    h.real[s] = mode == 0 ? real[s] : nullptr;
+    h.dreal[s] = dreal ? dreal[s] : nullptr;
+    h.dfake[s] = dfake ? dfake[s] : nullptr;
+    h.n[s] = numel[s];
+  }
+  h.scales = scales; h.mode = mode; h.dtype = dtype;
+  return PNCE_OK;
+}
+int pnce_hinge_fwd(const void* const* real, const void* const* fake, const long long* numel, int scales, int mode,
+                   int dtype, float* dev_loss, void* stream) {
+  HingeParams h;
+  int rc = hinge_fill(h, real, fake, nullptr, nullptr, numel, scales, mode, dtype);
+  if (rc != PNCE_OK) return rc;
+  if (!dev_loss) return PNCE_ERR_ARG;
+  h.loss = dev_loss;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == PNCE_F32) k_hinge_fwd<float><<<1, kAugThreads, 0, st>>>(h);
+  else if (dtype == PNCE_F16) k_hinge_fwd<__half><<<1, kAugThreads, 0, st>>>(h);
+  else k_hinge_fwd<__nv_bfloat16><<<1, kAugThreads, 0, st>>>(h);
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+int pnce_hinge_bwd(const void* const* real, const void* const* fake, void* const* dreal, void* const* dfake,
+                   const long long* numel, int scales, int mode, int dtype, const float* dev_grad_out, void* stream) {
+  HingeParams h;
+  int rc = hinge_fill(h, real, fake, dreal, dfake, numel, scales, mode, dtype);
+  if (rc != PNCE_OK) return rc;
+  if (!dev_grad_out) return PNCE_ERR_ARG;
+  h.grad_out = dev_grad_out;
+  long long mx = 0;
+  for (int s = 0; s < scales; ++s) mx = numel[s] > mx ? numel[s] : mx;
+  long long gx = (mx + kAugThreads - 1) / kAugThreads;
+  if (gx > 1024) gx = 1024;
+  const dim3 grid((unsigned)gx, (unsigned)scales);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == PNCE_F32) k_hinge_bwd<float><<<grid, kAugThreads, 0, st>>>(h);
+  else if (dtype == PNCE_F16) k_hinge_bwd<__half><<<grid, kAugThreads, 0, st>>>(h);
+  else k_hinge_bwd<__nv_bfloat16><<<grid, kAugThreads, 0, st>>>(h);
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+
 size_t pnce_amp_adam_scratch_floats(int n_chunks) { return (size_t)(n_chunks < 0 ? 0 : n_chunks) + 2; }
 
 int pnce_selftest_umma(const void* a_blob, size_t a_bytes, const void* b_blob, size_t b_bytes,

@@ -213,6 +213,30 @@ int pnce_amp_adam_step(float* const* dev_param, float* const* dev_grad, float* c
                        int growth_interval, float max_grad_norm, double lr, double beta1, double beta2, double eps,
                        double weight_decay, float* dev_scratch, void* stream);
 
+/* ---- "next" row 4: D-side elementwise work -----------------------------------------------
+ * DiffAugment (training/diffaugment.py:6-60, policy color -> translation -> cutout, any of the three left out) as one
+ * pass over the images -- two launches with 'color' (contrast needs the per-image mean first), one without.  The
+ * random draws are the CALLER's: the same torch.rand / torch.randint calls as the reference, in the same order, so the
+ * parameters and the RNG stream are bit-identical; NULL pointers / zero cut sizes switch a stage off.
+ *   dev_rb/rs/rc : rand(B) in the image dtype (:8, :15, :22);  dev_tx/ty : randint(-shift, shift+1, (B,)) int64 (:28-29)
+ *   dev_ox/oy    : randint(0, H + (1 - cut_h % 2), (B,)) / same for W, int64 (:46-47);  cut_h/cut_w : int(H*ratio+.5) (:45)
+ *   backward = 0 : dev_out = augment(dev_in);   backward = 1 : dev_out = d loss / d input given dev_in = d loss / d output
+ *                  (the op is affine in the image, so the backward needs the parameters only)
+ *   dev_scratch  : pnce_diffaug_scratch_floats(B, H, W) floats (needed with 'color')                              */
+size_t pnce_diffaug_scratch_floats(int B, int H, int W);
+int pnce_diffaug(const void* dev_in, void* dev_out, int dtype, int B, int C, int H, int W, const void* dev_rb,
+                 const void* dev_rs, const void* dev_rc, const long long* dev_tx, const long long* dev_ty,
+                 const long long* dev_ox, const long long* dev_oy, int cut_h, int cut_w, float* dev_scratch,
+                 int backward, void* stream);
+/* Hinge losses over the list of discriminator outputs (losses/adv_hinge.py:6-62), one launch per direction.
+ *   mode 0: discriminator_hinge_loss(real_preds, fake_preds) (:6-32);  mode 1: generator_hinge_loss(fake_preds) (:35-62)
+ * real / fake / dreal / dfake are HOST arrays of `scales` device pointers (dreal / dfake entries may be NULL);
+ * numel[s] = elements of scale s; the loss leaves as one fp32 device scalar.                                      */
+int pnce_hinge_fwd(const void* const* real, const void* const* fake, const long long* numel, int scales, int mode,
+                   int dtype, float* dev_loss, void* stream);
+int pnce_hinge_bwd(const void* const* real, const void* const* fake, void* const* dreal, void* const* dfake,
+                   const long long* numel, int scales, int mode, int dtype, const float* dev_grad_out, void* stream);
+
 /* Library self-test of the tcgen05 building blocks (bulk copy -> smem, tcgen05.mma with a K-major
  * or MN-major B operand, commit, tcgen05.ld): D(128 x n) = A(128 x k) * B on pre-tiled bf16 operand
  * blobs with host-supplied descriptor strides.  *dev_err is set to 1 on a protocol timeout.       */
