@@ -53,12 +53,12 @@ __global__ void __launch_bounds__(kAugThreads) k_aug_reduce(const __grid_constan
       const int i = pix / a.W, j = pix - i * a.W;
       const int u = i + tx, v = j + ty;
       if (u < 0 || u >= a.H || v < 0 || v >= a.W || aug_cut(a, b, i, j)) continue;
-      for (int c = 0; c < C; ++c) acc += aug_ld<T>(a.x, img + (long long)c * HW + pix);
+      _Pragma("unroll") for (int c = 0; c < kAugMaxC; ++c) if (c < C) acc += aug_ld<T>(a.x, img + (long long)c * HW + pix);
     } else {
       float x1[kAugMaxC], m = 0.f;
-      for (int c = 0; c < C; ++c) { x1[c] = aug_ld<T>(a.x, img + (long long)c * HW + pix) + rb; m += x1[c]; }
+      _Pragma("unroll") for (int c = 0; c < kAugMaxC; ++c) if (c < C) { x1[c] = aug_ld<T>(a.x, img + (long long)c * HW + pix) + rb; m += x1[c]; }
       m /= (float)C;
-      for (int c = 0; c < C; ++c) acc += (x1[c] - m) * ss + m;
+      _Pragma("unroll") for (int c = 0; c < kAugMaxC; ++c) if (c < C) acc += (x1[c] - m) * ss + m;
     }
   }
   __shared__ float red[kAugThreads / 32];
@@ -72,35 +72,49 @@ __global__ void __launch_bounds__(kAugThreads) k_aug_reduce(const __grid_constan
   }
 }
 
+// Sum of image b's pass-1 partials, once per CTA (warp 0, fixed shuffle tree: the same bits in every CTA), broadcast
+// through shared memory.  Called by all threads of the CTA before anything returns.
+__device__ __forceinline__ float aug_image_sum(const AugParams& a, int b) {
+  __shared__ float s_tot;
+  if (threadIdx.x < 32) {
+    float v = 0.f;
+    for (int k = threadIdx.x; k < a.nblk; k += 32) v += a.part[(size_t)b * a.nblk + k];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) s_tot = v;
+  }
+  __syncthreads();
+  return s_tot;
+}
+
 // Pass 2, forward: one thread per OUTPUT pixel, all channels.  y[b,:,i,j] = cutout(i,j) ? 0 : color(x[b,:,i+tx,j+ty])
 // (zero when the source lies outside the image: the reference gathers from a zero-padded copy, :33-34).
 template <typename T>
 __global__ void __launch_bounds__(kAugThreads) k_aug_fwd(const __grid_constant__ AugParams a) {
   const int b = blockIdx.y, HW = a.H * a.W, C = a.C;
   const int pix = blockIdx.x * kAugThreads + threadIdx.x;
-  if (pix >= HW) return;
   const long long img = (long long)b * C * HW;
   const int i = pix / a.W, j = pix - i * a.W;
   const int u = i + (a.tx ? (int)a.tx[b] : 0), v = j + (a.ty ? (int)a.ty[b] : 0);
-  T* y = reinterpret_cast<T*>(a.y);
-  if (u < 0 || u >= a.H || v < 0 || v >= a.W || aug_cut(a, b, i, j)) {
-    for (int c = 0; c < C; ++c) y[img + (long long)c * HW + pix] = from_f32<T>(0.f);
-    return;
-  }
+  const bool live = pix < HW && u >= 0 && u < a.H && v >= 0 && v < a.W && !aug_cut(a, b, i, j);
   const int sp = u * a.W + v;
   float val[kAugMaxC];
-  for (int c = 0; c < C; ++c) val[c] = aug_ld<T>(a.x, img + (long long)c * HW + sp);
+  _Pragma("unroll") for (int c = 0; c < kAugMaxC; ++c) if (c < C) val[c] = live ? aug_ld<T>(a.x, img + (long long)c * HW + sp) : 0.f;
+  const float tot = a.rb ? aug_image_sum(a, b) : 0.f;             // the loads above are in flight across its barrier
+  if (pix >= HW) return;
+  T* y = reinterpret_cast<T*>(a.y);
+  if (!live) {
+    _Pragma("unroll") for (int c = 0; c < kAugMaxC; ++c) if (c < C) y[img + (long long)c * HW + pix] = from_f32<T>(0.f);
+    return;
+  }
   if (a.rb) {                                                         // 'color' = brightness, saturation, contrast :6-23
     const float rb = aug_ld<T>(a.rb, b) - 0.5f, ss = aug_ld<T>(a.rs, b) * 2.0f, sc = aug_ld<T>(a.rc, b) + 0.5f;
-    float mu = 0.f;
-    for (int k = 0; k < a.nblk; ++k) mu += a.part[(size_t)b * a.nblk + k];
-    mu /= (float)((long long)C * HW);
+    const float mu = tot / (float)((long long)C * HW);
     float m = 0.f;
-    for (int c = 0; c < C; ++c) { val[c] += rb; m += val[c]; }
+    _Pragma("unroll") for (int c = 0; c < kAugMaxC; ++c) if (c < C) { val[c] += rb; m += val[c]; }
     m /= (float)C;
-    for (int c = 0; c < C; ++c) val[c] = (((val[c] - m) * ss + m) - mu) * sc + mu;
+    _Pragma("unroll") for (int c = 0; c < kAugMaxC; ++c) if (c < C) val[c] = (((val[c] - m) * ss + m) - mu) * sc + mu;
   }
-  for (int c = 0; c < C; ++c) y[img + (long long)c * HW + pix] = from_f32<T>(val[c]);
+  _Pragma("unroll") for (int c = 0; c < kAugMaxC; ++c) if (c < C) y[img + (long long)c * HW + pix] = from_f32<T>(val[c]);
 }
 
 // Pass 2, backward: one thread per INPUT pixel (u,v); the only output pixel that read it is (u - tx, v - ty).
@@ -110,25 +124,24 @@ template <typename T>
 __global__ void __launch_bounds__(kAugThreads) k_aug_bwd(const __grid_constant__ AugParams a) {
   const int b = blockIdx.y, HW = a.H * a.W, C = a.C;
   const int pix = blockIdx.x * kAugThreads + threadIdx.x;
-  if (pix >= HW) return;
   const long long img = (long long)b * C * HW;
   const int u = pix / a.W, v = pix - u * a.W;
   const int i = u - (a.tx ? (int)a.tx[b] : 0), j = v - (a.ty ? (int)a.ty[b] : 0);
-  const bool live = i >= 0 && i < a.H && j >= 0 && j < a.W && !aug_cut(a, b, i, j);
+  const bool live = pix < HW && i >= 0 && i < a.H && j >= 0 && j < a.W && !aug_cut(a, b, i, j);
   float d[kAugMaxC];
-  for (int c = 0; c < C; ++c) d[c] = live ? aug_ld<T>(a.x, img + (long long)c * HW + i * a.W + j) : 0.f;
+  _Pragma("unroll") for (int c = 0; c < kAugMaxC; ++c) if (c < C) d[c] = live ? aug_ld<T>(a.x, img + (long long)c * HW + i * a.W + j) : 0.f;
+  const float tot = a.rb ? aug_image_sum(a, b) : 0.f;             // the loads above are in flight across its barrier
+  if (pix >= HW) return;
   if (a.rb) {
     const float ss = aug_ld<T>(a.rs, b) * 2.0f, sc = aug_ld<T>(a.rc, b) + 0.5f;
-    float tot = 0.f;
-    for (int k = 0; k < a.nblk; ++k) tot += a.part[(size_t)b * a.nblk + k];
     const float kappa = (1.0f - sc) * tot / (float)((long long)C * HW);
     float m = 0.f;
-    for (int c = 0; c < C; ++c) { d[c] = sc * d[c] + kappa; m += d[c]; }
+    _Pragma("unroll") for (int c = 0; c < kAugMaxC; ++c) if (c < C) { d[c] = sc * d[c] + kappa; m += d[c]; }
     m /= (float)C;
-    for (int c = 0; c < C; ++c) d[c] = ss * d[c] + (1.0f - ss) * m;
+    _Pragma("unroll") for (int c = 0; c < kAugMaxC; ++c) if (c < C) d[c] = ss * d[c] + (1.0f - ss) * m;
   }
   T* y = reinterpret_cast<T*>(a.y);
-  for (int c = 0; c < C; ++c) y[img + (long long)c * HW + pix] = from_f32<T>(d[c]);
+  _Pragma("unroll") for (int c = 0; c < kAugMaxC; ++c) if (c < C) y[img + (long long)c * HW + pix] = from_f32<T>(d[c]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -152,10 +165,20 @@ __global__ void __launch_bounds__(kAugThreads) k_hinge_fwd(const __grid_constant
   float total = 0.f;                                                  // thread 0 only
   for (int s = 0; s < h.scales; ++s) {
     float acc = 0.f;
-    for (long long i = threadIdx.x; i < h.n[s]; i += kAugThreads) {
-      const float f = aug_ld<T>(h.fake[s], i);
-      if (h.mode == 0) acc += fmaxf(1.0f - aug_ld<T>(h.real[s], i), 0.f) + fmaxf(1.0f + f, 0.f);
-      else acc -= f;
+    const long long n = h.n[s];
+    for (long long i0 = threadIdx.x; i0 < n; i0 += 8 * kAugThreads) {   // 8 (x2) independent loads in flight per thread
+      float f[8], r[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const long long i = i0 + (long long)k * kAugThreads;
+        f[k] = i < n ? aug_ld<T>(h.fake[s], i) : (h.mode == 0 ? -1.0f : 0.f);       // neutral elements of the two sums
+        r[k] = (h.mode == 0 && i < n) ? aug_ld<T>(h.real[s], i) : 1.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (h.mode == 0) acc += fmaxf(1.0f - r[k], 0.f) + fmaxf(1.0f + f[k], 0.f);
+        else acc -= f[k];
+      }
     }
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
