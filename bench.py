@@ -7,7 +7,9 @@
 
 A step = id draw + gather + normalise + logits + diagonal CE + full backward to the dense
 d tgt_feat of every layer, for one batch of synthetic feature maps; the
-generator passes are not part of the metric.  Prints ONE JSON line on rank 0.
+generator passes are not part of the metric.  Prints ONE JSON line on rank 0.  Secondary objects on that line
+(measured AFTER the timed region, N=1 only): head_mode, module_split, next_rows (the optimiser-side and D-side pieces
+of SURVEY.md 8f), e2e, cpu_baseline.
 """
 import argparse
 import gc
@@ -398,6 +400,9 @@ def main():
         out["head_mode"] = head_line(args, pn, src, tgt, math, patches_per_image)
         out["module_split"] = module_split_line(args, pn, src, tgt, math, patches_per_image)
 
+    if rank == 0 and world == 1 and not args.head and not args.no_head_line:
+        out["next_rows"] = next_rows_line(pn, dev)
+
     # ---- e2e: same metric through the public API with HOST buffers ------------------------------
     if not args.no_e2e:
         out["e2e"] = run_e2e(args, pn, crit, layers, tdtype, elem, dev, world, rank)
@@ -464,6 +469,51 @@ def ncu_traffic(kernel, batch, elem):
     if not d:
         return None
     return d["dram_bytes_per_launch"] * batch / d["batch"]
+
+
+def next_rows_line(pn, dev, n=30):
+    """Secondary measurements, after the timed region: the pieces around the path on the
+    reference generator's parameter shapes (tests/golden/model_param_shapes.json) and on 16 x 3 x 256 x 256 images.
+    Device time per call in us (CUDA events around n calls); never fatal for the bench line."""
+    try:
+        shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "model_param_shapes.json")))["generator"]
+        g = torch.Generator(device=dev).manual_seed(3)
+        params = [torch.nn.Parameter(torch.randn(*s, device=dev, generator=g) * 0.02) for s in shapes]
+        for p in params:
+            p.grad = torch.randn(p.shape, device=dev, generator=g) * 1e-4
+        net = torch.nn.Module()
+        net.params = torch.nn.ParameterList(params)
+        opt = torch.optim.Adam(net.parameters(), lr=2e-4, betas=(0.5, 0.999))
+        scaler = torch.amp.GradScaler("cuda", init_scale=1.0, growth_interval=10 ** 9)
+        scaler.scale(torch.zeros((), device=dev))
+        stepper, ema = pn.FusedAdamStep(opt, scaler, 10.0), pn.EMA(net, 0.999)
+        aug = pn.DiffAugment(["color", "translation", "cutout"])
+        x = (torch.rand(16, 3, 256, 256, device=dev, generator=g) * 2 - 1).requires_grad_()
+        up = torch.randn(16, 3, 256, 256, device=dev, generator=g)
+
+        def aug_step():
+            x.grad = None
+            aug(x).backward(up)
+
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return round(e0.elapsed_time(e1) / n * 1e3, 1)
+
+        return {"parameters": sum(p.numel() for p in params), "tensors": len(params),
+                "amp_adam_step_us": timed(stepper.step), "ema_update_us": timed(ema.update),
+                "diffaugment_fwd_bwd_b16_us": timed(aug_step),
+                "note": "unscale + clip + Adam + loss-scale update in 3 launches; EMA in 1; DiffAugment colour + translation + "
+                        "cutout in 2 + 2 (plus the 7 draws); DESIGN.md 7.2 - 7.5"}
+    except Exception as e:  # noqa: BLE001 - a secondary line must not take the bench down
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def head_line(args, pn, src, tgt, math, patches_per_image, steps=20):
