@@ -161,11 +161,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_gemm_tc(const __grid_constant
         v[k] = rowok ? x : 0.f;                               // padding rows stay exactly zero
       }
       if (mode == GM_DX) {
+        // same L2 evict_last policy as the loss kernel's dxT stores (loss_tc.cuh, st_dx)
+        const bool keep_dx = g_dx_evict_last != 0;
+        uint64_t pol_dx = 0;
+        if (keep_dx) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_dx));
         if (rowok) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const int c = ch * 32 + k;
-            if (c < pr.C) pr.outT[((size_t)b * pr.C + c) * Ppad + p] = v[k];
+            if (c < pr.C) st_dx(pr.outT + ((size_t)b * pr.C + c) * Ppad + p, v[k], keep_dx, pol_dx);
           }
         }
         continue;
