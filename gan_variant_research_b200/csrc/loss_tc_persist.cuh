@@ -49,7 +49,17 @@ struct TpItem {
   const LayerDev* L;
   int b, mh, halves, Ppad, P, C, Cp, Cp8, nstage, nj;
 };
+// Item order: the slots of the BlockMap run from the heaviest layer to the lightest (launch_loss_tc), ROTATED by
+// m.start[PNCE_MAX_LAYERS + 1] items, so that the first third of the CTAs starts on an item of the lightest layers and
+// the rest on a heavy one.  All CTAs start in lock-step on a cold L2 (the gather has just streamed 2 GB through it) and
+// every code path is slow the first time it runs (first item 42-61 k cycles vs 17-25 k in steady state; first pass-B
+// chunk 9 k vs 1.2 k -- per-item stamps, scratch/exp10.py; the kernel is 185 KB of SASS): two kinds of first item spread
+// those bursts.  Measured (scratch/exp34.py, B=64): kernel 95 -> 89-91 us for 24-100 light items first, 94 us for a whole
+// wave of light items, 97 us for two waves; the makespan model is indifferent to the rotation.
 __device__ __forceinline__ void tp_decode(const Params& p, const BlockMap& m, long long item, TpItem& t) {
+  const long long total = m.start[p.n_layers];
+  item += m.start[PNCE_MAX_LAYERS + 1];
+  if (item >= total) item -= total;
   const int slot = find_layer(m, item, p.n_layers);
   const LayerDev& L = p.L[m.layer[slot]];
   const int local = (int)(item - m.start[slot]);
@@ -433,10 +443,12 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
       dg.pass = !need_clamp || fabsf(ydr) <= cl;
       dg.d_w = dg.pass ? (ex2f(yd - lse2) - 1.f) * coef * wd : 0.f;
       dg.off = (uint32_t)((gi & 255) >> 3) * 2048u + rowoff + (uint32_t)(gi & 7) * 2u;
+      PNCE_TS(n, 14);
       for (int ch = half; ch < nch; ch += 2) {
         uint32_t r[32];
         tmem_ld32(trow + ch * 32, r);
         tmem_ld_wait();
+        if (ch == half) PNCE_TS(n, 15);
         if (need_clamp) tc_pass_b<true>(r, invk_s + ch * 32, a, cl, lse2, coef, x3, dzhi, dzlo, (uint32_t)(ch * 4) * 2048u + rowoff, s2);
         else tc_pass_b<false>(r, invk_s + ch * 32, a, cl, lse2, coef, x3, dzhi, dzlo, (uint32_t)(ch * 4) * 2048u + rowoff, s2);
         if (ch == chd) tc_fix_diag(dg, x3, dzhi, dzlo);

@@ -272,6 +272,7 @@ struct DebugKnobs {
   int persist_ctas = 0;      // > 0: grid of the persistent loss kernel (default: one CTA per SM)
   long long* trace = nullptr;
   cudaEvent_t post_gather_event = nullptr;   // recorded on the caller's stream between the gather and the loss kernel
+  long long loss_rot = 0;    // persistent loss kernel: 0 = a third of the CTAs start on light items (auto), -1 = plain heavy-first order, n > 0 = rotate by n
 };
 static DebugKnobs g_dbg;
 
@@ -317,6 +318,20 @@ static int launch_loss_tc(const Params& p, cudaStream_t st, bool single_launch =
     if (rc != PNCE_OK) return rc;
     Params q = p;
     q.total_ctas = (unsigned)grid;
+    // rotate the item list so that a third of the CTAs starts on an item of the lightest layers (tp_decode), taken
+    // from the END of the heavy-first order; an even count keeps the two halves of an image together
+    long long rot = 0;
+    if (g_dbg.loss_rot == 0) {
+      int cmin = p.L[order[p.n_layers - 1]].C;
+      long long light = 0;
+      for (int sl = p.n_layers - 1; sl >= 0 && p.L[order[sl]].C == cmin; --sl) light += m.start[sl + 1] - m.start[sl];
+      rot = light < grid / 3 ? light : grid / 3;
+      rot &= ~1LL;
+      if (light == acc) rot = 0;                                // one kind of item only: nothing to reorder
+    } else if (g_dbg.loss_rot > 0) {
+      rot = g_dbg.loss_rot < acc ? g_dbg.loss_rot : 0;
+    }
+    m.start[PNCE_MAX_LAYERS + 1] = rot > 0 ? acc - rot : 0;
     k_loss_tc_p<<<(unsigned)grid, kTpThreads, kTpSmemBytes, st>>>(q, m);
     PNCE_CUDA(cudaGetLastError());
     return PNCE_OK;
@@ -486,6 +501,7 @@ int pnce_debug_set(int key, long long value) {
     case 7: g_dbg.persist_ctas = (int)value; break;
     case 8: g_gather_in_layer_order = (int)value; break;
     case 10: g_dbg.post_gather_event = reinterpret_cast<cudaEvent_t>(value); break;
+    case 11: g_dbg.loss_rot = value; break;
     case 9: { int v = (int)value; PNCE_CUDA(cudaMemcpyToSymbol(g_dx_evict_last, &v, sizeof(int))); break; }
     default: return PNCE_ERR_ARG;
   }

@@ -17,7 +17,7 @@ t = tr.cpu().numpy()
 tl = t[64:64 + 3 * G].reshape(G, 3)
 t0 = (tl[:, 1] - tl[:, 1].min()) / 1e3; t1 = (tl[:, 2] - tl[:, 1].min()) / 1e3
 print(f'CTA timeline: start {t0.min():.1f}..{t0.max():.1f} us, end {t1.min():.1f}..{t1.max():.1f} us, makespan {t1.max():.1f}')
-names = {0: 'E:norm', 1: 'E:zfull', 2: 'E:A', 3: 'E:B', 4: 'E:dqfull', 5: 'E:dQ', 6: 'M:zfree', 7: 'M:P1', 8: 'M:dz0', 9: 'M:P2', 10: 'P:ring', 11: 'P:P1ld', 12: 'P:zfull', 13: 'P:P2ld'}
+names = {0: 'E:norm', 1: 'E:zfull', 2: 'E:A', 3: 'E:B', 4: 'E:dqfull', 5: 'E:dQ', 6: 'M:zfree', 7: 'M:P1', 8: 'M:dz0', 9: 'M:P2', 10: 'P:ring', 11: 'P:P1ld', 12: 'P:zfull', 13: 'P:P2ld', 14: 'E:preB', 15: 'E:B0ld'}
 for sel, nm in ((0, 'CTA 0'), (1, 'CTA grid/2')):
     st = t[64 + 3 * G + sel * 128: 64 + 3 * G + sel * 128 + 128].reshape(8, 16)
     ref = st[st > 0].min()
