@@ -272,6 +272,7 @@ struct DebugKnobs {
   int persist_ctas = 0;      // > 0: grid of the persistent loss kernel (default: one CTA per SM)
   long long* trace = nullptr;
   cudaEvent_t post_gather_event = nullptr;   // recorded on the caller's stream between the gather and the loss kernel
+  int loss_repeat = 0;       // n > 0: launch the loss kernel n extra times first (is its start-up cost cache coldness?)
   long long loss_rot = 0;    // persistent loss kernel: 0 = a third of the CTAs start on light items (auto), -1 = plain heavy-first order, n > 0 = rotate by n
 };
 static DebugKnobs g_dbg;
@@ -392,6 +393,10 @@ static int forward_tc(Params& p, cudaStream_t st, bool planned = false) {
     rc = launch_gather_tc(p, st);
     if (rc != PNCE_OK) return rc;
     if (g_dbg.post_gather_event) PNCE_CUDA(cudaEventRecord(g_dbg.post_gather_event, st));
+    for (int r = 0; r < g_dbg.loss_repeat; ++r) {              // experiment: warm launches in front of the real one
+      rc = launch_loss_tc(p, st);
+      if (rc != PNCE_OK) return rc;
+    }
     return launch_loss_tc(p, st);
   }
   AuxStreams* ax = nullptr;
@@ -502,6 +507,7 @@ int pnce_debug_set(int key, long long value) {
     case 8: g_gather_in_layer_order = (int)value; break;
     case 10: g_dbg.post_gather_event = reinterpret_cast<cudaEvent_t>(value); break;
     case 11: g_dbg.loss_rot = value; break;
+    case 13: g_dbg.loss_repeat = (int)value; break;
     case 9: { int v = (int)value; PNCE_CUDA(cudaMemcpyToSymbol(g_dx_evict_last, &v, sizeof(int))); break; }
     default: return PNCE_ERR_ARG;
   }

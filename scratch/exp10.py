@@ -12,7 +12,8 @@ crit = pn.PatchNCELoss(0.07, 256)
 for _ in range(3): crit(src, tgt)
 G = 148
 tr = torch.zeros(64 + 3 * G + 256 + 64, dtype=torch.int64, device=dev)
-lib.pnce_debug_set(3, tr.data_ptr()); crit(src, tgt); torch.cuda.synchronize(); lib.pnce_debug_set(3, 0)
+rep = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+lib.pnce_debug_set(13, rep); lib.pnce_debug_set(3, tr.data_ptr()); crit(src, tgt); torch.cuda.synchronize(); lib.pnce_debug_set(3, 0); lib.pnce_debug_set(13, 0)
 t = tr.cpu().numpy()
 tl = t[64:64 + 3 * G].reshape(G, 3)
 t0 = (tl[:, 1] - tl[:, 1].min()) / 1e3; t1 = (tl[:, 2] - tl[:, 1].min()) / 1e3
