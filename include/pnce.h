@@ -28,7 +28,9 @@ extern "C" {
 
 #define PNCE_ABI_VERSION 2
 #define PNCE_MAX_LAYERS 8      /* nce_layers per call (reference config uses 5 ids -> 4 maps)   */
-#define PNCE_MAX_PATCHES 4096  /* P = min(num_patches, H*W)  patchnce_cut.py:60                 */
+#define PNCE_MAX_PATCHES 4096  /* P = min(num_patches, H*W)  patchnce_cut.py:60; argument check only: the
+                                * kernels take P <= 1024 (tensor cores, C <= 256) or P <= 1280 (fp32 CUDA cores),
+                                * PNCE_ERR_UNSUPPORTED beyond                                                  */
 #define PNCE_MAX_CHANNELS 1024
 
 typedef enum {

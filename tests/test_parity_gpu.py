@@ -661,3 +661,30 @@ def test_more_images_than_the_finalize_has_lanes(pn, orc, b):
                                                      [i.numpy() for i in ids], 0.07)
         assert loss.item() == pytest.approx(want, rel=2e-5), math
         assert_grad_close(t[0].grad.cpu().numpy(), gw[0], 2e-4, f"{math} B={b}")
+
+
+@pytest.mark.parametrize("b,c,h,w,p", [(2, 8, 40, 40, 1280), (2, 512, 12, 12, 64), (1, 1024, 8, 8, 33), (2, 300, 36, 36, 1100)])
+def test_largest_supported_shapes(pn, orc, b, c, h, w, p):
+    """Outside the tensor-core envelope (P <= 1024, C <= 256) the fp32 CUDA-core kernels take over: up to 1280 patches
+    (its 32-row logits tile must fit shared memory) and up to 1024 channels."""
+    g = torch.Generator().manual_seed(c + p)
+    src = [torch.randn(b, c, h, w, generator=g)]
+    tgt = [torch.randn(b, c, h, w, generator=g)]
+    ids = [torch.randint(0, h * w, (min(p, h * w),), generator=g)]
+    t = [x.cuda().requires_grad_() for x in tgt]
+    loss = pn.fused_patchnce([x.cuda() for x in src], t, [i.cuda() for i in ids], 0.07)
+    loss.backward()
+    want, _, gw = orc.patchnce_loss_and_grads_np([x.numpy() for x in src], [x.numpy() for x in tgt],
+                                                 [i.numpy() for i in ids], 0.07)
+    assert loss.item() == pytest.approx(want, rel=2e-5)
+    assert_grad_close(t[0].grad.cpu().numpy(), gw[0], 2e-4, "large shape", ids=ids[0].numpy())
+
+
+@pytest.mark.parametrize("c,h,w,p", [(8, 40, 40, 1500), (8, 70, 70, 4096), (1025, 4, 4, 16)])
+def test_shapes_beyond_the_limits_fail_loudly(pn, c, h, w, p):
+    g = torch.Generator().manual_seed(1)
+    src = [torch.randn(1, c, h, w, generator=g).cuda()]
+    tgt = [torch.randn(1, c, h, w, generator=g).cuda().requires_grad_()]
+    ids = [torch.randint(0, h * w, (min(p, h * w),), generator=g).cuda()]
+    with pytest.raises(RuntimeError, match="outside compiled limits|not supported"):
+        pn.fused_patchnce(src, tgt, ids, 0.07)
