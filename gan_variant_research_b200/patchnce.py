@@ -825,7 +825,7 @@ def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0
     return loss, ids
 
 
-def install_reference_shim(optimiser_side: bool = False):
+def install_reference_shim(optimiser_side: bool = False, d_side: bool = False):
     """Make ``from GAN_Variant1.losses.patchnce_cut import compute_patchnce_loss`` resolve to this
     implementation, so the unchanged reference training loop (train_cutpp.py:28) uses the B200
     path.  Call before importing ``GAN_Variant1.training.train_cutpp``.
@@ -833,8 +833,15 @@ def install_reference_shim(optimiser_side: bool = False):
     ``optimiser_side=True`` also re-points the two optimiser-side seams of SURVEY.md section 8f row 3 (the
     reference package must be importable): ``GAN_Variant1.utils.io_ckpt.EMA`` (imported by name at
     train_cutpp.py:34) -> the one-launch ``EMA``, and ``AMPContext.step_optimizer`` (amp_utils.py:29) -> the
-    three-launch ``amp_step_optimizer``."""
+    three-launch ``amp_step_optimizer``.  ``d_side=True`` does the same for row 4: ``training.diffaugment.DiffAugment``
+    (imported by name at train_cutpp.py:30) and ``losses.adv_hinge.discriminator_hinge_loss`` / ``generator_hinge_loss``."""
     import types
+    if d_side:
+        import importlib
+        from . import dside
+        importlib.import_module("GAN_Variant1.training.diffaugment").DiffAugment = dside.DiffAugment
+        ah = importlib.import_module("GAN_Variant1.losses.adv_hinge")
+        ah.discriminator_hinge_loss, ah.generator_hinge_loss = dside.discriminator_hinge_loss, dside.generator_hinge_loss
     if optimiser_side:
         import importlib
         from .amp_step import amp_step_optimizer

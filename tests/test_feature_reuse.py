@@ -154,8 +154,12 @@ def test_shim_repoints_the_optimiser_side_seams():
         import GAN_Variant1.utils.amp_utils as au
         import GAN_Variant1.utils.io_ckpt as ck
         keep = (ck.EMA, au.AMPContext.step_optimizer)
-        pn.install_reference_shim(optimiser_side=True)
+        import GAN_Variant1.training.diffaugment as da
+        import GAN_Variant1.losses.adv_hinge as ah
+        pn.install_reference_shim(optimiser_side=True, d_side=True)
         assert ck.EMA is pn.EMA and au.AMPContext.step_optimizer is pn.amp_step_optimizer
+        assert da.DiffAugment is pn.DiffAugment and ah.generator_hinge_loss is pn.generator_hinge_loss
+        assert ah.discriminator_hinge_loss is pn.discriminator_hinge_loss
         from GAN_Variant1.losses.patchnce_cut import compute_patchnce_loss
         assert compute_patchnce_loss is pn.compute_patchnce_loss
         ck.EMA, au.AMPContext.step_optimizer = keep
