@@ -3,17 +3,19 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpnce.so")
+# PNCE_EXPERIMENTS=1 selects the experiment build (pnce_debug_* hooks, scratch/ scripts only), see build.py
+LIB_PATH = os.path.join(HERE, "libpnce_exp.so" if os.environ.get("PNCE_EXPERIMENTS", "") not in ("", "0") else "libpnce.so")
 
 PNCE_F32, PNCE_F16, PNCE_BF16 = 0, 1, 2
 MATH_SIMT_F32, MATH_TC_BF16X3, MATH_TC_BF16 = 0, 1, 2
 MAX_LAYERS = 8
 MAX_PATCHES = 4096
 MAX_CHANNELS = 1024
+ABI_VERSION = 3
 
 EXPORTS = [
     "pnce_abi_version", "pnce_status_string", "pnce_last_cuda_error", "pnce_workspace_bytes",
-    "pnce_fwd", "pnce_bwd", "pnce_plan_bytes", "pnce_plan_ids", "pnce_fwd_planned", "pnce_bwd_planned", "pnce_sample_fwd", "pnce_sample_bwd_workspace_bytes",
+    "pnce_fwd", "pnce_bwd", "pnce_fwd_draw", "pnce_plan_ids_draw", "pnce_draw_ids", "pnce_plan_bytes", "pnce_plan_ids", "pnce_fwd_planned", "pnce_bwd_planned", "pnce_sample_fwd", "pnce_sample_bwd_workspace_bytes",
     "pnce_sample_bwd", "pnce_sample_multi_fwd", "pnce_sample_multi_bwd_workspace_bytes", "pnce_sample_multi_bwd",
     "pnce_rows_loss_workspace_bytes", "pnce_rows_loss_fwd_bwd", "pnce_selftest_umma",
     "pnce_multi_chunk_elems", "pnce_multi_axpby", "pnce_amp_adam_scratch_floats", "pnce_amp_adam_step",
@@ -66,6 +68,10 @@ def load():
     lib.pnce_last_cuda_error.restype = ctypes.c_char_p
     lib.pnce_workspace_bytes.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, ctypes.POINTER(sz)]
     lib.pnce_fwd.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, f32, i32, vp, sz, vp, vp, vp]
+    u64 = ctypes.c_ulonglong
+    lib.pnce_fwd_draw.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, f32, i32, vp, sz, u64, u64, vp, vp, vp]
+    lib.pnce_plan_ids_draw.argtypes = [ctypes.POINTER(PnceLayer), i32, u64, u64, vp, sz, vp]
+    lib.pnce_draw_ids.argtypes = [ctypes.POINTER(PnceLayer), i32, u64, u64, vp]
     lib.pnce_bwd.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, i32, vp, sz, vp, vp]
     lib.pnce_plan_bytes.argtypes = [ctypes.POINTER(PnceLayer), i32, ctypes.POINTER(sz)]
     lib.pnce_plan_ids.argtypes = [ctypes.POINTER(PnceLayer), i32, vp, sz, vp]
@@ -101,7 +107,7 @@ def load():
             getattr(lib, name).restype = i32
     lib.pnce_amp_adam_scratch_floats.restype = sz
     lib.pnce_diffaug_scratch_floats.restype = sz
-    if lib.pnce_abi_version() != 2:
+    if lib.pnce_abi_version() != ABI_VERSION:
         raise PnceError("libpnce.so ABI version mismatch")
     _lib = lib
     return lib

@@ -126,6 +126,10 @@ class FusedAdamStep:
             scale_ptr, tracker_ptr, ctypes.c_float(gf), ctypes.c_float(bf), int(gi), ctypes.c_float(mx),
             float(g["lr"]), float(beta1), float(beta2), float(g["eps"]), float(g["weight_decay"]),
             self._scratch.data_ptr(), torch.cuda.current_stream(self._dev).cuda_stream), "pnce_amp_adam_step")
+        # parameters (and gradients: unscaled + clipped in place) were written through raw pointers -- bump the
+        # version counters like an in-place torch op would (feature_reuse's staleness guard reads them)
+        torch._C._increment_version(params)
+        torch._C._increment_version([p.grad for p in params])
 
     def last_total_norm(self) -> torch.Tensor:
         """Total gradient norm of the last step (after unscaling, before clipping) -- a device scalar, no sync."""

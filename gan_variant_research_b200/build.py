@@ -6,15 +6,18 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libpnce.so")
+# PNCE_EXPERIMENTS=1: the build with the pnce_debug_* hooks the scripts under scratch/ use (never the shipped library)
+EXPERIMENTS = os.environ.get("PNCE_EXPERIMENTS", "") not in ("", "0")
+LIB = os.path.join(HERE, "libpnce_exp.so" if EXPERIMENTS else "libpnce.so")
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-shared", "-Xcompiler", "-fPIC",
+    "-Xlinker", "--version-script=" + os.path.join(CSRC, "pnce.map"),
 ]
 
 
 def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".map")))
 
 
 def is_stale():
@@ -30,7 +33,7 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    cmd = [nvcc] + NVCC_FLAGS + (["-DPNCE_EXPERIMENTS"] if EXPERIMENTS else []) + (["-Xptxas", "-v"] if verbose else []) + \
         ["-o", LIB + ".tmp", os.path.join(CSRC, "pnce_api.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

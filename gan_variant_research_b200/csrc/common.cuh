@@ -70,6 +70,10 @@ struct Params {
   float* lossimg;            // [n_layers][B]
   int* valid;                // [n_layers][B]
   const float* grad_out;     // device scalar or NULL (=1)
+  // ids drawn by the library (pnce_fwd_draw / pnce_plan_ids_draw): layer l's ids are what torch.randint(0, HW, (P,))
+  // returns on a CUDA generator at (rng_seed, rng_offset + 4 l); k_prep writes them to L.ids before sorting them
+  unsigned long long rng_seed, rng_offset;
+  int rng_draw;
   long long* trace;          // debug: clock64 stamps of two CTAs of the tcgen05 loss kernel, or NULL
 };
 

@@ -176,8 +176,12 @@ __global__ void __launch_bounds__(kAugThreads) k_hinge_fwd(const __grid_constant
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        if (h.mode == 0) acc += fmaxf(1.0f - r[k], 0.f) + fmaxf(1.0f + f[k], 0.f);
-        else acc -= f[k];
+        if (h.mode == 0) {
+          // torch.relu propagates NaN (fmaxf would return the other operand and hide a diverged discriminator
+          // from train_step's non-finite check, train_cutpp.py:326-329)
+          const float vr = 1.0f - r[k], vf = 1.0f + f[k];
+          acc += ((vr > 0.f || vr != vr) ? vr : 0.f) + ((vf > 0.f || vf != vf) ? vf : 0.f);
+        } else acc -= f[k];
       }
     }
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -199,8 +203,8 @@ __global__ void __launch_bounds__(kAugThreads) k_hinge_bwd(const __grid_constant
   const float g = *h.grad_out / (float)h.scales / (float)h.n[s];
   for (long long i = (long long)blockIdx.x * kAugThreads + threadIdx.x; i < h.n[s]; i += (long long)gridDim.x * kAugThreads) {
     if (h.mode == 0) {
-      if (h.dreal[s]) reinterpret_cast<T*>(h.dreal[s])[i] = from_f32<T>(aug_ld<T>(h.real[s], i) < 1.0f ? -0.5f * g : 0.f);
-      if (h.dfake[s]) reinterpret_cast<T*>(h.dfake[s])[i] = from_f32<T>(aug_ld<T>(h.fake[s], i) > -1.0f ? 0.5f * g : 0.f);
+      if (h.dreal[s]) reinterpret_cast<T*>(h.dreal[s])[i] = from_f32<T>(!(aug_ld<T>(h.real[s], i) >= 1.0f) ? -0.5f * g : 0.f);   // relu backward passes the gradient at NaN
+      if (h.dfake[s]) reinterpret_cast<T*>(h.dfake[s])[i] = from_f32<T>(!(aug_ld<T>(h.fake[s], i) <= -1.0f) ? 0.5f * g : 0.f);
     } else if (h.dfake[s]) {
       reinterpret_cast<T*>(h.dfake[s])[i] = from_f32<T>(-g);
     }

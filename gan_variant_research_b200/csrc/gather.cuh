@@ -2,6 +2,8 @@
 // 32-patch tile), plus one "prep" CTA per layer that sorts the ids and builds the position bitmap
 // the dense backward needs.  Replaces patchnce_cut.py:56-78 (view/permute, index, stack, normalize).
 #pragma once
+#include <curand_kernel.h>
+
 #include "common.cuh"
 
 namespace pnce {
@@ -9,7 +11,16 @@ namespace pnce {
 // --------------------------------------------------------------------------------------------
 // prep CTA: ids -> (sid, perm, rank, cslot).  P <= PNCE_MAX_PATCHES.   smem: keys[N2] (u64).
 // --------------------------------------------------------------------------------------------
-__device__ void prep_layer(const LayerDev& L, unsigned long long* keys) {
+// draw != 0: the ids are DRAWN here first, bit for bit what `torch.randint(0, HW, (P,), device='cuda')` returns
+// (patchnce_cut.py:63) for a CUDA generator at (seed, offset): ATen's random_from_to kernel
+// (native/cuda/DistributionTemplates.h: distribution_elementwise_grid_stride_kernel with a grid that covers all P
+// elements in one sweep) gives element i the first 32-bit word of the Philox4x32-10 block of subsequence i at counter
+// offset / 4 -- curand_init(seed, i, offset) + curand4().x -- reduced by `% range` (ATen/core/TransformationHelper.h
+// uniform_int_from_to; range = HW < 2^32, base = 0).  One randint call advances the generator's offset by 4; the host
+// does the same (patchnce.py).  The int64 ids are written to L.ids, the caller's buffer, so that PatchNCELoss /
+// PatchSampleF can hand them out like the reference does.
+__device__ void prep_layer(const LayerDev& L, unsigned long long* keys, int draw = 0, unsigned long long seed = 0,
+                           unsigned long long offset = 0) {
   const int tid = threadIdx.x;
   const int P = L.P;
   int N2 = 1;
@@ -17,8 +28,17 @@ __device__ void prep_layer(const LayerDev& L, unsigned long long* keys) {
   for (int i = tid; i < N2; i += kThreads) {
     unsigned long long k = ~0ull;
     if (i < P) {
-      long long id = L.ids[i];
-      id = id < 0 ? 0 : (id >= L.HW ? L.HW - 1 : id);          // memory safety only; randint is in range
+      long long id;
+      if (draw) {
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, (unsigned long long)i, offset, &st);
+        const uint4 r = curand4(&st);
+        id = (long long)(r.x % (unsigned)L.HW);
+        const_cast<long long*>(L.ids)[i] = id;
+      } else {
+        id = L.ids[i];
+        id = id < 0 ? 0 : (id >= L.HW ? L.HW - 1 : id);        // memory safety only; randint is in range
+      }
       k = ((unsigned long long)(unsigned)id << 32) | (unsigned)i;
     }
     keys[i] = k;
@@ -149,7 +169,7 @@ __global__ void __launch_bounds__(kThreads) k_gather_prep(const __grid_constant_
   if (blk >= n_gather) {
     const int l = (int)(blk - n_gather);
     if (l == 0 && threadIdx.x == 0 && p.counter != nullptr) {
-      *p.counter = 0u;
+      p.counter[0] = 0u; p.counter[1] = 0u;
       if (p.nonfinite != nullptr) p.nonfinite[1] = 0;
     }
     if (p.L[l].sid == nullptr) return;

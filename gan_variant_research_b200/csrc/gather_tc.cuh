@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kThreads) k_gather_tc(const __grid_constant__ 
   if (blk == 0 && threadIdx.x == 0 && p.b0 == 0 && p.counter != nullptr) {
     // launch-sequence state of the loss kernel that follows on this stream (k_prep does the same when it
     // runs on this stream; with pnce_plan_ids it ran elsewhere, before the workspace existed)
-    *p.counter = 0u;
+    p.counter[0] = 0u; p.counter[1] = 0u;
     if (p.nonfinite != nullptr) p.nonfinite[1] = 0;
   }
   const int slot = find_layer(m, blk, p.n_layers);
@@ -110,13 +110,13 @@ __global__ void __launch_bounds__(kThreads) k_prep(const __grid_constant__ Param
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int l = blockIdx.x;
   if (l == 0 && threadIdx.x == 0 && p.counter != nullptr) {
-    *p.counter = 0u;
+    p.counter[0] = 0u; p.counter[1] = 0u;
     if (p.nonfinite != nullptr) p.nonfinite[1] = 0;
   }
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
   int N2 = 1;
   while (N2 < p.L[l].P) N2 <<= 1;
-  prep_layer(p.L[l], keys);
+  prep_layer(p.L[l], keys, p.rng_draw, p.rng_seed, p.rng_offset + 4ull * (unsigned long long)l);
 }
 
 }  // namespace pnce

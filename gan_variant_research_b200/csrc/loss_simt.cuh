@@ -64,6 +64,8 @@ __device__ void finalize_losses(const Params& p) {
   }
   if (tid == 0) {
     p.loss_out[0] = total / (float)nl;                          // :40
+    // a tcgen05 pipeline that timed out (umma::mbar_wait) left garbage behind: say so in the value itself
+    if (__ldcg(p.counter + 1) != 0u) p.loss_out[0] = __int_as_float(0x7fc00000);
     int nb = 0;
     for (int l = 0; l < nl; ++l) nb += layer_bad[l];
     if (p.nonfinite) *p.nonfinite = bad_total - nb;             // images guarded (layer guards are not counted)
@@ -110,7 +112,7 @@ __device__ __forceinline__ void last_cta_finalize(const Params& p, int* flag_s) 
   if (*flag_s) {
     __threadfence();
     finalize_losses(p);
-    if (threadIdx.x == 0) *p.counter = 0u;
+    if (threadIdx.x == 0) { p.counter[0] = 0u; p.counter[1] = 0u; }
   }
 }
 

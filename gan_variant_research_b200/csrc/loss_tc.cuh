@@ -253,7 +253,11 @@ __device__ __forceinline__ void tc_q_unpack(const TcQChunk& qc, float (&q)[32]) 
 // reads that would interleave with the dense kernel's 7 TB/s write stream (measured: dense 464 -> 454 us,
 // step 896 -> 877 us; pnce_debug_set key 9 = 0 turns it off).  k_dense_flat reads them with ld.global.cs,
 // which hands the lines back to the replacement policy as soon as they are consumed.
+#ifdef PNCE_EXPERIMENTS
 __device__ int g_dx_evict_last = 1;
+#else
+constexpr int g_dx_evict_last = 1;
+#endif
 __device__ __forceinline__ void st_dx(float* p, float v, bool keep, uint64_t pol) {
   if (keep) asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
   else *p = v;
@@ -357,7 +361,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
   volatile int* dead = &sh->dead;
   long long* tr = nullptr;                                   // debug stamps (pnce_debug_set key 3)
   if (p.trace != nullptr && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) tr = p.trace + (blockIdx.x ? 16 : 0);
+#ifdef PNCE_EXPERIMENTS
 #define PNCE_TR(slot) do { if (tr) tr[slot] = clock64(); } while (0)
+#else
+#define PNCE_TR(slot) do { } while (0)
+#endif
   // debug timeline: (sm id, start ns, end ns) of every CTA at trace[64 + 3 * blockIdx.x]
   if (p.trace != nullptr && tid == 0) {
     unsigned sm; unsigned long long t;
@@ -664,7 +672,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
-  if (tid == 0 && sh->dead && p.nonfinite != nullptr) *reinterpret_cast<volatile int*>(p.nonfinite + 1) = 1;   // protocol timeout flag (may be mapped host memory)
+  if (tid == 0 && sh->dead) {
+    p.counter[1] = 1u;                                        // finalize_losses turns the loss into NaN (in-band)
+    if (p.nonfinite != nullptr) *reinterpret_cast<volatile int*>(p.nonfinite + 1) = 1;   // protocol timeout flag (may be mapped host memory)
+  }
   if (p.trace != nullptr && tid == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -151,7 +151,11 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
   long long* trs = nullptr;
   if (p.trace != nullptr && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2))
     trs = p.trace + 64 + 3 * (size_t)gridDim.x + (blockIdx.x ? 128 : 0);
+#ifdef PNCE_EXPERIMENTS
 #define PNCE_TS(n_, slot_) do { if (trs && (n_) < 8) trs[(n_) * 16 + (slot_)] = clock64(); } while (0)
+#else
+#define PNCE_TS(n_, slot_) do { } while (0)
+#endif
 
   if (tid == 0) {
     for (int k = 0; k < kTcSlots1; ++k) { mbar_init(&sh->full1[k], 1); mbar_init(&sh->empty1[k], 1); }
@@ -522,7 +526,10 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
-  if (tid == 0 && sh->dead && p.nonfinite != nullptr) *reinterpret_cast<volatile int*>(p.nonfinite + 1) = 1;   // protocol timeout flag (may be mapped host memory)
+  if (tid == 0 && sh->dead) {
+    p.counter[1] = 1u;                                        // finalize_losses turns the loss into NaN (in-band)
+    if (p.nonfinite != nullptr) *reinterpret_cast<volatile int*>(p.nonfinite + 1) = 1;   // protocol timeout flag (may be mapped host memory)
+  }
   if (p.trace != nullptr && tid == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -239,7 +239,11 @@ static int launch_prep(const Params& p, cudaStream_t st) {
   return PNCE_OK;
 }
 
-static int g_gather_in_layer_order = 0;   // debug knob 8
+#ifdef PNCE_EXPERIMENTS
+static int g_gather_in_layer_order = 0;   // experiment knob 8
+#else
+static constexpr int g_gather_in_layer_order = 0;
+#endif
 
 static int launch_gather_tc(const Params& p, cudaStream_t st) {
   BlockMap m;
@@ -264,7 +268,10 @@ static int launch_gather_tc(const Params& p, cudaStream_t st) {
   return PNCE_OK;
 }
 
-// Experiment knobs (pnce_debug_set; not part of pnce.h).  0 = library default.
+// Experiment knobs.  The shipped library is built WITHOUT -DPNCE_EXPERIMENTS: the knobs are then compile-time
+// constants at their defaults and neither pnce_debug_* nor the experiment kernels exist in libpnce.so (every
+// exported symbol is declared in include/pnce.h).  `PNCE_EXPERIMENTS=1 python -m gan_variant_research_b200.build`
+// builds libpnce_exp.so with the hooks for the scripts under scratch/.  0 = library default.
 struct DebugKnobs {
   int dense_flags = 0;       // bit 0: skip the patch phase (fill ceiling)
   int fwd_chunks = 0;        // n > 1: cut the tensor-core forward into n chunks, loss(c) on an aux stream || gather(c+1)
@@ -275,7 +282,11 @@ struct DebugKnobs {
   int loss_repeat = 0;       // n > 0: launch the loss kernel n extra times first (is its start-up cost cache coldness?)
   long long loss_rot = 0;    // persistent loss kernel: 0 = a third of the CTAs start on light items (auto), -1 = plain heavy-first order, n > 0 = rotate by n
 };
+#ifdef PNCE_EXPERIMENTS
 static DebugKnobs g_dbg;
+#else
+static constexpr DebugKnobs g_dbg{};
+#endif
 
 static int sm_count(int* out) {
   static thread_local int cached_dev = -1, cached = 0;
@@ -496,7 +507,8 @@ const char* pnce_status_string(int s) {
 
 const char* pnce_last_cuda_error(void) { return g_cuda_err; }
 
-// Experiment hooks (not part of pnce.h).
+#ifdef PNCE_EXPERIMENTS
+// Experiment hooks (libpnce_exp.so only; not part of pnce.h).
 int pnce_debug_set(int key, long long value) {
   switch (key) {
     case 1: g_dbg.dense_flags = (int)value; break;
@@ -561,6 +573,7 @@ int pnce_debug_set_l2_fetch_granularity(int bytes) {
   PNCE_CUDA(cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
   return (int)v;
 }
+#endif  // PNCE_EXPERIMENTS
 
 int pnce_workspace_bytes(const pnce_layer_t* layers, int n_layers, int batch, size_t* bytes) {
   if (bytes == nullptr) return PNCE_ERR_ARG;
@@ -577,7 +590,7 @@ int pnce_workspace_bytes(const pnce_layer_t* layers, int n_layers, int batch, si
 
 static int fwd_impl(const pnce_layer_t* layers, int n_layers, int batch, int dtype, float temperature,
                     int math_mode, void* ws, size_t ws_bytes, void* plan, size_t plan_bytes, float* loss_out,
-                    int* nonfinite, void* stream) {
+                    int* nonfinite, void* stream, const unsigned long long* rng = nullptr) {
   int rc = check_layers(layers, n_layers, batch);
   if (rc != PNCE_OK) return rc;
   if (dtype < PNCE_F32 || dtype > PNCE_BF16 || loss_out == nullptr || !(temperature > 0.f)) return PNCE_ERR_ARG;
@@ -603,6 +616,10 @@ static int fwd_impl(const pnce_layer_t* layers, int n_layers, int batch, int dty
   p.nonfinite = nonfinite;
   p.trace = g_dbg.trace;
   p.b0 = 0; p.bn = batch;
+  if (rng != nullptr) {
+    if (!tc || plan != nullptr) return PNCE_ERR_UNSUPPORTED;   // the draw rides on k_prep (tensor-core path, unplanned)
+    p.rng_draw = 1; p.rng_seed = rng[0]; p.rng_offset = rng[1];
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (tc) return forward_tc(p, st, plan != nullptr);
   rc = launch_gather(p, n_layers, st);
@@ -614,6 +631,14 @@ int pnce_fwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, flo
              int math_mode, void* ws, size_t ws_bytes, float* loss_out, int* nonfinite, void* stream) {
   return fwd_impl(layers, n_layers, batch, dtype, temperature, math_mode, ws, ws_bytes, nullptr, 0, loss_out,
                   nonfinite, stream);
+}
+
+int pnce_fwd_draw(const pnce_layer_t* layers, int n_layers, int batch, int dtype, float temperature,
+                  int math_mode, void* ws, size_t ws_bytes, unsigned long long philox_seed,
+                  unsigned long long philox_offset, float* loss_out, int* nonfinite, void* stream) {
+  const unsigned long long rng[2] = {philox_seed, philox_offset};
+  return fwd_impl(layers, n_layers, batch, dtype, temperature, math_mode, ws, ws_bytes, nullptr, 0, loss_out,
+                  nonfinite, stream, rng);
 }
 
 int pnce_fwd_planned(const pnce_layer_t* layers, int n_layers, int batch, int dtype, float temperature,
@@ -632,7 +657,8 @@ int pnce_plan_bytes(const pnce_layer_t* layers, int n_layers, size_t* bytes) {
   return PNCE_OK;
 }
 
-int pnce_plan_ids(const pnce_layer_t* layers, int n_layers, void* plan, size_t plan_bytes, void* stream) {
+static int plan_ids_impl(const pnce_layer_t* layers, int n_layers, void* plan, size_t plan_bytes, void* stream,
+                         const unsigned long long* rng) {
   int rc = check_layers(layers, n_layers, 1);
   if (rc != PNCE_OK) return rc;
   if (plan == nullptr || (reinterpret_cast<uintptr_t>(plan) & 255u)) return PNCE_ERR_WORKSPACE;
@@ -649,7 +675,49 @@ int pnce_plan_ids(const pnce_layer_t* layers, int n_layers, void* plan, size_t p
     L.C = a.C; L.HW = a.H * a.W; L.P = a.P;
   }
   carve_plan(layers, n_layers, plan, &p);
+  if (rng != nullptr) { p.rng_draw = 1; p.rng_seed = rng[0]; p.rng_offset = rng[1]; }
   return launch_prep(p, static_cast<cudaStream_t>(stream));    // counter == nullptr: nothing else is touched
+}
+
+int pnce_plan_ids(const pnce_layer_t* layers, int n_layers, void* plan, size_t plan_bytes, void* stream) {
+  return plan_ids_impl(layers, n_layers, plan, plan_bytes, stream, nullptr);
+}
+
+int pnce_plan_ids_draw(const pnce_layer_t* layers, int n_layers, unsigned long long philox_seed,
+                       unsigned long long philox_offset, void* plan, size_t plan_bytes, void* stream) {
+  const unsigned long long rng[2] = {philox_seed, philox_offset};
+  return plan_ids_impl(layers, n_layers, plan, plan_bytes, stream, rng);
+}
+
+// The draw alone (no sort): for callers that only need the ids (PatchSampleF with patch_ids=None).
+__global__ void __launch_bounds__(kThreads) k_draw_ids(const __grid_constant__ Params p) {
+  const LayerDev& L = p.L[blockIdx.x];
+  const unsigned long long off = p.rng_offset + 4ull * blockIdx.x;
+  for (int i = threadIdx.x; i < L.P; i += kThreads) {
+    curandStatePhilox4_32_10_t st;
+    curand_init(p.rng_seed, (unsigned long long)i, off, &st);
+    const uint4 r = curand4(&st);
+    const_cast<long long*>(L.ids)[i] = (long long)(r.x % (unsigned)L.HW);
+  }
+}
+
+int pnce_draw_ids(const pnce_layer_t* layers, int n_layers, unsigned long long philox_seed,
+                  unsigned long long philox_offset, void* stream) {
+  int rc = check_layers(layers, n_layers, 1);
+  if (rc != PNCE_OK) return rc;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.n_layers = n_layers;
+  p.rng_draw = 1; p.rng_seed = philox_seed; p.rng_offset = philox_offset;
+  for (int l = 0; l < n_layers; ++l) {
+    const pnce_layer_t& a = layers[l];
+    if (a.ids == nullptr || (reinterpret_cast<uintptr_t>(a.ids) & 7u)) return PNCE_ERR_ARG;
+    p.L[l].ids = reinterpret_cast<const long long*>(a.ids);
+    p.L[l].HW = a.H * a.W; p.L[l].P = a.P;
+  }
+  k_draw_ids<<<(unsigned)n_layers, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
 }
 
 static int bwd_impl(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int math_mode, void* ws,
@@ -973,7 +1041,7 @@ int pnce_rows_loss_fwd_bwd(const float* q, const float* k, int batch, int P, int
     T.qn = const_cast<float*>(q);
     T.kn = const_cast<float*>(k);
     T.dq_rows = dq_out;
-    PNCE_CUDA(cudaMemsetAsync(t.counter, 0, sizeof(unsigned), st0));
+    PNCE_CUDA(cudaMemsetAsync(t.counter, 0, 2 * sizeof(unsigned), st0));
     const long long threads = 2ll * batch * T.Ppad * (T.Cp >> 3);
     k_rows_pack<<<(unsigned)((threads + kThreads - 1) / kThreads), kThreads, 0, st0>>>(t);
     PNCE_CUDA(cudaGetLastError());
@@ -990,7 +1058,7 @@ int pnce_rows_loss_fwd_bwd(const float* q, const float* k, int batch, int P, int
   L.kn = const_cast<float*>(k);
   L.dq_rows = dq_out;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  PNCE_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned), st));
+  PNCE_CUDA(cudaMemsetAsync(p.counter, 0, 2 * sizeof(unsigned), st));
   return launch_loss_simt(p, st);
 }
 

@@ -43,13 +43,23 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
   return ok;
 }
 // Bounded wait: a protocol bug must surface as an error code, never as a hung GPU.
-// Returns false (and raises *dead) after ~2^27 cycles; once dead every later wait falls through.
+// Returns false (and raises *dead) after kMbarTimeoutNs of WALL time (%globaltimer -- an SM cycle count would also
+// run while the context is time-sliced out on a shared GPU, under MPS or a debugger, and could trip on a healthy
+// kernel); once dead every later wait falls through.  The loss kernels then write NaN into the loss (in-band, so the
+// failure is visible without the status words, e.g. in a CUDA-graph replay) and raise the timeout flag.
+constexpr unsigned long long kMbarTimeoutNs = 2000000000ull;        // 2 s; a whole step takes < 1 ms
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* dead) {
   if (mbar_try_wait(bar, parity)) return true;
-  const long long t0 = clock64();
+  const unsigned long long t0 = global_ns();
+  unsigned spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (*dead) return false;
-    if (clock64() - t0 > (1ll << 27)) {
+    if ((++spins & 255u) == 0 && global_ns() - t0 > kMbarTimeoutNs) {
       *dead = 1;
       return false;
     }

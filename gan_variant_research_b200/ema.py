@@ -88,6 +88,9 @@ class EMA:
         self.backup = {n: self._backup_flat[o:o + s].view_as(p)
                        for n, o, s, p in zip(self._names, self._offs, self._sizes, self._params)}
         self._launch(self._param_ptrs, self._shadow_ptrs, 0.0, 0.0, 1)
+        # the kernel wrote the parameters through raw pointers: tell autograd's version counters, which is what
+        # anything that caches values derived from the parameters checks (feature_reuse._params_version)
+        torch._C._increment_version(self._params)
 
     def restore(self):
         """Put the original parameters back -- :38-43."""
@@ -95,6 +98,7 @@ class EMA:
             raise KeyError("restore() without apply_shadow()")      # the reference raises KeyError on backup[name]
         self._refresh_param_table()
         self._launch(self._param_ptrs, self._backup_ptrs, 0.0, 0.0, 1)
+        torch._C._increment_version(self._params)
         self.backup = {}
 
     def state_dict(self):

@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes
 import sys
+import threading
 from typing import List, Optional, Sequence
 
 import torch
@@ -77,83 +78,103 @@ def draw_patch_ids(feat: torch.Tensor, num_patches: int) -> torch.Tensor:
     return torch.randint(0, hw, (patch_count(num_patches, hw),), device=feat.device)
 
 
-_ID_STREAMS = {}         # device index -> side stream the id draws are issued on
+_ID_STREAMS = {}         # device index -> side stream the id draw + sort are issued on
 _SIDE_STREAM_MIN_BYTES = 1 << 30
 
 
-def draw_patch_ids_all(feats, num_patches: int, want_plan: bool = False) -> List[torch.Tensor]:
-    """One ``draw_patch_ids`` per layer, in layer order (patchnce_cut.py:36-38, :63) -- issued on a
-    side stream.  The draws read nothing but the generator state, which torch advances on the HOST at
-    launch time, so the ids and the RNG stream are exactly what the reference gets; on a side stream
-    the five tiny Philox kernels run under whatever the caller's stream is still busy with (the
-    previous backward, the generator's forward) instead of sitting at the head of this step's
-    critical path (measured: 18 us of a 0.92 ms step at B=64).  While a CUDA graph is being captured
-    the draws stay on the capturing stream.  ``want_plan``: the id sort (k_prep, 8 us + two launch gaps)
-    goes to the side stream as well; ``fused_patchnce`` picks the result up."""
-    if len(feats) == 0:
-        return []
-    dev = feats[0].device
-    # small problems are bound by this Python host, not by the GPU (DESIGN.md 4.5): the stream switch would
-    # only add host time there.  ~1 GB of feature maps is where the step's GPU time passes the host's.
-    small = sum(f.numel() * f.element_size() for f in feats) < _SIDE_STREAM_MIN_BYTES
-    if not feats[0].is_cuda or small or torch.cuda.is_current_stream_capturing():
-        return [draw_patch_ids(f, num_patches) for f in feats]
-    main = torch.cuda.current_stream(dev)
+def _id_stream(dev) -> "torch.cuda.Stream":
     side = _ID_STREAMS.get(dev.index)
     if side is None:
         # high priority: its few small CTAs take the first slots that free up under a kernel that fills the GPU
         # (at equal priority they wait until that kernel's whole grid has been dispatched)
         side = _ID_STREAMS[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
-    with torch.cuda.stream(side):
-        ids = [draw_patch_ids(f, num_patches) for f in feats]
-        plan = _plan_ids_on_current_stream(feats, ids) if want_plan else None
-    main.wait_stream(side)
-    for i in ids:
-        i.record_stream(main)        # allocated on the side stream's pool, consumed on the caller's
-    if plan is not None:
-        plan.record_stream(main)
-        _PLANS[id(ids[0])] = (ids[0], plan)      # handed to fused_patchnce through the first id tensor
-    return ids
+    return side
 
 
-_PLANS = {}             # id(first id tensor) -> (that tensor, plan buffer) of the most recent side-stream draw
-_PLAN_BYTES = {}        # layer geometry -> pnce_plan_bytes
+def draw_patch_ids_all(feats, num_patches: int) -> List[torch.Tensor]:
+    """One ``draw_patch_ids`` per layer, in layer order (patchnce_cut.py:36-38, :63): the torch.randint
+    path, used while a CUDA graph is being captured (torch's graph-safe generator state), on the fp32
+    CUDA-core path and whenever the in-library draw has not been validated (``_philox_ready``)."""
+    return [draw_patch_ids(f, num_patches) for f in feats]
 
 
-def _plan_ids_on_current_stream(feats, ids) -> Optional[torch.Tensor]:
-    """k_prep (sorted ids, ranks, per-tile slot ranges of every layer) into a buffer of its own, on the
-    current -- side -- stream: like the draws it depends on nothing but the ids (include/pnce.h,
-    pnce_plan_ids).  None when the shapes are outside the tensor-core kernels' envelope."""
-    if len(feats) > _lib.MAX_LAYERS or any(f.dim() != 4 or f.shape[1] > 256 or i.numel() > 1024
-                                           for f, i in zip(feats, ids)):
-        return None
-    lib = _lib.load()
-    n = len(feats)
-    arr = (_lib.PnceLayer * n)()
-    for l, (f, i) in enumerate(zip(feats, ids)):
-        arr[l].ids = i.data_ptr()
-        arr[l].C, arr[l].H, arr[l].W, arr[l].P = f.shape[1], f.shape[2], f.shape[3], i.numel()
-    key = tuple((f.shape[1], f.shape[2], f.shape[3], i.numel()) for f, i in zip(feats, ids))
-    nbytes = _PLAN_BYTES.get(key)
-    if nbytes is None:
-        sz = ctypes.c_size_t(0)
-        _lib.check(lib.pnce_plan_bytes(arr, n, ctypes.byref(sz)), "pnce_plan_bytes")
-        nbytes = _PLAN_BYTES[key] = sz.value
+# ------------------------------------------------------------------------------------------------
+# the id draw inside the library (pnce_fwd_draw / pnce_plan_ids_draw / pnce_draw_ids, include/pnce.h)
+# ------------------------------------------------------------------------------------------------
+_PHILOX_OK = {}          # device index -> True (validated against torch.randint) / False (disabled)
+
+
+def _philox_ready(dev) -> bool:
+    """True when the library may draw the ids itself on ``dev``.  Checked ONCE per device and process: a handful
+    of ``torch.randint`` calls (sizes that exercise one- and multi-block launches) against ``pnce_draw_ids`` at the
+    same generator state, and the generator's offset bookkeeping (+4 per call).  The generator is left exactly as
+    it was found.  Any mismatch -- another torch build with another sampling law -- switches the library draw off
+    for good and the host keeps calling ``torch.randint`` like the reference does (ids stay bit-exact either way)."""
+    ok = _PHILOX_OK.get(dev.index)
+    if ok is not None:
+        return ok
+    if torch.cuda.is_current_stream_capturing():
+        return False                                  # decide later, outside the capture
+    ok = False
+    try:
+        gen = torch.cuda.default_generators[dev.index]
+        state = gen.get_state()
+        probes = [(256 * 256, 256), (64 * 64, 256), (128 * 128, 1024), (100, 100), (7, 7), (512 * 512, 300)]
+        ref = [torch.randint(0, hw, (p,), device=dev) for hw, p in probes]
+        end = gen.get_offset()
+        gen.set_state(state)
+        seed, off = gen.initial_seed(), gen.get_offset()
+        ours = [torch.empty(p, dtype=torch.int64, device=dev) for _, p in probes]
+        arr = (_lib.PnceLayer * len(probes))()
+        for l, ((hw, p), o) in enumerate(zip(probes, ours)):
+            arr[l].ids, arr[l].C, arr[l].H, arr[l].W, arr[l].P = o.data_ptr(), 1, 1, hw, p
+        with _on_device(dev):
+            _lib.check(_lib.load().pnce_draw_ids(arr, len(probes), seed, off, _stream_ptr(dev)), "pnce_draw_ids")
+        ok = end == off + 4 * len(probes) and all(torch.equal(a, b) for a, b in zip(ref, ours))
+        gen.set_state(state)
+        if not ok:
+            print("gan_variant_research_b200: torch.randint does not follow the Philox law the library draws ids "
+                  "with on this torch build; falling back to torch.randint calls (ids stay bit-exact).", file=sys.stderr)
+    except Exception as e:  # noqa: BLE001 - an unexpected generator API: stay on torch.randint
+        print(f"gan_variant_research_b200: in-library id draw disabled ({type(e).__name__}: {e})", file=sys.stderr)
+        ok = False
+    _PHILOX_OK[dev.index] = ok
+    return ok
+
+
+def draw_ids(feats, num_patches: int) -> List[torch.Tensor]:
+    """The reference's id draws for a list of maps (one per layer, layer order, patchnce_cut.py:60-63) in ONE
+    launch of the library (``pnce_draw_ids``) when the in-library draw is validated on this device, else the
+    ``torch.randint`` calls themselves.  Same ids, same generator state afterwards, either way."""
+    feats = list(feats)
+    if not feats:
+        return []
     dev = feats[0].device
-    plan = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    _lib.check(lib.pnce_plan_ids(arr, n, plan.data_ptr(), nbytes, _stream_ptr(dev)), "pnce_plan_ids")
-    return plan
+    if (not feats[0].is_cuda or any(f.device != dev for f in feats) or len(feats) > _lib.MAX_LAYERS
+            or torch.cuda.is_current_stream_capturing() or not _philox_ready(dev)):
+        return draw_patch_ids_all(feats, num_patches)
+    n = len(feats)
+    hw = [f.shape[2] * f.shape[3] for f in feats]
+    p_list = [patch_count(num_patches, x) for x in hw]
+    arr = (_lib.PnceLayer * n)()
+    with _on_device(dev):
+        ids_all = torch.empty(sum(p_list), dtype=torch.int64, device=dev)
+        ptr = ids_all.data_ptr()
+        for l in range(n):
+            arr[l].ids, arr[l].C, arr[l].H, arr[l].W, arr[l].P = ptr, 1, 1, hw[l], p_list[l]
+            ptr += 8 * p_list[l]
+        seed, off = _philox_take(dev, n)
+        _lib.check(_lib.load().pnce_draw_ids(arr, n, seed, off, _stream_ptr(dev)), "pnce_draw_ids")
+    return list(ids_all.split(p_list))
 
 
-def _take_plan(ids_list) -> Optional[torch.Tensor]:
-    """The plan buffer that belongs to exactly these id tensors, if the side-stream draw made one."""
-    if not ids_list:
-        return None
-    hit = _PLANS.pop(id(ids_list[0]), None)
-    _PLANS.clear()                                   # at most one draw is ever pending
-    if hit is None or hit[0] is not ids_list[0]:
-        return None
-    return hit[1]
+def _philox_take(dev, n_draws: int):
+    """(seed, offset) of the device's default CUDA generator, which is advanced by what ``n_draws`` randint calls
+    consume (4 each) -- the RNG stream stays aligned with the reference's training step."""
+    gen = torch.cuda.default_generators[dev.index]
+    off = gen.get_offset()
+    gen.set_offset(off + 4 * n_draws)
+    return gen.initial_seed(), off
 
 
 class _PinnedAlias:
@@ -199,7 +220,8 @@ class _WarnQueue:
     INTO PINNED HOST MEMORY (zero-copy over PCIe: pinned allocations are device-addressable under
     unified addressing), so no D2H memcpy sits on the stream between the forward and the backward
     kernels.  A ring of 64 slots, each guarded by a CUDA event recorded after the launch; a slot is
-    reused once its event has completed."""
+    reused once its event has completed.  One queue per device; a lock makes it safe to call from
+    several threads (the autograd engine's threads never touch it: only forwards do)."""
     SLOTS = 64
 
     def __init__(self):
@@ -207,76 +229,142 @@ class _WarnQueue:
         self.host = None
         self.free = []
         self.events = []
+        self.lock = threading.Lock()
 
-    def acquire(self, device):
-        """-> (slot, device-usable pointer to int32[2]) or (None, 0) while a CUDA graph is being captured."""
+    def acquire(self):
+        """-> (slot, device-usable pointer to int32[2]) or (None, 0) while a CUDA graph is being captured
+        (then the failure of a launch shows in-band: the loss is NaN, include/pnce.h)."""
         if torch.cuda.is_current_stream_capturing():
             return None, 0
-        if self.host is None:
-            self.host = torch.zeros(self.SLOTS, 2, dtype=torch.int32).pin_memory()
-            self.free = list(range(self.SLOTS))
-            self.events = [torch.cuda.Event() for _ in range(self.SLOTS)]
-        if not self.free:
-            self.poll()
-            if not self.free:                    # 64 launches in flight un-polled: wait for the oldest
-                self.pending[0][0].synchronize()
-                self.poll()
-        slot = self.free.pop()
-        self.host[slot].zero_()
-        return slot, self.host[slot].data_ptr()
+        with self.lock:
+            if self.host is None:
+                self.host = torch.zeros(self.SLOTS, 2, dtype=torch.int32).pin_memory()
+                self.base = self.host.data_ptr()
+                self.free = list(range(self.SLOTS))
+                self.events = [torch.cuda.Event() for _ in range(self.SLOTS)]
+            if not self.free:
+                self._poll(False)
+                if not self.free:                    # 64 launches in flight un-polled: wait for the oldest
+                    self.pending[0][0].synchronize()
+                    self._poll(False)
+            slot = self.free.pop()
+        # no reset needed: every launch sequence writes both words (word 1 is cleared by its first kernel, word 0
+        # is written by the loss kernel's last CTA)
+        return slot, self.base + 8 * slot
 
-    def commit(self, slot, device):
+    def commit(self, slot, stream):
         if slot is None:
             return
         ev = self.events[slot]
-        ev.record(torch.cuda.current_stream(device))
-        self.pending.append((ev, slot))
+        ev.record(stream)
+        with self.lock:
+            self.pending.append((ev, slot))
 
     def poll(self, block: bool = False) -> int:
         """Print the reference's warning for finished launches; returns images guarded so far."""
         if not self.pending or torch.cuda.is_current_stream_capturing():
             return 0                             # (cudaEventQuery is not allowed while a graph is being captured)
-        total, keep = 0, []
+        with self.lock:
+            return self._poll(block)
+
+    def _poll(self, block: bool) -> int:
+        total, keep, proto_err = 0, [], False
         for ev, slot in self.pending:
             if block:
                 ev.synchronize()
             if ev.query():
                 n, proto = int(self.host[slot, 0]), int(self.host[slot, 1])
                 self.free.append(slot)
-                if proto:
-                    raise _lib.PnceError("libpnce kernel protocol timeout (tcgen05 pipeline stalled)")
+                proto_err = proto_err or bool(proto)
                 if n:
                     print(f"Warning: NaN in PatchNCE loss. {n} (layer, image) loss(es) replaced by 0.")
                 total += n
             else:
                 keep.append((ev, slot))
         self.pending = keep
+        if proto_err:
+            raise _lib.PnceError("libpnce kernel protocol timeout (tcgen05 pipeline stalled)")
         return total
 
 
-_warnings = _WarnQueue()
+_WARN_QUEUES = {}        # device index -> _WarnQueue
+
+
+def _warn_queue(dev) -> _WarnQueue:
+    q = _WARN_QUEUES.get(dev.index)
+    if q is None:
+        q = _WARN_QUEUES.setdefault(dev.index, _WarnQueue())
+    return q
 
 
 def poll_nonfinite_warnings(block: bool = False) -> int:
-    return _warnings.poll(block)
+    return sum(q.poll(block) for q in list(_WARN_QUEUES.values()))
 
 
 # ------------------------------------------------------------------------------------------------
-# fused path: all layers, forward = 2 launches, backward = 1 launch
+# fused path: all layers, forward = 3 launches (id draw + sort | gather | logits/CE/dQ), backward = 1
 # ------------------------------------------------------------------------------------------------
-class _Plan:
-    """Everything the two C-ABI calls need that is not a differentiable input."""
+class _ShapePlan:
+    """Everything a fused call needs that depends only on the problem SHAPE (device, dtype, batch, layer
+    geometry, patch counts, math mode) -- built once and reused by every step of a training loop, so that the
+    host side of a step is a handful of pointer stores and one C call each way (small batches are bound by this
+    host path, not by the GPU: DESIGN.md 4.5).  The C-ABI layer tables are owned here; the forward table and the
+    backward table are separate objects because autograd runs ``backward`` on its own thread, and each is
+    guarded by a lock so that two Python threads sharing a shape do not interleave their pointer stores."""
 
-    def __init__(self, src_feats, ids_list, temperature, math, dp_group=None):
-        self.src_feats = src_feats
-        self.ids_list = ids_list
-        self.temperature = float(temperature)
-        self.math = math
-        self.dp_group = dp_group      # head mode: process group whose ranks average the head gradients
-        self.idplan = None            # k_prep's outputs when the id sort already ran on the side stream
+    __slots__ = ("n", "batch", "dtype", "dtype_code", "math", "math_code", "dev", "p_list", "p_total", "tc",
+                 "ws_bytes", "plan_bytes", "fwd_layers", "bwd_layers", "fwd_lock", "bwd_lock", "big", "shapes")
+
+    def __init__(self, dev, dtype, shapes, p_list, math):
+        lib = _lib.load()
+        self.n, self.batch, self.dtype, self.dev, self.math = len(shapes), shapes[0][0], dtype, dev, math
+        self.dtype_code, self.math_code = _DTYPES[dtype], _MATH[math]
+        self.shapes = shapes
+        self.p_list, self.p_total = list(p_list), sum(p_list)
+        self.fwd_layers = (_lib.PnceLayer * self.n)()
+        self.bwd_layers = (_lib.PnceLayer * self.n)()
+        for arr in (self.fwd_layers, self.bwd_layers):
+            for l, ((_, c, h, w), p) in enumerate(zip(shapes, p_list)):
+                arr[l].C, arr[l].H, arr[l].W, arr[l].P = c, h, w, p
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.pnce_workspace_bytes(self.fwd_layers, self.n, self.batch, ctypes.byref(nbytes)),
+                   "pnce_workspace_bytes")
+        self.ws_bytes = nbytes.value
+        # the tensor-core kernels' envelope (csrc/pnce_api.cu tc_shapes_ok); outside it the fp32 CUDA-core kernels run
+        self.tc = math != "simt_f32" and all(c <= 256 and p <= 1024 for (_, c, _, _), p in zip(shapes, p_list))
+        self.plan_bytes = 0
+        if self.tc:
+            _lib.check(lib.pnce_plan_bytes(self.fwd_layers, self.n, ctypes.byref(nbytes)), "pnce_plan_bytes")
+            self.plan_bytes = nbytes.value
+        # ~1 GB of feature maps is where a step's GPU time passes the host's: from there on the id draw + sort go
+        # to a side stream, under whatever the GPU is still busy with (below, the stream switch only costs host time)
+        elem = 4 if dtype == torch.float32 else 2
+        self.big = 2 * elem * sum(b * c * h * w for b, c, h, w in shapes)
+        self.fwd_lock, self.bwd_lock = threading.Lock(), threading.Lock()
 
 
-_WS_BYTES = {}      # (batch, layer shapes) -> pnce_workspace_bytes, queried once per problem shape
+_SHAPE_PLANS = {}
+
+
+def _shape_plan(tgt, p_list, math) -> _ShapePlan:
+    t0 = tgt[0]
+    key = (t0.device.index, t0.dtype, math, tuple(p_list), *[t.shape for t in tgt])
+    sp = _SHAPE_PLANS.get(key)
+    if sp is None:
+        if len(_SHAPE_PLANS) > 256:                  # a caller cycling through many shapes: do not grow without bound
+            _SHAPE_PLANS.clear()
+        sp = _SHAPE_PLANS[key] = _ShapePlan(t0.device, t0.dtype, [tuple(t.shape) for t in tgt], p_list, math)
+    return sp
+
+
+class _Call:
+    """One fused call: the shape plan plus what is not a differentiable input."""
+    __slots__ = ("sp", "src", "ids", "temperature", "rng", "idplan")
+
+    def __init__(self, sp, src, ids, temperature, rng=None, idplan=None):
+        self.sp, self.src, self.ids, self.temperature = sp, src, ids, float(temperature)
+        self.rng = rng            # (philox seed, offset): the library draws the ids itself (pnce_fwd_draw)
+        self.idplan = idplan      # k_prep's outputs when the id draw + sort already ran on the side stream
 
 
 def _layer_array(src, tgt, dtgt, ids):
@@ -294,87 +382,94 @@ def _layer_array(src, tgt, dtgt, ids):
 
 class _FusedPatchNCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan: _Plan, *tgt_feats):
+    def forward(ctx, call: _Call, *tgt_feats):
         lib = _lib.load()
-        tgt = [t.detach() for t in tgt_feats]
-        src, ids = plan.src_feats, plan.ids_list
-        dev = tgt[0].device
-        batch = tgt[0].shape[0]
-        n = len(tgt)
-        dtype = _DTYPES[tgt[0].dtype]
-        layers = _layer_array(src, tgt, None, ids)
-        key = (batch, tuple((t.shape[1], t.shape[2], t.shape[3], i.numel()) for t, i in zip(tgt, ids)))
-        ws_bytes = _WS_BYTES.get(key)
-        if ws_bytes is None:
-            nbytes = ctypes.c_size_t(0)
-            _lib.check(lib.pnce_workspace_bytes(layers, n, batch, ctypes.byref(nbytes)), "pnce_workspace_bytes")
-            ws_bytes = _WS_BYTES[key] = nbytes.value
+        sp = call.sp
+        dev = sp.dev
+        n = sp.n
         with _on_device(dev):
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            ws = torch.empty(sp.ws_bytes, dtype=torch.uint8, device=dev)
             out = torch.empty(1 + n, dtype=torch.float32, device=dev)
-            slot, flag_ptr = _warnings.acquire(dev)           # both words are written by the kernels
-            if plan.idplan is None:
-                _lib.check(lib.pnce_fwd(layers, n, batch, dtype, plan.temperature, _MATH[plan.math],
-                                        ws.data_ptr(), ws_bytes, out.data_ptr(), flag_ptr or None,
-                                        _stream_ptr(dev)), "pnce_fwd")
-            else:
-                _lib.check(lib.pnce_fwd_planned(layers, n, batch, dtype, plan.temperature, _MATH[plan.math],
-                                                ws.data_ptr(), ws_bytes, plan.idplan.data_ptr(),
-                                                plan.idplan.numel(), out.data_ptr(), flag_ptr or None,
-                                                _stream_ptr(dev)), "pnce_fwd_planned")
-            _warnings.commit(slot, dev)
+            wq = _warn_queue(dev)
+            slot, flag_ptr = wq.acquire()                     # both words are written by the kernels
+            stream = torch.cuda.current_stream(dev)
+            st = stream.cuda_stream
+            with sp.fwd_lock:
+                layers = sp.fwd_layers
+                for l in range(n):
+                    a = layers[l]
+                    a.src, a.tgt, a.ids = call.src[l].data_ptr(), tgt_feats[l].data_ptr(), call.ids[l].data_ptr()
+                if call.rng is not None:
+                    rc = lib.pnce_fwd_draw(layers, n, sp.batch, sp.dtype_code, call.temperature, sp.math_code,
+                                           ws.data_ptr(), sp.ws_bytes, call.rng[0], call.rng[1], out.data_ptr(),
+                                           flag_ptr or None, st)
+                elif call.idplan is None:
+                    rc = lib.pnce_fwd(layers, n, sp.batch, sp.dtype_code, call.temperature, sp.math_code,
+                                      ws.data_ptr(), sp.ws_bytes, out.data_ptr(), flag_ptr or None, st)
+                else:
+                    rc = lib.pnce_fwd_planned(layers, n, sp.batch, sp.dtype_code, call.temperature, sp.math_code,
+                                              ws.data_ptr(), sp.ws_bytes, call.idplan.data_ptr(),
+                                              call.idplan.numel(), out.data_ptr(), flag_ptr or None, st)
+            if rc != 0:
+                _lib.check(rc, "pnce_fwd")
+            wq.commit(slot, stream)
         # the workspace goes through save_for_backward: autograd then frees it with the graph, right after
         # backward() -- kept as a plain ctx attribute it lived as long as the loss tensor did, and a caller that
         # holds on to the loss across steps (loss = step()) made every step allocate a second 0.26 GB workspace
         ctx.save_for_backward(ws)
-        ctx.plan, ctx.ws_bytes = plan, ws_bytes
-        ctx.layers = layers              # the backward only fills in the dtgt pointers
-        ctx.tgt_meta = [(t.shape, t.dtype) for t in tgt]
-        ctx.tgt_keep = tgt               # shapes only matter, but keeps data_ptrs stable for the struct
-        ctx.dev, ctx.batch, ctx.dtype = dev, batch, dtype
+        ctx.call = call
+        ctx.tgt_keep = tgt_feats          # shapes / dtypes of the gradients to allocate
         ctx.layer_losses = out[1:]
-        return out.narrow(0, 0, 1).reshape(())
+        return out[0]
 
     @staticmethod
     def backward(ctx, grad_out):
         lib = _lib.load()
-        dev = ctx.dev
-        g = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous()
+        call = ctx.call
+        sp = call.sp
+        dev = sp.dev
+        g = grad_out
+        if g.dtype != torch.float32 or g.device != dev or not g.is_contiguous():
+            g = g.detach().to(device=dev, dtype=torch.float32).contiguous()
         (ws,) = ctx.saved_tensors
         with _on_device(dev):
-            grads = [torch.empty(shape, dtype=dt, device=dev) for shape, dt in ctx.tgt_meta]
-            layers = ctx.layers
-            for l, gl in enumerate(grads):
-                layers[l].dtgt = gl.data_ptr()
-            if ctx.plan.idplan is None:
-                _lib.check(lib.pnce_bwd(layers, len(grads), ctx.batch, ctx.dtype, _MATH[ctx.plan.math],
-                                        ws.data_ptr(), ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev)),
-                           "pnce_bwd")
-            else:
-                _lib.check(lib.pnce_bwd_planned(layers, len(grads), ctx.batch, ctx.dtype, _MATH[ctx.plan.math],
-                                                ws.data_ptr(), ctx.ws_bytes, ctx.plan.idplan.data_ptr(),
-                                                ctx.plan.idplan.numel(), g.data_ptr(), _stream_ptr(dev)),
-                           "pnce_bwd_planned")
+            grads = [torch.empty_like(t) for t in ctx.tgt_keep]
+            st = _stream_ptr(dev)
+            with sp.bwd_lock:
+                layers = sp.bwd_layers
+                for l in range(sp.n):
+                    layers[l].dtgt = grads[l].data_ptr()
+                if call.idplan is None:
+                    rc = lib.pnce_bwd(layers, sp.n, sp.batch, sp.dtype_code, sp.math_code, ws.data_ptr(),
+                                      sp.ws_bytes, g.data_ptr(), st)
+                else:
+                    rc = lib.pnce_bwd_planned(layers, sp.n, sp.batch, sp.dtype_code, sp.math_code, ws.data_ptr(),
+                                              sp.ws_bytes, call.idplan.data_ptr(), call.idplan.numel(),
+                                              g.data_ptr(), st)
+            if rc != 0:
+                _lib.check(rc, "pnce_bwd")
         return (None, *grads)
 
 
 def _prepare_maps(src_feats, tgt_feats):
-    if len(src_feats) != len(tgt_feats):
-        # the reference zips and silently truncates (:36) but divides by len(src_feats) (:40)
-        n = min(len(src_feats), len(tgt_feats))
-        tgt_feats = list(tgt_feats)[:n]
-        src_trunc = list(src_feats)[:n]
-    else:
-        src_trunc = list(src_feats)
-    if len(src_trunc) == 0:
-        raise ZeroDivisionError("division by zero")      # what `total_loss / len(src_feats)` raises (:40)
-    if len(src_trunc) > _lib.MAX_LAYERS:
+    """The reference's argument handling (patchnce_cut.py:25-40) plus what the C ABI needs: CUDA tensors,
+    (B, C, H, W), src/tgt of equal shape, contiguous NCHW.  Returns (src, tgt, len(src_feats))."""
+    n_src = len(src_feats)
+    n = min(n_src, len(tgt_feats))                   # the reference zips and silently truncates (:36) ...
+    if n_src == 0:
+        raise ZeroDivisionError("division by zero")  # ... but divides by len(src_feats) (:40)
+    if n == 0:
+        raise RuntimeError("no target feature maps")
+    if n > _lib.MAX_LAYERS:
         raise RuntimeError(f"at most {_lib.MAX_LAYERS} nce layers per call")
     src, tgt = [], []
-    for s, t in zip(src_trunc, tgt_feats):
-        _require_cuda(t, "tgt_feat")
-        _require_cuda(s, "src_feat")
-        if s.dim() != 4 or t.dim() != 4:
+    for l in range(n):
+        s, t = src_feats[l], tgt_feats[l]
+        if not t.is_cuda:
+            _require_cuda(t, "tgt_feat")
+        if not s.is_cuda:
+            _require_cuda(s, "src_feat")
+        if t.dim() != 4 or s.dim() != 4:
             raise ValueError("not enough values to unpack (expected 4): feature maps must be (B, C, H, W)")
         if s.shape != t.shape:
             raise RuntimeError(f"src/tgt feature shapes differ: {tuple(s.shape)} vs {tuple(t.shape)}")
@@ -382,9 +477,26 @@ def _prepare_maps(src_feats, tgt_feats):
             raise RuntimeError(f"unsupported feature dtype {t.dtype}")
         if s.dtype != t.dtype:
             s = s.to(t.dtype)
-        src.append(s.detach().contiguous())
-        tgt.append(t.contiguous())
-    return src, tgt, len(src_feats)
+        if s.requires_grad:
+            s = s.detach()
+        src.append(s if s.is_contiguous() else s.contiguous())
+        tgt.append(t if t.is_contiguous() else t.contiguous())
+    return src, tgt, n_src
+
+
+def _uniform(tgt) -> bool:
+    """One C-ABI call covers every layer only if they share batch size, dtype and device (the reference treats
+    each layer on its own, patchnce_cut.py:36-38, so mixed lists are valid input there)."""
+    t0 = tgt[0]
+    for t in tgt:
+        if t.shape[0] != t0.shape[0] or t.dtype != t0.dtype or t.device != t0.device:
+            return False
+    return True
+
+
+def _fused_call(src, tgt, ids, temperature, math, rng=None, idplan=None):
+    sp = _shape_plan(tgt, [i.numel() for i in ids], math)
+    return _FusedPatchNCE.apply(_Call(sp, src, ids, temperature, rng, idplan), *tgt)
 
 
 def fused_patchnce(src_feats, tgt_feats, ids_list, temperature=0.07, math: Optional[str] = None,
@@ -392,19 +504,24 @@ def fused_patchnce(src_feats, tgt_feats, ids_list, temperature=0.07, math: Optio
     """All-layer PatchNCE on dense NCHW maps with given ids.  Returns the scalar loss tensor
     (fp32, on device, differentiable w.r.t. every ``tgt_feats[l]`` that requires grad)."""
     src, tgt, n_src = _prepare_maps(src_feats, tgt_feats)
-    ids = []
-    for i, t in zip(ids_list, tgt):
-        _require_cuda(i, "patch_ids")
-        ids.append(i.to(torch.int64).contiguous())
-        if ids[-1].numel() > _lib.MAX_PATCHES:
-            raise RuntimeError(f"num_patches > {_lib.MAX_PATCHES} is not supported")
-    plan = _Plan(src, ids, temperature, math or DEFAULT_MATH)
-    idplan = _take_plan(ids_list)
-    if idplan is not None and all(a is b for a, b in zip(ids, ids_list)) and plan.math != "simt_f32":
-        plan.idplan = idplan
-    loss = _FusedPatchNCE.apply(plan, *tgt)
     n = len(tgt)
+    if len(ids_list) < n:
+        raise RuntimeError(f"{len(ids_list)} id tensors for {n} layers")
+    ids = []
+    for i in list(ids_list)[:n]:
+        _require_cuda(i, "patch_ids")
+        if i.dtype != torch.int64 or not i.is_contiguous():
+            i = i.to(torch.int64).contiguous()
+        if i.numel() > _lib.MAX_PATCHES:
+            raise RuntimeError(f"num_patches > {_lib.MAX_PATCHES} is not supported")
+        ids.append(i)
+    math = math or DEFAULT_MATH
     denom = n_src if denom_layers is None else denom_layers
+    if _uniform(tgt):
+        loss = _fused_call(src, tgt, ids, temperature, math)
+    else:
+        # layers of different batch size / dtype: one call per layer, summed like the reference's loop (:36-40)
+        loss = sum(_fused_call([s], [t], [i], temperature, math) for s, t, i in zip(src, tgt, ids)) / float(n)
     if denom != n:                       # zip truncation case: kernel divided by n, reference by len(src)
         loss = loss * (float(n) / float(denom))
     return loss
@@ -432,13 +549,55 @@ class PatchNCELoss(nn.Module):
     def forward(self, a, b, batch_size: Optional[int] = None):
         if isinstance(a, torch.Tensor) and a.dim() == 2:
             return rows_patchnce(a, b, self.temperature, self.num_patches, batch_size, self.math)
-        src_feats, tgt_feats = list(a), list(b)
-        _warnings.poll()
-        n = min(len(src_feats), len(tgt_feats))
-        ids = draw_patch_ids_all(src_feats[:n], self.num_patches,                      # :60-63
-                                 want_plan=(self.math or DEFAULT_MATH) != "simt_f32")
+        src, tgt, n_src = _prepare_maps(a, b)
+        n = len(tgt)
+        dev = tgt[0].device
+        _warn_queue(dev).poll()
+        math = self.math or DEFAULT_MATH
+        if not _uniform(tgt):
+            ids = draw_patch_ids_all(src, self.num_patches)                           # :60-63
+            self.last_patch_ids = ids
+            return fused_patchnce(src, tgt, ids, self.temperature, math, denom_layers=n_src)
+        p_list = [patch_count(self.num_patches, t.shape[2] * t.shape[3]) for t in tgt]    # :60
+        if max(p_list) > _lib.MAX_PATCHES:
+            raise RuntimeError(f"num_patches > {_lib.MAX_PATCHES} is not supported")
+        sp = _shape_plan(tgt, p_list, math)
+        rng = idplan = None
+        if sp.tc and not torch.cuda.is_current_stream_capturing() and _philox_ready(dev):
+            # the library draws the ids (bit for bit torch.randint's, :63) inside its id-sort launch: no randint
+            # launches, and the generator is advanced by exactly what they would have consumed
+            if sp.big < _SIDE_STREAM_MIN_BYTES:
+                with _on_device(dev):
+                    ids_all = torch.empty(sp.p_total, dtype=torch.int64, device=dev)
+                rng = _philox_take(dev, n)
+            else:
+                # draw + sort on a high-priority side stream: they depend on nothing but the generator state, so they
+                # run under whatever the caller's stream is still busy with (in a steady loop, the previous step's
+                # dense kernel) instead of at the head of this step's critical path
+                main, side = torch.cuda.current_stream(dev), _id_stream(dev)
+                seed, off = _philox_take(dev, n)
+                with torch.cuda.stream(side):
+                    ids_all = torch.empty(sp.p_total, dtype=torch.int64, device=dev)
+                    idplan = torch.empty(sp.plan_bytes, dtype=torch.uint8, device=dev)
+                    with sp.fwd_lock:
+                        layers = sp.fwd_layers
+                        ptr = ids_all.data_ptr()
+                        for l in range(n):
+                            layers[l].ids = ptr
+                            ptr += 8 * p_list[l]
+                        _lib.check(_lib.load().pnce_plan_ids_draw(layers, n, seed, off, idplan.data_ptr(), sp.plan_bytes,
+                                                                  side.cuda_stream), "pnce_plan_ids_draw")
+                main.wait_stream(side)
+                ids_all.record_stream(main)      # allocated on the side stream's pool, consumed on the caller's
+                idplan.record_stream(main)
+            ids = list(ids_all.split(p_list))
+        else:
+            ids = draw_patch_ids_all(src, self.num_patches)                           # :60-63
         self.last_patch_ids = ids
-        return fused_patchnce(src_feats, tgt_feats, ids, self.temperature, self.math)
+        loss = _FusedPatchNCE.apply(_Call(sp, src, ids, self.temperature, rng, idplan), *tgt)
+        if n_src != n:                       # zip truncation: the kernel divided by n, the reference by len(src_feats) (:40)
+            loss = loss * (float(n) / float(n_src))
+        return loss
 
 
 def compute_patchnce_loss(generator, src_images, tgt_images, nce_layers, temperature=0.07,
@@ -575,6 +734,9 @@ class _SampleAllFn(torch.autograd.Function):
         return (None, None, *dfeats, *([None] * n))
 
 
+_ROWS_WS_BYTES = {}      # (batch, P, D) -> pnce_rows_loss_workspace_bytes, queried once per shape
+
+
 class _RowsLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, batch, p, temperature, math):
@@ -583,24 +745,25 @@ class _RowsLossFn(torch.autograd.Function):
         kk = k.detach().to(torch.float32).contiguous()
         d = qq.shape[1]
         dev = qq.device
-        key = ("rows", batch, p, d)
-        ws_bytes = _WS_BYTES.get(key)
+        key = (batch, p, d)
+        ws_bytes = _ROWS_WS_BYTES.get(key)
         if ws_bytes is None:
             nbytes = ctypes.c_size_t(0)
             _lib.check(lib.pnce_rows_loss_workspace_bytes(batch, p, d, ctypes.byref(nbytes)),
                        "pnce_rows_loss_workspace_bytes")
-            ws_bytes = _WS_BYTES[key] = nbytes.value
+            ws_bytes = _ROWS_WS_BYTES[key] = nbytes.value
         nbytes = ctypes.c_size_t(ws_bytes)
         with _on_device(dev):
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
             out = torch.empty(2, dtype=torch.float32, device=dev)
-            slot, flag_ptr = _warnings.acquire(dev)
+            wq = _warn_queue(dev)
+            slot, flag_ptr = wq.acquire()
             dq = torch.empty_like(qq)
             _lib.check(lib.pnce_rows_loss_fwd_bwd(qq.data_ptr(), kk.data_ptr(), batch, p, d, temperature,
                                                   _MATH[math], ws.data_ptr(), nbytes.value, out.data_ptr(),
                                                   flag_ptr or None, dq.data_ptr(), None, _stream_ptr(dev)),
                        "pnce_rows_loss_fwd_bwd")
-            _warnings.commit(slot, dev)
+            wq.commit(slot, torch.cuda.current_stream(dev))
         ctx.save_for_backward(dq)
         ctx.q_dtype = q.dtype
         return out.narrow(0, 0, 1).reshape(())
@@ -667,7 +830,7 @@ class PatchSampleF(nn.Module):
         if patch_ids is not None:
             return_ids = [patch_ids[k].to(device=f.device, dtype=torch.int64).contiguous() for k, f in enumerate(feats)]
         else:
-            return_ids = [draw_patch_ids(f, num_patches) for f in feats]
+            return_ids = draw_ids(feats, num_patches)
         same = all(f.shape[0] == feats[0].shape[0] and f.dtype == feats[0].dtype and f.device == feats[0].device
                    for f in feats)
         if same and 0 < len(feats) <= _lib.MAX_LAYERS and feats[0].dtype in _DTYPES:
@@ -682,6 +845,15 @@ class PatchSampleF(nn.Module):
                 rows = torch.nn.functional.normalize(mlp(rows), dim=1, eps=NORM_EPS)
             return_feats.append(rows)
         return return_feats, return_ids
+
+
+class _HeadCall:
+    """What the two fused head calls need that is not a differentiable input."""
+    __slots__ = ("src_feats", "ids_list", "temperature", "math", "dp_group")
+
+    def __init__(self, src_feats, ids_list, temperature, math, dp_group=None):
+        self.src_feats, self.ids_list, self.temperature, self.math = src_feats, ids_list, float(temperature), math
+        self.dp_group = dp_group      # process group whose ranks average the head gradients (None: single process)
 
 
 class _FusedHeadPatchNCE(torch.autograd.Function):
@@ -711,11 +883,12 @@ class _FusedHeadPatchNCE(torch.autograd.Function):
         with torch.cuda.device(dev):
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
             out = torch.empty(1 + n, dtype=torch.float32, device=dev)
-            slot, flag_ptr = _warnings.acquire(dev)
+            wq = _warn_queue(dev)
+            slot, flag_ptr = wq.acquire()
             _lib.check(lib.pnce_head_fwd(layers, heads, n, batch, dtype, nc, plan.temperature, _MATH[plan.math],
                                          ws.data_ptr(), nbytes.value, out.data_ptr(), flag_ptr or None,
                                          _stream_ptr(dev)), "pnce_head_fwd")
-            _warnings.commit(slot, dev)
+            wq.commit(slot, torch.cuda.current_stream(dev))
         ctx.save_for_backward(ws)            # freed with the graph, right after backward() (see _FusedPatchNCE)
         ctx.plan, ctx.ws_bytes, ctx.nc = plan, nbytes.value, nc
         ctx.tgt_keep, ctx.params = tgt, params
@@ -808,8 +981,10 @@ def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0
     if not netF.mlp_init:
         netF.create_mlp(tgt_feats)
     src, tgt, _ = _prepare_maps(src_feats, tgt_feats)
+    if not _uniform(tgt):
+        raise RuntimeError("fused head: every layer must share batch size, dtype and device (use fused=False)")
     if patch_ids is None:
-        ids = draw_patch_ids_all(tgt, num_patches)
+        ids = draw_ids(tgt, num_patches)
     else:
         ids = [i.to(device=t.device, dtype=torch.int64).contiguous() for i, t in zip(patch_ids, tgt)]
     params = []
@@ -819,8 +994,8 @@ def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0
     if dp_group is not None:
         from . import dp
         dp_group = dp.resolve_group(dp_group)          # None when not initialised or world size 1
-    plan = _Plan(src, ids, temperature, math or DEFAULT_MATH, dp_group)
-    _warnings.poll()
+    plan = _HeadCall(src, ids, temperature, math or DEFAULT_MATH, dp_group)
+    _warn_queue(tgt[0].device).poll()
     loss = _FusedHeadPatchNCE.apply(plan, netF.nc, *tgt, *params)
     return loss, ids
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PNCE_ABI_VERSION 2
+#define PNCE_ABI_VERSION 3
 #define PNCE_MAX_LAYERS 8      /* nce_layers per call (reference config uses 5 ids -> 4 maps)   */
 #define PNCE_MAX_PATCHES 4096  /* P = min(num_patches, H*W)  patchnce_cut.py:60; argument check only: the
                                 * kernels take P <= 1024 (tensor cores, C <= 256) or P <= 1280 (fp32 CUDA cores),
@@ -76,7 +76,8 @@ int pnce_workspace_bytes(const pnce_layer_t* layers, int n_layers, int batch, si
  *   dev_loss_out : float[1 + n_layers]  -> [0] total loss, [1+l] layer losses
  *   dev_nonfinite: int[2]               -> [0] number of (layer,image) pairs whose loss was replaced
  *                                          by 0 (the reference prints a warning for each, :98);
- *                                          [1] internal kernel-protocol timeout flag (must read 0) */
+ *                                          [1] internal kernel-protocol timeout flag (must read 0; when it is
+ *                                          raised dev_loss_out[0] is NaN as well, so the failure is visible in-band) */
 int pnce_fwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, float temperature,
              int math_mode, void* dev_workspace, size_t workspace_bytes, float* dev_loss_out,
              int* dev_nonfinite, void* stream);
@@ -95,6 +96,26 @@ int pnce_fwd_planned(const pnce_layer_t* layers, int n_layers, int batch, int dt
 int pnce_bwd_planned(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int math_mode,
                      void* dev_workspace, size_t workspace_bytes, void* dev_plan, size_t plan_bytes,
                      const float* dev_grad_out, void* stream);
+
+/* The id draw of patchnce_cut.py:60-63 done BY THE LIBRARY, inside the id-sort launch: layers[l].ids must point to
+ * WRITABLE int64[P] buffers and receives, for l = 0, 1, ..., exactly what l-th call of
+ *     torch.randint(0, H*W, (P,), device='cuda')
+ * returns when the CUDA generator's Philox state is (philox_seed, philox_offset): ATen's random_from_to kernel gives
+ * element i the first 32-bit word of Philox4x32-10(key = seed, subsequence = i, counter = offset / 4) modulo H*W, and
+ * every call advances the offset by 4 -- so layer l draws at philox_offset + 4 l and the CALLER advances its generator
+ * by 4 * n_layers (torch: gen.set_offset(gen.get_offset() + 4 * n)) to keep the RNG stream aligned with the reference's
+ * training step.  Saves the n_layers randint launches (and their host time) per step; the Python host validates the
+ * law against torch.randint once per process and falls back to calling torch.randint if it ever stops holding.
+ *   pnce_fwd_draw      : pnce_fwd with the draw (tensor-core math modes; PNCE_ERR_UNSUPPORTED otherwise)
+ *   pnce_plan_ids_draw : pnce_plan_ids with the draw (then pnce_fwd_planned / pnce_bwd_planned)
+ *   pnce_draw_ids      : the draw alone (only layers[l].ids, H, W, P are read)                                */
+int pnce_fwd_draw(const pnce_layer_t* layers, int n_layers, int batch, int dtype, float temperature,
+                  int math_mode, void* dev_workspace, size_t workspace_bytes, unsigned long long philox_seed,
+                  unsigned long long philox_offset, float* dev_loss_out, int* dev_nonfinite, void* stream);
+int pnce_plan_ids_draw(const pnce_layer_t* layers, int n_layers, unsigned long long philox_seed,
+                       unsigned long long philox_offset, void* dev_plan, size_t plan_bytes, void* stream);
+int pnce_draw_ids(const pnce_layer_t* layers, int n_layers, unsigned long long philox_seed,
+                  unsigned long long philox_offset, void* stream);
 
 /* Backward: writes every layers[l].dtgt densely (zero off the sampled positions, duplicate ids
  * accumulated) scaled by the upstream gradient *dev_grad_out (NULL = 1.0).  `math_mode` and the

@@ -79,8 +79,9 @@ def d_hinge_np(real, fake):
     """(loss, [d real], [d fake]) of discriminator_hinge_loss, adv_hinge.py:6-32."""
     s = len(real)
     loss = sum(0.5 * (np.maximum(1 - r, 0).mean() + np.maximum(1 + f, 0).mean()) for r, f in zip(real, fake)) / s
-    dr = [np.where(r < 1, -0.5 / (s * r.size), 0.0) for r in real]
-    df = [np.where(f > -1, 0.5 / (s * f.size), 0.0) for f in fake]
+    # torch.relu: NaN propagates in the forward (np.maximum does the same) and its backward passes the gradient at NaN
+    dr = [np.where(~(r >= 1), -0.5 / (s * r.size), 0.0) for r in real]
+    df = [np.where(~(f <= -1), 0.5 / (s * f.size), 0.0) for f in fake]
     return float(loss), dr, df
 
 

@@ -79,6 +79,21 @@ def main():
     out["hinge:g_loss"] = np.float64(lg.item())
     for i in range(2):
         out[f"hinge:g_dfake{i}"] = fake[i].grad.numpy().copy()
+    # non-finite discriminator outputs (a diverged D): torch.relu propagates NaN, so d_loss is NaN and train_step's
+    # check raises (train_cutpp.py:326-329); relu's backward lets the upstream gradient through at a NaN input
+    realn = [torch.randn(2, 1, 4, 4, generator=g), torch.randn(2, 1, 3, 3, generator=g)]
+    faken = [torch.randn(2, 1, 4, 4, generator=g), torch.randn(2, 1, 3, 3, generator=g)]
+    realn[0].view(-1)[3] = float("nan")
+    faken[1].view(-1)[5] = float("nan")
+    faken[0].view(-1)[1] = float("inf")
+    realn = [t.requires_grad_() for t in realn]
+    faken = [t.requires_grad_() for t in faken]
+    ldn = discriminator_hinge_loss(realn, faken)
+    (ldn * 3.0).backward()
+    out["hinge_nan:d_loss"] = np.float64(ldn.item())
+    for i in range(2):
+        out[f"hinge_nan:real{i}"] = realn[i].detach().numpy(); out[f"hinge_nan:fake{i}"] = faken[i].detach().numpy()
+        out[f"hinge_nan:d_dreal{i}"] = realn[i].grad.numpy().copy(); out[f"hinge_nan:d_dfake{i}"] = faken[i].grad.numpy().copy()
     np.savez_compressed(os.path.join(OUT, "dside_reference.npz"), **out)
     print("wrote dside_reference.npz with", len(out), "arrays")
 

@@ -27,7 +27,12 @@ def test_header_symbols_are_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in pnce.h but not exported"
     assert sorted(_lib.EXPORTS) == declared
-    assert lib.pnce_abi_version() == 2
+    # ... and nothing else leaves the library: no experiment hooks (pnce_debug_*), no kernel launch stubs
+    import subprocess
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True)
+    exported = sorted(line.split()[-1] for line in nm.stdout.splitlines() if line.split()[1:2] and line.split()[1] in "TDBRW")
+    assert exported == declared, sorted(set(exported) ^ set(declared))
+    assert lib.pnce_abi_version() == _lib.ABI_VERSION
 
 
 def test_ctypes_struct_matches_header_layout():

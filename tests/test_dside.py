@@ -63,6 +63,36 @@ def test_hinge_oracle_matches_the_reference_fixture():
         close(3.0 * df[i], d[f"hinge:g_dfake{i}"], 1e-6)
 
 
+def test_hinge_oracle_propagates_nonfinite_scores_like_the_reference():
+    """A diverged discriminator (NaN / Inf scores): d_loss must be NaN so that train_step's check raises
+    (train_cutpp.py:326-329); relu's backward passes the gradient at a NaN input (fixture from the reference)."""
+    from oracle import dside_oracle as orc
+    d = np.load(GOLD)
+    real = [d[f"hinge_nan:real{i}"].astype(np.float64) for i in range(2)]
+    fake = [d[f"hinge_nan:fake{i}"].astype(np.float64) for i in range(2)]
+    with np.errstate(invalid="ignore"):
+        loss, dr, df = orc.d_hinge_np(real, fake)
+    assert np.isnan(loss) and np.isnan(float(d["hinge_nan:d_loss"]))
+    for i in range(2):
+        close(3.0 * dr[i], d[f"hinge_nan:d_dreal{i}"], 1e-6); close(3.0 * df[i], d[f"hinge_nan:d_dfake{i}"], 1e-6)
+
+
+@pytest.mark.gpu
+def test_cuda_hinge_propagates_nonfinite_scores_like_the_reference():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import gan_variant_research_b200 as pn
+    d = np.load(GOLD)
+    real = [_dev(d[f"hinge_nan:real{i}"], torch.float32).requires_grad_() for i in range(2)]
+    fake = [_dev(d[f"hinge_nan:fake{i}"], torch.float32).requires_grad_() for i in range(2)]
+    ld = pn.discriminator_hinge_loss(real, fake)
+    (ld * 3.0).backward()
+    assert np.isnan(ld.item())
+    for i in range(2):
+        close(real[i].grad.cpu().numpy(), d[f"hinge_nan:d_dreal{i}"], 2e-6, "d real")
+        close(fake[i].grad.cpu().numpy(), d[f"hinge_nan:d_dfake{i}"], 2e-6, "d fake")
+
+
 def test_policy_validation_and_cpu_tensors_fail_loudly():
     import gan_variant_research_b200 as pn
     with pytest.raises(NotImplementedError):

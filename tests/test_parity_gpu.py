@@ -134,6 +134,44 @@ def test_patch_ids_bit_exact_and_rng_stream_aligned(pn, orc):
     assert torch.equal(after_side, after_want)
 
 
+def test_library_id_draw_follows_torch_randint_bit_for_bit(pn):
+    """pnce_draw_ids / pnce_fwd_draw draw the ids inside the library: for any seed, any generator offset and any
+    (H*W, P) they must be exactly what the reference's ``torch.randint(0, HW, (P,), device=...)`` calls return
+    (patchnce_cut.py:63), and the generator must end up where those calls would have left it."""
+    from gan_variant_research_b200 import patchnce as pmod
+    dev = torch.device("cuda", torch.cuda.current_device())
+    assert pmod._philox_ready(dev), "the in-library draw was rejected on this torch build (host fell back to randint)"
+    cases = [(256 * 256, 256), (64 * 64, 256), (128 * 128, 256), (512 * 512, 1024), (128 * 128, 1024), (9, 9), (1, 1),
+             (300, 256), (1 << 20, 4096)]
+    for seed in (0, 7, 1234567891011, 2 ** 63 - 5):
+        torch.manual_seed(seed)
+        torch.rand(3 + seed % 5, device=dev)                       # some offset into the stream
+        state = torch.cuda.get_rng_state(dev)
+        want = [torch.randint(0, hw, (p,), device=dev) for hw, p in cases[:8]]
+        after_want = torch.rand(5, device=dev)
+        torch.cuda.set_rng_state(state, dev)
+        feats = [torch.empty(1, 1, 1, hw, device=dev) for hw, _ in cases[:8]]
+        got = []
+        for f, (_, p) in zip(feats, cases[:8]):                    # P differs per layer: one call each
+            got += pn.draw_ids([f], p)
+        after_got = torch.rand(5, device=dev)
+        for g, w in zip(got, want):
+            assert g.dtype == torch.int64 and torch.equal(g, w)
+        assert torch.equal(after_got, after_want)
+        # several layers in one launch
+        torch.cuda.set_rng_state(state, dev)
+        want8 = [torch.randint(0, hw, (min(256, hw),), device=dev) for hw, _ in cases]
+        torch.cuda.set_rng_state(state, dev)
+        got8 = pn.draw_ids([torch.empty(1, 1, 1, hw, device=dev) for hw, _ in cases[:8]], 256)
+        assert all(torch.equal(g, w) for g, w in zip(got8, want8))
+    # P = 4096 spans 16 blocks of torch's launch
+    torch.manual_seed(3)
+    w = torch.randint(0, 1 << 20, (4096,), device=dev)
+    torch.manual_seed(3)
+    (g,) = pn.draw_ids([torch.empty(1, 1, 1024, 1024, device=dev)], 4096)
+    assert torch.equal(g, w)
+
+
 @pytest.mark.parametrize("math", ["simt_f32", "tc_bf16x3"])
 @pytest.mark.parametrize("b", [1, 2])
 def test_survey_tripwire_full_size(pn, b, math):
@@ -565,7 +603,6 @@ def test_side_stream_id_plan_gives_identical_results(pn, orc):
     try:
         torch.manual_seed(9)
         lb = crit(src, tgt_b)
-        assert pmod._PLANS == {}                       # the plan was picked up by the fused call
         (lb * 2.0).backward()
     finally:
         pmod._SIDE_STREAM_MIN_BYTES = keep
