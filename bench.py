@@ -7,9 +7,13 @@
 
 A step = id draw + gather + normalise + logits + diagonal CE + full backward to the dense
 d tgt_feat of every layer, for one batch of synthetic feature maps; the
-generator passes are not part of the metric.  Prints ONE JSON line on rank 0.  Secondary objects on that line
-(measured AFTER the timed region, N=1 only): head_mode, module_split, next_rows (the optimiser-side and D-side pieces
-of SURVEY.md 8f), e2e, cpu_baseline.
+generator passes are not part of the metric.  Prints ONE JSON line on rank 0.  Secondary objects on that line, all
+measured AFTER the timed region:
+  at every N : head_mode (netF head, its gradient all-reduce INSIDE the timed steps when N > 1), strong (global batch
+               64 sharded over the N ranks: strong scaling), nccl_selfcheck (N > 1: data-parallel head gradients
+               against the full batch on one rank), e2e
+  at N = 1   : configs (B = 1, B = 16, fp16 maps: BASELINE configs 1-3 and the AMP regime), module_split, next_rows
+               (the optimiser-side and D-side pieces of SURVEY.md 8f), cpu_baseline.
 """
 import argparse
 import gc
@@ -226,7 +230,9 @@ def run_reference(args):
     n_patches = b * sum(min(args.patches, h * w) for _, h, w, _ in layers)
     value = n_patches * args.steps / dt
     sample = (f"each step = B={b} images of the workload (reference backward is O(B^2), full B={args.batch} "
-              f"would take minutes per step), all {cores} host threads, fp32")
+              f"would take minutes per step), all {cores} host threads, fp32; SINGLE HOST PROCESS whatever --gpus says "
+              "(the reference has no distributed code, SURVEY.md 0): its value does not grow with N, so a ratio against "
+              "it at N > 1 compares N GPUs with one CPU process")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -234,7 +240,7 @@ def run_reference(args):
         "config": workload_config(args, layers),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "processes": 1,
     }))
 
 
@@ -388,6 +394,8 @@ def main():
         n = len(d)
         out["step_us"] = {"p10": round(d[n // 10], 1), "p50": round(d[n // 2], 1), "p90": round(d[(9 * n) // 10], 1),
                           "max": round(d[-1], 1), "max_at_step": slowest, "host_issue_p50": round(h[n // 2], 1), "host_issue_max": round(h[-1], 1)}
+        # the same path roofline on the MEDIAN step (the mean above carries the start-up step after the barrier)
+        roof_path["frac_p50"] = path_bytes / (d[n // 2] * 1e-6) / 1e9 / peak
     kernels = kernel_breakdown(step)        # on every rank: head mode's backward holds a collective
     if rank == 0:
         out["kernels_us"] = kernels
@@ -396,11 +404,18 @@ def main():
     if args.head:
         out["config"]["workload"] = out["config"]["workload"].replace(
             "reference-exact mode (no netF head)", "netF head mode (Linear-ReLU-Linear, nc=256, tcgen05)")
-    elif rank == 0 and world == 1 and not args.no_head_line:
-        out["head_mode"] = head_line(args, pn, src, tgt, math, patches_per_image)
-        out["module_split"] = module_split_line(args, pn, src, tgt, math, patches_per_image)
-
+    elif not args.no_head_line:
+        # every rank takes part (world > 1: the head-gradient all-reduce is a collective); rank 0 reports
+        hm = head_line(args, pn, src, tgt, math, patches_per_image, world, dev)
+        st = strong_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers, elem, peak)
+        sc = nccl_selfcheck(args, pn, layers, dev, world, rank, math) if world > 1 else None
+        if rank == 0:
+            out["head_mode"], out["strong"] = hm, st
+            if sc is not None:
+                out["nccl_selfcheck"] = sc
     if rank == 0 and world == 1 and not args.head and not args.no_head_line:
+        out["module_split"] = module_split_line(args, pn, src, tgt, math, patches_per_image)
+        out["configs"] = config_lines(args, pn, layers, dev, math, peak)
         out["next_rows"] = next_rows_line(pn, dev)
 
     # ---- e2e: same metric through the public API with HOST buffers ------------------------------
@@ -516,31 +531,192 @@ def next_rows_line(pn, dev, n=30):
         return {"error": f"{type(e).__name__}: {e}"}
 
 
-def head_line(args, pn, src, tgt, math, patches_per_image, steps=20):
-    """Secondary measurement: the same maps through the netF head (nc=256), fused tcgen05 path."""
-    torch.manual_seed(11)
-    netF = pn.PatchSampleF(use_mlp=True, nc=256).to(tgt[0].device)
-    netF.create_mlp(tgt)
-
-    def step():
-        for t in tgt:
-            t.grad = None
-        netF.zero_grad(set_to_none=True)
-        loss, _ = pn.patchnce_with_head(netF, src, tgt, args.tau, args.patches, math=math)
-        loss.backward()
-
-    for _ in range(3):
+def timed_steps(step, steps, warmup, world, dev):
+    """ms per step of `step` on this job: barrier + synchronize on both sides, CUDA events, max over ranks."""
+    for _ in range(warmup):
         step()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        torch.distributed.barrier()
     torch.cuda.synchronize()
     e0.record()
     for _ in range(steps):
         step()
     e1.record()
+    if world > 1:
+        torch.distributed.barrier()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    return {"ms_per_step": ms, "value": args.batch * patches_per_image / (ms * 1e-3), "unit": UNIT, "nc": 256,
-            "steps": steps, "note": "netF head Linear-ReLU-Linear on tcgen05, parity unpinned by the reference"}
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def head_line(args, pn, src, tgt, math, patches_per_image, world, dev, steps=20):
+    """Secondary measurement at EVERY N: the same maps through the netF head (nc=256), fused tcgen05 path.  With
+    N > 1 the head gradients are all-reduced (NCCL, the only collective of the path) INSIDE every
+    timed step: `patchnce_with_head(..., dp_group=True)` starts it on a side stream under the dense kernel."""
+    torch.manual_seed(11)              # identical head weights on every rank
+    netF = pn.PatchSampleF(use_mlp=True, nc=256).to(dev)
+    netF.create_mlp(tgt)
+    torch.manual_seed(7)               # identical ids on every rank
+
+    def step():
+        for t in tgt:
+            t.grad = None
+        netF.zero_grad(set_to_none=True)
+        loss, _ = pn.patchnce_with_head(netF, src, tgt, args.tau, args.patches, math=math,
+                                        dp_group=True if world > 1 else None)
+        loss.backward()
+
+    ms = timed_steps(step, steps, 3, world, dev)
+    nparams = sum(p.numel() for p in netF.parameters())
+    return {"ms_per_step": ms, "value": world * args.batch * patches_per_image / (ms * 1e-3), "unit": UNIT, "nc": 256,
+            "steps": steps, "n_gpus": world, "scaling": "weak",
+            "collective": (f"one flat NCCL all-reduce(AVG) of the {nparams} head gradients per step, inside the timed "
+                           "region, overlapped with the dense kernel") if world > 1 else "none (single GPU)",
+            "note": "netF head Linear-ReLU-Linear on tcgen05, parity unpinned by the reference"}
+
+
+def strong_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers, elem, peak, global_batch=64):
+    """STRONG scaling (BASELINE config 5 as written: 'batch 64 ... across 2/4/8'): the global batch of 64 images is
+    sharded over the N ranks, 64/N images each, reference-exact mode (no collective), through PatchNCELoss.forward
+    + backward exactly like the headline -- and the same step replayed from a CUDA graph (GPU time without the
+    Python host), which is what a fixed-shape training loop can do."""
+    if global_batch % world or global_batch // world > args.batch:
+        return {"skipped": f"global batch {global_batch} does not shard over {world} ranks of <= {args.batch} images"}
+    b = global_batch // world
+    s_src = [x[:b] for x in src]
+    s_tgt = [x.detach()[:b].requires_grad_() for x in tgt]
+    crit = pn.PatchNCELoss(args.tau, args.patches, [0, 4, 8, 12, 13], math=math)
+    torch.manual_seed(7)
+
+    def step():
+        for t in s_tgt:
+            t.grad = None
+        crit(s_src, s_tgt).backward()
+
+    steps = 50 if b >= 32 else 200
+    ms = timed_steps(step, steps, 10, world, dev)
+    path_bytes = algorithmic_bytes_per_image(layers, args.patches, elem) * b
+    out = {"global_batch": global_batch, "batch_per_gpu": b, "n_gpus": world, "scaling": "strong", "steps": steps,
+           "ms_per_step": ms, "value": global_batch * patches_per_image / (ms * 1e-3), "unit": UNIT,
+           "roofline_path_frac": path_bytes / (ms * 1e-3) / 1e9 / peak,
+           "api": "PatchNCELoss.forward + backward (eager, ids drawn inside the library)"}
+    try:
+        d_tgt = [t.detach() for t in s_tgt]
+        dms = timed_steps(lambda: crit.loss_and_grads(s_src, d_tgt), steps, 10, world, dev)
+        out["direct"] = {"ms_per_step": dms, "value": global_batch * patches_per_image / (dms * 1e-3),
+                         "roofline_path_frac": path_bytes / (dms * 1e-3) / 1e9 / peak,
+                         "api": "PatchNCELoss.loss_and_grads: the same forward + backward in one autograd-free call "
+                                "(no engine hand-off, no ones_like of the root gradient)"}
+    except Exception as e:  # noqa: BLE001 - secondary
+        out["direct"] = {"error": f"{type(e).__name__}: {e}"}
+    try:
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.cuda.graph(g):
+            step()
+        gms = timed_steps(g.replay, steps, 5, world, dev)
+        out["graph_replay"] = {"ms_per_step": gms, "value": global_batch * patches_per_image / (gms * 1e-3),
+                               "note": "the same fwd+bwd step captured once (static inputs, ids drawn by torch.randint "
+                                       "inside the graph) and replayed: device time without the Python host"}
+    except Exception as e:  # noqa: BLE001 - secondary
+        out["graph_replay"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
+def nccl_selfcheck(args, pn, layers, dev, world, rank, math, b=2):
+    """N > 1: the data-parallel head path against the full batch on ONE rank, on this job's own NCCL communicator
+    (the two-GPU pytest cases are skipped on single-GPU test boxes; this runs wherever the scaling bench runs).
+    Every rank takes b images (maps seeded per rank), same ids, `dp_group=True`; rank 0 then rebuilds all N shards
+    from their seeds, runs the whole batch alone and compares: loss, averaged head gradients, its own dense
+    gradients."""
+    import torch.distributed as dist
+    try:
+        torch.manual_seed(11)
+        netF = pn.PatchSampleF(use_mlp=True, nc=256).to(dev)
+        my_src, my_tgt = make_maps(layers, b, torch.float32, dev, 4321 + rank)
+        my_tgt = [t.requires_grad_() for t in my_tgt]
+        netF.create_mlp(my_tgt)
+        torch.manual_seed(5)
+        ids = pn.draw_ids(my_tgt, args.patches)
+        loss, _ = pn.patchnce_with_head(netF, my_src, my_tgt, args.tau, args.patches, patch_ids=ids, math=math,
+                                        dp_group=True)
+        loss.backward()
+        dp_grads = torch.cat([p.grad.reshape(-1).float() for p in netF.parameters()])
+        mean_loss = loss.detach().clone()
+        dist.all_reduce(mean_loss, op=dist.ReduceOp.SUM)
+        mean_loss /= world
+        # the same reduction through the un-overlapped helper must agree with itself across ranks
+        spread = dp_grads.clone()
+        dist.all_reduce(spread, op=dist.ReduceOp.MAX)
+        rank_spread = float((spread - dp_grads).abs().max().item())
+        res = None
+        if rank == 0:
+            shards = [make_maps(layers, b, torch.float32, dev, 4321 + r) for r in range(world)]
+            f_src = [torch.cat([sh[0][l] for sh in shards]) for l in range(len(layers))]
+            f_tgt = [torch.cat([sh[1][l] for sh in shards]).requires_grad_() for l in range(len(layers))]
+            netF.zero_grad(set_to_none=True)
+            full, _ = pn.patchnce_with_head(netF, f_src, f_tgt, args.tau, args.patches, patch_ids=ids, math=math)
+            full.backward()
+            ref = torch.cat([p.grad.reshape(-1).float() for p in netF.parameters()])
+            g_err = float(((dp_grads - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item())
+            l_err = abs(float(mean_loss.item()) - float(full.item())) / abs(float(full.item()))
+            d_err = max(float(((f.grad[:b] * world - m.grad).abs().max() / m.grad.abs().max().clamp_min(1e-30)).item())
+                        for f, m in zip(f_tgt, my_tgt))
+            res = {"ranks": world, "images_per_rank": b, "head_grad_rel_err": g_err, "loss_rel_err": l_err,
+                   "dense_grad_rel_err": d_err, "rank_spread_abs": rank_spread,
+                   "ok": bool(g_err < 2e-3 and l_err < 1e-4 and d_err < 2e-3 and rank_spread == 0.0),
+                   "what": "patchnce_with_head(dp_group=True) on N ranks vs the full batch on rank 0"}
+        dist.barrier()
+        return res
+    except Exception as e:  # noqa: BLE001
+        try:
+            dist.barrier()
+        except Exception:  # noqa: BLE001
+            pass
+        return {"ok": False, "error": f"{type(e).__name__}: {e}"} if rank == 0 else None
+
+
+def config_lines(args, pn, layers, dev, math, peak):
+    """N = 1: the other BASELINE configurations of the loss on one GPU -- B = 1 (configs 1 and 2) and B = 16 (config 3)
+    in fp32, and fp16 maps at the headline batch (the AMP regime train_cutpp.py:268 runs in) -- each through
+    PatchNCELoss.forward + backward with its own path roofline."""
+    rows = []
+    ppi = sum(min(args.patches, h * w) for _, h, w, _ in layers)
+    for name, b, tdtype, elem in (("b1_fp32", 1, torch.float32, 4), ("b16_fp32", 16, torch.float32, 4),
+                                  (f"b{args.batch}_fp16", args.batch, torch.float16, 2)):
+        try:
+            src, tgt = make_maps(layers, b, tdtype, dev, 99)
+            tgt = [t.requires_grad_() for t in tgt]
+            crit = pn.PatchNCELoss(args.tau, args.patches, [0, 4, 8, 12, 13], math=math)
+
+            def step():
+                for t in tgt:
+                    t.grad = None
+                crit(src, tgt).backward()
+
+            steps = 200 if b <= 16 else 30
+            ms = timed_steps(step, steps, 10, 1, dev)
+            d_tgt = [t.detach() for t in tgt]
+            dms = timed_steps(lambda: crit.loss_and_grads(src, d_tgt), steps, 10, 1, dev)
+            pb = algorithmic_bytes_per_image(layers, args.patches, elem) * b
+            rows.append({"config": name, "batch": b, "dtype": str(tdtype).replace("torch.", ""), "steps": steps,
+                         "ms_per_step": ms, "value": b * ppi / (ms * 1e-3), "unit": UNIT,
+                         "direct_ms_per_step": dms,
+                         "roofline_path": {"bound": "hbm", "achieved": pb / (ms * 1e-3) / 1e9, "peak": peak,
+                                           "unit": "GB/s", "frac": pb / (ms * 1e-3) / 1e9 / peak}})
+            del src, tgt
+        except Exception as e:  # noqa: BLE001
+            rows.append({"config": name, "error": f"{type(e).__name__}: {e}"})
+    torch.cuda.empty_cache()
+    return rows
 
 
 def module_split_line(args, pn, src, tgt, math, patches_per_image, steps=20):
@@ -630,12 +806,31 @@ def run_e2e(args, pn, crit, layers, tdtype, elem, dev, world, rank):
     loss_zc = float(h_loss.item())
     bulk_steps = max(2, args.e2e_steps // 2)
     dt_bulk = timed(step_bulk, bulk_steps)
+    # the other end of the claim: the dense gradients are ALSO brought back to the host every step (a caller whose
+    # generator backward does not run on this GPU) -- 3.2 GB of D2H per step at B=64, PCIe-bound
+    h_grads = [torch.empty(s, dtype=tdtype).pin_memory() for s in shapes]
+
+    def step_grads_d2h():
+        step_zero_copy()
+        for h, t in zip(h_grads, a_tgt):
+            h.copy_(t.grad, non_blocking=True)
+
+    gd_steps = max(2, args.e2e_steps // 3)
+    dt_gd = timed(step_grads_d2h, gd_steps)
+    with_grads = {"value": world * B * patches_per_image * gd_steps / dt_gd, "unit": UNIT,
+                  "h2d_bytes_per_step": sampled * 32, "d2h_bytes_per_step": 4 + n_elem * elem, "steps": gd_steps,
+                  "note": "zero-copy inputs as in the headline e2e, plus every dense d tgt_feat copied to pinned host "
+                          "memory inside the timed region"}
     return {"value": world * B * patches_per_image * args.e2e_steps / dt, "unit": UNIT,
             "h2d_bytes_per_step": sampled * 32, "d2h_bytes_per_step": 4,
             "steps": args.e2e_steps, "loss": loss_zc,
             "api": "PatchNCELoss.forward + backward on pinned host maps via pinned_as_device (zero-copy: the gather "
                    "reads one 32-byte sector per sampled element over PCIe; h2d_bytes counts those sectors, "
                    f"useful bytes = {sampled * elem})",
+            "n_gpus": world,
+            "scaling_note": "per-rank host memory and PCIe are shared on one box: this number scales worse than the "
+                            "device-resident one (0.63 efficiency at N=8 in round 1)",
+            "with_grads_d2h": with_grads,
             "bulk_copy": {"value": world * B * patches_per_image * bulk_steps / dt_bulk, "unit": UNIT,
                           "h2d_bytes_per_step": 2 * n_elem * elem, "steps": bulk_steps,
                           "note": "whole maps copied H2D every step, then the device path (PCIe-bound)"}}

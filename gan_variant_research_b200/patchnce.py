@@ -38,7 +38,9 @@ NORM_EPS = 1e-6          # F.normalize(..., eps=1e-6)   patchnce_cut.py:77-78
 
 
 def _stream_ptr(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    # the raw cudaStream_t of torch's current stream (torch.cuda.current_stream(device).cuda_stream, without building
+    # the Stream object: 0.2 us instead of 2.2 us, on a path that small batches are bound by)
+    return torch._C._cuda_getCurrentRawStream(device.index)
 
 
 class _NullCtx:
@@ -219,16 +221,18 @@ class _WarnQueue:
     """The kernels write their two status words (guarded-image count, protocol-timeout flag) STRAIGHT
     INTO PINNED HOST MEMORY (zero-copy over PCIe: pinned allocations are device-addressable under
     unified addressing), so no D2H memcpy sits on the stream between the forward and the backward
-    kernels.  A ring of 64 slots, each guarded by a CUDA event recorded after the launch; a slot is
-    reused once its event has completed.  One queue per device; a lock makes it safe to call from
-    several threads (the autograd engine's threads never touch it: only forwards do)."""
+    kernels -- and no CUDA event either: the host stores -1 into word 0 before the launch and the loss
+    kernel's last CTA overwrites it with the count (>= 0) when the forward is done, so "word 0 >= 0" IS the
+    completion test (an event record + query per step cost ~8 us of host time, which small batches are bound
+    by).  A ring of 64 slots, one queue per device; a lock makes it safe to call from several threads (the
+    autograd engine's threads never touch it: only forwards do)."""
     SLOTS = 64
 
     def __init__(self):
-        self.pending = []
+        self.pending = []            # slots in launch order
         self.host = None
+        self.words = None            # numpy view of the pinned buffer: plain loads and stores, no tensor indexing
         self.free = []
-        self.events = []
         self.lock = threading.Lock()
 
     def acquire(self):
@@ -239,48 +243,44 @@ class _WarnQueue:
         with self.lock:
             if self.host is None:
                 self.host = torch.zeros(self.SLOTS, 2, dtype=torch.int32).pin_memory()
+                self.words = self.host.numpy()
                 self.base = self.host.data_ptr()
                 self.free = list(range(self.SLOTS))
-                self.events = [torch.cuda.Event() for _ in range(self.SLOTS)]
             if not self.free:
                 self._poll(False)
-                if not self.free:                    # 64 launches in flight un-polled: wait for the oldest
-                    self.pending[0][0].synchronize()
-                    self._poll(False)
+                if not self.free:                    # 64 launches in flight un-polled: drain the device
+                    torch.cuda.synchronize()
+                    self._poll(True)
             slot = self.free.pop()
-        # no reset needed: every launch sequence writes both words (word 1 is cleared by its first kernel, word 0
-        # is written by the loss kernel's last CTA)
+            self.words[slot, 0] = -1                 # "in flight"; word 1 is cleared by the sequence's first kernel
+            self.words[slot, 1] = 0
+            self.pending.append(slot)
         return slot, self.base + 8 * slot
-
-    def commit(self, slot, stream):
-        if slot is None:
-            return
-        ev = self.events[slot]
-        ev.record(stream)
-        with self.lock:
-            self.pending.append((ev, slot))
 
     def poll(self, block: bool = False) -> int:
         """Print the reference's warning for finished launches; returns images guarded so far."""
-        if not self.pending or torch.cuda.is_current_stream_capturing():
-            return 0                             # (cudaEventQuery is not allowed while a graph is being captured)
+        if not self.pending:
+            return 0
+        if block:
+            if torch.cuda.is_current_stream_capturing():
+                return 0
+            torch.cuda.synchronize()
         with self.lock:
             return self._poll(block)
 
-    def _poll(self, block: bool) -> int:
+    def _poll(self, drained: bool) -> int:
         total, keep, proto_err = 0, [], False
-        for ev, slot in self.pending:
-            if block:
-                ev.synchronize()
-            if ev.query():
-                n, proto = int(self.host[slot, 0]), int(self.host[slot, 1])
+        w = self.words
+        for slot in self.pending:
+            n = int(w[slot, 0])
+            if n >= 0 or drained:
                 self.free.append(slot)
-                proto_err = proto_err or bool(proto)
-                if n:
+                proto_err = proto_err or bool(w[slot, 1])
+                if n > 0:
                     print(f"Warning: NaN in PatchNCE loss. {n} (layer, image) loss(es) replaced by 0.")
-                total += n
+                    total += n
             else:
-                keep.append((ev, slot))
+                keep.append(slot)
         self.pending = keep
         if proto_err:
             raise _lib.PnceError("libpnce kernel protocol timeout (tcgen05 pipeline stalled)")
@@ -357,6 +357,31 @@ def _shape_plan(tgt, p_list, math) -> _ShapePlan:
     return sp
 
 
+class _FlatIds:
+    """The ids of every layer in ONE int64 buffer (what the library's draw fills); quacks like the list of per-layer
+    tensors as far as the C-ABI glue is concerned (``ids[l].data_ptr()``) without creating the views."""
+    __slots__ = ("flat", "ptrs")
+
+    class _Ptr:
+        __slots__ = ("p",)
+
+        def __init__(self, p):
+            self.p = p
+
+        def data_ptr(self):
+            return self.p
+
+    def __init__(self, flat, p_list):
+        self.flat = flat
+        base, self.ptrs = flat.data_ptr(), []
+        for p in p_list:
+            self.ptrs.append(_FlatIds._Ptr(base))
+            base += 8 * p
+
+    def __getitem__(self, l):
+        return self.ptrs[l]
+
+
 class _Call:
     """One fused call: the shape plan plus what is not a differentiable input."""
     __slots__ = ("sp", "src", "ids", "temperature", "rng", "idplan")
@@ -380,39 +405,72 @@ def _layer_array(src, tgt, dtgt, ids):
     return arr
 
 
+def _run_fwd(call: _Call, tgt_feats):
+    """The forward launches of one fused call (id draw + sort | gather | logits, CE and the gradient rows):
+    -> (workspace, out) with out[0] = loss, out[1 + l] = layer losses."""
+    lib = _lib.load()
+    sp = call.sp
+    dev = sp.dev
+    n = sp.n
+    with _on_device(dev):
+        ws = torch.empty(sp.ws_bytes, dtype=torch.uint8, device=dev)
+        out = torch.empty(1 + n, dtype=torch.float32, device=dev)
+        slot, flag_ptr = _warn_queue(dev).acquire()           # both words are written by the kernels
+        st = _stream_ptr(dev)
+        src, ids = call.src, call.ids
+        with sp.fwd_lock:
+            layers = sp.fwd_layers
+            for l in range(n):
+                a = layers[l]
+                a.src, a.tgt, a.ids = src[l].data_ptr(), tgt_feats[l].data_ptr(), ids[l].data_ptr()
+            if call.rng is not None:
+                rc = lib.pnce_fwd_draw(layers, n, sp.batch, sp.dtype_code, call.temperature, sp.math_code,
+                                       ws.data_ptr(), sp.ws_bytes, call.rng[0], call.rng[1], out.data_ptr(),
+                                       flag_ptr or None, st)
+            elif call.idplan is None:
+                rc = lib.pnce_fwd(layers, n, sp.batch, sp.dtype_code, call.temperature, sp.math_code,
+                                  ws.data_ptr(), sp.ws_bytes, out.data_ptr(), flag_ptr or None, st)
+            else:
+                rc = lib.pnce_fwd_planned(layers, n, sp.batch, sp.dtype_code, call.temperature, sp.math_code,
+                                          ws.data_ptr(), sp.ws_bytes, call.idplan.data_ptr(),
+                                          call.idplan.numel(), out.data_ptr(), flag_ptr or None, st)
+        if rc != 0:
+            _lib.check(rc, "pnce_fwd")
+    return ws, out
+
+
+def _run_bwd(call: _Call, ws, grad_out, tgt_like):
+    """The backward launch: dense d loss / d tgt_feat of every layer, scaled by ``grad_out`` (device scalar or None = 1)."""
+    lib = _lib.load()
+    sp = call.sp
+    dev = sp.dev
+    g = grad_out
+    if g is not None and (g.dtype != torch.float32 or g.device != dev or not g.is_contiguous()):
+        g = g.detach().to(device=dev, dtype=torch.float32).contiguous()
+    with _on_device(dev):
+        grads = [torch.empty_like(t) for t in tgt_like]
+        st = _stream_ptr(dev)
+        ids = call.ids
+        with sp.bwd_lock:
+            layers = sp.bwd_layers
+            for l in range(sp.n):
+                layers[l].dtgt, layers[l].ids = grads[l].data_ptr(), ids[l].data_ptr()
+            gp = g.data_ptr() if g is not None else None
+            if call.idplan is None:
+                rc = lib.pnce_bwd(layers, sp.n, sp.batch, sp.dtype_code, sp.math_code, ws.data_ptr(),
+                                  sp.ws_bytes, gp, st)
+            else:
+                rc = lib.pnce_bwd_planned(layers, sp.n, sp.batch, sp.dtype_code, sp.math_code, ws.data_ptr(),
+                                          sp.ws_bytes, call.idplan.data_ptr(), call.idplan.numel(), gp, st)
+        if rc != 0:
+            _lib.check(rc, "pnce_bwd")
+    return grads
+
+
 class _FusedPatchNCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, call: _Call, *tgt_feats):
-        lib = _lib.load()
-        sp = call.sp
-        dev = sp.dev
-        n = sp.n
-        with _on_device(dev):
-            ws = torch.empty(sp.ws_bytes, dtype=torch.uint8, device=dev)
-            out = torch.empty(1 + n, dtype=torch.float32, device=dev)
-            wq = _warn_queue(dev)
-            slot, flag_ptr = wq.acquire()                     # both words are written by the kernels
-            stream = torch.cuda.current_stream(dev)
-            st = stream.cuda_stream
-            with sp.fwd_lock:
-                layers = sp.fwd_layers
-                for l in range(n):
-                    a = layers[l]
-                    a.src, a.tgt, a.ids = call.src[l].data_ptr(), tgt_feats[l].data_ptr(), call.ids[l].data_ptr()
-                if call.rng is not None:
-                    rc = lib.pnce_fwd_draw(layers, n, sp.batch, sp.dtype_code, call.temperature, sp.math_code,
-                                           ws.data_ptr(), sp.ws_bytes, call.rng[0], call.rng[1], out.data_ptr(),
-                                           flag_ptr or None, st)
-                elif call.idplan is None:
-                    rc = lib.pnce_fwd(layers, n, sp.batch, sp.dtype_code, call.temperature, sp.math_code,
-                                      ws.data_ptr(), sp.ws_bytes, out.data_ptr(), flag_ptr or None, st)
-                else:
-                    rc = lib.pnce_fwd_planned(layers, n, sp.batch, sp.dtype_code, call.temperature, sp.math_code,
-                                              ws.data_ptr(), sp.ws_bytes, call.idplan.data_ptr(),
-                                              call.idplan.numel(), out.data_ptr(), flag_ptr or None, st)
-            if rc != 0:
-                _lib.check(rc, "pnce_fwd")
-            wq.commit(slot, stream)
+        ws, out = _run_fwd(call, tgt_feats)
         # the workspace goes through save_for_backward: autograd then frees it with the graph, right after
         # backward() -- kept as a plain ctx attribute it lived as long as the loss tensor did, and a caller that
         # holds on to the loss across steps (loss = step()) made every step allocate a second 0.26 GB workspace
@@ -424,36 +482,15 @@ class _FusedPatchNCE(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        lib = _lib.load()
-        call = ctx.call
-        sp = call.sp
-        dev = sp.dev
-        g = grad_out
-        if g.dtype != torch.float32 or g.device != dev or not g.is_contiguous():
-            g = g.detach().to(device=dev, dtype=torch.float32).contiguous()
         (ws,) = ctx.saved_tensors
-        with _on_device(dev):
-            grads = [torch.empty_like(t) for t in ctx.tgt_keep]
-            st = _stream_ptr(dev)
-            with sp.bwd_lock:
-                layers = sp.bwd_layers
-                for l in range(sp.n):
-                    layers[l].dtgt = grads[l].data_ptr()
-                if call.idplan is None:
-                    rc = lib.pnce_bwd(layers, sp.n, sp.batch, sp.dtype_code, sp.math_code, ws.data_ptr(),
-                                      sp.ws_bytes, g.data_ptr(), st)
-                else:
-                    rc = lib.pnce_bwd_planned(layers, sp.n, sp.batch, sp.dtype_code, sp.math_code, ws.data_ptr(),
-                                              sp.ws_bytes, call.idplan.data_ptr(), call.idplan.numel(),
-                                              g.data_ptr(), st)
-            if rc != 0:
-                _lib.check(rc, "pnce_bwd")
-        return (None, *grads)
+        return (None, *_run_bwd(ctx.call, ws, grad_out, ctx.tgt_keep))
 
 
 def _prepare_maps(src_feats, tgt_feats):
     """The reference's argument handling (patchnce_cut.py:25-40) plus what the C ABI needs: CUDA tensors,
-    (B, C, H, W), src/tgt of equal shape, contiguous NCHW.  Returns (src, tgt, len(src_feats))."""
+    (B, C, H, W), src/tgt of equal shape, contiguous NCHW.  Returns (src, tgt, len(src_feats), uniform); ``uniform``:
+    every layer shares batch size, dtype and device, so ONE C-ABI call covers them all (the reference treats each
+    layer on its own, :36-38, so mixed lists are valid input there and take one call per layer here)."""
     n_src = len(src_feats)
     n = min(n_src, len(tgt_feats))                   # the reference zips and silently truncates (:36) ...
     if n_src == 0:
@@ -463,35 +500,32 @@ def _prepare_maps(src_feats, tgt_feats):
     if n > _lib.MAX_LAYERS:
         raise RuntimeError(f"at most {_lib.MAX_LAYERS} nce layers per call")
     src, tgt = [], []
+    t0 = tgt_feats[0]
+    b0, dt0, dev0 = (t0.shape[0] if t0.dim() else -1), t0.dtype, t0.device
+    uniform = True
     for l in range(n):
         s, t = src_feats[l], tgt_feats[l]
-        if not t.is_cuda:
+        if s.shape != t.shape or s.dtype != t.dtype or s.device != t.device or t.dim() != 4 or not t.is_cuda:
+            # off the fast path: say what is wrong, or convert what may be converted
             _require_cuda(t, "tgt_feat")
-        if not s.is_cuda:
             _require_cuda(s, "src_feat")
-        if t.dim() != 4 or s.dim() != 4:
-            raise ValueError("not enough values to unpack (expected 4): feature maps must be (B, C, H, W)")
-        if s.shape != t.shape:
-            raise RuntimeError(f"src/tgt feature shapes differ: {tuple(s.shape)} vs {tuple(t.shape)}")
-        if t.dtype not in _DTYPES:
-            raise RuntimeError(f"unsupported feature dtype {t.dtype}")
-        if s.dtype != t.dtype:
+            if t.dim() != 4 or s.dim() != 4:
+                raise ValueError("not enough values to unpack (expected 4): feature maps must be (B, C, H, W)")
+            if s.shape != t.shape:
+                raise RuntimeError(f"src/tgt feature shapes differ: {tuple(s.shape)} vs {tuple(t.shape)}")
+            if s.device != t.device:
+                raise RuntimeError(f"src/tgt features on different devices: {s.device} vs {t.device}")
             s = s.to(t.dtype)
+        dt = t.dtype
+        if dt is not dt0 or t.shape[0] != b0 or t.device != dev0:
+            uniform = False
+        if dt not in _DTYPES:
+            raise RuntimeError(f"unsupported feature dtype {dt}")
         if s.requires_grad:
             s = s.detach()
         src.append(s if s.is_contiguous() else s.contiguous())
         tgt.append(t if t.is_contiguous() else t.contiguous())
-    return src, tgt, n_src
-
-
-def _uniform(tgt) -> bool:
-    """One C-ABI call covers every layer only if they share batch size, dtype and device (the reference treats
-    each layer on its own, patchnce_cut.py:36-38, so mixed lists are valid input there)."""
-    t0 = tgt[0]
-    for t in tgt:
-        if t.shape[0] != t0.shape[0] or t.dtype != t0.dtype or t.device != t0.device:
-            return False
-    return True
+    return src, tgt, n_src, uniform
 
 
 def _fused_call(src, tgt, ids, temperature, math, rng=None, idplan=None):
@@ -503,7 +537,7 @@ def fused_patchnce(src_feats, tgt_feats, ids_list, temperature=0.07, math: Optio
                    denom_layers: Optional[int] = None):
     """All-layer PatchNCE on dense NCHW maps with given ids.  Returns the scalar loss tensor
     (fp32, on device, differentiable w.r.t. every ``tgt_feats[l]`` that requires grad)."""
-    src, tgt, n_src = _prepare_maps(src_feats, tgt_feats)
+    src, tgt, n_src, uniform = _prepare_maps(src_feats, tgt_feats)
     n = len(tgt)
     if len(ids_list) < n:
         raise RuntimeError(f"{len(ids_list)} id tensors for {n} layers")
@@ -517,7 +551,7 @@ def fused_patchnce(src_feats, tgt_feats, ids_list, temperature=0.07, math: Optio
         ids.append(i)
     math = math or DEFAULT_MATH
     denom = n_src if denom_layers is None else denom_layers
-    if _uniform(tgt):
+    if uniform:
         loss = _fused_call(src, tgt, ids, temperature, math)
     else:
         # layers of different batch size / dtype: one call per layer, summed like the reference's loop (:36-40)
@@ -544,20 +578,55 @@ class PatchNCELoss(nn.Module):
         self.num_patches = num_patches
         self.nce_layers = list(nce_layers)      # stored, never used -- as in the reference (:22)
         self.math = math
-        self.last_patch_ids: Optional[List[torch.Tensor]] = None
+        self._last_ids = None
+
+    @property
+    def last_patch_ids(self) -> Optional[List[torch.Tensor]]:
+        """The ids of the most recent ``forward(src_feats, tgt_feats)``: one int64 (P_l,) tensor per layer."""
+        v = self._last_ids
+        if isinstance(v, tuple):                 # (flat buffer the library drew into, patch counts): split on demand
+            v = self.__dict__["_last_ids"] = list(v[0].split(v[1]))
+        return v
 
     def forward(self, a, b, batch_size: Optional[int] = None):
         if isinstance(a, torch.Tensor) and a.dim() == 2:
             return rows_patchnce(a, b, self.temperature, self.num_patches, batch_size, self.math)
-        src, tgt, n_src = _prepare_maps(a, b)
+        call, tgt, scale = self._begin(a, b)
+        if call is None:
+            return tgt                               # mixed layers: the per-layer composition already ran
+        loss = _FusedPatchNCE.apply(call, *tgt)
+        return loss if scale is None else loss * scale
+
+    def loss_and_grads(self, src_feats, tgt_feats, grad_output: Optional[torch.Tensor] = None):
+        """``forward(src_feats, tgt_feats)`` and its complete backward in ONE call, without autograd: returns
+        ``(loss, [d (grad_output * loss) / d tgt_feats[l]])`` -- same ids (one draw per layer, generator advanced
+        like the reference's), same kernels, same values as ``loss = forward(...); loss.backward(grad_output)``.
+        For training loops that drive the generator's backward themselves (``feat.backward(grad)``) and for
+        small batches, where autograd's fixed cost per backward() (engine thread hand-off, the ones_like of the
+        root gradient: ~100 us of host time) is more than the whole step's GPU time."""
+        call, tgt, scale = self._begin(src_feats, tgt_feats)
+        if call is None:
+            raise RuntimeError("loss_and_grads needs layers of one batch size, dtype and device")
+        tgt = [t.detach() for t in tgt]
+        ws, out = _run_fwd(call, tgt)
+        g = grad_output
+        if scale is not None:
+            g = torch.full((), scale, device=out.device) if g is None else g.to(torch.float32) * scale
+        grads = _run_bwd(call, ws, g, tgt)
+        loss = out[0]
+        return (loss if scale is None else loss * scale), grads
+
+    def _begin(self, a, b):
+        """Argument handling + the id draw of one ``forward``: -> (call, tgt, scale)."""
+        src, tgt, n_src, uniform = _prepare_maps(a, b)
         n = len(tgt)
         dev = tgt[0].device
         _warn_queue(dev).poll()
         math = self.math or DEFAULT_MATH
-        if not _uniform(tgt):
+        if not uniform:
             ids = draw_patch_ids_all(src, self.num_patches)                           # :60-63
-            self.last_patch_ids = ids
-            return fused_patchnce(src, tgt, ids, self.temperature, math, denom_layers=n_src)
+            self.__dict__["_last_ids"] = ids
+            return None, fused_patchnce(src, tgt, ids, self.temperature, math, denom_layers=n_src), None
         p_list = [patch_count(self.num_patches, t.shape[2] * t.shape[3]) for t in tgt]    # :60
         if max(p_list) > _lib.MAX_PATCHES:
             raise RuntimeError(f"num_patches > {_lib.MAX_PATCHES} is not supported")
@@ -590,14 +659,13 @@ class PatchNCELoss(nn.Module):
                 main.wait_stream(side)
                 ids_all.record_stream(main)      # allocated on the side stream's pool, consumed on the caller's
                 idplan.record_stream(main)
-            ids = list(ids_all.split(p_list))
+            ids = _FlatIds(ids_all, p_list)
+            self.__dict__["_last_ids"] = (ids_all, p_list)       # nn.Module.__setattr__ costs 3 us; split lazily
         else:
             ids = draw_patch_ids_all(src, self.num_patches)                           # :60-63
-        self.last_patch_ids = ids
-        loss = _FusedPatchNCE.apply(_Call(sp, src, ids, self.temperature, rng, idplan), *tgt)
-        if n_src != n:                       # zip truncation: the kernel divided by n, the reference by len(src_feats) (:40)
-            loss = loss * (float(n) / float(n_src))
-        return loss
+            self.__dict__["_last_ids"] = ids
+        # zip truncation: the kernel divides by n, the reference by len(src_feats) (:40)
+        return _Call(sp, src, ids, self.temperature, rng, idplan), tgt, (None if n_src == n else float(n) / float(n_src))
 
 
 def compute_patchnce_loss(generator, src_images, tgt_images, nce_layers, temperature=0.07,
@@ -763,7 +831,6 @@ class _RowsLossFn(torch.autograd.Function):
                                                   _MATH[math], ws.data_ptr(), nbytes.value, out.data_ptr(),
                                                   flag_ptr or None, dq.data_ptr(), None, _stream_ptr(dev)),
                        "pnce_rows_loss_fwd_bwd")
-            wq.commit(slot, torch.cuda.current_stream(dev))
         ctx.save_for_backward(dq)
         ctx.q_dtype = q.dtype
         return out.narrow(0, 0, 1).reshape(())
@@ -888,7 +955,6 @@ class _FusedHeadPatchNCE(torch.autograd.Function):
             _lib.check(lib.pnce_head_fwd(layers, heads, n, batch, dtype, nc, plan.temperature, _MATH[plan.math],
                                          ws.data_ptr(), nbytes.value, out.data_ptr(), flag_ptr or None,
                                          _stream_ptr(dev)), "pnce_head_fwd")
-            wq.commit(slot, torch.cuda.current_stream(dev))
         ctx.save_for_backward(ws)            # freed with the graph, right after backward() (see _FusedPatchNCE)
         ctx.plan, ctx.ws_bytes, ctx.nc = plan, nbytes.value, nc
         ctx.tgt_keep, ctx.params = tgt, params
@@ -980,8 +1046,8 @@ def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0
         raise RuntimeError("fused head: nc must be 128 or 256, num_patches <= 256 and C <= 256")
     if not netF.mlp_init:
         netF.create_mlp(tgt_feats)
-    src, tgt, _ = _prepare_maps(src_feats, tgt_feats)
-    if not _uniform(tgt):
+    src, tgt, _, uniform = _prepare_maps(src_feats, tgt_feats)
+    if not uniform:
         raise RuntimeError("fused head: every layer must share batch size, dtype and device (use fused=False)")
     if patch_ids is None:
         ids = draw_ids(tgt, num_patches)

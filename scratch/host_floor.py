@@ -48,6 +48,19 @@ for B in (1, 2, 4, 8, 16, 64):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
+    # the autograd-free entry: forward + backward in one call
+    dt = [t.detach() for t in tgt]
+    for _ in range(20):
+        crit.loss_and_grads(src, dt)
+    torch.cuda.synchronize()
+    e0.record()
+    t00 = time.perf_counter()
+    for _ in range(n):
+        crit.loss_and_grads(src, dt)
+    host_direct = time.perf_counter() - t00
+    e1.record()
+    torch.cuda.synchronize()
+    dms = e0.elapsed_time(e1) / n
     # graph replay of the same step (static inputs): GPU-only time
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
@@ -71,8 +84,22 @@ for B in (1, 2, 4, 8, 16, 64):
     except Exception as e:  # noqa: BLE001
         gms = repr(e)
     out[B] = {"ms_per_step": round(ms, 4), "host_fwd_us": round(hf / n * 1e6, 1), "host_bwd_us": round(hb / n * 1e6, 1),
-              "host_loop_us": round(host_total / n * 1e6, 1), "graph_replay_ms": gms if isinstance(gms, str) else round(gms, 4)}
+              "host_loop_us": round(host_total / n * 1e6, 1),
+              "direct_ms": round(dms, 4), "direct_host_us": round(host_direct / n * 1e6, 1), "graph_replay_ms": gms if isinstance(gms, str) else round(gms, 4)}
     print(B, out[B], flush=True)
+    if B == 8:
+        # GPU timeline of one eager step: kernel start / duration / gap to the previous kernel's end
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+        prev_end = None
+        for e in evs[-12:]:
+            gap = (e.time_range.start - prev_end) if prev_end is not None else 0
+            print(f"   {e.name[:60]:60s} dur {e.time_range.elapsed_us():7.1f} us  gap {gap:7.1f} us")
+            prev_end = e.time_range.end
     del src, tgt
     torch.cuda.empty_cache()
 print(json.dumps(out))

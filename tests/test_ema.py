@@ -63,16 +63,17 @@ def test_cuda_ema_is_bit_identical_to_the_reference():
             np.testing.assert_array_equal(v.cpu().numpy(), d[f"s{step}:{n}"], err_msg=f"step {step} {n}")
     sd = ema.state_dict()
     assert sd["decay"] == float(d["decay"]) and set(sd["shadow"]) == set(ema.shadow)
-    v0 = [p._version for p in net.parameters()]
+    trainable = [p for p in net.parameters() if p.requires_grad]      # the frozen parameter is skipped (:19-21)
+    v0 = [p._version for p in trainable]
     ema.apply_shadow()
     # the kernels write parameters through raw pointers: the version counters must still move, or anything keyed on
     # them (the encoder-feature cache, feature_reuse.py) would serve values computed with the old weights
-    assert all(p._version > a for p, a in zip(net.parameters(), v0))
+    assert all(p._version > a for p, a in zip(trainable, v0))
     for n, p in net.named_parameters():
         np.testing.assert_array_equal(p.detach().cpu().numpy(), d[f"applied:{n}"])
-    v1 = [p._version for p in net.parameters()]
+    v1 = [p._version for p in trainable]
     ema.restore()
-    assert all(p._version > a for p, a in zip(net.parameters(), v1))
+    assert all(p._version > a for p, a in zip(trainable, v1))
     for n, p in net.named_parameters():
         np.testing.assert_array_equal(p.detach().cpu().numpy(), d[f"final:{n}"])
     with pytest.raises(KeyError):

@@ -725,3 +725,69 @@ def test_shapes_beyond_the_limits_fail_loudly(pn, c, h, w, p):
     ids = [torch.randint(0, h * w, (min(p, h * w),), generator=g).cuda()]
     with pytest.raises(RuntimeError, match="outside compiled limits|not supported"):
         pn.fused_patchnce(src, tgt, ids, 0.07)
+
+
+def test_loss_and_grads_equals_forward_backward(pn):
+    """The autograd-free entry (forward + complete backward in one call) returns what loss.backward(g) leaves in .grad --
+    bit for bit: same ids from the same generator state, same kernels."""
+    g = torch.Generator().manual_seed(21)
+    shapes = [(32, 24, 24), (64, 16, 16), (128, 40, 40)]
+    src = [torch.randn(3, *s, generator=g).cuda() for s in shapes]
+    tgt = [torch.randn(3, *s, generator=g).cuda().requires_grad_() for s in shapes]
+    crit = pn.PatchNCELoss(0.07, 256)
+    up = torch.tensor(2.5, device="cuda")
+    torch.manual_seed(4)
+    la = crit(src, tgt)
+    la.backward(up)
+    ids_a = [i.clone() for i in crit.last_patch_ids]
+    after_a = torch.rand(3, device="cuda")
+    torch.manual_seed(4)
+    lb, grads = crit.loss_and_grads(src, [t.detach() for t in tgt], up)
+    after_b = torch.rand(3, device="cuda")
+    assert la.item() == lb.item() and torch.equal(after_a, after_b)
+    assert all(torch.equal(a, b) for a, b in zip(ids_a, crit.last_patch_ids))
+    for t, gr in zip(tgt, grads):
+        assert gr.shape == t.shape and torch.equal(t.grad, gr)
+    # unit upstream gradient when none is given; a truncated layer list is scaled like the reference (:36-40)
+    torch.manual_seed(4)
+    lc, gc = crit.loss_and_grads(src, [t.detach() for t in tgt])
+    assert lc.item() == la.item()
+    for a, b in zip(grads, gc):
+        assert torch.allclose(a, b * 2.5, rtol=1e-6, atol=0)
+    torch.manual_seed(4)
+    ld, gd = crit.loss_and_grads(src, [t.detach() for t in tgt[:2]])
+    torch.manual_seed(4)
+    tg2 = [t.detach().clone().requires_grad_() for t in tgt[:2]]
+    le = crit(src, tg2)
+    le.backward()
+    assert ld.item() == pytest.approx(le.item(), rel=1e-6)
+    for a, t in zip(gd, tg2):
+        assert torch.allclose(a, t.grad, rtol=1e-6, atol=0)
+    assert pn.poll_nonfinite_warnings(block=True) == 0
+
+
+def test_layers_of_mixed_dtype_and_batch_follow_the_reference_loop(pn, orc):
+    """The reference handles every layer on its own (patchnce_cut.py:36-38): a list whose layers differ in dtype or
+    batch size is valid input there.  One C-ABI call carries ONE dtype and batch, so such lists take a call per
+    layer -- never a reinterpretation of another layer's memory."""
+    g = torch.Generator().manual_seed(33)
+    specs = [(2, 32, 12, 12, torch.float32), (3, 16, 10, 10, torch.float32), (2, 64, 8, 8, torch.float16)]
+    src = [torch.randn(b, c, h, w, generator=g).to(dt) for b, c, h, w, dt in specs]
+    tgt = [torch.randn(b, c, h, w, generator=g).to(dt) for b, c, h, w, dt in specs]
+    t = [x.cuda().requires_grad_() for x in tgt]
+    crit = pn.PatchNCELoss(0.07, 64)
+    torch.manual_seed(12)
+    loss = crit([x.cuda() for x in src], t)
+    loss.backward()
+    ids = crit.last_patch_ids
+    assert len(ids) == 3
+    want = 0.0
+    for l in range(3):
+        w, _, gw = orc.patchnce_loss_and_grads_np([src[l].float().numpy()], [tgt[l].float().numpy()], [ids[l].cpu().numpy()],
+                                                  0.07, upstream=1.0 / 3.0)
+        want += w / 3.0
+        tol = 2e-4 if specs[l][4] == torch.float32 else 2e-2
+        assert_grad_close(t[l].grad.float().cpu().numpy(), gw[0], tol, f"layer {l}", ids=ids[l].cpu().numpy())
+    assert loss.item() == pytest.approx(want, rel=2e-4)
+    with pytest.raises(RuntimeError):
+        pn.fused_patchnce([x.cuda() for x in src], t, ids[:2], 0.07)          # fewer id tensors than layers
