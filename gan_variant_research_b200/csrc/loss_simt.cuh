@@ -21,13 +21,16 @@ __host__ __device__ inline size_t loss_simt_smem_bytes(int P) {
 // non-finite guards, batch and layer means.  Parallel over the batch (a block-wide reduction in a
 // fixed order per layer) -- a single thread walking L*B values costs one L2 round trip per value,
 // ~40 us at B=64, on the critical path of every step.
-__device__ void finalize_losses(const Params& p) {
+constexpr int kFinalizeScratchBytes = (32 + 32 + PNCE_MAX_LAYERS + 1) * 4;
+__device__ void finalize_losses(const Params& p, void* scratch) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
   const int B = p.B, nl = p.n_layers;
-  __shared__ float w_sum[32];                                   // one slot per warp of ANY launch shape (k_loss_tc_p: 11-12 warps)
-  __shared__ int w_bad[32];
-  __shared__ int layer_bad[PNCE_MAX_LAYERS];
-  __shared__ int any_guard;
+  // scratch: kFinalizeScratchBytes of the caller's shared memory (the tcgen05 kernels have no static shared memory to
+  // spare: static + dynamic is exactly the 227 KB a CTA may have, and a static array costs a whole 1 KB of alignment)
+  float* w_sum = static_cast<float*>(scratch);                  // [32] one slot per warp of ANY launch shape (k_loss_tc_p: 11 warps)
+  int* w_bad = reinterpret_cast<int*>(w_sum + 32);              // [32]
+  int* layer_bad = w_bad + 32;                                  // [PNCE_MAX_LAYERS]
+  int& any_guard = layer_bad[PNCE_MAX_LAYERS];
   float total = 0.f;                                            // thread 0 only
   int bad_total = 0;
   for (int l = 0; l < nl; ++l) {
@@ -101,7 +104,7 @@ __device__ void finalize_losses(const Params& p) {
   }
 }
 
-__device__ __forceinline__ void last_cta_finalize(const Params& p, int* flag_s) {
+__device__ __forceinline__ void last_cta_finalize(const Params& p, int* flag_s, void* scratch) {
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -111,7 +114,7 @@ __device__ __forceinline__ void last_cta_finalize(const Params& p, int* flag_s) 
   __syncthreads();
   if (*flag_s) {
     __threadfence();
-    finalize_losses(p);
+    finalize_losses(p, scratch);
     if (threadIdx.x == 0) { p.counter[0] = 0u; p.counter[1] = 0u; }
   }
 }
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(kThreads) k_loss_simt(const __grid_constant__ 
     }
   }
 
-  last_cta_finalize(p, flag_s);
+  last_cta_finalize(p, flag_s, sm);                            // every phase is over: the logits tile is free scratch
 }
 
 }  // namespace pnce

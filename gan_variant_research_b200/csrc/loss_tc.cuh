@@ -290,7 +290,7 @@ __device__ __forceinline__ void tc_dq_chunk(const uint32_t (&r)[32], const TcQCh
     }
     return;
   }
-  if (rowok) {
+  if (rowok && g_dx_evict_last != 2) {                         // 2: experiment knob (no stores at all)
     const bool keep = g_dx_evict_last != 0;
     uint64_t pol = 0;
     if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     p.trace[64 + 3 * (size_t)blockIdx.x + 2] = (long long)t;
   }
-  last_cta_finalize(p, &sh->flag);
+  last_cta_finalize(p, &sh->flag, smem);                       // every CTA-wide phase is over (the __syncthreads above): the ring is free scratch
 }
 
 // -------------------------------------------------------------------------------------------------

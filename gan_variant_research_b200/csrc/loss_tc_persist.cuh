@@ -37,10 +37,11 @@ struct TpShared {
   uint32_t tmem_base;
   int dead, flag, badk;
   float red[2][8];
-  float xch[128];            // exchange between the two warps of a quadrant (odd-chunk warp -> even-chunk warp -> back):
-                             // partial sum of exp2 after pass A, partial sum_j dZ_ij y_ij after pass B
+  float xch[3][128];         // exchange between the two warps of a quadrant (odd-chunk warp -> even-chunk warp -> back):
+                             // [0] partial sum of exp2, [1] partial sum_j e_ij y_ij (single pass) or sum_j dZ_ij y_ij
+                             // (two passes), [2] the diagonal logit (known to the warp that owns the diagonal's chunk)
 };
-constexpr int kTpSharedBytes = 1024;       // 227 KB minus the 1 KB the driver reserves per CTA is the budget
+constexpr int kTpSharedBytes = 2048;       // the kernel has no static shared memory: all 227 KB are dynamic
 constexpr int kTpSmemBytes = 2 * kTcStageBytes + 2 * kTcDzBytes + 1024 /*invk*/ + kTpSharedBytes;
 static_assert(sizeof(TpShared) <= kTpSharedBytes, "TpShared must fit its slot");
 static_assert(kTpSmemBytes <= 227 * 1024, "shared memory budget");
@@ -100,28 +101,122 @@ __device__ __forceinline__ void tp_row_ss_load(const Params& p, const BlockMap& 
     ss[s] = (s < t.nstage && gi < t.P) ? __ldcg(t.L->qss + ((size_t)t.b * t.nstage + s) * t.Ppad + gi) : 0.f;
 }
 
-// dQ epilogue of the channel chunks s = half, half + 2, ... of this thread's row (the partner warp of the
-// quadrant takes the others); q values are fetched two own-chunks ahead.
-template <int NPC>
-__device__ __forceinline__ void tp_dq_epilogue(uint32_t tacc, int half, int nstage, int C, const __nv_bfloat16* __restrict__ qh,
-                                               const __nv_bfloat16* __restrict__ ql, float* __restrict__ dxrow, float c1,
-                                               float c2, bool rowok, __nv_bfloat16* dyh, __nv_bfloat16* dyl,
-                                               TcQChunk& qa, TcQChunk& qb) {
-  using namespace umma;
-  for (int s = half; s < nstage; s += 4) {
-    uint32_t r[32];
-    tmem_ld32(tacc + s * 32, r);
-    tmem_ld_wait();
-    tc_dq_chunk<NPC>(r, qa, dxrow + (size_t)s * 32 * NPC, C - s * 32, c1, c2, rowok,
-                     dyh ? dyh + (size_t)s * 4096 : nullptr, dyl ? dyl + (size_t)s * 4096 : nullptr, 0);
-    tc_q_load(qa, qh, ql, s + 4, nstage);
-    if (s + 2 < nstage) {
-      tmem_ld32(tacc + (s + 2) * 32, r);
-      tmem_ld_wait();
-      tc_dq_chunk<NPC>(r, qb, dxrow + (size_t)(s + 2) * 32 * NPC, C - (s + 2) * 32, c1, c2, rowok,
-                       dyh ? dyh + (size_t)(s + 2) * 4096 : nullptr, dyl ? dyl + (size_t)(s + 2) * 4096 : nullptr, 0);
-      tc_q_load(qb, qh, ql, s + 6, nstage);
+
+// ---- the epilogue warps' inner loops, written COMPACT on purpose ------------------------------------------------
+// The first version of this kernel unrolled every pass over a whole 32-column chunk, twice (register double buffers)
+// and per template variant: 244 KB of SASS, ~50 KB of it executed per item by eleven warps in four roles -- far more
+// than the 32 KB instruction cache level behind the schedulers' 6 KB L0s.  ncu: "no instruction" was the second
+// largest stall of the kernel (1.5 warp-cycles per issued instruction) and phase stamps showed a few dozen
+// instructions between two barriers taking 2-3 k cycles.  The loops below walk a row in steps of EIGHT columns
+// (tcgen05.ld 32x32b.x8, two register buffers so that the load of step n+1 flies under the arithmetic of step n) and
+// stay rolled: the body of a pass is ~250 instructions, that of the dQ epilogue ~400.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// Key-chunk order of an item.  Single-pass softmax (below) defers the release of the four chunks that hold the
+// diagonals of the item's own 128 rows until the row sums are known, so those chunks go LAST: with two row halves
+// the first half (rows 0..127, diagonals in chunks 0..3) visits 4..7 first; the second half's natural order already
+// ends on its diagonals (4..7).  nd = number of chunks visited before chunk 0 (0: natural order).
+__host__ __device__ __forceinline__ int tp_rot_count(bool rot, int nj) { return (rot && nj > 4) ? nj - 4 : 0; }
+__device__ __forceinline__ int tp_chunk_all(int k, int nd) { return k < nd ? 4 + k : k - nd; }
+// the same order restricted to the chunks of one parity (an epilogue warp takes every other chunk)
+__device__ __forceinline__ int tp_chunk_at(int k, int half, int hi_cnt) {
+  return k < hi_cnt ? 4 + half + 2 * k : half + 2 * (k - hi_cnt);
+}
+
+enum { kPassSingle = 0, kPassA = 1, kPassB = 2 };
+struct TpPassArgs {
+  const float* invk_s;       // 1 / ||k_j|| (0 for padding / non-finite keys)
+  unsigned char *dzhi, *dzlo;
+  uint64_t* dzready;
+  float a, cl, lse2, coef;
+  uint32_t rowoff;
+  int chd, lane;
+  bool x3, defer;            // defer: the warp that owns the diagonal's chunk releases it later (single pass)
+};
+
+// One step = 8 logits of this thread's row (chunk c, columns g8 * 8 ...).
+//   kPassSingle  e = exp2(y) ONCE: unnormalised e / ||k_j|| -> dZ operand (bf16 hi + lo), se += e, s2 += e y.  No running
+//                maximum is needed when the clamp cannot bind (|y| <= log2(e) / tau <= 71: exp2 and a sum of 1024 of
+//                them fit fp32); the row factor coef / se commutes with dQ' = E K and is applied in the dQ epilogue,
+//                the "- I" term is patched into the operand by the diagonal's owner once se is known.
+//   kPassA / B   the two-pass form for temperatures where the +-50 clamp can bind (patchnce_cut.py:88): A = row sum
+//                of exp2 of the clamped logits, B = dZ = (softmax - I) coef with the clamp's backward mask.
+// Padding columns (w == 0 -> y = 0 -> exp2 = 1) are kept out of se by a select: subtracting their count cancels
+// catastrophically when every real logit is far below zero (scratch/stress.py).  Replaces patchnce_cut.py:85-94 + autograd.
+template <int MODE>
+__device__ __forceinline__ void tp_pass_step(const uint32_t (&r)[8], int c, int g8, const TpPassArgs& A, float& se0,
+                                             float& se1, float& s2, float& ydacc, const TcDiag& dg) {
+  const float* wk = A.invk_s + c * 32 + g8 * 8;
+  const float4 w0 = *reinterpret_cast<const float4*>(wk), w1 = *reinterpret_cast<const float4*>(wk + 4);
+  const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+  float dd[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const float y = __uint_as_float(r[t]) * A.a * ww[t];
+    if (MODE == kPassSingle) {
+      const float e = ex2f(y);
+      if (t & 1) se1 += (ww[t] != 0.f) ? e : 0.f;
+      else se0 += (ww[t] != 0.f) ? e : 0.f;
+      s2 = fmaf(e, y, s2);
+      dd[t] = e * ww[t];
+    } else if (MODE == kPassA) {
+      const float e = ex2f(fminf(fmaxf(y, -A.cl), A.cl));
+      if (t & 1) se1 += (ww[t] != 0.f) ? e : 0.f;
+      else se0 += (ww[t] != 0.f) ? e : 0.f;
+    } else {
+      const float yc = fminf(fmaxf(y, -A.cl), A.cl);
+      float d = ex2f(yc - A.lse2) * A.coef;
+      d = (fabsf(y) <= A.cl) ? d : 0.f;                         // clamp backward mask (inclusive)
+      s2 = fmaf(d, y, s2);
+      dd[t] = d * ww[t];
     }
+  }
+  if (MODE != kPassA) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+      hw[k2] = bf16x2_bits(dd[2 * k2], dd[2 * k2 + 1]);
+      lw[k2] = bf16x2_bits(dd[2 * k2] - __uint_as_float(hw[k2] << 16), dd[2 * k2 + 1] - __uint_as_float(hw[k2] & 0xffff0000u));
+    }
+    const uint32_t off = (uint32_t)(c * 4 + g8) * 2048u + A.rowoff;       // 8-column slab of the A operand
+    *reinterpret_cast<uint4*>(A.dzhi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    if (A.x3) *reinterpret_cast<uint4*>(A.dzlo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+  if (MODE != kPassB && c == A.chd) {                           // raw accumulator of the row's diagonal element
+    const int dsel = (g8 == (A.lane >> 3)) ? (A.lane & 7) : -1;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) ydacc = (t == dsel) ? __uint_as_float(r[t]) : ydacc;
+  }
+  if (MODE != kPassA && g8 == 3) {                              // chunk complete: hand it to the MMA thread
+    if (MODE == kPassB && c == A.chd) tc_fix_diag(dg, A.x3, A.dzhi, A.dzlo);
+    umma::fence_proxy_async_smem();
+    if (!(A.defer && c == A.chd)) umma::mbar_arrive(&A.dzready[c]);       // 128 arrivals release chunk c
+  }
+}
+
+// nmine chunks of this warp's parity, in the item's chunk order; trow = TMEM address of the logits row block.
+template <int MODE>
+__device__ __forceinline__ void tp_pass(uint32_t trow, int nmine, int half, int hi_cnt, const TpPassArgs& A, float& se0,
+                                        float& se1, float& s2, float& ydacc, const TcDiag& dg) {
+  using namespace umma;
+  const int nsteps = nmine * 4;
+  if (nsteps == 0) return;
+  uint32_t ra[8], rb[8];
+  tmem_ld8(trow + tp_chunk_at(0, half, hi_cnt) * 32, ra);
+#pragma unroll 1
+  for (int st = 0; st < nsteps; st += 2) {
+    const int c = tp_chunk_at(st >> 2, half, hi_cnt), g8 = st & 3;         // g8 = 0 or 2
+    tmem_ld_wait();
+    tmem_ld8(trow + c * 32 + (g8 + 1) * 8, rb);
+    tp_pass_step<MODE>(ra, c, g8, A, se0, se1, s2, ydacc, dg);
+    tmem_ld_wait();
+    if (st + 2 < nsteps) tmem_ld8(trow + tp_chunk_at((st + 2) >> 2, half, hi_cnt) * 32 + ((st + 2) & 3) * 8, ra);
+    tp_pass_step<MODE>(rb, c, g8 + 1, A, se0, se1, s2, ydacc, dg);
   }
 }
 
@@ -138,6 +233,7 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long total = m.start[p.n_layers];
   const bool x3 = (p.math == PNCE_MATH_TC_BF16X3);
+  const bool single_pass = !((1.0f / p.tau) * 1.02f > kClamp);  // |cos| <= 1: the +-50 clamp cannot bind (every CUT temperature)
   volatile int* dead = &sh->dead;
   if (p.trace != nullptr && tid == 0) {                       // debug timeline: (sm id, start ns, end ns) per CTA
     unsigned sm; unsigned long long t;
@@ -150,9 +246,9 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
   // at trace[64 + 3 * grid + (sel * 8 + n) * 16 + slot]
   long long* trs = nullptr;
   if (p.trace != nullptr && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2))
-    trs = p.trace + 64 + 3 * (size_t)gridDim.x + (blockIdx.x ? 128 : 0);
+    trs = p.trace + 64 + 3 * (size_t)gridDim.x + (blockIdx.x ? 256 : 0);
 #ifdef PNCE_EXPERIMENTS
-#define PNCE_TS(n_, slot_) do { if (trs && (n_) < 8) trs[(n_) * 16 + (slot_)] = clock64(); } while (0)
+#define PNCE_TS(n_, slot_) do { if (trs && (n_) < 8) trs[(n_) * 32 + (slot_)] = clock64(); } while (0)
 #else
 #define PNCE_TS(n_, slot_) do { } while (0)
 #endif
@@ -211,8 +307,9 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
         if (ok) ok = mbar_wait(&sh->zfull, (uint32_t)n & 1u, dead);    // phase-1 MMAs drained: ring changes geometry
         PNCE_TS(n, 12);
         const int ns2 = tp_slots2(t.Cp);
-        for (int j = 0; j < t.nj && ok; ++j) {
-          const int slot = j % ns2;
+        const int nd = tp_rot_count(single_pass && t.halves == 2 && t.mh == 0, t.nj);
+        for (int k = 0; k < t.nj && ok; ++k) {
+          const int slot = k % ns2, j = tp_chunk_all(k, nd);  // the MMA thread's chunk order
           ok = mbar_wait(&sh->empty2[slot], (e2par >> slot) & 1u, dead);
           e2par ^= 1u << slot;
           if (!ok) break;
@@ -285,11 +382,12 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
         //      epilogue threads' program order (tcgen05 fences on both sides of dzready) ----
         const int ns2 = tp_slots2(t.Cp);
         const uint32_t k2bytes = (uint32_t)t.Cp * 64u;
-        for (int j = 0; j < t.nj && ok; ++j) {
-          const int slot = j % ns2;
+        const int nd = tp_rot_count(single_pass && t.halves == 2 && t.mh == 0, t.nj);
+        for (int k = 0; k < t.nj && ok; ++k) {
+          const int slot = k % ns2, j = tp_chunk_all(k, nd);  // diagonal chunks last (released after the row sums)
           ok = mbar_wait(&sh->dzready[j], (dzphase >> j) & 1u, dead);
           dzphase ^= 1u << j;
-          if (j == 0) PNCE_TS(n, 8);
+          if (k == 0) PNCE_TS(n, 8);
           if (ok) ok = mbar_wait(&sh->full2[slot], (f2par >> slot) & 1u, dead);
           f2par ^= 1u << slot;
           tc_fence_after();
@@ -298,7 +396,7 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
           for (int ks = 0; ks < 2; ++ks) {                   // 16 keys per MMA
             const uint64_t a_hi = smem_desc(dzh + (uint32_t)(j * 2 + ks) * 4096u, 2048, 128);
             const uint64_t b_hi = smem_desc(st + (uint32_t)ks * 2u * lbo2, lbo2, 128);
-            mma_bf16(tmem + 256u, a_hi, b_hi, idesc2, (j | ks) ? 1u : 0u);
+            mma_bf16(tmem + 256u, a_hi, b_hi, idesc2, (k | ks) ? 1u : 0u);
             if (x3) {
               const uint64_t a_lo = smem_desc(dzl + (uint32_t)(j * 2 + ks) * 4096u, 2048, 128);
               const uint64_t b_lo = smem_desc(st + k2bytes + (uint32_t)ks * 2u * lbo2, lbo2, 128);
@@ -344,7 +442,7 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
     const int et = tid - 64;                                 // 0..255
     const float inv_tau = 1.0f / p.tau;
     const float cl = kClamp * kLog2e;
-    const bool need_clamp = inv_tau * 1.02f > kClamp;        // |cos| <= 1: the clamp cannot bind otherwise
+    const bool need_clamp = !single_pass;
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t rowoff = (uint32_t)(i >> 3) * 128u + (uint32_t)(i & 7) * 16u;
     if (et != 0) trs = nullptr;
@@ -388,83 +486,88 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
       const float coef = rowok ? 1.0f / ((float)P * (float)p.B * (float)p.n_layers) : 0.f;
       const int chd = (gi & 255) >> 5;                        // chunk holding this row's diagonal (warp-uniform)
       const int nch = t.nj;                                   // chunks that hold real columns
-      const bool pad = (nch * 32 != P);                       // the last chunk holds padding columns (masked in pass A)
-      // ---- pass A: row sum of exp2 over this warp's chunks, diagonal ----
-      mbar_wait(&sh->zfull, par, dead);
-      tc_fence_after();
-      PNCE_TS(n, 1);
-      float se4[4] = {0.f, 0.f, 0.f, 0.f};
-      float ydacc = 0.f;                                      // raw accumulator of the diagonal element
-      for (int ch = half; ch < nch; ch += 2) {
-        uint32_t r[32];
-        tmem_ld32(trow + ch * 32, r);
-        tmem_ld_wait();
-        if (pad && ch == nch - 1) {
-          if (need_clamp) tc_pass_a_masked<true>(r, invk_s + ch * 32, a, cl, se4);
-          else tc_pass_a_masked<false>(r, invk_s + ch * 32, a, cl, se4);
-        } else if (need_clamp) tc_pass_a<true>(r, invk_s + ch * 32, a, cl, se4);
-        else tc_pass_a<false>(r, invk_s + ch * 32, a, cl, se4);
-        if (ch == chd) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) ydacc = (k == lane) ? __uint_as_float(r[k]) : ydacc;
-        }
-      }
-      float se = (se4[0] + se4[1]) + (se4[2] + se4[3]);
-      if (half == 1) sh->xch[i] = se;
-      // raw q for the dQ epilogue comes from this row's slice of the Q operand blob: pulled into L2 now
-      // (the lines fly under pass B)
+      const bool single = !need_clamp;
+      const bool rot = single && t.halves == 2 && mh == 0;    // chunk order of the item: tp_rot_count
+      const int nmine = (nch - half + 1) >> 1;                // chunks of this warp's parity
+      const int hi_cnt = (rot && nch > 4 + half) ? (nch - 4 - half + 1) >> 1 : 0;
+      // raw q of this row for the dQ epilogue comes from its slice of the Q operand blob
       const size_t qoff = (((size_t)b * t.halves + mh) * t.Cp8 * 16 + (size_t)(i >> 3)) * 64 + (size_t)(i & 7) * 8;
       const __nv_bfloat16* __restrict__ qh = L.qhi + qoff;
       const __nv_bfloat16* __restrict__ ql = (x3 && L.qlo != nullptr) ? L.qlo + qoff : nullptr;
-      if ((i & 7) == 0) {                                      // 8 rows share each 128-byte line
-        for (int s8 = half; s8 < nstage * 4; s8 += 2) {
+      // the warp that owns the diagonal's chunk owns the diagonal logit, the row loss and the "- I" fix-up
+      const bool own = (chd & 1) == half && chd < nch;
+      const float wd = invk_s[gi & 255];                      // 1 / ||k_i|| of the row's own key
+      TpPassArgs A;
+      A.invk_s = invk_s; A.dzhi = dzhi; A.dzlo = dzlo; A.dzready = sh->dzready;
+      A.a = a; A.cl = cl; A.lse2 = 0.f; A.coef = coef; A.rowoff = rowoff; A.chd = chd; A.lane = lane; A.x3 = x3;
+      A.defer = single;
+      TcDiag dg;
+      dg.rowok = rowok; dg.pass = true; dg.d_w = 0.f;
+      dg.off = (uint32_t)((gi & 255) >> 3) * 2048u + rowoff + (uint32_t)(gi & 7) * 2u;
+      mbar_wait(&sh->zfull, par, dead);
+      tc_fence_after();
+      PNCE_TS(n, 1);
+      if ((i & 7) == 0) {                                      // 8 rows share each 128-byte line: pull raw q into L2
+        for (int s8 = half; s8 < nstage * 4; s8 += 2) {        // (the lines fly under the pass)
           prefetch_l2(qh + (size_t)s8 * 1024);
           if (ql != nullptr) prefetch_l2(ql + (size_t)s8 * 1024);
         }
       }
+      float se0 = 0.f, se1 = 0.f, s2 = 0.f, ydacc = 0.f;
+      if (single) {
+        // ---- ONE pass: exp2 once, unnormalised operand, row sums alongside ----
+        tp_pass<kPassSingle>(trow, nmine, half, hi_cnt, A, se0, se1, s2, ydacc, dg);
+        PNCE_TS(n, 3);
+        tc_fence_before();
+        mbar_arrive(&sh->zfree);                               // the logits tile may be overwritten by the next item
+        mbar_arrive(&sh->normfree);                            // and so may invk_s / badk (wd, badrow were read above)
+      } else {
+        // ---- pass A: row sum of exp2 of the clamped logits ----
+        tp_pass<kPassA>(trow, nmine, half, 0, A, se0, se1, s2, ydacc, dg);
+      }
+      float se = se0 + se1;
+      if (half == 1) { sh->xch[0][i] = se; sh->xch[1][i] = s2; }
+      if (own) sh->xch[2][i] = ydacc * a * wd;                 // diagonal logit (log2 units), unclamped
+      // next item's row sums of squares: the loads fly under the exchange and what follows
+      if (item + gridDim.x < total) tp_row_ss_load(p, m, item + gridDim.x, i, ssq);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (half == 0) {
-        se += sh->xch[i];
-        sh->xch[i] = se;
+        se += sh->xch[0][i]; sh->xch[0][i] = se;
+        if (single) { s2 += sh->xch[1][i]; sh->xch[1][i] = s2; }
       }
+      const float ydr = sh->xch[2][i];
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (half == 1) se = sh->xch[i];
+      if (half == 1) { se = sh->xch[0][i]; if (single) s2 = sh->xch[1][i]; }
       PNCE_TS(n, 2);
-      // next item's row sums of squares: the loads fly under pass B
-      if (item + gridDim.x < total) tp_row_ss_load(p, m, item + gridDim.x, i, ssq);
-      // the warp that owns the diagonal's chunk (chd) owns the diagonal logit, the row loss and the "- I" fix-up
-      const bool own = (chd & 1) == half;
-      const float wd = invk_s[gi & 255];
-      const float ydr = ydacc * a * wd;                       // unclamped diagonal logit (log2 units); owner only
-      const float yd = need_clamp ? fminf(fmaxf(ydr, -cl), cl) : ydr;
       const float lse2 = lg2f(se);
+      const float yd = single ? ydr : fminf(fmaxf(ydr, -cl), cl);
       float rowloss = (rowok && own) ? (lse2 - yd) * kLn2 : 0.f;            // :94, labels = arange
       if (badrow && rowok && own) rowloss = __int_as_float(0x7fc00000);
-      // ---- pass B: dZ (pre-divided by ||k_j||) -> smem A operand chunk by chunk, s_i ----
-      float s2 = 0.f;
-      TcDiag dg;
-      dg.rowok = rowok;
-      dg.pass = !need_clamp || fabsf(ydr) <= cl;
-      dg.d_w = dg.pass ? (ex2f(yd - lse2) - 1.f) * coef * wd : 0.f;
-      dg.off = (uint32_t)((gi & 255) >> 3) * 2048u + rowoff + (uint32_t)(gi & 7) * 2u;
-      PNCE_TS(n, 14);
-      for (int ch = half; ch < nch; ch += 2) {
-        uint32_t r[32];
-        tmem_ld32(trow + ch * 32, r);
-        tmem_ld_wait();
-        if (ch == half) PNCE_TS(n, 15);
-        if (need_clamp) tc_pass_b<true>(r, invk_s + ch * 32, a, cl, lse2, coef, x3, dzhi, dzlo, (uint32_t)(ch * 4) * 2048u + rowoff, s2);
-        else tc_pass_b<false>(r, invk_s + ch * 32, a, cl, lse2, coef, x3, dzhi, dzlo, (uint32_t)(ch * 4) * 2048u + rowoff, s2);
-        if (ch == chd) tc_fix_diag(dg, x3, dzhi, dzlo);
-        fence_proxy_async_smem();
-        mbar_arrive(&sh->dzready[ch]);                         // 128 arrivals release chunk ch to the MMA thread
+      if (single) {
+        if (own) {
+          // the "- I" term: dQ' = sum_j e_ij k^_j - se_i k^_i, i.e. the diagonal entry of the operand becomes
+          // (e_ii - se_i) / ||k_i||; this warp's 32 arrivals then release the chunk
+          dg.d_w = (ex2f(ydr) - se) * wd;
+          tc_fix_diag(dg, x3, dzhi, dzlo);
+          fence_proxy_async_smem();
+          mbar_arrive(&sh->dzready[chd]);
+        }
+        s2 = coef * (s2 / se - ydr);                            // sum_j dZ_ij y_ij with dZ = coef (e / se - I)
+      } else {
+        // ---- pass B: dZ (pre-divided by ||k_j||) -> smem A operand chunk by chunk, s_i ----
+        dg.pass = fabsf(ydr) <= cl;
+        dg.d_w = dg.pass ? (ex2f(yd - lse2) - 1.f) * coef * wd : 0.f;
+        A.lse2 = lse2;
+        PNCE_TS(n, 14);
+        s2 = 0.f;
+        tp_pass<kPassB>(trow, nmine, half, 0, A, se0, se1, s2, ydacc, dg);
+        PNCE_TS(n, 3);
+        tc_fence_before();
+        mbar_arrive(&sh->zfree);
+        mbar_arrive(&sh->normfree);
+        if (rowok && own && dg.pass) s2 = fmaf(-coef, ydr, s2);  // the diagonal's "- I" term of sum_j dZ_ij y_ij
+        if (half == 1) sh->xch[1][i] = s2;
       }
-      PNCE_TS(n, 3);
-      tc_fence_before();
-      mbar_arrive(&sh->zfree);                                 // the logits tile may be overwritten by the next item
-      mbar_arrive(&sh->normfree);                              // and so may invk_s / qnrm / badk
-      if (rowok && own && dg.pass) s2 = fmaf(-coef, ydr, s2);  // the diagonal's "- I" term of sum_j dZ_ij y_ij
-      if (half == 1) sh->xch[i] = s2;
       // row losses: warp shuffle, then one partial per item (deterministic order)
       rowloss = warp_sum(rowloss);
       if (lane == 0) sh->red[n & 1][half * 4 + q] = rowloss;
@@ -473,29 +576,29 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
         const float* rd = sh->red[n & 1];
         L.partial[(size_t)b * L.nparts + mh] = ((rd[0] + rd[4]) + (rd[1] + rd[5])) + ((rd[2] + rd[6]) + (rd[3] + rd[7]));
       }
-      if (half == 0) {
-        s2 += sh->xch[i];
-        sh->xch[i] = s2;
+      if (!single) {
+        if (half == 0) { s2 += sh->xch[1][i]; sh->xch[1][i] = s2; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 1) s2 = sh->xch[1][i];
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (half == 1) s2 = sh->xch[i];
       const float s_i = s2 * kLn2;                              // sum_j dZ_ij z_ij
       // ---- dQ epilogue: dq/tau -> normalise backward -> dxT (coalesced: lane <-> consecutive slot) ----
       //   dx = dq*sc - q_raw * (sc^2 s_i)       with dq = acc / tau;  g / eps when ||q|| < eps
-      const float c1 = inv_tau * sc;
+      //   single pass: acc holds the unnormalised sum, dq = (coef / se) acc / tau
+      const float c1 = single ? inv_tau * sc * (coef / se) : inv_tau * sc;
       const float c2 = (noproj || p.rows_mode) ? 0.f : sc * sc * s_i;   // rows API: rows are used as given, no projection
       float* __restrict__ dxrow = L.dxT + (size_t)b * C * Ppad + (rowok ? gi : 0);   // dxpitch == Ppad on this path
       __nv_bfloat16* dyh = L.dyhi ? L.dyhi + qoff : nullptr;   // head mode: d loss / d (head output) as a row blob
       __nv_bfloat16* dyl = (L.dyhi && L.dylo) ? L.dylo + qoff : nullptr;
-      TcQChunk qa, qb;                                         // this warp's first two channel chunks of raw q:
-      tc_q_load(qa, qh, ql, half, nstage);                     // in flight while the dQ MMAs finish
-      tc_q_load(qb, qh, ql, half + 2, nstage);
+      TcQChunk qn;                                             // this warp's first channel chunk of raw q: in flight
+      if (!p.rows_mode) tc_q_load(qn, qh, ql, half, nstage);   // while the dQ MMAs finish
       mbar_wait(&sh->dqfull, par, dead);
       tc_fence_after();
       PNCE_TS(n, 4);
       if (p.rows_mode) {
         // module-split rows API: d loss / d q row-major, rows in the caller's order (the raw q values are not needed)
         float* __restrict__ drow = L.dq_rows + ((size_t)b * P + (rowok ? gi : 0)) * C;
+#pragma unroll 1
         for (int s = half; s < nstage; s += 2) {
           uint32_t r[32];
           tmem_ld32(trow + 256u + s * 32, r);
@@ -515,8 +618,20 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
             }
           }
         }
-      } else if (Ppad == 128) tp_dq_epilogue<128>(trow + 256u, half, nstage, C, qh, ql, dxrow, c1, c2, rowok, dyh, dyl, qa, qb);
-      else tp_dq_epilogue<256>(trow + 256u, half, nstage, C, qh, ql, dxrow, c1, c2, rowok, dyh, dyl, qa, qb);
+      } else {
+        // this warp's channel chunks s = half, half + 2, ... (the partner warp of the quadrant takes the others);
+        // raw q is fetched one own-chunk ahead
+#pragma unroll 1
+        for (int s = half; s < nstage; s += 2) {
+          uint32_t r[32];
+          tmem_ld32(trow + 256u + s * 32, r);
+          const TcQChunk qc = qn;
+          tc_q_load(qn, qh, ql, s + 2, nstage);
+          tmem_ld_wait();
+          tc_dq_chunk<0>(r, qc, dxrow + (size_t)s * 32 * Ppad, C - s * 32, c1, c2, rowok,
+                         dyh ? dyh + (size_t)s * 4096 : nullptr, dyl ? dyl + (size_t)s * 4096 : nullptr, Ppad);
+        }
+      }
       tc_fence_before();
       PNCE_TS(n, 5);
     }
@@ -535,7 +650,7 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     p.trace[64 + 3 * (size_t)blockIdx.x + 2] = (long long)t;
   }
-  last_cta_finalize(p, &sh->flag);
+  last_cta_finalize(p, &sh->flag, smem);                       // every CTA-wide phase is over (the __syncthreads above): the ring is free scratch
 }
 
 }  // namespace pnce
