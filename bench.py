@@ -326,18 +326,19 @@ def main():
         time.sleep(args.settle)
     if rank == 0:
         sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the cyclic garbage collector stays out of the timed region (what timeit does): a full collection over
+    # torch's heap takes 3-15 ms, and it used to land on the second timed step, when nothing is queued ahead
+    # of the host yet -- one long step in an otherwise flat series (step_us.max / max_at_step).  Collected and
+    # switched off BEFORE the warm-up steps, so that they run in the regime of the timed ones (a collection
+    # between the two also walks the whole heap through the CPU caches right before the first timed step).
+    gc.collect()
+    gc.disable()
     for _ in range(max(args.warmup, 3)):
         loss = step()                       # same object lifetimes as in the timed loop (the allocator's steady state)
     barrier()
     if rank == 0:
         sampler.begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # the cyclic garbage collector stays out of the timed region (what timeit does): a full collection over
-    # torch's heap takes 3-15 ms, and it used to land on the second timed step, when nothing is queued ahead
-    # of the host yet -- one long step in an otherwise flat series (step_us.max / max_at_step)
-    gc.collect()
-    gc.disable()
-    barrier()
     e0.record()
     for i in range(args.steps):
         h0 = time.perf_counter()

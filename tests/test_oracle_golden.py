@@ -105,6 +105,32 @@ def test_survey_tripwire_full_size(golden_dir, b):
             assert np.linalg.norm(gnp) == pytest.approx(float(d[f"gnorm{i}"]), rel=1e-4)
 
 
+def test_oracle_on_the_frozen_generator_maps(golden_dir):
+    """Both restatements of the oracle against the reference's loss and gradients on the feature maps of the unmodified
+    ResNetGenerator (oracle/make_golden_generator.py): dead post-ReLU patches (the g / eps branch of F.normalize's
+    backward, patchnce_cut.py:77-78) and 16x16 maps sampled several times per position."""
+    d = np.load(os.path.join(golden_dir, "generator_maps_b5.npz"))
+    n = int(d["n_layers"])
+    src = [d[f"src{i}"] for i in range(n)]
+    tgt = [d[f"tgt{i}"] for i in range(n)]
+    ids = [d[f"ids{i}"] for i in range(n)]
+    up = float(d["upstream"])
+    loss, _, grads = orc.patchnce_loss_and_grads_np(src, tgt, ids, 0.07, upstream=up)
+    assert loss == pytest.approx(float(d["loss"]), rel=2e-6)
+    for i in range(n):
+        want = d[f"grad{i}"].astype(np.float64)
+        assert np.abs(grads[i] - want).max() <= 2e-4 * np.abs(want).max()
+    # the op-for-op torch port draws the same ids from the same seed
+    t = [torch.from_numpy(x).requires_grad_() for x in tgt]
+    torch.manual_seed(7)
+    tl, tids = orc.patchnce_loss_torch([torch.from_numpy(x) for x in src], t, 0.07, 256)
+    (tl * up).backward()
+    assert tl.item() == pytest.approx(float(d["loss"]), rel=1e-6)
+    for i in range(n):
+        np.testing.assert_array_equal(tids[i].numpy(), ids[i])
+        np.testing.assert_allclose(t[i].grad.numpy(), d[f"grad{i}"], rtol=1e-4, atol=1e-6 * np.abs(d[f"grad{i}"]).max())
+
+
 def test_invalid_layer_ids_are_skipped_and_mean_divides_by_returned_maps(golden_dir):
     """[0,4,8,12,16] returns 4 maps (id 16 never matches) and the loss divides by 4
     (generator_resnet_attn.py:203-235, patchnce_cut.py:40).  Checked with a stub generator that

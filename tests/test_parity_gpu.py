@@ -87,6 +87,41 @@ def test_fused_matches_reference_goldens(pn, path, math):
     assert pn.poll_nonfinite_warnings(block=True) >= 0      # raises on a kernel protocol timeout
 
 
+def _assert_rows_close(got, want, ids, rtol, what):
+    """Gradient rows (one per sampled position, all channels) compared each against ITS OWN largest entry: a dead
+    post-ReLU patch (||q|| < eps -> the g / eps branch, patchnce_cut.py:77 backward) has rows ~1e6 times larger than
+    its neighbours and would hide every other row behind a single max-norm."""
+    b, c = got.shape[:2]
+    g = got.reshape(b, c, -1)[:, :, np.unique(ids)].astype(np.float64)
+    w = want.reshape(b, c, -1)[:, :, np.unique(ids)].astype(np.float64)
+    scale = np.maximum(np.abs(w).max(axis=1, keepdims=True), 1e-12 * np.abs(w).max())
+    err = (np.abs(g - w) / scale).max()
+    assert err <= rtol, f"{what}: row-relative err {err:.3e} > {rtol}"
+
+
+@pytest.mark.parametrize("math", ["simt_f32", "tc_bf16x3"])
+def test_real_generator_maps_match_the_reference(pn, math):
+    """Feature maps of the unmodified reference ResNetGenerator (generator_resnet_attn.py:190-235, frozen by
+    oracle/make_golden_generator.py) through the CUDA path: real post-InstanceNorm / post-ReLU / residual-sum statistics
+    (dead 8-channel patches that take the g / eps branch, 16x16 maps where 256 draws hit every position several
+    times).  The fixture's ids are passed in (torch's CPU and CUDA generators draw different streams; the id law is
+    tested separately); loss and d loss / d tgt_feat against the reference's own."""
+    d = np.load(os.path.join(HERE, "golden", "generator_maps_b5.npz"))
+    n = int(d["n_layers"])
+    src = [dev(d[f"src{i}"]) for i in range(n)]
+    tgt = [dev(d[f"tgt{i}"]).requires_grad_() for i in range(n)]
+    ids = [dev(d[f"ids{i}"]) for i in range(n)]
+    loss = pn.fused_patchnce(src, tgt, ids, 0.07, math=math)
+    (loss * float(d["upstream"])).backward()
+    ltol, gtol = MATH_TOL[math]
+    assert loss.item() == pytest.approx(float(d["loss"]), rel=ltol)
+    for i in range(n):
+        got, want = tgt[i].grad.cpu().numpy(), d[f"grad{i}"]
+        assert_grad_close(got, want, gtol, f"layer {i}", ids=d[f"ids{i}"])
+        _assert_rows_close(got, want, d[f"ids{i}"], 5 * gtol, f"layer {i}")
+    assert pn.poll_nonfinite_warnings(block=True) == 0
+
+
 def test_nonfinite_images_are_counted_and_reported(pn, capsys):
     d, src, tgt, ids, _ = load_small(os.path.join(HERE, "golden", "small_nan_image.npz"))
     pn.poll_nonfinite_warnings(block=True)
