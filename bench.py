@@ -410,10 +410,13 @@ def main():
         hm = head_line(args, pn, src, tgt, math, patches_per_image, world, dev)
         st = strong_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers, elem, peak)
         sc = nccl_selfcheck(args, pn, layers, dev, world, rank, math) if world > 1 else None
+        gr = grad_reducer_line(pn, dev, world) if world > 1 else None
         if rank == 0:
             out["head_mode"], out["strong"] = hm, st
             if sc is not None:
                 out["nccl_selfcheck"] = sc
+            if gr is not None:
+                out["grad_reducer"] = gr
     if rank == 0 and world == 1 and not args.head and not args.no_head_line:
         out["module_split"] = module_split_line(args, pn, src, tgt, math, patches_per_image)
         out["configs"] = config_lines(args, pn, layers, dev, math, peak)
@@ -683,6 +686,59 @@ def nccl_selfcheck(args, pn, layers, dev, world, rank, math, b=2):
         except Exception:  # noqa: BLE001
             pass
         return {"ok": False, "error": f"{type(e).__name__}: {e}"} if rank == 0 else None
+
+
+def grad_reducer_line(pn, dev, world, n=20):
+    """N > 1, SURVEY.md 8f row 1 (BASELINE config 5: "NCCL allreduce of netF/G/D grads"): dp.GradReducer averaging the
+    gradients of a parameter set shaped like the reference generator (tests/golden/model_param_shapes.json, 11.4 M
+    values in 48 tensors, 45.5 MB) over the N ranks -- flat fp32 buckets all-reduced (mean) on a side stream from
+    post-accumulate-grad hooks, written back at the end of backward().  The backward pass here is the cheapest
+    one that reaches every parameter (loss = sum of the parameter sums), so the number is the reducer's own cost:
+    hooks, bucket copies, NCCL, write-back -- not hidden under a generator backward as it is in training."""
+    import torch.distributed as dist
+    from gan_variant_research_b200 import dp
+    try:
+        shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "model_param_shapes.json")))["generator"]
+        torch.manual_seed(100 + dist.get_rank())
+        params = [torch.randn(*s, device=dev).requires_grad_() for s in shapes]
+
+        def backward():
+            for p in params:
+                p.grad = None
+            total = params[0].sum()
+            for p in params[1:]:
+                total = total + p.sum()
+            total.backward()
+
+        def timed():
+            for _ in range(5):
+                backward()
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                backward()
+            e1.record()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        plain = timed()
+        red = dp.GradReducer(params)
+        with_red = timed()
+        # averaged gradients are identical on every rank (each rank's own are all ones here: the mean is 1)
+        ok = all(bool(torch.allclose(p.grad, torch.ones_like(p))) for p in params)
+        red.remove()
+        nbytes = 4 * sum(p.numel() for p in params)
+        return {"n_gpus": world, "tensors": len(params), "bytes": nbytes, "buckets": len(red.buckets),
+                "backward_ms": plain, "backward_with_reducer_ms": with_red, "reducer_ms": with_red - plain,
+                "allreduce_gbs": nbytes / max(with_red - plain, 1e-9) / 1e6, "averaged_ok": ok,
+                "what": "dp.GradReducer on reference-generator-shaped parameters, NCCL all-reduce(mean) per bucket"}
+    except Exception as e:  # noqa: BLE001 - secondary
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def config_lines(args, pn, layers, dev, math, peak):
