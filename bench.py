@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--tau", type=float, default=0.07)
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--math", default=None)
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"],
+                    help="nhwc: the maps are torch.channels_last (an extension of the reference's interface: the gather "
+                         "then reads contiguous rows); the default is the reference's contiguous NCHW")
     ap.add_argument("--cpu-batch", type=int, default=4, help="images in the CPU-baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-steps", type=int, default=10)
@@ -251,6 +254,8 @@ def workload_config(args, layers):
                     f"), P={args.patches}, tau={args.tau}, batch {args.batch} images per GPU "
                     "(BASELINE config 5 per-GPU batch, weak scaling), reference-exact mode (no netF head)",
         "layers": args.layers, "batch_per_gpu": args.batch, "num_patches": args.patches,
+        "layout": "nchw (the reference's contiguous maps)" if args.layout == "nchw" else
+                  "nhwc (torch.channels_last maps: an extension, not the reference's interface)",
         "l2_policy": "inputs larger than L2 (feature maps >> 126 MB), no explicit flush",
         "parallelism": f"dp{args.gpus} (batch sharded, identical ids, no collective in no-head mode)",
     }
@@ -279,6 +284,9 @@ def main():
     math = args.math or pn.DEFAULT_MATH
     B = args.batch
     src, tgt = make_maps(layers, B, tdtype, dev, 1234 + rank)
+    if args.layout == "nhwc":
+        src = [x.contiguous(memory_format=torch.channels_last) for x in src]
+        tgt = [x.contiguous(memory_format=torch.channels_last) for x in tgt]
     tgt = [t.requires_grad_() for t in tgt]
     crit = pn.PatchNCELoss(args.tau, args.patches, [0, 4, 8, 12, 13], math=math)
     netF = None
@@ -363,9 +371,10 @@ def main():
     peak, peak_src = peaks()
 
     dense_bytes = dense_kernel_bytes_per_image(layers, args.patches, elem) * B
-    roof = {"bound": "hbm", "kernel": "k_dense_flat (dense d tgt_feat: zero fill + sampled values, one write per line)",
+    dense_name = "k_dense_nhwc" if args.layout == "nhwc" and not args.head else "k_dense_flat"
+    roof = {"bound": "hbm", "kernel": dense_name + " (dense d tgt_feat: zero fill + sampled values, one write per line)",
             "achieved": dense_bytes / (bwd_med * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            "peak_source": peak_src, "traffic": ncu_traffic("k_dense_flat", B, elem), "launch_ms": bwd_med}
+            "peak_source": peak_src, "traffic": ncu_traffic(dense_name, B, elem), "launch_ms": bwd_med}
     roof["note"] = ("write-only stream (zero fill + sampled values): it can exceed the measured peak, which is a "
                     "read+write copy (6457 GB/s); cudaMemset of the same bytes reaches ~7.3 TB/s on this GPU")
     if args.head:
@@ -409,6 +418,9 @@ def main():
         # every rank takes part (world > 1: the head-gradient all-reduce is a collective); rank 0 reports
         hm = head_line(args, pn, src, tgt, math, patches_per_image, world, dev)
         st = strong_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers, elem, peak)
+        nh = nhwc_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers, elem, peak) if args.layout == "nchw" else None
+        if rank == 0 and nh is not None:
+            out["nhwc"] = nh
         sc = nccl_selfcheck(args, pn, layers, dev, world, rank, math) if world > 1 else None
         gr = grad_reducer_line(pn, dev, world) if world > 1 else None
         if rank == 0:
@@ -633,6 +645,53 @@ def strong_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers,
     except Exception as e:  # noqa: BLE001 - secondary
         out["graph_replay"] = {"error": f"{type(e).__name__}: {e}"}
     return out
+
+
+def nhwc_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers, elem, peak, steps=20):
+    """Secondary measurement at EVERY N: the same values stored channels-last (torch.channels_last), through the same
+    PatchNCELoss.forward + backward.  NOT the reference's interface (its .view(B, C, -1) takes contiguous NCHW only):
+    an extension for generators run in channels_last, reported beside the parity mode, never instead of it.  The
+    path roofline uses the same algorithmic bytes (a patch is 2 P C useful bytes in either layout)."""
+    try:
+        cl = torch.channels_last
+        s_src = [x.contiguous(memory_format=cl) for x in src]
+        s_tgt = [x.detach().contiguous(memory_format=cl).requires_grad_() for x in tgt]
+        crit = pn.PatchNCELoss(args.tau, args.patches, [0, 4, 8, 12, 13], math=math)
+        torch.manual_seed(7)
+
+        def step():
+            for t in s_tgt:
+                t.grad = None
+            crit(s_src, s_tgt).backward()
+
+        ms = timed_steps(step, steps, 5, world, dev)
+        path_bytes = algorithmic_bytes_per_image(layers, args.patches, elem) * args.batch
+        out = {"ms_per_step": ms, "value": world * args.batch * patches_per_image / (ms * 1e-3), "unit": UNIT,
+               "steps": steps, "n_gpus": world, "scaling": "weak", "layout": "channels_last (B, H, W, C) storage",
+               "roofline_path": {"bound": "hbm", "achieved": path_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": path_bytes / (ms * 1e-3) / 1e9 / peak},
+               "kernels_us": kernel_breakdown(step),
+               "note": "extension: channels-last maps (the reference's .view rejects them); same ids / loss / gradient law"}
+        b = 64 // world if 64 % world == 0 and 64 // world <= args.batch else None
+        if b is not None and b < args.batch:                   # strong scaling of the global batch of 64 in this layout
+            t_src = [x[:b] for x in s_src]
+            t_tgt = [x.detach()[:b].requires_grad_() for x in s_tgt]
+
+            def sstep():
+                for t in t_tgt:
+                    t.grad = None
+                crit(t_src, t_tgt).backward()
+
+            sms = timed_steps(sstep, 200, 10, world, dev)
+            d_tgt = [t.detach() for t in t_tgt]
+            dms = timed_steps(lambda: crit.loss_and_grads(t_src, d_tgt), 200, 10, world, dev)
+            out["strong"] = {"global_batch": 64, "batch_per_gpu": b, "ms_per_step": sms,
+                             "value": 64 * patches_per_image / (sms * 1e-3), "direct_ms_per_step": dms,
+                             "direct_value": 64 * patches_per_image / (dms * 1e-3)}
+        del s_src, s_tgt
+        return out
+    except Exception as e:  # noqa: BLE001 - secondary
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def nccl_selfcheck(args, pn, layers, dev, world, rank, math, b=2):

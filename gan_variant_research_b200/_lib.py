@@ -11,11 +11,12 @@ MATH_SIMT_F32, MATH_TC_BF16X3, MATH_TC_BF16 = 0, 1, 2
 MAX_LAYERS = 8
 MAX_PATCHES = 4096
 MAX_CHANNELS = 1024
-ABI_VERSION = 3
+ABI_VERSION = 4
+LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 
 EXPORTS = [
     "pnce_abi_version", "pnce_status_string", "pnce_last_cuda_error", "pnce_workspace_bytes",
-    "pnce_fwd", "pnce_bwd", "pnce_fwd_draw", "pnce_plan_ids_draw", "pnce_draw_ids", "pnce_plan_bytes", "pnce_plan_ids", "pnce_fwd_planned", "pnce_bwd_planned", "pnce_sample_fwd", "pnce_sample_bwd_workspace_bytes",
+    "pnce_fwd", "pnce_bwd", "pnce_fwd_ex", "pnce_bwd_ex", "pnce_fwd_draw", "pnce_plan_ids_draw", "pnce_draw_ids", "pnce_plan_bytes", "pnce_plan_ids", "pnce_fwd_planned", "pnce_bwd_planned", "pnce_sample_fwd", "pnce_sample_bwd_workspace_bytes",
     "pnce_sample_bwd", "pnce_sample_multi_fwd", "pnce_sample_multi_bwd_workspace_bytes", "pnce_sample_multi_bwd",
     "pnce_rows_loss_workspace_bytes", "pnce_rows_loss_fwd_bwd", "pnce_selftest_umma",
     "pnce_multi_chunk_elems", "pnce_multi_axpby", "pnce_amp_adam_scratch_floats", "pnce_amp_adam_step",
@@ -73,6 +74,9 @@ def load():
     lib.pnce_plan_ids_draw.argtypes = [ctypes.POINTER(PnceLayer), i32, u64, u64, vp, sz, vp]
     lib.pnce_draw_ids.argtypes = [ctypes.POINTER(PnceLayer), i32, u64, u64, vp]
     lib.pnce_bwd.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, i32, vp, sz, vp, vp]
+    lib.pnce_fwd_ex.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, i32, f32, i32, vp, sz, vp, sz,
+                                ctypes.POINTER(u64), vp, vp, vp]
+    lib.pnce_bwd_ex.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, i32, i32, vp, sz, vp, sz, vp, vp]
     lib.pnce_plan_bytes.argtypes = [ctypes.POINTER(PnceLayer), i32, ctypes.POINTER(sz)]
     lib.pnce_plan_ids.argtypes = [ctypes.POINTER(PnceLayer), i32, vp, sz, vp]
     lib.pnce_fwd_planned.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, f32, i32, vp, sz, vp, sz, vp, vp, vp]

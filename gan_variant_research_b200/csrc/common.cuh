@@ -62,6 +62,8 @@ struct Params {
   int raw;                   // module-split API: 1 = rows are the raw patches (no L2 normalisation)
   int rows_mode;             // module-split rows API on the tensor-core kernel: rows are used as given (no
                              // normalisation, no normalise backward), d loss / d q leaves row-major in dq_rows
+  int nhwc;                  // channels-last maps (nhwc.cuh): src/tgt/dtgt are (B, HW, C) storage and dxT holds ROW-major
+                             // rows [image][sorted slot][C]; tensor-core path only
   int b0, bn;                // images [b0, b0+bn) of the batch are covered by this launch (chunked forward)
   unsigned total_ctas;       // loss CTAs over all chunks: the one that arrives last finalises
   float* loss_out;           // [1 + n_layers]

@@ -97,7 +97,9 @@ __device__ void finalize_losses(const Params& p, void* scratch) {
           int c = (int)(i / L.P), pp = (int)(i % L.P);
           float inv = L.qinv[(size_t)b * L.P + pp];
           float v = (!layer_bad[l] && !(inv == inv)) ? __int_as_float(0x7fc00000) : 0.f;
-          L.dxT[((size_t)b * L.C + c) * L.dxpitch + (L.sorted ? pp : L.rank[pp])] = v;
+          const int slot = L.sorted ? pp : L.rank[pp];
+          if (p.nhwc) L.dxT[((size_t)b * L.dxpitch + slot) * L.C + c] = v;        // row-major rows (channels-last maps)
+          else L.dxT[((size_t)b * L.C + c) * L.dxpitch + slot] = v;
         }
       }
     }

@@ -262,14 +262,22 @@ __device__ __forceinline__ void st_dx(float* p, float v, bool keep, uint64_t pol
   if (keep) asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
   else *p = v;
 }
+__device__ __forceinline__ void st_dx4(float* p, float a, float b, float c, float d, bool keep, uint64_t pol) {
+  if (keep)
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol)
+                 : "memory");
+  else *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
 
 // dQ epilogue for one 32-channel chunk; NPC = pitch of dxT rows (compile-time: immediates; 0 = run time).
 // Head mode (dyh != NULL): the gradient w.r.t. the head output leaves as a bf16 hi(+lo) row blob
 // (the A operand of the head's backward GEMMs) instead of fp32 rows; padding rows are written as 0.
+// rm (channels-last maps, nhwc.cuh): the rows leave ROW-major -- dp = this row's 32 channels, np_rt = C; every
+// thread writes one whole 128-byte line.
 template <int NPC>
 __device__ __forceinline__ void tc_dq_chunk(const uint32_t (&r)[32], const TcQChunk& qc, float* __restrict__ dp,
                                             int nvalid, float c1, float c2, bool rowok, __nv_bfloat16* dyh,
-                                            __nv_bfloat16* dyl, int np_rt) {
+                                            __nv_bfloat16* dyl, int np_rt, bool rm = false) {
   const size_t NP = NPC ? (size_t)NPC : (size_t)np_rt;
   float qv[32], out[32];
   tc_q_unpack(qc, qv);
@@ -294,6 +302,17 @@ __device__ __forceinline__ void tc_dq_chunk(const uint32_t (&r)[32], const TcQCh
     const bool keep = g_dx_evict_last != 0;
     uint64_t pol = 0;
     if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    if (rm) {
+      if (nvalid >= 32 && (np_rt & 3) == 0) {
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) st_dx4(dp + k4 * 4, out[k4 * 4], out[k4 * 4 + 1], out[k4 * 4 + 2], out[k4 * 4 + 3], keep, pol);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (k < nvalid) st_dx(dp + k, out[k], keep, pol);
+      }
+      return;
+    }
     if (nvalid >= 32) {
 #pragma unroll
       for (int k = 0; k < 32; ++k) st_dx(dp + k * NP, out[k], keep, pol);
@@ -310,9 +329,10 @@ __device__ __forceinline__ void tc_dq_epilogue(uint32_t tacc, int nstage, int C,
                                                const __nv_bfloat16* __restrict__ ql, float* __restrict__ dxrow,
                                                float c1, float c2, bool rowok, __nv_bfloat16* dyh,
                                                __nv_bfloat16* dyl, uint64_t* dqfull, volatile int* dead,
-                                               TcQChunk& qa, TcQChunk& qb, int np_rt = 0, uint32_t parity = 0u) {
+                                               TcQChunk& qa, TcQChunk& qb, int np_rt = 0, uint32_t parity = 0u,
+                                               bool rm = false) {
   using namespace umma;
-  const size_t NP = NPC ? (size_t)NPC : (size_t)np_rt;
+  const size_t NP = rm ? (size_t)1 : (NPC ? (size_t)NPC : (size_t)np_rt);   // rm: dxrow is this row, channels contiguous
   mbar_wait(dqfull, parity, dead);
   tc_fence_after();
   for (int s = 0; s < nstage; s += 2) {
@@ -320,14 +340,14 @@ __device__ __forceinline__ void tc_dq_epilogue(uint32_t tacc, int nstage, int C,
     tmem_ld32(tacc + s * 32, r);
     tmem_ld_wait();
     tc_dq_chunk<NPC>(r, qa, dxrow + (size_t)s * 32 * NP, C - s * 32, c1, c2, rowok,
-                     dyh ? dyh + (size_t)s * 4096 : nullptr, dyl ? dyl + (size_t)s * 4096 : nullptr, np_rt);
+                     dyh ? dyh + (size_t)s * 4096 : nullptr, dyl ? dyl + (size_t)s * 4096 : nullptr, np_rt, rm);
     tc_q_load(qa, qh, ql, s + 2, nstage);                     // two chunks ahead (static double buffer)
     if (s + 1 < nstage) {
       tmem_ld32(tacc + (s + 1) * 32, r);
       tmem_ld_wait();
       tc_dq_chunk<NPC>(r, qb, dxrow + (size_t)(s + 1) * 32 * NP, C - (s + 1) * 32, c1, c2, rowok,
                        dyh ? dyh + (size_t)(s + 1) * 4096 : nullptr, dyl ? dyl + (size_t)(s + 1) * 4096 : nullptr,
-                       np_rt);
+                       np_rt, rm);
       tc_q_load(qb, qh, ql, s + 3, nstage);
     }
   }
@@ -654,11 +674,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       const float c1 = inv_tau * sc;
       const float c2 = noproj ? 0.f : sc * sc * s_i;
       float* __restrict__ dxrow = L.dxT + (size_t)b * C * Ppad + (rowok ? gi : 0);   // dxpitch == Ppad on this path
+      if (p.nhwc) dxrow = L.dxT + ((size_t)b * Ppad + (rowok ? gi : 0)) * C;         // channels-last maps: row-major rows
       PNCE_TR(5);
       // head mode: d loss / d (head output) as a row blob [tile = b*halves+mh][c/8][16][8][8]
       __nv_bfloat16* dyh = L.dyhi ? L.dyhi + qoff : nullptr;
       __nv_bfloat16* dyl = (L.dyhi && L.dylo) ? L.dylo + qoff : nullptr;
-      switch (Ppad >> 7) {
+      if (p.nhwc) tc_dq_epilogue<0>(trow + 256u, nstage, C, qh, ql, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb, C, 0u, true);
+      else switch (Ppad >> 7) {
         case 1: tc_dq_epilogue<128>(trow + 256u, nstage, C, qh, ql, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb); break;
         case 2: tc_dq_epilogue<256>(trow + 256u, nstage, C, qh, ql, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb); break;
         default: tc_dq_epilogue<0>(trow + 256u, nstage, C, qh, ql, dxrow, c1, c2, rowok, dyh, dyl, &sh->dqfull, dead, qa, qb, Ppad); break;

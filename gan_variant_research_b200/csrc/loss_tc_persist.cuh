@@ -588,6 +588,8 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
       const float c1 = single ? inv_tau * sc * (coef / se) : inv_tau * sc;
       const float c2 = (noproj || p.rows_mode) ? 0.f : sc * sc * s_i;   // rows API: rows are used as given, no projection
       float* __restrict__ dxrow = L.dxT + (size_t)b * C * Ppad + (rowok ? gi : 0);   // dxpitch == Ppad on this path
+      const bool rm = p.nhwc != 0;                             // channels-last maps: row-major rows [slot][C]
+      if (rm) dxrow = L.dxT + ((size_t)b * Ppad + (rowok ? gi : 0)) * C;
       __nv_bfloat16* dyh = L.dyhi ? L.dyhi + qoff : nullptr;   // head mode: d loss / d (head output) as a row blob
       __nv_bfloat16* dyl = (L.dyhi && L.dylo) ? L.dylo + qoff : nullptr;
       TcQChunk qn;                                             // this warp's first channel chunk of raw q: in flight
@@ -628,8 +630,8 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
           const TcQChunk qc = qn;
           tc_q_load(qn, qh, ql, s + 2, nstage);
           tmem_ld_wait();
-          tc_dq_chunk<0>(r, qc, dxrow + (size_t)s * 32 * Ppad, C - s * 32, c1, c2, rowok,
-                         dyh ? dyh + (size_t)s * 4096 : nullptr, dyl ? dyl + (size_t)s * 4096 : nullptr, Ppad);
+          tc_dq_chunk<0>(r, qc, dxrow + (rm ? (size_t)s * 32 : (size_t)s * 32 * Ppad), C - s * 32, c1, c2, rowok,
+                         dyh ? dyh + (size_t)s * 4096 : nullptr, dyl ? dyl + (size_t)s * 4096 : nullptr, rm ? C : Ppad, rm);
         }
       }
       tc_fence_before();

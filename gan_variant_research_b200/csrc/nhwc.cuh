@@ -1,0 +1,220 @@
+// Channels-last (NHWC) maps on the tensor-core path: gather and dense backward.
+//
+// The reference's loss takes contiguous NCHW maps (`feat.view(B, C, -1)`, patchnce_cut.py:56), where every channel of
+// a sampled patch sits in a DRAM line of its own: the gather of DESIGN.md 4 pulls 29.6 MB of 128-byte lines per image
+// to use 1.57 MB of them.  A generator run in torch.channels_last hands out (B, H, W, C) storage, where a patch IS a
+// contiguous row of C values -- the same algorithm then reads exactly the bytes it uses.  This is an EXTENSION of the
+// reference's interface (its .view() rejects such maps), selected by the `layout` argument of pnce_fwd_ex / pnce_bwd_ex;
+// ids, loss and gradient values follow the same law as the NCHW path (the oracle on the permuted data).
+//   k_gather_tc_nhwc : warp <-> (side, image, 8 sorted patch slots, 32-channel chunk); lane <-> (slot, 8 channels):
+//                      4 lanes read one patch's 128 contiguous bytes (fp32), 8 lanes write one 128-byte core matrix.
+//   k_dense_nhwc     : one 128-thread CTA per <= 8 KB tile of d tgt (a few whole positions), address order; a tile
+//                      without sampled positions (most of them) is a pure zero fill from registers.
+// The gradient rows arrive ROW-major ([image][sorted slot][C], Params::nhwc) from the loss kernels.
+#pragma once
+#include "common.cuh"
+#include "gather_tc.cuh"
+
+namespace pnce {
+
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = __ldcg(reinterpret_cast<const float4*>(p)), b = __ldcg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <> struct Vec8<__half> {
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+    const uint4 a = __ldcg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[k]);
+      v[2 * k] = __low2float(h); v[2 * k + 1] = __high2float(h);
+    }
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 a = __ldcg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[2 * k] = __uint_as_float(w[k] << 16); v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
+  }
+};
+
+// One warp item of the NHWC gather; writes exactly what gather_tc_chunk writes for the same (side, image, slots, chunk).
+template <typename T>
+__device__ __forceinline__ void gather_nhwc_item(const LayerDev& L, int b0, int B, long long witem, int lane) {
+  const int nchunk = L.nchunk, np8 = L.Ppad >> 3;
+  const int s = (int)(witem % nchunk);
+  const int p8 = (int)((witem / nchunk) % np8);
+  const long long rest = witem / nchunk / np8;
+  const int b = b0 + (int)(rest % B);
+  const int side = (int)(rest / B);                          // 0 = src (k), 1 = tgt (q)
+  const int C = L.C, HW = L.HW, P = L.P, Ppad = L.Ppad, Cp8 = L.Cp >> 3;
+  const int p = p8 * 8 + (lane & 7);                         // sorted slot
+  const int g = lane >> 3;                                   // 8-channel group of the chunk
+  const int c8 = s * 4 + g, c0 = c8 * 8;
+  const bool valid = p < P;
+  const int id = valid ? __ldg(L.sid + p) : 0;
+  const T* base = reinterpret_cast<const T*>(side ? L.tgt : L.src);
+  const T* row = base + ((size_t)b * HW + id) * C + c0;
+  const bool vec = (((size_t)C * sizeof(T)) & 15u) == 0 && (reinterpret_cast<uintptr_t>(base) & 15u) == 0;
+  float v[8];
+  if (valid && vec && c0 + 8 <= C) {
+    Vec8<T>::load(row, v);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (valid && c0 + k < C) ? to_f32<T>(__ldcg(row + k)) : 0.f;
+  }
+  float ss = 0.f;
+  int bad = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    ss = fmaf(v[k], v[k], ss);
+    bad |= !isfinite(v[k]);
+  }
+  ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+  bad |= __shfl_xor_sync(0xffffffffu, bad, 8);
+  bad |= __shfl_xor_sync(0xffffffffu, bad, 16);
+  float* ssbase = side ? L.qss : L.kss;                      // NULL in head mode (the head's output is normalised)
+  if (ssbase != nullptr && g == 0) ssbase[((size_t)b * nchunk + s) * Ppad + p] = bad ? __int_as_float(0x7fc00000) : ss;
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float a = v[2 * k], c2 = v[2 * k + 1];
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a), ch = __float2bfloat16_rn(c2);
+    const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+    const __nv_bfloat16 cl = __float2bfloat16_rn(c2 - __bfloat162float(ch));
+    hw[k] = pack_bf16x2(ah, ch);
+    lw[k] = pack_bf16x2(al, cl);
+  }
+  __nv_bfloat16* hi_base = side ? L.qhi : L.khi;
+  __nv_bfloat16* lo_base = side ? L.qlo : L.klo;
+  size_t cm;                                                  // core-matrix index, as in gather_tc_chunk
+  if (side || L.head_src_rows) cm = (((size_t)b * (Ppad >> 7) + (p >> 7)) * Cp8 + c8) * 16 + ((p & 127) >> 3);
+  else {
+    const int pb = p >> 8;
+    const int nb8 = min(256, Ppad - pb * 256) >> 3;
+    cm = (((size_t)b * Ppad + (size_t)pb * 256) * Cp8) / 8 + (size_t)c8 * nb8 + ((p & 255) >> 3);
+  }
+  const size_t off = cm * 64 + (size_t)(p & 7) * 8;
+  *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  if (lo_base != nullptr) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  if (!side && !L.head_src_rows) {
+    const size_t off2 = (((size_t)b * (Ppad >> 3) + (p >> 3)) * Cp8 + c8) * 64 + (size_t)(p & 7) * 8;
+    *reinterpret_cast<uint4*>(L.k2hi + off2) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    if (L.k2lo != nullptr) *reinterpret_cast<uint4*>(L.k2lo + off2) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
+// grid = sum_l ceil(2 * B * (Ppad_l / 8) * nchunk_l / 8) CTAs of 8 warps; m.start counts CTAs per launch slot
+__global__ void __launch_bounds__(kThreads) k_gather_tc_nhwc(const __grid_constant__ Params p,
+                                                             const __grid_constant__ BlockMap m) {
+  const long long blk = blockIdx.x;
+  if (blk == 0 && threadIdx.x == 0 && p.b0 == 0 && p.counter != nullptr) {
+    p.counter[0] = 0u; p.counter[1] = 0u;                      // launch-sequence state, as in k_gather_tc
+    if (p.nonfinite != nullptr) p.nonfinite[1] = 0;
+  }
+  const int slot = find_layer(m, blk, p.n_layers);
+  const int l = m.layer[slot];
+  const LayerDev& L = p.L[l];
+  const long long witem = (blk - m.start[slot]) * 8 + (threadIdx.x >> 5);
+  const long long nitems = 2ll * p.bn * (L.Ppad >> 3) * L.nchunk;
+  if (witem >= nitems) return;
+  const int lane = threadIdx.x & 31;
+  if (p.dtype == PNCE_F32) gather_nhwc_item<float>(L, p.b0, p.bn, witem, lane);
+  else if (p.dtype == PNCE_F16) gather_nhwc_item<__half>(L, p.b0, p.bn, witem, lane);
+  else gather_nhwc_item<__nv_bfloat16>(L, p.b0, p.bn, witem, lane);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Dense d tgt_feat for channels-last maps: (B, HW, C) storage, written exactly once, tiles in address order.
+// A tile = TPOS whole positions (TPOS * C * sizeof(T) <= 8 KB).  The sorted slots that fall into a tile are a
+// contiguous range [ja, jb) of sid[]; it is found from k_prep's 2048-position bucket table (one or two buckets,
+// their candidates compared in parallel).  No sampled position in the tile: 128-bit zero stores straight from
+// registers.  Otherwise the tile is staged in shared memory, thread <-> channel adds up the row-major gradient
+// rows of every run of equal ids in sorted order (the order of the NCHW kernel), and the tile is copied out.
+// -------------------------------------------------------------------------------------------------
+struct DenseNhwcMap {
+  long long start[PNCE_MAX_LAYERS + 1];        // tile prefix per layer
+  int tiles[PNCE_MAX_LAYERS];                  // tiles per image
+  int tpos[PNCE_MAX_LAYERS];                   // positions per tile
+};
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(128) k_dense_nhwc(const __grid_constant__ Params p,
+                                                    const __grid_constant__ DenseNhwcMap m) {
+  __shared__ __align__(16) T tile[kFlatBytes / sizeof(T)];
+  __shared__ int s_ja, s_jb;
+  const int tid = threadIdx.x;
+  const long long item = blockIdx.x;
+  int l = 0;
+  for (int i = 1; i < p.n_layers; ++i)
+    if (item >= m.start[i]) l = i;
+  const LayerDev& L = p.L[l];
+  const long long local = item - m.start[l];
+  const int tiles = m.tiles[l], TPOS = m.tpos[l];
+  const int b = (int)(local / tiles);
+  const int t = (int)(local - (long long)b * tiles);
+  const int P = L.P, HW = L.HW, C = L.C;
+  const int pos0 = t * TPOS, npos = min(TPOS, HW - pos0), pos1 = pos0 + npos;
+  const int ntab = (HW + kTilePos - 1) / kTilePos;
+  const int jlo = __ldg(L.cslot + pos0 / kTilePos);
+  const int jhi = __ldg(L.cslot + min((pos1 - 1) / kTilePos + 1, ntab));
+  if (tid == 0) { s_ja = P; s_jb = 0; }
+  __syncthreads();
+  for (int j = jlo + tid; j < jhi; j += 128) {
+    const int q = __ldg(L.sid + j);
+    if (q >= pos0 && q < pos1) { atomicMin(&s_ja, j); atomicMax(&s_jb, j + 1); }
+  }
+  __syncthreads();
+  const int ja = s_ja, jb = s_jb;
+  const int nelem = npos * C;
+  T* dst = reinterpret_cast<T*>(L.dtgt) + ((size_t)b * HW + pos0) * C;
+  if (ja >= jb) {                                              // nothing sampled here: pure fill
+    if (VEC) {
+      const int n16 = (nelem * (int)sizeof(T)) >> 4;
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+      for (int i = tid; i < n16; i += 128) __stcs(d4 + i, make_uint4(0u, 0u, 0u, 0u));
+    } else {
+      for (int i = tid; i < nelem; i += 128) dst[i] = from_f32<T>(0.f);
+    }
+    return;
+  }
+  uint4* t4 = reinterpret_cast<uint4*>(tile);
+  const int n16s = (nelem * (int)sizeof(T) + 15) >> 4;
+  for (int i = tid; i < n16s; i += 128) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  const float g = p.grad_out ? __ldg(p.grad_out) : 1.0f;
+  const float* __restrict__ dx = L.dxT + ((size_t)b * L.dxpitch) * C;      // row-major rows [slot][C]
+  for (int c = tid; c < C; c += 128) {
+    int qprev = __ldg(L.sid + ja);
+    float acc = 0.f;
+    for (int j = ja; j < jb; ++j) {
+      const int q = __ldg(L.sid + j);
+      if (q != qprev) {
+        tile[(size_t)(qprev - pos0) * C + c] = from_f32<T>(acc * g);
+        acc = 0.f;
+        qprev = q;
+      }
+      acc += __ldcs(dx + (size_t)j * C + c);                   // last use of the row: streaming
+    }
+    tile[(size_t)(qprev - pos0) * C + c] = from_f32<T>(acc * g);
+  }
+  __syncthreads();
+  if (VEC) {
+    const int n16 = (nelem * (int)sizeof(T)) >> 4;
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int i = tid; i < n16; i += 128) __stcs(d4 + i, t4[i]);
+  } else {
+    for (int i = tid; i < nelem; i += 128) dst[i] = tile[i];
+  }
+}
+
+}  // namespace pnce

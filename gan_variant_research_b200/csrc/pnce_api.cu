@@ -13,6 +13,7 @@
 #include "loss_simt.cuh"
 #include "loss_tc.cuh"
 #include "loss_tc_persist.cuh"
+#include "nhwc.cuh"
 #include "rows_pack.cuh"
 #include "multi_tensor.cuh"
 #include "sample_bwd.cuh"
@@ -256,6 +257,19 @@ static int launch_gather_tc(const Params& p, cudaStream_t st) {
     for (int i = 1; i < p.n_layers; ++i)
       for (int j = i; j > 0 && p.L[order[j]].C <= p.L[order[j - 1]].C; --j) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
   long long acc = 0;
+  if (p.nhwc) {
+    // channels-last maps: one warp per (side, image, 8 slots, 32-channel chunk), 8 warps per CTA
+    for (int s = 0; s < p.n_layers; ++s) {
+      m.start[s] = acc;
+      m.layer[s] = order[s];
+      acc += (2ll * p.bn * (p.L[order[s]].Ppad >> 3) * p.L[order[s]].nchunk + 7) / 8;
+    }
+    m.start[p.n_layers] = acc;
+    if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+    k_gather_tc_nhwc<<<(unsigned)acc, kThreads, 0, st>>>(p, m);
+    PNCE_CUDA(cudaGetLastError());
+    return PNCE_OK;
+  }
   for (int s = 0; s < p.n_layers; ++s) {
     m.start[s] = acc;
     m.layer[s] = order[s];
@@ -428,7 +442,39 @@ static int forward_tc(Params& p, cudaStream_t st, bool planned = false) {
   return PNCE_OK;
 }
 
+static int launch_dense_nhwc(const Params& p, cudaStream_t st) {
+  const size_t es = dtype_size(p.dtype);
+  DenseNhwcMap f;
+  memset(&f, 0, sizeof(f));
+  bool vec = true;
+  long long tot = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const size_t rowbytes = (size_t)p.L[l].C * es;
+    if (rowbytes > kFlatBytes) return PNCE_ERR_UNSUPPORTED;
+    f.start[l] = tot;
+    f.tpos[l] = (int)(kFlatBytes / rowbytes);
+    f.tiles[l] = (p.L[l].HW + f.tpos[l] - 1) / f.tpos[l];
+    if ((rowbytes % 16 != 0) || (reinterpret_cast<uintptr_t>(p.L[l].dtgt) & 15u)) vec = false;
+    tot += (long long)p.B * f.tiles[l];
+  }
+  f.start[p.n_layers] = tot;
+  if (tot > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+  const unsigned grid = (unsigned)tot;
+  if (vec) {
+    if (p.dtype == PNCE_F32) k_dense_nhwc<float, true><<<grid, 128, 0, st>>>(p, f);
+    else if (p.dtype == PNCE_F16) k_dense_nhwc<__half, true><<<grid, 128, 0, st>>>(p, f);
+    else k_dense_nhwc<__nv_bfloat16, true><<<grid, 128, 0, st>>>(p, f);
+  } else {
+    if (p.dtype == PNCE_F32) k_dense_nhwc<float, false><<<grid, 128, 0, st>>>(p, f);
+    else if (p.dtype == PNCE_F16) k_dense_nhwc<__half, false><<<grid, 128, 0, st>>>(p, f);
+    else k_dense_nhwc<__nv_bfloat16, false><<<grid, 128, 0, st>>>(p, f);
+  }
+  PNCE_CUDA(cudaGetLastError());
+  return PNCE_OK;
+}
+
 static int launch_dense(const Params& p, cudaStream_t st) {
+  if (p.nhwc) return launch_dense_nhwc(p, st);
   const size_t es = dtype_size(p.dtype);
   // default: one small CTA per 8 KB tile, in address order
   DenseFlatMap f;
@@ -590,8 +636,9 @@ int pnce_workspace_bytes(const pnce_layer_t* layers, int n_layers, int batch, si
 
 static int fwd_impl(const pnce_layer_t* layers, int n_layers, int batch, int dtype, float temperature,
                     int math_mode, void* ws, size_t ws_bytes, void* plan, size_t plan_bytes, float* loss_out,
-                    int* nonfinite, void* stream, const unsigned long long* rng = nullptr) {
+                    int* nonfinite, void* stream, const unsigned long long* rng = nullptr, int layout = PNCE_LAYOUT_NCHW) {
   int rc = check_layers(layers, n_layers, batch);
+  if (layout != PNCE_LAYOUT_NCHW && layout != PNCE_LAYOUT_NHWC) return PNCE_ERR_ARG;
   if (rc != PNCE_OK) return rc;
   if (dtype < PNCE_F32 || dtype > PNCE_BF16 || loss_out == nullptr || !(temperature > 0.f)) return PNCE_ERR_ARG;
   if (math_mode < PNCE_MATH_SIMT_F32 || math_mode > PNCE_MATH_TC_BF16) return PNCE_ERR_ARG;
@@ -616,6 +663,10 @@ static int fwd_impl(const pnce_layer_t* layers, int n_layers, int batch, int dty
   p.nonfinite = nonfinite;
   p.trace = g_dbg.trace;
   p.b0 = 0; p.bn = batch;
+  if (layout == PNCE_LAYOUT_NHWC) {
+    if (!tc) return PNCE_ERR_UNSUPPORTED;                      // channels-last maps: tensor-core path only
+    p.nhwc = 1;
+  }
   if (rng != nullptr) {
     if (!tc || plan != nullptr) return PNCE_ERR_UNSUPPORTED;   // the draw rides on k_prep (tensor-core path, unplanned)
     p.rng_draw = 1; p.rng_seed = rng[0]; p.rng_offset = rng[1];
@@ -721,8 +772,10 @@ int pnce_draw_ids(const pnce_layer_t* layers, int n_layers, unsigned long long p
 }
 
 static int bwd_impl(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int math_mode, void* ws,
-                    size_t ws_bytes, void* plan, size_t plan_bytes, const float* grad_out, void* stream) {
+                    size_t ws_bytes, void* plan, size_t plan_bytes, const float* grad_out, void* stream,
+                    int layout = PNCE_LAYOUT_NCHW) {
   int rc = check_layers(layers, n_layers, batch);
+  if (layout != PNCE_LAYOUT_NCHW && layout != PNCE_LAYOUT_NHWC) return PNCE_ERR_ARG;
   if (rc != PNCE_OK) return rc;
   if (dtype < PNCE_F32 || dtype > PNCE_BF16) return PNCE_ERR_ARG;
   rc = check_alignment(layers, n_layers, dtype, true);
@@ -736,7 +789,23 @@ static int bwd_impl(const pnce_layer_t* layers, int n_layers, int batch, int dty
     return PNCE_ERR_WORKSPACE;
   p.dtype = dtype;
   p.grad_out = grad_out;
+  if (layout == PNCE_LAYOUT_NHWC) {
+    if (!tc) return PNCE_ERR_UNSUPPORTED;
+    p.nhwc = 1;
+  }
   return launch_dense(p, static_cast<cudaStream_t>(stream));
+}
+
+int pnce_fwd_ex(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int layout, float temperature,
+                int math_mode, void* ws, size_t ws_bytes, void* plan, size_t plan_bytes,
+                const unsigned long long* philox, float* loss_out, int* nonfinite, void* stream) {
+  return fwd_impl(layers, n_layers, batch, dtype, temperature, math_mode, ws, ws_bytes, plan, plan_bytes, loss_out,
+                  nonfinite, stream, philox, layout);
+}
+
+int pnce_bwd_ex(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int layout, int math_mode, void* ws,
+                size_t ws_bytes, void* plan, size_t plan_bytes, const float* grad_out, void* stream) {
+  return bwd_impl(layers, n_layers, batch, dtype, math_mode, ws, ws_bytes, plan, plan_bytes, grad_out, stream, layout);
 }
 
 int pnce_bwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int math_mode, void* ws,

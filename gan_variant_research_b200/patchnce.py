@@ -313,11 +313,12 @@ class _ShapePlan:
     guarded by a lock so that two Python threads sharing a shape do not interleave their pointer stores."""
 
     __slots__ = ("n", "batch", "dtype", "dtype_code", "math", "math_code", "dev", "p_list", "p_total", "tc",
-                 "ws_bytes", "plan_bytes", "fwd_layers", "bwd_layers", "fwd_lock", "bwd_lock", "big", "shapes")
+                 "ws_bytes", "plan_bytes", "fwd_layers", "bwd_layers", "fwd_lock", "bwd_lock", "big", "shapes", "nhwc")
 
-    def __init__(self, dev, dtype, shapes, p_list, math):
+    def __init__(self, dev, dtype, shapes, p_list, math, nhwc=False):
         lib = _lib.load()
         self.n, self.batch, self.dtype, self.dev, self.math = len(shapes), shapes[0][0], dtype, dev, math
+        self.nhwc = nhwc                         # channels-last storage (pnce_fwd_ex / pnce_bwd_ex, LAYOUT_NHWC)
         self.dtype_code, self.math_code = _DTYPES[dtype], _MATH[math]
         self.shapes = shapes
         self.p_list, self.p_total = list(p_list), sum(p_list)
@@ -331,7 +332,9 @@ class _ShapePlan:
                    "pnce_workspace_bytes")
         self.ws_bytes = nbytes.value
         # the tensor-core kernels' envelope (csrc/pnce_api.cu tc_shapes_ok); outside it the fp32 CUDA-core kernels run
-        self.tc = math != "simt_f32" and all(c <= 256 and p <= 1024 for (_, c, _, _), p in zip(shapes, p_list))
+        self.tc = tc_envelope(shapes, p_list, math)
+        if nhwc and not self.tc:
+            raise RuntimeError("channels-last maps need the tensor-core path (C <= 256, P <= 1024, math != simt_f32)")
         self.plan_bytes = 0
         if self.tc:
             _lib.check(lib.pnce_plan_bytes(self.fwd_layers, self.n, ctypes.byref(nbytes)), "pnce_plan_bytes")
@@ -346,14 +349,24 @@ class _ShapePlan:
 _SHAPE_PLANS = {}
 
 
-def _shape_plan(tgt, p_list, math) -> _ShapePlan:
+def tc_envelope(shapes, p_list, math) -> bool:
+    """The tensor-core kernels' envelope (csrc/pnce_api.cu tc_shapes_ok); outside it the fp32 CUDA-core kernels run."""
+    return math != "simt_f32" and all(s[1] <= 256 and p <= 1024 for s, p in zip(shapes, p_list))
+
+
+def _is_nhwc(t) -> bool:
+    """(B, C, H, W) tensor whose storage is dense (B, H, W, C): torch.channels_last (and not also plain contiguous)."""
+    return t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _shape_plan(tgt, p_list, math, nhwc=False) -> _ShapePlan:
     t0 = tgt[0]
-    key = (t0.device.index, t0.dtype, math, tuple(p_list), *[t.shape for t in tgt])
+    key = (t0.device.index, t0.dtype, math, nhwc, tuple(p_list), *[t.shape for t in tgt])
     sp = _SHAPE_PLANS.get(key)
     if sp is None:
         if len(_SHAPE_PLANS) > 256:                  # a caller cycling through many shapes: do not grow without bound
             _SHAPE_PLANS.clear()
-        sp = _SHAPE_PLANS[key] = _ShapePlan(t0.device, t0.dtype, [tuple(t.shape) for t in tgt], p_list, math)
+        sp = _SHAPE_PLANS[key] = _ShapePlan(t0.device, t0.dtype, [tuple(t.shape) for t in tgt], p_list, math, nhwc)
     return sp
 
 
@@ -423,7 +436,13 @@ def _run_fwd(call: _Call, tgt_feats):
             for l in range(n):
                 a = layers[l]
                 a.src, a.tgt, a.ids = src[l].data_ptr(), tgt_feats[l].data_ptr(), ids[l].data_ptr()
-            if call.rng is not None:
+            if sp.nhwc:
+                philox = (ctypes.c_ulonglong * 2)(call.rng[0], call.rng[1]) if call.rng is not None else None
+                pl = call.idplan
+                rc = lib.pnce_fwd_ex(layers, n, sp.batch, sp.dtype_code, _lib.LAYOUT_NHWC, call.temperature,
+                                     sp.math_code, ws.data_ptr(), sp.ws_bytes, pl.data_ptr() if pl is not None else None,
+                                     pl.numel() if pl is not None else 0, philox, out.data_ptr(), flag_ptr or None, st)
+            elif call.rng is not None:
                 rc = lib.pnce_fwd_draw(layers, n, sp.batch, sp.dtype_code, call.temperature, sp.math_code,
                                        ws.data_ptr(), sp.ws_bytes, call.rng[0], call.rng[1], out.data_ptr(),
                                        flag_ptr or None, st)
@@ -456,7 +475,12 @@ def _run_bwd(call: _Call, ws, grad_out, tgt_like):
             for l in range(sp.n):
                 layers[l].dtgt, layers[l].ids = grads[l].data_ptr(), ids[l].data_ptr()
             gp = g.data_ptr() if g is not None else None
-            if call.idplan is None:
+            if sp.nhwc:
+                pl = call.idplan
+                rc = lib.pnce_bwd_ex(layers, sp.n, sp.batch, sp.dtype_code, _lib.LAYOUT_NHWC, sp.math_code,
+                                     ws.data_ptr(), sp.ws_bytes, pl.data_ptr() if pl is not None else None,
+                                     pl.numel() if pl is not None else 0, gp, st)
+            elif call.idplan is None:
                 rc = lib.pnce_bwd(layers, sp.n, sp.batch, sp.dtype_code, sp.math_code, ws.data_ptr(),
                                   sp.ws_bytes, gp, st)
             else:
@@ -486,11 +510,16 @@ class _FusedPatchNCE(torch.autograd.Function):
         return (None, *_run_bwd(ctx.call, ws, grad_out, ctx.tgt_keep))
 
 
-def _prepare_maps(src_feats, tgt_feats):
+def _prepare_maps(src_feats, tgt_feats, math=None, patches=None):
     """The reference's argument handling (patchnce_cut.py:25-40) plus what the C ABI needs: CUDA tensors,
     (B, C, H, W), src/tgt of equal shape, contiguous NCHW.  Returns (src, tgt, len(src_feats), uniform); ``uniform``:
-    every layer shares batch size, dtype and device, so ONE C-ABI call covers them all (the reference treats each
-    layer on its own, :36-38, so mixed lists are valid input there and take one call per layer here)."""
+    every layer shares batch size, dtype, device and memory layout, so ONE C-ABI call covers them all (the reference
+    treats each layer on its own, :36-38, so mixed lists are valid input there and take one call per layer here).
+
+    Channels-last target maps (``torch.channels_last``: an extension, the reference's ``.view`` rejects them) are
+    kept as they are when the layer fits the tensor-core kernels (``math``; ``patches`` = num_patches or the list of
+    id counts) -- the gather then reads each patch as one contiguous row, and the gradient comes back channels-last;
+    otherwise they are re-laid out to NCHW like any other non-contiguous input."""
     n_src = len(src_feats)
     n = min(n_src, len(tgt_feats))                   # the reference zips and silently truncates (:36) ...
     if n_src == 0:
@@ -503,6 +532,7 @@ def _prepare_maps(src_feats, tgt_feats):
     t0 = tgt_feats[0]
     b0, dt0, dev0 = (t0.shape[0] if t0.dim() else -1), t0.dtype, t0.device
     uniform = True
+    nh0 = None
     for l in range(n):
         s, t = src_feats[l], tgt_feats[l]
         if s.shape != t.shape or s.dtype != t.dtype or s.device != t.device or t.dim() != 4 or not t.is_cuda:
@@ -523,13 +553,26 @@ def _prepare_maps(src_feats, tgt_feats):
             raise RuntimeError(f"unsupported feature dtype {dt}")
         if s.requires_grad:
             s = s.detach()
-        src.append(s if s.is_contiguous() else s.contiguous())
-        tgt.append(t if t.is_contiguous() else t.contiguous())
+        nh = False
+        if not t.is_contiguous() and math is not None and _is_nhwc(t):
+            hw = t.shape[2] * t.shape[3]
+            pl = patch_count(patches, hw) if isinstance(patches, int) else int(patches[l].numel())
+            nh = tc_envelope([t.shape], [pl], math)
+        if nh0 is None:
+            nh0 = nh
+        elif nh != nh0:
+            uniform = False
+        if nh:
+            src.append(s if _is_nhwc(s) else s.contiguous(memory_format=torch.channels_last))
+            tgt.append(t)
+        else:
+            src.append(s if s.is_contiguous() else s.contiguous())
+            tgt.append(t if t.is_contiguous() else t.contiguous())
     return src, tgt, n_src, uniform
 
 
 def _fused_call(src, tgt, ids, temperature, math, rng=None, idplan=None):
-    sp = _shape_plan(tgt, [i.numel() for i in ids], math)
+    sp = _shape_plan(tgt, [i.numel() for i in ids], math, _is_nhwc(tgt[0]))
     return _FusedPatchNCE.apply(_Call(sp, src, ids, temperature, rng, idplan), *tgt)
 
 
@@ -537,10 +580,11 @@ def fused_patchnce(src_feats, tgt_feats, ids_list, temperature=0.07, math: Optio
                    denom_layers: Optional[int] = None):
     """All-layer PatchNCE on dense NCHW maps with given ids.  Returns the scalar loss tensor
     (fp32, on device, differentiable w.r.t. every ``tgt_feats[l]`` that requires grad)."""
-    src, tgt, n_src, uniform = _prepare_maps(src_feats, tgt_feats)
+    math = math or DEFAULT_MATH
+    if len(ids_list) < min(len(src_feats), len(tgt_feats)):
+        raise RuntimeError(f"{len(ids_list)} id tensors for {min(len(src_feats), len(tgt_feats))} layers")
+    src, tgt, n_src, uniform = _prepare_maps(src_feats, tgt_feats, math, list(ids_list))
     n = len(tgt)
-    if len(ids_list) < n:
-        raise RuntimeError(f"{len(ids_list)} id tensors for {n} layers")
     ids = []
     for i in list(ids_list)[:n]:
         _require_cuda(i, "patch_ids")
@@ -549,7 +593,6 @@ def fused_patchnce(src_feats, tgt_feats, ids_list, temperature=0.07, math: Optio
         if i.numel() > _lib.MAX_PATCHES:
             raise RuntimeError(f"num_patches > {_lib.MAX_PATCHES} is not supported")
         ids.append(i)
-    math = math or DEFAULT_MATH
     denom = n_src if denom_layers is None else denom_layers
     if uniform:
         loss = _fused_call(src, tgt, ids, temperature, math)
@@ -618,11 +661,11 @@ class PatchNCELoss(nn.Module):
 
     def _begin(self, a, b):
         """Argument handling + the id draw of one ``forward``: -> (call, tgt, scale)."""
-        src, tgt, n_src, uniform = _prepare_maps(a, b)
+        math = self.math or DEFAULT_MATH
+        src, tgt, n_src, uniform = _prepare_maps(a, b, math, int(self.num_patches))
         n = len(tgt)
         dev = tgt[0].device
         _warn_queue(dev).poll()
-        math = self.math or DEFAULT_MATH
         if not uniform:
             ids = draw_patch_ids_all(src, self.num_patches)                           # :60-63
             self.__dict__["_last_ids"] = ids
@@ -630,7 +673,7 @@ class PatchNCELoss(nn.Module):
         p_list = [patch_count(self.num_patches, t.shape[2] * t.shape[3]) for t in tgt]    # :60
         if max(p_list) > _lib.MAX_PATCHES:
             raise RuntimeError(f"num_patches > {_lib.MAX_PATCHES} is not supported")
-        sp = _shape_plan(tgt, p_list, math)
+        sp = _shape_plan(tgt, p_list, math, _is_nhwc(tgt[0]))
         rng = idplan = None
         if sp.tc and not torch.cuda.is_current_stream_capturing() and _philox_ready(dev):
             # the library draws the ids (bit for bit torch.randint's, :63) inside its id-sort launch: no randint

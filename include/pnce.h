@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PNCE_ABI_VERSION 3
+#define PNCE_ABI_VERSION 4
 #define PNCE_MAX_LAYERS 8      /* nce_layers per call (reference config uses 5 ids -> 4 maps)   */
 #define PNCE_MAX_PATCHES 4096  /* P = min(num_patches, H*W)  patchnce_cut.py:60; argument check only: the
                                 * kernels take P <= 1024 (tensor cores, C <= 256) or P <= 1280 (fp32 CUDA cores),
@@ -123,6 +123,24 @@ int pnce_draw_ids(const pnce_layer_t* layers, int n_layers, unsigned long long p
  * chain of SURVEY.md section 8 row a11 (index_put_ / select_backward / zeros + adds).           */
 int pnce_bwd(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int math_mode,
              void* dev_workspace, size_t workspace_bytes, const float* dev_grad_out, void* stream);
+
+/* ---- channels-last maps (an extension: the reference's `feat.view(B, C, -1)`, patchnce_cut.py:56, only takes
+ * contiguous NCHW) ------------------------------------------------------------------------------------------------
+ * With layout = PNCE_LAYOUT_NHWC every layers[l].src / tgt / dtgt is the storage of a torch.channels_last tensor:
+ * logical shape (B, C, H, W), memory order (B, H, W, C) -- a sampled patch is then C CONTIGUOUS values instead of C
+ * values in C different DRAM lines, and the gather reads exactly the bytes it uses.  Ids, loss and
+ * gradient values obey the same law as the NCHW entry points (the oracle on the permuted data).  Tensor-core math
+ * modes and their shape envelope only (PNCE_ERR_UNSUPPORTED otherwise).
+ *   pnce_fwd_ex = pnce_fwd (plan == NULL, philox == NULL), pnce_fwd_draw (philox = {seed, offset}) or
+ *                 pnce_fwd_planned (plan != NULL, from pnce_plan_ids / pnce_plan_ids_draw) with a layout;
+ *   pnce_bwd_ex = pnce_bwd / pnce_bwd_planned with a layout.  PNCE_LAYOUT_NCHW makes them the calls above.        */
+typedef enum { PNCE_LAYOUT_NCHW = 0, PNCE_LAYOUT_NHWC = 1 } pnce_layout_t;
+int pnce_fwd_ex(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int layout, float temperature,
+                int math_mode, void* dev_workspace, size_t workspace_bytes, void* dev_plan, size_t plan_bytes,
+                const unsigned long long* philox_seed_offset, float* dev_loss_out, int* dev_nonfinite, void* stream);
+int pnce_bwd_ex(const pnce_layer_t* layers, int n_layers, int batch, int dtype, int layout, int math_mode,
+                void* dev_workspace, size_t workspace_bytes, void* dev_plan, size_t plan_bytes,
+                const float* dev_grad_out, void* stream);
 
 /* ---- north-star module split ------------------------------ */
 
