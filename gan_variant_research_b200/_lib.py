@@ -21,6 +21,7 @@ EXPORTS = [
     "pnce_rows_loss_workspace_bytes", "pnce_rows_loss_fwd_bwd", "pnce_selftest_umma",
     "pnce_multi_chunk_elems", "pnce_multi_axpby", "pnce_amp_adam_scratch_floats", "pnce_amp_adam_step",
     "pnce_diffaug_scratch_floats", "pnce_diffaug", "pnce_hinge_fwd", "pnce_hinge_bwd",
+    "pnce_netf_workspace_bytes", "pnce_netf_fwd", "pnce_netf_bwd",
     "pnce_head_workspace_bytes", "pnce_head_fwd", "pnce_head_bwd", "pnce_head_bwd_params", "pnce_head_bwd_dense",
 ]
 
@@ -94,6 +95,9 @@ def load():
                                   vp, sz, vp, vp, vp]
     for fn in (lib.pnce_head_bwd, lib.pnce_head_bwd_params, lib.pnce_head_bwd_dense):
         fn.argtypes = [ctypes.POINTER(PnceLayer), ctypes.POINTER(PnceHead), i32, i32, i32, i32, i32, vp, sz, vp, vp]
+    lib.pnce_netf_workspace_bytes.argtypes = [ctypes.POINTER(PnceSample), i32, i32, i32, ctypes.POINTER(sz)]
+    for fn in (lib.pnce_netf_fwd, lib.pnce_netf_bwd):
+        fn.argtypes = [ctypes.POINTER(PnceSample), ctypes.POINTER(PnceHead), i32, i32, i32, i32, i32, i32, vp, sz, vp, vp]
     lib.pnce_multi_axpby.argtypes = [vp, vp, vp, vp, vp, i32, f32, f32, i32, vp]
     f64 = ctypes.c_double
     lib.pnce_amp_adam_scratch_floats.argtypes = [i32]

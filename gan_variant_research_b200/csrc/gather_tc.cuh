@@ -23,7 +23,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
 }
 
 template <typename T>
-__device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long local) {
+__device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long local, int side0) {
   const int nchunk = L.nchunk;
   const int npb = (L.Ppad + 255) >> 8;                       // CTAs of 256 patch slots per (image, side, chunk)
   const int s = (int)(local % nchunk);
@@ -31,7 +31,7 @@ __device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long loca
   const long long rest = local / nchunk / npb;
   const int p = pb * 256 + threadIdx.x;
   const int b = b0 + (int)(rest % B);
-  const int side = (int)(rest / B);                          // 0 = src (k), 1 = tgt (q)
+  const int side = (int)(rest / B) + side0;                  // 0 = src (k), 1 = tgt (q); side0 = 1: tgt only
   const int C = L.C, HW = L.HW, P = L.P, Ppad = L.Ppad, Cp8 = L.Cp >> 3;
   if (p >= Ppad) return;
   const bool valid = p < P;
@@ -99,9 +99,9 @@ __global__ void __launch_bounds__(kThreads) k_gather_tc(const __grid_constant__ 
   const int slot = find_layer(m, blk, p.n_layers);
   const int l = m.layer[slot];                                 // launch_gather_tc orders light layers first
   const long long local = blk - m.start[slot];
-  if (p.dtype == PNCE_F32) gather_tc_chunk<float>(p.L[l], p.b0, p.bn, local);
-  else if (p.dtype == PNCE_F16) gather_tc_chunk<__half>(p.L[l], p.b0, p.bn, local);
-  else gather_tc_chunk<__nv_bfloat16>(p.L[l], p.b0, p.bn, local);
+  if (p.dtype == PNCE_F32) gather_tc_chunk<float>(p.L[l], p.b0, p.bn, local, p.side0);
+  else if (p.dtype == PNCE_F16) gather_tc_chunk<__half>(p.L[l], p.b0, p.bn, local, p.side0);
+  else gather_tc_chunk<__nv_bfloat16>(p.L[l], p.b0, p.bn, local, p.side0);
 }
 
 // One CTA per layer: ids -> (sid, perm, rank, ustart, bitmap, prefix); CTA 0 also resets the

@@ -23,7 +23,7 @@
 
 namespace pnce {
 
-enum GemmMode { GM_H = 0, GM_YQ = 1, GM_YK = 2, GM_DH = 3, GM_DX = 4 };
+enum GemmMode { GM_H = 0, GM_YQ = 1, GM_YK = 2, GM_DH = 3, GM_DX = 4, GM_YROWS = 5 };
 
 struct GemmProb {
   const __nv_bfloat16 *a_hi, *a_lo;       // row blob, K columns
@@ -34,8 +34,14 @@ struct GemmProb {
   __nv_bfloat16 *o_hi, *o_lo;              // GM_H / GM_DH / GM_YQ: row blob with N columns
   __nv_bfloat16 *k_hi, *k_lo, *k2_hi, *k2_lo;   // GM_YK: the two K layouts of k_loss_tc
   float* ss;                               // GM_YQ / GM_YK: [B][N/32][Ppad] partial sums of squares
-  float* outT;                             // GM_DX: dxT [B][C][Ppad]
+  float* outT;                             // GM_DX: dxT [B][C][Ppad], or row-major [B][Ppad][C] with rm != 0
   const __nv_bfloat16* mask_hi;            // GM_DH: H blob (hi part), same indexing as o_hi
+  // GM_YROWS (PatchSampleF(use_mlp=True).forward, persistent kernel only): y / max(||y||, eps) leaves as fp32 rows
+  // (B*P, N) in the CALLER's row order (row b*P + perm[slot]), with the norm bookkeeping of pnce_sample_fwd in inv_out
+  float* rows_out;
+  float* inv_out;
+  const int* perm;                         // sorted slot -> original index (k_prep)
+  int rm;                                  // GM_DX: row-major rows (channels-last maps, nhwc.cuh)
 };
 
 constexpr int kGemmMaxProb = 16;
@@ -205,7 +211,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_gemm_tc(const __grid_constant
         split8(v8, hi, lo);
         const int n8 = ch * 4 + g8;
         if (mode == GM_YK) {
-          const size_t o1 = (((size_t)b * N8 + n8) * (Ppad >> 3) + (p >> 3)) * 64 + (size_t)(p & 7) * 8;
+          // key blocks of <= 256 rows, one after the other (gather_tc_chunk's K layout; one block when Ppad <= 256)
+          const int pb = p >> 8, nb8 = min(256, Ppad - pb * 256) >> 3;
+          const size_t o1 = ((((size_t)b * Ppad + (size_t)pb * 256) * N8) / 8 + (size_t)n8 * nb8 + ((p & 255) >> 3)) * 64 + (size_t)(p & 7) * 8;
           const size_t o2 = (((size_t)b * (Ppad >> 3) + (p >> 3)) * N8 + n8) * 64 + (size_t)(p & 7) * 8;
           *reinterpret_cast<uint4*>(pr.k_hi + o1) = hi;
           *reinterpret_cast<uint4*>(pr.k2_hi + o2) = hi;

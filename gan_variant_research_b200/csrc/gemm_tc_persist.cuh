@@ -15,7 +15,7 @@ namespace pnce {
 
 constexpr int kGpThreads = 320;
 constexpr int kGpSlots = 8;
-constexpr int kGpSmemBytes = kGpSlots * kGemmStageBytes + 512;
+constexpr int kGpSmemBytes = kGpSlots * kGemmStageBytes + 512 + 2048;   // + GM_YROWS row-norm exchange [2][2][128] floats
 
 struct GpShared {
   uint64_t full[kGpSlots], empty[kGpSlots], accfull[2], accfree[2];
@@ -137,6 +137,51 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
       mbar_wait(&sh->accfull[n & 1], ((uint32_t)n >> 1) & 1u, dead);
       tc_fence_after();
       const int nch = N >> 5;
+      if (mode == GM_YROWS) {
+        // ---- PatchSampleF(use_mlp=True) output: y = acc + b2, out = y / max(||y||, eps) as fp32 rows.  The row norm
+        //      needs every column, and the two warps of a quadrant hold alternate chunks: pass 1 sums the squares and
+        //      swaps the partial sums through shared memory, pass 2 re-reads the accumulator and writes the rows ----
+        float* xss = reinterpret_cast<float*>(smem + kGpSlots * kGemmStageBytes + 512) + (n & 1) * 256;
+        float ssum = 0.f;
+        for (int ch = half; ch < nch; ch += 2) {
+          uint32_t r[32];
+          tmem_ld32(trow + ch * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float x = __uint_as_float(r[k]) + __ldg(pr.bias + ch * 32 + k);
+            ssum = fmaf(x, x, ssum);
+          }
+        }
+        xss[half * 128 + i] = ssum;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");       // the two warps of this quadrant
+        const float nrm = sqrtf(xss[i] + xss[128 + i]);
+        const float den = (nrm == nrm) ? fmaxf(nrm, kNormEps) : nrm;      // clamp_min keeps NaN (F.normalize, patchnce_cut.py:77)
+        const float scale = 1.0f / den;
+        const size_t orow = ((size_t)b * pr.P + (rowok ? __ldg(pr.perm + p) : 0)) * N;
+        if (rowok && half == 0 && pr.inv_out != nullptr)
+          pr.inv_out[orow / N] = (nrm == nrm) ? (nrm < kNormEps ? -1.0f / kNormEps : 1.0f / nrm) : nrm;
+        for (int ch = half; ch < nch; ch += 2) {
+          uint32_t r[32];
+          tmem_ld32(trow + ch * 32, r);
+          tmem_ld_wait();
+          if (rowok) {
+            float* o = pr.rows_out + orow + ch * 32;
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+              float4 v4;
+              v4.x = (__uint_as_float(r[k4 * 4 + 0]) + __ldg(pr.bias + ch * 32 + k4 * 4 + 0)) * scale;
+              v4.y = (__uint_as_float(r[k4 * 4 + 1]) + __ldg(pr.bias + ch * 32 + k4 * 4 + 1)) * scale;
+              v4.z = (__uint_as_float(r[k4 * 4 + 2]) + __ldg(pr.bias + ch * 32 + k4 * 4 + 2)) * scale;
+              v4.w = (__uint_as_float(r[k4 * 4 + 3]) + __ldg(pr.bias + ch * 32 + k4 * 4 + 3)) * scale;
+              *reinterpret_cast<float4*>(o + k4 * 4) = v4;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&sh->accfree[n & 1]);
+        continue;
+      }
       for (int ch = half; ch < nch; ch += 2) {
         uint32_t r[32];
         tmem_ld32(trow + ch * 32, r);
@@ -162,7 +207,17 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
           const bool keep_dx = g_dx_evict_last != 0;
           uint64_t pol_dx = 0;
           if (keep_dx) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_dx));
-          if (rowok) {
+          if (rowok && pr.rm) {                               // channels-last maps: row-major rows, one 128-byte line per thread
+            float* o = pr.outT + ((size_t)b * Ppad + p) * pr.C + ch * 32;
+            if (ch * 32 + 32 <= pr.C && (pr.C & 3) == 0) {
+#pragma unroll
+              for (int k4 = 0; k4 < 8; ++k4) st_dx4(o + k4 * 4, v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3], keep_dx, pol_dx);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (ch * 32 + k < pr.C) st_dx(o + k, v[k], keep_dx, pol_dx);
+            }
+          } else if (rowok) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
               const int c = ch * 32 + k;
@@ -201,7 +256,9 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
           split8(v8, hi, lo);
           const int n8 = ch * 4 + g8;
           if (mode == GM_YK) {
-            const size_t o1 = (((size_t)b * N8 + n8) * (Ppad >> 3) + (p >> 3)) * 64 + (size_t)(p & 7) * 8;
+            // key blocks of <= 256 rows, one after the other (gather_tc_chunk's K layout; one block when Ppad <= 256)
+            const int pb = p >> 8, nb8 = min(256, Ppad - pb * 256) >> 3;
+            const size_t o1 = ((((size_t)b * Ppad + (size_t)pb * 256) * N8) / 8 + (size_t)n8 * nb8 + ((p & 255) >> 3)) * 64 + (size_t)(p & 7) * 8;
             const size_t o2 = (((size_t)b * (Ppad >> 3) + (p >> 3)) * N8 + n8) * 64 + (size_t)(p & 7) * 8;
             *reinterpret_cast<uint4*>(pr.k_hi + o1) = hi;
             *reinterpret_cast<uint4*>(pr.k2_hi + o2) = hi;

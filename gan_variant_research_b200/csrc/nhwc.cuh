@@ -48,13 +48,13 @@ template <> struct Vec8<__nv_bfloat16> {
 
 // One warp item of the NHWC gather; writes exactly what gather_tc_chunk writes for the same (side, image, slots, chunk).
 template <typename T>
-__device__ __forceinline__ void gather_nhwc_item(const LayerDev& L, int b0, int B, long long witem, int lane) {
+__device__ __forceinline__ void gather_nhwc_item(const LayerDev& L, int b0, int B, long long witem, int lane, int side0) {
   const int nchunk = L.nchunk, np8 = L.Ppad >> 3;
   const int s = (int)(witem % nchunk);
   const int p8 = (int)((witem / nchunk) % np8);
   const long long rest = witem / nchunk / np8;
   const int b = b0 + (int)(rest % B);
-  const int side = (int)(rest / B);                          // 0 = src (k), 1 = tgt (q)
+  const int side = (int)(rest / B) + side0;                  // 0 = src (k), 1 = tgt (q); side0 = 1: tgt only
   const int C = L.C, HW = L.HW, P = L.P, Ppad = L.Ppad, Cp8 = L.Cp >> 3;
   const int p = p8 * 8 + (lane & 7);                         // sorted slot
   const int g = lane >> 3;                                   // 8-channel group of the chunk
@@ -125,12 +125,12 @@ __global__ void __launch_bounds__(kThreads) k_gather_tc_nhwc(const __grid_consta
   const int l = m.layer[slot];
   const LayerDev& L = p.L[l];
   const long long witem = (blk - m.start[slot]) * 8 + (threadIdx.x >> 5);
-  const long long nitems = 2ll * p.bn * (L.Ppad >> 3) * L.nchunk;
+  const long long nitems = (long long)(2 - p.side0) * p.bn * (L.Ppad >> 3) * L.nchunk;
   if (witem >= nitems) return;
   const int lane = threadIdx.x & 31;
-  if (p.dtype == PNCE_F32) gather_nhwc_item<float>(L, p.b0, p.bn, witem, lane);
-  else if (p.dtype == PNCE_F16) gather_nhwc_item<__half>(L, p.b0, p.bn, witem, lane);
-  else gather_nhwc_item<__nv_bfloat16>(L, p.b0, p.bn, witem, lane);
+  if (p.dtype == PNCE_F32) gather_nhwc_item<float>(L, p.b0, p.bn, witem, lane, p.side0);
+  else if (p.dtype == PNCE_F16) gather_nhwc_item<__half>(L, p.b0, p.bn, witem, lane, p.side0);
+  else gather_nhwc_item<__nv_bfloat16>(L, p.b0, p.bn, witem, lane, p.side0);
 }
 
 // -------------------------------------------------------------------------------------------------

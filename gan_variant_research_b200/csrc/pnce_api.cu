@@ -14,6 +14,7 @@
 #include "loss_tc.cuh"
 #include "loss_tc_persist.cuh"
 #include "nhwc.cuh"
+#include "netf.cuh"
 #include "rows_pack.cuh"
 #include "multi_tensor.cuh"
 #include "sample_bwd.cuh"
@@ -262,7 +263,7 @@ static int launch_gather_tc(const Params& p, cudaStream_t st) {
     for (int s = 0; s < p.n_layers; ++s) {
       m.start[s] = acc;
       m.layer[s] = order[s];
-      acc += (2ll * p.bn * (p.L[order[s]].Ppad >> 3) * p.L[order[s]].nchunk + 7) / 8;
+      acc += ((long long)(2 - p.side0) * p.bn * (p.L[order[s]].Ppad >> 3) * p.L[order[s]].nchunk + 7) / 8;
     }
     m.start[p.n_layers] = acc;
     if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
@@ -273,7 +274,7 @@ static int launch_gather_tc(const Params& p, cudaStream_t st) {
   for (int s = 0; s < p.n_layers; ++s) {
     m.start[s] = acc;
     m.layer[s] = order[s];
-    acc += 2ll * p.bn * ((p.L[order[s]].Ppad + 255) / 256) * p.L[order[s]].nchunk;
+    acc += (long long)(2 - p.side0) * p.bn * ((p.L[order[s]].Ppad + 255) / 256) * p.L[order[s]].nchunk;
   }
   m.start[p.n_layers] = acc;
   if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
@@ -1150,7 +1151,7 @@ struct HeadPlan {
 static bool head_shapes_ok(const pnce_layer_t* layers, int n_layers, int nc) {
   if (nc != 128 && nc != 256) return false;
   for (int l = 0; l < n_layers; ++l)
-    if (layers[l].P > 256 || layers[l].C > 256) return false;
+    if (layers[l].P > 1024 || layers[l].C > 256) return false;
   return true;
 }
 
@@ -1220,7 +1221,8 @@ static size_t carve_head(const pnce_layer_t* layers, int n_layers, int B, int nc
     V.qss = cv.take<float>((size_t)B * (nc / 32) * Ppad);
     V.kss = cv.take<float>((size_t)B * (nc / 32) * Ppad);
     V.qinv = cv.take<float>((size_t)B * a.P);
-    V.partial = cv.take<float>((size_t)B * 2);
+    V.kinv = cv.take<float>((size_t)B * Ppad);                  // key-blocked loss kernel (P > 256)
+    V.partial = cv.take<float>((size_t)B * (Ppad / 128 > 2 ? Ppad / 128 : 2));
     V.dxT = nullptr;
     const int tiles = B * (Ppad / 128);
     hb.slabs = tiles < 8 ? tiles : 8;
@@ -1490,6 +1492,305 @@ int pnce_head_bwd_params(const pnce_layer_t* layers, const pnce_head_t* heads, i
 int pnce_head_bwd_dense(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
                         int nc, int math_mode, void* ws, size_t ws_bytes, const float* grad_out, void* stream) {
   return head_bwd_phases(2, layers, heads, n_layers, batch, dtype, nc, math_mode, ws, ws_bytes, grad_out, stream);
+}
+
+
+// ---- PatchSampleF(use_mlp=True) as a module of its own ------------------------------------------------------------
+namespace pnce {
+
+struct NetfPlan {
+  Params pg;                                   // the maps: gather of raw patches, dense backward of dX
+  HeadLayerBufs hb[PNCE_MAX_LAYERS];           // xq = X blob, hq = H blob, dh = dH blob, weight blobs, split-K partials
+  __nv_bfloat16* dy[PNCE_MAX_LAYERS][2];       // d loss / d Y blob (hi, lo)
+};
+
+static size_t carve_netf(const pnce_sample_t* sm, int n, int B, int nc, bool x3, void* ws, NetfPlan* out) {
+  Carver cv(ws);
+  NetfPlan local;
+  NetfPlan* np = out ? out : &local;
+  memset(np, 0, sizeof(NetfPlan));
+  Params& pg = np->pg;
+  pg.n_layers = n;
+  pg.B = B;
+  pg.side0 = 1;                                // one side only: the maps play the "tgt" role of the fused kernels
+  const int nparts = x3 ? 2 : 1;
+  for (int l = 0; l < n; ++l) {
+    const pnce_sample_t& a = sm[l];
+    LayerDev& G = pg.L[l];
+    HeadLayerBufs& hb = np->hb[l];
+    const int Ppad = (a.P + 127) / 128 * 128, Cp = (a.C + 31) / 32 * 32;
+    G.tgt = a.feat; G.dtgt = a.dfeat;
+    G.ids = reinterpret_cast<const long long*>(a.ids);
+    G.C = a.C; G.HW = a.H * a.W; G.P = a.P;
+    G.ntiles = (a.P + kRowTile - 1) / kRowTile;
+    G.sorted = 1;
+    G.Cp = Cp; G.Ppad = Ppad; G.nchunk = Cp / 32; G.nparts = Ppad / 128;
+    G.head_src_rows = 1;
+    G.sid = cv.take<int>(a.P);
+    G.perm = cv.take<int>(a.P);
+    G.rank = cv.take<int>(a.P);
+    G.cslot = cv.take<int>((size_t)(G.HW + kTilePos - 1) / kTilePos + 1);
+    G.dxpitch = Ppad;
+    G.dxT = cv.take<float>((size_t)B * a.C * Ppad);
+    const size_t xblob = (size_t)B * Ppad * Cp, yblob = (size_t)B * Ppad * nc;
+    for (int k = 0; k < nparts; ++k) {
+      hb.xq[k] = cv.take<__nv_bfloat16>(xblob);
+      hb.hq[k] = cv.take<__nv_bfloat16>(yblob);
+      hb.dh[k] = cv.take<__nv_bfloat16>(yblob);
+      np->dy[l][k] = cv.take<__nv_bfloat16>(yblob);
+      hb.w1[k] = cv.take<__nv_bfloat16>((size_t)nc * Cp);
+      hb.w1t[k] = cv.take<__nv_bfloat16>((size_t)nc * Cp);
+      hb.w2[k] = cv.take<__nv_bfloat16>((size_t)nc * nc);
+      hb.w2t[k] = cv.take<__nv_bfloat16>((size_t)nc * nc);
+    }
+    G.qhi = hb.xq[0]; G.qlo = hb.xq[1];
+    const int tiles = B * (Ppad / 128);
+    hb.slabs = tiles < 8 ? tiles : 8;
+    hb.pw2 = cv.take<float>((size_t)hb.slabs * nc * nc);
+    hb.pb2 = cv.take<float>((size_t)hb.slabs * nc);
+    hb.pw1 = cv.take<float>((size_t)hb.slabs * nc * Cp);
+    hb.pb1 = cv.take<float>((size_t)hb.slabs * nc);
+  }
+  return align_up(cv.off, 256);
+}
+
+static int check_netf(const pnce_sample_t* sm, const pnce_head_t* heads, int n, int batch, int dtype, int layout, int nc,
+                      int math_mode, void* ws) {
+  int rc = check_samples(sm, n, batch, dtype);
+  if (rc != PNCE_OK) return rc;
+  if (heads == nullptr) return PNCE_ERR_ARG;
+  if (layout != PNCE_LAYOUT_NCHW && layout != PNCE_LAYOUT_NHWC) return PNCE_ERR_ARG;
+  if (math_mode != PNCE_MATH_TC_BF16X3 && math_mode != PNCE_MATH_TC_BF16) return PNCE_ERR_UNSUPPORTED;
+  if (nc != 128 && nc != 256) return PNCE_ERR_UNSUPPORTED;
+  for (int l = 0; l < n; ++l) {
+    if (sm[l].P > 1024 || sm[l].C > 256) return PNCE_ERR_UNSUPPORTED;
+    const pnce_head_t& h = heads[l];
+    if (!h.w1 || !h.b1 || !h.w2 || !h.b2) return PNCE_ERR_ARG;
+  }
+  if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
+  return PNCE_OK;
+}
+
+}  // namespace pnce
+
+int pnce_netf_workspace_bytes(const pnce_sample_t* maps, int n_maps, int batch, int nc, size_t* bytes) {
+  if (bytes == nullptr) return PNCE_ERR_ARG;
+  int rc = check_samples(maps, n_maps, batch, PNCE_F32);
+  if (rc != PNCE_OK) return rc;
+  if (nc != 128 && nc != 256) return PNCE_ERR_UNSUPPORTED;
+  for (int l = 0; l < n_maps; ++l)
+    if (maps[l].P > 1024 || maps[l].C > 256) return PNCE_ERR_UNSUPPORTED;
+  *bytes = carve_netf(maps, n_maps, batch, nc, true, nullptr, nullptr);
+  return PNCE_OK;
+}
+
+int pnce_netf_fwd(const pnce_sample_t* maps, const pnce_head_t* heads, int n_maps, int batch, int dtype, int layout,
+                  int nc, int math_mode, void* ws, size_t ws_bytes, int* dev_status, void* stream) {
+  int rc = check_netf(maps, heads, n_maps, batch, dtype, layout, nc, math_mode, ws);
+  if (rc != PNCE_OK) return rc;
+  const bool x3 = math_mode == PNCE_MATH_TC_BF16X3;
+  static thread_local NetfPlan np;
+  if (carve_netf(maps, n_maps, batch, nc, x3, ws, &np) > ws_bytes) return PNCE_ERR_WORKSPACE;
+  Params& pg = np.pg;
+  for (int l = 0; l < n_maps; ++l) {
+    if (maps[l].feat == nullptr || maps[l].rows == nullptr || maps[l].inv == nullptr) return PNCE_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(maps[l].feat) & (dtype_size(dtype) - 1)) return PNCE_ERR_ALIGN;
+    if (reinterpret_cast<uintptr_t>(maps[l].rows) & 15u) return PNCE_ERR_ALIGN;
+  }
+  pg.dtype = dtype;
+  pg.math = math_mode;
+  pg.nhwc = layout == PNCE_LAYOUT_NHWC ? 1 : 0;
+  pg.b0 = 0; pg.bn = batch;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // 1. ids -> sorted slots; weights -> operand blobs (plain and transposed: the backward needs both)
+  rc = launch_prep(pg, st);
+  if (rc != PNCE_OK) return rc;
+  {
+    static thread_local WprepLaunch wl;
+    memset(&wl, 0, sizeof(wl));
+    int blocks = 0;
+    auto add = [&](const float* w, __nv_bfloat16* hi, __nv_bfloat16* lo, int R, int Cw, int N, int K, int tr) {
+      WprepJob& j = wl.job[wl.n];
+      j.w = w; j.hi = hi; j.lo = lo; j.R = R; j.Cw = Cw; j.N = N; j.K = K; j.transpose = tr;
+      wl.start[wl.n++] = blocks;
+      blocks += (N / 8) * (K / 8);
+    };
+    for (int l = 0; l < n_maps; ++l) {
+      const HeadLayerBufs& hb = np.hb[l];
+      const int C = maps[l].C, Cp = pg.L[l].Cp;
+      add(heads[l].w1, hb.w1[0], hb.w1[1], nc, C, nc, Cp, 0);
+      add(heads[l].w1, hb.w1t[0], hb.w1t[1], nc, C, Cp, nc, 1);
+      add(heads[l].w2, hb.w2[0], hb.w2[1], nc, nc, nc, nc, 0);
+      add(heads[l].w2, hb.w2t[0], hb.w2t[1], nc, nc, nc, nc, 1);
+    }
+    wl.start[wl.n] = blocks;
+    k_wprep<<<(unsigned)blocks, 64, 0, st>>>(wl);
+    PNCE_CUDA(cudaGetLastError());
+  }
+  // 2. raw patches as the X row blob (sorted-slot order)
+  rc = launch_gather_tc(pg, st);
+  if (rc != PNCE_OK) return rc;
+  // 3. H = relu(X W1^T + b1)
+  static thread_local GemmLaunch g;
+  memset(&g, 0, sizeof(g));
+  g.x3 = x3 ? 1 : 0;
+  g.err = dev_status;
+  for (int l = 0; l < n_maps; ++l) {
+    const HeadLayerBufs& hb = np.hb[l];
+    const LayerDev& G = pg.L[l];
+    GemmProb& pr = g.pr[g.n++];
+    pr.a_hi = hb.xq[0]; pr.a_lo = hb.xq[1]; pr.b_hi = hb.w1[0]; pr.b_lo = hb.w1[1];
+    pr.bias = heads[l].b1;
+    pr.K = G.Cp; pr.N = nc; pr.tiles = batch * (G.Ppad / 128); pr.mode = GM_H;
+    pr.P = G.P; pr.Ppad = G.Ppad; pr.halves = G.Ppad / 128; pr.C = G.C;
+    pr.o_hi = hb.hq[0]; pr.o_lo = hb.hq[1];
+  }
+  rc = launch_gemm(g, st);
+  if (rc != PNCE_OK) return rc;
+  // 4. Y = H W2^T + b2, L2-normalised, as fp32 rows in the caller's row order
+  memset(&g, 0, sizeof(g));
+  g.x3 = x3 ? 1 : 0;
+  g.err = dev_status;
+  for (int l = 0; l < n_maps; ++l) {
+    const HeadLayerBufs& hb = np.hb[l];
+    const LayerDev& G = pg.L[l];
+    GemmProb& pr = g.pr[g.n++];
+    pr.a_hi = hb.hq[0]; pr.a_lo = hb.hq[1]; pr.b_hi = hb.w2[0]; pr.b_lo = hb.w2[1];
+    pr.bias = heads[l].b2;
+    pr.K = nc; pr.N = nc; pr.tiles = batch * (G.Ppad / 128); pr.mode = GM_YROWS;
+    pr.P = G.P; pr.Ppad = G.Ppad; pr.halves = G.Ppad / 128; pr.C = nc;
+    pr.rows_out = maps[l].rows; pr.inv_out = maps[l].inv; pr.perm = G.perm;
+  }
+  return launch_gemm(g, st);
+}
+
+int pnce_netf_bwd(const pnce_sample_t* maps, const pnce_head_t* heads, int n_maps, int batch, int dtype, int layout,
+                  int nc, int math_mode, void* ws, size_t ws_bytes, int* dev_status, void* stream) {
+  int rc = check_netf(maps, heads, n_maps, batch, dtype, layout, nc, math_mode, ws);
+  if (rc != PNCE_OK) return rc;
+  const bool x3 = math_mode == PNCE_MATH_TC_BF16X3;
+  static thread_local NetfPlan np;
+  if (carve_netf(maps, n_maps, batch, nc, x3, ws, &np) > ws_bytes) return PNCE_ERR_WORKSPACE;
+  Params& pg = np.pg;
+  bool dense = true;
+  for (int l = 0; l < n_maps; ++l) {
+    const pnce_head_t& h = heads[l];
+    if (!h.dw1 || !h.db1 || !h.dw2 || !h.db2) return PNCE_ERR_ARG;
+    if (!maps[l].drows || !maps[l].rows || !maps[l].inv) return PNCE_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(maps[l].drows) & 15u) || (reinterpret_cast<uintptr_t>(maps[l].rows) & 15u)) return PNCE_ERR_ALIGN;
+    if (maps[l].dfeat == nullptr) dense = false;                // maps without gradient: every dfeat NULL
+    else if (reinterpret_cast<uintptr_t>(maps[l].dfeat) & (dtype_size(dtype) - 1)) return PNCE_ERR_ALIGN;
+  }
+  if (!dense)
+    for (int l = 0; l < n_maps; ++l)
+      if (maps[l].dfeat != nullptr) return PNCE_ERR_ARG;
+  pg.dtype = dtype;
+  pg.math = math_mode;
+  pg.nhwc = layout == PNCE_LAYOUT_NHWC ? 1 : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // 1. normalise backward, d loss / d Y as a row blob
+  {
+    static thread_local NetfPackLaunch pk;
+    memset(&pk, 0, sizeof(pk));
+    pk.n = n_maps; pk.B = batch;
+    long long acc = 0;
+    for (int l = 0; l < n_maps; ++l) {
+      const LayerDev& G = pg.L[l];
+      NetfPackJob& j = pk.job[l];
+      j.g = maps[l].drows; j.y = maps[l].rows; j.inv = maps[l].inv; j.perm = G.perm;
+      j.hi = np.dy[l][0]; j.lo = np.dy[l][1];
+      j.P = G.P; j.Ppad = G.Ppad; j.N = nc;
+      pk.start[l] = acc;
+      acc += ((long long)batch * G.Ppad + 7) / 8;
+    }
+    pk.start[n_maps] = acc;
+    if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+    k_netf_dy_pack<<<(unsigned)acc, kThreads, 0, st>>>(pk);
+    PNCE_CUDA(cudaGetLastError());
+  }
+  // 2. dH = (dY W2) * [H > 0]
+  static thread_local GemmLaunch g;
+  memset(&g, 0, sizeof(g));
+  g.x3 = x3 ? 1 : 0;
+  g.err = dev_status;
+  for (int l = 0; l < n_maps; ++l) {
+    const HeadLayerBufs& hb = np.hb[l];
+    const LayerDev& G = pg.L[l];
+    GemmProb& pr = g.pr[g.n++];
+    pr.a_hi = np.dy[l][0]; pr.a_lo = np.dy[l][1]; pr.b_hi = hb.w2t[0]; pr.b_lo = hb.w2t[1];
+    pr.K = nc; pr.N = nc; pr.tiles = batch * (G.Ppad / 128); pr.mode = GM_DH;
+    pr.P = G.P; pr.Ppad = G.Ppad; pr.halves = G.Ppad / 128; pr.C = nc;
+    pr.o_hi = hb.dh[0]; pr.o_lo = hb.dh[1]; pr.mask_hi = hb.hq[0];
+  }
+  rc = launch_gemm(g, st);
+  if (rc != PNCE_OK) return rc;
+  // 3. dX = dH W1 -> the gradient rows the dense backward reads
+  if (dense) {
+    memset(&g, 0, sizeof(g));
+    g.x3 = x3 ? 1 : 0;
+    g.err = dev_status;
+    for (int l = 0; l < n_maps; ++l) {
+      const HeadLayerBufs& hb = np.hb[l];
+      const LayerDev& G = pg.L[l];
+      GemmProb& pr = g.pr[g.n++];
+      pr.a_hi = hb.dh[0]; pr.a_lo = hb.dh[1]; pr.b_hi = hb.w1t[0]; pr.b_lo = hb.w1t[1];
+      pr.K = nc; pr.N = G.Cp; pr.tiles = batch * (G.Ppad / 128); pr.mode = GM_DX;
+      pr.P = G.P; pr.Ppad = G.Ppad; pr.halves = G.Ppad / 128; pr.C = G.C;
+      pr.outT = G.dxT; pr.rm = pg.nhwc;
+    }
+    rc = launch_gemm(g, st);
+    if (rc != PNCE_OK) return rc;
+  }
+  // 4. weight / bias gradients (split-K partials + deterministic reduce)
+  static thread_local WgradLaunch wg;
+  memset(&wg, 0, sizeof(wg));
+  wg.x3 = x3 ? 1 : 0;
+  wg.err = dev_status;
+  long long acc = 0;
+  for (int l = 0; l < n_maps; ++l) {
+    const HeadLayerBufs& hb = np.hb[l];
+    const LayerDev& G = pg.L[l];
+    const int tiles = batch * (G.Ppad / 128);
+    for (int which = 0; which < 2; ++which) {
+      WgradProb& pr = wg.pr[wg.n];
+      pr.a_hi = which ? hb.dh[0] : np.dy[l][0]; pr.a_lo = which ? hb.dh[1] : np.dy[l][1];
+      pr.b_hi = which ? hb.xq[0] : hb.hq[0]; pr.b_lo = which ? hb.xq[1] : hb.hq[1];
+      pr.NA = nc; pr.N = which ? G.Cp : nc; pr.tiles = tiles; pr.slabs = hb.slabs;
+      pr.partial = which ? hb.pw1 : hb.pw2; pr.pbias = which ? hb.pb1 : hb.pb2;
+      wg.start[wg.n++] = acc;
+      acc += (long long)hb.slabs * (nc / 128);
+    }
+  }
+  wg.start[wg.n] = acc;
+  rc = set_smem(k_wgrad_tc, kWgSmemBytes);
+  if (rc != PNCE_OK) return rc;
+  k_wgrad_tc<<<(unsigned)acc, kTcThreads, kWgSmemBytes, st>>>(wg);
+  PNCE_CUDA(cudaGetLastError());
+  {
+    static thread_local WreduceLaunch rl;
+    memset(&rl, 0, sizeof(rl));
+    rl.grad_out = nullptr;                                     // the incoming rows already carry the upstream gradient
+    int blocks = 0;
+    for (int l = 0; l < n_maps; ++l) {
+      const HeadLayerBufs& hb = np.hb[l];
+      const LayerDev& G = pg.L[l];
+      for (int which = 0; which < 2; ++which) {
+        WreduceJob& j = rl.job[rl.n];
+        j.partial = which ? hb.pw1 : hb.pw2; j.pbias = which ? hb.pb1 : hb.pb2;
+        j.dw = which ? heads[l].dw1 : heads[l].dw2; j.db = which ? heads[l].db1 : heads[l].db2;
+        j.NA = nc; j.N = which ? G.Cp : nc; j.Nout = which ? G.C : nc; j.slabs = hb.slabs;
+        rl.start[rl.n++] = blocks;
+        blocks += (int)(((long long)nc * j.N + nc + kThreads - 1) / kThreads);
+      }
+    }
+    rl.start[rl.n] = blocks;
+    k_wreduce<<<(unsigned)blocks, kThreads, 0, st>>>(rl);
+    PNCE_CUDA(cudaGetLastError());
+  }
+  // 5. dense d feat (zero fill + sampled positions)
+  if (!dense) return PNCE_OK;
+  pg.grad_out = nullptr;
+  return launch_dense(pg, st);
 }
 
 int pnce_multi_axpby(float* const* dev_dst, const float* const* dev_src, const long long* dev_numel,

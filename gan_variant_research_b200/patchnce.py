@@ -298,7 +298,13 @@ def _warn_queue(dev) -> _WarnQueue:
 
 
 def poll_nonfinite_warnings(block: bool = False) -> int:
-    return sum(q.poll(block) for q in list(_WARN_QUEUES.values()))
+    total = sum(q.poll(block) for q in list(_WARN_QUEUES.values()))
+    if block and not torch.cuda.is_current_stream_capturing():
+        for t in list(_NETF_STATUS.values()):
+            if int(t.item()) != 0:
+                t.zero_()
+                raise _lib.PnceError("libpnce kernel protocol timeout (tcgen05 pipeline stalled, netF head)")
+    return total
 
 
 # ------------------------------------------------------------------------------------------------
@@ -845,6 +851,104 @@ class _SampleAllFn(torch.autograd.Function):
         return (None, None, *dfeats, *([None] * n))
 
 
+_NETF_STATUS = {}        # device index -> int32[1] the netF kernels raise on a protocol timeout (checked when polling)
+
+
+def _netf_status(dev) -> torch.Tensor:
+    t = _NETF_STATUS.get(dev.index)
+    if t is None:
+        t = _NETF_STATUS[dev.index] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return t
+
+
+class _NetFFn(torch.autograd.Function):
+    """``PatchSampleF(use_mlp=True).forward`` for every map at once, in libpnce: raw gather -> Linear(C_l, nc) -> ReLU ->
+    Linear(nc, nc) -> L2 normalise on tcgen05 (``pnce_netf_fwd``: k_prep, k_wprep, k_gather_tc, 2 x k_gemm_tc_p), and its
+    backward (``pnce_netf_bwd``: normalise backward + dY blob, dH, dX, k_wgrad_tc, k_wreduce, one dense launch).
+    Inputs: nc, n, math, the n maps, the n id tensors, 4 n head parameters (w1, b1, w2, b2 per map)."""
+
+    @staticmethod
+    def forward(ctx, nc, n, math, *args):
+        lib = _lib.load()
+        nhwc = all(_is_nhwc(a) for a in args[:n])
+        feats = [a.detach() if nhwc else a.detach().contiguous() for a in args[:n]]
+        ids = list(args[n:2 * n])
+        params = [a.detach().to(torch.float32).contiguous() for a in args[2 * n:]]
+        dev = feats[0].device
+        b = feats[0].shape[0]
+        maps = (_lib.PnceSample * n)()
+        heads = (_lib.PnceHead * n)()
+        rows, invs = [], []
+        with _on_device(dev):
+            for l, (f, i) in enumerate(zip(feats, ids)):
+                _, c, h, w = f.shape
+                p = i.numel()
+                r = torch.empty(b * p, nc, dtype=torch.float32, device=dev)
+                v = torch.empty(b * p, dtype=torch.float32, device=dev)
+                rows.append(r)
+                invs.append(v)
+                maps[l].feat, maps[l].ids, maps[l].rows, maps[l].inv = f.data_ptr(), i.data_ptr(), r.data_ptr(), v.data_ptr()
+                maps[l].C, maps[l].H, maps[l].W, maps[l].P = c, h, w, p
+                w1, b1, w2, b2 = params[4 * l:4 * l + 4]
+                heads[l].w1, heads[l].b1, heads[l].w2, heads[l].b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+            nbytes = ctypes.c_size_t(0)
+            _lib.check(lib.pnce_netf_workspace_bytes(maps, n, b, nc, ctypes.byref(nbytes)), "pnce_netf_workspace_bytes")
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            layout = _lib.LAYOUT_NHWC if nhwc else _lib.LAYOUT_NCHW
+            _lib.check(lib.pnce_netf_fwd(maps, heads, n, b, _DTYPES[feats[0].dtype], layout, nc, _MATH[math], ws.data_ptr(),
+                                         nbytes.value, _netf_status(dev).data_ptr(), _stream_ptr(dev)), "pnce_netf_fwd")
+        ctx.meta = (nc, n, math, b, dev, layout, nbytes.value, [(tuple(f.shape), f.dtype) for f in feats],
+                    [(a.shape, a.dtype) for a in args[2 * n:]])
+        ctx.feat_like = feats                    # layout / dtype of the dense gradients (no data is read in the backward)
+        ctx.save_for_backward(ws, *ids, *rows, *invs, *params)
+        return tuple(rows)
+
+    @staticmethod
+    def backward(ctx, *drows):
+        lib = _lib.load()
+        nc, n, math, b, dev, layout, ws_bytes, fmeta, pmeta = ctx.meta
+        saved = ctx.saved_tensors
+        ws, ids, rows, invs, params = saved[0], saved[1:1 + n], saved[1 + n:1 + 2 * n], saved[1 + 2 * n:1 + 3 * n], saved[1 + 3 * n:]
+        need_dense = any(ctx.needs_input_grad[3:3 + n])
+        maps = (_lib.PnceSample * n)()
+        heads = (_lib.PnceHead * n)()
+        with _on_device(dev):
+            keep, dfeats = [], []
+            sizes = [p.numel() for p in params]
+            flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            pgrads = [v.view_as(p) for v, p in zip(flat.split(sizes), params)]
+            for l in range(n):
+                (_, c, h, w), _dt = fmeta[l]
+                p = ids[l].numel()
+                g = drows[l]
+                g = (torch.zeros(b * p, nc, dtype=torch.float32, device=dev) if g is None
+                     else g.detach().to(torch.float32).contiguous())
+                keep.append(g)
+                d = torch.empty_like(ctx.feat_like[l]) if need_dense else None
+                dfeats.append(d)
+                maps[l].ids, maps[l].rows, maps[l].inv, maps[l].drows = (ids[l].data_ptr(), rows[l].data_ptr(),
+                                                                         invs[l].data_ptr(), g.data_ptr())
+                maps[l].dfeat = d.data_ptr() if d is not None else None
+                maps[l].C, maps[l].H, maps[l].W, maps[l].P = c, h, w, p
+                w1, b1, w2, b2 = params[4 * l:4 * l + 4]
+                d1, e1, d2, e2 = pgrads[4 * l:4 * l + 4]
+                heads[l].w1, heads[l].b1, heads[l].w2, heads[l].b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+                heads[l].dw1, heads[l].db1, heads[l].dw2, heads[l].db2 = d1.data_ptr(), e1.data_ptr(), d2.data_ptr(), e2.data_ptr()
+            _lib.check(lib.pnce_netf_bwd(maps, heads, n, b, _DTYPES[fmeta[0][1]], layout, nc, _MATH[math], ws.data_ptr(),
+                                         ws_bytes, _netf_status(dev).data_ptr(), _stream_ptr(dev)), "pnce_netf_bwd")
+        pgrads = [pg.to(dt).reshape(shape) for pg, (shape, dt) in zip(pgrads, pmeta)]
+        return (None, None, None, *dfeats, *([None] * n), *pgrads)
+
+
+def netf_fused_supported(use_mlp, nc, feats, ids, math) -> bool:
+    """The tcgen05 head kernels cover nc in {128, 256}, P <= 1024, C <= 256, maps of one batch size / dtype / device."""
+    if not use_mlp or nc not in (128, 256) or math == "simt_f32" or not 0 < len(feats) <= _lib.MAX_LAYERS:
+        return False
+    f0 = feats[0]
+    return all(f.dim() == 4 and f.shape[1] <= 256 and i.numel() <= 1024 and f.shape[0] == f0.shape[0] and f.dtype == f0.dtype
+               and f.device == f0.device and f.dtype in _DTYPES for f, i in zip(feats, ids))
+
+
 _ROWS_WS_BYTES = {}      # (batch, P, D) -> pnce_rows_loss_workspace_bytes, queried once per shape
 
 
@@ -910,12 +1014,13 @@ class PatchSampleF(nn.Module):
     ``use_mlp=True`` adds the netF head Linear(C_l, nc) -> ReLU -> Linear(nc, nc) before the
     normalisation (created lazily per layer on first use, like upstream CUT's ``create_mlp``)."""
 
-    def __init__(self, use_mlp: bool = False, nc: int = 256, init_gain: float = 0.02):
+    def __init__(self, use_mlp: bool = False, nc: int = 256, init_gain: float = 0.02, math: Optional[str] = None):
         super().__init__()
         self.use_mlp = use_mlp
         self.nc = nc
         self.init_gain = init_gain
         self.mlp_init = False
+        self.math = math                         # contraction engine of the fused head (None: DEFAULT_MATH)
 
     def create_mlp(self, feats):
         for mlp_id, feat in enumerate(feats):
@@ -941,6 +1046,16 @@ class PatchSampleF(nn.Module):
             return_ids = [patch_ids[k].to(device=f.device, dtype=torch.int64).contiguous() for k, f in enumerate(feats)]
         else:
             return_ids = draw_ids(feats, num_patches)
+        math = self.math or DEFAULT_MATH
+        if netf_fused_supported(self.use_mlp, self.nc, feats, return_ids, math):
+            # the whole head in libpnce, on the tensor cores: gather -> Linear -> ReLU -> Linear -> normalise (and, through
+            # autograd, d feat and the weight gradients); other shapes take the composition below (gather in libpnce,
+            # the two Linear layers in ATen)
+            params = []
+            for l in range(len(feats)):
+                mlp = getattr(self, f"mlp_{l}")
+                params += [mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias]
+            return list(_NetFFn.apply(self.nc, len(feats), math, *feats, *return_ids, *params)), return_ids
         same = all(f.shape[0] == feats[0].shape[0] and f.dtype == feats[0].dtype and f.device == feats[0].device
                    for f in feats)
         if same and 0 < len(feats) <= _lib.MAX_LAYERS and feats[0].dtype in _DTYPES:
@@ -1049,10 +1164,10 @@ class _FusedHeadPatchNCE(torch.autograd.Function):
 
 
 def fused_head_supported(netF: "PatchSampleF", feats, num_patches) -> bool:
-    """The tcgen05 head kernels cover nc in {128, 256}, P <= 256 and C <= 256 (every 256^2 CUT layer)."""
+    """The tcgen05 head kernels cover nc in {128, 256}, P <= 1024 and C <= 256 (every CUT layer up to 512^2, P = 1024)."""
     if not netF.use_mlp or netF.nc not in (128, 256):
         return False
-    return all(f.shape[1] <= 256 and patch_count(num_patches, f.shape[2] * f.shape[3]) <= 256 for f in feats)
+    return all(f.shape[1] <= 256 and patch_count(num_patches, f.shape[2] * f.shape[3]) <= 1024 for f in feats)
 
 
 def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0.07, num_patches=256,
@@ -1086,7 +1201,7 @@ def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0
             total = l if total is None else total + l
         return total / len(feat_q), ids
     if not fused_head_supported(netF, tgt_feats, num_patches):
-        raise RuntimeError("fused head: nc must be 128 or 256, num_patches <= 256 and C <= 256")
+        raise RuntimeError("fused head: nc must be 128 or 256, num_patches <= 1024 and C <= 256")
     if not netF.mlp_init:
         netF.create_mlp(tgt_feats)
     src, tgt, _, uniform = _prepare_maps(src_feats, tgt_feats)

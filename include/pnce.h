@@ -189,7 +189,7 @@ int pnce_sample_multi_bwd(const pnce_sample_t* maps, int n_maps, int batch, int 
  * PatchSampleF(use_mlp=True): raw gather -> Linear(C_l, nc) -> ReLU -> Linear(nc, nc) -> L2 normalise for the
  * src (k, no gradient) and tgt (q) patches of every layer, then the same logits / diagonal CE as
  * pnce_fwd on the head's output; all contractions on tcgen05 (math_mode TC_BF16X3 or TC_BF16).
- * Supported: nc = 128 or 256, P <= 256, C <= 256.  Weights are fp32, nn.Linear layout (out, in).      */
+ * Supported: nc = 128 or 256, P <= 1024, C <= 256.  Weights are fp32, nn.Linear layout (out, in).     */
 typedef struct pnce_head {
   const float* w1;  /* (nc, C)  */
   const float* b1;  /* (nc)     */
@@ -219,6 +219,22 @@ int pnce_head_bwd_params(const pnce_layer_t* layers, const pnce_head_t* heads, i
 int pnce_head_bwd_dense(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
                         int nc, int math_mode, void* dev_workspace, size_t workspace_bytes,
                         const float* dev_grad_out, void* stream);
+
+/* ---- PatchSampleF(use_mlp=True).forward(feats, num_patches, patch_ids) as a module of its own (north_star's netF
+ * signature; absent from the reference): for every map, raw gather -> Linear(C_l, nc) ->
+ * ReLU -> Linear(nc, nc) -> x / max(||x||, 1e-6), all contractions on tcgen05, and its backward.
+ *   forward : reads maps[l].feat / ids, writes maps[l].rows (B*P, nc) fp32 -- normalised, row b*P + p <-> ids[p], the
+ *             order upstream CUT's PatchSampleF returns -- and maps[l].inv (B*P), the norm bookkeeping of pnce_sample_fwd;
+ *   backward: reads maps[l].drows (gradient w.r.t. rows), rows and inv of the forward and the SAME workspace (it holds
+ *             the gathered patches, the hidden activations and the sorted ids); writes every heads[l].d* and, unless
+ *             every maps[l].dfeat is NULL (maps without gradient), the dense maps[l].dfeat.
+ * nc = 128 or 256, P <= 1024, C <= 256; math_mode TC_BF16X3 or TC_BF16; layout as in pnce_fwd_ex.
+ * dev_status: int[1], set to 1 on a kernel-protocol timeout (may be NULL).                                        */
+int pnce_netf_workspace_bytes(const pnce_sample_t* maps, int n_maps, int batch, int nc, size_t* bytes);
+int pnce_netf_fwd(const pnce_sample_t* maps, const pnce_head_t* heads, int n_maps, int batch, int dtype, int layout,
+                  int nc, int math_mode, void* dev_workspace, size_t workspace_bytes, int* dev_status, void* stream);
+int pnce_netf_bwd(const pnce_sample_t* maps, const pnce_head_t* heads, int n_maps, int batch, int dtype, int layout,
+                  int nc, int math_mode, void* dev_workspace, size_t workspace_bytes, int* dev_status, void* stream);
 
 /* ---- "next" row 3: optimiser-side multi-tensor ops ------------------------------------
  * One launch over a list of fp32 tensors described by device-resident tables (built once by the caller: parameter
