@@ -688,6 +688,24 @@ def nhwc_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers, e
             out["strong"] = {"global_batch": 64, "batch_per_gpu": b, "ms_per_step": sms,
                              "value": 64 * patches_per_image / (sms * 1e-3), "direct_ms_per_step": dms,
                              "direct_value": 64 * patches_per_image / (dms * 1e-3)}
+        # the netF head on the same channels-last maps (collective inside the timed region when N > 1)
+        torch.manual_seed(11)
+        netF = pn.PatchSampleF(use_mlp=True, nc=256).to(dev)
+        netF.create_mlp(s_tgt)
+        torch.manual_seed(7)
+
+        def hstep():
+            for t in s_tgt:
+                t.grad = None
+            netF.zero_grad(set_to_none=True)
+            loss, _ = pn.patchnce_with_head(netF, s_src, s_tgt, args.tau, args.patches, math=math,
+                                            dp_group=True if world > 1 else None)
+            loss.backward()
+
+        hms = timed_steps(hstep, steps, 3, world, dev)
+        out["head_mode"] = {"ms_per_step": hms, "value": world * args.batch * patches_per_image / (hms * 1e-3), "unit": UNIT,
+                            "roofline_path_frac": path_bytes / (hms * 1e-3) / 1e9 / peak,
+                            "kernels_us": kernel_breakdown(hstep) if world == 1 else None}
         del s_src, s_tgt
         return out
     except Exception as e:  # noqa: BLE001 - secondary

@@ -1288,12 +1288,13 @@ int pnce_head_workspace_bytes(const pnce_layer_t* layers, int n_layers, int batc
   return PNCE_OK;
 }
 
-int pnce_head_fwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
-                  int nc, float temperature, int math_mode, void* ws, size_t ws_bytes, float* loss_out,
-                  int* nonfinite, void* stream) {
+static int head_fwd_impl(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
+                         int layout, int nc, float temperature, int math_mode, void* ws, size_t ws_bytes, float* loss_out,
+                         int* nonfinite, void* stream) {
   int rc = check_head_args(layers, heads, n_layers, batch, dtype, nc, math_mode, ws, false);
   if (rc != PNCE_OK) return rc;
   if (loss_out == nullptr || !(temperature > 0.f)) return PNCE_ERR_ARG;
+  if (layout != PNCE_LAYOUT_NCHW && layout != PNCE_LAYOUT_NHWC) return PNCE_ERR_ARG;
   const bool x3 = math_mode == PNCE_MATH_TC_BF16X3;
   static thread_local HeadPlan hp;
   if (carve_head(layers, n_layers, batch, nc, x3, ws, &hp) > ws_bytes) return PNCE_ERR_WORKSPACE;
@@ -1306,6 +1307,7 @@ int pnce_head_fwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_la
   pl.loss_out = loss_out;
   pg.nonfinite = pl.nonfinite = nonfinite;
   pg.b0 = pl.b0 = 0; pg.bn = pl.bn = batch;
+  pg.nhwc = layout == PNCE_LAYOUT_NHWC ? 1 : 0;               // the maps; the head's output (pl) has no layout
   pl.trace = g_dbg.trace;
   // 1. ids -> sorted slots; weights -> operand blobs
   rc = launch_prep(pg, st);
@@ -1386,9 +1388,11 @@ int pnce_head_fwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_la
 // phases: bit 0 = head backward proper (dH, dX, weight / bias gradients), bit 1 = dense d tgt_feat
 static int head_bwd_phases(int phases, const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch,
                            int dtype, int nc, int math_mode, void* ws, size_t ws_bytes, const float* grad_out,
-                           void* stream) {
+                           void* stream, int layout = PNCE_LAYOUT_NCHW) {
   int rc = check_head_args(layers, heads, n_layers, batch, dtype, nc, math_mode, ws, (phases & 2) != 0);
   if (rc != PNCE_OK) return rc;
+  if (layout != PNCE_LAYOUT_NCHW && layout != PNCE_LAYOUT_NHWC) return PNCE_ERR_ARG;
+  if (phases < 1 || phases > 3) return PNCE_ERR_ARG;
   if (phases & 1)
     for (int l = 0; l < n_layers; ++l)
       if (!heads[l].dw1 || !heads[l].db1 || !heads[l].dw2 || !heads[l].db2) return PNCE_ERR_ARG;
@@ -1399,6 +1403,7 @@ static int head_bwd_phases(int phases, const pnce_layer_t* layers, const pnce_he
   Params& pg = hp.pg;
   pg.dtype = dtype;
   pg.grad_out = grad_out;
+  pg.nhwc = layout == PNCE_LAYOUT_NHWC ? 1 : 0;
   if (!(phases & 1)) return launch_dense(pg, st);
   static thread_local GemmLaunch g;
   // 1. dH = (dY W2) * [H > 0]
@@ -1426,7 +1431,7 @@ static int head_bwd_phases(int phases, const pnce_layer_t* layers, const pnce_he
     pr.a_hi = hb.dh[0]; pr.a_lo = hb.dh[1]; pr.b_hi = hb.w1t[0]; pr.b_lo = hb.w1t[1];
     pr.K = nc; pr.N = G.Cp; pr.tiles = batch * (G.Ppad / 128); pr.mode = GM_DX;
     pr.P = G.P; pr.Ppad = G.Ppad; pr.halves = G.Ppad / 128; pr.C = G.C;
-    pr.outT = G.dxT;
+    pr.outT = G.dxT; pr.rm = pg.nhwc;
   }
   rc = launch_gemm(g, st);
   if (rc != PNCE_OK) return rc;
@@ -1481,6 +1486,22 @@ static int head_bwd_phases(int phases, const pnce_layer_t* layers, const pnce_he
   return launch_dense(pg, st);
 }
 
+int pnce_head_fwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
+                  int nc, float temperature, int math_mode, void* ws, size_t ws_bytes, float* loss_out,
+                  int* nonfinite, void* stream) {
+  return head_fwd_impl(layers, heads, n_layers, batch, dtype, PNCE_LAYOUT_NCHW, nc, temperature, math_mode, ws, ws_bytes,
+                       loss_out, nonfinite, stream);
+}
+int pnce_head_fwd_ex(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype, int layout,
+                     int nc, float temperature, int math_mode, void* ws, size_t ws_bytes, float* loss_out,
+                     int* nonfinite, void* stream) {
+  return head_fwd_impl(layers, heads, n_layers, batch, dtype, layout, nc, temperature, math_mode, ws, ws_bytes, loss_out,
+                       nonfinite, stream);
+}
+int pnce_head_bwd_ex(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype, int layout,
+                     int phases, int nc, int math_mode, void* ws, size_t ws_bytes, const float* grad_out, void* stream) {
+  return head_bwd_phases(phases, layers, heads, n_layers, batch, dtype, nc, math_mode, ws, ws_bytes, grad_out, stream, layout);
+}
 int pnce_head_bwd(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype,
                   int nc, int math_mode, void* ws, size_t ws_bytes, const float* grad_out, void* stream) {
   return head_bwd_phases(3, layers, heads, n_layers, batch, dtype, nc, math_mode, ws, ws_bytes, grad_out, stream);

@@ -1110,11 +1110,12 @@ class _FusedHeadPatchNCE(torch.autograd.Function):
             out = torch.empty(1 + n, dtype=torch.float32, device=dev)
             wq = _warn_queue(dev)
             slot, flag_ptr = wq.acquire()
-            _lib.check(lib.pnce_head_fwd(layers, heads, n, batch, dtype, nc, plan.temperature, _MATH[plan.math],
-                                         ws.data_ptr(), nbytes.value, out.data_ptr(), flag_ptr or None,
-                                         _stream_ptr(dev)), "pnce_head_fwd")
+            layout = _lib.LAYOUT_NHWC if _is_nhwc(tgt[0]) else _lib.LAYOUT_NCHW      # _prepare_maps made the layers uniform
+            _lib.check(lib.pnce_head_fwd_ex(layers, heads, n, batch, dtype, layout, nc, plan.temperature, _MATH[plan.math],
+                                            ws.data_ptr(), nbytes.value, out.data_ptr(), flag_ptr or None,
+                                            _stream_ptr(dev)), "pnce_head_fwd")
         ctx.save_for_backward(ws)            # freed with the graph, right after backward() (see _FusedPatchNCE)
-        ctx.plan, ctx.ws_bytes, ctx.nc = plan, nbytes.value, nc
+        ctx.plan, ctx.ws_bytes, ctx.nc, ctx.layout = plan, nbytes.value, nc, layout
         ctx.tgt_keep, ctx.params = tgt, params
         ctx.param_meta = [(a.shape, a.dtype) for a in args[n:]]
         ctx.dev, ctx.batch, ctx.dtype = dev, batch, dtype
@@ -1143,21 +1144,21 @@ class _FusedHeadPatchNCE(torch.autograd.Function):
                 heads[l].dw1, heads[l].db1, heads[l].dw2, heads[l].db2 = (d1.data_ptr(), e1.data_ptr(),
                                                                           d2.data_ptr(), e2.data_ptr())
             (ws,) = ctx.saved_tensors
-            args = (layers, heads, n, ctx.batch, ctx.dtype, ctx.nc, _MATH[ctx.plan.math], ws.data_ptr(),
-                    ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev))
+            tail = (ctx.nc, _MATH[ctx.plan.math], ws.data_ptr(), ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev))
+            head = (layers, heads, n, ctx.batch, ctx.dtype, ctx.layout)
             if group is None:
-                _lib.check(lib.pnce_head_bwd(*args), "pnce_head_bwd")
+                _lib.check(lib.pnce_head_bwd_ex(*head, 3, *tail), "pnce_head_bwd")
             else:
                 # data parallel: head gradients first, their all-reduce on a side stream UNDER the dense kernel
                 from . import dp
-                _lib.check(lib.pnce_head_bwd_params(*args), "pnce_head_bwd_params")
+                _lib.check(lib.pnce_head_bwd_ex(*head, 1, *tail), "pnce_head_bwd_params")
                 main = torch.cuda.current_stream(dev)
                 side = dp.comm_stream(dev)
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     dp.allreduce_flat_(flat, group, average=True)
                 flat.record_stream(side)
-                _lib.check(lib.pnce_head_bwd_dense(*args), "pnce_head_bwd_dense")
+                _lib.check(lib.pnce_head_bwd_ex(*head, 2, *tail), "pnce_head_bwd_dense")
                 main.wait_stream(side)
         pgrads = [pg.to(dt).reshape(shape) for pg, (shape, dt) in zip(pgrads, ctx.param_meta)]
         return (None, None, *grads, *pgrads)
@@ -1204,9 +1205,9 @@ def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0
         raise RuntimeError("fused head: nc must be 128 or 256, num_patches <= 1024 and C <= 256")
     if not netF.mlp_init:
         netF.create_mlp(tgt_feats)
-    src, tgt, _, uniform = _prepare_maps(src_feats, tgt_feats)
+    src, tgt, _, uniform = _prepare_maps(src_feats, tgt_feats, math or DEFAULT_MATH, int(num_patches))
     if not uniform:
-        raise RuntimeError("fused head: every layer must share batch size, dtype and device (use fused=False)")
+        raise RuntimeError("fused head: every layer must share batch size, dtype, device and layout (use fused=False)")
     if patch_ids is None:
         ids = draw_ids(tgt, num_patches)
     else:

@@ -220,6 +220,15 @@ int pnce_head_bwd_dense(const pnce_layer_t* layers, const pnce_head_t* heads, in
                         int nc, int math_mode, void* dev_workspace, size_t workspace_bytes,
                         const float* dev_grad_out, void* stream);
 
+/* The fused head on channels-last maps (layout as in pnce_fwd_ex); phases: 1 = pnce_head_bwd_params, 2 = pnce_head_bwd_dense,
+ * 3 = pnce_head_bwd.                                                                                              */
+int pnce_head_fwd_ex(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype, int layout,
+                     int nc, float temperature, int math_mode, void* dev_workspace, size_t workspace_bytes,
+                     float* dev_loss_out, int* dev_nonfinite, void* stream);
+int pnce_head_bwd_ex(const pnce_layer_t* layers, const pnce_head_t* heads, int n_layers, int batch, int dtype, int layout,
+                     int phases, int nc, int math_mode, void* dev_workspace, size_t workspace_bytes,
+                     const float* dev_grad_out, void* stream);
+
 /* ---- PatchSampleF(use_mlp=True).forward(feats, num_patches, patch_ids) as a module of its own (north_star's netF
  * signature; absent from the reference): for every map, raw gather -> Linear(C_l, nc) ->
  * ReLU -> Linear(nc, nc) -> x / max(||x||, 1e-6), all contractions on tcgen05, and its backward.

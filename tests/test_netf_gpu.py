@@ -177,3 +177,31 @@ def test_head_with_1024_patches(pn, orc, fused):
             if name in ("W1", "b1"):
                 a, c = a[keep], c[keep]
             assert_grad_close(a, c, 1e-3, f"d{name} layer {l}")
+
+
+@pytest.mark.parametrize("p", [64, 300])
+def test_fused_head_on_channels_last_maps_equals_nchw(pn, p):
+    """patchnce_with_head (fused) on torch.channels_last maps: same loss, dense gradient (channels-last, exact zeros off
+    the samples) and head gradients as on the NCHW storage of the same values (same kernels after the gather, so the
+    agreement is to rounding of the norms, not 1e-3)."""
+    shapes = [(64, 32, 32), (128, 16, 16), (24, 20, 12)]
+    src, tgt, ids = _head_problem(11, 3, shapes, p)
+    netF = _make_head(pn, 256, [x.cuda() for x in tgt])
+    idd = [i.cuda() for i in ids]
+    out = []
+    for cl in (False, True):
+        netF.zero_grad()
+        mk = (lambda x: x.cuda().contiguous(memory_format=CL)) if cl else (lambda x: x.cuda())
+        t = [mk(x).requires_grad_() for x in tgt]
+        loss, _ = pn.patchnce_with_head(netF, [mk(x) for x in src], t, 0.07, p, idd, fused=True)
+        loss.backward()
+        out.append((loss.detach(), [x.grad for x in t], [q.grad.clone() for q in netF.parameters()]))
+    assert pn.poll_nonfinite_warnings(block=True) == 0
+    (l0, g0, w0), (l1, g1, w1) = out
+    assert l1.item() == pytest.approx(l0.item(), rel=1e-6)
+    for a, c, i in zip(g0, g1, ids):
+        if a.shape[1] > 1:
+            assert c.is_contiguous(memory_format=CL)
+        assert_grad_close(c.cpu().numpy(), a.cpu().numpy(), 1e-5, "d tgt", ids=i)
+    for a, c in zip(w0, w1):
+        assert_grad_close(c.cpu().numpy(), a.cpu().numpy(), 1e-5, "head gradient")
