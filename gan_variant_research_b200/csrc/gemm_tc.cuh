@@ -255,6 +255,9 @@ struct WgradLaunch {
   int n, x3;
   int* err;
 };
+// (Measured and rejected: two stages of HALF a row tile each -- 64 rows of K, 16 + N/8 bulk copies of 1 KB per part because
+// the 64 rows of an 8-column slab are 1 KB inside the slab's 2 KB -- so that loads fly under the other half's MMAs:
+// 117 us vs 95 us at B=64; the bulk-copy engine is built for few large copies)
 constexpr int kWgOffAlo = 32768, kWgOffBhi = 65536, kWgOffBlo = 131072, kWgOffOnes = 196608;
 constexpr int kWgSmemBytes = 196608 + 4096 + 256;
 

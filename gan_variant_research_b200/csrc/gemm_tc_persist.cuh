@@ -15,7 +15,7 @@ namespace pnce {
 
 constexpr int kGpThreads = 320;
 constexpr int kGpSlots = 8;
-constexpr int kGpSmemBytes = kGpSlots * kGemmStageBytes + 512 + 2048;   // + GM_YROWS row-norm exchange [2][2][128] floats
+constexpr int kGpSmemBytes = kGpSlots * kGemmStageBytes + 512 + 2048 + 2048;   // + GM_YROWS row-norm exchange [2][2][128] floats + bias [2][256]
 
 struct GpShared {
   uint64_t full[kGpSlots], empty[kGpSlots], accfull[2], accfree[2];
@@ -134,6 +134,13 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
       const int Ppad = pr.Ppad, mode = pr.mode;
       const uint32_t trow = tmem + (uint32_t)(n & 1) * 256u + ((uint32_t)(q * 32) << 16);
       const size_t rowblob = ((size_t)tile * N8 * 16 + (size_t)(i >> 3)) * 64 + (size_t)(i & 7) * 8;   // + n8 * 1024
+      // this tile's bias (or zeros) in shared memory: one load per epilogue thread instead of one per element and thread
+      float* bias_s = reinterpret_cast<float*>(smem + kGpSlots * kGemmStageBytes + 512 + 2048) + (n & 1) * 256;
+      {
+        const int et = tid - 64;
+        bias_s[et] = (pr.bias != nullptr && et < N) ? __ldg(pr.bias + et) : 0.f;
+        asm volatile("bar.sync 5, 256;" ::: "memory");
+      }
       mbar_wait(&sh->accfull[n & 1], ((uint32_t)n >> 1) & 1u, dead);
       tc_fence_after();
       const int nch = N >> 5;
@@ -149,12 +156,17 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
           tmem_ld_wait();
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            const float x = __uint_as_float(r[k]) + __ldg(pr.bias + ch * 32 + k);
+            const float x = __uint_as_float(r[k]) + bias_s[ch * 32 + k];
             ssum = fmaf(x, x, ssum);
           }
         }
         xss[half * 128 + i] = ssum;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");       // the two warps of this quadrant
+        switch (q) {                                              // the two warps of this quadrant (immediate barrier ids)
+          case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+          case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+          case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+          default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+        }
         const float nrm = sqrtf(xss[i] + xss[128 + i]);
         const float den = (nrm == nrm) ? fmaxf(nrm, kNormEps) : nrm;      // clamp_min keeps NaN (F.normalize, patchnce_cut.py:77)
         const float scale = 1.0f / den;
@@ -170,10 +182,10 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
 #pragma unroll
             for (int k4 = 0; k4 < 8; ++k4) {
               float4 v4;
-              v4.x = (__uint_as_float(r[k4 * 4 + 0]) + __ldg(pr.bias + ch * 32 + k4 * 4 + 0)) * scale;
-              v4.y = (__uint_as_float(r[k4 * 4 + 1]) + __ldg(pr.bias + ch * 32 + k4 * 4 + 1)) * scale;
-              v4.z = (__uint_as_float(r[k4 * 4 + 2]) + __ldg(pr.bias + ch * 32 + k4 * 4 + 2)) * scale;
-              v4.w = (__uint_as_float(r[k4 * 4 + 3]) + __ldg(pr.bias + ch * 32 + k4 * 4 + 3)) * scale;
+              v4.x = (__uint_as_float(r[k4 * 4 + 0]) + bias_s[ch * 32 + k4 * 4 + 0]) * scale;
+              v4.y = (__uint_as_float(r[k4 * 4 + 1]) + bias_s[ch * 32 + k4 * 4 + 1]) * scale;
+              v4.z = (__uint_as_float(r[k4 * 4 + 2]) + bias_s[ch * 32 + k4 * 4 + 2]) * scale;
+              v4.w = (__uint_as_float(r[k4 * 4 + 3]) + bias_s[ch * 32 + k4 * 4 + 3]) * scale;
               *reinterpret_cast<float4*>(o + k4 * 4) = v4;
             }
           }
@@ -182,24 +194,32 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
         mbar_arrive(&sh->accfree[n & 1]);
         continue;
       }
-      for (int ch = half; ch < nch; ch += 2) {
-        uint32_t r[32];
-        tmem_ld32(trow + ch * 32, r);
-        // the ReLU mask of this chunk (GM_DH) is fetched while the TMEM load is in flight
-        uint4 hm[4];
-        if (mode == GM_DH) {
+      // ---- every other mode: this warp's chunks ch = half, half + 2, ..., software-pipelined -- the TMEM load (and the
+      //      ReLU mask, GM_DH) of the next chunk are in flight while the current one is processed.  One warp per
+      //      scheduler pair leaves every load latency exposed otherwise (ncu: tensor pipe 26-41 % active, the launch was
+      //      epilogue-bound: ~21 k cycles per 128 x 256 tile against 6 k of MMAs) ----
+      uint32_t ra[32], rb[32];
+      uint4 hm[4];                                             // GM_DH: ReLU mask of the NEXT chunk to process (single buffer,
+                                                               // reloaded as soon as it has been applied)
+      auto load_mask = [&](int ch) {
+        if (mode == GM_DH && ch < nch) {
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8)
             hm[g8] = __ldcg(reinterpret_cast<const uint4*>(pr.mask_hi + rowblob + (size_t)(ch * 4 + g8) * 1024));
         }
-        tmem_ld_wait();
+      };
+      auto chunk = [&](int ch, const uint32_t (&r)[32]) {
         float v[32];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          float x = __uint_as_float(r[k]);
-          if (pr.bias != nullptr) x += __ldg(pr.bias + ch * 32 + k);
-          if (mode == GM_H) x = fmaxf(x, 0.f);
-          v[k] = rowok ? x : 0.f;                             // padding rows stay exactly zero
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + k4 * 4);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int t4 = 0; t4 < 4; ++t4) {
+            float x = __uint_as_float(r[k4 * 4 + t4]) + bb[t4];
+            if (mode == GM_H) x = fmaxf(x, 0.f);
+            v[k4 * 4 + t4] = rowok ? x : 0.f;                   // padding rows stay exactly zero
+          }
         }
         if (mode == GM_DX) {
           // same L2 evict_last policy as the loss kernel's dxT stores (loss_tc.cuh, st_dx): k_wgrad_tc runs between this
@@ -209,7 +229,10 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
           if (keep_dx) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_dx));
           if (rowok && pr.rm) {                               // channels-last maps: row-major rows, one 128-byte line per thread
             float* o = pr.outT + ((size_t)b * Ppad + p) * pr.C + ch * 32;
-            if (ch * 32 + 32 <= pr.C && (pr.C & 3) == 0) {
+            if (ch * 32 + 32 <= pr.C && (pr.C & 7) == 0) {
+#pragma unroll
+              for (int k8 = 0; k8 < 4; ++k8) st_dx8(o + k8 * 8, v + k8 * 8, keep_dx, pol_dx);
+            } else if (ch * 32 + 32 <= pr.C && (pr.C & 3) == 0) {
 #pragma unroll
               for (int k4 = 0; k4 < 8; ++k4) st_dx4(o + k4 * 4, v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3], keep_dx, pol_dx);
             } else {
@@ -224,7 +247,7 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
               if (c < pr.C) st_dx(pr.outT + ((size_t)b * pr.C + c) * Ppad + p, v[k], keep_dx, pol_dx);
             }
           }
-          continue;
+          return;
         }
         if (mode == GM_DH) {
 #pragma unroll
@@ -236,6 +259,7 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
               if ((wv[k2] & 0x7fff0000u) == 0u) v[g8 * 8 + 2 * k2 + 1] = 0.f;
             }
           }
+          load_mask(ch + 2);                                    // flies under the split + stores below and the next TMEM wait
         }
         if (mode == GM_YQ || mode == GM_YK) {
           float ssum = 0.f;
@@ -271,6 +295,19 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
             *reinterpret_cast<uint4*>(pr.o_hi + o) = hi;
             if (x3) *reinterpret_cast<uint4*>(pr.o_lo + o) = lo;
           }
+        }
+      };
+      if (half < nch) tmem_ld32(trow + half * 32, ra);
+      load_mask(half);
+#pragma unroll 1
+      for (int ch = half; ch < nch; ch += 4) {
+        tmem_ld_wait();
+        if (ch + 2 < nch) tmem_ld32(trow + (ch + 2) * 32, rb);
+        chunk(ch, ra);
+        if (ch + 2 < nch) {
+          tmem_ld_wait();
+          if (ch + 4 < nch) tmem_ld32(trow + (ch + 4) * 32, ra);
+          chunk(ch + 2, rb);
         }
       }
       tc_fence_before();

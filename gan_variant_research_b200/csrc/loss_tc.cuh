@@ -268,6 +268,17 @@ __device__ __forceinline__ void st_dx4(float* p, float a, float b, float c, floa
                  : "memory");
   else *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
+// one whole 32-byte sector per lane (sm_100: STG.256); 128-bit row stores from 32 different rows are 32 HALF sectors
+__device__ __forceinline__ void st_dx8(float* p, const float* v, bool keep, uint64_t pol) {
+  if (keep)
+    asm volatile("st.global.L2::cache_hint.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(p), "f"(v[0]), "f"(v[1]),
+                 "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(pol)
+                 : "memory");
+  else
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
 
 // dQ epilogue for one 32-channel chunk; NPC = pitch of dxT rows (compile-time: immediates; 0 = run time).
 // Head mode (dyh != NULL): the gradient w.r.t. the head output leaves as a bf16 hi(+lo) row blob
@@ -303,7 +314,10 @@ __device__ __forceinline__ void tc_dq_chunk(const uint32_t (&r)[32], const TcQCh
     uint64_t pol = 0;
     if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     if (rm) {
-      if (nvalid >= 32 && (np_rt & 3) == 0) {
+      if (nvalid >= 32 && (np_rt & 7) == 0) {
+#pragma unroll
+        for (int k8 = 0; k8 < 4; ++k8) st_dx8(dp + k8 * 8, out + k8 * 8, keep, pol);
+      } else if (nvalid >= 32 && (np_rt & 3) == 0) {
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) st_dx4(dp + k4 * 4, out[k4 * 4], out[k4 * 4 + 1], out[k4 * 4 + 2], out[k4 * 4 + 3], keep, pol);
       } else {

@@ -19,9 +19,16 @@ namespace pnce {
 
 template <typename T> struct Vec8;
 template <> struct Vec8<float> {
+  // one 256-bit load (sm_100: LDG.256) = this lane's whole 32-byte sector; two 128-bit loads ask L1 for it twice
   static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
-    const float4 a = __ldcg(reinterpret_cast<const float4*>(p)), b = __ldcg(reinterpret_cast<const float4*>(p) + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    if ((reinterpret_cast<uintptr_t>(p) & 31u) == 0) {
+      asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                   : "l"(p));
+    } else {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(p)), b = __ldcg(reinterpret_cast<const float4*>(p) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
   }
 };
 template <> struct Vec8<__half> {
@@ -46,31 +53,41 @@ template <> struct Vec8<__nv_bfloat16> {
   }
 };
 
-// One warp item of the NHWC gather; writes exactly what gather_tc_chunk writes for the same (side, image, slots, chunk).
+// One warp item of the NHWC gather = (side, image, 8 sorted slots, 32-channel chunk); it writes exactly what
+// gather_tc_chunk writes for the same coordinates.  Split in two so that a warp can have the loads of several items
+// in flight before it touches the first value (the kernel is latency-bound: one dependent sid -> row chain per item).
+struct NhwcItem {
+  int s, b, side, p, c8;
+  bool valid;
+};
 template <typename T>
-__device__ __forceinline__ void gather_nhwc_item(const LayerDev& L, int b0, int B, long long witem, int lane, int side0) {
+__device__ __forceinline__ void gather_nhwc_load(const LayerDev& L, int b0, int B, long long witem, int lane, int side0,
+                                                 NhwcItem& it, float (&v)[8]) {
   const int nchunk = L.nchunk, np8 = L.Ppad >> 3;
-  const int s = (int)(witem % nchunk);
+  it.s = (int)(witem % nchunk);
   const int p8 = (int)((witem / nchunk) % np8);
   const long long rest = witem / nchunk / np8;
-  const int b = b0 + (int)(rest % B);
-  const int side = (int)(rest / B) + side0;                  // 0 = src (k), 1 = tgt (q); side0 = 1: tgt only
-  const int C = L.C, HW = L.HW, P = L.P, Ppad = L.Ppad, Cp8 = L.Cp >> 3;
-  const int p = p8 * 8 + (lane & 7);                         // sorted slot
-  const int g = lane >> 3;                                   // 8-channel group of the chunk
-  const int c8 = s * 4 + g, c0 = c8 * 8;
-  const bool valid = p < P;
-  const int id = valid ? __ldg(L.sid + p) : 0;
-  const T* base = reinterpret_cast<const T*>(side ? L.tgt : L.src);
-  const T* row = base + ((size_t)b * HW + id) * C + c0;
+  it.b = b0 + (int)(rest % B);
+  it.side = (int)(rest / B) + side0;                         // 0 = src (k), 1 = tgt (q); side0 = 1: tgt only
+  const int C = L.C, HW = L.HW;
+  it.p = p8 * 8 + (lane & 7);                                // sorted slot
+  it.c8 = it.s * 4 + (lane >> 3);                            // 8-channel group
+  const int c0 = it.c8 * 8;
+  it.valid = it.p < L.P;
+  const int id = it.valid ? __ldg(L.sid + it.p) : 0;
+  const T* base = reinterpret_cast<const T*>(it.side ? L.tgt : L.src);
+  const T* row = base + ((size_t)it.b * HW + id) * C + c0;
   const bool vec = (((size_t)C * sizeof(T)) & 15u) == 0 && (reinterpret_cast<uintptr_t>(base) & 15u) == 0;
-  float v[8];
-  if (valid && vec && c0 + 8 <= C) {
+  if (it.valid && vec && c0 + 8 <= C) {
     Vec8<T>::load(row, v);
   } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = (valid && c0 + k < C) ? to_f32<T>(__ldcg(row + k)) : 0.f;
+    for (int k = 0; k < 8; ++k) v[k] = (it.valid && c0 + k < C) ? to_f32<T>(__ldcg(row + k)) : 0.f;
   }
+}
+__device__ __forceinline__ void gather_nhwc_store(const LayerDev& L, const NhwcItem& it, int lane, const float (&v)[8]) {
+  const int nchunk = L.nchunk, Ppad = L.Ppad, Cp8 = L.Cp >> 3;
+  const int s = it.s, b = it.b, side = it.side, p = it.p, c8 = it.c8;
   float ss = 0.f;
   int bad = 0;
 #pragma unroll
@@ -83,7 +100,7 @@ __device__ __forceinline__ void gather_nhwc_item(const LayerDev& L, int b0, int 
   bad |= __shfl_xor_sync(0xffffffffu, bad, 8);
   bad |= __shfl_xor_sync(0xffffffffu, bad, 16);
   float* ssbase = side ? L.qss : L.kss;                      // NULL in head mode (the head's output is normalised)
-  if (ssbase != nullptr && g == 0) ssbase[((size_t)b * nchunk + s) * Ppad + p] = bad ? __int_as_float(0x7fc00000) : ss;
+  if (ssbase != nullptr && (lane >> 3) == 0) ssbase[((size_t)b * nchunk + s) * Ppad + p] = bad ? __int_as_float(0x7fc00000) : ss;
   uint32_t hw[4], lw[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -113,7 +130,21 @@ __device__ __forceinline__ void gather_nhwc_item(const LayerDev& L, int b0, int 
   }
 }
 
-// grid = sum_l ceil(2 * B * (Ppad_l / 8) * nchunk_l / 8) CTAs of 8 warps; m.start counts CTAs per launch slot
+constexpr int kNhwcItemsPerWarp = 2;
+template <typename T>
+__device__ __forceinline__ void gather_nhwc_warp(const LayerDev& L, int b0, int B, long long w0, long long nitems, int lane,
+                                                 int side0) {
+  NhwcItem it[kNhwcItemsPerWarp];
+  float v[kNhwcItemsPerWarp][8];
+#pragma unroll
+  for (int n = 0; n < kNhwcItemsPerWarp; ++n)
+    if (w0 + n < nitems) gather_nhwc_load<T>(L, b0, B, w0 + n, lane, side0, it[n], v[n]);
+#pragma unroll
+  for (int n = 0; n < kNhwcItemsPerWarp; ++n)
+    if (w0 + n < nitems) gather_nhwc_store(L, it[n], lane, v[n]);
+}
+
+// grid = sum_l ceil(items_l / 16) CTAs of 8 warps, 2 items per warp; items_l = sides * B * (Ppad_l / 8) * nchunk_l
 __global__ void __launch_bounds__(kThreads) k_gather_tc_nhwc(const __grid_constant__ Params p,
                                                              const __grid_constant__ BlockMap m) {
   const long long blk = blockIdx.x;
@@ -124,13 +155,13 @@ __global__ void __launch_bounds__(kThreads) k_gather_tc_nhwc(const __grid_consta
   const int slot = find_layer(m, blk, p.n_layers);
   const int l = m.layer[slot];
   const LayerDev& L = p.L[l];
-  const long long witem = (blk - m.start[slot]) * 8 + (threadIdx.x >> 5);
+  const long long w0 = ((blk - m.start[slot]) * 8 + (threadIdx.x >> 5)) * kNhwcItemsPerWarp;
   const long long nitems = (long long)(2 - p.side0) * p.bn * (L.Ppad >> 3) * L.nchunk;
-  if (witem >= nitems) return;
+  if (w0 >= nitems) return;
   const int lane = threadIdx.x & 31;
-  if (p.dtype == PNCE_F32) gather_nhwc_item<float>(L, p.b0, p.bn, witem, lane, p.side0);
-  else if (p.dtype == PNCE_F16) gather_nhwc_item<__half>(L, p.b0, p.bn, witem, lane, p.side0);
-  else gather_nhwc_item<__nv_bfloat16>(L, p.b0, p.bn, witem, lane, p.side0);
+  if (p.dtype == PNCE_F32) gather_nhwc_warp<float>(L, p.b0, p.bn, w0, nitems, lane, p.side0);
+  else if (p.dtype == PNCE_F16) gather_nhwc_warp<__half>(L, p.b0, p.bn, w0, nitems, lane, p.side0);
+  else gather_nhwc_warp<__nv_bfloat16>(L, p.b0, p.bn, w0, nitems, lane, p.side0);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -140,6 +171,8 @@ __global__ void __launch_bounds__(kThreads) k_gather_tc_nhwc(const __grid_consta
 // their candidates compared in parallel).  No sampled position in the tile: 128-bit zero stores straight from
 // registers.  Otherwise the tile is staged in shared memory, thread <-> channel adds up the row-major gradient
 // rows of every run of equal ids in sorted order (the order of the NCHW kernel), and the tile is copied out.
+// (Measured and rejected: a store-first variant without shared memory -- zero stores issued before the slot lookup,
+// slot range by warp ballots, hit rows overwritten after one barrier -- 460 vs 454 us at B=64.)
 // -------------------------------------------------------------------------------------------------
 struct DenseNhwcMap {
   long long start[PNCE_MAX_LAYERS + 1];        // tile prefix per layer

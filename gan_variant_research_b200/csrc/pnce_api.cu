@@ -259,11 +259,11 @@ static int launch_gather_tc(const Params& p, cudaStream_t st) {
       for (int j = i; j > 0 && p.L[order[j]].C <= p.L[order[j - 1]].C; --j) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
   long long acc = 0;
   if (p.nhwc) {
-    // channels-last maps: one warp per (side, image, 8 slots, 32-channel chunk), 8 warps per CTA
+    // channels-last maps: warp items (side, image, 8 slots, 32-channel chunk), 8 warps per CTA, kNhwcItemsPerWarp each
     for (int s = 0; s < p.n_layers; ++s) {
       m.start[s] = acc;
       m.layer[s] = order[s];
-      acc += ((long long)(2 - p.side0) * p.bn * (p.L[order[s]].Ppad >> 3) * p.L[order[s]].nchunk + 7) / 8;
+      acc += ((long long)(2 - p.side0) * p.bn * (p.L[order[s]].Ppad >> 3) * p.L[order[s]].nchunk + 8 * kNhwcItemsPerWarp - 1) / (8 * kNhwcItemsPerWarp);
     }
     m.start[p.n_layers] = acc;
     if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
