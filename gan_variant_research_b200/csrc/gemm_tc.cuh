@@ -296,6 +296,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       for (int t = t0; t < t1; ++t) {
+        // the single stage cannot load ahead; pull the NEXT row tile's operands into L2 while this one's MMAs run
+        // (both blobs come from DRAM otherwise, and that latency would sit in front of every step)
+        if (t + 1 < t1) {
+          const size_t an = ((size_t)(t + 1) * NA8 + (size_t)ih * 16) * 2048, bn = (size_t)(t + 1) * N8 * 2048;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char*>(pr.a_hi) + an), "r"(abytes) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char*>(pr.b_hi) + bn), "r"(bbytes) : "memory");
+          if (x3) {
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char*>(pr.a_lo) + an), "r"(abytes) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char*>(pr.b_lo) + bn), "r"(bbytes) : "memory");
+          }
+        }
         if (!mbar_wait(&sh->empty, ((uint32_t)(t - t0) & 1u) ^ 1u, dead)) break;
         mbar_expect_tx(&sh->full, (abytes + bbytes) * (x3 ? 2u : 1u));
         const size_t ao = ((size_t)t * NA8 + (size_t)ih * 16) * 2048;

@@ -13,9 +13,14 @@
 
 namespace pnce {
 
-constexpr int kGpThreads = 320;
-constexpr int kGpSlots = 8;
-constexpr int kGpSmemBytes = kGpSlots * kGemmStageBytes + 512 + 2048 + 2048;   // + GM_YROWS row-norm exchange [2][2][128] floats + bias [2][256]
+constexpr int kGpEpiWarps = 16;            // four per TMEM lane quadrant = four per warp scheduler
+constexpr int kGpThreads = 64 + 32 * kGpEpiWarps;
+// stages of 32 columns of K (A hi 8K | A lo 8K | B hi 16K | B lo 16K = 48 KB), 4 slots: the same 192 KB in flight as 8
+// slots of 16 columns, in half as many (twice as large) bulk copies
+constexpr int kGpSlots = 4;
+constexpr int kGpStageBytes = 2 * kGemmStageBytes;
+constexpr int kGpOffAlo = 2 * kGemmOffAlo, kGpOffBhi = 2 * kGemmOffBhi, kGpOffBlo = 2 * kGemmOffBlo;
+constexpr int kGpSmemBytes = kGpSlots * kGpStageBytes + 512 + 4096 + 2048;   // + GM_YROWS row-norm exchange [2][4][128] floats + bias [2][256]
 
 struct GpShared {
   uint64_t full[kGpSlots], empty[kGpSlots], accfull[2], accfree[2];
@@ -34,20 +39,20 @@ __device__ __forceinline__ void gp_decode(const GemmLaunch& g, long long t, GpTi
     if (t >= g.start[i]) pi = i;
   o.pr = &g.pr[pi];
   o.tile = (int)(t - g.start[pi]);
-  o.K = o.pr->K; o.N = o.pr->N; o.nstage = o.K >> 4;
+  o.K = o.pr->K; o.N = o.pr->N; o.nstage = o.K >> 5;
 }
 
 __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_constant__ GemmLaunch g) {
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
-  GpShared* sh = reinterpret_cast<GpShared*>(smem + kGpSlots * kGemmStageBytes);
+  GpShared* sh = reinterpret_cast<GpShared*>(smem + kGpSlots * kGpStageBytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long total = g.start[g.n];
   const bool x3 = g.x3 != 0;
   volatile int* dead = &sh->dead;
   if (tid == 0) {
     for (int k = 0; k < kGpSlots; ++k) { mbar_init(&sh->full[k], 1); mbar_init(&sh->empty[k], 1); }
-    for (int k = 0; k < 2; ++k) { mbar_init(&sh->accfull[k], 1); mbar_init(&sh->accfree[k], 256); }
+    for (int k = 0; k < 2; ++k) { mbar_init(&sh->accfull[k], 1); mbar_init(&sh->accfree[k], 32 * kGpEpiWarps); }
     sh->dead = 0;
     fence_barrier_init();
   }
@@ -66,21 +71,23 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
         GpTile w;
         gp_decode(g, t, w);
         const GemmProb& pr = *w.pr;
-        const uint32_t bbytes = (uint32_t)w.N * 32u;          // one B chunk: 2 slabs x N rows x 16 B
+        const uint32_t bbytes = (uint32_t)w.N * 64u;          // one B chunk: 4 slabs x N rows x 16 B
         const unsigned char* ga_hi = reinterpret_cast<const unsigned char*>(pr.a_hi) + (size_t)w.tile * (w.K >> 3) * 2048;
         const unsigned char* ga_lo = reinterpret_cast<const unsigned char*>(pr.a_lo) + (size_t)w.tile * (w.K >> 3) * 2048;
         const unsigned char* gb_hi = reinterpret_cast<const unsigned char*>(pr.b_hi);
         const unsigned char* gb_lo = reinterpret_cast<const unsigned char*>(pr.b_lo);
+        // (measured and rejected: an L2 prefetch of the next tile's activations and ReLU mask here -- GEMM launches 228 ->
+        //  260 us per step; the same prefetch does pay in k_wgrad_tc, whose single stage cannot load ahead)
         for (int s = 0; s < w.nstage; ++s, ++it) {
           const int slot = it % kGpSlots;
           ok = mbar_wait(&sh->empty[slot], ((it / kGpSlots) & 1u) ^ 1u, dead);
           if (!ok) break;
-          unsigned char* st = smem + slot * kGemmStageBytes;
-          mbar_expect_tx(&sh->full[slot], (4096u + bbytes) * (x3 ? 2u : 1u));
-          bulk_g2s(st, ga_hi + (size_t)s * 4096, 4096u, &sh->full[slot]);
-          if (x3) bulk_g2s(st + kGemmOffAlo, ga_lo + (size_t)s * 4096, 4096u, &sh->full[slot]);
-          bulk_g2s(st + kGemmOffBhi, gb_hi + (size_t)s * bbytes, bbytes, &sh->full[slot]);
-          if (x3) bulk_g2s(st + kGemmOffBlo, gb_lo + (size_t)s * bbytes, bbytes, &sh->full[slot]);
+          unsigned char* st = smem + slot * kGpStageBytes;
+          mbar_expect_tx(&sh->full[slot], (8192u + bbytes) * (x3 ? 2u : 1u));
+          bulk_g2s(st, ga_hi + (size_t)s * 8192, 8192u, &sh->full[slot]);
+          if (x3) bulk_g2s(st + kGpOffAlo, ga_lo + (size_t)s * 8192, 8192u, &sh->full[slot]);
+          bulk_g2s(st + kGpOffBhi, gb_hi + (size_t)s * bbytes, bbytes, &sh->full[slot]);
+          if (x3) bulk_g2s(st + kGpOffBlo, gb_lo + (size_t)s * bbytes, bbytes, &sh->full[slot]);
         }
       }
     }
@@ -103,15 +110,18 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
           const int slot = it % kGpSlots;
           ok = mbar_wait(&sh->full[slot], (it / kGpSlots) & 1u, dead);
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + slot * kGemmStageBytes);
-          const uint64_t a_hi = smem_desc(st, 2048, 128);
-          const uint64_t b_hi = smem_desc(st + kGemmOffBhi, lbo_b, 128);
-          mma_bf16(acc, a_hi, b_hi, idesc, s ? 1u : 0u);
-          if (x3) {
-            const uint64_t a_lo = smem_desc(st + kGemmOffAlo, 2048, 128);
-            const uint64_t b_lo = smem_desc(st + kGemmOffBlo, lbo_b, 128);
-            mma_bf16(acc, a_hi, b_lo, idesc, 1u);
-            mma_bf16(acc, a_lo, b_hi, idesc, 1u);
+          const uint32_t st = smem_u32(smem + slot * kGpStageBytes);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {                     // 16 columns of K = 2 slabs per MMA
+            const uint64_t a_hi = smem_desc(st + ks * 4096, 2048, 128);
+            const uint64_t b_hi = smem_desc(st + kGpOffBhi + ks * 2 * lbo_b, lbo_b, 128);
+            mma_bf16(acc, a_hi, b_hi, idesc, (s | ks) ? 1u : 0u);
+            if (x3) {
+              const uint64_t a_lo = smem_desc(st + kGpOffAlo + ks * 4096, 2048, 128);
+              const uint64_t b_lo = smem_desc(st + kGpOffBlo + ks * 2 * lbo_b, lbo_b, 128);
+              mma_bf16(acc, a_hi, b_lo, idesc, 1u);
+              mma_bf16(acc, a_lo, b_hi, idesc, 1u);
+            }
           }
           mma_commit(&sh->empty[slot]);
         }
@@ -121,7 +131,8 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
   } else {
     // ===================== epilogue: two warps per quadrant, thread <-> row of the tile =====================
     const int q = warp & 3, i = q * 32 + lane;
-    const int half = (warp - 2) >> 2;                        // 0: even 32-column chunks, 1: odd ones
+    const int half = (warp - 2) >> 2;                        // this warp's 32-column chunks: half, half + 4, ...
+    constexpr int kSub = kGpEpiWarps / 4;
     int n = 0;
     for (long long t = blockIdx.x; t < total; t += gridDim.x, ++n) {
       GpTile w;
@@ -135,11 +146,11 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
       const uint32_t trow = tmem + (uint32_t)(n & 1) * 256u + ((uint32_t)(q * 32) << 16);
       const size_t rowblob = ((size_t)tile * N8 * 16 + (size_t)(i >> 3)) * 64 + (size_t)(i & 7) * 8;   // + n8 * 1024
       // this tile's bias (or zeros) in shared memory: one load per epilogue thread instead of one per element and thread
-      float* bias_s = reinterpret_cast<float*>(smem + kGpSlots * kGemmStageBytes + 512 + 2048) + (n & 1) * 256;
+      float* bias_s = reinterpret_cast<float*>(smem + kGpSlots * kGpStageBytes + 512 + 4096) + (n & 1) * 256;
       {
         const int et = tid - 64;
-        bias_s[et] = (pr.bias != nullptr && et < N) ? __ldg(pr.bias + et) : 0.f;
-        asm volatile("bar.sync 5, 256;" ::: "memory");
+        if (et < 256) bias_s[et] = (pr.bias != nullptr && et < N) ? __ldg(pr.bias + et) : 0.f;
+        asm volatile("bar.sync 5, %0;" ::"n"(32 * kGpEpiWarps) : "memory");
       }
       mbar_wait(&sh->accfull[n & 1], ((uint32_t)n >> 1) & 1u, dead);
       tc_fence_after();
@@ -148,9 +159,9 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
         // ---- PatchSampleF(use_mlp=True) output: y = acc + b2, out = y / max(||y||, eps) as fp32 rows.  The row norm
         //      needs every column, and the two warps of a quadrant hold alternate chunks: pass 1 sums the squares and
         //      swaps the partial sums through shared memory, pass 2 re-reads the accumulator and writes the rows ----
-        float* xss = reinterpret_cast<float*>(smem + kGpSlots * kGemmStageBytes + 512) + (n & 1) * 256;
+        float* xss = reinterpret_cast<float*>(smem + kGpSlots * kGpStageBytes + 512) + (n & 1) * (kSub * 128);
         float ssum = 0.f;
-        for (int ch = half; ch < nch; ch += 2) {
+        for (int ch = half; ch < nch; ch += kSub) {
           uint32_t r[32];
           tmem_ld32(trow + ch * 32, r);
           tmem_ld_wait();
@@ -162,18 +173,21 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
         }
         xss[half * 128 + i] = ssum;
         switch (q) {                                              // the two warps of this quadrant (immediate barrier ids)
-          case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-          case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-          case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-          default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+          case 0: asm volatile("bar.sync 1, %0;" ::"n"(32 * kSub) : "memory"); break;
+          case 1: asm volatile("bar.sync 2, %0;" ::"n"(32 * kSub) : "memory"); break;
+          case 2: asm volatile("bar.sync 3, %0;" ::"n"(32 * kSub) : "memory"); break;
+          default: asm volatile("bar.sync 4, %0;" ::"n"(32 * kSub) : "memory"); break;
         }
-        const float nrm = sqrtf(xss[i] + xss[128 + i]);
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < kSub; ++k) tot += xss[k * 128 + i];
+        const float nrm = sqrtf(tot);
         const float den = (nrm == nrm) ? fmaxf(nrm, kNormEps) : nrm;      // clamp_min keeps NaN (F.normalize, patchnce_cut.py:77)
         const float scale = 1.0f / den;
         const size_t orow = ((size_t)b * pr.P + (rowok ? __ldg(pr.perm + p) : 0)) * N;
         if (rowok && half == 0 && pr.inv_out != nullptr)
           pr.inv_out[orow / N] = (nrm == nrm) ? (nrm < kNormEps ? -1.0f / kNormEps : 1.0f / nrm) : nrm;
-        for (int ch = half; ch < nch; ch += 2) {
+        for (int ch = half; ch < nch; ch += kSub) {
           uint32_t r[32];
           tmem_ld32(trow + ch * 32, r);
           tmem_ld_wait();
@@ -194,11 +208,11 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
         mbar_arrive(&sh->accfree[n & 1]);
         continue;
       }
-      // ---- every other mode: this warp's chunks ch = half, half + 2, ..., software-pipelined -- the TMEM load (and the
-      //      ReLU mask, GM_DH) of the next chunk are in flight while the current one is processed.  One warp per
-      //      scheduler pair leaves every load latency exposed otherwise (ncu: tensor pipe 26-41 % active, the launch was
-      //      epilogue-bound: ~21 k cycles per 128 x 256 tile against 6 k of MMAs) ----
-      uint32_t ra[32], rb[32];
+      // ---- every other mode: this warp's chunks ch = half, half + 4, ...  Sixteen epilogue warps (four per scheduler)
+      //      hide the TMEM / shared / global latencies of one another: with eight, software-pipelined (the TMEM load of the
+      //      next chunk in flight under the current one, 168 registers), the launch stayed issue-starved -- ncu: 1.2 warp
+      //      instructions per cycle and SM, ~20 k of them and ~17 k cycles per 128 x 256 tile against 7 k of MMAs ----
+      uint32_t ra[32];
       uint4 hm[4];                                             // GM_DH: ReLU mask of the NEXT chunk to process (single buffer,
                                                                // reloaded as soon as it has been applied)
       auto load_mask = [&](int ch) {
@@ -259,7 +273,7 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
               if ((wv[k2] & 0x7fff0000u) == 0u) v[g8 * 8 + 2 * k2 + 1] = 0.f;
             }
           }
-          load_mask(ch + 2);                                    // flies under the split + stores below and the next TMEM wait
+          load_mask(ch + kSub);                                 // flies under the split + stores below and the next TMEM wait
         }
         if (mode == GM_YQ || mode == GM_YK) {
           float ssum = 0.f;
@@ -297,21 +311,15 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
           }
         }
       };
-      if (half < nch) tmem_ld32(trow + half * 32, ra);
       load_mask(half);
 #pragma unroll 1
-      for (int ch = half; ch < nch; ch += 4) {
+      for (int ch = half; ch < nch; ch += kSub) {
+        tmem_ld32(trow + ch * 32, ra);
         tmem_ld_wait();
-        if (ch + 2 < nch) tmem_ld32(trow + (ch + 2) * 32, rb);
         chunk(ch, ra);
-        if (ch + 2 < nch) {
-          tmem_ld_wait();
-          if (ch + 4 < nch) tmem_ld32(trow + (ch + 4) * 32, ra);
-          chunk(ch + 2, rb);
-        }
       }
       tc_fence_before();
-      mbar_arrive(&sh->accfree[n & 1]);                       // 256 arrivals hand the buffer back to the MMA thread
+      mbar_arrive(&sh->accfree[n & 1]);                       // every epilogue thread arrives: the buffer goes back to the MMA thread
     }
   }
   __syncthreads();

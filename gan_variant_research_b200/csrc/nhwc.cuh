@@ -63,12 +63,16 @@ struct NhwcItem {
 template <typename T>
 __device__ __forceinline__ void gather_nhwc_load(const LayerDev& L, int b0, int B, long long witem, int lane, int side0,
                                                  NhwcItem& it, float (&v)[8]) {
-  const int nchunk = L.nchunk, np8 = L.Ppad >> 3;
-  it.s = (int)(witem % nchunk);
-  const int p8 = (int)((witem / nchunk) % np8);
-  const long long rest = witem / nchunk / np8;
-  it.b = b0 + (int)(rest % B);
-  it.side = (int)(rest / B) + side0;                         // 0 = src (k), 1 = tgt (q); side0 = 1: tgt only
+  // 32-bit index arithmetic (the launch checks that the item count fits): 64-bit divisions by run-time values cost ~100
+  // instructions each, and this kernel has few others
+  const unsigned nchunk = (unsigned)L.nchunk, np8 = (unsigned)L.Ppad >> 3, wi = (unsigned)witem;
+  const unsigned g1 = wi / nchunk;
+  it.s = (int)(wi - g1 * nchunk);
+  const unsigned rest = g1 / np8;
+  const int p8 = (int)(g1 - rest * np8);
+  const unsigned sd = rest / (unsigned)B;
+  it.b = b0 + (int)(rest - sd * (unsigned)B);
+  it.side = (int)sd + side0;                                 // 0 = src (k), 1 = tgt (q); side0 = 1: tgt only
   const int C = L.C, HW = L.HW;
   it.p = p8 * 8 + (lane & 7);                                // sorted slot
   it.c8 = it.s * 4 + (lane >> 3);                            // 8-channel group

@@ -263,7 +263,9 @@ static int launch_gather_tc(const Params& p, cudaStream_t st) {
     for (int s = 0; s < p.n_layers; ++s) {
       m.start[s] = acc;
       m.layer[s] = order[s];
-      acc += ((long long)(2 - p.side0) * p.bn * (p.L[order[s]].Ppad >> 3) * p.L[order[s]].nchunk + 8 * kNhwcItemsPerWarp - 1) / (8 * kNhwcItemsPerWarp);
+      const long long items = (long long)(2 - p.side0) * p.bn * (p.L[order[s]].Ppad >> 3) * p.L[order[s]].nchunk;
+      if (items > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;   // the kernel's item arithmetic is 32-bit
+      acc += (items + 8 * kNhwcItemsPerWarp - 1) / (8 * kNhwcItemsPerWarp);
     }
     m.start[p.n_layers] = acc;
     if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
