@@ -148,6 +148,50 @@ __device__ __forceinline__ void tc_pass_b(const uint32_t (&r)[32], const float* 
   }
 }
 
+// ---- single-pass softmax over one 32-column chunk (key-blocked kernel, P > 256, clamp cannot bind): e = exp2(y) once,
+//      the UNNORMALISED e / ||k_j|| is the dQ operand, se += e (padding columns masked), s2 += e y.  The row factor
+//      coef / se and the "- I" term are applied afterwards (the diagonal entry is patched once se is complete).
+__device__ __forceinline__ void tc_pass_single(const uint32_t (&r)[32], const float* __restrict__ wk, float a, bool x3,
+                                               unsigned char* dzhi, unsigned char* dzlo, uint32_t off0, float (&se)[4],
+                                               float& s2) {
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8) {
+    float dd[8];
+#pragma unroll
+    for (int h4 = 0; h4 < 2; ++h4) {
+      const float4 w = *reinterpret_cast<const float4*>(wk + g8 * 8 + h4 * 4);
+      const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float y = __uint_as_float(r[g8 * 8 + h4 * 4 + t]) * a * ww[t];
+        const float e = ex2f(y);
+        se[t] += (ww[t] != 0.f) ? e : 0.f;
+        s2 = fmaf(e, y, s2);
+        dd[h4 * 4 + t] = e * ww[t];
+      }
+    }
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+      hw[k2] = bf16x2_bits(dd[2 * k2], dd[2 * k2 + 1]);
+      const float r0 = dd[2 * k2] - __uint_as_float(hw[k2] << 16);
+      const float r1 = dd[2 * k2 + 1] - __uint_as_float(hw[k2] & 0xffff0000u);
+      lw[k2] = bf16x2_bits(r0, r1);
+    }
+    const uint32_t off = off0 + (uint32_t)g8 * 2048u;
+    *reinterpret_cast<uint4*>(dzhi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    if (x3) *reinterpret_cast<uint4*>(dzlo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+// Key-block and chunk order of an item in single-pass mode: the block that holds the diagonals of the item's own 128 rows
+// goes LAST, and inside it the (up to) four chunks with those diagonals go last -- they are released only when the row
+// sums are complete.  dlo = first diagonal chunk of that block (0 or 4), nch = its chunks that hold real columns.
+__device__ __forceinline__ int tc_block_at(int o, int nkb, int kbd) { return o < nkb - 1 ? (o < kbd ? o : o + 1) : kbd; }
+__device__ __forceinline__ int tc_chunk_last(int k, int nch, int dlo) {
+  const int nn = dlo == 0 ? (nch > 4 ? nch - 4 : 0) : (nch < 4 ? nch : 4);      // chunks without diagonals come first
+  return k < nn ? (dlo == 0 ? k + 4 : k) : dlo + (k - nn);
+}
+
 // Both passes walk the row in 32-column chunks with two STATIC register buffers so that the
 // tcgen05.ld of chunk ch+1 is in flight while chunk ch is processed.
 template <bool CLAMP>
@@ -392,6 +436,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
   const bool multi = nkb > 1;
   const int nslots1 = multi ? 2 : kTcSlots1;                  // the dZ region is busy in pass 2 of the multi-block case
   const bool x3 = (p.math == PNCE_MATH_TC_BF16X3);
+  // more than one key block and the +-50 clamp cannot bind (|cos| <= 1, every CUT temperature): ONE pass per block --
+  // exp2 once, unnormalised operand, no recomputation of the logits (the two-pass form stays for clamp-binding tau)
+  const bool single = multi && !((1.0f / p.tau) * 1.02f > kClamp);
+  const int kbd_item = (mh * 128) >> 8;                       // key block with the diagonals of this item's rows
+  const int dlo_item = ((mh * 128) & 255) >> 5;               // and the first of its (up to four) diagonal chunks
   volatile int* dead = &sh->dead;
   long long* tr = nullptr;                                   // debug stamps (pnce_debug_set key 3)
   if (p.trace != nullptr && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) tr = p.trace + (blockIdx.x ? 16 : 0);
@@ -423,7 +472,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
-  const int npass = multi ? 2 : 1;
+  const int npass = (multi && !single) ? 2 : 1;
 
   if (warp == 0) {
     // ===================== producer =====================
@@ -438,7 +487,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       uint32_t it1 = 0, it2 = 0, nz = 0;
       bool ok = true;
       for (int pass = 0; pass < npass && ok; ++pass) {
-        for (int kb = 0; kb < nkb && ok; ++kb) {
+        for (int o = 0; o < nkb && ok; ++o) {
+          const int kb = single ? tc_block_at(o, nkb, kbd_item) : o;
           const int NB = min(256, Ppad - kb * 256);           // keys of this block (128 or 256)
           const uint32_t kbytes = (uint32_t)NB * 64u;         // one K chunk: 4 slabs x NB/8 core matrices x 128 B
           const size_t kblk = (size_t)kb * 256 * Cp * 2;      // blocks are stored one after the other
@@ -460,7 +510,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
             // that the Z block's MMAs have drained, and handed back when this block's dQ MMAs have
             const int key0 = kb * 256, keys = min(P, key0 + 256) - key0;
             const int nj = (keys + 31) >> 5;
-            for (int j = 0; j < nj && ok; ++j, ++it2) {
+            const bool lastblk = single && o == nkb - 1;
+            for (int k = 0; k < nj && ok; ++k, ++it2) {
+              const int j = lastblk ? tc_chunk_last(k, nj, dlo_item) : k;     // the MMA thread's chunk order
               const int slot = it2 % kTcSlots2;
               ok = mbar_wait(&sh->empty2[slot], ((it2 / kTcSlots2) & 1u) ^ 1u, dead);
               if (!ok) break;
@@ -469,7 +521,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
               bulk_g2s(st, g2_hi + (size_t)(kb * 8 + j) * k2bytes, k2bytes, &sh->full2[slot]);
               if (x3) bulk_g2s(st + 16384, g2_lo + (size_t)(kb * 8 + j) * k2bytes, k2bytes, &sh->full2[slot]);
             }
-            if (multi && kb + 1 < nkb && ok) ok = mbar_wait(&sh->p2done, (uint32_t)kb & 1u, dead);
+            if (multi && o + 1 < nkb && ok) ok = mbar_wait(&sh->p2done, (uint32_t)o & 1u, dead);
           }
           ++nz;
         }
@@ -481,17 +533,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       const uint32_t idesc2 = idesc_bf16(128, Cp, 0, 1);     // dQ: B read MN-major (N = channel)
       const uint32_t dzh = smem_u32(dzhi), dzl = smem_u32(dzlo);
       const uint32_t lbo2 = (uint32_t)Cp8 * 128u;             // 8-key group stride of a key-major chunk
-      uint32_t it1 = 0, it2 = 0, nz = 0;
+      uint32_t it1 = 0, it2 = 0, nz = 0, dzphase = 0;          // dzphase bit j: parity of the next completion of dzready[j]
       bool ok = true;
       PNCE_TR(8);
       for (int pass = 0; pass < npass && ok; ++pass) {
-        for (int kb = 0; kb < nkb && ok; ++kb) {
+        for (int o = 0; o < nkb && ok; ++o) {
+          const int kb = single ? tc_block_at(o, nkb, kbd_item) : o;
           const int NB = min(256, Ppad - kb * 256);
           const uint32_t idesc1 = idesc_bf16(128, NB, 0, 0);
           const uint32_t lbo_k = (uint32_t)NB * 16u;          // slab (c/8) stride of a K chunk in smem
-          // the previous Z block must have been read out of TMEM.  Pass 1: the epilogue says so (zfree);
-          // pass 2, kb > 0: implied by having consumed every dzready of the previous block.
-          if (multi && nz > 0 && (pass == 0 || kb == 0)) ok = mbar_wait(&sh->zfree, (nz - 1) & 1u, dead);
+          // the previous Z block must have been read out of TMEM.  Pass 1 of two: the epilogue says so (zfree);
+          // pass 2 / single pass, block > 0: implied by having consumed every dzready of the previous block.
+          if (multi && !single && nz > 0 && (pass == 0 || kb == 0)) ok = mbar_wait(&sh->zfree, (nz - 1) & 1u, dead);
           // ---- Z block = Q_half K_block^T ----
           for (int s = 0; s < nstage && ok; ++s, ++it1) {
             const int slot = it1 % nslots1;
@@ -519,18 +572,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
           // ---- dQ += dZ_block K_block, one stage per 32 keys, released chunk by chunk by the epilogue ----
           const int key0 = kb * 256, keys = min(P, key0 + 256) - key0;
           const int nj = (keys + 31) >> 5;
-          for (int j = 0; j < nj && ok; ++j, ++it2) {
+          const bool lastblk = single && o == nkb - 1;
+          for (int k = 0; k < nj && ok; ++k, ++it2) {
+            const int j = lastblk ? tc_chunk_last(k, nj, dlo_item) : k;       // diagonal chunks last (released after the row sums)
             const int slot = it2 % kTcSlots2;
-            ok = mbar_wait(&sh->dzready[j], (uint32_t)kb & 1u, dead);
+            ok = mbar_wait(&sh->dzready[j], (dzphase >> j) & 1u, dead);   // per-chunk phase: blocks differ in chunk count
+            dzphase ^= 1u << j;
             if (ok) ok = mbar_wait(&sh->full2[slot], (it2 / kTcSlots2) & 1u, dead);
             tc_fence_after();
-            if (kb == 0 && j == 0) PNCE_TR(10);
+            if (o == 0 && k == 0) PNCE_TR(10);
             const uint32_t st = smem_u32(stage0 + slot * kTcStage2Bytes);
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {                 // 16 keys per MMA
               const uint64_t a_hi = smem_desc(dzh + (uint32_t)(j * 2 + ks) * 4096u, 2048, 128);
               const uint64_t b_hi = smem_desc(st + (uint32_t)ks * 2u * lbo2, lbo2, 128);
-              mma_bf16(tmem + 256u, a_hi, b_hi, idesc2, (kb | j | ks) ? 1u : 0u);
+              mma_bf16(tmem + 256u, a_hi, b_hi, idesc2, (o | k | ks) ? 1u : 0u);
               if (x3) {
                 const uint64_t a_lo = smem_desc(dzl + (uint32_t)(j * 2 + ks) * 4096u, 2048, 128);
                 const uint64_t b_lo = smem_desc(st + 16384u + (uint32_t)ks * 2u * lbo2, lbo2, 128);
@@ -606,75 +662,154 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       const int chd = (gi & 255) >> 5;                        // and the chunk inside it (both warp-uniform)
       uint32_t nz = 0;
       PNCE_TR(1);
-      // ---- pass A: row sum of exp2 over all key blocks, diagonal ----
-      float se4[4] = {0.f, 0.f, 0.f, 0.f};
-      float ydacc = 0.f;                                      // raw accumulator of the diagonal element
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int key0 = kb * 256, keys = min(P, key0 + 256) - key0;
-        const int nch = (keys + 31) >> 5;                     // chunks that hold real columns
-        const bool pad = (nch * 32 != keys);                  // the block's last chunk holds padding columns
-        if (kb > 0) {                                          // swap in this block's 1/||k_j||
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int j = et; j < 256; j += 128) invk_s[j] = (key0 + j < Ppad) ? __ldcg(L.kinv + (size_t)b * Ppad + key0 + j) : 0.f;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-        mbar_wait(&sh->zfull, nz & 1u, dead);
-        ++nz;
-        tc_fence_after();
-        if (kb == 0) PNCE_TR(2);
-        const int cd = (kb == kbd) ? chd : -1;
-        if (need_clamp) tc_row_pass_a<true>(trow, nch, invk_s, a, cl, cd, lane, se4, ydacc, pad);
-        else tc_row_pass_a<false>(trow, nch, invk_s, a, cl, cd, lane, se4, ydacc, pad);
-        if (multi) {
-          tc_fence_before();
-          mbar_arrive(&sh->zfree);                             // this Z block may be overwritten
-        }
-      }
-      const float wd = multi ? __ldcg(L.kinv + (size_t)b * Ppad + (rowok ? gi : 0)) : invk_s[gi];
-      const float ydr = ydacc * a * wd;                       // unclamped diagonal logit (log2 units)
-      const float yd = need_clamp ? fminf(fmaxf(ydr, -cl), cl) : ydr;
-      const float se = (se4[0] + se4[1]) + (se4[2] + se4[3]);   // padding columns were masked out in pass A
-      const float lse2 = lg2f(se);
-      float rowloss = rowok ? (lse2 - yd) * kLn2 : 0.f;        // :94, labels = arange
-      if (badrow && rowok) rowloss = __int_as_float(0x7fc00000);
-      PNCE_TR(3);
-      // raw q of the first two channel chunks for the dQ epilogue, from this row's slice of the Q operand
-      // blob: issued now, so the loads fly under pass B (phase 2 finishes right behind pass B: there is
-      // no other slack to hide them in)
+      float rowloss, s_i, c1;
       const size_t qoff = (((size_t)b * halves + mh) * Cp8 * 16 + (size_t)(i >> 3)) * 64 + (size_t)(i & 7) * 8;
-      const __nv_bfloat16* __restrict__ qh = L.qhi + qoff;
+      const __nv_bfloat16* __restrict__ qh = L.qhi + qoff;     // raw q of this row for the dQ epilogue: its slice of the Q blob
       const __nv_bfloat16* __restrict__ ql = (x3 && L.qlo != nullptr) ? L.qlo + qoff : nullptr;
       TcQChunk qa, qb;
-      tc_q_load(qa, qh, ql, 0, nstage);
-      tc_q_load(qb, qh, ql, 1, nstage);
-      // ---- pass B: dZ (pre-divided by ||k_j||) -> smem A operand chunk by chunk, s_i ----
-      float s2 = 0.f;
       const uint32_t rowoff = (uint32_t)(i >> 3) * 128u + (uint32_t)(i & 7) * 16u;
       TcDiag dg;
       dg.rowok = rowok;
-      dg.pass = !need_clamp || fabsf(ydr) <= cl;
-      dg.d_w = dg.pass ? (ex2f(yd - lse2) - 1.f) * coef * wd : 0.f;
+      dg.pass = true;
+      dg.d_w = 0.f;
       dg.off = (uint32_t)((gi & 255) >> 3) * 2048u + rowoff + (uint32_t)(gi & 7) * 2u;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int key0 = kb * 256, keys = min(P, key0 + 256) - key0;
-        const int nch = (keys + 31) >> 5;
-        if (multi) {
-          // this block's 1/||k_j||; the Z block is recomputed by the MMA thread (pass 2).  zfull of this
-          // block also means the previous block's dQ MMAs have finished reading the dZ operand.
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int j = et; j < 256; j += 128) invk_s[j] = (key0 + j < Ppad) ? __ldcg(L.kinv + (size_t)b * Ppad + key0 + j) : 0.f;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (single) {
+        // ---- ONE pass per key block (P > 256, clamp cannot bind): exp2 once, unnormalised operand, dQ' += E_blk K_blk;
+        //      row sums alongside; the block with this item's diagonals last, its diagonal chunks last and released
+        //      only once the row sum is complete (the "- I" patch needs it) ----
+        float se4[4] = {0.f, 0.f, 0.f, 0.f};
+        float s2 = 0.f, ydacc = 0.f;
+        bool own_deferred = false;
+        for (int o = 0; o < nkb; ++o) {
+          const int kb = tc_block_at(o, nkb, kbd_item);
+          const int key0 = kb * 256, keys = min(P, key0 + 256) - key0;
+          const int nch = (keys + 31) >> 5;                     // chunks that hold real columns
+          const bool lastblk = o == nkb - 1;
+          if (o > 0 || kb != 0) {                                // swap in this block's 1/||k_j|| (the prologue left block 0's)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int j = et; j < 256; j += 128) invk_s[j] = (key0 + j < Ppad) ? __ldcg(L.kinv + (size_t)b * Ppad + key0 + j) : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
+          // zfull of this block also means the previous block's dQ MMAs have finished reading the operand region
           mbar_wait(&sh->zfull, nz & 1u, dead);
           ++nz;
           tc_fence_after();
+          if (o == 0) PNCE_TR(2);
+          if (lastblk) {                                         // the dQ epilogue's first raw-q chunks fly under the last block
+            tc_q_load(qa, qh, ql, 0, nstage);
+            tc_q_load(qb, qh, ql, 1, nstage);
+          }
+          const int cd = (kb == kbd) ? chd : -1;
+          uint32_t r0[32], r1[32];
+          tmem_ld32(trow + (lastblk ? tc_chunk_last(0, nch, dlo_item) : 0) * 32, r0);
+          for (int k = 0; k < nch; k += 2) {
+            const int ca = lastblk ? tc_chunk_last(k, nch, dlo_item) : k;
+            const int cb = (k + 1 < nch) ? (lastblk ? tc_chunk_last(k + 1, nch, dlo_item) : k + 1) : -2;
+            tmem_ld_wait();
+            if (cb >= 0) tmem_ld32(trow + cb * 32, r1);
+            tc_pass_single(r0, invk_s + ca * 32, a, x3, dzhi, dzlo, (uint32_t)(ca * 4) * 2048u + rowoff, se4, s2);
+            if (ca == cd) {
+#pragma unroll
+              for (int kk = 0; kk < 32; ++kk) ydacc = (kk == lane) ? __uint_as_float(r0[kk]) : ydacc;
+            }
+            fence_proxy_async_smem();
+            if (ca == cd) own_deferred = true;
+            else mbar_arrive(&sh->dzready[ca]);                  // 128 arrivals release chunk ca to the MMA thread
+            if (cb >= 0) {
+              tmem_ld_wait();
+              if (k + 2 < nch) tmem_ld32(trow + (lastblk ? tc_chunk_last(k + 2, nch, dlo_item) : k + 2) * 32, r0);
+              tc_pass_single(r1, invk_s + cb * 32, a, x3, dzhi, dzlo, (uint32_t)(cb * 4) * 2048u + rowoff, se4, s2);
+              if (cb == cd) {
+#pragma unroll
+                for (int kk = 0; kk < 32; ++kk) ydacc = (kk == lane) ? __uint_as_float(r1[kk]) : ydacc;
+              }
+              fence_proxy_async_smem();
+              if (cb == cd) own_deferred = true;
+              else mbar_arrive(&sh->dzready[cb]);
+            }
+          }
         }
-        const int cd = (kb == kbd) ? chd : -1;
-        uint64_t* dzr = sh->dzready;
-        if (need_clamp) tc_row_pass_b<true>(trow, nch, invk_s, a, cl, lse2, coef, x3, dzhi, dzlo, rowoff, cd, dg, dzr, s2);
-        else tc_row_pass_b<false>(trow, nch, invk_s, a, cl, lse2, coef, x3, dzhi, dzlo, rowoff, cd, dg, dzr, s2);
+        const float wd = __ldcg(L.kinv + (size_t)b * Ppad + (rowok ? gi : 0));
+        const float ydr = ydacc * a * wd;                       // diagonal logit (log2 units)
+        const float se = (se4[0] + se4[1]) + (se4[2] + se4[3]);
+        const float lse2 = lg2f(se);
+        rowloss = rowok ? (lse2 - ydr) * kLn2 : 0.f;            // :94, labels = arange
+        if (badrow && rowok) rowloss = __int_as_float(0x7fc00000);
+        PNCE_TR(3);
+        if (own_deferred) {
+          // the "- I" term: dQ' = sum_j e_ij k^_j - se_i k^_i, i.e. the operand's diagonal entry becomes
+          // (e_ii - se_i) / ||k_i||; this warp's 32 arrivals then release its chunk
+          dg.d_w = (ex2f(ydr) - se) * wd;
+          tc_fix_diag(dg, x3, dzhi, dzlo);
+          fence_proxy_async_smem();
+          mbar_arrive(&sh->dzready[chd]);
+        }
+        s_i = coef * (s2 / se - ydr) * kLn2;                    // sum_j dZ_ij z_ij with dZ = coef (e / se - I)
+        c1 = inv_tau * sc * (coef / se);                         // the accumulator holds the unnormalised sum
+      } else {
+        // ---- pass A: row sum of exp2 over all key blocks, diagonal ----
+        float se4[4] = {0.f, 0.f, 0.f, 0.f};
+        float ydacc = 0.f;                                      // raw accumulator of the diagonal element
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int key0 = kb * 256, keys = min(P, key0 + 256) - key0;
+          const int nch = (keys + 31) >> 5;                     // chunks that hold real columns
+          const bool pad = (nch * 32 != keys);                  // the block's last chunk holds padding columns
+          if (kb > 0) {                                          // swap in this block's 1/||k_j||
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int j = et; j < 256; j += 128) invk_s[j] = (key0 + j < Ppad) ? __ldcg(L.kinv + (size_t)b * Ppad + key0 + j) : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
+          mbar_wait(&sh->zfull, nz & 1u, dead);
+          ++nz;
+          tc_fence_after();
+          if (kb == 0) PNCE_TR(2);
+          const int cd = (kb == kbd) ? chd : -1;
+          if (need_clamp) tc_row_pass_a<true>(trow, nch, invk_s, a, cl, cd, lane, se4, ydacc, pad);
+          else tc_row_pass_a<false>(trow, nch, invk_s, a, cl, cd, lane, se4, ydacc, pad);
+          if (multi) {
+            tc_fence_before();
+            mbar_arrive(&sh->zfree);                             // this Z block may be overwritten
+          }
+        }
+        const float wd = multi ? __ldcg(L.kinv + (size_t)b * Ppad + (rowok ? gi : 0)) : invk_s[gi];
+        const float ydr = ydacc * a * wd;                       // unclamped diagonal logit (log2 units)
+        const float yd = need_clamp ? fminf(fmaxf(ydr, -cl), cl) : ydr;
+        const float se = (se4[0] + se4[1]) + (se4[2] + se4[3]);   // padding columns were masked out in pass A
+        const float lse2 = lg2f(se);
+        rowloss = rowok ? (lse2 - yd) * kLn2 : 0.f;              // :94, labels = arange
+        if (badrow && rowok) rowloss = __int_as_float(0x7fc00000);
+        PNCE_TR(3);
+        // raw q of the first two channel chunks for the dQ epilogue, from this row's slice of the Q operand
+        // blob: issued now, so the loads fly under pass B (phase 2 finishes right behind pass B: there is
+        // no other slack to hide them in)
+        tc_q_load(qa, qh, ql, 0, nstage);
+        tc_q_load(qb, qh, ql, 1, nstage);
+        // ---- pass B: dZ (pre-divided by ||k_j||) -> smem A operand chunk by chunk, s_i ----
+        float s2 = 0.f;
+        dg.pass = !need_clamp || fabsf(ydr) <= cl;
+        dg.d_w = dg.pass ? (ex2f(yd - lse2) - 1.f) * coef * wd : 0.f;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int key0 = kb * 256, keys = min(P, key0 + 256) - key0;
+          const int nch = (keys + 31) >> 5;
+          if (multi) {
+            // this block's 1/||k_j||; the Z block is recomputed by the MMA thread (pass 2).  zfull of this
+            // block also means the previous block's dQ MMAs have finished reading the dZ operand.
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int j = et; j < 256; j += 128) invk_s[j] = (key0 + j < Ppad) ? __ldcg(L.kinv + (size_t)b * Ppad + key0 + j) : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&sh->zfull, nz & 1u, dead);
+            ++nz;
+            tc_fence_after();
+          }
+          const int cd = (kb == kbd) ? chd : -1;
+          uint64_t* dzr = sh->dzready;
+          if (need_clamp) tc_row_pass_b<true>(trow, nch, invk_s, a, cl, lse2, coef, x3, dzhi, dzlo, rowoff, cd, dg, dzr, s2);
+          else tc_row_pass_b<false>(trow, nch, invk_s, a, cl, lse2, coef, x3, dzhi, dzlo, rowoff, cd, dg, dzr, s2);
+        }
+        if (rowok && dg.pass) s2 = fmaf(-coef, ydr, s2);         // the diagonal's "- I" term of sum_j dZ_ij y_ij
+        s_i = s2 * kLn2;                                          // sum_j dZ_ij z_ij
+        c1 = inv_tau * sc;
       }
-      if (rowok && dg.pass) s2 = fmaf(-coef, ydr, s2);         // the diagonal's "- I" term of sum_j dZ_ij y_ij
-      const float s_i = s2 * kLn2;                              // sum_j dZ_ij z_ij
       tc_fence_before();
       PNCE_TR(4);
       // row losses: warp shuffle, then one partial per CTA (deterministic order)
@@ -685,7 +820,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
       // ---- dQ epilogue: dq/tau -> normalise backward -> dxT (coalesced: lane <-> consecutive slot) ----
       // F.normalize backward: (g - x^(x^.g)) / n when n >= eps, else g / eps
       //   dx = dq*sc - q_raw * (sc^2 s_i)       with dq = acc / tau
-      const float c1 = inv_tau * sc;
       const float c2 = noproj ? 0.f : sc * sc * s_i;
       float* __restrict__ dxrow = L.dxT + (size_t)b * C * Ppad + (rowok ? gi : 0);   // dxpitch == Ppad on this path
       if (p.nhwc) dxrow = L.dxT + ((size_t)b * Ppad + (rowok ? gi : 0)) * C;         // channels-last maps: row-major rows
