@@ -951,6 +951,31 @@ def run_e2e(args, pn, crit, layers, tdtype, elem, dev, world, rank):
 
     gd_steps = max(2, args.e2e_steps // 3)
     dt_gd = timed(step_grads_d2h, gd_steps)
+    # the same zero-copy step on CHANNELS-LAST host maps (the extension of DESIGN.md 4.7; the same pinned bytes re-read
+    # as (B, H, W, C) storage -- the values are random either way): a sampled patch is one contiguous row, so the gather
+    # pulls the useful bytes over PCIe instead of one 32-byte sector per element
+    nhwc = None
+    try:
+        def cl_view(h, s):
+            b, c, hh, ww = s
+            return h.view(-1).view(b, hh, ww, c).permute(0, 3, 1, 2)
+        c_src = [pn.pinned_as_device(cl_view(h, s), dev) for h, s in zip(h_src, shapes)]
+        c_tgt = [pn.pinned_as_device(cl_view(h, s), dev).requires_grad_() for h, s in zip(h_tgt, shapes)]
+
+        def step_zero_copy_cl():
+            for t in c_tgt:
+                t.grad = None
+            loss = crit(c_src, c_tgt)
+            loss.backward()
+            h_loss.copy_(loss.detach(), non_blocking=True)
+
+        dt_cl = timed(step_zero_copy_cl, args.e2e_steps)
+        nhwc = {"value": world * B * patches_per_image * args.e2e_steps / dt_cl, "unit": UNIT,
+                "h2d_bytes_per_step": sampled * elem, "d2h_bytes_per_step": 4, "steps": args.e2e_steps,
+                "note": "channels-last pinned host maps (extension, not the reference's layout): each sampled patch is one "
+                        "contiguous row over PCIe"}
+    except Exception as e:  # noqa: BLE001 - secondary
+        nhwc = {"error": f"{type(e).__name__}: {e}"}
     with_grads = {"value": world * B * patches_per_image * gd_steps / dt_gd, "unit": UNIT,
                   "h2d_bytes_per_step": sampled * 32, "d2h_bytes_per_step": 4 + n_elem * elem, "steps": gd_steps,
                   "note": "zero-copy inputs as in the headline e2e, plus every dense d tgt_feat copied to pinned host "
@@ -965,6 +990,7 @@ def run_e2e(args, pn, crit, layers, tdtype, elem, dev, world, rank):
             "scaling_note": "per-rank host memory and PCIe are shared on one box: this number scales worse than the "
                             "device-resident one (0.63 efficiency at N=8 in round 1)",
             "with_grads_d2h": with_grads,
+            "channels_last": nhwc,
             "bulk_copy": {"value": world * B * patches_per_image * bulk_steps / dt_bulk, "unit": UNIT,
                           "h2d_bytes_per_step": 2 * n_elem * elem, "steps": bulk_steps,
                           "note": "whole maps copied H2D every step, then the device path (PCIe-bound)"}}

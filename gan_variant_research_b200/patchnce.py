@@ -201,6 +201,10 @@ def pinned_as_device(t: torch.Tensor, device=None) -> torch.Tensor:
     tensors), so ``pinned_as_device(h).requires_grad_()`` works as a target map."""
     if t.is_cuda:
         return t
+    if t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last) and t.is_pinned():
+        # channels-last host maps: alias the dense (B, H, W, C) storage, hand back the (B, C, H, W) view -- the gather then
+        # pulls each sampled patch as ONE contiguous row over PCIe (DESIGN.md 4.7)
+        return pinned_as_device(t.permute(0, 2, 3, 1), device).permute(0, 3, 1, 2)
     if not t.is_pinned() or not t.is_contiguous():
         raise RuntimeError("pinned_as_device needs a pinned, contiguous host tensor (tensor.pin_memory())")
     if t.dtype == torch.bfloat16:            # no typestr for bf16: alias the bits as int16, then view

@@ -153,3 +153,32 @@ def test_channels_last_outside_the_tensor_core_envelope_is_relaid_out(pn, orc):
         loss.backward()
         assert loss.item() == pytest.approx(want, rel=2e-5)
         assert_grad_close(t[0].grad.cpu().numpy(), gw[0], 2e-4, math, ids=ids[0].numpy())
+
+
+def test_channels_last_pinned_host_maps_zero_copy(pn):
+    """Channels-last maps left in pinned HOST memory (pinned_as_device aliases the dense (B, H, W, C) storage): the gather
+    pulls each sampled patch as one row over PCIe; results are bit-identical to device-resident channels-last copies."""
+    g = torch.Generator().manual_seed(8)
+    shapes = [(2, 32, 24, 24), (2, 64, 16, 16)]
+    def pinned_cl(s):
+        b, c, h, w = s
+        base = torch.randn(b, h, w, c, generator=g).pin_memory()
+        return base.permute(0, 3, 1, 2)
+    h_src = [pinned_cl(s) for s in shapes]
+    h_tgt = [pinned_cl(s) for s in shapes]
+    a_src = [pn.pinned_as_device(h) for h in h_src]
+    a_tgt = [pn.pinned_as_device(h).requires_grad_() for h in h_tgt]
+    assert a_src[0].is_cuda and a_src[0].data_ptr() == h_src[0].data_ptr() and is_cl(a_src[0]) and a_src[0].shape == h_src[0].shape
+    d_src = [h.cuda() for h in h_src]
+    d_tgt = [h.cuda().requires_grad_() for h in h_tgt]
+    assert is_cl(d_src[0]) and not d_src[0].is_contiguous()
+    crit = pn.PatchNCELoss(0.07, 128)
+    torch.manual_seed(5)
+    la = crit(a_src, a_tgt)
+    la.backward()
+    torch.manual_seed(5)
+    ld = crit(d_src, d_tgt)
+    ld.backward()
+    assert la.item() == ld.item()
+    for x, y in zip(a_tgt, d_tgt):
+        assert x.grad.is_cuda and torch.equal(x.grad, y.grad)
