@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pin", action="store_true", help="N > 1: do not give every rank its own slice of the host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--head", action="store_true", help="time the netF-head mode (nc=256) as the workload")
     ap.add_argument("--no-head-line", action="store_true", help="skip the secondary head-mode measurement")
@@ -275,6 +276,18 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    pinned = None
+    if world > 1 and not args.no_pin:
+        # one slice of the box's host cores per rank (what numactl / taskset do for a multi-process job): the ranks' Python
+        # threads otherwise migrate over all cores and the small-batch (host-bound) lines lose up to 1.6x at N = 8
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local * per:(local + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+            pinned = len(mine)
+        except (AttributeError, OSError):
+            pinned = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -393,6 +406,8 @@ def main():
         "roofline": roof, "roofline_path": roof_path, "clocks": clocks,
         "gpu_launches": (10 if args.head else 4) * args.steps, "loss": float(loss.item()),
     }
+    if pinned is not None:
+        out["host_cores_per_rank"] = pinned
     if rank == 0:
         # distribution of the per-step device time inside the timed region (ms_per_step is its mean): a handful of
         # slow steps means the host stalled (a busy node), a uniform shift means the kernels themselves moved
@@ -406,11 +421,9 @@ def main():
                           "max": round(d[-1], 1), "max_at_step": slowest, "host_issue_p50": round(h[n // 2], 1), "host_issue_max": round(h[-1], 1)}
         # the same path roofline on the MEDIAN step (the mean above carries the start-up step after the barrier)
         roof_path["frac_p50"] = path_bytes / (d[n // 2] * 1e-6) / 1e9 / peak
-    kernels = kernel_breakdown(step)        # on every rank: head mode's backward holds a collective
-    if rank == 0:
-        out["kernels_us"] = kernels
-        if not args.head and "k_gather_tc" in kernels and "k_loss_tc_p" in kernels:
-            out["roofline_other_kernels"] = other_kernel_rooflines(args, layers, B, elem, kernels, peak)
+    # the per-kernel breakdowns use torch.profiler, which leaves CUPTI attached to the process (+11 % on a host-bound step,
+    # measured): every TIMED secondary line below runs first, the breakdowns after them
+    breakdowns = [("kernels_us", step)]
     if args.head:
         out["config"]["workload"] = out["config"]["workload"].replace(
             "reference-exact mode (no netF head)", "netF head mode (Linear-ReLU-Linear, nc=256, tcgen05)")
@@ -418,7 +431,7 @@ def main():
         # every rank takes part (world > 1: the head-gradient all-reduce is a collective); rank 0 reports
         hm = head_line(args, pn, src, tgt, math, patches_per_image, world, dev)
         st = strong_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers, elem, peak)
-        nh = nhwc_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers, elem, peak) if args.layout == "nchw" else None
+        nh = nhwc_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers, elem, peak, breakdowns) if args.layout == "nchw" else None
         if rank == 0 and nh is not None:
             out["nhwc"] = nh
         sc = nccl_selfcheck(args, pn, layers, dev, world, rank, math) if world > 1 else None
@@ -432,6 +445,20 @@ def main():
     if rank == 0 and world == 1 and not args.head and not args.no_head_line:
         out["module_split"] = module_split_line(args, pn, src, tgt, math, patches_per_image)
         out["configs"] = config_lines(args, pn, layers, dev, math, peak)
+    for key, fn in breakdowns:                # on every rank: head mode's backward holds a collective
+        k = kernel_breakdown(fn)
+        if rank != 0:
+            continue
+        if key == "kernels_us":
+            out["kernels_us"] = k
+            if not args.head and "k_gather_tc" in k and "k_loss_tc_p" in k:
+                out["roofline_other_kernels"] = other_kernel_rooflines(args, layers, B, elem, k, peak)
+        elif isinstance(out.get("nhwc"), dict):
+            tgt_d = out["nhwc"] if key == "nhwc" else out["nhwc"].get("head_mode")
+            if isinstance(tgt_d, dict):
+                tgt_d["kernels_us"] = k
+    breakdowns.clear()
+    if rank == 0 and world == 1 and not args.head and not args.no_head_line:
         out["next_rows"] = next_rows_line(pn, dev)
 
     # ---- e2e: same metric through the public API with HOST buffers ------------------------------
@@ -647,7 +674,7 @@ def strong_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers,
     return out
 
 
-def nhwc_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers, elem, peak, steps=20):
+def nhwc_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers, elem, peak, breakdowns, steps=20):
     """Secondary measurement at EVERY N: the same values stored channels-last (torch.channels_last), through the same
     PatchNCELoss.forward + backward.  NOT the reference's interface (its .view(B, C, -1) takes contiguous NCHW only):
     an extension for generators run in channels_last, reported beside the parity mode, never instead of it.  The
@@ -670,7 +697,6 @@ def nhwc_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers, e
                "steps": steps, "n_gpus": world, "scaling": "weak", "layout": "channels_last (B, H, W, C) storage",
                "roofline_path": {"bound": "hbm", "achieved": path_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": path_bytes / (ms * 1e-3) / 1e9 / peak},
-               "kernels_us": kernel_breakdown(step),
                "note": "extension: channels-last maps (the reference's .view rejects them); same ids / loss / gradient law"}
         b = 64 // world if 64 % world == 0 and 64 // world <= args.batch else None
         if b is not None and b < args.batch:                   # strong scaling of the global batch of 64 in this layout
@@ -704,9 +730,10 @@ def nhwc_line(args, pn, src, tgt, math, patches_per_image, world, dev, layers, e
 
         hms = timed_steps(hstep, steps, 3, world, dev)
         out["head_mode"] = {"ms_per_step": hms, "value": world * args.batch * patches_per_image / (hms * 1e-3), "unit": UNIT,
-                            "roofline_path_frac": path_bytes / (hms * 1e-3) / 1e9 / peak,
-                            "kernels_us": kernel_breakdown(hstep) if world == 1 else None}
-        del s_src, s_tgt
+                            "roofline_path_frac": path_bytes / (hms * 1e-3) / 1e9 / peak}
+        breakdowns.append(("nhwc", step))          # run by main() after every timed line (the closures keep the maps alive)
+        if world == 1:
+            breakdowns.append(("nhwc_head", hstep))
         return out
     except Exception as e:  # noqa: BLE001 - secondary
         return {"error": f"{type(e).__name__}: {e}"}
