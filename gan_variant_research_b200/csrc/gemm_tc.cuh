@@ -50,6 +50,7 @@ struct GemmLaunch {
   long long start[kGemmMaxProb + 1];
   int n, x3;
   int* err;                                // protocol-timeout flag (nonfinite[1])
+  int dbg;                                 // experiment build only: 1 = epilogue without global stores, 2 = empty epilogue
 };
 
 // ring: 4 slots x 24 KB (16 columns of K per stage: A hi 4K | A lo 4K | B hi 8K | B lo 8K) = 96 KB, so two

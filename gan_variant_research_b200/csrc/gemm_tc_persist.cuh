@@ -155,6 +155,13 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
       mbar_wait(&sh->accfull[n & 1], ((uint32_t)n >> 1) & 1u, dead);
       tc_fence_after();
       const int nch = N >> 5;
+#ifdef PNCE_EXPERIMENTS
+      if (g.dbg == 2) {                                        // experiment: what does the launch cost without any epilogue work?
+        tc_fence_before();
+        mbar_arrive(&sh->accfree[n & 1]);
+        continue;
+      }
+#endif
       if (mode == GM_YROWS) {
         // ---- PatchSampleF(use_mlp=True) output: y = acc + b2, out = y / max(||y||, eps) as fp32 rows.  The row norm
         //      needs every column, and the two warps of a quadrant hold alternate chunks: pass 1 sums the squares and
@@ -222,6 +229,11 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
             hm[g8] = __ldcg(reinterpret_cast<const uint4*>(pr.mask_hi + rowblob + (size_t)(ch * 4 + g8) * 1024));
         }
       };
+      // per-tile address bases of the blob stores (64-bit arithmetic once per tile, not once per 8-column slab)
+      const int pb = p >> 8, nb8 = min(256, Ppad - pb * 256) >> 3;   // GM_YK: key blocks of <= 256 rows, one after the other
+      const size_t yk1 = ((((size_t)b * Ppad + (size_t)pb * 256) * N8) / 8 + ((p & 255) >> 3)) * 64 + (size_t)(p & 7) * 8;   // + n8 * nb8 * 64
+      const size_t yk2 = (((size_t)b * (Ppad >> 3) + (p >> 3)) * N8) * 64 + (size_t)(p & 7) * 8;                               // + n8 * 64
+      const bool padded = (pr.P & 127) != 0;                   // only then does a tile hold rows past P
       auto chunk = [&](int ch, const uint32_t (&r)[32]) {
         float v[32];
 #pragma unroll
@@ -232,8 +244,12 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
           for (int t4 = 0; t4 < 4; ++t4) {
             float x = __uint_as_float(r[k4 * 4 + t4]) + bb[t4];
             if (mode == GM_H) x = fmaxf(x, 0.f);
-            v[k4 * 4 + t4] = rowok ? x : 0.f;                   // padding rows stay exactly zero
+            v[k4 * 4 + t4] = x;
           }
+        }
+        if (padded && !rowok) {                                 // padding rows stay exactly zero
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = 0.f;
         }
         if (mode == GM_DX) {
           // same L2 evict_last policy as the loss kernel's dxT stores (loss_tc.cuh, st_dx): k_wgrad_tc runs between this
@@ -276,14 +292,16 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
           load_mask(ch + kSub);                                 // flies under the split + stores below and the next TMEM wait
         }
         if (mode == GM_YQ || mode == GM_YK) {
-          float ssum = 0.f;
-          bool bad = false;
+          // a non-finite element makes the sum of squares non-finite; so does a finite row beyond 1.8e19, which the
+          // reference would normalise to 0 -- the head's output is O(1), the per-element test is not worth 2 instructions
+          float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            ssum = fmaf(v[k], v[k], ssum);
-            bad |= !isfinite(v[k]);
+          for (int k = 0; k < 32; k += 2) {
+            s0 = fmaf(v[k], v[k], s0);
+            s1 = fmaf(v[k + 1], v[k + 1], s1);
           }
-          pr.ss[((size_t)b * nch + ch) * Ppad + p] = bad ? __int_as_float(0x7fc00000) : ssum;
+          const float ssum = s0 + s1;
+          pr.ss[((size_t)b * nch + ch) * Ppad + p] = isfinite(ssum) ? ssum : __int_as_float(0x7fc00000);
         }
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
@@ -294,10 +312,11 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
           split8(v8, hi, lo);
           const int n8 = ch * 4 + g8;
           if (mode == GM_YK) {
-            // key blocks of <= 256 rows, one after the other (gather_tc_chunk's K layout; one block when Ppad <= 256)
-            const int pb = p >> 8, nb8 = min(256, Ppad - pb * 256) >> 3;
-            const size_t o1 = ((((size_t)b * Ppad + (size_t)pb * 256) * N8) / 8 + (size_t)n8 * nb8 + ((p & 255) >> 3)) * 64 + (size_t)(p & 7) * 8;
-            const size_t o2 = (((size_t)b * (Ppad >> 3) + (p >> 3)) * N8 + n8) * 64 + (size_t)(p & 7) * 8;
+            const size_t o1 = yk1 + (size_t)(n8 * nb8) * 64;
+            const size_t o2 = yk2 + (size_t)n8 * 64;
+#ifdef PNCE_EXPERIMENTS
+            if (g.dbg == 1 && (hi.x | lo.x) != 0x7fc1u) continue;   // experiment: compute everything, store (almost) nothing
+#endif
             *reinterpret_cast<uint4*>(pr.k_hi + o1) = hi;
             *reinterpret_cast<uint4*>(pr.k2_hi + o2) = hi;
             if (x3) {
@@ -306,6 +325,9 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
             }
           } else {
             const size_t o = rowblob + (size_t)n8 * 1024;
+#ifdef PNCE_EXPERIMENTS
+            if (g.dbg == 1 && (hi.x | lo.x) != 0x7fc1u) continue;
+#endif
             *reinterpret_cast<uint4*>(pr.o_hi + o) = hi;
             if (x3) *reinterpret_cast<uint4*>(pr.o_lo + o) = lo;
           }

@@ -297,6 +297,7 @@ struct DebugKnobs {
   long long* trace = nullptr;
   cudaEvent_t post_gather_event = nullptr;   // recorded on the caller's stream between the gather and the loss kernel
   int loss_repeat = 0;       // n > 0: launch the loss kernel n extra times first (is its start-up cost cache coldness?)
+  int gemm_dbg = 0;          // head GEMM epilogue: 1 = no global stores, 2 = empty (where does a launch's time go?)
   long long loss_rot = 0;    // persistent loss kernel: 0 = a third of the CTAs start on light items (auto), -1 = plain heavy-first order, n > 0 = rotate by n
 };
 #ifdef PNCE_EXPERIMENTS
@@ -569,6 +570,7 @@ int pnce_debug_set(int key, long long value) {
     case 10: g_dbg.post_gather_event = reinterpret_cast<cudaEvent_t>(value); break;
     case 11: g_dbg.loss_rot = value; break;
     case 13: g_dbg.loss_repeat = (int)value; break;
+    case 14: g_dbg.gemm_dbg = (int)value; break;
     case 9: { int v = (int)value; PNCE_CUDA(cudaMemcpyToSymbol(g_dx_evict_last, &v, sizeof(int))); break; }
     default: return PNCE_ERR_ARG;
   }
@@ -1237,6 +1239,7 @@ static size_t carve_head(const pnce_layer_t* layers, int n_layers, int B, int nc
 }
 
 static int launch_gemm(GemmLaunch& g, cudaStream_t st) {
+  g.dbg = g_dbg.gemm_dbg;
   long long acc = 0;
   for (int i = 0; i < g.n; ++i) { g.start[i] = acc; acc += g.pr[i].tiles; }
   g.start[g.n] = acc;
