@@ -852,9 +852,14 @@ def config_lines(args, pn, layers, dev, math, peak):
     rows = []
     ppi = sum(min(args.patches, h * w) for _, h, w, _ in layers)
     for name, b, tdtype, elem in (("b1_fp32", 1, torch.float32, 4), ("b16_fp32", 16, torch.float32, 4),
-                                  (f"b{args.batch}_fp16", args.batch, torch.float16, 2)):
+                                  (f"b{args.batch}_fp16", args.batch, torch.float16, 2),
+                                  ("b1_fp32_channels_last", 1, torch.float32, 4), ("b16_fp32_channels_last", 16, torch.float32, 4),
+                                  (f"b{args.batch}_fp16_channels_last", args.batch, torch.float16, 2)):
         try:
             src, tgt = make_maps(layers, b, tdtype, dev, 99)
+            if name.endswith("channels_last"):                # the extension of DESIGN.md 4.7, not the reference's layout
+                src = [x.contiguous(memory_format=torch.channels_last) for x in src]
+                tgt = [x.contiguous(memory_format=torch.channels_last) for x in tgt]
             tgt = [t.requires_grad_() for t in tgt]
             crit = pn.PatchNCELoss(args.tau, args.patches, [0, 4, 8, 12, 13], math=math)
 

@@ -33,7 +33,8 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-DPNCE_EXPERIMENTS"] if EXPERIMENTS else []) + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("PNCE_NVCC_EXTRA", "").split() if EXPERIMENTS else []      # experiment builds only (e.g. -DPNCE_GP_PIPE=1)
+    cmd = [nvcc] + NVCC_FLAGS + (["-DPNCE_EXPERIMENTS"] if EXPERIMENTS else []) + extra + (["-Xptxas", "-v"] if verbose else []) + \
         ["-o", LIB + ".tmp", os.path.join(CSRC, "pnce_api.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
