@@ -258,7 +258,9 @@ struct WgradLaunch {
 };
 // (Measured and rejected: two stages of HALF a row tile each -- 64 rows of K, 16 + N/8 bulk copies of 1 KB per part because
 // the 64 rows of an 8-column slab are 1 KB inside the slab's 2 KB -- so that loads fly under the other half's MMAs:
-// 117 us vs 95 us at B=64; the bulk-copy engine is built for few large copies)
+// 117 us vs 95 us at B=64; the bulk-copy engine is built for few large copies, DESIGN.md 4.6.  Also rejected: the A tile
+// resident and two buffers for the N/2-column HALVES of the B tile (only the A tile loaded with nothing to hide behind):
+// 144 us vs 87 us -- an M=128 MMA costs ~130 cycles whatever N is, so halving N doubles the MMA time.)
 constexpr int kWgOffAlo = 32768, kWgOffBhi = 65536, kWgOffBlo = 131072, kWgOffOnes = 196608;
 constexpr int kWgSmemBytes = 196608 + 4096 + 256;
 
