@@ -23,11 +23,16 @@ for case in range(ncase):
         src = [x.relu() for x in src]; tgt = [x.relu() for x in tgt]
     pm._SIDE_STREAM_MIN_BYTES = 0 if rnd.random() < 0.5 else (1 << 30)
     crit = pn.PatchNCELoss(tau, p, math=math)
-    t = [x.cuda().requires_grad_() for x in tgt]
+    cl = rnd.random() < 0.5                                     # half the cases: torch.channels_last maps
+    p_eff = rnd.choice([p, p, 300, 700]) if cl else p           # and some of those with more than 256 patches
+    if p_eff != p:
+        p = p_eff; crit = pn.PatchNCELoss(tau, p, math=math)
+    mk = (lambda x: x.cuda().contiguous(memory_format=torch.channels_last)) if cl else (lambda x: x.cuda())
+    t = [mk(x).requires_grad_() for x in tgt]
     up = rnd.choice([1.0, 0.25, 1024.0])
     for rep in range(2):
         for x in t: x.grad = None
-        loss = crit([x.cuda() for x in src], t)
+        loss = crit([mk(x) for x in src], t)
         (loss * up).backward()
     ids = [i.cpu().numpy() for i in crit.last_patch_ids]
     want, _, gw = orc.patchnce_loss_and_grads_np([x.numpy() for x in src], [x.numpy() for x in tgt], ids, tau, upstream=up)
@@ -43,6 +48,6 @@ for case in range(ncase):
     tol_l, tol_g = (2e-5, 2e-4) if tau > 0.05 else (2e-4, 2e-3)
     worst['loss'] = max(worst['loss'], le); worst['grad'] = max(worst['grad'], ge)
     if not (le <= tol_l and ge <= tol_g) or not np.isfinite(le + ge):
-        print(f'MISMATCH case {case}: b={b} shapes={shapes} p={p} tau={tau} math={math} loss err {le:.2e} grad err {ge:.2e}')
+        print(f'MISMATCH case {case}: b={b} shapes={shapes} p={p} tau={tau} math={math} channels_last={cl} loss err {le:.2e} grad err {ge:.2e}')
 n = pn.poll_nonfinite_warnings(block=True)
 print(f'{ncase} cases done, worst loss err {worst["loss"]:.2e}, worst grad err {worst["grad"]:.2e}, guarded images {n}')
