@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
   struct Sh { uint64_t full, empty, dfull; uint32_t tmem_base; int dead; };
-  Sh* sh = reinterpret_cast<Sh*>(smem + kWgOffOnes + 4096);
+  Sh* sh = reinterpret_cast<Sh*>(smem + kWgOffOnes + 4096);      // (the 4 KB at kWgOffOnes held a tile of ones: see the bias note below)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int pi = 0;
   for (int i = 1; i < g.n; ++i)
@@ -282,13 +282,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
   const bool x3 = g.x3 != 0;
   volatile int* dead = &sh->dead;
   if (tid == 0) {
-    mbar_init(&sh->full, 1); mbar_init(&sh->empty, 1); mbar_init(&sh->dfull, 1);
+    // empty: the MMA thread's commit + one arrival per epilogue warp (they read the A tile for the bias sums)
+    mbar_init(&sh->full, 1); mbar_init(&sh->empty, 1 + 4); mbar_init(&sh->dfull, 1);
     sh->dead = 0;
     fence_barrier_init();
   }
-  // the bias operand: 16 "columns" x 128 rows of bf16 ones (any layout: all elements equal)
-  for (int k = tid; k < 4096 / 4; k += kTcThreads) reinterpret_cast<uint32_t*>(smem + kWgOffOnes)[k] = 0x3f803f80u;
-  fence_proxy_async_smem();
   if (warp == 1) tmem_alloc<512>(&sh->tmem_base);
   tc_fence_before();
   __syncthreads();
@@ -325,10 +323,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16(128, N, 1, 1);        // A and B both MN-major
-      const uint32_t idesc1 = idesc_bf16(128, 16, 1, 1);
       const uint32_t sa = smem_u32(smem), sal = smem_u32(smem + kWgOffAlo);
       const uint32_t sb = smem_u32(smem + kWgOffBhi), sbl = smem_u32(smem + kWgOffBlo);
-      const uint32_t so = smem_u32(smem + kWgOffOnes);
       bool ok = true;
       for (int t = t0; t < t1 && ok; ++t) {
         ok = mbar_wait(&sh->full, (uint32_t)(t - t0) & 1u, dead);
@@ -338,16 +334,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
           // MN-major: LBO = stride between 8-row K groups (128 B), SBO = between 8-column MN chunks (2048 B)
           const uint64_t a_hi = smem_desc(sa + ks * 256, 128, 2048);
           const uint64_t b_hi = smem_desc(sb + ks * 256, 128, 2048);
-          const uint64_t ones = smem_desc(so, 128, 256);
           const uint32_t acc = (t > t0 || ks) ? 1u : 0u;
           mma_bf16(tmem, a_hi, b_hi, idesc, acc);
-          mma_bf16(tmem + 256u, a_hi, ones, idesc1, acc);
           if (x3) {
             const uint64_t a_lo = smem_desc(sal + ks * 256, 128, 2048);
             const uint64_t b_lo = smem_desc(sbl + ks * 256, 128, 2048);
             mma_bf16(tmem, a_hi, b_lo, idesc, 1u);
             mma_bf16(tmem, a_lo, b_hi, idesc, 1u);
-            mma_bf16(tmem + 256u, a_lo, ones, idesc1, 1u);
           }
         }
         mma_commit(&sh->empty);
@@ -357,6 +350,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
   } else {
     const int q = warp & 3, i = q * 32 + lane;                // output row = column ih*128 + i of the A blob
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    // ---- bias gradient = column sums of the A tile, on the CUDA cores while the MMAs run.  (It used to be two extra MMAs
+    //      per 16 rows against a tile of ones, N = 16: an M = 128 MMA costs ~130 cycles whatever N is, so they were 16 of a
+    //      row tile's 40 MMAs.)  Thread <-> (8-column slab et >> 3, row et & 7 of every 8-row group): 16 + 16 LDS.128 per
+    //      row tile, 8 partial sums per thread, folded over the 8 rows of a group by shuffles at the end ----
+    const int et = tid - 64;
+    float bs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bs[k] = 0.f;
+    {
+      const unsigned char* arow = smem + (size_t)(et >> 3) * 2048 + (size_t)(et & 7) * 16;
+      for (int t = t0; t < t1; ++t) {
+        if (!mbar_wait(&sh->full, (uint32_t)(t - t0) & 1u, dead)) break;
+#pragma unroll 4
+        for (int rg = 0; rg < 16; ++rg) {
+          const uint4 h = *reinterpret_cast<const uint4*>(arow + rg * 128);
+          const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) {
+            bs[2 * k2] += __uint_as_float(hw[k2] << 16);
+            bs[2 * k2 + 1] += __uint_as_float(hw[k2] & 0xffff0000u);
+          }
+          if (x3) {
+            const uint4 l = *reinterpret_cast<const uint4*>(arow + kWgOffAlo + rg * 128);
+            const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              bs[2 * k2] += __uint_as_float(lw[k2] << 16);
+              bs[2 * k2 + 1] += __uint_as_float(lw[k2] & 0xffff0000u);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->empty);                 // this warp is done with the stage
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        bs[k] += __shfl_xor_sync(0xffffffffu, bs[k], 1);
+        bs[k] += __shfl_xor_sync(0xffffffffu, bs[k], 2);
+        bs[k] += __shfl_xor_sync(0xffffffffu, bs[k], 4);
+      }
+    }
     mbar_wait(&sh->dfull, 0u, dead);
     tc_fence_after();
     float* out = pr.partial + (((size_t)slab * nhalf + ih) * 128 + i) * N;
@@ -375,11 +409,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
         *reinterpret_cast<float4*>(out + ch * 32 + k4 * 4) = o;
       }
     }
-    {
-      uint32_t r[32];
-      tmem_ld32(trow + 256u, r);                              // only column 0 is meaningful; x32 keeps one ld shape
-      tmem_ld_wait();
-      pr.pbias[(size_t)slab * pr.NA + ih * 128 + i] = any ? __uint_as_float(r[0]) : 0.f;
+    if ((et & 7) == 0) {                                      // columns (et >> 3) * 8 ... + 7 of this CTA's 128
+      float* pb = pr.pbias + (size_t)slab * pr.NA + ih * 128 + (et >> 3) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pb[k] = any ? bs[k] : 0.f;
     }
     tc_fence_before();
   }
