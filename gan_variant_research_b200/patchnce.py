@@ -81,7 +81,11 @@ def draw_patch_ids(feat: torch.Tensor, num_patches: int) -> torch.Tensor:
 
 
 _ID_STREAMS = {}         # device index -> side stream the id draw + sort are issued on
-_SIDE_STREAM_MIN_BYTES = 1 << 30
+# The side-stream route costs ~120 us more HOST time per step than the in-line one (stream switch, two allocations on
+# the side pool, event hand-over, record_stream) and takes the 8 us id sort off the GPU's critical path: it pays once a step's
+# GPU time is comfortably above the host's ~0.3 ms, i.e. from ~2.5 GB of feature maps (B >= 25 at the CUT shapes in fp32;
+# at B = 16 -- 1.6 GB, 0.25 ms of GPU work -- it made the step host-bound: 0.31 vs 0.26 ms)
+_SIDE_STREAM_MIN_BYTES = 5 << 29
 
 
 def _id_stream(dev) -> "torch.cuda.Stream":
@@ -349,8 +353,8 @@ class _ShapePlan:
         if self.tc:
             _lib.check(lib.pnce_plan_bytes(self.fwd_layers, self.n, ctypes.byref(nbytes)), "pnce_plan_bytes")
             self.plan_bytes = nbytes.value
-        # ~1 GB of feature maps is where a step's GPU time passes the host's: from there on the id draw + sort go
-        # to a side stream, under whatever the GPU is still busy with (below, the stream switch only costs host time)
+        # bytes of feature maps: from _SIDE_STREAM_MIN_BYTES on, the id draw + sort go to a side stream, under whatever
+        # the GPU is still busy with (below, the stream switch only costs host time)
         elem = 4 if dtype == torch.float32 else 2
         self.big = 2 * elem * sum(b * c * h * w for b, c, h, w in shapes)
         self.fwd_lock, self.bwd_lock = threading.Lock(), threading.Lock()

@@ -13,7 +13,7 @@ from bench import LAYER_SETS, make_maps  # noqa: E402
 dev = torch.device("cuda", 0)
 layers = LAYER_SETS["b5"]
 out = {}
-for B in (1, 2, 4, 8, 16, 64):
+for B in (1, 8, 16, 24, 32, 64):
     src, tgt = make_maps(layers, B, torch.float32, dev, 1234)
     tgt = [t.requires_grad_() for t in tgt]
     crit = pn.PatchNCELoss(0.07, 256, [0, 4, 8, 12, 13])

@@ -21,7 +21,7 @@ for case in range(ncase):
     tgt = [torch.randn(b, *s, generator=g) for s in shapes]
     if rnd.random() < 0.3:
         src = [x.relu() for x in src]; tgt = [x.relu() for x in tgt]
-    pm._SIDE_STREAM_MIN_BYTES = 0 if rnd.random() < 0.5 else (1 << 30)
+    pm._SIDE_STREAM_MIN_BYTES = 0 if rnd.random() < 0.5 else (5 << 29)
     crit = pn.PatchNCELoss(tau, p, math=math)
     cl = rnd.random() < 0.5                                     # half the cases: torch.channels_last maps
     p_eff = rnd.choice([p, p, 300, 700]) if cl else p           # and some of those with more than 256 patches
