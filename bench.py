@@ -881,6 +881,45 @@ def config_lines(args, pn, layers, dev, math, peak):
             del src, tgt
         except Exception as e:  # noqa: BLE001
             rows.append({"config": name, "error": f"{type(e).__name__}: {e}"})
+    # the north-star shape (netF head, dim 256) at the batches the reference trains with: the fused head through autograd
+    # (patchnce_with_head + backward) and through the autograd-free entry (head_loss_and_grads)
+    for name, b in (("b1_fp32_head", 1), ("b16_fp32_head", 16)):
+        try:
+            src, tgt = make_maps(layers, b, torch.float32, dev, 99)
+            tgt = [t.requires_grad_() for t in tgt]
+            torch.manual_seed(3)
+            netF = pn.PatchSampleF(use_mlp=True, nc=256).to(dev)
+            netF.create_mlp(tgt)
+            hp = list(netF.parameters())
+
+            def hstep():
+                for t in tgt:
+                    t.grad = None
+                for q in hp:
+                    q.grad = None
+                loss, _ = pn.patchnce_with_head(netF, src, tgt, args.tau, args.patches, math=math)
+                loss.backward()
+
+            d_tgt = [t.detach() for t in tgt]
+
+            def dstep():
+                for q in hp:
+                    q.grad = None
+                pn.head_loss_and_grads(netF, src, d_tgt, args.tau, args.patches, math=math)
+
+            ms = timed_steps(hstep, 200, 10, 1, dev)
+            dms = timed_steps(dstep, 200, 10, 1, dev)
+            pb = algorithmic_bytes_per_image(layers, args.patches, 4) * b
+            rows.append({"config": name, "batch": b, "dtype": "float32", "nc": 256, "steps": 200, "ms_per_step": ms,
+                         "value": b * ppi / (ms * 1e-3), "unit": UNIT, "direct_ms_per_step": dms,
+                         "direct_value": b * ppi / (dms * 1e-3),
+                         "roofline_path": {"bound": "hbm", "achieved": pb / (ms * 1e-3) / 1e9, "peak": peak,
+                                           "unit": "GB/s", "frac": pb / (ms * 1e-3) / 1e9 / peak,
+                                           "frac_direct": pb / (dms * 1e-3) / 1e9 / peak},
+                         "note": "netF head Linear-ReLU-Linear on tcgen05, parity unpinned by the reference"})
+            del src, tgt, netF
+        except Exception as e:  # noqa: BLE001
+            rows.append({"config": name, "error": f"{type(e).__name__}: {e}"})
     torch.cuda.empty_cache()
     return rows
 

@@ -1089,6 +1089,85 @@ class _HeadCall:
         self.dp_group = dp_group      # process group whose ranks average the head gradients (None: single process)
 
 
+def _head_fwd(plan, nc, tgt, params):
+    """pnce_head_fwd_ex on one set of maps and head parameters -> (workspace, out, state for _head_bwd)."""
+    lib = _lib.load()
+    n = len(tgt)
+    src, ids = plan.src_feats, plan.ids_list
+    dev = tgt[0].device
+    batch = tgt[0].shape[0]
+    dtype = _DTYPES[tgt[0].dtype]
+    layers = _layer_array(src, tgt, None, ids)
+    heads = (_lib.PnceHead * n)()
+    for l in range(n):
+        h = heads[l]
+        h.w1, h.b1, h.w2, h.b2 = (params[4 * l].data_ptr(), params[4 * l + 1].data_ptr(),
+                                  params[4 * l + 2].data_ptr(), params[4 * l + 3].data_ptr())
+    layout = _lib.LAYOUT_NHWC if _is_nhwc(tgt[0]) else _lib.LAYOUT_NCHW      # _prepare_maps made the layers uniform
+    key = (dev.index, dtype, layout, nc, tuple(t.shape for t in tgt), tuple(layers[l].P for l in range(n)))
+    ws_bytes = _HEAD_WS_BYTES.get(key)
+    if ws_bytes is None:
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.pnce_head_workspace_bytes(layers, n, batch, nc, ctypes.byref(nbytes)),
+                   "pnce_head_workspace_bytes")
+        if len(_HEAD_WS_BYTES) > 256:
+            _HEAD_WS_BYTES.clear()
+        ws_bytes = _HEAD_WS_BYTES[key] = nbytes.value
+    with _on_device(dev):
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        out = torch.empty(1 + n, dtype=torch.float32, device=dev)
+        wq = _warn_queue(dev)
+        slot, flag_ptr = wq.acquire()
+        _lib.check(lib.pnce_head_fwd_ex(layers, heads, n, batch, dtype, layout, nc, plan.temperature, _MATH[plan.math],
+                                        ws.data_ptr(), ws_bytes, out.data_ptr(), flag_ptr or None,
+                                        _stream_ptr(dev)), "pnce_head_fwd")
+    return ws, out, (ws_bytes, layout, dev, batch, dtype, heads)
+
+
+def _head_bwd(plan, nc, tgt, params, ws, state, g, flat=None):
+    """pnce_head_bwd_ex: dense d tgt_feat per layer + every head gradient in ONE flat fp32 buffer (so that the
+    data-parallel all-reduce needs no packing) -> (grads, flat, sizes).  ``g``: fp32 scalar tensor on the device."""
+    lib = _lib.load()
+    ws_bytes, layout, dev, batch, dtype, heads = state
+    n = len(tgt)
+    group = plan.dp_group
+    with _on_device(dev):
+        grads = [torch.empty_like(t) for t in tgt]
+        sizes = [p.numel() for p in params]
+        if flat is None:
+            flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        layers = _layer_array(plan.src_feats, tgt, grads, plan.ids_list)
+        ptr, k = flat.data_ptr(), 0
+        for l in range(n):                                   # the weight pointers are those of the forward call
+            h = heads[l]
+            h.dw1 = ptr; ptr += 4 * sizes[k]
+            h.db1 = ptr; ptr += 4 * sizes[k + 1]
+            h.dw2 = ptr; ptr += 4 * sizes[k + 2]
+            h.db2 = ptr; ptr += 4 * sizes[k + 3]
+            k += 4
+        tail = (nc, _MATH[plan.math], ws.data_ptr(), ws_bytes, g.data_ptr(), _stream_ptr(dev))
+        head = (layers, heads, n, batch, dtype, layout)
+        if group is None:
+            _lib.check(lib.pnce_head_bwd_ex(*head, 3, *tail), "pnce_head_bwd")
+        else:
+            # data parallel: head gradients first, their all-reduce on a side stream UNDER the dense kernel
+            from . import dp
+            _lib.check(lib.pnce_head_bwd_ex(*head, 1, *tail), "pnce_head_bwd_params")
+            main = torch.cuda.current_stream(dev)
+            side = dp.comm_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dp.allreduce_flat_(flat, group, average=True)
+            flat.record_stream(side)
+            _lib.check(lib.pnce_head_bwd_ex(*head, 2, *tail), "pnce_head_bwd_dense")
+            main.wait_stream(side)
+    return grads, flat, sizes
+
+
+def _f32c(a):
+    return a if (a.dtype is torch.float32 and a.is_contiguous()) else a.detach().to(torch.float32).contiguous()
+
+
 class _FusedHeadPatchNCE(torch.autograd.Function):
     """All layers of the head path through the C ABI: pnce_head_fwd (prep, weight blobs, gather,
     2 GEMM launches, fused logits/CE/dY) and pnce_head_bwd (dH, dX, weight gradients, dense d tgt).
@@ -1096,80 +1175,45 @@ class _FusedHeadPatchNCE(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, plan, nc, *args):
-        lib = _lib.load()
         n = len(plan.ids_list)
-        tgt = [t.detach() for t in args[:n]]
-        params = [a.detach().to(torch.float32).contiguous() for a in args[n:]]
-        src, ids = plan.src_feats, plan.ids_list
-        dev = tgt[0].device
-        batch = tgt[0].shape[0]
-        dtype = _DTYPES[tgt[0].dtype]
-        layers = _layer_array(src, tgt, None, ids)
-        heads = (_lib.PnceHead * n)()
-        for l in range(n):
-            w1, b1, w2, b2 = params[4 * l:4 * l + 4]
-            heads[l].w1, heads[l].b1, heads[l].w2, heads[l].b2 = (w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
-                                                                  b2.data_ptr())
-        nbytes = ctypes.c_size_t(0)
-        _lib.check(lib.pnce_head_workspace_bytes(layers, n, batch, nc, ctypes.byref(nbytes)),
-                   "pnce_head_workspace_bytes")
-        with torch.cuda.device(dev):
-            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
-            out = torch.empty(1 + n, dtype=torch.float32, device=dev)
-            wq = _warn_queue(dev)
-            slot, flag_ptr = wq.acquire()
-            layout = _lib.LAYOUT_NHWC if _is_nhwc(tgt[0]) else _lib.LAYOUT_NCHW      # _prepare_maps made the layers uniform
-            _lib.check(lib.pnce_head_fwd_ex(layers, heads, n, batch, dtype, layout, nc, plan.temperature, _MATH[plan.math],
-                                            ws.data_ptr(), nbytes.value, out.data_ptr(), flag_ptr or None,
-                                            _stream_ptr(dev)), "pnce_head_fwd")
+        # inside Function.forward grad mode is off: the arguments are used as they are (no detach / view per tensor --
+        # with 4 parameters per layer those calls were a third of the step's host time at small batches)
+        tgt = list(args[:n])
+        params = [_f32c(a) for a in args[n:]]
+        ws, out, state = _head_fwd(plan, nc, tgt, params)
         ctx.save_for_backward(ws)            # freed with the graph, right after backward() (see _FusedPatchNCE)
-        ctx.plan, ctx.ws_bytes, ctx.nc, ctx.layout = plan, nbytes.value, nc, layout
+        ctx.plan, ctx.nc, ctx.state = plan, nc, state
         ctx.tgt_keep, ctx.params = tgt, params
         ctx.param_meta = [(a.shape, a.dtype) for a in args[n:]]
-        ctx.dev, ctx.batch, ctx.dtype = dev, batch, dtype
         ctx.layer_losses = out[1:]
         return out.narrow(0, 0, 1).reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
-        lib = _lib.load()
-        dev, n = ctx.dev, len(ctx.tgt_keep)
-        g = grad_out.detach().to(device=dev, dtype=torch.float32).contiguous()
-        group = ctx.plan.dp_group
-        with torch.cuda.device(dev):
-            grads = [torch.empty_like(t) for t in ctx.tgt_keep]
-            # every head gradient is a view of ONE flat fp32 buffer: the data-parallel all-reduce needs no packing
-            sizes = [p.numel() for p in ctx.params]
-            flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-            pgrads = [v.view_as(p) for v, p in zip(flat.split(sizes), ctx.params)]
-            layers = _layer_array(ctx.plan.src_feats, ctx.tgt_keep, grads, ctx.plan.ids_list)
-            heads = (_lib.PnceHead * n)()
-            for l in range(n):
-                w1, b1, w2, b2 = ctx.params[4 * l:4 * l + 4]
-                d1, e1, d2, e2 = pgrads[4 * l:4 * l + 4]
-                heads[l].w1, heads[l].b1, heads[l].w2, heads[l].b2 = (w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
-                                                                      b2.data_ptr())
-                heads[l].dw1, heads[l].db1, heads[l].dw2, heads[l].db2 = (d1.data_ptr(), e1.data_ptr(),
-                                                                          d2.data_ptr(), e2.data_ptr())
-            (ws,) = ctx.saved_tensors
-            tail = (ctx.nc, _MATH[ctx.plan.math], ws.data_ptr(), ctx.ws_bytes, g.data_ptr(), _stream_ptr(dev))
-            head = (layers, heads, n, ctx.batch, ctx.dtype, ctx.layout)
-            if group is None:
-                _lib.check(lib.pnce_head_bwd_ex(*head, 3, *tail), "pnce_head_bwd")
-            else:
-                # data parallel: head gradients first, their all-reduce on a side stream UNDER the dense kernel
-                from . import dp
-                _lib.check(lib.pnce_head_bwd_ex(*head, 1, *tail), "pnce_head_bwd_params")
-                main = torch.cuda.current_stream(dev)
-                side = dp.comm_stream(dev)
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    dp.allreduce_flat_(flat, group, average=True)
-                flat.record_stream(side)
-                _lib.check(lib.pnce_head_bwd_ex(*head, 2, *tail), "pnce_head_bwd_dense")
-                main.wait_stream(side)
-        pgrads = [pg.to(dt).reshape(shape) for pg, (shape, dt) in zip(pgrads, ctx.param_meta)]
+        dev = ctx.state[2]
+        g = grad_out
+        if g.dtype is not torch.float32 or g.device != dev or not g.is_contiguous():
+            g = g.detach().to(device=dev, dtype=torch.float32).contiguous()
+        (ws,) = ctx.saved_tensors
+        grads, flat, sizes = _head_bwd(ctx.plan, ctx.nc, ctx.tgt_keep, ctx.params, ws, ctx.state, g)
+        pgrads = [v.view(shape) if dt is torch.float32 else v.view(shape).to(dt)
+                  for v, (shape, dt) in zip(torch.split_with_sizes(flat, sizes), ctx.param_meta)]
         return (None, None, *grads, *pgrads)
+
+
+_HEAD_WS_BYTES = {}      # pnce_head_workspace_bytes per (device, dtype, layout, nc, map shapes, patch counts)
+
+
+def _head_params(netF, n):
+    """w1, b1, w2, b2 of mlp_0 .. mlp_{n-1}, read straight from the module dictionaries (nn.Sequential.__getitem__
+    and Module.__getattr__ cost ~50 us per step for five layers: more than the GPU needs for a B = 1 step)."""
+    params = []
+    mods = netF._modules
+    for l in range(n):
+        seq = mods[f"mlp_{l}"]._modules
+        p0, p2 = seq["0"]._parameters, seq["2"]._parameters
+        params += [p0["weight"], p0["bias"], p2["weight"], p2["bias"]]
+    return params
 
 
 def fused_head_supported(netF: "PatchSampleF", feats, num_patches) -> bool:
@@ -1209,6 +1253,13 @@ def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0
             l = rows_patchnce(q, k, temperature, num_patches, batch, math)
             total = l if total is None else total + l
         return total / len(feat_q), ids
+    plan, tgt, params, ids = _head_begin(netF, src_feats, tgt_feats, temperature, num_patches, patch_ids, math, dp_group)
+    loss = _FusedHeadPatchNCE.apply(plan, netF.nc, *tgt, *params)
+    return loss, ids
+
+
+def _head_begin(netF, src_feats, tgt_feats, temperature, num_patches, patch_ids, math, dp_group):
+    """Argument handling + id draw of one fused head call -> (plan, tgt maps, head parameters, ids)."""
     if not fused_head_supported(netF, tgt_feats, num_patches):
         raise RuntimeError("fused head: nc must be 128 or 256, num_patches <= 1024 and C <= 256")
     if not netF.mlp_init:
@@ -1220,17 +1271,65 @@ def patchnce_with_head(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0
         ids = draw_ids(tgt, num_patches)
     else:
         ids = [i.to(device=t.device, dtype=torch.int64).contiguous() for i, t in zip(patch_ids, tgt)]
-    params = []
-    for l in range(len(tgt)):
-        mlp = getattr(netF, f"mlp_{l}")
-        params += [mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias]
+    params = _head_params(netF, len(tgt))
     if dp_group is not None:
         from . import dp
         dp_group = dp.resolve_group(dp_group)          # None when not initialised or world size 1
     plan = _HeadCall(src, ids, temperature, math or DEFAULT_MATH, dp_group)
     _warn_queue(tgt[0].device).poll()
-    loss = _FusedHeadPatchNCE.apply(plan, netF.nc, *tgt, *params)
-    return loss, ids
+    return plan, tgt, params, ids
+
+
+def head_loss_and_grads(netF: "PatchSampleF", src_feats, tgt_feats, temperature=0.07, num_patches=256,
+                        patch_ids=None, math: Optional[str] = None, grad_output: Optional[torch.Tensor] = None,
+                        dp_group=None):
+    """``patchnce_with_head`` (fused path) and its complete backward in ONE call, without autograd -- the head-mode
+    counterpart of ``PatchNCELoss.loss_and_grads``.  Returns ``(loss, [d (grad_output * loss) / d tgt_feats[l]], ids)``
+    and ACCUMULATES the head gradients into ``p.grad`` of netF's parameters (assigned when ``p.grad is None``: views
+    of one flat fp32 buffer, already averaged over ``dp_group``), exactly what ``loss.backward(grad_output)`` leaves
+    there.  Same ids, kernels and values as the autograd route; no ``Function.apply``, no engine hand-off and no
+    ``AccumulateGrad`` per parameter (20 of them for five layers): at the batches the reference trains with, that
+    host work is longer than the GPU's.  For loops that drive the generator's backward themselves:
+    ``torch.autograd.backward(tgt_feats, grads)``."""
+    if (math or DEFAULT_MATH) == "simt_f32":
+        raise RuntimeError("head_loss_and_grads runs the tensor-core head only")
+    plan, tgt, params, ids = _head_begin(netF, src_feats, tgt_feats, temperature, num_patches, patch_ids, math, dp_group)
+    dev = tgt[0].device
+    with torch.no_grad():
+        tgt = [t.detach() for t in tgt]
+        w = [_f32c(p_) for p_ in params]
+        ws, out, state = _head_fwd(plan, netF.nc, tgt, w)
+        g = grad_output
+        if g is None:
+            g = _one(dev)
+        elif g.dtype is not torch.float32 or g.device != dev or not g.is_contiguous():
+            g = g.detach().to(device=dev, dtype=torch.float32).contiguous()
+        grads, flat, sizes = _head_bwd(plan, netF.nc, tgt, w, ws, state, g)
+        views = None
+        for k, p_ in enumerate(params):
+            if not p_.requires_grad:
+                continue
+            if views is None:
+                views = torch.split_with_sizes(flat, sizes)
+            v = views[k].view(p_.shape)
+            if p_.dtype is not torch.float32:
+                v = v.to(p_.dtype)
+            if p_.grad is None:
+                p_.grad = v
+            else:
+                p_.grad.add_(v)
+    return out[0], grads, ids
+
+
+_ONES = {}
+
+
+def _one(dev) -> torch.Tensor:
+    """A device-resident fp32 1.0 per device (the upstream gradient of a plain ``backward()``)."""
+    t = _ONES.get(dev.index)
+    if t is None:
+        t = _ONES[dev.index] = torch.ones((), dtype=torch.float32, device=dev)
+    return t
 
 
 def install_reference_shim(optimiser_side: bool = False, d_side: bool = False):

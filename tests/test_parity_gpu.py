@@ -826,3 +826,52 @@ def test_layers_of_mixed_dtype_and_batch_follow_the_reference_loop(pn, orc):
     assert loss.item() == pytest.approx(want, rel=2e-4)
     with pytest.raises(RuntimeError):
         pn.fused_patchnce([x.cuda() for x in src], t, ids[:2], 0.07)          # fewer id tensors than layers
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_head_loss_and_grads_equals_the_autograd_route(pn, nhwc):
+    """The autograd-free head entry returns / leaves in .grad what patchnce_with_head(...).backward(g) does, bit for bit
+    (same ids from the same generator state, same kernels), and accumulates into existing parameter gradients."""
+    g = torch.Generator().manual_seed(33)
+    shapes = [(32, 24, 24), (64, 16, 16), (128, 20, 20)]
+    mf = torch.channels_last if nhwc else torch.contiguous_format
+    src = [torch.randn(3, *s, generator=g).cuda().contiguous(memory_format=mf) for s in shapes]
+    tgt = [torch.randn(3, *s, generator=g).cuda().contiguous(memory_format=mf).requires_grad_() for s in shapes]
+    torch.manual_seed(2)
+    netF = pn.PatchSampleF(use_mlp=True, nc=256).cuda()
+    netF.create_mlp(tgt)
+    for p_ in netF.parameters():                       # non-zero biases, larger weights than the 0.02 init
+        p_.data.normal_(0.0, 0.1)
+    up = torch.tensor(1.75, device="cuda")
+    torch.manual_seed(9)
+    la, ids_a = pn.patchnce_with_head(netF, src, tgt, 0.07, 64)
+    la.backward(up)
+    after_a = torch.rand(3, device="cuda")
+    ref_p = [p_.grad.clone() for p_ in netF.parameters()]
+    for p_ in netF.parameters():
+        p_.grad = None
+    torch.manual_seed(9)
+    lb, grads, ids_b = pn.head_loss_and_grads(netF, src, [t.detach() for t in tgt], 0.07, 64, grad_output=up)
+    after_b = torch.rand(3, device="cuda")
+    assert la.item() == lb.item() and torch.equal(after_a, after_b)
+    assert all(torch.equal(a, b) for a, b in zip(ids_a, ids_b))
+    for t, gr in zip(tgt, grads):
+        assert gr.shape == t.shape and torch.equal(t.grad, gr)
+        assert gr.is_contiguous(memory_format=mf)
+    for p_, r in zip(netF.parameters(), ref_p):
+        assert p_.grad.shape == p_.shape and torch.equal(p_.grad, r)
+    # a second call accumulates into the existing gradients, like autograd
+    torch.manual_seed(9)
+    pn.head_loss_and_grads(netF, src, [t.detach() for t in tgt], 0.07, 64, grad_output=up)
+    for p_, r in zip(netF.parameters(), ref_p):
+        assert torch.allclose(p_.grad, 2 * r, rtol=1e-6, atol=0)
+    # unit upstream gradient when none is given; frozen parameters get no gradient
+    for p_ in netF.parameters():
+        p_.grad = None
+    netF.mlp_1[0].weight.requires_grad_(False)
+    torch.manual_seed(9)
+    lc, gc, _ = pn.head_loss_and_grads(netF, src, [t.detach() for t in tgt], 0.07, 64)
+    assert lc.item() == la.item() and netF.mlp_1[0].weight.grad is None
+    for a, b in zip(grads, gc):
+        assert torch.allclose(a, b * 1.75, rtol=1e-6, atol=1e-12)
