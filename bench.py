@@ -951,8 +951,21 @@ def module_split_line(args, pn, src, tgt, math, patches_per_image, steps=20):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+
+    def step_list():
+        for t in tgt:
+            t.grad = None
+        with torch.no_grad():
+            feat_k, ids = samp(src, args.patches, None)
+        feat_q, _ = samp(tgt, args.patches, ids)
+        crit(feat_q, feat_k, batch_size=batch).backward()
+
+    lms = timed_steps(step_list, steps, 3, 1, tgt[0].device)
     return {"ms_per_step": ms, "value": args.batch * patches_per_image / (ms * 1e-3), "unit": UNIT, "steps": steps,
-            "note": "PatchSampleF.forward(feats, num_patches, patch_ids) + per-layer PatchNCELoss(feat_q, feat_k)"}
+            "note": "PatchSampleF.forward(feats, num_patches, patch_ids) + per-layer PatchNCELoss(feat_q, feat_k)",
+            "list_form": {"ms_per_step": lms, "value": args.batch * patches_per_image / (lms * 1e-3), "unit": UNIT,
+                          "note": "the same composition with PatchNCELoss(feat_q_list, feat_k_list): every layer's rows "
+                                  "loss in one library call (pnce_rows_loss_multi_fwd_bwd)"}}
 
 
 def run_e2e(args, pn, crit, layers, tdtype, elem, dev, world, rank):

@@ -22,6 +22,7 @@ from .patchnce import (  # noqa: F401
     pinned_as_device,
     poll_nonfinite_warnings,
     rows_patchnce,
+    rows_patchnce_multi,
 )
 from .ema import EMA  # noqa: F401
 from .dside import DiffAugment, discriminator_hinge_loss, generator_hinge_loss  # noqa: F401
@@ -30,7 +31,7 @@ from .feature_reuse import EncoderFeatureCache, enable_encoder_feature_reuse  # 
 from .dp import GradReducer, allreduce_head_grads, broadcast_patch_ids, shard_batch  # noqa: F401
 
 __all__ = [
-    "PatchNCELoss", "PatchSampleF", "compute_patchnce_loss", "fused_patchnce", "rows_patchnce",
+    "PatchNCELoss", "PatchSampleF", "compute_patchnce_loss", "fused_patchnce", "rows_patchnce", "rows_patchnce_multi",
     "draw_patch_ids", "draw_patch_ids_all", "draw_ids", "pinned_as_device", "patch_count", "install_reference_shim", "poll_nonfinite_warnings",
     "DEFAULT_MATH", "patchnce_with_head", "head_loss_and_grads", "allreduce_head_grads", "broadcast_patch_ids", "shard_batch", "GradReducer", "EMA",
     "EncoderFeatureCache", "enable_encoder_feature_reuse", "FusedAdamStep", "amp_step_optimizer",

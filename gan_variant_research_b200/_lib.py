@@ -18,7 +18,8 @@ EXPORTS = [
     "pnce_abi_version", "pnce_status_string", "pnce_last_cuda_error", "pnce_workspace_bytes",
     "pnce_fwd", "pnce_bwd", "pnce_fwd_ex", "pnce_bwd_ex", "pnce_fwd_draw", "pnce_plan_ids_draw", "pnce_draw_ids", "pnce_plan_bytes", "pnce_plan_ids", "pnce_fwd_planned", "pnce_bwd_planned", "pnce_sample_fwd", "pnce_sample_bwd_workspace_bytes",
     "pnce_sample_bwd", "pnce_sample_multi_fwd", "pnce_sample_multi_bwd_workspace_bytes", "pnce_sample_multi_bwd",
-    "pnce_rows_loss_workspace_bytes", "pnce_rows_loss_fwd_bwd", "pnce_selftest_umma",
+    "pnce_rows_loss_workspace_bytes", "pnce_rows_loss_fwd_bwd", "pnce_rows_loss_multi_workspace_bytes", "pnce_rows_loss_multi_fwd_bwd",
+    "pnce_selftest_umma",
     "pnce_multi_chunk_elems", "pnce_multi_axpby", "pnce_amp_adam_scratch_floats", "pnce_amp_adam_step",
     "pnce_diffaug_scratch_floats", "pnce_diffaug", "pnce_hinge_fwd", "pnce_hinge_bwd",
     "pnce_netf_workspace_bytes", "pnce_netf_fwd", "pnce_netf_bwd",
@@ -40,6 +41,12 @@ class PnceSample(ctypes.Structure):
     _fields_ = [("feat", ctypes.c_void_p), ("ids", ctypes.c_void_p), ("rows", ctypes.c_void_p),
                 ("inv", ctypes.c_void_p), ("drows", ctypes.c_void_p), ("dfeat", ctypes.c_void_p),
                 ("C", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("P", ctypes.c_int32)]
+
+
+class PnceRows(ctypes.Structure):
+    """struct pnce_rows (include/pnce.h)."""
+    _fields_ = [("q", ctypes.c_void_p), ("k", ctypes.c_void_p), ("dq", ctypes.c_void_p),
+                ("P", ctypes.c_int32), ("D", ctypes.c_int32)]
 
 
 class PnceHead(ctypes.Structure):
@@ -90,6 +97,8 @@ def load():
     lib.pnce_sample_multi_bwd.argtypes = [ctypes.POINTER(PnceSample), i32, i32, i32, vp, sz, vp]
     lib.pnce_rows_loss_workspace_bytes.argtypes = [i32, i32, i32, ctypes.POINTER(sz)]
     lib.pnce_rows_loss_fwd_bwd.argtypes = [vp, vp, i32, i32, i32, f32, i32, vp, sz, vp, vp, vp, vp, vp]
+    lib.pnce_rows_loss_multi_workspace_bytes.argtypes = [ctypes.POINTER(PnceRows), i32, i32, ctypes.POINTER(sz)]
+    lib.pnce_rows_loss_multi_fwd_bwd.argtypes = [ctypes.POINTER(PnceRows), i32, i32, f32, i32, vp, sz, vp, vp, vp]
     lib.pnce_head_workspace_bytes.argtypes = [ctypes.POINTER(PnceLayer), i32, i32, i32, ctypes.POINTER(sz)]
     lib.pnce_head_fwd.argtypes = [ctypes.POINTER(PnceLayer), ctypes.POINTER(PnceHead), i32, i32, i32, i32, f32, i32,
                                   vp, sz, vp, vp, vp]

@@ -1136,6 +1136,95 @@ int pnce_rows_loss_fwd_bwd(const float* q, const float* k, int batch, int P, int
   return launch_loss_simt(p, st);
 }
 
+// every layer of a PatchSampleF output in one pack launch + one loss launch (tensor-core modes)
+static size_t carve_rows_multi_tc(const pnce_rows_t* rows, int n, int B, bool x3, void* ws, pnce::Params* out) {
+  using namespace pnce;
+  Carver cv(ws);
+  static thread_local Params p;
+  memset(&p, 0, sizeof(p));
+  p.n_layers = n; p.B = B; p.rows_mode = 1;
+  p.counter = cv.take<unsigned>(64);
+  p.lossimg = cv.take<float>((size_t)n * B);
+  p.valid = cv.take<int>((size_t)n * B);
+  for (int l = 0; l < n; ++l) {
+    LayerDev& L = p.L[l];
+    const int P = rows[l].P, D = rows[l].D;
+    L.C = D; L.P = P; L.HW = 1; L.nwords = 1;
+    L.ntiles = (P + kRowTile - 1) / kRowTile;
+    L.sorted = 1;
+    L.Cp = (D + 31) / 32 * 32;
+    L.Ppad = (P + 127) / 128 * 128;
+    L.nchunk = L.Cp / 32;
+    L.nparts = L.Ppad / 128;
+    L.dxpitch = L.Ppad;
+    const size_t blob = (size_t)B * L.Ppad * L.Cp;
+    L.qhi = cv.take<__nv_bfloat16>(blob);
+    L.khi = cv.take<__nv_bfloat16>(blob);
+    L.k2hi = cv.take<__nv_bfloat16>(blob);
+    if (x3) {
+      L.qlo = cv.take<__nv_bfloat16>(blob);
+      L.klo = cv.take<__nv_bfloat16>(blob);
+      L.k2lo = cv.take<__nv_bfloat16>(blob);
+    }
+    L.qss = cv.take<float>((size_t)B * L.nchunk * L.Ppad);
+    L.kss = cv.take<float>((size_t)B * L.nchunk * L.Ppad);
+    L.partial = cv.take<float>((size_t)B * 2);
+    L.qn = const_cast<float*>(rows[l].q);
+    L.kn = const_cast<float*>(rows[l].k);
+    L.dq_rows = rows[l].dq;
+  }
+  if (out) *out = p;
+  return align_up(cv.off, 256);
+}
+
+static int check_rows_multi(const pnce_rows_t* rows, int n, int batch) {
+  if (rows == nullptr || n < 1 || n > PNCE_MAX_LAYERS || batch < 1) return PNCE_ERR_ARG;
+  for (int l = 0; l < n; ++l) {
+    if (rows[l].P < 1 || rows[l].D < 1) return PNCE_ERR_ARG;
+    if (!rows_tc_ok(rows[l].P, rows[l].D)) return PNCE_ERR_UNSUPPORTED;
+  }
+  return PNCE_OK;
+}
+
+int pnce_rows_loss_multi_workspace_bytes(const pnce_rows_t* rows, int n_layers, int batch, size_t* bytes) {
+  if (bytes == nullptr) return PNCE_ERR_ARG;
+  int rc = check_rows_multi(rows, n_layers, batch);
+  if (rc != PNCE_OK) return rc;
+  *bytes = carve_rows_multi_tc(rows, n_layers, batch, true, nullptr, nullptr);
+  return PNCE_OK;
+}
+
+int pnce_rows_loss_multi_fwd_bwd(const pnce_rows_t* rows, int n_layers, int batch, float temperature, int math_mode,
+                                 void* ws, size_t ws_bytes, float* loss_out, int* nonfinite, void* stream) {
+  using namespace pnce;
+  int rc = check_rows_multi(rows, n_layers, batch);
+  if (rc != PNCE_OK) return rc;
+  if (!loss_out || !(temperature > 0.f)) return PNCE_ERR_ARG;
+  if (math_mode != PNCE_MATH_TC_BF16X3 && math_mode != PNCE_MATH_TC_BF16) return PNCE_ERR_UNSUPPORTED;
+  if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u)) return PNCE_ERR_WORKSPACE;
+  for (int l = 0; l < n_layers; ++l)
+    if (!rows[l].q || !rows[l].k || !rows[l].dq) return PNCE_ERR_ARG;
+  static thread_local Params t;
+  if (carve_rows_multi_tc(rows, n_layers, batch, math_mode == PNCE_MATH_TC_BF16X3, ws, &t) > ws_bytes)
+    return PNCE_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  t.math = math_mode;
+  t.tau = temperature;
+  t.loss_out = loss_out;
+  t.nonfinite = nonfinite;
+  t.b0 = 0; t.bn = batch;
+  PNCE_CUDA(cudaMemsetAsync(t.counter, 0, 2 * sizeof(unsigned), st));
+  long long most = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    const long long threads = 2ll * batch * t.L[l].Ppad * (t.L[l].Cp >> 3);
+    if (threads > most) most = threads;
+  }
+  const dim3 grid((unsigned)((most + kThreads - 1) / kThreads), (unsigned)n_layers);
+  k_rows_pack<<<grid, kThreads, 0, st>>>(t);
+  PNCE_CUDA(cudaGetLastError());
+  return launch_loss_tc(t, st);
+}
+
 // ---- netF head (tcgen05) ---------------------------------------------------------------------
 
 namespace pnce {

@@ -648,6 +648,9 @@ class PatchNCELoss(nn.Module):
     def forward(self, a, b, batch_size: Optional[int] = None):
         if isinstance(a, torch.Tensor) and a.dim() == 2:
             return rows_patchnce(a, b, self.temperature, self.num_patches, batch_size, self.math)
+        if not isinstance(a, torch.Tensor) and len(a) > 0 and a[0].dim() == 2:
+            # two lists of (B*P_l, D_l) rows (what PatchSampleF returns): every layer in one call, mean over layers
+            return rows_patchnce_multi(a, b, self.temperature, self.num_patches, batch_size, self.math)
         call, tgt, scale = self._begin(a, b)
         if call is None:
             return tgt                               # mixed layers: the per-layer composition already ran
@@ -879,33 +882,46 @@ class _NetFFn(torch.autograd.Function):
     def forward(ctx, nc, n, math, *args):
         lib = _lib.load()
         nhwc = all(_is_nhwc(a) for a in args[:n])
-        feats = [a.detach() if nhwc else a.detach().contiguous() for a in args[:n]]
+        # grad mode is off in here: maps and parameters are used as they are (per-tensor detach / to / contiguous calls
+        # were most of this function's host time)
+        feats = [a if (nhwc or a.is_contiguous()) else a.contiguous() for a in args[:n]]
         ids = list(args[n:2 * n])
-        params = [a.detach().to(torch.float32).contiguous() for a in args[2 * n:]]
+        params = [_f32c(a) for a in args[2 * n:]]
         dev = feats[0].device
         b = feats[0].shape[0]
         maps = (_lib.PnceSample * n)()
         heads = (_lib.PnceHead * n)()
         rows, invs = [], []
+        key = [dev.index, b, nc, nhwc]
         with _on_device(dev):
-            for l, (f, i) in enumerate(zip(feats, ids)):
+            for l in range(n):
+                f, i = feats[l], ids[l]
                 _, c, h, w = f.shape
                 p = i.numel()
                 r = torch.empty(b * p, nc, dtype=torch.float32, device=dev)
                 v = torch.empty(b * p, dtype=torch.float32, device=dev)
                 rows.append(r)
                 invs.append(v)
-                maps[l].feat, maps[l].ids, maps[l].rows, maps[l].inv = f.data_ptr(), i.data_ptr(), r.data_ptr(), v.data_ptr()
-                maps[l].C, maps[l].H, maps[l].W, maps[l].P = c, h, w, p
-                w1, b1, w2, b2 = params[4 * l:4 * l + 4]
-                heads[l].w1, heads[l].b1, heads[l].w2, heads[l].b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
-            nbytes = ctypes.c_size_t(0)
-            _lib.check(lib.pnce_netf_workspace_bytes(maps, n, b, nc, ctypes.byref(nbytes)), "pnce_netf_workspace_bytes")
-            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+                m = maps[l]
+                m.feat, m.ids, m.rows, m.inv = f.data_ptr(), i.data_ptr(), r.data_ptr(), v.data_ptr()
+                m.C, m.H, m.W, m.P = c, h, w, p
+                key += [c, h, w, p]
+                hd = heads[l]
+                hd.w1, hd.b1, hd.w2, hd.b2 = (params[4 * l].data_ptr(), params[4 * l + 1].data_ptr(),
+                                              params[4 * l + 2].data_ptr(), params[4 * l + 3].data_ptr())
+            key = tuple(key)
+            ws_bytes = _NETF_WS_BYTES.get(key)
+            if ws_bytes is None:
+                nbytes = ctypes.c_size_t(0)
+                _lib.check(lib.pnce_netf_workspace_bytes(maps, n, b, nc, ctypes.byref(nbytes)), "pnce_netf_workspace_bytes")
+                if len(_NETF_WS_BYTES) > 256:
+                    _NETF_WS_BYTES.clear()
+                ws_bytes = _NETF_WS_BYTES[key] = nbytes.value
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             layout = _lib.LAYOUT_NHWC if nhwc else _lib.LAYOUT_NCHW
             _lib.check(lib.pnce_netf_fwd(maps, heads, n, b, _DTYPES[feats[0].dtype], layout, nc, _MATH[math], ws.data_ptr(),
-                                         nbytes.value, _netf_status(dev).data_ptr(), _stream_ptr(dev)), "pnce_netf_fwd")
-        ctx.meta = (nc, n, math, b, dev, layout, nbytes.value, [(tuple(f.shape), f.dtype) for f in feats],
+                                         ws_bytes, _netf_status(dev).data_ptr(), _stream_ptr(dev)), "pnce_netf_fwd")
+        ctx.meta = (nc, n, math, b, dev, layout, ws_bytes, [(tuple(f.shape), f.dtype) for f in feats],
                     [(a.shape, a.dtype) for a in args[2 * n:]])
         ctx.feat_like = feats                    # layout / dtype of the dense gradients (no data is read in the backward)
         ctx.save_for_backward(ws, *ids, *rows, *invs, *params)
@@ -924,28 +940,37 @@ class _NetFFn(torch.autograd.Function):
             keep, dfeats = [], []
             sizes = [p.numel() for p in params]
             flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-            pgrads = [v.view_as(p) for v, p in zip(flat.split(sizes), params)]
+            ptr = flat.data_ptr()
             for l in range(n):
                 (_, c, h, w), _dt = fmeta[l]
                 p = ids[l].numel()
                 g = drows[l]
-                g = (torch.zeros(b * p, nc, dtype=torch.float32, device=dev) if g is None
-                     else g.detach().to(torch.float32).contiguous())
+                if g is None:
+                    g = torch.zeros(b * p, nc, dtype=torch.float32, device=dev)
+                elif g.dtype is not torch.float32 or not g.is_contiguous():
+                    g = g.detach().to(torch.float32).contiguous()
                 keep.append(g)
                 d = torch.empty_like(ctx.feat_like[l]) if need_dense else None
                 dfeats.append(d)
-                maps[l].ids, maps[l].rows, maps[l].inv, maps[l].drows = (ids[l].data_ptr(), rows[l].data_ptr(),
-                                                                         invs[l].data_ptr(), g.data_ptr())
-                maps[l].dfeat = d.data_ptr() if d is not None else None
-                maps[l].C, maps[l].H, maps[l].W, maps[l].P = c, h, w, p
-                w1, b1, w2, b2 = params[4 * l:4 * l + 4]
-                d1, e1, d2, e2 = pgrads[4 * l:4 * l + 4]
-                heads[l].w1, heads[l].b1, heads[l].w2, heads[l].b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
-                heads[l].dw1, heads[l].db1, heads[l].dw2, heads[l].db2 = d1.data_ptr(), e1.data_ptr(), d2.data_ptr(), e2.data_ptr()
+                m = maps[l]
+                m.ids, m.rows, m.inv, m.drows = ids[l].data_ptr(), rows[l].data_ptr(), invs[l].data_ptr(), g.data_ptr()
+                m.dfeat = d.data_ptr() if d is not None else None
+                m.C, m.H, m.W, m.P = c, h, w, p
+                hd = heads[l]
+                hd.w1, hd.b1, hd.w2, hd.b2 = (params[4 * l].data_ptr(), params[4 * l + 1].data_ptr(),
+                                              params[4 * l + 2].data_ptr(), params[4 * l + 3].data_ptr())
+                hd.dw1 = ptr; ptr += 4 * sizes[4 * l]
+                hd.db1 = ptr; ptr += 4 * sizes[4 * l + 1]
+                hd.dw2 = ptr; ptr += 4 * sizes[4 * l + 2]
+                hd.db2 = ptr; ptr += 4 * sizes[4 * l + 3]
             _lib.check(lib.pnce_netf_bwd(maps, heads, n, b, _DTYPES[fmeta[0][1]], layout, nc, _MATH[math], ws.data_ptr(),
                                          ws_bytes, _netf_status(dev).data_ptr(), _stream_ptr(dev)), "pnce_netf_bwd")
-        pgrads = [pg.to(dt).reshape(shape) for pg, (shape, dt) in zip(pgrads, pmeta)]
+        pgrads = [v.view(shape) if dt is torch.float32 else v.view(shape).to(dt)
+                  for v, (shape, dt) in zip(torch.split_with_sizes(flat, sizes), pmeta)]
         return (None, None, None, *dfeats, *([None] * n), *pgrads)
+
+
+_NETF_WS_BYTES = {}      # pnce_netf_workspace_bytes per (device, batch, nc, layout, map geometry, patch counts)
 
 
 def netf_fused_supported(use_mlp, nc, feats, ids, math) -> bool:
@@ -994,6 +1019,90 @@ class _RowsLossFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         (dq,) = ctx.saved_tensors
         return (dq * grad_out).to(ctx.q_dtype), None, None, None, None, None
+
+
+class _RowsLossMultiFn(torch.autograd.Function):
+    """``mean_l PatchNCELoss(feat_q[l], feat_k[l])`` for every layer of a ``PatchSampleF`` output in ONE call of the
+    library (pnce_rows_loss_multi_fwd_bwd: one pack launch, one tcgen05 loss launch).  Inputs: batch, temperature, math,
+    n, the n query row tensors, the n (detached) key row tensors."""
+
+    @staticmethod
+    def forward(ctx, batch, temperature, math, n, *args):
+        lib = _lib.load()
+        qs = [_f32c(a) for a in args[:n]]
+        ks = [_f32c(a) for a in args[n:]]
+        dev = qs[0].device
+        rows = (_lib.PnceRows * n)()
+        key = ["multi", batch]
+        with _on_device(dev):
+            dqs = [torch.empty_like(q) for q in qs]
+            for l in range(n):
+                r = rows[l]
+                r.q, r.k, r.dq = qs[l].data_ptr(), ks[l].data_ptr(), dqs[l].data_ptr()
+                r.P, r.D = qs[l].shape[0] // batch, qs[l].shape[1]
+                key += [r.P, r.D]
+            key = tuple(key)
+            ws_bytes = _ROWS_WS_BYTES.get(key)
+            if ws_bytes is None:
+                nbytes = ctypes.c_size_t(0)
+                _lib.check(lib.pnce_rows_loss_multi_workspace_bytes(rows, n, batch, ctypes.byref(nbytes)),
+                           "pnce_rows_loss_multi_workspace_bytes")
+                ws_bytes = _ROWS_WS_BYTES[key] = nbytes.value
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            out = torch.empty(1 + n, dtype=torch.float32, device=dev)
+            slot, flag_ptr = _warn_queue(dev).acquire()
+            _lib.check(lib.pnce_rows_loss_multi_fwd_bwd(rows, n, batch, temperature, _MATH[math], ws.data_ptr(), ws_bytes,
+                                                        out.data_ptr(), flag_ptr or None, _stream_ptr(dev)),
+                       "pnce_rows_loss_multi_fwd_bwd")
+        ctx.save_for_backward(*dqs)
+        ctx.q_dtypes = [a.dtype for a in args[:n]]
+        ctx.layer_losses = out[1:]
+        return out.narrow(0, 0, 1).reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dqs = torch._foreach_mul(list(ctx.saved_tensors), grad_out)            # one launch for every layer
+        dqs = [d if d.dtype is dt else d.to(dt) for d, dt in zip(dqs, ctx.q_dtypes)]
+        return (None, None, None, None, *dqs, *([None] * len(dqs)))
+
+
+def rows_patchnce_multi(feat_q, feat_k, temperature=0.07, num_patches=256, batch_size=None, math=None):
+    """``mean_l PatchNCELoss(feat_q[l], feat_k[l])`` over two LISTS of row tensors (one (B*P_l, D_l) pair per layer, as
+    ``PatchSampleF`` returns them) -- upstream CUT's ``for f_q, f_k in zip(feat_q, feat_k): total += crit(f_q, f_k)``
+    followed by ``/ n_layers``, as one call of the library when every layer fits the tensor-core kernel (P, D <= 256);
+    other shapes take the per-layer calls."""
+    feat_q, feat_k = list(feat_q), list(feat_k)
+    n = len(feat_q)
+    if n == 0 or n != len(feat_k):
+        raise RuntimeError("feat_q and feat_k must be two lists of the same, non-zero length")
+    math = math or DEFAULT_MATH
+    batches = []
+    for q, k in zip(feat_q, feat_k):
+        _require_cuda(q, "feat_q")
+        _require_cuda(k, "feat_k")
+        if q.shape != k.shape or q.dim() != 2:
+            raise RuntimeError("feat_q and feat_k must both be (B*P, D)")
+        rows = q.shape[0]
+        if batch_size is None:
+            p = min(int(num_patches), rows)
+            if rows % p:
+                raise RuntimeError(f"{rows} rows are not a multiple of num_patches={p}; pass batch_size")
+            batches.append(rows // p)
+        else:
+            if rows % batch_size:
+                raise RuntimeError(f"{rows} rows are not a multiple of batch_size={batch_size}")
+            batches.append(int(batch_size))
+    b0, dev = batches[0], feat_q[0].device
+    fused = (math != "simt_f32" and n <= _lib.MAX_LAYERS and all(b == b0 for b in batches)
+             and all(q.device == dev and q.shape[0] // b0 <= 256 and q.shape[1] <= 256 for q in feat_q))
+    if not fused:
+        total = None
+        for q, k, b in zip(feat_q, feat_k, batches):
+            l = rows_patchnce(q, k, temperature, num_patches, b, math)
+            total = l if total is None else total + l
+        return total / n
+    ks = [k.detach() if k.requires_grad else k for k in feat_k]          # upstream CUT and the reference (:142) detach k
+    return _RowsLossMultiFn.apply(b0, float(temperature), math, n, *feat_q, *ks)
 
 
 def rows_patchnce(feat_q, feat_k, temperature=0.07, num_patches=256, batch_size=None, math=None):
@@ -1059,10 +1168,7 @@ class PatchSampleF(nn.Module):
             # the whole head in libpnce, on the tensor cores: gather -> Linear -> ReLU -> Linear -> normalise (and, through
             # autograd, d feat and the weight gradients); other shapes take the composition below (gather in libpnce,
             # the two Linear layers in ATen)
-            params = []
-            for l in range(len(feats)):
-                mlp = getattr(self, f"mlp_{l}")
-                params += [mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias]
+            params = _head_params(self, len(feats))
             return list(_NetFFn.apply(self.nc, len(feats), math, *feats, *return_ids, *params)), return_ids
         same = all(f.shape[0] == feats[0].shape[0] and f.dtype == feats[0].dtype and f.device == feats[0].device
                    for f in feats)

@@ -168,6 +168,22 @@ int pnce_rows_loss_fwd_bwd(const float* dev_q, const float* dev_k, int batch, in
                            size_t workspace_bytes, float* dev_loss_out, int* dev_nonfinite,
                            float* dev_dq_out, float* dev_dk_out, void* stream);
 
+/* The same loss for EVERY layer of a PatchSampleF output in one call (upstream CUT loops `crit(f_q, f_k)` over the
+ * layers and averages: one pack launch + one tcgen05 loss launch instead of one pair per layer, and the light layers
+ * fill the SMs the heavy ones leave idle).  loss_out[0] = mean over layers, loss_out[1 + l] = layer l;
+ * rows[l].dq = d loss_out[0] / d q_l for unit upstream (the 1/n_layers factor included).  Tensor-core modes only,
+ * P <= 256 and D <= 256 for every layer (PNCE_ERR_UNSUPPORTED otherwise: call the per-layer entry).   patchnce_cut.py:36-40, :83-103 */
+typedef struct pnce_rows {
+  const float* q;     /* (B*P, D) fp32 rows, grouped per image, already L2-normalised */
+  const float* k;     /* (B*P, D) fp32 keys (no gradient: the reference detaches them, :142) */
+  float*       dq;    /* (B*P, D) fp32, written */
+  int32_t      P, D;
+} pnce_rows_t;
+int pnce_rows_loss_multi_workspace_bytes(const pnce_rows_t* rows, int n_layers, int batch, size_t* bytes);
+int pnce_rows_loss_multi_fwd_bwd(const pnce_rows_t* rows, int n_layers, int batch, float temperature, int math_mode,
+                                 void* dev_workspace, size_t workspace_bytes, float* dev_loss_out, int* dev_nonfinite,
+                                 void* stream);
+
 /* All maps of one PatchSampleF call in ONE launch each way (the per-map entry points above cost a launch per
  * layer and leave the GPU half empty on the small layers): forward reads feat / ids and writes rows (and inv,
  * NULL for all layers = raw patches); backward reads drows / rows / inv / ids and writes dfeat densely.   */

@@ -335,6 +335,52 @@ def test_module_split_composes_to_the_reference(pn):
         assert_grad_close(tt.grad.cpu().numpy(), g, 1e-4, f"layer {i}", ids=ids[i])
 
 
+def test_module_split_list_form_is_one_call_and_composes_to_the_reference(pn):
+    """PatchNCELoss(feat_q_list, feat_k_list) -- every layer of PatchSampleF's output in ONE library call -- equals the
+    per-layer loop / L on the reference-frozen fixture, loss and dense gradients; a layer outside the tensor-core
+    envelope (D > 256) sends the whole list through the per-layer calls with the same result."""
+    d, src, tgt, ids, grads = load_small(os.path.join(HERE, "golden", "small_ragged.npz"))
+    t = [dev(x).requires_grad_() for x in tgt]
+    s = [dev(x) for x in src]
+    idd = [dev(i) for i in ids]
+    sampler, crit = pn.PatchSampleF(), pn.PatchNCELoss(0.07, 64)
+    fq, _ = sampler(t, 64, idd)
+    with torch.no_grad():
+        fk, _ = sampler(s, 64, idd)
+    loss = crit(fq, fk, batch_size=3)
+    (loss * 3.0).backward()
+    assert loss.item() == pytest.approx(float(d["loss"]), rel=2e-5)
+    for i, (tt, g) in enumerate(zip(t, grads)):
+        assert_grad_close(tt.grad.cpu().numpy() / 3.0, g, 1e-4, f"layer {i}", ids=ids[i])
+    # the same rows through the per-layer calls
+    q2 = [q.detach().clone().requires_grad_() for q in fq]
+    total = 0.0
+    for q, k in zip(q2, fk):
+        total = total + crit(q, k, batch_size=3)
+    per_layer = total / len(q2)
+    per_layer.backward()
+    q3 = [q.detach().clone().requires_grad_() for q in fq]
+    fused = pn.rows_patchnce_multi(q3, fk, 0.07, 64, batch_size=3)
+    fused.backward()
+    assert fused.item() == pytest.approx(per_layer.item(), rel=1e-6)
+    for a, b in zip(q3, q2):
+        torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-9)
+    # one launch of each kernel for the whole list
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        pn.rows_patchnce_multi([q.detach() for q in fq], fk, 0.07, 64, batch_size=3)
+        torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages() if "pnce::" in e.key for _ in range(e.count)]
+    assert sum("k_rows_pack" in n for n in names) == 1 and sum("k_loss_tc" in n for n in names) == 1, names
+    # a wide layer (D = 320) is outside the envelope: per-layer route, same numbers as calling it layer by layer
+    g = torch.Generator().manual_seed(5)
+    wide_q = torch.nn.functional.normalize(torch.randn(3 * 64, 320, generator=g), dim=1).cuda()
+    wide_k = torch.nn.functional.normalize(torch.randn(3 * 64, 320, generator=g), dim=1).cuda()
+    mixed = pn.rows_patchnce_multi([fq[0].detach(), wide_q], [fk[0], wide_k], 0.07, 64, batch_size=3)
+    want = (pn.rows_patchnce(fq[0].detach(), fk[0], 0.07, 64, 3) + pn.rows_patchnce(wide_q, wide_k, 0.07, 64, 3)) / 2
+    assert mixed.item() == pytest.approx(want.item(), rel=1e-6)
+
+
 def test_rows_loss_matches_torch(pn):
     g = torch.Generator().manual_seed(41)
     b, p, dd = 3, 100, 48
