@@ -408,6 +408,25 @@ def main():
     }
     if pinned is not None:
         out["host_cores_per_rank"] = pinned
+    # where the dense gradients live: compressible device memory (csrc/comp_alloc.cuh) when the device grants it -- said
+    # in the line, with the same step on default-pool memory beside it (timed after the headline region, same maps)
+    grads_compressed = all(pn.gradient_is_compressed(t.grad) for t in tgt if t.grad is not None)
+    out["config"]["grad_memory"] = ("compressible (cuMemCreate CU_MEM_ALLOCATION_COMP_GENERIC via a torch MemPool: B200 L2/HBM "
+                                    "compute-data compression; PNCE_GRAD_COMPRESSION=0 turns it off)" if grads_compressed
+                                    else "default pool")
+    if grads_compressed:
+        if dense_name == "k_dense_flat" and ncu_traffic("k_dense_flat_compressible", B, elem) is not None:
+            roof["traffic"] = ncu_traffic("k_dense_flat_compressible", B, elem)
+        roof["note"] += ("; the gradients are in compressible memory: the zero lines are compressed between L2 and HBM, so "
+                         "DRAM traffic (ncu) is BELOW the algorithmic bytes")
+        pn.set_gradient_compression(False)
+        pms = timed_steps(step, min(args.steps, 50), 3, world, dev)
+        pn.set_gradient_compression(True)
+        for _ in range(3):
+            step()
+        out["plain_alloc"] = {"ms_per_step": pms, "value": world * B * patches_per_image / (pms * 1e-3), "unit": UNIT,
+                              "roofline_path_frac": path_bytes / (pms * 1e-3) / 1e9 / peak,
+                              "note": "the same step with the dense gradients in torch's default pool (no compression)"}
     if rank == 0:
         # distribution of the per-step device time inside the timed region (ms_per_step is its mean): a handful of
         # slow steps means the host stalled (a busy node), a uniform shift means the kernels themselves moved

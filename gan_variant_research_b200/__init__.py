@@ -15,6 +15,7 @@ from .patchnce import (  # noqa: F401
     draw_ids,
     fused_head_supported,
     fused_patchnce,
+    gradient_is_compressed,
     head_loss_and_grads,
     install_reference_shim,
     patch_count,
@@ -23,6 +24,7 @@ from .patchnce import (  # noqa: F401
     poll_nonfinite_warnings,
     rows_patchnce,
     rows_patchnce_multi,
+    set_gradient_compression,
 )
 from .ema import EMA  # noqa: F401
 from .dside import DiffAugment, discriminator_hinge_loss, generator_hinge_loss  # noqa: F401
@@ -33,7 +35,7 @@ from .dp import GradReducer, allreduce_head_grads, broadcast_patch_ids, shard_ba
 __all__ = [
     "PatchNCELoss", "PatchSampleF", "compute_patchnce_loss", "fused_patchnce", "rows_patchnce", "rows_patchnce_multi",
     "draw_patch_ids", "draw_patch_ids_all", "draw_ids", "pinned_as_device", "patch_count", "install_reference_shim", "poll_nonfinite_warnings",
-    "DEFAULT_MATH", "patchnce_with_head", "head_loss_and_grads", "allreduce_head_grads", "broadcast_patch_ids", "shard_batch", "GradReducer", "EMA",
+    "DEFAULT_MATH", "patchnce_with_head", "head_loss_and_grads", "set_gradient_compression", "gradient_is_compressed", "allreduce_head_grads", "broadcast_patch_ids", "shard_batch", "GradReducer", "EMA",
     "EncoderFeatureCache", "enable_encoder_feature_reuse", "FusedAdamStep", "amp_step_optimizer",
     "DiffAugment", "discriminator_hinge_loss", "generator_hinge_loss",
 ]

@@ -19,7 +19,7 @@ EXPORTS = [
     "pnce_fwd", "pnce_bwd", "pnce_fwd_ex", "pnce_bwd_ex", "pnce_fwd_draw", "pnce_plan_ids_draw", "pnce_draw_ids", "pnce_plan_bytes", "pnce_plan_ids", "pnce_fwd_planned", "pnce_bwd_planned", "pnce_sample_fwd", "pnce_sample_bwd_workspace_bytes",
     "pnce_sample_bwd", "pnce_sample_multi_fwd", "pnce_sample_multi_bwd_workspace_bytes", "pnce_sample_multi_bwd",
     "pnce_rows_loss_workspace_bytes", "pnce_rows_loss_fwd_bwd", "pnce_rows_loss_multi_workspace_bytes", "pnce_rows_loss_multi_fwd_bwd",
-    "pnce_selftest_umma",
+    "pnce_selftest_umma", "pnce_comp_supported", "pnce_comp_alloc", "pnce_comp_free", "pnce_comp_is_compressed",
     "pnce_multi_chunk_elems", "pnce_multi_axpby", "pnce_amp_adam_scratch_floats", "pnce_amp_adam_step",
     "pnce_diffaug_scratch_floats", "pnce_diffaug", "pnce_hinge_fwd", "pnce_hinge_bwd",
     "pnce_netf_workspace_bytes", "pnce_netf_fwd", "pnce_netf_bwd",
@@ -122,9 +122,15 @@ def load():
     lib.pnce_hinge_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
     u32 = ctypes.c_uint
     lib.pnce_selftest_umma.argtypes = [vp, sz, vp, sz, u32, u32, u32, u32, u32, u32, i32, i32, i32, vp, vp, vp]
+    lib.pnce_comp_supported.argtypes = [i32]
+    lib.pnce_comp_alloc.argtypes = [ctypes.c_ssize_t, i32, vp]
+    lib.pnce_comp_alloc.restype = vp
+    lib.pnce_comp_free.argtypes = [vp, ctypes.c_ssize_t, i32, vp]
+    lib.pnce_comp_free.restype = None
+    lib.pnce_comp_is_compressed.argtypes = [vp]
     for name in EXPORTS:
         if name not in ("pnce_status_string", "pnce_last_cuda_error", "pnce_amp_adam_scratch_floats",
-                        "pnce_diffaug_scratch_floats"):
+                        "pnce_diffaug_scratch_floats", "pnce_comp_alloc", "pnce_comp_free"):
             getattr(lib, name).restype = i32
     lib.pnce_amp_adam_scratch_floats.restype = sz
     lib.pnce_diffaug_scratch_floats.restype = sz

@@ -11,7 +11,7 @@ EXPERIMENTS = os.environ.get("PNCE_EXPERIMENTS", "") not in ("", "0")
 LIB = os.path.join(HERE, "libpnce_exp.so" if EXPERIMENTS else "libpnce.so")
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-exceptions",      # plain C ABI: no libstdc++ at run time
     "-Xlinker", "--version-script=" + os.path.join(CSRC, "pnce.map"),
 ]
 
@@ -25,7 +25,7 @@ def is_stale():
         return True
     t = os.path.getmtime(LIB)
     hdr = os.path.join(HERE, "..", "include", "pnce.h")
-    return any(os.path.getmtime(s) > t for s in sources() + [hdr])
+    return any(os.path.getmtime(s) > t for s in sources() + [hdr, os.path.abspath(__file__)])
 
 
 def build(force=False, verbose=False):

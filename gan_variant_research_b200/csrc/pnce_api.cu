@@ -19,6 +19,7 @@
 #include "multi_tensor.cuh"
 #include "sample_bwd.cuh"
 #include "dside.cuh"
+#include "comp_alloc.cuh"
 
 namespace pnce {
 

@@ -319,6 +319,19 @@ int pnce_hinge_fwd(const void* const* real, const void* const* fake, const long 
 int pnce_hinge_bwd(const void* const* real, const void* const* fake, void* const* dreal, void* const* dfake,
                    const long long* numel, int scales, int mode, int dtype, const float* dev_grad_out, void* stream);
 
+/* ---- compressible device memory for the dense gradients (B200 L2 / HBM compute-data compression) ---------------
+ * d tgt_feat (row a11: the `zeros` + `index_put_` autograd materialises, patchnce_cut.py:66-74 backward) is a zero fill
+ * with a sampled float in a few per cent of its lines; in memory created with CU_MEM_ALLOCATION_COMP_GENERIC the dense
+ * kernels write it ~12 % faster and the generator's backward reads it ~40 % faster.  pnce_comp_alloc / pnce_comp_free
+ * have the signature torch.cuda.memory.CUDAPluggableAllocator binds (alloc(size, device, stream) -> ptr or NULL;
+ * free(ptr, size, device, stream)); a caller without torch maps them onto its own allocator hooks.  Memory comes from
+ * cuMemCreate / cuMemMap (plain VMM memory when the device refuses compression); every pointer handed out must come
+ * back through pnce_comp_free.                                                                                      */
+int   pnce_comp_supported(int device);
+void* pnce_comp_alloc(ptrdiff_t size, int device, void* stream);
+void  pnce_comp_free(void* ptr, ptrdiff_t size, int device, void* stream);
+int   pnce_comp_is_compressed(const void* ptr);
+
 /* Library self-test of the tcgen05 building blocks (bulk copy -> smem, tcgen05.mma with a K-major
  * or MN-major B operand, commit, tcgen05.ld): D(128 x n) = A(128 x k) * B on pre-tiled bf16 operand
  * blobs with host-supplied descriptor strides.  *dev_err is set to 1 on a protocol timeout.       */

@@ -921,3 +921,62 @@ def test_head_loss_and_grads_equals_the_autograd_route(pn, nhwc):
     assert lc.item() == la.item() and netF.mlp_1[0].weight.grad is None
     for a, b in zip(grads, gc):
         assert torch.allclose(a, b * 1.75, rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_dense_gradients_in_compressible_memory_are_the_same_gradients(pn):
+    """The dense gradients of large calls are allocated from a MemPool backed by the library's compressible allocator
+    (csrc/comp_alloc.cuh).  Only the allocation differs: values are bit-identical to the default pool's, on the fused path
+    (NCHW and channels-last), the fused head and the module-split backward; tensors behave like any other (clone, cpu,
+    in-place math, freeing and re-use across steps)."""
+    from gan_variant_research_b200 import _lib, patchnce as pm
+    dev_ = torch.device("cuda", torch.cuda.current_device())
+    supported = _lib.load().pnce_comp_supported(dev_.index) == 1
+    g = torch.Generator().manual_seed(77)
+    shapes = [(32, 40, 40), (64, 16, 16), (128, 24, 24)]
+    src = [torch.randn(4, *s, generator=g).cuda() for s in shapes]
+    tgt0 = [torch.randn(4, *s, generator=g).cuda() for s in shapes]
+    old = (pm._GRAD_COMPRESSION, pm._GRAD_COMPRESSION_MIN_BYTES)
+    try:
+        results = {}
+        for on in (False, True):
+            pn.set_gradient_compression(on, min_bytes=0)
+            for layout in ("nchw", "nhwc"):
+                mf = torch.channels_last if layout == "nhwc" else torch.contiguous_format
+                s_ = [x.clone(memory_format=mf) for x in src]
+                for rep in range(3):                               # blocks are freed and re-used across steps
+                    t_ = [x.detach().clone(memory_format=mf).requires_grad_() for x in tgt0]
+                    torch.manual_seed(5)
+                    loss = pn.PatchNCELoss(0.07, 128)(s_, t_)
+                    loss.backward(torch.tensor(3.0, device="cuda"))
+                grads = [t.grad for t in t_]
+                if on and supported:
+                    assert all(pn.gradient_is_compressed(x) for x in grads)
+                if not on:
+                    assert not any(pn.gradient_is_compressed(x) for x in grads)
+                for x in grads:
+                    assert x.is_contiguous(memory_format=mf)
+                    x.mul_(1.0)                                    # ordinary tensors: in-place math, copies
+                results[(on, layout)] = (loss.item(), [x.clone().cpu() for x in grads])
+            torch.manual_seed(5)
+            netF = pn.PatchSampleF(use_mlp=True, nc=128).cuda()
+            t_ = [x.clone().requires_grad_() for x in tgt0]
+            netF.create_mlp(t_)
+            torch.manual_seed(6)
+            hl, _ = pn.patchnce_with_head(netF, src, t_, 0.07, 128)
+            hl.backward()
+            results[(on, "head")] = (hl.item(), [t.grad.clone().cpu() for t in t_])
+            t_ = [x.clone().requires_grad_() for x in tgt0]
+            torch.manual_seed(6)
+            rows, ids = pn.PatchSampleF()(t_, 128)
+            ups = [torch.randn(r.shape, generator=torch.Generator().manual_seed(40 + i)).cuda() for i, r in enumerate(rows)]
+            torch.autograd.backward(rows, ups)
+            results[(on, "split")] = (0.0, [t.grad.clone().cpu() for t in t_])
+        for key in ("nchw", "nhwc", "head", "split"):
+            a, b = results[(False, key)], results[(True, key)]
+            assert a[0] == b[0]
+            for x, y in zip(a[1], b[1]):
+                assert torch.equal(x, y), key
+        torch.cuda.empty_cache()                                   # hands the pool's blocks back through pnce_comp_free
+    finally:
+        pn.set_gradient_compression(*old)
