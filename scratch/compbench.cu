@@ -76,6 +76,37 @@ static float time_fill_bulk(float4* buf, size_t bytes, int mode, uint32_t pm) {
   float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
   return ms / reps;
 }
+// one CTA per CHUNK of several contiguous 8 KB tiles (a whole (b, c) row of the gradient): does the fill keep its rate when
+// a CTA walks many tiles?  (on plain memory persistent / multi-tile CTAs lose the linear DRAM write front: DESIGN.md 4.2)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_fill_chunk(float4* out, int tiles_per_cta, uint32_t pm, uint32_t seed) {
+  const size_t base = (size_t)blockIdx.x * tiles_per_cta * 512;
+  for (int t = 0; t < tiles_per_cta; ++t) {
+#pragma unroll
+    for (int k = 0; k < 512 / THREADS; ++k) {
+      const size_t i = base + (size_t)t * 512 + k * THREADS + threadIdx.x;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint32_t line = (uint32_t)(i >> 3);
+      const uint32_t h = hash(line * 2654435761u + seed);
+      if ((h % 1000u) < pm && (i & 7) == ((h >> 12) & 7)) v.x = __uint_as_float((hash(h) & 0x007fffffu) | 0x3f800000u);
+      __stcs(out + i, v);
+    }
+  }
+}
+template <int THREADS>
+static float time_fill_chunk(float4* buf, size_t bytes, int tiles_per_cta, uint32_t pm) {
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const unsigned grid = (unsigned)(bytes / 8192 / tiles_per_cta);
+  for (int w = 0; w < 3; ++w) k_fill_chunk<THREADS><<<grid, THREADS>>>(buf, tiles_per_cta, pm, 17u + w);
+  CK(cudaEventRecord(e0));
+  const int reps = 10;
+  for (int r = 0; r < reps; ++r) k_fill_chunk<THREADS><<<grid, THREADS>>>(buf, tiles_per_cta, pm, 100u + r);
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  return ms / reps;
+}
 __global__ void __launch_bounds__(256) k_sum(const float4* in, size_t n4, float* out) {
   float acc = 0.f;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
@@ -155,6 +186,9 @@ int main() {
     const float s5 = time_fill<0>(bufs[b], want, 1, 500);
     const float l1 = time_fill<0>(bufs[b], want, 3, 117), l2 = time_fill<0>(bufs[b], want, 3, 390), l3 = time_fill<0>(bufs[b], want, 3, 860);
     const float c1 = time_fill<1>(bufs[b], want, 3, 117), c0 = time_fill<1>(bufs[b], want, 0, 0);
+    printf("%-18s CTA per chunk (11.7 %% lines): 128 thr x 2 / 8 / 32 tiles: %.3f / %.3f / %.3f ms | 256 thr x 2 / 8 / 32 tiles: %.3f / %.3f / %.3f ms\n", names[b],
+           time_fill_chunk<128>(bufs[b], want, 2, 117), time_fill_chunk<128>(bufs[b], want, 8, 117), time_fill_chunk<128>(bufs[b], want, 32, 117),
+           time_fill_chunk<256>(bufs[b], want, 2, 117), time_fill_chunk<256>(bufs[b], want, 8, 117), time_fill_chunk<256>(bufs[b], want, 32, 117));
     printf("%-18s staged + one bulk store per tile: zeros %.3f ms | one float in 11.7 %% of the lines %.3f ms | 86 %%: %.3f ms\n", names[b],
            time_fill_bulk(bufs[b], want, 0, 0), time_fill_bulk(bufs[b], want, 3, 117), time_fill_bulk(bufs[b], want, 3, 860));
     printf("%-18s st.global.cs: zeros %.3f ms | one float in 11.7 %% of the lines %.3f ms\n", names[b], c0, c1);
