@@ -11,7 +11,7 @@ MATH_SIMT_F32, MATH_TC_BF16X3, MATH_TC_BF16 = 0, 1, 2
 MAX_LAYERS = 8
 MAX_PATCHES = 4096
 MAX_CHANNELS = 1024
-ABI_VERSION = 4
+ABI_VERSION = 5
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 
 EXPORTS = [

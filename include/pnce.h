@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PNCE_ABI_VERSION 4
+#define PNCE_ABI_VERSION 5
 #define PNCE_MAX_LAYERS 8      /* nce_layers per call (reference config uses 5 ids -> 4 maps)   */
 #define PNCE_MAX_PATCHES 4096  /* P = min(num_patches, H*W)  patchnce_cut.py:60; argument check only: the
                                 * kernels take P <= 1024 (tensor cores, C <= 256) or P <= 1280 (fp32 CUDA cores),
