@@ -900,6 +900,29 @@ def config_lines(args, pn, layers, dev, math, peak):
             del src, tgt
         except Exception as e:  # noqa: BLE001
             rows.append({"config": name, "error": f"{type(e).__name__}: {e}"})
+    # BASELINE config 4: 512^2 images (every HW x 4), P = 1024, B = 8 -- the key-blocked tcgen05 kernel (k_loss_tc)
+    try:
+        big = [(c, 2 * h, 2 * w, relu) for c, h, w, relu in layers]
+        src, tgt = make_maps(big, 8, torch.float32, dev, 99)
+        tgt = [t.requires_grad_() for t in tgt]
+        crit4 = pn.PatchNCELoss(args.tau, 1024, [0, 4, 8, 12, 13], math=math)
+
+        def step4():
+            for t in tgt:
+                t.grad = None
+            crit4(src, tgt).backward()
+
+        ms = timed_steps(step4, 50, 10, 1, dev)
+        ppi4 = sum(min(1024, h * w) for _, h, w, _ in big)
+        pb = algorithmic_bytes_per_image(big, 1024, 4) * 8
+        rows.append({"config": "cfg4_b8_512sq_p1024", "batch": 8, "dtype": "float32", "num_patches": 1024, "steps": 50,
+                     "ms_per_step": ms, "value": 8 * ppi4 / (ms * 1e-3), "unit": UNIT,
+                     "roofline_path": {"bound": "hbm", "achieved": pb / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": pb / (ms * 1e-3) / 1e9 / peak}})
+        del src, tgt
+    except Exception as e:  # noqa: BLE001
+        rows.append({"config": "cfg4_b8_512sq_p1024", "error": f"{type(e).__name__}: {e}"})
+    torch.cuda.empty_cache()
     # the north-star shape (netF head, dim 256) at the batches the reference trains with: the fused head through autograd
     # (patchnce_with_head + backward) and through the autograd-free entry (head_loss_and_grads)
     for name, b in (("b1_fp32_head", 1), ("b16_fp32_head", 16)):

@@ -465,6 +465,36 @@ static int launch_dense_nhwc(const Params& p, cudaStream_t st) {
   f.start[p.n_layers] = tot;
   if (tot > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)tot;
+  bool two = vec && !(g_dbg.dense_flags & 32);               // experiment bit 32: the one-launch kernel
+  for (int l = 0; l < p.n_layers && two; ++l) two = (p.L[l].C % 4) == 0 && p.L[l].C <= 256;
+  if (two) {
+    // bare zero fill of every map, then the sampled rows (nhwc.cuh)
+    FillMap fm;
+    ScatterMap sm;
+    memset(&fm, 0, sizeof(fm));
+    memset(&sm, 0, sizeof(sm));
+    long long tiles = 0, items = 0;
+    fm.n = p.n_layers;
+    for (int l = 0; l < p.n_layers; ++l) {
+      fm.start[l] = tiles;
+      fm.bytes[l] = (unsigned long long)p.B * p.L[l].HW * p.L[l].C * es;
+      fm.base[l] = p.L[l].dtgt;
+      tiles += (long long)((fm.bytes[l] + kFlatBytes - 1) / kFlatBytes);
+      sm.start[l] = items;
+      items += (long long)p.B * p.L[l].P;
+    }
+    fm.start[p.n_layers] = tiles;
+    sm.start[p.n_layers] = items;
+    if (tiles > 0x7fffffffLL || items > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
+    k_fill_zero<<<(unsigned)tiles, 128, 0, st>>>(fm);
+    PNCE_CUDA(cudaGetLastError());
+    const unsigned sgrid = (unsigned)((items + 7) / 8);
+    if (p.dtype == PNCE_F32) k_scatter_nhwc<float><<<sgrid, 256, 0, st>>>(p, sm);
+    else if (p.dtype == PNCE_F16) k_scatter_nhwc<__half><<<sgrid, 256, 0, st>>>(p, sm);
+    else k_scatter_nhwc<__nv_bfloat16><<<sgrid, 256, 0, st>>>(p, sm);
+    PNCE_CUDA(cudaGetLastError());
+    return PNCE_OK;
+  }
   if (vec) {
     if (p.dtype == PNCE_F32) k_dense_nhwc<float, true><<<grid, 128, 0, st>>>(p, f);
     else if (p.dtype == PNCE_F16) k_dense_nhwc<__half, true><<<grid, 128, 0, st>>>(p, f);

@@ -5,7 +5,7 @@ import torch
 import gan_variant_research_b200 as pn
 from bench import kernel_breakdown, timed_steps
 B5_512 = [(64, 512, 512), (256, 128, 128), (256, 128, 128), (128, 256, 256), (64, 512, 512)]
-dev = torch.device('cuda')
+dev = torch.device('cuda', 0)
 for layout in ('nchw', 'nhwc'):
     for dtype in (torch.float32, torch.float16):
         g = torch.Generator(device='cuda').manual_seed(1)

@@ -18,10 +18,10 @@ def step():
     crit.loss_and_grads(src, tgt)
 for comp in (False, True):
     pn.set_gradient_compression(comp)
-    for flags in (0, 1, 2, 4):
+    for flags in (0, 32):
         lib.pnce_debug_set(1, flags)
         ms = timed_steps(step, 50, 5, 1, dev)
         kb = kernel_breakdown(step, 10)
-        dk = {k: v for k, v in kb.items() if 'dense' in k}
+        dk = {k: v for k, v in kb.items() if 'dense' in k or 'fill' in k or 'scatter' in k}
         print(f'{layout} compressible={comp} dense flags={flags}: step {ms*1e3:.1f} us  {dk}', flush=True)
     lib.pnce_debug_set(1, 0)
