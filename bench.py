@@ -384,8 +384,9 @@ def main():
     peak, peak_src = peaks()
 
     dense_bytes = dense_kernel_bytes_per_image(layers, args.patches, elem) * B
-    dense_name = "k_dense_nhwc" if args.layout == "nhwc" and not args.head else "k_dense_flat"
-    roof = {"bound": "hbm", "kernel": dense_name + " (dense d tgt_feat: zero fill + sampled values, one write per line)",
+    dense_name = "k_fill_zero" if args.layout == "nhwc" and not args.head else "k_dense_flat"
+    roof = {"bound": "hbm", "kernel": (dense_name + " (dense d tgt_feat: zero fill + sampled values, one write per line)" if dense_name == "k_dense_flat"
+                                       else "k_fill_zero + k_scatter_nhwc (dense d tgt_feat: zero fill of every map, then the sampled rows)"),
             "achieved": dense_bytes / (bwd_med * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "peak_source": peak_src, "traffic": ncu_traffic(dense_name, B, elem), "launch_ms": bwd_med}
     roof["note"] = ("write-only stream (zero fill + sampled values): it can exceed the measured peak, which is a "
