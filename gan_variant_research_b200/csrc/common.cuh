@@ -102,6 +102,17 @@ template <> __device__ __forceinline__ float from_f32<float>(float v) { return v
 template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// Programmatic dependent launch (griddepcontrol, sm_90+): FIRST statement of every kernel of this library.  The host
+// launches the kernels of one step with cudaLaunchAttributeProgrammaticStreamSerialization (pnce_api.cu: launch_k), so
+// the next kernel's CTAs are dispatched while this one drains and its launch latency is hidden; `wait` returns once
+// every prerequisite grid has completed and its memory is visible, so nothing after it can see half-written data or
+// overwrite what a predecessor still reads (every kernel waits before its first global access, which makes completion
+// transitive along the stream).  Both instructions are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -42,6 +42,7 @@ __device__ __forceinline__ bool aug_cut(const AugParams& a, int b, int i, int j)
 // pixel (not cut out, translation source inside the image).  grid = (nblk, B); fixed-order partials: deterministic.
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(kAugThreads) k_aug_reduce(const __grid_constant__ AugParams a) {
+  pdl_enter();
   const int b = blockIdx.y, HW = a.H * a.W, C = a.C;
   const long long img = (long long)b * C * HW;
   float acc = 0.f;
@@ -90,6 +91,7 @@ __device__ __forceinline__ float aug_image_sum(const AugParams& a, int b) {
 // (zero when the source lies outside the image: the reference gathers from a zero-padded copy, :33-34).
 template <typename T>
 __global__ void __launch_bounds__(kAugThreads) k_aug_fwd(const __grid_constant__ AugParams a) {
+  pdl_enter();
   const int b = blockIdx.y, HW = a.H * a.W, C = a.C;
   const int pix = blockIdx.x * kAugThreads + threadIdx.x;
   const long long img = (long long)b * C * HW;
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(kAugThreads) k_aug_fwd(const __grid_constant__
 //   saturation: s_s d + (1 - s_s) mean_c(d);  brightness: identity.
 template <typename T>
 __global__ void __launch_bounds__(kAugThreads) k_aug_bwd(const __grid_constant__ AugParams a) {
+  pdl_enter();
   const int b = blockIdx.y, HW = a.H * a.W, C = a.C;
   const int pix = blockIdx.x * kAugThreads + threadIdx.x;
   const long long img = (long long)b * C * HW;
@@ -161,6 +164,7 @@ struct HingeParams {
 
 template <typename T>
 __global__ void __launch_bounds__(kAugThreads) k_hinge_fwd(const __grid_constant__ HingeParams h) {
+  pdl_enter();
   __shared__ float red[kAugThreads / 32];
   float total = 0.f;                                                  // thread 0 only
   for (int s = 0; s < h.scales; ++s) {
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__(kAugThreads) k_hinge_fwd(const __grid_constant
 
 template <typename T>
 __global__ void __launch_bounds__(kAugThreads) k_hinge_bwd(const __grid_constant__ HingeParams h) {
+  pdl_enter();
   const int s = blockIdx.y;
   const float g = *h.grad_out / (float)h.scales / (float)h.n[s];
   for (long long i = (long long)blockIdx.x * kAugThreads + threadIdx.x; i < h.n[s]; i += (long long)gridDim.x * kAugThreads) {

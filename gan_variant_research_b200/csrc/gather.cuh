@@ -163,6 +163,7 @@ __device__ void gather_tile(const LayerDev& L, int B, int side0, int raw, long l
 // dynamic smem = max(32*(Cmax+1)*4 + 544*4, N2max*8 + 64)
 __global__ void __launch_bounds__(kThreads) k_gather_prep(const __grid_constant__ Params p,
                                                           const __grid_constant__ BlockMap m) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const long long blk = blockIdx.x;
   const long long n_gather = m.start[p.n_layers];

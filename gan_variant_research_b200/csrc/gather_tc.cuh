@@ -89,6 +89,7 @@ __device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long loca
 // grid = sum_l 2 * B * ceil(Ppad_l / 256) * nchunk_l
 __global__ void __launch_bounds__(kThreads) k_gather_tc(const __grid_constant__ Params p,
                                                         const __grid_constant__ BlockMap m) {
+  pdl_enter();
   const long long blk = blockIdx.x;
   if (blk == 0 && threadIdx.x == 0 && p.b0 == 0 && p.counter != nullptr) {
     // launch-sequence state of the loss kernel that follows on this stream (k_prep does the same when it
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(kThreads) k_gather_tc(const __grid_constant__ 
 // One CTA per layer: ids -> (sid, perm, rank, ustart, bitmap, prefix); CTA 0 also resets the
 // last-CTA counter and the protocol flag of the launch sequence.
 __global__ void __launch_bounds__(kThreads) k_prep(const __grid_constant__ Params p) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int l = blockIdx.x;
   if (l == 0 && threadIdx.x == 0 && p.counter != nullptr) {

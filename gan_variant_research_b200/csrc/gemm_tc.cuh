@@ -78,6 +78,7 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
 }
 
 __global__ void __launch_bounds__(kTcThreads, 2) k_gemm_tc(const __grid_constant__ GemmLaunch g) {
+  pdl_enter();
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
   GemmShared* sh = reinterpret_cast<GemmShared*>(smem + kGemmSlots * kGemmStageBytes);
@@ -265,6 +266,7 @@ constexpr int kWgOffAlo = 32768, kWgOffBhi = 65536, kWgOffBlo = 131072, kWgOffOn
 constexpr int kWgSmemBytes = 196608 + 4096 + 256;
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constant__ WgradLaunch g) {
+  pdl_enter();
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
   struct Sh { uint64_t full, empty, dfull; uint32_t tmem_base; int dead; };
@@ -436,6 +438,7 @@ struct WreduceLaunch {
   const float* grad_out;
 };
 __global__ void __launch_bounds__(kThreads) k_wreduce(const __grid_constant__ WreduceLaunch gl) {
+  pdl_enter();
   int ji = 0;
   for (int i = 1; i < gl.n; ++i)
     if ((int)blockIdx.x >= gl.start[i]) ji = i;
@@ -471,6 +474,7 @@ struct WprepLaunch {
   int n;
 };
 __global__ void __launch_bounds__(64) k_wprep(const __grid_constant__ WprepLaunch g) {
+  pdl_enter();
   int ji = 0;
   for (int i = 1; i < g.n; ++i)
     if ((int)blockIdx.x >= g.start[i]) ji = i;

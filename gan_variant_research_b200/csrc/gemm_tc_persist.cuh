@@ -43,6 +43,7 @@ __device__ __forceinline__ void gp_decode(const GemmLaunch& g, long long t, GpTi
 }
 
 __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_constant__ GemmLaunch g) {
+  pdl_enter();
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
   GpShared* sh = reinterpret_cast<GpShared*>(smem + kGpSlots * kGpStageBytes);

@@ -123,6 +123,7 @@ __device__ __forceinline__ void last_cta_finalize(const Params& p, int* flag_s, 
 
 __global__ void __launch_bounds__(kThreads) k_loss_simt(const __grid_constant__ Params p,
                                                         const __grid_constant__ BlockMap m) {
+  pdl_enter();
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int l = find_layer(m, blockIdx.x, p.n_layers);

@@ -413,6 +413,7 @@ __device__ __forceinline__ void tc_dq_epilogue(uint32_t tacc, int nstage, int C,
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant__ Params p,
                                                            const __grid_constant__ BlockMap m) {
+  pdl_enter();
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
   unsigned char* stage0 = smem;
@@ -868,6 +869,7 @@ struct ProbeArgs {
 };
 
 __global__ void __launch_bounds__(128, 1) k_umma_probe(const __grid_constant__ ProbeArgs a) {
+  pdl_enter();
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
   __shared__ uint64_t full, done;

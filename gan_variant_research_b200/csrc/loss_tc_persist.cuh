@@ -222,6 +222,7 @@ __device__ __forceinline__ void tp_pass(uint32_t trow, int nmine, int half, int 
 
 __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_constant__ Params p,
                                                              const __grid_constant__ BlockMap m) {
+  pdl_enter();
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
   unsigned char* stage0 = smem;

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(kMtThreads) k_multi_axpby(float* const* __rest
                                                             const int* __restrict__ chunk_tensor,
                                                             const long long* __restrict__ chunk_start, float a,
                                                             float b, int mode) {
+  pdl_enter();
   const int t = chunk_tensor[blockIdx.x];
   const long long e0 = chunk_start[blockIdx.x];
   const long long n = numel[t];
@@ -84,6 +85,7 @@ __device__ __forceinline__ float amp_inv_scale(const float* scale) {
 // pass 1: non-finite check on the raw gradients (_amp_foreach_non_finite_check_and_unscale_) and the sum of squares of
 // the unscaled ones, one partial per chunk (reduced in a fixed order by pass 2: deterministic).
 __global__ void __launch_bounds__(kMtThreads) k_amp_gradnorm(AmpAdamTable a) {
+  pdl_enter();
   const int t = a.chunk_tensor[blockIdx.x];
   const long long e0 = a.chunk_start[blockIdx.x], n = a.numel[t];
   const long long e1 = (e0 + kMtChunk < n) ? e0 + kMtChunk : n;
@@ -150,6 +152,7 @@ __device__ __forceinline__ void amp_adam_elem(float& p, float& g, float& m, floa
 
 // pass 2: unscale, clip, Adam.  Gradients are written back unscaled and clipped, as the reference leaves them.
 __global__ void __launch_bounds__(kMtThreads) k_amp_adam(AmpAdamTable a) {
+  pdl_enter();
   __shared__ double redbuf[kMtThreads / 32];
   const int t = a.chunk_tensor[blockIdx.x];
   const long long e0 = a.chunk_start[blockIdx.x], n = a.numel[t];
@@ -201,6 +204,7 @@ __global__ void __launch_bounds__(kMtThreads) k_amp_adam(AmpAdamTable a) {
 
 // pass 3 (one CTA): step counters, GradScaler.update() (_amp_update_scale_), scratch reset for the next call.
 __global__ void __launch_bounds__(kMtThreads) k_amp_finish(AmpAdamTable a) {
+  pdl_enter();
   __shared__ double redbuf[kMtThreads / 32];
   const float total = amp_total_sumsq(a.scratch + 2, a.n_chunks, reinterpret_cast<float*>(redbuf));
   const bool found = a.scratch[0] != 0.f;

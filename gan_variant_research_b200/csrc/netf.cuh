@@ -26,6 +26,7 @@ struct NetfPackLaunch {
 };
 
 __global__ void __launch_bounds__(kThreads) k_netf_dy_pack(const __grid_constant__ NetfPackLaunch a) {
+  pdl_enter();
   int l = 0;
   for (int i = 1; i < a.n; ++i)
     if ((long long)blockIdx.x >= a.start[i]) l = i;

@@ -151,6 +151,7 @@ __device__ __forceinline__ void gather_nhwc_warp(const LayerDev& L, int b0, int 
 // grid = sum_l ceil(items_l / 16) CTAs of 8 warps, 2 items per warp; items_l = sides * B * (Ppad_l / 8) * nchunk_l
 __global__ void __launch_bounds__(kThreads) k_gather_tc_nhwc(const __grid_constant__ Params p,
                                                              const __grid_constant__ BlockMap m) {
+  pdl_enter();
   const long long blk = blockIdx.x;
   if (blk == 0 && threadIdx.x == 0 && p.b0 == 0 && p.counter != nullptr) {
     p.counter[0] = 0u; p.counter[1] = 0u;                      // launch-sequence state, as in k_gather_tc
@@ -187,6 +188,7 @@ struct DenseNhwcMap {
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(128) k_dense_nhwc(const __grid_constant__ Params p,
                                                     const __grid_constant__ DenseNhwcMap m) {
+  pdl_enter();
   __shared__ __align__(16) T tile[kFlatBytes / sizeof(T)];
   __shared__ int s_ja, s_jb;
   const int tid = threadIdx.x;
@@ -269,6 +271,7 @@ struct FillMap {
   int n;
 };
 __global__ void __launch_bounds__(128) k_fill_zero(const __grid_constant__ FillMap m) {
+  pdl_enter();
   const unsigned item = blockIdx.x;
   int l = 0;
   for (int i = 1; i < m.n; ++i)
@@ -303,6 +306,7 @@ struct ScatterMap {
 // warp <-> (layer, image, sorted slot); the head of a run of equal ids writes the position's C values
 template <typename T>
 __global__ void __launch_bounds__(256) k_scatter_nhwc(const __grid_constant__ Params p, const __grid_constant__ ScatterMap m) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (item >= m.start[p.n_layers]) return;

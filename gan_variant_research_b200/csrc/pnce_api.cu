@@ -166,6 +166,37 @@ static size_t gather_smem_bytes(const Params& p, bool with_prep) {
   return need;
 }
 
+// Every kernel of the library is launched through launch_k: with programmatic dependent launch allowed (the default;
+// PNCE_PDL=0 in the environment turns it off, read once per process) the launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization, every kernel starts with pdl_enter() (common.cuh: signal the
+// dependents, then wait for the prerequisite grids before the first global access), so along one stream the next
+// kernel's CTAs are dispatched while the previous grid drains instead of after it has retired -- the launch and
+// scheduling latency between the kernels of a step (2-4 us per boundary; a B = 8 step has four kernels of 7-60 us)
+// disappears, and results cannot change: no kernel touches memory before its predecessors have completed.
+static int pdl_allowed() {
+  static const int v = [] {
+    const char* e = getenv("PNCE_PDL");
+    return e != nullptr ? atoi(e) : 23;
+  }();
+  return v;
+}
+
+// SITE: 1 id prep, 2 gather, 4 loss, 8 dense backward, 16 everything else (PNCE_PDL is a mask over the sites)
+template <int SITE = 16, typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl_allowed() & SITE) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is sticky per kernel and
 // device: what has been set is remembered so the driver call is made once, not per launch.
 struct SmemOptIn { const void* fn; int dev; size_t bytes; };
@@ -202,7 +233,7 @@ static int launch_gather(const Params& p, int n_prep, cudaStream_t st) {
   int rc = set_smem(k_gather_prep, smem);
   if (rc != PNCE_OK) return rc;
   if (acc + n_prep > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
-  k_gather_prep<<<(unsigned)(acc + n_prep), kThreads, smem, st>>>(p, m);
+  launch_k<2>(k_gather_prep, (unsigned)(acc + n_prep), kThreads, smem, st, p, m);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
@@ -224,7 +255,7 @@ static int launch_loss_simt(const Params& p, cudaStream_t st) {
   if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
   Params q = p;
   q.total_ctas = (unsigned)acc;
-  k_loss_simt<<<(unsigned)acc, kThreads, smem, st>>>(q, m);
+  launch_k<4>(k_loss_simt, (unsigned)acc, kThreads, smem, st, q, m);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
@@ -237,7 +268,7 @@ static int launch_prep(const Params& p, cudaStream_t st) {
     const size_t s = (size_t)n2 * 8 + 64;
     if (s > smem) smem = s;
   }
-  k_prep<<<(unsigned)p.n_layers, kThreads, smem, st>>>(p);
+  launch_k<1>(k_prep, (unsigned)p.n_layers, kThreads, smem, st, p);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
@@ -270,7 +301,7 @@ static int launch_gather_tc(const Params& p, cudaStream_t st) {
     }
     m.start[p.n_layers] = acc;
     if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
-    k_gather_tc_nhwc<<<(unsigned)acc, kThreads, 0, st>>>(p, m);
+    launch_k<2>(k_gather_tc_nhwc, (unsigned)acc, kThreads, 0, st, p, m);
     PNCE_CUDA(cudaGetLastError());
     return PNCE_OK;
   }
@@ -281,7 +312,7 @@ static int launch_gather_tc(const Params& p, cudaStream_t st) {
   }
   m.start[p.n_layers] = acc;
   if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
-  k_gather_tc<<<(unsigned)acc, kThreads, 0, st>>>(p, m);
+  launch_k<2>(k_gather_tc, (unsigned)acc, kThreads, 0, st, p, m);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
@@ -363,13 +394,13 @@ static int launch_loss_tc(const Params& p, cudaStream_t st, bool single_launch =
       rot = g_dbg.loss_rot < acc ? g_dbg.loss_rot : 0;
     }
     m.start[PNCE_MAX_LAYERS + 1] = rot > 0 ? acc - rot : 0;
-    k_loss_tc_p<<<(unsigned)grid, kTpThreads, kTpSmemBytes, st>>>(q, m);
+    launch_k<4>(k_loss_tc_p, (unsigned)grid, kTpThreads, kTpSmemBytes, st, q, m);
     PNCE_CUDA(cudaGetLastError());
     return PNCE_OK;
   }
   int rc = set_smem(k_loss_tc, kTcSmemBytes);
   if (rc != PNCE_OK) return rc;
-  k_loss_tc<<<(unsigned)acc, kTcThreads, kTcSmemBytes, st>>>(p, m);
+  launch_k<4>(k_loss_tc, (unsigned)acc, kTcThreads, kTcSmemBytes, st, p, m);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
@@ -486,23 +517,23 @@ static int launch_dense_nhwc(const Params& p, cudaStream_t st) {
     fm.start[p.n_layers] = tiles;
     sm.start[p.n_layers] = items;
     if (tiles > 0x7fffffffLL || items > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
-    k_fill_zero<<<(unsigned)tiles, 128, 0, st>>>(fm);
+    launch_k<8>(k_fill_zero, (unsigned)tiles, 128, 0, st, fm);
     PNCE_CUDA(cudaGetLastError());
     const unsigned sgrid = (unsigned)((items + 7) / 8);
-    if (p.dtype == PNCE_F32) k_scatter_nhwc<float><<<sgrid, 256, 0, st>>>(p, sm);
-    else if (p.dtype == PNCE_F16) k_scatter_nhwc<__half><<<sgrid, 256, 0, st>>>(p, sm);
-    else k_scatter_nhwc<__nv_bfloat16><<<sgrid, 256, 0, st>>>(p, sm);
+    if (p.dtype == PNCE_F32) launch_k<8>(k_scatter_nhwc<float>, sgrid, 256, 0, st, p, sm);
+    else if (p.dtype == PNCE_F16) launch_k<8>(k_scatter_nhwc<__half>, sgrid, 256, 0, st, p, sm);
+    else launch_k<8>(k_scatter_nhwc<__nv_bfloat16>, sgrid, 256, 0, st, p, sm);
     PNCE_CUDA(cudaGetLastError());
     return PNCE_OK;
   }
   if (vec) {
-    if (p.dtype == PNCE_F32) k_dense_nhwc<float, true><<<grid, 128, 0, st>>>(p, f);
-    else if (p.dtype == PNCE_F16) k_dense_nhwc<__half, true><<<grid, 128, 0, st>>>(p, f);
-    else k_dense_nhwc<__nv_bfloat16, true><<<grid, 128, 0, st>>>(p, f);
+    if (p.dtype == PNCE_F32) launch_k<8>(k_dense_nhwc<float, true>, grid, 128, 0, st, p, f);
+    else if (p.dtype == PNCE_F16) launch_k<8>(k_dense_nhwc<__half, true>, grid, 128, 0, st, p, f);
+    else launch_k<8>(k_dense_nhwc<__nv_bfloat16, true>, grid, 128, 0, st, p, f);
   } else {
-    if (p.dtype == PNCE_F32) k_dense_nhwc<float, false><<<grid, 128, 0, st>>>(p, f);
-    else if (p.dtype == PNCE_F16) k_dense_nhwc<__half, false><<<grid, 128, 0, st>>>(p, f);
-    else k_dense_nhwc<__nv_bfloat16, false><<<grid, 128, 0, st>>>(p, f);
+    if (p.dtype == PNCE_F32) launch_k<8>(k_dense_nhwc<float, false>, grid, 128, 0, st, p, f);
+    else if (p.dtype == PNCE_F16) launch_k<8>(k_dense_nhwc<__half, false>, grid, 128, 0, st, p, f);
+    else launch_k<8>(k_dense_nhwc<__nv_bfloat16, false>, grid, 128, 0, st, p, f);
   }
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
@@ -529,21 +560,21 @@ static int launch_dense(const Params& p, cudaStream_t st) {
   if (tot > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)tot;
   if (vec && (g_dbg.dense_flags & 2)) {                      // experiment: store-first variant
-    if (p.dtype == PNCE_F32) k_dense_direct<float, 128><<<grid, 128, 0, st>>>(p, f);
-    else if (p.dtype == PNCE_F16) k_dense_direct<__half, 128><<<grid, 128, 0, st>>>(p, f);
-    else k_dense_direct<__nv_bfloat16, 128><<<grid, 128, 0, st>>>(p, f);
+    if (p.dtype == PNCE_F32) launch_k<8>(k_dense_direct<float, 128>, grid, 128, 0, st, p, f);
+    else if (p.dtype == PNCE_F16) launch_k<8>(k_dense_direct<__half, 128>, grid, 128, 0, st, p, f);
+    else launch_k<8>(k_dense_direct<__nv_bfloat16, 128>, grid, 128, 0, st, p, f);
   } else if (vec && (g_dbg.dense_flags & 4)) {               // experiment: 64-thread CTAs (more tiles in flight per SM)
-    if (p.dtype == PNCE_F32) k_dense_flat<float, 64, true><<<grid, 64, 0, st>>>(p, f);
-    else if (p.dtype == PNCE_F16) k_dense_flat<__half, 64, true><<<grid, 64, 0, st>>>(p, f);
-    else k_dense_flat<__nv_bfloat16, 64, true><<<grid, 64, 0, st>>>(p, f);
+    if (p.dtype == PNCE_F32) launch_k<8>(k_dense_flat<float, 64, true>, grid, 64, 0, st, p, f);
+    else if (p.dtype == PNCE_F16) launch_k<8>(k_dense_flat<__half, 64, true>, grid, 64, 0, st, p, f);
+    else launch_k<8>(k_dense_flat<__nv_bfloat16, 64, true>, grid, 64, 0, st, p, f);
   } else if (vec) {
-    if (p.dtype == PNCE_F32) k_dense_flat<float, 128, true><<<grid, 128, 0, st>>>(p, f);
-    else if (p.dtype == PNCE_F16) k_dense_flat<__half, 128, true><<<grid, 128, 0, st>>>(p, f);
-    else k_dense_flat<__nv_bfloat16, 128, true><<<grid, 128, 0, st>>>(p, f);
+    if (p.dtype == PNCE_F32) launch_k<8>(k_dense_flat<float, 128, true>, grid, 128, 0, st, p, f);
+    else if (p.dtype == PNCE_F16) launch_k<8>(k_dense_flat<__half, 128, true>, grid, 128, 0, st, p, f);
+    else launch_k<8>(k_dense_flat<__nv_bfloat16, 128, true>, grid, 128, 0, st, p, f);
   } else {
-    if (p.dtype == PNCE_F32) k_dense_flat<float, 128, false><<<grid, 128, 0, st>>>(p, f);
-    else if (p.dtype == PNCE_F16) k_dense_flat<__half, 128, false><<<grid, 128, 0, st>>>(p, f);
-    else k_dense_flat<__nv_bfloat16, 128, false><<<grid, 128, 0, st>>>(p, f);
+    if (p.dtype == PNCE_F32) launch_k<8>(k_dense_flat<float, 128, false>, grid, 128, 0, st, p, f);
+    else if (p.dtype == PNCE_F16) launch_k<8>(k_dense_flat<__half, 128, false>, grid, 128, 0, st, p, f);
+    else launch_k<8>(k_dense_flat<__nv_bfloat16, 128, false>, grid, 128, 0, st, p, f);
   }
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
@@ -610,6 +641,7 @@ int pnce_debug_set(int key, long long value) {
 // Experiment: occupy `n_sms` SMs (one CTA with 227 KB of shared memory each) until *stop != 0 (bounded, ~40 ms):
 // what do the other kernels lose when a persistent kernel owns part of the GPU?
 __global__ void k_debug_blocker(volatile int* stop, int* resident) {
+  pdl_enter();
   extern __shared__ unsigned char bs[];
   if (threadIdx.x == 0) atomicAdd(resident, 1);
   const long long t0 = clock64();
@@ -628,6 +660,7 @@ int pnce_debug_block_sms(int n_sms, int* stop_and_resident, void* stream) {
 // Experiment (scratch/exp31.py): zero fill by 128-thread CTAs without shared memory -- can it run beside k_loss_tc_p?
 // ctas > 0: persistent grid-stride CTAs; ctas == 0: one CTA per 8 KB, in address order.
 __global__ void __launch_bounds__(128) k_debug_fill(float4* __restrict__ p, long long n16, int persistent) {
+  pdl_enter();
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   if (persistent) {
     for (long long i = (long long)blockIdx.x * 128 + threadIdx.x; i < n16; i += (long long)gridDim.x * 128) p[i] = z;
@@ -778,6 +811,7 @@ int pnce_plan_ids_draw(const pnce_layer_t* layers, int n_layers, unsigned long l
 
 // The draw alone (no sort): for callers that only need the ids (PatchSampleF with patch_ids=None).
 __global__ void __launch_bounds__(kThreads) k_draw_ids(const __grid_constant__ Params p) {
+  pdl_enter();
   const LayerDev& L = p.L[blockIdx.x];
   const unsigned long long off = p.rng_offset + 4ull * blockIdx.x;
   for (int i = threadIdx.x; i < L.P; i += kThreads) {
@@ -802,7 +836,7 @@ int pnce_draw_ids(const pnce_layer_t* layers, int n_layers, unsigned long long p
     p.L[l].ids = reinterpret_cast<const long long*>(a.ids);
     p.L[l].HW = a.H * a.W; p.L[l].P = a.P;
   }
-  k_draw_ids<<<(unsigned)n_layers, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  launch_k(k_draw_ids, (unsigned)n_layers, kThreads, 0, static_cast<cudaStream_t>(stream), p);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
@@ -913,6 +947,7 @@ int pnce_sample_bwd_workspace_bytes(int batch, int C, int H, int W, int P, size_
 
 // One-CTA launch of the id prep alone (module-split backward has no gather to ride on).
 __global__ void __launch_bounds__(kThreads) k_prep_only(const __grid_constant__ Params p) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
   int N2 = 1;
@@ -945,12 +980,12 @@ int pnce_sample_bwd(const float* drows, const float* rows, const float* inv, int
   int n2 = 1;
   while (n2 < P) n2 <<= 1;
   const size_t prep_smem = (size_t)n2 * 8 + 64;
-  k_prep_only<<<1, kThreads, prep_smem, st>>>(p);
+  launch_k(k_prep_only, 1, kThreads, prep_smem, st, p);
   PNCE_CUDA(cudaGetLastError());
   const size_t smem = (size_t)kRowTile * (C + 1) * sizeof(float);
   rc = set_smem(k_rows_normbwd, smem);
   if (rc != PNCE_OK) return rc;
-  k_rows_normbwd<<<(unsigned)(batch * L.ntiles), kThreads, smem, st>>>(p, drows, rows, 0);
+  launch_k(k_rows_normbwd, (unsigned)(batch * L.ntiles), kThreads, smem, st, p, drows, rows, 0);
   PNCE_CUDA(cudaGetLastError());
   return launch_dense(p, st);
 }
@@ -1051,7 +1086,7 @@ int pnce_sample_multi_bwd(const pnce_sample_t* sm, int n, int batch, int dtype, 
   if (rc != PNCE_OK) return rc;
   for (int l = 0; l < n; ++l) {
     const LayerDev& L = p.L[l];
-    k_rows_normbwd<<<(unsigned)(batch * L.ntiles), kThreads, (size_t)kRowTile * (L.C + 1) * sizeof(float), st>>>(
+    launch_k(k_rows_normbwd, (unsigned)(batch * L.ntiles), kThreads, (size_t)kRowTile * (L.C + 1) * sizeof(float), st, 
         p, sm[l].drows, sm[l].rows, l);
     PNCE_CUDA(cudaGetLastError());
   }
@@ -1148,7 +1183,7 @@ int pnce_rows_loss_fwd_bwd(const float* q, const float* k, int batch, int P, int
     T.dq_rows = dq_out;
     PNCE_CUDA(cudaMemsetAsync(t.counter, 0, 2 * sizeof(unsigned), st0));
     const long long threads = 2ll * batch * T.Ppad * (T.Cp >> 3);
-    k_rows_pack<<<(unsigned)((threads + kThreads - 1) / kThreads), kThreads, 0, st0>>>(t);
+    launch_k(k_rows_pack, (unsigned)((threads + kThreads - 1) / kThreads), kThreads, 0, st0, t);
     PNCE_CUDA(cudaGetLastError());
     return launch_loss_tc(t, st0);
   }
@@ -1251,7 +1286,7 @@ int pnce_rows_loss_multi_fwd_bwd(const pnce_rows_t* rows, int n_layers, int batc
     if (threads > most) most = threads;
   }
   const dim3 grid((unsigned)((most + kThreads - 1) / kThreads), (unsigned)n_layers);
-  k_rows_pack<<<grid, kThreads, 0, st>>>(t);
+  launch_k(k_rows_pack, grid, kThreads, 0, st, t);
   PNCE_CUDA(cudaGetLastError());
   return launch_loss_tc(t, st);
 }
@@ -1373,13 +1408,13 @@ static int launch_gemm(GemmLaunch& g, cudaStream_t st) {
     if (grid > acc) grid = acc;
     rc = set_smem(k_gemm_tc_p, kGpSmemBytes);
     if (rc != PNCE_OK) return rc;
-    k_gemm_tc_p<<<(unsigned)grid, kGpThreads, kGpSmemBytes, st>>>(g);
+    launch_k(k_gemm_tc_p, (unsigned)grid, kGpThreads, kGpSmemBytes, st, g);
     PNCE_CUDA(cudaGetLastError());
     return PNCE_OK;
   }
   int rc = set_smem(k_gemm_tc, kGemmSmemBytes);
   if (rc != PNCE_OK) return rc;
-  k_gemm_tc<<<(unsigned)acc, kTcThreads, kGemmSmemBytes, st>>>(g);
+  launch_k(k_gemm_tc, (unsigned)acc, kTcThreads, kGemmSmemBytes, st, g);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
@@ -1456,7 +1491,7 @@ static int head_fwd_impl(const pnce_layer_t* layers, const pnce_head_t* heads, i
       add(heads[l].w2, hb.w2t[0], hb.w2t[1], nc, nc, nc, nc, 1);  // B[j][i] = W2[i][j]      (dH = dY W2)
     }
     wl.start[wl.n] = blocks;
-    k_wprep<<<(unsigned)blocks, 64, 0, st>>>(wl);
+    launch_k(k_wprep, (unsigned)blocks, 64, 0, st, wl);
     PNCE_CUDA(cudaGetLastError());
   }
   // 2. raw patches of both sides as row blobs
@@ -1583,7 +1618,7 @@ static int head_bwd_phases(int phases, const pnce_layer_t* layers, const pnce_he
   wg.start[wg.n] = acc;
   rc = set_smem(k_wgrad_tc, kWgSmemBytes);
   if (rc != PNCE_OK) return rc;
-  k_wgrad_tc<<<(unsigned)acc, kTcThreads, kWgSmemBytes, st>>>(wg);
+  launch_k(k_wgrad_tc, (unsigned)acc, kTcThreads, kWgSmemBytes, st, wg);
   PNCE_CUDA(cudaGetLastError());
   {
     static thread_local WreduceLaunch rl;
@@ -1603,7 +1638,7 @@ static int head_bwd_phases(int phases, const pnce_layer_t* layers, const pnce_he
       }
     }
     rl.start[rl.n] = blocks;
-    k_wreduce<<<(unsigned)blocks, kThreads, 0, st>>>(rl);
+    launch_k(k_wreduce, (unsigned)blocks, kThreads, 0, st, rl);
     PNCE_CUDA(cudaGetLastError());
   }
   // 4. dense d tgt_feat (zero fill + sampled positions), scaled by the upstream gradient
@@ -1770,7 +1805,7 @@ int pnce_netf_fwd(const pnce_sample_t* maps, const pnce_head_t* heads, int n_map
       add(heads[l].w2, hb.w2t[0], hb.w2t[1], nc, nc, nc, nc, 1);
     }
     wl.start[wl.n] = blocks;
-    k_wprep<<<(unsigned)blocks, 64, 0, st>>>(wl);
+    launch_k(k_wprep, (unsigned)blocks, 64, 0, st, wl);
     PNCE_CUDA(cudaGetLastError());
   }
   // 2. raw patches as the X row blob (sorted-slot order)
@@ -1851,7 +1886,7 @@ int pnce_netf_bwd(const pnce_sample_t* maps, const pnce_head_t* heads, int n_map
     }
     pk.start[n_maps] = acc;
     if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
-    k_netf_dy_pack<<<(unsigned)acc, kThreads, 0, st>>>(pk);
+    launch_k(k_netf_dy_pack, (unsigned)acc, kThreads, 0, st, pk);
     PNCE_CUDA(cudaGetLastError());
   }
   // 2. dH = (dY W2) * [H > 0]
@@ -1910,7 +1945,7 @@ int pnce_netf_bwd(const pnce_sample_t* maps, const pnce_head_t* heads, int n_map
   wg.start[wg.n] = acc;
   rc = set_smem(k_wgrad_tc, kWgSmemBytes);
   if (rc != PNCE_OK) return rc;
-  k_wgrad_tc<<<(unsigned)acc, kTcThreads, kWgSmemBytes, st>>>(wg);
+  launch_k(k_wgrad_tc, (unsigned)acc, kTcThreads, kWgSmemBytes, st, wg);
   PNCE_CUDA(cudaGetLastError());
   {
     static thread_local WreduceLaunch rl;
@@ -1930,7 +1965,7 @@ int pnce_netf_bwd(const pnce_sample_t* maps, const pnce_head_t* heads, int n_map
       }
     }
     rl.start[rl.n] = blocks;
-    k_wreduce<<<(unsigned)blocks, kThreads, 0, st>>>(rl);
+    launch_k(k_wreduce, (unsigned)blocks, kThreads, 0, st, rl);
     PNCE_CUDA(cudaGetLastError());
   }
   // 5. dense d feat (zero fill + sampled positions)
@@ -1945,7 +1980,7 @@ int pnce_multi_axpby(float* const* dev_dst, const float* const* dev_src, const l
   if (!dev_dst || !dev_src || !dev_numel || !dev_chunk_tensor || !dev_chunk_start || n_chunks < 0) return PNCE_ERR_ARG;
   if (mode != 0 && mode != 1) return PNCE_ERR_ARG;
   if (n_chunks == 0) return PNCE_OK;
-  k_multi_axpby<<<(unsigned)n_chunks, kMtThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(k_multi_axpby, (unsigned)n_chunks, kMtThreads, 0, static_cast<cudaStream_t>(stream), 
       dev_dst, dev_src, dev_numel, dev_chunk_tensor, dev_chunk_start, a, b, mode);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
@@ -1977,10 +2012,10 @@ int pnce_amp_adam_step(float* const* dev_param, float* const* dev_grad, float* c
   a.scratch = dev_scratch;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n_chunks > 0) {
-    k_amp_gradnorm<<<(unsigned)n_chunks, kMtThreads, 0, st>>>(a);
-    k_amp_adam<<<(unsigned)n_chunks, kMtThreads, 0, st>>>(a);
+    launch_k(k_amp_gradnorm, (unsigned)n_chunks, kMtThreads, 0, st, a);
+    launch_k(k_amp_adam, (unsigned)n_chunks, kMtThreads, 0, st, a);
   }
-  k_amp_finish<<<1, kMtThreads, 0, st>>>(a);       // with no gradients at all GradScaler.update() still runs
+  launch_k(k_amp_finish, 1, kMtThreads, 0, st, a);       // with no gradients at all GradScaler.update() still runs
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
@@ -2018,11 +2053,11 @@ int pnce_diffaug(const void* dev_in, void* dev_out, int dtype, int B, int C, int
 #define PNCE_AUG_LAUNCH(T)                                                              \
   do {                                                                                  \
     if (color) {                                                                        \
-      if (backward) k_aug_reduce<T, true><<<rgrid, kAugThreads, 0, st>>>(a);            \
-      else k_aug_reduce<T, false><<<rgrid, kAugThreads, 0, st>>>(a);                    \
+      if (backward) launch_k(k_aug_reduce<T, true>, rgrid, kAugThreads, 0, st, a);            \
+      else launch_k(k_aug_reduce<T, false>, rgrid, kAugThreads, 0, st, a);                    \
     }                                                                                   \
-    if (backward) k_aug_bwd<T><<<grid, kAugThreads, 0, st>>>(a);                        \
-    else k_aug_fwd<T><<<grid, kAugThreads, 0, st>>>(a);                                 \
+    if (backward) launch_k(k_aug_bwd<T>, grid, kAugThreads, 0, st, a);                        \
+    else launch_k(k_aug_fwd<T>, grid, kAugThreads, 0, st, a);                                 \
   } while (0)
   if (dtype == PNCE_F32) PNCE_AUG_LAUNCH(float);
   else if (dtype == PNCE_F16) PNCE_AUG_LAUNCH(__half);
@@ -2058,9 +2093,9 @@ int pnce_hinge_fwd(const void* const* real, const void* const* fake, const long 
   if (!dev_loss) return PNCE_ERR_ARG;
   h.loss = dev_loss;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == PNCE_F32) k_hinge_fwd<float><<<1, kAugThreads, 0, st>>>(h);
-  else if (dtype == PNCE_F16) k_hinge_fwd<__half><<<1, kAugThreads, 0, st>>>(h);
-  else k_hinge_fwd<__nv_bfloat16><<<1, kAugThreads, 0, st>>>(h);
+  if (dtype == PNCE_F32) launch_k(k_hinge_fwd<float>, 1, kAugThreads, 0, st, h);
+  else if (dtype == PNCE_F16) launch_k(k_hinge_fwd<__half>, 1, kAugThreads, 0, st, h);
+  else launch_k(k_hinge_fwd<__nv_bfloat16>, 1, kAugThreads, 0, st, h);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
@@ -2077,9 +2112,9 @@ int pnce_hinge_bwd(const void* const* real, const void* const* fake, void* const
   if (gx > 1024) gx = 1024;
   const dim3 grid((unsigned)gx, (unsigned)scales);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == PNCE_F32) k_hinge_bwd<float><<<grid, kAugThreads, 0, st>>>(h);
-  else if (dtype == PNCE_F16) k_hinge_bwd<__half><<<grid, kAugThreads, 0, st>>>(h);
-  else k_hinge_bwd<__nv_bfloat16><<<grid, kAugThreads, 0, st>>>(h);
+  if (dtype == PNCE_F32) launch_k(k_hinge_bwd<float>, grid, kAugThreads, 0, st, h);
+  else if (dtype == PNCE_F16) launch_k(k_hinge_bwd<__half>, grid, kAugThreads, 0, st, h);
+  else launch_k(k_hinge_bwd<__nv_bfloat16>, grid, kAugThreads, 0, st, h);
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }

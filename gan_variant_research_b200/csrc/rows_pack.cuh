@@ -14,6 +14,7 @@ namespace pnce {
 
 // grid = (ceil(2 * B * Ppad * Cp8 / 256) of the largest layer, n_layers); side 0 = k, 1 = q
 __global__ void __launch_bounds__(kThreads) k_rows_pack(const __grid_constant__ Params p) {
+  pdl_enter();
   const LayerDev& L = p.L[blockIdx.y];
   const int Ppad = L.Ppad, P = L.P, C = L.C, Cp8 = L.Cp >> 3, nchunk = L.nchunk;
   const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;

@@ -9,6 +9,7 @@ namespace pnce {
 __global__ void __launch_bounds__(kThreads) k_rows_normbwd(const __grid_constant__ Params p,
                                                            const float* __restrict__ drows,
                                                            const float* __restrict__ rows, int l) {
+  pdl_enter();
   extern __shared__ __align__(16) float st[];
   const LayerDev& L = p.L[l];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
