@@ -15,6 +15,9 @@
  *   - thread-safe per (workspace, stream) pair.
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     PNCE_ERR_CUDA.
+ *   - kernels are launched with programmatic dependent launch allowed (every kernel waits for its
+ *     prerequisite grids before its first global access, so stream order is what the caller sees);
+ *     the environment variable PNCE_PDL=0, read once per process, launches them the ordinary way.
  */
 #ifndef PNCE_H_
 #define PNCE_H_
