@@ -13,7 +13,8 @@ measured AFTER the timed region:
                64 sharded over the N ranks: strong scaling), nccl_selfcheck (N > 1: data-parallel head gradients
                against the full batch on one rank), e2e
   at N = 1   : configs (B = 1, B = 16, fp16 maps: BASELINE configs 1-3 and the AMP regime), module_split, next_rows
-               (the optimiser-side and D-side pieces of SURVEY.md 8f), cpu_baseline.
+               (the optimiser-side and D-side pieces of SURVEY.md 8f), train_step (BASELINE configs 2 / 3: the whole
+               train_step order on stand-in networks, with the PatchNCE share), cpu_baseline.
 """
 import argparse
 import gc
@@ -480,6 +481,7 @@ def main():
     breakdowns.clear()
     if rank == 0 and world == 1 and not args.head and not args.no_head_line:
         out["next_rows"] = next_rows_line(pn, dev)
+        out["train_step"] = train_step_line(pn, dev)
 
     # ---- e2e: same metric through the public API with HOST buffers ------------------------------
     if not args.no_e2e:
@@ -590,6 +592,83 @@ def next_rows_line(pn, dev, n=30):
                 "diffaugment_fwd_bwd_b16_us": timed(aug_step),
                 "note": "unscale + clip + Adam + loss-scale update in 3 launches; EMA in 1; DiffAugment colour + translation + "
                         "cutout in 2 + 2 (plus the 7 draws); DESIGN.md 7.2 - 7.5"}
+    except Exception as e:  # noqa: BLE001 - a secondary line must not take the bench down
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+def train_step_line(pn, dev, timed=8):
+    """BASELINE configs 2 and 3: the reference's whole train_step order (training/train_cutpp.py:206-331 --
+    D step, G step with the adversarial hinge + PatchNCE, AMP optimiser steps, EMA) at 256 x 256 under autocast, batch 1
+    with lambda_NCE = 1 and batch 16 with lambda_NCE = 10, built from this package's pieces around STAND-IN networks with
+    the reference's shapes (tests/standin_generator.py: ResNet-9, ngf 64; a 70 x 70-PatchGAN-shaped discriminator -- the
+    reference's own models are Python under /root/reference and do not travel to the GPU box).  `patchnce_ms` is the
+    difference to the same step without the PatchNCE term: what the loss, its second feature pass and its share of the
+    generator's backward cost inside the step.  After the timed region; never fatal for the bench line."""
+    try:
+        import torch.nn as nn
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from standin_generator import StandInGenerator
+        layers = [0, 4, 8, 12, 13]
+
+        def make_d():
+            mods, ch = [nn.Conv2d(3, 64, 4, 2, 1), nn.LeakyReLU(0.2)], 64
+            for s in (2, 2, 1):
+                mods += [nn.Conv2d(ch, ch * 2, 4, s, 1), nn.InstanceNorm2d(ch * 2), nn.LeakyReLU(0.2)]
+                ch *= 2
+            return nn.Sequential(*mods, nn.Conv2d(ch, 1, 4, 1, 1))
+
+        out = {}
+        for name, b, lam in (("config2_b1", 1, 1.0), ("config3_b16_fastcut", 16, 10.0)):
+            torch.manual_seed(0)
+            gen, dis = StandInGenerator(ngf=64, n_blocks=9).to(dev), make_d().to(dev)
+            og = torch.optim.Adam(gen.parameters(), lr=2e-4, betas=(0.5, 0.999))
+            od = torch.optim.Adam(dis.parameters(), lr=2e-4, betas=(0.5, 0.999))
+            scaler = torch.amp.GradScaler("cuda")
+            pn.enable_encoder_feature_reuse(gen, layers)
+            ema, aug = pn.EMA(gen, 0.999), pn.DiffAugment(["color", "translation", "cutout"])
+            sg, sd = pn.FusedAdamStep(og, scaler, 10.0), pn.FusedAdamStep(od, scaler, 10.0)
+            photos = torch.rand(b, 3, 256, 256, device=dev) * 2 - 1
+
+            def step(with_nce):
+                od.zero_grad()                                                    # D step, train_cutpp.py:229-253
+                with torch.autocast("cuda"):
+                    fake = gen(photos)
+                    d_loss = pn.discriminator_hinge_loss(dis(aug(photos)), dis(aug(fake.detach())))
+                scaler.scale(d_loss).backward()
+                sd.step()
+                og.zero_grad()                                                    # G step, :266-308
+                with torch.autocast("cuda"):
+                    fake = gen(photos)
+                    g_loss = pn.generator_hinge_loss(dis(aug(fake)))
+                    if with_nce:
+                        g_loss = g_loss + lam * pn.compute_patchnce_loss(gen, photos, fake, nce_layers=layers,
+                                                                         temperature=0.07, num_patches=256)
+                scaler.scale(g_loss).backward()
+                sg.step()
+                ema.update()                                                      # :310-312
+                return g_loss
+
+            ms = {}
+            for with_nce in (True, False, True):                                 # the first pass warms cuDNN and the allocator
+                for _ in range(3):
+                    step(with_nce)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(timed):
+                    last = step(with_nce)
+                e1.record()
+                torch.cuda.synchronize()
+                ms[with_nce] = e0.elapsed_time(e1) / timed
+            out[name] = {"batch": b, "lambda_nce": lam, "ms_per_step": round(ms[True], 3),
+                         "ms_per_step_without_patchnce": round(ms[False], 3), "patchnce_ms": round(ms[True] - ms[False], 3),
+                         "patchnce_share": round((ms[True] - ms[False]) / ms[True], 4), "g_loss": float(last.item())}
+            del gen, dis, og, od, ema, aug, sg, sd, photos
+            torch.cuda.empty_cache()
+        out["note"] = ("stand-in networks with the reference's shapes, every piece from this package (fused DiffAugment, hinge "
+                       "losses, PatchNCE with encoder-feature reuse, 3-launch AMP optimiser step, 1-launch EMA), no .item() "
+                       "reads inside the step; the same loop from stock torch pieces: scratch/train_step_bench.py, DESIGN.md 7.6")
+        return out
     except Exception as e:  # noqa: BLE001 - a secondary line must not take the bench down
         return {"error": f"{type(e).__name__}: {e}"}
 

@@ -103,6 +103,67 @@ def allreduce_head_grads(module: torch.nn.Module, group=None, average: bool = Tr
     return off
 
 
+class _MultiCopy:
+    """Bucket <-> gradients in one launch each way: ``pnce_multi_axpby`` (mode 1, dst = src; include/pnce.h, the kernel
+    behind ``EMA``) over device tables of the bucket's slot addresses and of the gradients' addresses.  A reducer over the
+    reference generator's 48 parameter tensors otherwise issues 96 slice copies per backward and is bound by their host
+    time, not by NCCL.  The gradient table is re-uploaded only when a gradient tensor has moved (``zero_grad`` drops the
+    tensors, the caching allocator usually hands the same blocks back)."""
+
+    def __init__(self, flat, slots):
+        from . import _lib
+        self._lib = _lib
+        self.dev = flat.device
+        self.params = [p for p, _, _ in slots]
+        chunk = _lib.load().pnce_multi_chunk_elems()
+        ct, cs = [], []
+        for t, (_, _, n) in enumerate(slots):
+            for e in range(0, n, chunk):
+                ct.append(t)
+                cs.append(e)
+        self.n_chunks = len(ct)
+        self.chunk_tensor = torch.tensor(ct, dtype=torch.int32, device=self.dev)
+        self.chunk_start = torch.tensor(cs, dtype=torch.int64, device=self.dev)
+        self.numel = torch.tensor([n for _, _, n in slots], dtype=torch.int64, device=self.dev)
+        base, item = flat.data_ptr(), flat.element_size()
+        self.slot_ptrs = torch.tensor([base + off * item for _, off, _ in slots], dtype=torch.int64, device=self.dev)
+        self.grad_ptr_list, self.grad_ptrs = None, None
+
+    def _grads(self):
+        grads = [p.grad for p in self.params]
+        for g in grads:
+            if g is None or g.dtype != torch.float32 or not g.is_cuda or not g.is_contiguous() or g.is_sparse:
+                return None
+        ptrs = [g.data_ptr() for g in grads]
+        if ptrs != self.grad_ptr_list:
+            self.grad_ptr_list = ptrs
+            self.grad_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.dev)
+        return grads
+
+    def _launch(self, dst, src):
+        import ctypes
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        with torch.cuda.device(self.dev):
+            self._lib.check(self._lib.load().pnce_multi_axpby(dst.data_ptr(), src.data_ptr(), self.numel.data_ptr(),
+                                                              self.chunk_tensor.data_ptr(), self.chunk_start.data_ptr(),
+                                                              self.n_chunks, ctypes.c_float(0.0), ctypes.c_float(0.0), 1, st),
+                            "pnce_multi_axpby")
+
+    def pack(self) -> bool:
+        if self._grads() is None:
+            return False
+        self._launch(self.slot_ptrs, self.grad_ptrs)
+        return True
+
+    def unpack(self) -> bool:
+        grads = self._grads()
+        if grads is None:
+            return False
+        self._launch(self.grad_ptrs, self.slot_ptrs)
+        torch._C._increment_version(grads)           # written through raw pointers: tell autograd's version counters
+        return True
+
+
 class GradReducer:
     """Data-parallel gradient averaging around the UNCHANGED reference training step (SURVEY.md section 8f row 1,
     BASELINE config 5: "NCCL allreduce of netF/G/D grads"): attach it to the generator's and the
@@ -113,10 +174,11 @@ class GradReducer:
 
     Mechanics (what DDP's reducer does, kept small): parameters are grouped into flat fp32 buckets of
     ``bucket_bytes`` in reverse registration order (gradients arrive roughly back to front); a
-    post-accumulate-grad hook copies each gradient into its bucket slot; a full bucket is all-reduced
-    (mean) on a side stream while the backward pass keeps running; an end-of-backward callback launches the
-    buckets that only filled partially (a pass that touches a subset of the parameters, e.g. the D step),
-    joins the side stream and copies the averaged values back into ``.grad``.  Scaled (GradScaler)
+    post-accumulate-grad hook marks each gradient ready; a full bucket is packed (one multi-tensor launch of
+    libpnce on GPUs, ``_MultiCopy``) and all-reduced (mean) on a side stream while the backward pass keeps
+    running; an end-of-backward callback launches the buckets that only filled partially (a pass that touches
+    a subset of the parameters, e.g. the D step), joins the side stream and copies the averaged values back
+    into ``.grad`` (again one launch per complete bucket).  Scaled (GradScaler)
     gradients average like any others; an inf on one rank becomes an inf on all, so every rank skips the
     same steps."""
 
@@ -141,14 +203,14 @@ class GradReducer:
 
     def _close_bucket(self, plist):
         dev = plist[0].device
-        total = sum(p.numel() for p in plist)
-        flat = torch.zeros(total, dtype=torch.float32, device=dev)
         slots, off = [], 0
         for k, p in enumerate(plist):
             slots.append((p, off, p.numel()))
             self.where[id(p)] = (len(self.buckets), k)
-            off += p.numel()
-        self.buckets.append({"flat": flat, "slots": slots, "ready": set(), "launched": False})
+            off += (p.numel() + 3) // 4 * 4          # every slot starts on a 16-byte boundary (128-bit copies)
+        flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.buckets.append({"flat": flat, "slots": slots, "ready": set(), "launched": False,
+                             "multi": _MultiCopy(flat, slots) if flat.is_cuda else None})
 
     def remove(self):
         for h in self._handles:
@@ -161,9 +223,7 @@ class GradReducer:
             return
         bi, si = self.where[id(p)]
         b = self.buckets[bi]
-        _, off, n = b["slots"][si]
-        b["flat"][off:off + n].copy_(p.grad.detach().reshape(-1))
-        b["ready"].add(si)
+        b["ready"].add(si)                               # the gradient is copied when its bucket is launched
         if not self._callback_queued:
             self._callback_queued = True
             torch.autograd.Variable._execution_engine.queue_callback(self._finalize)
@@ -173,6 +233,12 @@ class GradReducer:
     def _launch(self, b):
         flat = b["flat"]
         b["launched"] = True
+        # gradients -> bucket: ONE multi-tensor launch of libpnce when the whole bucket is ready and every gradient is a
+        # contiguous fp32 CUDA tensor (the usual case), one copy per ready slot otherwise
+        if not (len(b["ready"]) == len(b["slots"]) and b["multi"] is not None and b["multi"].pack()):
+            for si in b["ready"]:
+                p, off, n = b["slots"][si]
+                flat[off:off + n].copy_(p.grad.detach().reshape(-1))
         if flat.is_cuda:
             main = torch.cuda.current_stream(flat.device)
             side = comm_stream(flat.device)
@@ -192,8 +258,9 @@ class GradReducer:
             flat = b["flat"]
             if flat.is_cuda:
                 torch.cuda.current_stream(flat.device).wait_stream(comm_stream(flat.device))
-            for si in b["ready"]:
-                p, off, n = b["slots"][si]
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            if not (len(b["ready"]) == len(b["slots"]) and b["multi"] is not None and b["multi"].unpack()):
+                for si in b["ready"]:
+                    p, off, n = b["slots"][si]
+                    p.grad.copy_(flat[off:off + n].view_as(p.grad))
             b["ready"] = set()
             b["launched"] = False
