@@ -62,6 +62,12 @@ class EMA:
     def _refresh_param_table(self):
         ptrs = [p.data_ptr() for p in self._params]
         if self._param_ptrs is None or ptrs != self._param_ptr_list:
+            # storage moved (.to(memory_format=...), .to(device), re-created parameters): the kernel walks raw storage in the
+            # shadow's contiguous order, so a channels-last or otherwise strided parameter must fail loudly, not average
+            # permuted values
+            for n, p in zip(self._names, self._params):
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or p.device != self._dev:
+                    raise RuntimeError(f"EMA: parameter {n} is no longer a contiguous fp32 CUDA tensor on {self._dev}")
             self._param_ptr_list = ptrs
             self._param_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self._dev)
 

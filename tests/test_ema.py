@@ -120,3 +120,19 @@ def test_cpu_parameters_are_refused():
     import gan_variant_research_b200 as pn
     with pytest.raises(RuntimeError, match="CUDA"):
         pn.EMA(torch.nn.Linear(2, 2))
+
+
+@pytest.mark.gpu
+def test_parameters_moved_to_channels_last_are_refused_loudly():
+    """The kernel walks raw storage in the shadow's contiguous order: a model converted to torch.channels_last after
+    the EMA was built must raise at the next update(), not average permuted values."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import gan_variant_research_b200 as pn
+    net = torch.nn.Conv2d(8, 16, 3).cuda()
+    ema = pn.EMA(net, decay=0.9)
+    ema.update()
+    net.to(memory_format=torch.channels_last)
+    assert not net.weight.is_contiguous()
+    with pytest.raises(RuntimeError, match="contiguous"):
+        ema.update()
