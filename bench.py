@@ -496,7 +496,10 @@ def main():
 
 def kernel_breakdown(step, n=5):
     """Mean duration (us) of every kernel of one step, from the torch profiler over n extra steps AFTER the
-    timed region (never inside it): says which launch moved when ms_per_step moves."""
+    timed region (never inside it): says which launch moved when ms_per_step moves.  The library's kernels are
+    chained by programmatic dependent launch: a kernel is resident -- and "running" for the profiler --
+    while it still waits for its predecessor, so each of them is counted from the end of the library kernel it
+    overlaps at its start (the id prep on its side stream is no predecessor)."""
     try:
         from torch.profiler import ProfilerActivity, profile
         torch.cuda.synchronize()
@@ -504,12 +507,21 @@ def kernel_breakdown(step, n=5):
             for _ in range(n):
                 step()
             torch.cuda.synchronize()
+        evs = []
+        for e in prof.events():
+            if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start:
+                evs.append((e.name, float(e.time_range.start), float(e.time_range.end)))
+        evs.sort(key=lambda t: t[1])
+        ours = [(nm, a, b) for nm, a, b in evs
+                if ("pnce::" in nm or nm.startswith("k_")) and "k_prep" not in nm and "k_draw" not in nm]
         rows = {}
-        for e in prof.key_averages():
-            if e.device_time_total > 0:
-                name = e.key.split("(")[0].replace("void ", "").replace("pnce::", "").split("<")[0]
-                rows[name[:40]] = round(rows.get(name[:40], 0.0) + e.device_time_total / n, 1)
-        return dict(sorted(rows.items(), key=lambda kv: -kv[1])[:8])
+        for nm, a, b in evs:
+            if "pnce::" in nm or nm.startswith("k_"):
+                ends = [pb for pn_, pa, pb in ours if pa < a < pb <= b]
+                a = max([a] + ends)
+            name = nm.split("(")[0].replace("void ", "").replace("pnce::", "").split("<")[0][:40]
+            rows[name] = rows.get(name, 0.0) + (b - a) / n
+        return dict(sorted(((k, round(v, 1)) for k, v in rows.items()), key=lambda kv: -kv[1])[:8])
     except Exception as e:                                     # noqa: BLE001
         return {"unavailable": repr(e)}
 
