@@ -182,8 +182,8 @@ static int pdl_allowed() {
 }
 
 // SITE: 1 id prep, 2 gather, 4 loss, 8 dense backward, 16 everything else.  PNCE_PDL is a mask over the sites; the default,
-// 23, leaves the dense-backward launches out: with the attribute on them the NEXT step's gather runs 30 % slower on
-// compressible gradient memory (measured, mechanism not identified), and they have nothing to gain --
+// 23, leaves the dense-backward launches out: with the attribute on them the NEXT step's gather runs 30 % slower from
+// B = 8 on (measured, mechanism not identified), and they have nothing to gain --
 // their predecessor is the persistent loss kernel, whose CTAs hold every SM until they exit.
 template <int SITE = 16, typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
