@@ -19,8 +19,10 @@ namespace pnce {
 // uniform_int_from_to; range = HW < 2^32, base = 0).  One randint call advances the generator's offset by 4; the host
 // does the same (patchnce.py).  The int64 ids are written to L.ids, the caller's buffer, so that PatchNCELoss /
 // PatchSampleF can hand them out like the reference does.
+// write = false: only the sorted keys in shared memory are produced (k_gather_tc_fold: every gather CTA of a small
+// problem sorts its layer's ids itself instead of waiting for a k_prep launch; ONE CTA per layer writes the tables).
 __device__ void prep_layer(const LayerDev& L, unsigned long long* keys, int draw = 0, unsigned long long seed = 0,
-                           unsigned long long offset = 0) {
+                           unsigned long long offset = 0, bool write = true) {
   const int tid = threadIdx.x;
   const int P = L.P;
   int N2 = 1;
@@ -34,7 +36,7 @@ __device__ void prep_layer(const LayerDev& L, unsigned long long* keys, int draw
         curand_init(seed, (unsigned long long)i, offset, &st);
         const uint4 r = curand4(&st);
         id = (long long)(r.x % (unsigned)L.HW);
-        const_cast<long long*>(L.ids)[i] = id;
+        if (write) const_cast<long long*>(L.ids)[i] = id;
       } else {
         id = L.ids[i];
         id = id < 0 ? 0 : (id >= L.HW ? L.HW - 1 : id);        // memory safety only; randint is in range
@@ -58,6 +60,7 @@ __device__ void prep_layer(const LayerDev& L, unsigned long long* keys, int draw
       __syncthreads();
     }
   }
+  if (!write) return;
   // sid / perm / rank
   for (int i = tid; i < P; i += kThreads) {
     const int id = (int)(keys[i] >> 32);

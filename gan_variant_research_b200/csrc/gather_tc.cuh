@@ -22,8 +22,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+// keys_s != NULL (k_gather_tc_fold): the layer's sorted (id, index) keys are in shared memory, sid[] is not read
 template <typename T>
-__device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long local, int side0) {
+__device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long local, int side0,
+                                const unsigned long long* keys_s = nullptr) {
   const int nchunk = L.nchunk;
   const int npb = (L.Ppad + 255) >> 8;                       // CTAs of 256 patch slots per (image, side, chunk)
   const int s = (int)(local % nchunk);
@@ -35,7 +37,7 @@ __device__ void gather_tc_chunk(const LayerDev& L, int b0, int B, long long loca
   const int C = L.C, HW = L.HW, P = L.P, Ppad = L.Ppad, Cp8 = L.Cp >> 3;
   if (p >= Ppad) return;
   const bool valid = p < P;
-  const int id = valid ? __ldg(L.sid + p) : 0;                // already clamped to [0, HW) by k_prep
+  const int id = valid ? (keys_s != nullptr ? (int)(keys_s[p] >> 32) : __ldg(L.sid + p)) : 0;   // clamped to [0, HW) by the id prep
   const T* col = reinterpret_cast<const T*>(side ? L.tgt : L.src) + (size_t)b * C * HW + id;
   float v[32];
 #pragma unroll
@@ -103,6 +105,33 @@ __global__ void __launch_bounds__(kThreads) k_gather_tc(const __grid_constant__ 
   if (p.dtype == PNCE_F32) gather_tc_chunk<float>(p.L[l], p.b0, p.bn, local, p.side0);
   else if (p.dtype == PNCE_F16) gather_tc_chunk<__half>(p.L[l], p.b0, p.bn, local, p.side0);
   else gather_tc_chunk<__nv_bfloat16>(p.L[l], p.b0, p.bn, local, p.side0);
+}
+
+// Small problems (launch_gather_tc: at most kFoldMaxCtas gather CTAs, ids not planned ahead): the id prep of k_prep is
+// FOLDED into the gather -- every CTA draws (or reads) and sorts its layer's ids in shared memory (P <= 1024 keys, 36-55
+// barrier steps: ~1.5 us beside its 32 sector loads per thread) and the first CTA of each layer also writes the tables the
+// loss and dense kernels read (sid, perm, rank, cslot; the ids themselves in draw mode).  One launch and its 8-10 us on the
+// critical path less per step: at B = 1 a step is four kernels of 10-25 us each.  Same values bit for bit: prep_layer is
+// the one routine.  dynamic smem = N2max * 8 + 64.
+constexpr int kFoldMaxCtas = 512;        // measured: B = 8 (384 CTAs) 149 -> 143 us per step, B = 16 (768 CTAs) 240 -> 242 us
+__global__ void __launch_bounds__(kThreads) k_gather_tc_fold(const __grid_constant__ Params p,
+                                                             const __grid_constant__ BlockMap m) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const long long blk = blockIdx.x;
+  if (blk == 0 && threadIdx.x == 0 && p.b0 == 0 && p.counter != nullptr) {
+    p.counter[0] = 0u; p.counter[1] = 0u;
+    if (p.nonfinite != nullptr) p.nonfinite[1] = 0;
+  }
+  const int slot = find_layer(m, blk, p.n_layers);
+  const int l = m.layer[slot];
+  const long long local = blk - m.start[slot];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  prep_layer(p.L[l], keys, p.rng_draw, p.rng_seed, p.rng_offset + 4ull * (unsigned long long)l, local == 0);
+  __syncthreads();
+  if (p.dtype == PNCE_F32) gather_tc_chunk<float>(p.L[l], p.b0, p.bn, local, p.side0, keys);
+  else if (p.dtype == PNCE_F16) gather_tc_chunk<__half>(p.L[l], p.b0, p.bn, local, p.side0, keys);
+  else gather_tc_chunk<__nv_bfloat16>(p.L[l], p.b0, p.bn, local, p.side0, keys);
 }
 
 // One CTA per layer: ids -> (sid, perm, rank, ustart, bitmap, prefix); CTA 0 also resets the

@@ -62,7 +62,7 @@ struct NhwcItem {
 };
 template <typename T>
 __device__ __forceinline__ void gather_nhwc_load(const LayerDev& L, int b0, int B, long long witem, int lane, int side0,
-                                                 NhwcItem& it, float (&v)[8]) {
+                                                 NhwcItem& it, float (&v)[8], const unsigned long long* keys_s = nullptr) {
   // 32-bit index arithmetic (the launch checks that the item count fits): 64-bit divisions by run-time values cost ~100
   // instructions each, and this kernel has few others
   const unsigned nchunk = (unsigned)L.nchunk, np8 = (unsigned)L.Ppad >> 3, wi = (unsigned)witem;
@@ -78,7 +78,7 @@ __device__ __forceinline__ void gather_nhwc_load(const LayerDev& L, int b0, int 
   it.c8 = it.s * 4 + (lane >> 3);                            // 8-channel group
   const int c0 = it.c8 * 8;
   it.valid = it.p < L.P;
-  const int id = it.valid ? __ldg(L.sid + it.p) : 0;
+  const int id = it.valid ? (keys_s != nullptr ? (int)(keys_s[it.p] >> 32) : __ldg(L.sid + it.p)) : 0;
   const T* base = reinterpret_cast<const T*>(it.side ? L.tgt : L.src);
   const T* row = base + ((size_t)it.b * HW + id) * C + c0;
   const bool vec = (((size_t)C * sizeof(T)) & 15u) == 0 && (reinterpret_cast<uintptr_t>(base) & 15u) == 0;
@@ -137,12 +137,12 @@ __device__ __forceinline__ void gather_nhwc_store(const LayerDev& L, const NhwcI
 constexpr int kNhwcItemsPerWarp = 2;
 template <typename T>
 __device__ __forceinline__ void gather_nhwc_warp(const LayerDev& L, int b0, int B, long long w0, long long nitems, int lane,
-                                                 int side0) {
+                                                 int side0, const unsigned long long* keys_s = nullptr) {
   NhwcItem it[kNhwcItemsPerWarp];
   float v[kNhwcItemsPerWarp][8];
 #pragma unroll
   for (int n = 0; n < kNhwcItemsPerWarp; ++n)
-    if (w0 + n < nitems) gather_nhwc_load<T>(L, b0, B, w0 + n, lane, side0, it[n], v[n]);
+    if (w0 + n < nitems) gather_nhwc_load<T>(L, b0, B, w0 + n, lane, side0, it[n], v[n], keys_s);
 #pragma unroll
   for (int n = 0; n < kNhwcItemsPerWarp; ++n)
     if (w0 + n < nitems) gather_nhwc_store(L, it[n], lane, v[n]);
@@ -167,6 +167,32 @@ __global__ void __launch_bounds__(kThreads) k_gather_tc_nhwc(const __grid_consta
   if (p.dtype == PNCE_F32) gather_nhwc_warp<float>(L, p.b0, p.bn, w0, nitems, lane, p.side0);
   else if (p.dtype == PNCE_F16) gather_nhwc_warp<__half>(L, p.b0, p.bn, w0, nitems, lane, p.side0);
   else gather_nhwc_warp<__nv_bfloat16>(L, p.b0, p.bn, w0, nitems, lane, p.side0);
+}
+
+// The same gather with the id prep folded in (small problems, see k_gather_tc_fold in gather_tc.cuh): every CTA sorts
+// its layer's ids in shared memory, the first CTA of each layer writes the tables.  dynamic smem = N2max * 8 + 64.
+__global__ void __launch_bounds__(kThreads) k_gather_tc_nhwc_fold(const __grid_constant__ Params p,
+                                                                  const __grid_constant__ BlockMap m) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const long long blk = blockIdx.x;
+  if (blk == 0 && threadIdx.x == 0 && p.b0 == 0 && p.counter != nullptr) {
+    p.counter[0] = 0u; p.counter[1] = 0u;
+    if (p.nonfinite != nullptr) p.nonfinite[1] = 0;
+  }
+  const int slot = find_layer(m, blk, p.n_layers);
+  const int l = m.layer[slot];
+  const LayerDev& L = p.L[l];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  prep_layer(L, keys, p.rng_draw, p.rng_seed, p.rng_offset + 4ull * (unsigned long long)l, blk == m.start[slot]);
+  __syncthreads();
+  const long long w0 = ((blk - m.start[slot]) * 8 + (threadIdx.x >> 5)) * kNhwcItemsPerWarp;
+  const long long nitems = (long long)(2 - p.side0) * p.bn * (L.Ppad >> 3) * L.nchunk;
+  if (w0 >= nitems) return;
+  const int lane = threadIdx.x & 31;
+  if (p.dtype == PNCE_F32) gather_nhwc_warp<float>(L, p.b0, p.bn, w0, nitems, lane, p.side0, keys);
+  else if (p.dtype == PNCE_F16) gather_nhwc_warp<__half>(L, p.b0, p.bn, w0, nitems, lane, p.side0, keys);
+  else gather_nhwc_warp<__nv_bfloat16>(L, p.b0, p.bn, w0, nitems, lane, p.side0, keys);
 }
 
 // -------------------------------------------------------------------------------------------------

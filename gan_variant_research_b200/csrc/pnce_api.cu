@@ -181,6 +181,15 @@ static int pdl_allowed() {
   return v;
 }
 
+// PNCE_FOLD_PREP=0: always launch k_prep (A/B of the folded id prep, gather_tc.cuh)
+static bool pnce_fold_allowed() {
+  static const bool v = [] {
+    const char* e = getenv("PNCE_FOLD_PREP");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return v;
+}
+
 // SITE: 1 id prep, 2 gather, 4 loss, 8 dense backward, 16 everything else.  PNCE_PDL is a mask over the sites; the default,
 // 23, leaves the dense-backward launches out: with the attribute on them the NEXT step's gather runs 30 % slower from
 // B = 8 on (measured, mechanism not identified), and they have nothing to gain --
@@ -282,7 +291,36 @@ static int g_gather_in_layer_order = 0;   // experiment knob 8
 static constexpr int g_gather_in_layer_order = 0;
 #endif
 
-static int launch_gather_tc(const Params& p, cudaStream_t st) {
+// NCHW gather CTAs of the whole batch, and whether the id prep is folded into them (gather_tc.cuh: k_gather_tc_fold)
+static long long gather_tc_ctas(const Params& p, int images) {
+  long long acc = 0;
+  for (int l = 0; l < p.n_layers; ++l)
+    acc += (long long)(2 - p.side0) * images * ((p.L[l].Ppad + 255) / 256) * p.L[l].nchunk;
+  return acc;
+}
+static long long gather_nhwc_ctas(const Params& p, int images) {
+  long long acc = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const long long items = (long long)(2 - p.side0) * images * (p.L[l].Ppad >> 3) * p.L[l].nchunk;
+    acc += (items + 8 * kNhwcItemsPerWarp - 1) / (8 * kNhwcItemsPerWarp);
+  }
+  return acc;
+}
+static bool gather_tc_folds(const Params& p) {
+  return pnce_fold_allowed() && (p.nhwc ? gather_nhwc_ctas(p, p.B) : gather_tc_ctas(p, p.B)) <= kFoldMaxCtas;
+}
+static size_t fold_smem_bytes(const Params& p) {
+  size_t smem = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    int n2 = 1;
+    while (n2 < p.L[l].P) n2 <<= 1;
+    const size_t b = (size_t)n2 * 8 + 64;
+    if (b > smem) smem = b;
+  }
+  return smem;
+}
+
+static int launch_gather_tc(const Params& p, cudaStream_t st, bool fold = false) {
   BlockMap m;
   memset(&m, 0, sizeof(m));
   // light layers (small C) first, heavy layers last: the loss kernel starts with the heavy layers, whose
@@ -304,7 +342,8 @@ static int launch_gather_tc(const Params& p, cudaStream_t st) {
     }
     m.start[p.n_layers] = acc;
     if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
-    launch_k<2>(k_gather_tc_nhwc, (unsigned)acc, kThreads, 0, st, p, m);
+    if (fold) launch_k<2>(k_gather_tc_nhwc_fold, (unsigned)acc, kThreads, fold_smem_bytes(p), st, p, m);
+    else launch_k<2>(k_gather_tc_nhwc, (unsigned)acc, kThreads, 0, st, p, m);
     PNCE_CUDA(cudaGetLastError());
     return PNCE_OK;
   }
@@ -315,7 +354,11 @@ static int launch_gather_tc(const Params& p, cudaStream_t st) {
   }
   m.start[p.n_layers] = acc;
   if (acc > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
-  launch_k<2>(k_gather_tc, (unsigned)acc, kThreads, 0, st, p, m);
+  if (fold) {
+    launch_k<2>(k_gather_tc_fold, (unsigned)acc, kThreads, fold_smem_bytes(p), st, p, m);
+  } else {
+    launch_k<2>(k_gather_tc, (unsigned)acc, kThreads, 0, st, p, m);
+  }
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
 }
@@ -439,7 +482,10 @@ static int aux_streams(AuxStreams** out) {
 
 static int forward_tc(Params& p, cudaStream_t st, bool planned = false) {
   int rc = PNCE_OK;
-  if (!planned) rc = launch_prep(p, st);      // planned: pnce_plan_ids has run k_prep already (gather CTA 0 resets the counter)
+  // planned: pnce_plan_ids has run k_prep already (gather CTA 0 resets the counter); small problems: the gather CTAs
+  // sort the ids themselves (k_gather_tc_fold), no k_prep launch
+  const bool fold = !planned && g_dbg.fwd_chunks <= 1 && gather_tc_folds(p);
+  if (!planned && !fold) rc = launch_prep(p, st);
   if (rc != PNCE_OK) return rc;
   int ctas_per_image = 0;
   for (int l = 0; l < p.n_layers; ++l) ctas_per_image += p.L[l].Ppad / 128;
@@ -454,7 +500,7 @@ static int forward_tc(Params& p, cudaStream_t st, bool planned = false) {
   p.total_ctas = (unsigned)(p.B * ctas_per_image);
   if (nchunk == 1) {
     p.b0 = 0; p.bn = p.B;
-    rc = launch_gather_tc(p, st);
+    rc = launch_gather_tc(p, st, fold);
     if (rc != PNCE_OK) return rc;
     if (g_dbg.post_gather_event) PNCE_CUDA(cudaEventRecord(g_dbg.post_gather_event, st));
     for (int r = 0; r < g_dbg.loss_repeat; ++r) {              // experiment: warm launches in front of the real one
