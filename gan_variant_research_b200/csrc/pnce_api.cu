@@ -1519,7 +1519,8 @@ static int head_fwd_impl(const pnce_layer_t* layers, const pnce_head_t* heads, i
   pg.nhwc = layout == PNCE_LAYOUT_NHWC ? 1 : 0;               // the maps; the head's output (pl) has no layout
   pl.trace = g_dbg.trace;
   // 1. ids -> sorted slots; weights -> operand blobs
-  rc = launch_prep(pg, st);
+  const bool fold = gather_tc_folds(pg);                      // small problems: the gather CTAs sort the ids themselves
+  if (!fold) rc = launch_prep(pg, st);
   if (rc != PNCE_OK) return rc;
   {
     static thread_local WprepLaunch wl;
@@ -1544,7 +1545,7 @@ static int head_fwd_impl(const pnce_layer_t* layers, const pnce_head_t* heads, i
     PNCE_CUDA(cudaGetLastError());
   }
   // 2. raw patches of both sides as row blobs
-  rc = launch_gather_tc(pg, st);
+  rc = launch_gather_tc(pg, st, fold);
   if (rc != PNCE_OK) return rc;
   // 3. H = relu(X W1^T + b1), both sides
   static thread_local GemmLaunch g;
@@ -1833,7 +1834,8 @@ int pnce_netf_fwd(const pnce_sample_t* maps, const pnce_head_t* heads, int n_map
   pg.b0 = 0; pg.bn = batch;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // 1. ids -> sorted slots; weights -> operand blobs (plain and transposed: the backward needs both)
-  rc = launch_prep(pg, st);
+  const bool fold = gather_tc_folds(pg);                      // small problems: the gather CTAs sort the ids themselves
+  if (!fold) rc = launch_prep(pg, st);
   if (rc != PNCE_OK) return rc;
   {
     static thread_local WprepLaunch wl;
@@ -1858,7 +1860,7 @@ int pnce_netf_fwd(const pnce_sample_t* maps, const pnce_head_t* heads, int n_map
     PNCE_CUDA(cudaGetLastError());
   }
   // 2. raw patches as the X row blob (sorted-slot order)
-  rc = launch_gather_tc(pg, st);
+  rc = launch_gather_tc(pg, st, fold);
   if (rc != PNCE_OK) return rc;
   // 3. H = relu(X W1^T + b1)
   static thread_local GemmLaunch g;
