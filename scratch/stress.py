@@ -1,7 +1,7 @@
 """Randomised stress of the fused path against the oracle: ragged shapes, every math mode, both id paths
 (in-line and side-stream plan), repeated launches (races in the persistent kernels would show as mismatches
 or protocol timeouts)."""
-import sys, random
+import os, sys, random
 sys.path.insert(0, '.')
 import numpy as np, torch
 import gan_variant_research_b200 as pn
@@ -17,6 +17,8 @@ for case in range(ncase):
     tau = rnd.choice([0.07, 0.07, 0.07, 0.5, 0.015])
     math = rnd.choice(['tc_bf16x3', 'tc_bf16x3', 'simt_f32'])
     g = torch.Generator().manual_seed(case)
+    if os.environ.get('STRESS_ID_SEED'):                       # reproducible ids per case (the default run leaves the CUDA generator alone)
+        torch.cuda.manual_seed(1000 + case)
     src = [torch.randn(b, *s, generator=g) for s in shapes]
     tgt = [torch.randn(b, *s, generator=g) for s in shapes]
     if rnd.random() < 0.3:
@@ -44,7 +46,12 @@ for case in range(ncase):
             assert np.abs(got).max() < 1e-2 * up, (case, l)    # what is left is cancellation noise, bounded
             continue
         sc = np.abs(gw[l]).max()
-        ge = max(ge, np.abs(got - gw[l]).max() / sc)
+        ge_l = np.abs(got - gw[l]).max() / sc
+        if ge_l > 5e-4 and os.environ.get('STRESS_VERBOSE'):
+            bad = np.abs(got - gw[l]) > 2e-4 * sc
+            rows = np.unique(np.nonzero(bad.reshape(bad.shape[0], bad.shape[1], -1))[2])
+            print(f'   case {case} layer {l} shape {shapes[l]} tau {tau} math {math}: err {ge_l:.2e}, {int(bad.sum())} elements off in {len(rows)} positions, {len(np.unique(ids[l]))} distinct ids of {len(ids[l])}')
+        ge = max(ge, ge_l)
     tol_l, tol_g = (2e-5, 2e-4) if tau > 0.05 else (2e-4, 2e-3)
     worst['loss'] = max(worst['loss'], le); worst['grad'] = max(worst['grad'], ge)
     if not (le <= tol_l and ge <= tol_g) or not np.isfinite(le + ge):
