@@ -498,8 +498,8 @@ def kernel_breakdown(step, n=5):
     """Mean duration (us) of every kernel of one step, from the torch profiler over n extra steps AFTER the
     timed region (never inside it): says which launch moved when ms_per_step moves.  The library's kernels are
     chained by programmatic dependent launch: a kernel is resident -- and "running" for the profiler --
-    while it still waits for its predecessor, so each of them is counted from the end of the library kernel it
-    overlaps at its start (the id prep on its side stream is no predecessor)."""
+    while it still waits for its predecessor, so each of them is counted from the end of the library kernel that
+    started before it and ends inside it (a side-stream id prep under the previous dense kernel fits neither way)."""
     try:
         from torch.profiler import ProfilerActivity, profile
         torch.cuda.synchronize()
@@ -512,8 +512,7 @@ def kernel_breakdown(step, n=5):
             if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start:
                 evs.append((e.name, float(e.time_range.start), float(e.time_range.end)))
         evs.sort(key=lambda t: t[1])
-        ours = [(nm, a, b) for nm, a, b in evs
-                if ("pnce::" in nm or nm.startswith("k_")) and "k_prep" not in nm and "k_draw" not in nm]
+        ours = [(nm, a, b) for nm, a, b in evs if "pnce::" in nm or nm.startswith("k_")]
         rows = {}
         for nm, a, b in evs:
             if "pnce::" in nm or nm.startswith("k_"):

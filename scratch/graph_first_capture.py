@@ -48,6 +48,20 @@ with torch.cuda.stream(s):
         step()
 torch.cuda.current_stream().wait_stream(s)
 torch.cuda.synchronize()
+if len(sys.argv) > 2:                      # a long eager history first, as scratch/host_floor.py has (n eager + n direct steps)
+    nlong = int(sys.argv[2])
+    for _ in range(nlong):
+        step()
+    dt = [t.detach() for t in tgt]
+    for _ in range(nlong):
+        crit.loss_and_grads(src, dt)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(s)
 for name in ("draw_patch_ids_all", "_run_fwd", "_run_bwd", "_shape_plan", "_prepare_maps", "_warn_queue"):
     if hasattr(P, name):
         wrap(P, name)
