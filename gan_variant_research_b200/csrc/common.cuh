@@ -102,7 +102,8 @@ template <> __device__ __forceinline__ float from_f32<float>(float v) { return v
 template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-// Programmatic dependent launch (griddepcontrol, sm_90+): FIRST statement of every kernel of this library.  The host
+// Programmatic dependent launch (griddepcontrol, sm_90+): FIRST statement of every kernel of this library except the
+// dense-backward kernels, which are always launched the ordinary way (pnce_api.cu: launch_k, SITE 0).  The host
 // launches the kernels of one step with cudaLaunchAttributeProgrammaticStreamSerialization (pnce_api.cu: launch_k), so
 // the next kernel's CTAs are dispatched while this one drains and its launch latency is hidden; `wait` returns once
 // every prerequisite grid has completed and its memory is visible, so nothing after it can see half-written data or

@@ -29,7 +29,6 @@ struct DenseFlatMap {
 template <typename T, int THREADS, bool VEC>
 __global__ void __launch_bounds__(THREADS) k_dense_flat(const __grid_constant__ Params p,
                                                         const __grid_constant__ DenseFlatMap m) {
-  pdl_enter();
   constexpr int TP = kFlatBytes / (int)sizeof(T);          // positions per tile
   constexpr int SUB = TP / kTilePos;                       // k_prep table entries per tile
   constexpr int KS = 256 / THREADS;                        // slots per thread on the prefetching path
@@ -118,7 +117,6 @@ __global__ void __launch_bounds__(THREADS) k_dense_flat(const __grid_constant__ 
 template <typename T, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_dense_direct(const __grid_constant__ Params p,
                                                           const __grid_constant__ DenseFlatMap m) {
-  pdl_enter();
   constexpr int TP = kFlatBytes / (int)sizeof(T);          // positions per tile
   constexpr int SUB = TP / kTilePos;                       // k_prep table entries per tile
   constexpr int KS = 256 / THREADS;                        // slots per thread on the prefetching path

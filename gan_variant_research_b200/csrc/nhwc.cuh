@@ -214,7 +214,6 @@ struct DenseNhwcMap {
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(128) k_dense_nhwc(const __grid_constant__ Params p,
                                                     const __grid_constant__ DenseNhwcMap m) {
-  pdl_enter();
   __shared__ __align__(16) T tile[kFlatBytes / sizeof(T)];
   __shared__ int s_ja, s_jb;
   const int tid = threadIdx.x;
@@ -297,7 +296,6 @@ struct FillMap {
   int n;
 };
 __global__ void __launch_bounds__(128) k_fill_zero(const __grid_constant__ FillMap m) {
-  pdl_enter();
   const unsigned item = blockIdx.x;
   int l = 0;
   for (int i = 1; i < m.n; ++i)
@@ -332,7 +330,6 @@ struct ScatterMap {
 // warp <-> (layer, image, sorted slot); the head of a run of equal ids writes the position's C values
 template <typename T>
 __global__ void __launch_bounds__(256) k_scatter_nhwc(const __grid_constant__ Params p, const __grid_constant__ ScatterMap m) {
-  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (item >= m.start[p.n_layers]) return;

@@ -176,7 +176,7 @@ static size_t gather_smem_bytes(const Params& p, bool with_prep) {
 static int pdl_allowed() {
   static const int v = [] {
     const char* e = getenv("PNCE_PDL");
-    return e != nullptr ? atoi(e) : 23;
+    return e != nullptr ? atoi(e) : 23;   // bit 8 is unused: see SITE 0 below
   }();
   return v;
 }
@@ -190,10 +190,12 @@ static bool pnce_fold_allowed() {
   return v;
 }
 
-// SITE: 1 id prep, 2 gather, 4 loss, 8 dense backward, 16 everything else.  PNCE_PDL is a mask over the sites; the default,
-// 23, leaves the dense-backward launches out: with the attribute on them the NEXT step's gather runs 30 % slower from
-// B = 8 on (measured, mechanism not identified), and they have nothing to gain --
-// their predecessor is the persistent loss kernel, whose CTAs hold every SM until they exit.
+// SITE: 1 id prep, 2 gather, 4 loss, 16 everything else; PNCE_PDL is a mask over the sites (default: all of them).  SITE 0 =
+// the dense-backward kernels (k_dense_*, k_fill_zero, k_scatter_nhwc): ALWAYS launched the ordinary way, and they are the
+// only kernels without pdl_enter().  With the attribute on them the NEXT step's gather ran 30 % slower from B = 8 on
+// (measured, mechanism not identified), they have nothing to gain -- their predecessor is the persistent
+// loss kernel, whose CTAs hold every SM until they exit -- and the two instructions themselves cost k_fill_zero 8 % (393 216
+// CTAs of a few dozen instructions each: 378 -> 407 us at B = 64).
 template <int SITE = 16, typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -566,23 +568,23 @@ static int launch_dense_nhwc(const Params& p, cudaStream_t st) {
     fm.start[p.n_layers] = tiles;
     sm.start[p.n_layers] = items;
     if (tiles > 0x7fffffffLL || items > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
-    launch_k<8>(k_fill_zero, (unsigned)tiles, 128, 0, st, fm);
+    launch_k<0>(k_fill_zero, (unsigned)tiles, 128, 0, st, fm);
     PNCE_CUDA(cudaGetLastError());
     const unsigned sgrid = (unsigned)((items + 7) / 8);
-    if (p.dtype == PNCE_F32) launch_k<8>(k_scatter_nhwc<float>, sgrid, 256, 0, st, p, sm);
-    else if (p.dtype == PNCE_F16) launch_k<8>(k_scatter_nhwc<__half>, sgrid, 256, 0, st, p, sm);
-    else launch_k<8>(k_scatter_nhwc<__nv_bfloat16>, sgrid, 256, 0, st, p, sm);
+    if (p.dtype == PNCE_F32) launch_k<0>(k_scatter_nhwc<float>, sgrid, 256, 0, st, p, sm);
+    else if (p.dtype == PNCE_F16) launch_k<0>(k_scatter_nhwc<__half>, sgrid, 256, 0, st, p, sm);
+    else launch_k<0>(k_scatter_nhwc<__nv_bfloat16>, sgrid, 256, 0, st, p, sm);
     PNCE_CUDA(cudaGetLastError());
     return PNCE_OK;
   }
   if (vec) {
-    if (p.dtype == PNCE_F32) launch_k<8>(k_dense_nhwc<float, true>, grid, 128, 0, st, p, f);
-    else if (p.dtype == PNCE_F16) launch_k<8>(k_dense_nhwc<__half, true>, grid, 128, 0, st, p, f);
-    else launch_k<8>(k_dense_nhwc<__nv_bfloat16, true>, grid, 128, 0, st, p, f);
+    if (p.dtype == PNCE_F32) launch_k<0>(k_dense_nhwc<float, true>, grid, 128, 0, st, p, f);
+    else if (p.dtype == PNCE_F16) launch_k<0>(k_dense_nhwc<__half, true>, grid, 128, 0, st, p, f);
+    else launch_k<0>(k_dense_nhwc<__nv_bfloat16, true>, grid, 128, 0, st, p, f);
   } else {
-    if (p.dtype == PNCE_F32) launch_k<8>(k_dense_nhwc<float, false>, grid, 128, 0, st, p, f);
-    else if (p.dtype == PNCE_F16) launch_k<8>(k_dense_nhwc<__half, false>, grid, 128, 0, st, p, f);
-    else launch_k<8>(k_dense_nhwc<__nv_bfloat16, false>, grid, 128, 0, st, p, f);
+    if (p.dtype == PNCE_F32) launch_k<0>(k_dense_nhwc<float, false>, grid, 128, 0, st, p, f);
+    else if (p.dtype == PNCE_F16) launch_k<0>(k_dense_nhwc<__half, false>, grid, 128, 0, st, p, f);
+    else launch_k<0>(k_dense_nhwc<__nv_bfloat16, false>, grid, 128, 0, st, p, f);
   }
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
@@ -609,21 +611,21 @@ static int launch_dense(const Params& p, cudaStream_t st) {
   if (tot > 0x7fffffffLL) return PNCE_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)tot;
   if (vec && (g_dbg.dense_flags & 2)) {                      // experiment: store-first variant
-    if (p.dtype == PNCE_F32) launch_k<8>(k_dense_direct<float, 128>, grid, 128, 0, st, p, f);
-    else if (p.dtype == PNCE_F16) launch_k<8>(k_dense_direct<__half, 128>, grid, 128, 0, st, p, f);
-    else launch_k<8>(k_dense_direct<__nv_bfloat16, 128>, grid, 128, 0, st, p, f);
+    if (p.dtype == PNCE_F32) launch_k<0>(k_dense_direct<float, 128>, grid, 128, 0, st, p, f);
+    else if (p.dtype == PNCE_F16) launch_k<0>(k_dense_direct<__half, 128>, grid, 128, 0, st, p, f);
+    else launch_k<0>(k_dense_direct<__nv_bfloat16, 128>, grid, 128, 0, st, p, f);
   } else if (vec && (g_dbg.dense_flags & 4)) {               // experiment: 64-thread CTAs (more tiles in flight per SM)
-    if (p.dtype == PNCE_F32) launch_k<8>(k_dense_flat<float, 64, true>, grid, 64, 0, st, p, f);
-    else if (p.dtype == PNCE_F16) launch_k<8>(k_dense_flat<__half, 64, true>, grid, 64, 0, st, p, f);
-    else launch_k<8>(k_dense_flat<__nv_bfloat16, 64, true>, grid, 64, 0, st, p, f);
+    if (p.dtype == PNCE_F32) launch_k<0>(k_dense_flat<float, 64, true>, grid, 64, 0, st, p, f);
+    else if (p.dtype == PNCE_F16) launch_k<0>(k_dense_flat<__half, 64, true>, grid, 64, 0, st, p, f);
+    else launch_k<0>(k_dense_flat<__nv_bfloat16, 64, true>, grid, 64, 0, st, p, f);
   } else if (vec) {
-    if (p.dtype == PNCE_F32) launch_k<8>(k_dense_flat<float, 128, true>, grid, 128, 0, st, p, f);
-    else if (p.dtype == PNCE_F16) launch_k<8>(k_dense_flat<__half, 128, true>, grid, 128, 0, st, p, f);
-    else launch_k<8>(k_dense_flat<__nv_bfloat16, 128, true>, grid, 128, 0, st, p, f);
+    if (p.dtype == PNCE_F32) launch_k<0>(k_dense_flat<float, 128, true>, grid, 128, 0, st, p, f);
+    else if (p.dtype == PNCE_F16) launch_k<0>(k_dense_flat<__half, 128, true>, grid, 128, 0, st, p, f);
+    else launch_k<0>(k_dense_flat<__nv_bfloat16, 128, true>, grid, 128, 0, st, p, f);
   } else {
-    if (p.dtype == PNCE_F32) launch_k<8>(k_dense_flat<float, 128, false>, grid, 128, 0, st, p, f);
-    else if (p.dtype == PNCE_F16) launch_k<8>(k_dense_flat<__half, 128, false>, grid, 128, 0, st, p, f);
-    else launch_k<8>(k_dense_flat<__nv_bfloat16, 128, false>, grid, 128, 0, st, p, f);
+    if (p.dtype == PNCE_F32) launch_k<0>(k_dense_flat<float, 128, false>, grid, 128, 0, st, p, f);
+    else if (p.dtype == PNCE_F16) launch_k<0>(k_dense_flat<__half, 128, false>, grid, 128, 0, st, p, f);
+    else launch_k<0>(k_dense_flat<__nv_bfloat16, 128, false>, grid, 128, 0, st, p, f);
   }
   PNCE_CUDA(cudaGetLastError());
   return PNCE_OK;
