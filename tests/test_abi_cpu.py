@@ -148,3 +148,37 @@ def test_pinned_view_refuses_pageable_memory():
     import gan_variant_research_b200 as pn
     with pytest.raises(RuntimeError, match="pinned"):
         pn.pinned_as_device(torch.zeros(4, 4))
+
+
+def test_every_kernel_launched_with_the_pdl_attribute_waits_for_its_predecessors(lib):
+    """Programmatic dependent launch is only safe because every kernel that may carry the launch attribute
+    executes griddepcontrol.wait (SASS: ACQBULK) before its first global access: a kernel added without pdl_enter() but
+    launched through launch_k's default site would race with its predecessor silently.  Checked on the built library:
+    the kernels WITHOUT the wait are exactly the dense-backward ones, and the host launches exactly those with
+    launch_k<0> (never the attribute)."""
+    import re
+    import shutil
+    import subprocess
+    from gan_variant_research_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not found")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    waits, name = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            waits[name] = False
+        elif name is not None and "ACQBULK" in line:
+            waits[name] = True
+    assert len(waits) >= 40, "no kernels found in the library's SASS"
+    no_wait = {re.search(r"\d+(k_[a-z_]+?)(?:I|E)", n).group(1) for n, w in waits.items() if not w}     # mangled -> k_name
+    dense = {"k_dense_flat", "k_dense_direct", "k_dense_nhwc", "k_fill_zero", "k_scatter_nhwc"}
+    assert no_wait == dense, no_wait ^ dense
+    src = open(os.path.join(ROOT, "gan_variant_research_b200", "csrc", "pnce_api.cu")).read()
+    site0 = set(re.findall(r"launch_k<0>\((k_[a-z_]+)", src))
+    assert site0 == dense, site0 ^ dense
+    for k in dense:                                              # and never through another site or a bare <<< >>>
+        assert not re.search(r"launch_k(?:<[1-9]\d*>)?\(" + k + r"\b", src), k
+        assert not re.search(k + r"(?:<[^<>;]*>)?<<<", src), k
