@@ -113,6 +113,12 @@ __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// The tcgen05 kernels split the pair: pdl_launch() first, then their prologue -- mbarrier initialisation, TMEM allocation,
+// the CTA-wide barrier: shared memory and TMEM only, 1-2 us per launch -- and pdl_wait() right behind it, still before the
+// first global access; the prologue then runs under the predecessor's tail.  (A TMEM allocation that finds the columns
+// still held by a predecessor's CTA on the same SM simply blocks until that CTA has exited.)
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

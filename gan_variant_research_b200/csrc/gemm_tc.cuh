@@ -78,7 +78,7 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
 }
 
 __global__ void __launch_bounds__(kTcThreads, 2) k_gemm_tc(const __grid_constant__ GemmLaunch g) {
-  pdl_enter();
+  pdl_launch();
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
   GemmShared* sh = reinterpret_cast<GemmShared*>(smem + kGemmSlots * kGemmStageBytes);
@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_gemm_tc(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                                 // prologue done: now wait for the prerequisite grids
   const uint32_t tmem = sh->tmem_base;
   const uint32_t bbytes = (uint32_t)N * 32u;                // one B chunk: 2 slabs x N rows x 16 B
   const uint32_t lbo_b = (uint32_t)N * 16u;
@@ -266,7 +267,7 @@ constexpr int kWgOffAlo = 32768, kWgOffBhi = 65536, kWgOffBlo = 131072, kWgOffOn
 constexpr int kWgSmemBytes = 196608 + 4096 + 256;
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constant__ WgradLaunch g) {
-  pdl_enter();
+  pdl_launch();
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
   struct Sh { uint64_t full, empty, dfull; uint32_t tmem_base; int dead; };
@@ -293,6 +294,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                                 // prologue done: now wait for the prerequisite grids
   const uint32_t tmem = sh->tmem_base;
   const uint32_t abytes = 16u * 2048u, bbytes = (uint32_t)N8 * 2048u;
 

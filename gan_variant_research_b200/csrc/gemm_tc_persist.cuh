@@ -43,7 +43,7 @@ __device__ __forceinline__ void gp_decode(const GemmLaunch& g, long long t, GpTi
 }
 
 __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_constant__ GemmLaunch g) {
-  pdl_enter();
+  pdl_launch();
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
   GpShared* sh = reinterpret_cast<GpShared*>(smem + kGpSlots * kGpStageBytes);
@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(kGpThreads, 1) k_gemm_tc_p(const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                                 // prologue done: now wait for the prerequisite grids
   const uint32_t tmem = sh->tmem_base;
 
   if (warp == 0) {

@@ -413,7 +413,7 @@ __device__ __forceinline__ void tc_dq_epilogue(uint32_t tacc, int nstage, int C,
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant__ Params p,
                                                            const __grid_constant__ BlockMap m) {
-  pdl_enter();
+  pdl_launch();
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
   unsigned char* stage0 = smem;
@@ -472,6 +472,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_loss_tc(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                                 // prologue done: now wait for the prerequisite grids
   const uint32_t tmem = sh->tmem_base;
   const int npass = (multi && !single) ? 2 : 1;
 

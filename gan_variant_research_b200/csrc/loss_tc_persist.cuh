@@ -222,7 +222,7 @@ __device__ __forceinline__ void tp_pass(uint32_t trow, int nmine, int half, int 
 
 __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_constant__ Params p,
                                                              const __grid_constant__ BlockMap m) {
-  pdl_enter();
+  pdl_launch();
   extern __shared__ __align__(1024) unsigned char smem[];
   using namespace umma;
   unsigned char* stage0 = smem;
@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(kTpThreads, 1) k_loss_tc_p(const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                                 // prologue done: now wait for the prerequisite grids
   const uint32_t tmem = sh->tmem_base;
 
   if (warp == 0) {
